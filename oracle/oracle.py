@@ -1,0 +1,235 @@
+"""ctypes front-end of the CPU oracle (oracle/pre3_oracle*.c).
+
+TEST INFRASTRUCTURE ONLY -- imported by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs.  The product package
+(3pre_b200/) never imports this module.
+
+Array conventions mirror MATLAB: a "3 x N" matrix is passed as a numpy array of
+shape (N, 3) C-contiguous (== 3 x N column-major); descriptors "128 x K" are
+(K, 128) C-contiguous.  Rotations come back as 3x3 numpy arrays (row-major).
+Indices are 0-based here; the MATLAB-facing layers add 1.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "libpre3_oracle.so")
+
+
+def build(force: bool = False) -> str:
+    """Compile the oracle (and oracle/_ref when /root/reference exists)."""
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.startswith("pre3_oracle") and f.endswith(".c")]
+    stale = force or not os.path.exists(_LIB_PATH) or any(
+        os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs
+    )
+    if stale:
+        subprocess.run(["make", "-C", _HERE, "oracle"], check=True, capture_output=True)
+    ref_so = os.path.join(_HERE, "_ref", "libsiftmatch_ref.so")
+    if os.path.exists("/root/reference/matlab_code/sift/siftmatch.c") and (force or not os.path.exists(ref_so)):
+        subprocess.run(["make", "-C", _HERE, "ref"], check=True, capture_output=True)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+class RansacResult(C.Structure):
+    _fields_ = [
+        ("status", C.c_int32),
+        ("state", C.c_int32),
+        ("best_fit", C.c_int32),
+        ("best_sample", C.c_int32),
+        ("best_iter", C.c_int32),
+        ("n_iter", C.c_int32),
+        ("n_consumed", C.c_int32),
+        ("pad", C.c_int32),
+        ("thr", C.c_double),
+        ("error_sum", C.c_double),
+        ("R", C.c_double * 9),
+        ("T", C.c_double * 3),
+        ("R_hyp", C.c_double * 9),
+        ("T_hyp", C.c_double * 3),
+    ]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB_PATH)
+        _lib.orc_distance_threshold.restype = C.c_double
+        _lib.orc_adaptive_niter.restype = C.c_double
+    return _lib
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+_MATCH = {
+    np.dtype(np.float64): ("orc_siftmatch_f64", C.c_double),
+    np.dtype(np.float32): ("orc_siftmatch_f32", C.c_float),
+    np.dtype(np.int8): ("orc_siftmatch_i8", C.c_byte),
+    np.dtype(np.uint8): ("orc_siftmatch_u8", C.c_ubyte),
+}
+
+
+def siftmatch(L1, L2, thresh: float = 1.5):
+    """siftmatch.c:83-132.  L1:(K1,ND), L2:(K2,ND) same dtype.  Returns
+    (pairs (n,2) int32 0-based, score (n,) float64)."""
+    L1 = np.ascontiguousarray(L1)
+    L2 = np.ascontiguousarray(L2)
+    if L1.dtype != L2.dtype:
+        raise ValueError("L1 and L2 must be of the same class")
+    if L1.dtype not in _MATCH:
+        raise ValueError("Unsupported numeric class")
+    if L1.shape[1] != L2.shape[1]:
+        raise ValueError("L1 and L2 must have the same number of rows")
+    name, ct = _MATCH[L1.dtype]
+    K1, ND = L1.shape
+    K2 = L2.shape[0]
+    pairs = np.zeros((max(K1, 1), 2), np.int32)
+    score = np.zeros(max(K1, 1), np.float64)
+    n = getattr(lib(), name)(_p(L1, ct), _p(L2, ct), K1, K2, ND, C.c_double(thresh), _p(pairs, C.c_int32), _p(score, C.c_double))
+    return pairs[:n].copy(), score[:n].copy()
+
+
+def find_transform_matrix(pset1, pset2, idx=None):
+    """find_transform_matrix.m:2-42.  pset: (n,3).  Returns rot(3,3), trans(3,), state."""
+    p1, p2 = _f64(pset1), _f64(pset2)
+    rot = np.zeros(9)
+    tr = np.zeros(3)
+    if idx is None:
+        n, ip = p1.shape[0], None
+    else:
+        idx = np.ascontiguousarray(idx, np.int32)
+        n, ip = idx.shape[0], _p(idx, C.c_int32)
+    st = lib().orc_find_transform(_p(p1, C.c_double), _p(p2, C.c_double), ip, n, _p(rot, C.c_double), _p(tr, C.c_double))
+    return rot.reshape(3, 3), tr, int(st)
+
+
+def horn(A, B, doScale: int = 1, idx=None, allow_small: bool = False):
+    """absoluteOrientationQuaternion.m:28-127.  A,B: (n,3); B ~ s*R*A + T.
+    Returns s, R(3,3), T(3,), err.  Raises for n<4 like the reference (:51-54)."""
+    a, b = _f64(A), _f64(B)
+    if a.shape != b.shape:
+        raise ValueError("Point sets need to have same size.")
+    if a.ndim != 2 or a.shape[1] != 3:
+        raise ValueError("Need points of dimension 3")
+    if idx is None:
+        n, ip = a.shape[0], None
+    else:
+        idx = np.ascontiguousarray(idx, np.int32)
+        n, ip = idx.shape[0], _p(idx, C.c_int32)
+    s = C.c_double()
+    err = C.c_double()
+    R = np.zeros(9)
+    T = np.zeros(3)
+    rc = lib().orc_horn(_p(a, C.c_double), _p(b, C.c_double), ip, n, int(doScale), int(allow_small), C.byref(s), _p(R, C.c_double), _p(T, C.c_double), C.byref(err))
+    if rc != 0:
+        raise ValueError("Need at least 4 point pairs")
+    return s.value, R.reshape(3, 3), T, err.value
+
+
+def score(R, T, Ya, Yb, thr):
+    """RANSAC_CALC_VER2.m:121-125,135.  Returns count, mask(N) bool, errsum."""
+    R, T, ya, yb = _f64(R).reshape(9), _f64(T), _f64(Ya), _f64(Yb)
+    N = ya.shape[0]
+    mask = np.zeros(max(N, 1), np.uint8)
+    es = C.c_double()
+    c = lib().orc_score(_p(R, C.c_double), _p(T, C.c_double), _p(ya, C.c_double), _p(yb, C.c_double), N, C.c_double(thr), _p(mask, C.c_uint8), C.byref(es))
+    return int(c), mask[:N].astype(bool), es.value
+
+
+def distance_threshold(Yb):
+    yb = _f64(Yb)
+    return float(lib().orc_distance_threshold(_p(yb, C.c_double), yb.shape[0]))
+
+
+def adaptive_niter(card, n_points, k=5, mult=5):
+    return float(lib().orc_adaptive_niter(int(card), int(n_points), int(k), int(mult)))
+
+
+def sample_sets(seed, pair, H, N, k):
+    """(H,k) int32 0-based ascending subsets -- the seeded stand-in for get_rand.m."""
+    out = np.zeros((H, k), np.int32)
+    L = lib()
+    L.orc_sample_set.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.POINTER(C.c_int32)]
+    for h in range(H):
+        L.orc_sample_set(seed, pair, h, N, k, _p(out[h], C.c_int32))
+    return out
+
+
+@dataclass
+class Ransac:
+    status: int
+    state: int
+    best_fit: int
+    best_sample: int
+    best_iter: int
+    n_iter: int
+    n_consumed: int
+    thr: float
+    error_sum: float
+    R: np.ndarray
+    T: np.ndarray
+    R_hyp: np.ndarray
+    T_hyp: np.ndarray
+    mask: np.ndarray
+    counts: np.ndarray | None = None
+    states: np.ndarray | None = None
+
+
+def _unpack(res, mask, counts=None, states=None):
+    return Ransac(
+        res.status, res.state, res.best_fit, res.best_sample, res.best_iter, res.n_iter, res.n_consumed,
+        res.thr, res.error_sum, np.array(res.R).reshape(3, 3), np.array(res.T), np.array(res.R_hyp).reshape(3, 3),
+        np.array(res.T_hyp), mask, counts, states,
+    )
+
+
+def ransac(Ya, Yb, samples, method=0, max_iteration=2000, distance_threshold=0.05, adaptive=True):
+    """RANSAC_CALC_VER2.m (method 0) / RANSAC_CALC_VER_test.m (method 1) with supplied
+    sample sets (H,k) int32 0-based."""
+    ya, yb = _f64(Ya), _f64(Yb)
+    N = ya.shape[0]
+    samples = np.ascontiguousarray(samples, np.int32)
+    H, k = samples.shape
+    res = RansacResult()
+    mask = np.zeros(max(N, 1), np.uint8)
+    counts = np.zeros(max(H, 1), np.int32)
+    states = np.zeros(max(H, 1), np.int8)
+    lib().orc_ransac(_p(ya, C.c_double), _p(yb, C.c_double), N, int(method), k, int(max_iteration), C.c_double(distance_threshold), int(bool(adaptive)), _p(samples, C.c_int32), H, C.byref(res), _p(mask, C.c_uint8), _p(counts, C.c_int32), _p(states, C.c_int8))
+    return _unpack(res, mask[:N].astype(bool), counts[:H], states[:H])
+
+
+def pair(desc1, desc2, xyz1, xyz2, seed, pair_id, H=2000, ratio=1.5, method=0, k=5, max_iteration=2000, distance_threshold=0.05, adaptive=True):
+    """SIFT_match_save.m:33-53 for one pair (float64 descriptors).  Returns
+    (matches (n,2) int32 0-based, Ransac)."""
+    d1, d2, x1, x2 = _f64(desc1), _f64(desc2), _f64(xyz1), _f64(xyz2)
+    K1, ND = d1.shape
+    K2 = d2.shape[0]
+    pairs = np.zeros((max(K1, 1), 2), np.int32)
+    res = RansacResult()
+    mask = np.zeros(max(K1, 1), np.uint8)
+    L = lib()
+    L.orc_pair.argtypes = [C.POINTER(C.c_double)] * 4 + [C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_uint64, C.c_uint32, C.c_int, C.POINTER(C.c_int32), C.POINTER(RansacResult), C.POINTER(C.c_uint8)]
+    n = L.orc_pair(_p(d1, C.c_double), _p(d2, C.c_double), _p(x1, C.c_double), _p(x2, C.c_double), K1, K2, ND, ratio, method, k, max_iteration, distance_threshold, int(bool(adaptive)), seed, pair_id, H, _p(pairs, C.c_int32), C.byref(res), _p(mask, C.c_uint8))
+    return pairs[:n].copy(), _unpack(res, mask[:n].astype(bool))
+
+
+def R2q(R):
+    r = _f64(R).reshape(9)
+    q = np.zeros(4)
+    lib().orc_R2q(_p(r, C.c_double), _p(q, C.c_double))
+    return q

@@ -1,0 +1,142 @@
+"""Independent numpy / LAPACK restatement of the RANSAC path ("oracle A").
+
+TEST INFRASTRUCTURE ONLY.  Written separately from oracle/pre3_oracle.c: it uses
+LAPACK svd / eigh the way the MATLAB reference uses svd / eig, so it checks the
+Jacobi-based C oracle and the CUDA kernels to the north-star tolerance
+(1e-9 rad / 1e-9 m) rather than bit-for-bit.  Arrays: points are (N,3).
+`M/` = /root/reference/matlab_code/.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def find_transform_matrix(pset1, pset2):
+    """M/mex_files/RANSAC_CALCULATION/find_transform_matrix.m:9-42 (pset1 ~ rot*pset2 + trans)."""
+    p1 = np.asarray(pset1, float).T  # 3 x n
+    p2 = np.asarray(pset2, float).T
+    n = p2.shape[1]
+    ct1 = p1.sum(1) / n
+    ct2 = p2.sum(1) / n
+    q1 = p1 - ct1[:, None]
+    q2 = p2 - ct2[:, None]
+    H = q2 @ q1.T
+    U, S, Vt = np.linalg.svd(H)
+    V = Vt.T
+    sv = np.abs(S)
+    Xq = V @ U.T
+    mdet = np.linalg.det(Xq)
+    if round(mdet) == 1:
+        rot = Xq
+        return rot, ct1 - rot @ ct2, 1
+    if round(mdet) == -1:
+        zn = np.nonzero(sv < 1e-11)[0]
+        if zn.size == 1:
+            V[:, zn] = -V[:, zn]
+            rot = V @ U.T
+            return rot, ct1 - rot @ ct2, 2
+        return H, np.zeros(3), -1
+    return H, np.zeros(3), 0
+
+
+def horn(A, B, do_scale=True):
+    """M/absoluteOrientationQuaternion.m:56-127 (B ~ s*R*A + T) with the eigenvector of
+    the LARGEST eigenvalue."""
+    A = np.asarray(A, float).T
+    B = np.asarray(B, float).T
+    n = A.shape[1]
+    Ca = A.mean(1)
+    Cb = B.mean(1)
+    An = A - Ca[:, None]
+    Bn = B - Cb[:, None]
+    M = np.zeros((4, 4))
+    for i in range(n):
+        a = np.r_[0.0, An[:, i]]
+        b = np.r_[0.0, Bn[:, i]]
+        Ma = np.array([[a[0], -a[1], -a[2], -a[3]], [a[1], a[0], a[3], -a[2]], [a[2], -a[3], a[0], a[1]], [a[3], a[2], -a[1], a[0]]])
+        Mb = np.array([[b[0], -b[1], -b[2], -b[3]], [b[1], b[0], -b[3], b[2]], [b[2], b[3], b[0], -b[1]], [b[3], -b[2], b[1], b[0]]])
+        M += Ma.T @ Mb
+    w, E = np.linalg.eigh(0.5 * (M + M.T))
+    e = E[:, np.argmax(w)]
+    M1 = np.array([[e[0], -e[1], -e[2], -e[3]], [e[1], e[0], e[3], -e[2]], [e[2], -e[3], e[0], e[1]], [e[3], e[2], -e[1], e[0]]])
+    M2 = np.array([[e[0], -e[1], -e[2], -e[3]], [e[1], e[0], -e[3], e[2]], [e[2], e[3], e[0], -e[1]], [e[3], -e[2], e[1], e[0]]])
+    R = (M1.T @ M2)[1:, 1:]
+    if do_scale:
+        a = sum(Bn[:, i] @ R @ An[:, i] for i in range(n))
+        b = sum(Bn[:, i] @ Bn[:, i] for i in range(n))
+        s = b / a
+    else:
+        s = 1.0
+    T = Cb - s * R @ Ca
+    err = sum(np.linalg.norm(B[:, i] - (s * R @ A[:, i] + T)) for i in range(n))
+    return s, R, T, err
+
+
+def score(R, T, Ya, Yb, thr):
+    """RANSAC_CALC_VER2.m:121-125."""
+    Ya = np.asarray(Ya, float)
+    Yb = np.asarray(Yb, float)
+    res = Yb @ np.asarray(R).T + np.asarray(T)[None, :] - Ya
+    nr = np.sqrt(res[:, 0] ** 2 + res[:, 1] ** 2 + res[:, 2] ** 2)
+    mask = nr < thr
+    return int(mask.sum()), mask, float(nr[mask].sum()), nr
+
+
+def ransac_ver2(Ya, Yb, samples, max_iteration=2000, adaptive=True, method=0, distance_threshold=0.05):
+    """RANSAC_CALC_VER2.m:43-201 with supplied sample sets (H,k) 0-based."""
+    Ya = np.asarray(Ya, float)
+    Yb = np.asarray(Yb, float)
+    N = Ya.shape[0]
+    k = samples.shape[1]
+    if method == 0:
+        j = int(np.argmin(Yb[:, 2]))
+        thr = 0.01 * np.sqrt(Yb[j, 0] ** 2 + Yb[j, 1] ** 2 + Yb[j, 2] ** 2)
+        mult = 5
+    else:
+        thr = distance_threshold
+        mult = 1
+    n_iter = float(max_iteration)
+    max_support = 5
+    it = 1
+    rec = []
+    h = 0
+    while it < min(n_iter, max_iteration) and h < samples.shape[0]:
+        s = samples[h]
+        h += 1
+        if method == 0:
+            Rm, Tm, st = find_transform_matrix(Ya[s], Yb[s])
+            if st == -1:
+                continue
+        else:
+            _, Rm, Tm, _ = horn(Yb[s], Ya[s], False)
+        c, mask, es, _ = score(Rm, Tm, Ya, Yb, thr)
+        rec.append((c, es, h - 1, Rm, Tm, mask))
+        if c >= max_support:
+            max_support = c
+            if adaptive:
+                w = (c / N) ** k
+                with np.errstate(divide="ignore"):
+                    n_iter = mult * np.ceil(np.log(0.01) / np.log(1 - w)) if w < 1 else 0.0
+        it += 1
+    card = np.array([r[0] for r in rec])
+    es = np.array([r[1] for r in rec], float)
+    mx = card.max()
+    e1 = np.where((card != mx) | (card == 0), 10000.0, es)
+    best = int(np.argmin(e1))
+    c, _, hs, Rm, Tm, mask = rec[best]
+    if method == 0:
+        R, T, st = find_transform_matrix(Ya[mask], Yb[mask])
+    else:
+        _, R, T, _ = horn(Yb[mask], Ya[mask], False)
+        st = 1
+    return dict(R=R, T=T, state=st, best_fit=int(mx), best_sample=hs, mask=mask, n_iter=len(rec), thr=thr, error_sum=es[best])
+
+
+def rot_angle(Ra, Rb):
+    """Geodesic distance between two rotations, radians."""
+    D = np.asarray(Ra) @ np.asarray(Rb).T
+    c = np.clip((np.trace(D) - 1) / 2, -1, 1)
+    # for tiny angles use the skew part (acos loses precision near 1)
+    sk = 0.5 * np.array([D[2, 1] - D[1, 2], D[0, 2] - D[2, 0], D[1, 0] - D[0, 1]])
+    s = np.linalg.norm(sk)
+    return float(np.arctan2(s, c))
