@@ -1,0 +1,366 @@
+"""Host side of libpre3.so: a thin object over the C ABI (include/pre3.h).
+
+Array conventions (shared with oracle/oracle.py so that parity tests compare like with like):
+a MATLAB "3 x N" matrix is a numpy array of shape (N, 3), C-contiguous (the same bytes as
+3 x N column-major); "128 x K" descriptors are (K, 128); rotations are returned as 3x3
+numpy arrays in the usual row/column sense; indices are 0-based.  The MATLAB-shaped,
+1-based mirror of the reference's function signatures is 3pre_b200/matlab.py.
+
+torch is used only for device memory / streams (the *_dev methods take CUDA tensors).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib as L
+from ._lib import Pre3Error, RansacOpts, PairResult
+
+_CLS = {
+    np.dtype(np.float64): L.CLASS_DOUBLE,
+    np.dtype(np.float32): L.CLASS_SINGLE,
+    np.dtype(np.int8): L.CLASS_INT8,
+    np.dtype(np.uint8): L.CLASS_UINT8,
+}
+
+RESULT_DTYPE = np.dtype(
+    [("status", "<i4"), ("state", "<i4"), ("best_fit", "<i4"), ("best_sample", "<i4"), ("best_iter", "<i4"),
+     ("n_iter", "<i4"), ("n_consumed", "<i4"), ("n_matches", "<i4"), ("thr", "<f8"), ("error_sum", "<f8"),
+     ("R", "<f8", (9,)), ("T", "<f8", (3,)), ("R_hyp", "<f8", (9,)), ("T_hyp", "<f8", (3,))]
+)
+assert RESULT_DTYPE.itemsize == C.sizeof(PairResult) == 240
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return a.data_ptr()  # torch tensor
+
+
+def _c(a, dtype=None):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+def make_opts(method=L.METHOD_SVD, k=5, max_iteration=2000, adaptive=True, H=2000, distance_threshold=0.05,
+              ratio=1.5, seed=0) -> RansacOpts:
+    """options struct of RANSAC_CALC_VER2 (DistanceThreshold, MaxIteration: SIFT_match_save.m:49-50)
+    plus the explicit knobs the reference hard-codes (k: RANSAC_CALC_VER2.m:85)."""
+    return RansacOpts(int(method), int(k), int(max_iteration), int(bool(adaptive)), int(H), 0,
+                      float(distance_threshold), float(ratio), int(seed))
+
+
+@dataclass
+class Ransac:
+    """One pair's outputs, same field meaning as oracle.oracle.Ransac."""
+    status: int
+    state: int
+    best_fit: int
+    best_sample: int
+    best_iter: int
+    n_iter: int
+    n_consumed: int
+    n_matches: int
+    thr: float
+    error_sum: float
+    R: np.ndarray
+    T: np.ndarray
+    R_hyp: np.ndarray
+    T_hyp: np.ndarray
+    mask: np.ndarray | None = None
+    counts: np.ndarray | None = None
+    states: np.ndarray | None = None
+
+
+def unpack_result(rec, mask=None, counts=None, states=None) -> Ransac:
+    """rec: one element of a RESULT_DTYPE array.  R is stored column-major in the ABI."""
+    return Ransac(int(rec["status"]), int(rec["state"]), int(rec["best_fit"]), int(rec["best_sample"]),
+                  int(rec["best_iter"]), int(rec["n_iter"]), int(rec["n_consumed"]), int(rec["n_matches"]),
+                  float(rec["thr"]), float(rec["error_sum"]), np.array(rec["R"]).reshape(3, 3).T.copy(),
+                  np.array(rec["T"]), np.array(rec["R_hyp"]).reshape(3, 3).T.copy(), np.array(rec["T_hyp"]),
+                  mask, counts, states)
+
+
+class Context:
+    """pre3_ctx: one CUDA device, one stream, one workspace arena."""
+
+    def __init__(self, device: int = -1):
+        self._lib = L.load()
+        h = C.c_void_p()
+        rc = self._lib.pre3_create(C.byref(h), int(device))
+        self._h = h
+        if rc != L.OK:
+            msg = self._lib.pre3_last_error(h).decode() if h else "pre3_create failed"
+            if h:
+                self._lib.pre3_destroy(h)
+            self._h = None
+            raise Pre3Error(rc, msg)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.pre3_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc):
+        if rc != L.OK:
+            raise Pre3Error(rc, self._lib.pre3_last_error(self._h).decode())
+
+    # ---- context knobs ------------------------------------------------------------------
+    @staticmethod
+    def version() -> str:
+        return L.load().pre3_version().decode()
+
+    def set_stream(self, cuda_stream_ptr: int):
+        self._ck(self._lib.pre3_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def use_torch_stream(self):
+        import torch
+        self.set_stream(torch.cuda.current_stream().cuda_stream)
+
+    def set_match_engine(self, engine: int):
+        self._ck(self._lib.pre3_set_match_engine(self._h, int(engine)))
+
+    def sync(self):
+        self._ck(self._lib.pre3_sync(self._h))
+
+    def launch_count(self) -> int:
+        return int(self._lib.pre3_launch_count(self._h))
+
+    def timing_enable(self, on: bool = True):
+        self._ck(self._lib.pre3_timing_enable(self._h, int(bool(on))))
+
+    def timing_read(self) -> dict:
+        """{category: (total ms, launches)} of the bracketed launches since the last read."""
+        ms = np.zeros(L.TIMING_NCAT)
+        cnt = np.zeros(L.TIMING_NCAT, np.int64)
+        self._ck(self._lib.pre3_timing_read(self._h, _ptr(ms), _ptr(cnt)))
+        return {self._lib.pre3_timing_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(L.TIMING_NCAT)
+                if cnt[i]}
+
+    def measure_fp32_peak(self) -> float:
+        """FFMA-chain microbenchmark, TFLOP/s (the scoring roofline's denominator)."""
+        t = np.zeros(1)
+        self._ck(self._lib.pre3_measure_fp32_peak(self._h, _ptr(t)))
+        return float(t[0])
+
+    # ---- stage 1 ------------------------------------------------------------------------
+    def siftmatch(self, L1, L2, thresh: float = 1.5):
+        """L1 (K1,ND), L2 (K2,ND) same dtype in {f64,f32,i8,u8}.  Returns (pairs (n,2) int32
+        0-based in k1 order, score (n,) float64) -- siftmatch.c:83-132."""
+        L1, L2 = _c(L1), _c(L2)
+        if L1.dtype != L2.dtype:
+            raise ValueError("L1 and L2 must be of the same class")
+        if L1.dtype not in _CLS:
+            raise ValueError("Unsupported numeric class")
+        if L1.ndim != 2 or L2.ndim != 2 or L1.shape[1] != L2.shape[1]:
+            raise ValueError("L1 and L2 must have the same number of rows")
+        K1, ND = L1.shape
+        K2 = L2.shape[0]
+        pairs = np.zeros((max(K1, 1), 2), np.int32)
+        score = np.zeros(max(K1, 1), np.float64)
+        n = np.zeros(1, np.int32)
+        self._ck(self._lib.pre3_siftmatch(self._h, _ptr(L1), _ptr(L2), _CLS[L1.dtype], K1, K2, ND, float(thresh),
+                                          _ptr(pairs), _ptr(score), _ptr(n)))
+        return pairs[: n[0]].copy(), score[: n[0]].copy()
+
+    def siftmatch_batch(self, L1, L2, thresh: float = 1.5, k1_count=None, k2_count=None):
+        """L1 (P,K1,ND), L2 (P,K2,ND).  Returns list of (pairs, score) per problem."""
+        L1, L2 = _c(L1), _c(L2)
+        if L1.dtype != L2.dtype or L1.dtype not in _CLS:
+            raise ValueError("Unsupported numeric class")
+        P, K1, ND = L1.shape
+        K2 = L2.shape[1]
+        pairs = np.zeros((P, max(K1, 1), 2), np.int32)
+        score = np.zeros((P, max(K1, 1)), np.float64)
+        n = np.zeros(max(P, 1), np.int32)
+        k1c = None if k1_count is None else _c(k1_count, np.int32)
+        k2c = None if k2_count is None else _c(k2_count, np.int32)
+        self._ck(self._lib.pre3_siftmatch_batch(self._h, _ptr(L1), _ptr(L2), _CLS[L1.dtype], P, K1, K2, ND,
+                                                _ptr(k1c), _ptr(k2c), float(thresh), _ptr(pairs), _ptr(score),
+                                                _ptr(n)))
+        return [(pairs[p, : n[p]].copy(), score[p, : n[p]].copy()) for p in range(P)]
+
+    # ---- stage 2 ------------------------------------------------------------------------
+    def find_transform_matrix(self, pset1, pset2):
+        """pset (n,3).  Returns rot (3,3), trans (3,), state (find_transform_matrix.m:2-42)."""
+        p1, p2 = _c(pset1, np.float64), _c(pset2, np.float64)
+        rot, tr, st = np.zeros(9), np.zeros(3), np.zeros(1, np.int32)
+        self._ck(self._lib.pre3_find_transform_matrix(self._h, _ptr(p1), _ptr(p2), p1.shape[0], _ptr(rot), _ptr(tr),
+                                                      _ptr(st)))
+        return rot.reshape(3, 3).T.copy(), tr, int(st[0])
+
+    def horn(self, A, B, do_scale: int = 1):
+        """A,B (n,3), B ~ s*R*A + T.  Returns s, R, T, err (absoluteOrientationQuaternion.m:28-127)."""
+        a, b = _c(A, np.float64), _c(B, np.float64)
+        if a.shape != b.shape:
+            raise ValueError("Point sets need to have same size.")
+        if a.ndim != 2 or a.shape[1] != 3:
+            raise ValueError("Need points of dimension 3")
+        if a.shape[0] < 4:
+            raise ValueError("Need at least 4 point pairs")
+        s, err, R, T = np.zeros(1), np.zeros(1), np.zeros(9), np.zeros(3)
+        self._ck(self._lib.pre3_horn(self._h, _ptr(a), _ptr(b), a.shape[0], int(do_scale), _ptr(s), _ptr(R), _ptr(T),
+                                     _ptr(err)))
+        return float(s[0]), R.reshape(3, 3).T.copy(), T, float(err[0])
+
+    def fit_batch(self, Ya, Yb, samples, method=L.METHOD_SVD):
+        """samples (H,k) int32 0-based.  Returns R (H,3,3), T (H,3), state (H,)."""
+        ya, yb = _c(Ya, np.float64), _c(Yb, np.float64)
+        s = _c(samples, np.int32)
+        H, k = s.shape
+        R, T, st = np.zeros((H, 9)), np.zeros((H, 3)), np.zeros(H, np.int32)
+        self._ck(self._lib.pre3_fit_batch(self._h, _ptr(ya), _ptr(yb), ya.shape[0], _ptr(s), k, H, int(method),
+                                          _ptr(R), _ptr(T), _ptr(st)))
+        return R.reshape(H, 3, 3).transpose(0, 2, 1).copy(), T, st
+
+    # ---- stage 3 ------------------------------------------------------------------------
+    def score_batch(self, R, T, Ya, Yb, thr, want_errsum=True, want_mask=True):
+        """R (H,3,3), T (H,3).  Returns count (H,), errsum (H,)|None, mask (H,N) bool|None."""
+        R = np.asarray(R, np.float64).reshape(-1, 3, 3)
+        H = R.shape[0]
+        Rc = _c(R.transpose(0, 2, 1)).reshape(H, 9)  # column-major per hypothesis
+        T = _c(np.asarray(T, np.float64).reshape(H, 3))
+        ya, yb = _c(Ya, np.float64), _c(Yb, np.float64)
+        N = ya.shape[0]
+        cnt = np.zeros(H, np.int32)
+        es = np.zeros(H) if want_errsum else None
+        mk = np.zeros((H, max(N, 1)), np.uint8) if want_mask else None
+        self._ck(self._lib.pre3_score_batch(self._h, _ptr(Rc), _ptr(T), H, _ptr(ya), _ptr(yb), N, float(thr),
+                                            _ptr(cnt), _ptr(es), _ptr(mk)))
+        if mk is not None:
+            mk = mk.reshape(-1)[: H * N].reshape(H, N).astype(bool)
+        return cnt, es, mk
+
+    # ---- stages 2-4 ---------------------------------------------------------------------
+    def ransac(self, Ya, Yb, samples=None, opts: RansacOpts | None = None, **kw):
+        """One pair.  samples (H,k) int32 0-based or None (seeded).  Returns Ransac with mask,
+        counts, states (RANSAC_CALC_VER2.m:2-201 / RANSAC_CALC_VER_test.m)."""
+        ya, yb = _c(Ya, np.float64), _c(Yb, np.float64)
+        N = ya.shape[0]
+        o = opts or make_opts(**kw)
+        s = None
+        if samples is not None:
+            s = _c(samples, np.int32)
+            o.H, o.k = int(s.shape[0]), int(s.shape[1])
+        res = np.zeros(1, RESULT_DTYPE)
+        mask = np.zeros(max(N, 1), np.uint8)
+        counts = np.zeros(max(o.H, 1), np.int32)
+        states = np.zeros(max(o.H, 1), np.int8)
+        self._ck(self._lib.pre3_ransac(self._h, _ptr(ya), _ptr(yb), N, C.byref(o), _ptr(s), _ptr(res), _ptr(mask),
+                                       _ptr(counts), _ptr(states)))
+        return unpack_result(res[0], mask[:N].astype(bool), counts[: o.H], states[: o.H])
+
+    def ransac_batch(self, Ya, Yb, n_corr=None, samples=None, opts: RansacOpts | None = None, want_masks=True, **kw):
+        """Ya, Yb (P,Nmax,3); n_corr (P,) or None; samples (P,H,k) or None.  Returns
+        (results RESULT_DTYPE (P,), masks (P,Nmax) uint8 | None)."""
+        ya, yb = _c(Ya, np.float64), _c(Yb, np.float64)
+        P, Nmax = ya.shape[0], ya.shape[1]
+        o = opts or make_opts(**kw)
+        s = None
+        if samples is not None:
+            s = _c(samples, np.int32)
+            o.H, o.k = int(s.shape[1]), int(s.shape[2])
+        nc = None if n_corr is None else _c(n_corr, np.int32)
+        res = np.zeros(max(P, 1), RESULT_DTYPE)
+        masks = np.zeros((max(P, 1), max(Nmax, 1)), np.uint8) if want_masks else None
+        self._ck(self._lib.pre3_ransac_batch(self._h, _ptr(ya), _ptr(yb), _ptr(nc), P, Nmax, C.byref(o), _ptr(s),
+                                             _ptr(res), _ptr(masks)))
+        return res[:P], (masks[:P, :Nmax] if masks is not None else None)
+
+    # ---- whole pairs --------------------------------------------------------------------
+    def pairs(self, desc1, desc2, xyz1, xyz2, opts: RansacOpts | None = None, pair_id0=0, k1_count=None,
+              k2_count=None, want_matches=True, want_masks=True, out=None, **kw):
+        """desc (P,K,128) f64/f32/u8/i8, xyz (P,K,3) f64 -- numpy (pinned or pageable) host
+        arrays.  SIFT_match_save.m:33-53 for P pairs.  Returns (results (P,), matches (P,K1,2)
+        int32 | None, masks (P,K1) uint8 | None); the number of valid matches of pair p is
+        results['n_matches'][p].  `out`: optional preallocated (res, matches, masks) tuple."""
+        d1, d2 = _c(desc1), _c(desc2)
+        if d1.dtype != d2.dtype or d1.dtype not in _CLS:
+            raise ValueError("Unsupported numeric class")
+        x1, x2 = _c(xyz1, np.float64), _c(xyz2, np.float64)
+        P, K1, ND = d1.shape
+        K2 = d2.shape[1]
+        o = opts or make_opts(**kw)
+        k1c = None if k1_count is None else _c(k1_count, np.int32)
+        k2c = None if k2_count is None else _c(k2_count, np.int32)
+        if out is not None:
+            res, matches, masks = out
+        else:
+            res = np.zeros(max(P, 1), RESULT_DTYPE)
+            matches = np.zeros((max(P, 1), max(K1, 1), 2), np.int32) if want_matches else None
+            masks = np.zeros((max(P, 1), max(K1, 1)), np.uint8) if want_masks else None
+        self._ck(self._lib.pre3_pairs(self._h, _ptr(d1), _ptr(d2), _CLS[d1.dtype], _ptr(x1), _ptr(x2), P, K1, K2, ND,
+                                      _ptr(k1c), _ptr(k2c), C.byref(o), int(pair_id0), _ptr(res), _ptr(matches),
+                                      _ptr(masks)))
+        return res[:P], (matches[:P] if matches is not None else None), (masks[:P] if masks is not None else None)
+
+    # ---- device-pointer entry points (torch CUDA tensors, stream-ordered, no sync) --------
+    def pairs_dev(self, desc1, desc2, xyz1, xyz2, opts: RansacOpts, res, matches=None, masks=None, pair_id0=0,
+                  k1_count=None, k2_count=None):
+        """CUDA tensors: desc (P,K,128) f64/f32/u8/i8; xyz (P,K,3) f64; res uint8 (P,240);
+        matches int32 (P,K1,2) | None; masks uint8 (P,K1) | None."""
+        import torch
+        cls = {torch.float64: L.CLASS_DOUBLE, torch.float32: L.CLASS_SINGLE, torch.int8: L.CLASS_INT8,
+               torch.uint8: L.CLASS_UINT8}[desc1.dtype]
+        P, K1, ND = desc1.shape
+        K2 = desc2.shape[1]
+        for t in (desc1, desc2, xyz1, xyz2, res):
+            assert t.is_cuda and t.is_contiguous()
+        self._ck(self._lib.pre3_pairs_dev(self._h, _ptr(desc1), _ptr(desc2), cls, _ptr(xyz1), _ptr(xyz2), P, K1, K2,
+                                          ND, _ptr(k1_count), _ptr(k2_count), C.byref(opts), int(pair_id0),
+                                          _ptr(res), _ptr(matches), _ptr(masks)))
+
+    def siftmatch_batch_dev(self, L1, L2, pairs, score, n_out, thresh=1.5, k1_count=None, k2_count=None):
+        import torch
+        cls = {torch.float64: L.CLASS_DOUBLE, torch.float32: L.CLASS_SINGLE, torch.int8: L.CLASS_INT8,
+               torch.uint8: L.CLASS_UINT8}[L1.dtype]
+        P, K1, ND = L1.shape
+        K2 = L2.shape[1]
+        self._ck(self._lib.pre3_siftmatch_batch_dev(self._h, _ptr(L1), _ptr(L2), cls, P, K1, K2, ND, _ptr(k1_count),
+                                                    _ptr(k2_count), float(thresh), _ptr(pairs), _ptr(score),
+                                                    _ptr(n_out)))
+
+    def ransac_batch_dev(self, Ya, Yb, opts: RansacOpts, res, n_corr=None, samples=None, masks=None):
+        P, Nmax = Ya.shape[0], Ya.shape[1]
+        self._ck(self._lib.pre3_ransac_batch_dev(self._h, _ptr(Ya), _ptr(Yb), _ptr(n_corr), P, Nmax, C.byref(opts),
+                                                 _ptr(samples), _ptr(res), _ptr(masks)))
+
+    def distance_threshold_dev(self, Yb, out):
+        self._ck(self._lib.pre3_distance_threshold_dev(self._h, _ptr(Yb), Yb.shape[0], _ptr(out)))
+
+    def ransac_block_dev(self, Ya, Yb, opts: RansacOpts, h0: int, Hloc: int, thr: float, key, errsum=None,
+                         samples=None):
+        """Local best of hypotheses [h0, h0+Hloc) of one pair: key (1,) int64/uint64 tensor =
+        (count << 32) | (0xFFFFFFFF - global id); errsum (1,) f64 tensor | None."""
+        self._ck(self._lib.pre3_ransac_block_dev(self._h, _ptr(Ya), _ptr(Yb), Ya.shape[0], C.byref(opts),
+                                                 _ptr(samples), int(h0), int(Hloc), float(thr), _ptr(key),
+                                                 _ptr(errsum)))
+
+    def ransac_finish_dev(self, Ya, Yb, opts: RansacOpts, winner_id: int, thr: float, res, mask=None,
+                          sample_of_winner=None):
+        self._ck(self._lib.pre3_ransac_finish_dev(self._h, _ptr(Ya), _ptr(Yb), Ya.shape[0], C.byref(opts),
+                                                  _ptr(sample_of_winner), int(winner_id), float(thr), _ptr(res),
+                                                  _ptr(mask)))
+
+
+def R2q(R):
+    """slamToolbox R2q (R2q.m:11-55): q = [a -b -c -d]'.  R is a 3x3 array."""
+    Rc = _c(np.asarray(R, np.float64).T).reshape(9)  # column-major bytes
+    q = np.zeros(4)
+    L.load().pre3_R2q(_ptr(Rc), _ptr(q))
+    return q

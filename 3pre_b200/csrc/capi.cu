@@ -1,0 +1,684 @@
+// capi.cu -- the C ABI of libpre3.so (include/pre3.h): argument checks, workspace
+// carving, host<->device staging and kernel sequencing.  No arithmetic lives here.
+//
+// Every compute entry point fails with PRE3_ERR_CUDA when there is no CUDA device: there is
+// no CPU fallback by design (the CPU restatement lives in oracle/ and is test-only).
+#include <cstring>
+
+#include "common.cuh"
+#include "match.cuh"
+#include "ransac.cuh"
+
+using namespace pre3;
+
+namespace {
+
+size_t class_size(int cls) {
+  switch (cls) {
+    case PRE3_CLASS_DOUBLE: return 8;
+    case PRE3_CLASS_SINGLE: return 4;
+    case PRE3_CLASS_INT8:
+    case PRE3_CLASS_UINT8: return 1;
+    default: return 0;
+  }
+}
+
+#define PRE3_NEED(cond, msg) \
+  do {                       \
+    if (!(cond)) return fail(ctx, PRE3_ERR_ARG, msg); \
+  } while (0)
+
+int h2d(pre3_ctx* ctx, void* d, const void* h, size_t bytes) {
+  if (bytes == 0) return PRE3_OK;
+  PRE3_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return PRE3_OK;
+}
+
+int d2h(pre3_ctx* ctx, void* h, const void* d, size_t bytes) {
+  if (bytes == 0) return PRE3_OK;
+  PRE3_CUDA(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  return PRE3_OK;
+}
+
+int check_opts(pre3_ctx* ctx, const pre3_ransac_opts* o) {
+  PRE3_NEED(o != nullptr, "options missing");
+  PRE3_NEED(o->method == PRE3_METHOD_SVD || o->method == PRE3_METHOD_HORN, "unknown RANSAC method");
+  PRE3_NEED(o->k >= 3 && o->k <= 8, "minimal sample size k must be in 3..8");
+  PRE3_NEED(o->H >= 0, "H must be >= 0");
+  PRE3_NEED(o->max_iteration >= 0, "MaxIteration must be >= 0");
+  return PRE3_OK;
+}
+
+// ---- stage 1 on device buffers; workspace must already hold match_ws_bytes() ---------------
+size_t match_ws_bytes(int cls, int P, int K1, int K2, int ND) {
+  return match_workspace_bytes(cls, P, K1, K2, ND) + align_up(sizeof(MatchRow) * (size_t)P * K1) + 1024;
+}
+
+int match_impl(pre3_ctx* ctx, const void* dL1, const void* dL2, int cls, int P, int K1, int K2, int ND,
+               const int32_t* dk1, const int32_t* dk2, double thresh, MatchRow** rows_out) {
+  MatchRow* rows = ws_take<MatchRow>(ctx, (size_t)P * K1);
+  const float th = (float)thresh;  // narrowed like the reference (siftmatch.c:87,:205)
+  bool tc = false;
+  if (ctx->match_engine != PRE3_MATCH_EXACT) tc = match_tc_supported(cls, K1, K2, ND);
+  if (ctx->match_engine == PRE3_MATCH_TC && !tc)
+    return fail(ctx, PRE3_ERR_ARG, "tensor-core matcher needs class double/single and ND == 128");
+  if (tc)
+    PRE3_TRY(launch_match_tc(ctx, dL1, dL2, cls, P, K1, K2, ND, dk1, dk2, th, rows));
+  else
+    PRE3_TRY(launch_match_exact(ctx, dL1, dL2, cls, P, K1, K2, ND, dk1, dk2, th, rows));
+  *rows_out = rows;
+  return PRE3_OK;
+}
+
+int check_match_args(pre3_ctx* ctx, const void* L1, const void* L2, int cls, int P, int K1, int K2, int ND) {
+  PRE3_NEED(ctx != nullptr, "context missing");
+  if (class_size(cls) == 0) return fail(ctx, PRE3_ERR_CLASS, "Unsupported numeric class");
+  PRE3_NEED(P >= 0 && K1 >= 0 && K2 >= 0 && ND >= 0, "negative size");
+  PRE3_NEED((L1 != nullptr || (size_t)P * K1 * ND == 0) && (L2 != nullptr || (size_t)P * K2 * ND == 0),
+            "descriptor pointer missing");
+  return PRE3_OK;
+}
+
+// ---- stages 2-4 on device buffers; workspace must already hold ransac_ws_bytes() -----------
+size_t ransac_ws_bytes(int P, int Nmax, int H) { return ransac_workspace_bytes(P, Nmax, H) + 4096; }
+
+int ransac_impl(pre3_ctx* ctx, const double* dYa, const double* dYb, const int32_t* dn_corr, int P, int Nmax,
+                const pre3_ransac_opts& o, const int32_t* dsamples, uint32_t pair_id0, pre3_pair_result* dres,
+                uint8_t* dmasks, int32_t* dcounts, int8_t* dstates) {
+  RansacBuffers b{};
+  b.Ya = dYa;
+  b.Yb = dYb;
+  b.n_corr = dn_corr;
+  b.P = P;
+  b.Nmax = Nmax;
+  b.samples = dsamples;
+  b.pair_id0 = pair_id0;
+  ransac_carve(ctx, b, o.H);
+  PRE3_TRY(ensure_adaptive_table(ctx, o, Nmax));
+  PRE3_TRY(launch_prep(ctx, b, o, 0));
+  PRE3_TRY(launch_eval(ctx, b, o, 0));
+  PRE3_TRY(launch_select(ctx, b, o, dres, dmasks, dcounts, dstates));
+  return PRE3_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+// context
+// ================================================================================================
+extern "C" {
+
+const char* pre3_version(void) { return "pre3-b200 0.1 (sm_100a)"; }
+
+int pre3_create(pre3_ctx** out, int device) {
+  if (!out) return PRE3_ERR_ARG;
+  *out = nullptr;
+  pre3_ctx* ctx = new pre3_ctx();
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0) {
+    // keep the context alive so that pre3_last_error() can report why
+    ctx->err = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+               " (libpre3 has no CPU fallback)";
+    ctx->device = -1;
+    *out = ctx;
+    return PRE3_ERR_CUDA;
+  }
+  if (device < 0) {
+    e = cudaGetDevice(&device);
+    if (e != cudaSuccess) device = 0;
+  }
+  if (device >= ndev) {
+    ctx->err = "device index out of range";
+    ctx->device = -1;
+    *out = ctx;
+    return PRE3_ERR_ARG;
+  }
+  ctx->device = device;
+  *out = ctx;
+  PRE3_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  PRE3_CUDA(cudaGetDeviceProperties(&prop, device));
+  ctx->sm_count = prop.multiProcessorCount;
+  if (prop.major != 10) {
+    ctx->err = std::string("libpre3 is built for sm_100a only; device is sm_") + std::to_string(prop.major) +
+               std::to_string(prop.minor);
+    ctx->device = -1;
+    return PRE3_ERR_CUDA;
+  }
+  PRE3_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  ctx->own_stream = true;
+  return PRE3_OK;
+}
+
+void pre3_destroy(pre3_ctx* ctx) {
+  if (!ctx) return;
+  if (ctx->device >= 0) {
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->ws) cudaFree(ctx->ws);
+    if (ctx->d_tab) cudaFree(ctx->d_tab);
+    if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+    for (void* p : ctx->aux) cudaFree(p);
+    for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    for (int i = 0; i < 2; ++i) {
+      if (ctx->ev_slot_full[i]) cudaEventDestroy(ctx->ev_slot_full[i]);
+      if (ctx->ev_slot_free[i]) cudaEventDestroy(ctx->ev_slot_free[i]);
+    }
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  }
+  delete ctx;
+}
+
+const char* pre3_last_error(const pre3_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int pre3_set_stream(pre3_ctx* ctx, void* cuda_stream) {
+  if (!ctx || ctx->device < 0) return PRE3_ERR_CUDA;
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  ctx->stream = (cudaStream_t)cuda_stream;
+  ctx->own_stream = false;
+  return PRE3_OK;
+}
+
+int pre3_set_match_engine(pre3_ctx* ctx, int engine) {
+  if (!ctx) return PRE3_ERR_ARG;
+  if (engine < PRE3_MATCH_AUTO || engine > PRE3_MATCH_TC) return fail(ctx, PRE3_ERR_ARG, "unknown match engine");
+  ctx->match_engine = engine;
+  return PRE3_OK;
+}
+
+int pre3_sync(pre3_ctx* ctx) {
+  if (!ctx || ctx->device < 0) return ctx ? fail(ctx, PRE3_ERR_CUDA, "no CUDA device") : PRE3_ERR_ARG;
+  PRE3_CUDA(cudaStreamSynchronize(ctx->stream));
+  return PRE3_OK;
+}
+
+int64_t pre3_launch_count(const pre3_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int pre3_timing_enable(pre3_ctx* ctx, int on) {
+  if (!ctx || ctx->device < 0) return PRE3_ERR_CUDA;
+  ctx->timing = on != 0;
+  return PRE3_OK;
+}
+
+int pre3_timing_read(pre3_ctx* ctx, double* ms, int64_t* count) {
+  if (!ctx || ctx->device < 0) return PRE3_ERR_CUDA;
+  PRE3_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (const TimedSpan& s : ctx->spans) {
+    float t = 0.f;
+    PRE3_CUDA(cudaEventElapsedTime(&t, s.a, s.b));
+    if (ms) ms[s.cat] += (double)t;
+    if (count) count[s.cat] += 1;
+  }
+  ctx->spans.clear();
+  ctx->ev_used = 0;
+  return PRE3_OK;
+}
+
+const char* pre3_timing_name(int cat) {
+  static const char* names[T_NCAT] = {"convert", "match_tc", "match_exact", "rescore", "compact",
+                                      "prep",    "eval",     "select",      "other"};
+  return (cat >= 0 && cat < T_NCAT) ? names[cat] : "?";
+}
+
+#define PRE3_LIVE()                                                                          \
+  do {                                                                                       \
+    if (!ctx) return PRE3_ERR_ARG;                                                           \
+    if (ctx->device < 0) return fail(ctx, PRE3_ERR_CUDA, "no CUDA device (libpre3 has no CPU fallback)"); \
+    PRE3_CUDA(cudaSetDevice(ctx->device));                                                   \
+  } while (0)
+
+// ================================================================================================
+// stage 1
+// ================================================================================================
+int pre3_siftmatch_batch_dev(pre3_ctx* ctx, const void* dL1, const void* dL2, int cls, int P, int K1, int K2,
+                             int ND, const int32_t* dk1_count, const int32_t* dk2_count, double thresh,
+                             int32_t* dpairs, double* dscore, int32_t* dn_out) {
+  PRE3_LIVE();
+  PRE3_TRY(check_match_args(ctx, dL1, dL2, cls, P, K1, K2, ND));
+  PRE3_NEED(dn_out != nullptr, "n_out missing");
+  if (P == 0) return PRE3_OK;
+  PRE3_TRY(ws_reserve(ctx, match_ws_bytes(cls, P, K1, K2, ND)));
+  MatchRow* rows = nullptr;
+  if (K1 > 0) PRE3_TRY(match_impl(ctx, dL1, dL2, cls, P, K1, K2, ND, dk1_count, dk2_count, thresh, &rows));
+  PRE3_TRY(launch_match_compact(ctx, rows, P, K1, dk1_count, dpairs, dscore, dn_out, nullptr, nullptr, K2, nullptr,
+                                nullptr));
+  return PRE3_OK;
+}
+
+int pre3_siftmatch_batch(pre3_ctx* ctx, const void* L1, const void* L2, int cls, int P, int K1, int K2, int ND,
+                         const int32_t* k1_count, const int32_t* k2_count, double thresh, int32_t* pairs,
+                         double* score, int32_t* n_out) {
+  PRE3_LIVE();
+  PRE3_TRY(check_match_args(ctx, L1, L2, cls, P, K1, K2, ND));
+  PRE3_NEED(n_out != nullptr, "n_out missing");
+  if (P == 0) return PRE3_OK;
+  const size_t es = class_size(cls);
+  const size_t b1 = (size_t)P * K1 * ND * es, b2 = (size_t)P * K2 * ND * es;
+  const size_t np = (size_t)P * K1;
+  size_t need = match_ws_bytes(cls, P, K1, K2, ND) + align_up(b1) + align_up(b2) + 2 * align_up(4 * (size_t)P) +
+                align_up(8 * np) + align_up(8 * np) + align_up(4 * (size_t)P) + 4096;
+  PRE3_TRY(ws_reserve(ctx, need));
+  char* d1 = ws_take<char>(ctx, b1);
+  char* d2 = ws_take<char>(ctx, b2);
+  int32_t* dk1 = k1_count ? ws_take<int32_t>(ctx, P) : nullptr;
+  int32_t* dk2 = k2_count ? ws_take<int32_t>(ctx, P) : nullptr;
+  int32_t* dpairs = ws_take<int32_t>(ctx, 2 * np);
+  double* dscore = ws_take<double>(ctx, np);
+  int32_t* dn = ws_take<int32_t>(ctx, P);
+  PRE3_TRY(h2d(ctx, d1, L1, b1));
+  PRE3_TRY(h2d(ctx, d2, L2, b2));
+  if (dk1) PRE3_TRY(h2d(ctx, dk1, k1_count, 4 * (size_t)P));
+  if (dk2) PRE3_TRY(h2d(ctx, dk2, k2_count, 4 * (size_t)P));
+  MatchRow* rows = nullptr;
+  if (K1 > 0) PRE3_TRY(match_impl(ctx, d1, d2, cls, P, K1, K2, ND, dk1, dk2, thresh, &rows));
+  PRE3_TRY(launch_match_compact(ctx, rows, P, K1, dk1, dpairs, dscore, dn, nullptr, nullptr, K2, nullptr, nullptr));
+  if (pairs) PRE3_TRY(d2h(ctx, pairs, dpairs, 8 * np));
+  if (score) PRE3_TRY(d2h(ctx, score, dscore, 8 * np));
+  PRE3_TRY(d2h(ctx, n_out, dn, 4 * (size_t)P));
+  PRE3_CUDA(cudaStreamSynchronize(ctx->stream));
+  return PRE3_OK;
+}
+
+int pre3_siftmatch(pre3_ctx* ctx, const void* L1, const void* L2, int cls, int K1, int K2, int ND, double thresh,
+                   int32_t* pairs, double* score, int32_t* n_out) {
+  return pre3_siftmatch_batch(ctx, L1, L2, cls, 1, K1, K2, ND, nullptr, nullptr, thresh, pairs, score, n_out);
+}
+
+// ================================================================================================
+// stage 2
+// ================================================================================================
+static int fit_all_host(pre3_ctx* ctx, const double* p1, const double* p2, int n, int method, int do_scale,
+                        double* out15) {
+  const size_t pb = 3 * (size_t)n * sizeof(double);
+  PRE3_TRY(ws_reserve(ctx, 2 * align_up(pb) + 4096));
+  double* d1 = ws_take<double>(ctx, 3 * (size_t)n);
+  double* d2 = ws_take<double>(ctx, 3 * (size_t)n);
+  double* dout = ws_take<double>(ctx, 16);
+  PRE3_TRY(h2d(ctx, d1, p1, pb));
+  PRE3_TRY(h2d(ctx, d2, p2, pb));
+  PRE3_TRY(launch_fit_all(ctx, d1, d2, n, method, do_scale, dout));
+  PRE3_TRY(d2h(ctx, out15, dout, 15 * sizeof(double)));
+  PRE3_CUDA(cudaStreamSynchronize(ctx->stream));
+  return PRE3_OK;
+}
+
+int pre3_find_transform_matrix(pre3_ctx* ctx, const double* pset1, const double* pset2, int n, double* rot,
+                               double* trans, int32_t* state) {
+  PRE3_LIVE();
+  PRE3_NEED(pset1 && pset2 && rot && trans && state, "null pointer");
+  PRE3_NEED(n >= 0, "negative point count");
+  double out[15];
+  PRE3_TRY(fit_all_host(ctx, pset1, pset2, n, PRE3_METHOD_SVD, 0, out));
+  memcpy(rot, out, 9 * sizeof(double));
+  memcpy(trans, out + 9, 3 * sizeof(double));
+  *state = (int32_t)out[12];
+  return PRE3_OK;
+}
+
+int pre3_horn(pre3_ctx* ctx, const double* A, const double* B, int n, int do_scale, double* s, double* R, double* T,
+              double* err) {
+  PRE3_LIVE();
+  PRE3_NEED(A && B && R && T, "null pointer");
+  PRE3_NEED(n >= 4, "Need at least 4 point pairs");  // absoluteOrientationQuaternion.m:51-54
+  double out[15];
+  PRE3_TRY(fit_all_host(ctx, A, B, n, PRE3_METHOD_HORN, do_scale ? 1 : 0, out));
+  memcpy(R, out, 9 * sizeof(double));
+  memcpy(T, out + 9, 3 * sizeof(double));
+  if (s) *s = out[13];
+  if (err) *err = out[14];
+  return PRE3_OK;
+}
+
+int pre3_fit_batch(pre3_ctx* ctx, const double* Ya, const double* Yb, int N, const int32_t* samples, int k, int H,
+                   int method, double* R, double* T, int32_t* state) {
+  PRE3_LIVE();
+  PRE3_NEED(Ya && Yb && samples && R && T && state, "null pointer");
+  PRE3_NEED(N >= 1 && H >= 0, "bad sizes");
+  PRE3_NEED(k >= 3 && k <= 8, "minimal sample size k must be in 3..8");
+  PRE3_NEED(method == PRE3_METHOD_SVD || method == PRE3_METHOD_HORN, "unknown method");
+  if (H == 0) return PRE3_OK;
+  const size_t pb = 3 * (size_t)N * 8, sb = 4 * (size_t)k * H;
+  PRE3_TRY(ws_reserve(ctx, 2 * align_up(pb) + align_up(sb) + align_up(72 * (size_t)H) + align_up(24 * (size_t)H) +
+                               align_up(4 * (size_t)H) + 4096));
+  double* dYa = ws_take<double>(ctx, 3 * (size_t)N);
+  double* dYb = ws_take<double>(ctx, 3 * (size_t)N);
+  int32_t* ds = ws_take<int32_t>(ctx, (size_t)k * H);
+  double* dR = ws_take<double>(ctx, 9 * (size_t)H);
+  double* dT = ws_take<double>(ctx, 3 * (size_t)H);
+  int32_t* dst = ws_take<int32_t>(ctx, H);
+  PRE3_TRY(h2d(ctx, dYa, Ya, pb));
+  PRE3_TRY(h2d(ctx, dYb, Yb, pb));
+  PRE3_TRY(h2d(ctx, ds, samples, sb));
+  PRE3_TRY(launch_fit_only(ctx, dYa, dYb, N, ds, k, H, method, dR, dT, dst));
+  PRE3_TRY(d2h(ctx, R, dR, 72 * (size_t)H));
+  PRE3_TRY(d2h(ctx, T, dT, 24 * (size_t)H));
+  PRE3_TRY(d2h(ctx, state, dst, 4 * (size_t)H));
+  PRE3_CUDA(cudaStreamSynchronize(ctx->stream));
+  return PRE3_OK;
+}
+
+// ================================================================================================
+// stage 3
+// ================================================================================================
+int pre3_score_batch(pre3_ctx* ctx, const double* R, const double* T, int H, const double* Ya, const double* Yb,
+                     int N, double thr, int32_t* count, double* errsum, uint8_t* mask) {
+  PRE3_LIVE();
+  PRE3_NEED(R && T && Ya && Yb, "null pointer");
+  PRE3_NEED(N >= 0 && H >= 0, "bad sizes");
+  if (H == 0) return PRE3_OK;
+  const size_t pb = 3 * (size_t)N * 8;
+  const size_t mb = mask ? (size_t)N * H : 0;
+  PRE3_TRY(ws_reserve(ctx, 2 * align_up(pb) + align_up(72 * (size_t)H) + align_up(24 * (size_t)H) +
+                               align_up(4 * (size_t)H) + align_up(8 * (size_t)H) + align_up(mb) +
+                               2 * align_up(16 * (size_t)N) + 8192));
+  double* dYa = ws_take<double>(ctx, 3 * (size_t)N);
+  double* dYb = ws_take<double>(ctx, 3 * (size_t)N);
+  double* dR = ws_take<double>(ctx, 9 * (size_t)H);
+  double* dT = ws_take<double>(ctx, 3 * (size_t)H);
+  int32_t* dc = ws_take<int32_t>(ctx, H);
+  double* de = ws_take<double>(ctx, H);
+  uint8_t* dm = mask ? ws_take<uint8_t>(ctx, mb) : nullptr;
+  PRE3_TRY(h2d(ctx, dYa, Ya, pb));
+  PRE3_TRY(h2d(ctx, dYb, Yb, pb));
+  PRE3_TRY(h2d(ctx, dR, R, 72 * (size_t)H));
+  PRE3_TRY(h2d(ctx, dT, T, 24 * (size_t)H));
+  PRE3_TRY(launch_score_given(ctx, dR, dT, H, dYa, dYb, N, thr, dc, errsum ? de : nullptr, dm));
+  if (count) PRE3_TRY(d2h(ctx, count, dc, 4 * (size_t)H));
+  if (errsum) PRE3_TRY(d2h(ctx, errsum, de, 8 * (size_t)H));
+  if (mask) PRE3_TRY(d2h(ctx, mask, dm, mb));
+  PRE3_CUDA(cudaStreamSynchronize(ctx->stream));
+  return PRE3_OK;
+}
+
+// ================================================================================================
+// stages 2-4
+// ================================================================================================
+int pre3_ransac_batch_dev(pre3_ctx* ctx, const double* dYa, const double* dYb, const int32_t* dn_corr, int P,
+                          int Nmax, const pre3_ransac_opts* opts, const int32_t* dsamples, pre3_pair_result* dres,
+                          uint8_t* dmasks) {
+  PRE3_LIVE();
+  PRE3_TRY(check_opts(ctx, opts));
+  PRE3_NEED(P >= 0 && Nmax >= 0, "bad sizes");
+  PRE3_NEED(dres != nullptr, "result pointer missing");
+  if (P == 0) return PRE3_OK;
+  PRE3_TRY(ws_reserve(ctx, ransac_ws_bytes(P, Nmax, opts->H)));
+  return ransac_impl(ctx, dYa, dYb, dn_corr, P, Nmax, *opts, dsamples, 0, dres, dmasks, nullptr, nullptr);
+}
+
+static int ransac_batch_host(pre3_ctx* ctx, const double* Ya, const double* Yb, const int32_t* n_corr, int P,
+                             int Nmax, const pre3_ransac_opts* opts, const int32_t* samples, pre3_pair_result* res,
+                             uint8_t* masks, int32_t* counts, int8_t* states) {
+  PRE3_LIVE();
+  PRE3_TRY(check_opts(ctx, opts));
+  PRE3_NEED(P >= 0 && Nmax >= 0, "bad sizes");
+  PRE3_NEED(res != nullptr, "result pointer missing");
+  PRE3_NEED((Ya && Yb) || (size_t)P * Nmax == 0, "null correspondences");
+  if (P == 0) return PRE3_OK;
+  const int H = opts->H;
+  const size_t pb = 3 * (size_t)P * Nmax * 8;
+  const size_t sb = samples ? 4 * (size_t)P * opts->k * H : 0;
+  const size_t rb = sizeof(pre3_pair_result) * (size_t)P;
+  const size_t mb = masks ? (size_t)P * Nmax : 0;
+  const size_t cb = counts ? 4 * (size_t)P * H : 0, stb = states ? (size_t)P * H : 0;
+  PRE3_TRY(ws_reserve(ctx, ransac_ws_bytes(P, Nmax, H) + 2 * align_up(pb) + align_up(sb) + align_up(rb) +
+                               align_up(mb) + align_up(cb) + align_up(stb) + align_up(4 * (size_t)P) + 8192));
+  double* dYa = ws_take<double>(ctx, 3 * (size_t)P * Nmax);
+  double* dYb = ws_take<double>(ctx, 3 * (size_t)P * Nmax);
+  int32_t* ds = samples ? ws_take<int32_t>(ctx, (size_t)P * opts->k * H) : nullptr;
+  int32_t* dn = n_corr ? ws_take<int32_t>(ctx, P) : nullptr;
+  pre3_pair_result* dres = ws_take<pre3_pair_result>(ctx, P);
+  uint8_t* dm = masks ? ws_take<uint8_t>(ctx, mb) : nullptr;
+  int32_t* dc = counts ? ws_take<int32_t>(ctx, (size_t)P * H) : nullptr;
+  int8_t* dst = states ? ws_take<int8_t>(ctx, (size_t)P * H) : nullptr;
+  PRE3_TRY(h2d(ctx, dYa, Ya, pb));
+  PRE3_TRY(h2d(ctx, dYb, Yb, pb));
+  if (ds) PRE3_TRY(h2d(ctx, ds, samples, sb));
+  if (dn) PRE3_TRY(h2d(ctx, dn, n_corr, 4 * (size_t)P));
+  PRE3_TRY(ransac_impl(ctx, dYa, dYb, dn, P, Nmax, *opts, ds, 0, dres, dm, dc, dst));
+  PRE3_TRY(d2h(ctx, res, dres, rb));
+  if (masks) PRE3_TRY(d2h(ctx, masks, dm, mb));
+  if (counts) PRE3_TRY(d2h(ctx, counts, dc, cb));
+  if (states) PRE3_TRY(d2h(ctx, states, dst, stb));
+  PRE3_CUDA(cudaStreamSynchronize(ctx->stream));
+  return PRE3_OK;
+}
+
+int pre3_ransac_batch(pre3_ctx* ctx, const double* Ya, const double* Yb, const int32_t* n_corr, int P, int Nmax,
+                      const pre3_ransac_opts* opts, const int32_t* samples, pre3_pair_result* res, uint8_t* masks) {
+  return ransac_batch_host(ctx, Ya, Yb, n_corr, P, Nmax, opts, samples, res, masks, nullptr, nullptr);
+}
+
+int pre3_ransac(pre3_ctx* ctx, const double* Ya, const double* Yb, int N, const pre3_ransac_opts* opts,
+                const int32_t* samples, pre3_pair_result* res, uint8_t* mask, int32_t* counts, int8_t* states) {
+  return ransac_batch_host(ctx, Ya, Yb, nullptr, 1, N, opts, samples, res, mask, counts, states);
+}
+
+// ================================================================================================
+// whole frame pairs
+// ================================================================================================
+static size_t pairs_ws_bytes(int cls, int P, int K1, int K2, int ND, int H) {
+  return match_ws_bytes(cls, P, K1, K2, ND) + ransac_ws_bytes(P, K1, H) + 2 * align_up(24 * (size_t)P * K1) +
+         align_up(4 * (size_t)P) + align_up(8 * (size_t)P * K1) + 8192;
+}
+
+static int pairs_impl(pre3_ctx* ctx, const void* ddesc1, const void* ddesc2, int cls, const double* dxyz1,
+                      const double* dxyz2, int P, int K1, int K2, int ND, const int32_t* dk1, const int32_t* dk2,
+                      const pre3_ransac_opts& o, uint32_t pair_id0, pre3_pair_result* dres, int32_t* dmatches,
+                      uint8_t* dmasks) {
+  MatchRow* rows = nullptr;
+  if (K1 > 0) PRE3_TRY(match_impl(ctx, ddesc1, ddesc2, cls, P, K1, K2, ND, dk1, dk2, o.ratio, &rows));
+  double* dYa = ws_take<double>(ctx, 3 * (size_t)P * K1);
+  double* dYb = ws_take<double>(ctx, 3 * (size_t)P * K1);
+  int32_t* dn = ws_take<int32_t>(ctx, P);
+  int32_t* dpairs = dmatches ? dmatches : ws_take<int32_t>(ctx, 2 * (size_t)P * K1);
+  PRE3_TRY(launch_match_compact(ctx, rows, P, K1, dk1, dpairs, nullptr, dn, dxyz1, dxyz2, K2, dYa, dYb));
+  return ransac_impl(ctx, dYa, dYb, dn, P, K1, o, nullptr, pair_id0, dres, dmasks, nullptr, nullptr);
+}
+
+int pre3_pairs_dev(pre3_ctx* ctx, const void* ddesc1, const void* ddesc2, int cls, const double* dxyz1,
+                   const double* dxyz2, int P, int K1, int K2, int ND, const int32_t* dk1_count,
+                   const int32_t* dk2_count, const pre3_ransac_opts* opts, uint32_t pair_id0, pre3_pair_result* dres,
+                   int32_t* dmatches, uint8_t* dmasks) {
+  PRE3_LIVE();
+  PRE3_TRY(check_match_args(ctx, ddesc1, ddesc2, cls, P, K1, K2, ND));
+  PRE3_TRY(check_opts(ctx, opts));
+  PRE3_NEED(dres && dxyz1 && dxyz2, "null pointer");
+  if (P == 0) return PRE3_OK;
+  PRE3_TRY(ws_reserve(ctx, pairs_ws_bytes(cls, P, K1, K2, ND, opts->H)));
+  return pairs_impl(ctx, ddesc1, ddesc2, cls, dxyz1, dxyz2, P, K1, K2, ND, dk1_count, dk2_count, *opts, pair_id0, dres,
+                    dmatches, dmasks);
+}
+
+// Host buffers: the P pairs are cut into chunks that are staged on a second stream while the
+// previous chunk computes (double-buffered device staging), so that for whole-sequence runs the
+// PCIe copy of the descriptors -- 1 MB per 512x512 pair in class double -- overlaps the kernels.
+int pre3_pairs(pre3_ctx* ctx, const void* desc1, const void* desc2, int cls, const double* xyz1, const double* xyz2,
+               int P, int K1, int K2, int ND, const int32_t* k1_count, const int32_t* k2_count,
+               const pre3_ransac_opts* opts, uint32_t pair_id0, pre3_pair_result* res, int32_t* matches,
+               uint8_t* masks) {
+  PRE3_LIVE();
+  PRE3_TRY(check_match_args(ctx, desc1, desc2, cls, P, K1, K2, ND));
+  PRE3_TRY(check_opts(ctx, opts));
+  PRE3_NEED(res && xyz1 && xyz2, "null pointer");
+  if (P == 0) return PRE3_OK;
+  const size_t es = class_size(cls);
+  const size_t pb1 = (size_t)K1 * ND * es, pb2 = (size_t)K2 * ND * es;  // per pair
+  const size_t per_pair_in = pb1 + pb2 + 24 * ((size_t)K1 + K2) + 8;
+  // chunk size: ~64 MB of input per chunk, at least 1 pair, at most P
+  int C = (int)std::max<size_t>(1, std::min<size_t>((size_t)P, ((size_t)64 << 20) / std::max<size_t>(per_pair_in, 1)));
+  const int nchunks = (P + C - 1) / C;
+  // staging (two slots) lives outside the per-call arena: the arena is reset by every chunk
+  struct Slot {
+    char *d1, *d2;
+    double *x1, *x2;
+    int32_t *k1, *k2;
+    pre3_pair_result* r;
+    int32_t* m;
+    uint8_t* msk;
+  } slot[2];
+  const size_t slot_bytes = align_up(pb1 * C) + align_up(pb2 * C) + align_up(24 * (size_t)K1 * C) +
+                            align_up(24 * (size_t)K2 * C) + 2 * align_up(4 * (size_t)C) +
+                            align_up(sizeof(pre3_pair_result) * (size_t)C) + align_up(8 * (size_t)K1 * C) +
+                            align_up((size_t)K1 * C) + 4096;
+  PRE3_TRY(aux_reserve(ctx, 0, 2 * slot_bytes));
+  for (int s = 0; s < 2; ++s) {
+    char* base = ctx->aux[0] + s * slot_bytes;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+      char* p = base + off;
+      off += align_up(bytes);
+      return p;
+    };
+    slot[s].d1 = take(pb1 * C);
+    slot[s].d2 = take(pb2 * C);
+    slot[s].x1 = (double*)take(24 * (size_t)K1 * C);
+    slot[s].x2 = (double*)take(24 * (size_t)K2 * C);
+    slot[s].k1 = (int32_t*)take(4 * (size_t)C);
+    slot[s].k2 = (int32_t*)take(4 * (size_t)C);
+    slot[s].r = (pre3_pair_result*)take(sizeof(pre3_pair_result) * (size_t)C);
+    slot[s].m = (int32_t*)take(8 * (size_t)K1 * C);
+    slot[s].msk = (uint8_t*)take((size_t)K1 * C);
+  }
+  PRE3_TRY(ensure_copy_stream(ctx));
+  PRE3_TRY(ws_reserve(ctx, pairs_ws_bytes(cls, C, K1, K2, ND, opts->H)));
+  cudaStream_t cs = ctx->copy_stream;
+  auto stage_in = [&](int c) -> int {
+    const int s = c & 1;
+    const int p0 = c * C, n = std::min(C, P - p0);
+    // the slot may still be read by the compute of chunk c-2 / written back by its D2H
+    PRE3_CUDA(cudaStreamWaitEvent(cs, ctx->ev_slot_free[s], 0));
+    PRE3_CUDA(cudaMemcpyAsync(slot[s].d1, (const char*)desc1 + (size_t)p0 * pb1, pb1 * n, cudaMemcpyHostToDevice, cs));
+    PRE3_CUDA(cudaMemcpyAsync(slot[s].d2, (const char*)desc2 + (size_t)p0 * pb2, pb2 * n, cudaMemcpyHostToDevice, cs));
+    PRE3_CUDA(cudaMemcpyAsync(slot[s].x1, xyz1 + 3 * (size_t)p0 * K1, 24 * (size_t)K1 * n, cudaMemcpyHostToDevice, cs));
+    PRE3_CUDA(cudaMemcpyAsync(slot[s].x2, xyz2 + 3 * (size_t)p0 * K2, 24 * (size_t)K2 * n, cudaMemcpyHostToDevice, cs));
+    if (k1_count) PRE3_CUDA(cudaMemcpyAsync(slot[s].k1, k1_count + p0, 4 * (size_t)n, cudaMemcpyHostToDevice, cs));
+    if (k2_count) PRE3_CUDA(cudaMemcpyAsync(slot[s].k2, k2_count + p0, 4 * (size_t)n, cudaMemcpyHostToDevice, cs));
+    PRE3_CUDA(cudaEventRecord(ctx->ev_slot_full[s], cs));
+    return PRE3_OK;
+  };
+  // both slots start free
+  PRE3_CUDA(cudaEventRecord(ctx->ev_slot_free[0], ctx->stream));
+  PRE3_CUDA(cudaEventRecord(ctx->ev_slot_free[1], ctx->stream));
+  PRE3_TRY(stage_in(0));
+  for (int c = 0; c < nchunks; ++c) {
+    const int s = c & 1;
+    const int p0 = c * C, n = std::min(C, P - p0);
+    if (c + 1 < nchunks) PRE3_TRY(stage_in(c + 1));
+    PRE3_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_slot_full[s], 0));
+    ctx->ws_off = 0;  // arena reused by every chunk (stream order keeps it safe)
+    PRE3_TRY(pairs_impl(ctx, slot[s].d1, slot[s].d2, cls, slot[s].x1, slot[s].x2, n, K1, K2, ND,
+                        k1_count ? slot[s].k1 : nullptr, k2_count ? slot[s].k2 : nullptr, *opts,
+                        pair_id0 + (uint32_t)p0, slot[s].r, matches ? slot[s].m : nullptr,
+                        masks ? slot[s].msk : nullptr));
+    PRE3_TRY(d2h(ctx, res + p0, slot[s].r, sizeof(pre3_pair_result) * (size_t)n));
+    if (matches) PRE3_TRY(d2h(ctx, matches + 2 * (size_t)p0 * K1, slot[s].m, 8 * (size_t)K1 * n));
+    if (masks) PRE3_TRY(d2h(ctx, masks + (size_t)p0 * K1, slot[s].msk, (size_t)K1 * n));
+    PRE3_CUDA(cudaEventRecord(ctx->ev_slot_free[s], ctx->stream));
+  }
+  PRE3_CUDA(cudaStreamSynchronize(ctx->stream));
+  PRE3_CUDA(cudaStreamSynchronize(cs));
+  return PRE3_OK;
+}
+
+// ================================================================================================
+// hypothesis-block sharding
+// ================================================================================================
+int pre3_distance_threshold_dev(pre3_ctx* ctx, const double* dYb, int N, double* dthr) {
+  PRE3_LIVE();
+  PRE3_NEED(dYb && dthr, "null pointer");
+  return launch_threshold(ctx, dYb, N, dthr);
+}
+
+int pre3_ransac_block_dev(pre3_ctx* ctx, const double* dYa, const double* dYb, int N, const pre3_ransac_opts* opts,
+                          const int32_t* dsamples, int64_t h0, int Hloc, double thr, uint64_t* dkey,
+                          double* derrsum) {
+  PRE3_LIVE();
+  PRE3_TRY(check_opts(ctx, opts));
+  PRE3_NEED(dYa && dYb && dkey, "null pointer");
+  PRE3_NEED(N >= 1 && Hloc >= 0 && h0 >= 0, "bad sizes");
+  pre3_ransac_opts o = *opts;
+  o.H = Hloc;
+  o.adaptive = 0;  // fixed-H by construction
+  o.distance_threshold = thr;
+  PRE3_TRY(ws_reserve(ctx, ransac_ws_bytes(1, N, Hloc)));
+  RansacBuffers b{};
+  b.Ya = dYa;
+  b.Yb = dYb;
+  b.n_corr = nullptr;
+  b.P = 1;
+  b.Nmax = N;
+  b.samples = dsamples;
+  b.pair_id0 = 0;
+  ransac_carve(ctx, b, Hloc);
+  PRE3_TRY(launch_prep(ctx, b, o, 1));
+  PRE3_TRY(launch_eval(ctx, b, o, h0));
+  PRE3_TRY(launch_block_best(ctx, b, o, h0, Hloc, dkey, derrsum));
+  return PRE3_OK;
+}
+
+int pre3_ransac_finish_dev(pre3_ctx* ctx, const double* dYa, const double* dYb, int N, const pre3_ransac_opts* opts,
+                           const int32_t* dsamples_of_winner, int64_t winner_id, double thr, pre3_pair_result* dres,
+                           uint8_t* dmask) {
+  PRE3_LIVE();
+  PRE3_TRY(check_opts(ctx, opts));
+  PRE3_NEED(dYa && dYb && dres, "null pointer");
+  PRE3_NEED(N >= 1 && winner_id >= 0, "bad sizes");
+  pre3_ransac_opts o = *opts;
+  o.distance_threshold = thr;
+  PRE3_TRY(ws_reserve(ctx, ransac_ws_bytes(1, N, 1)));
+  RansacBuffers b{};
+  b.Ya = dYa;
+  b.Yb = dYb;
+  b.n_corr = nullptr;
+  b.P = 1;
+  b.Nmax = N;
+  b.samples = dsamples_of_winner;
+  b.pair_id0 = 0;
+  ransac_carve(ctx, b, 1);
+  uint8_t* scratch = ws_take<uint8_t>(ctx, (size_t)N);
+  PRE3_TRY(launch_prep(ctx, b, o, 1));
+  PRE3_TRY(launch_finish(ctx, b, o, winner_id, dres, dmask ? dmask : scratch));
+  return PRE3_OK;
+}
+
+// R2q of slamToolbox (M/slamToolbox_11_02_18/FrameTransforms/Rotations/R2q.m:11-55): host helper.
+void pre3_R2q(const double* Rc, double* q) {
+  // column-major: R(i,j) = Rc[3*(j-1) + (i-1)]
+  auto R = [&](int i, int j) { return Rc[3 * (j - 1) + (i - 1)]; };
+  const double T = ((R(1, 1) + R(2, 2)) + R(3, 3)) + 1.0;
+  double a, b, c, d;
+  if (T > 0.00000001) {
+    const double S = 2.0 * std::sqrt(T);
+    a = 0.25 * S;
+    b = (R(2, 3) - R(3, 2)) / S;
+    c = (R(3, 1) - R(1, 3)) / S;
+    d = (R(1, 2) - R(2, 1)) / S;
+  } else if (R(1, 1) > R(2, 2) && R(1, 1) > R(3, 3)) {
+    const double S = 2.0 * std::sqrt(1.0 + R(1, 1) - R(2, 2) - R(3, 3));
+    a = (R(2, 3) - R(3, 2)) / S;
+    b = 0.25 * S;
+    c = (R(1, 2) + R(2, 1)) / S;
+    d = (R(3, 1) + R(1, 3)) / S;
+  } else if (R(2, 2) > R(3, 3)) {
+    const double S = 2.0 * std::sqrt(1.0 + R(2, 2) - R(1, 1) - R(3, 3));
+    a = (R(3, 1) - R(1, 3)) / S;
+    b = (R(1, 2) + R(2, 1)) / S;
+    c = 0.25 * S;
+    d = (R(2, 3) + R(3, 2)) / S;
+  } else {
+    const double S = 2.0 * std::sqrt(1.0 + R(3, 3) - R(1, 1) - R(2, 2));
+    a = (R(1, 2) - R(2, 1)) / S;
+    b = (R(3, 1) + R(1, 3)) / S;
+    c = (R(2, 3) + R(3, 2)) / S;
+    d = 0.25 * S;
+  }
+  q[0] = a;
+  q[1] = -b;
+  q[2] = -c;
+  q[3] = -d;
+}
+
+}  // extern "C"

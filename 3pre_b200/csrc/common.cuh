@@ -1,0 +1,166 @@
+// common.cuh -- context, workspace arena and launch helpers shared by the libpre3 TUs.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/pre3.h"
+
+namespace pre3 {
+// per-kernel timing categories (pre3_timing_*): bench.py's roofline numbers come from here
+enum TimeCat { T_CONVERT = 0, T_MATCH_TC, T_MATCH_EXACT, T_RESCORE, T_COMPACT, T_PREP, T_EVAL, T_SELECT, T_OTHER, T_NCAT };
+struct TimedSpan {
+  int cat;
+  cudaEvent_t a, b;
+};
+}  // namespace pre3
+
+struct pre3_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int match_engine = PRE3_MATCH_AUTO;
+  int sm_count = 148;
+  int64_t launches = 0;
+  std::string err;
+  // growable device workspace (bump allocator, reset per API call)
+  char* ws = nullptr;
+  size_t ws_cap = 0;
+  size_t ws_off = 0;
+  std::vector<char*> retired;  // blocks replaced while a call was being assembled
+  // cached adaptive-iteration tables, keyed by (k, mult, Nmax, max_iteration)
+  int tab_k = -1, tab_mult = -1, tab_nmax = -1, tab_maxit = -1;
+  int32_t* d_tab = nullptr;       // triangular: row N starts at N*(N+1)/2, entries c = 0..N
+  // pinned staging for small results
+  void* h_pin = nullptr;
+  size_t h_pin_cap = 0;
+  // long-lived device buffers outside the per-call arena (chunk staging of pre3_pairs,
+  // pre-tiled fp16 operand images of the tensor-core matcher)
+  std::vector<char*> aux;
+  std::vector<size_t> aux_cap;
+  // second stream + events for copy/compute overlap in the host-pointer batch entry points
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_slot_full[2] = {nullptr, nullptr};
+  cudaEvent_t ev_slot_free[2] = {nullptr, nullptr};
+  // optional per-launch CUDA-event timing (off by default)
+  bool timing = false;
+  std::vector<pre3::TimedSpan> spans;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+};
+
+namespace pre3 {
+
+inline int fail(pre3_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->err = msg;
+  return code;
+}
+
+#define PRE3_CUDA(call)                                                                       \
+  do {                                                                                        \
+    cudaError_t e__ = (call);                                                                 \
+    if (e__ != cudaSuccess)                                                                   \
+      return pre3::fail(ctx, PRE3_ERR_CUDA,                                                   \
+                        std::string(#call) + ": " + cudaGetErrorString(e__) + " (" + __FILE__ + \
+                            ":" + std::to_string(__LINE__) + ")");                           \
+  } while (0)
+
+#define PRE3_TRY(call)         \
+  do {                         \
+    int rc__ = (call);         \
+    if (rc__ != PRE3_OK) return rc__; \
+  } while (0)
+
+// Bump allocation out of the context arena.  All sub-allocations of one API call must be
+// requested through ws_reserve() first (so that the block never moves mid-call).
+inline int ws_reserve(pre3_ctx* ctx, size_t bytes) {
+  ctx->ws_off = 0;
+  if (bytes <= ctx->ws_cap) return PRE3_OK;
+  size_t cap = ctx->ws_cap ? ctx->ws_cap : (size_t)1 << 20;
+  while (cap < bytes) cap *= 2;
+  if (ctx->ws) {
+    // earlier work on the stream may still use the old block: free after a sync
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->ws);
+    ctx->ws = nullptr;
+    ctx->ws_cap = 0;
+  }
+  cudaError_t e = cudaMalloc((void**)&ctx->ws, cap);
+  if (e != cudaSuccess) return fail(ctx, PRE3_ERR_ALLOC, std::string("cudaMalloc workspace: ") + cudaGetErrorString(e));
+  ctx->ws_cap = cap;
+  return PRE3_OK;
+}
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// Long-lived device buffer number `slot` of at least `bytes` (grown on demand, never shrunk).
+inline int aux_reserve(pre3_ctx* ctx, size_t slot, size_t bytes) {
+  if (ctx->aux.size() <= slot) {
+    ctx->aux.resize(slot + 1, nullptr);
+    ctx->aux_cap.resize(slot + 1, 0);
+  }
+  if (ctx->aux_cap[slot] >= bytes) return PRE3_OK;
+  if (ctx->aux[slot]) {
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    cudaFree(ctx->aux[slot]);
+    ctx->aux[slot] = nullptr;
+    ctx->aux_cap[slot] = 0;
+  }
+  cudaError_t e = cudaMalloc((void**)&ctx->aux[slot], bytes);
+  if (e != cudaSuccess) return fail(ctx, PRE3_ERR_ALLOC, std::string("cudaMalloc aux buffer: ") + cudaGetErrorString(e));
+  ctx->aux_cap[slot] = bytes;
+  return PRE3_OK;
+}
+
+inline int ensure_copy_stream(pre3_ctx* ctx) {
+  if (ctx->copy_stream) return PRE3_OK;
+  PRE3_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    PRE3_CUDA(cudaEventCreateWithFlags(&ctx->ev_slot_full[i], cudaEventDisableTiming));
+    PRE3_CUDA(cudaEventCreateWithFlags(&ctx->ev_slot_free[i], cudaEventDisableTiming));
+  }
+  return PRE3_OK;
+}
+
+template <typename T>
+inline T* ws_take(pre3_ctx* ctx, size_t count) {
+  size_t off = align_up(ctx->ws_off);
+  ctx->ws_off = off + count * sizeof(T);
+  return reinterpret_cast<T*>(ctx->ws + off);
+}
+
+inline void count_launch(pre3_ctx* ctx, int n = 1) { ctx->launches += n; }
+
+inline cudaEvent_t timing_event(pre3_ctx* ctx) {
+  if (ctx->ev_used == ctx->ev_pool.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    ctx->ev_pool.push_back(e);
+  }
+  return ctx->ev_pool[ctx->ev_used++];
+}
+
+// RAII: brackets the kernel launch(es) issued in its scope with two events on the context's
+// stream when timing is enabled; free otherwise.
+struct Span {
+  pre3_ctx* ctx;
+  TimedSpan s;
+  Span(pre3_ctx* c, int cat) : ctx(c) {
+    if (!ctx->timing) return;
+    s.cat = cat;
+    s.a = timing_event(ctx);
+    s.b = timing_event(ctx);
+    cudaEventRecord(s.a, ctx->stream);
+  }
+  ~Span() {
+    if (!ctx->timing) return;
+    cudaEventRecord(s.b, ctx->stream);
+    ctx->spans.push_back(s);
+  }
+};
+
+}  // namespace pre3

@@ -1,0 +1,311 @@
+// match_exact.cu -- stage 1 in the reference's own arithmetic, brute force.
+//
+// compare_mx*_CLASS of M/sift/siftmatch.c:83-132: for every column of L1 the squared L2
+// distance to every column of L2, accumulated bin by bin in the promoted type (:101-107,
+// double / float / int), best + second best with strict '<' (:110-116, first index wins),
+// Lowe's test with float casts (:122-123).  This kernel is (a) the engine for int8 / uint8
+// and for ND != 128, (b) the exact recomputation for rows the tensor-core proposal path
+// cannot certify.  Compile with -fmad=false: delta*delta and the add must not fuse, the
+// reference (gcc, x86-64, no -mfma) rounds twice.
+#include "match.cuh"
+
+namespace pre3 {
+
+constexpr int MT = 32;   // block tile: 32 L1 columns x 32 L2 columns
+constexpr int MB = 32;   // bins per shared-memory chunk
+
+template <typename ACC>
+struct Top2 {
+  ACC best, second;
+  int bestk;
+};
+
+template <typename ACC>
+__device__ __forceinline__ ACC maxval();
+template <>
+__device__ __forceinline__ double maxval<double>() { return INFINITY; }
+template <>
+__device__ __forceinline__ float maxval<float>() { return INFINITY; }
+template <>
+__device__ __forceinline__ int maxval<int>() { return 0x7fffffff; }
+
+template <typename ACC>
+__device__ __forceinline__ void top2_update(Top2<ACC>& s, ACC acc, int k2) {  // siftmatch.c:110-116
+  if (acc < s.best) {
+    s.second = s.best;
+    s.best = acc;
+    s.bestk = k2;
+  } else if (acc < s.second) {
+    s.second = acc;
+  }
+}
+
+// Order-independent merge of two partial states over disjoint column sets: the sequential
+// rule yields (min, first index of the min, second smallest with multiplicity).
+template <typename ACC>
+__device__ __forceinline__ void top2_merge(Top2<ACC>& a, const Top2<ACC>& b) {
+  const bool a_first = (a.best < b.best) || (a.best == b.best && (unsigned)a.bestk < (unsigned)b.bestk);
+  if (a_first) {
+    a.second = b.best < a.second ? b.best : a.second;
+  } else {
+    const ACC s = a.best < b.second ? a.best : b.second;
+    a.best = b.best;
+    a.bestk = b.bestk;
+    a.second = s;
+  }
+}
+
+template <typename T, typename ACC>
+__global__ void __launch_bounds__(256)
+k_match_exact(const T* __restrict__ L1, const T* __restrict__ L2, int K1, int K2, int ND,
+              const int32_t* __restrict__ k1c, const int32_t* __restrict__ k2c, float thresh,
+              const int32_t* __restrict__ row_list, const int32_t* __restrict__ row_list_n,
+              MatchRow* __restrict__ rows) {
+  __shared__ T sa[MT][MB + 1];
+  __shared__ T sb[MT][MB + 1];
+  const int p = blockIdx.y;
+  const int n1 = k1c ? min(k1c[p], K1) : K1;
+  const int n2 = k2c ? min(k2c[p], K2) : K2;
+  const int row0 = blockIdx.x * MT;
+  if (row0 >= n1) return;
+  const T* A = L1 + (size_t)p * K1 * ND;
+  const T* B = L2 + (size_t)p * K2 * ND;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  Top2<ACC> st[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    st[i].best = maxval<ACC>();
+    st[i].second = maxval<ACC>();
+    st[i].bestk = -1;
+  }
+  for (int col0 = 0; col0 < n2; col0 += MT) {
+    ACC acc[2][2] = {{0, 0}, {0, 0}};
+    for (int b0 = 0; b0 < ND; b0 += MB) {
+      __syncthreads();
+      for (int e = threadIdx.x; e < MT * MB; e += 256) {
+        const int r = e / MB, c = e % MB;
+        const int bin = b0 + c;
+        T va = 0, vb = 0;
+        if (bin < ND) {
+          if (row0 + r < n1) va = A[(size_t)(row0 + r) * ND + bin];
+          if (col0 + r < n2) vb = B[(size_t)(col0 + r) * ND + bin];
+        }
+        sa[r][c] = va;
+        sb[r][c] = vb;
+      }
+      __syncthreads();
+      const int nb = min(MB, ND - b0);
+      for (int c = 0; c < nb; ++c) {
+        const ACC a0 = (ACC)sa[2 * ty][c], a1 = (ACC)sa[2 * ty + 1][c];
+        const ACC c0 = (ACC)sb[2 * tx][c], c1 = (ACC)sb[2 * tx + 1][c];
+        ACC d;
+        d = a0 - c0;
+        acc[0][0] += d * d;
+        d = a0 - c1;
+        acc[0][1] += d * d;
+        d = a1 - c0;
+        acc[1][0] += d * d;
+        d = a1 - c1;
+        acc[1][1] += d * d;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int k2 = col0 + 2 * tx + j;
+        if (k2 < n2) top2_update(st[i], acc[i][j], k2);
+      }
+  }
+  // merge across the 16 threads (tx) that share a row pair: xor shuffles stay in the half-warp
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+#pragma unroll
+    for (int off = 8; off > 0; off >>= 1) {
+      Top2<ACC> o;
+      o.best = __shfl_xor_sync(0xffffffffu, st[i].best, off);
+      o.second = __shfl_xor_sync(0xffffffffu, st[i].second, off);
+      o.bestk = __shfl_xor_sync(0xffffffffu, st[i].bestk, off);
+      top2_merge(st[i], o);
+    }
+    const int k1 = row0 + 2 * ty + i;
+    if (tx == 0 && k1 < n1) {
+      MatchRow r;
+      r.best = (double)st[i].best;
+      r.bestk = st[i].bestk;
+      // thresh * (float) best <= (float) second_best && bestk != -1   (siftmatch.c:122-123)
+      r.accept = (__fmul_rn(thresh, (float)st[i].best) <= (float)st[i].second && st[i].bestk != -1) ? 1 : 0;
+      rows[(size_t)p * K1 + k1] = r;
+    }
+  }
+  (void)row_list;
+  (void)row_list_n;
+}
+
+// One warp per listed row: exact recomputation of rows the proposal path flagged.
+// row_list holds p*K1 + k1 entries, *row_list_n of them.
+template <typename T, typename ACC>
+__global__ void __launch_bounds__(256)
+k_match_rows_exact(const T* __restrict__ L1, const T* __restrict__ L2, int K1, int K2, int ND,
+                   const int32_t* __restrict__ k2c, float thresh, const int32_t* __restrict__ row_list,
+                   const int32_t* __restrict__ row_list_n, int list_cap, MatchRow* __restrict__ rows) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int n = min(*row_list_n, list_cap);
+  for (int w = blockIdx.x * wpb + (threadIdx.x >> 5); w < n; w += gridDim.x * wpb) {
+    const int rid = row_list[w];
+    const int p = rid / K1;
+    const int n2 = k2c ? min(k2c[p], K2) : K2;
+    const T* a = L1 + (size_t)rid * ND;
+    const T* B = L2 + (size_t)p * K2 * ND;
+    Top2<ACC> st;
+    st.best = maxval<ACC>();
+    st.second = maxval<ACC>();
+    st.bestk = -1;
+    for (int k2 = lane; k2 < n2; k2 += 32) {
+      const T* b = B + (size_t)k2 * ND;
+      ACC acc = 0;
+      for (int bin = 0; bin < ND; ++bin) {
+        const ACC d = (ACC)a[bin] - (ACC)b[bin];
+        acc += d * d;
+      }
+      top2_update(st, acc, k2);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      Top2<ACC> o;
+      o.best = __shfl_xor_sync(0xffffffffu, st.best, off);
+      o.second = __shfl_xor_sync(0xffffffffu, st.second, off);
+      o.bestk = __shfl_xor_sync(0xffffffffu, st.bestk, off);
+      top2_merge(st, o);
+    }
+    if (lane == 0) {
+      MatchRow r;
+      r.best = (double)st.best;
+      r.bestk = st.bestk;
+      r.accept = (__fmul_rn(thresh, (float)st.best) <= (float)st.second && st.bestk != -1) ? 1 : 0;
+      rows[rid] = r;
+    }
+  }
+}
+
+// rows -> compact list in k1 order + gathered correspondences.  One block per pair.
+__global__ void __launch_bounds__(256)
+k_match_compact(const MatchRow* __restrict__ rows, int K1, const int32_t* __restrict__ k1c,
+                int32_t* __restrict__ pairs, double* __restrict__ score, int32_t* __restrict__ n_out,
+                const double* __restrict__ xyz1, const double* __restrict__ xyz2, int K2,
+                double* __restrict__ Ya, double* __restrict__ Yb) {
+  __shared__ int s_warp[8];
+  __shared__ int s_base;
+  const int p = blockIdx.x;
+  const int n1 = k1c ? min(k1c[p], K1) : K1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  for (int r0 = 0; r0 < n1; r0 += 256) {
+    const int k1 = r0 + threadIdx.x;
+    MatchRow r;
+    r.accept = 0;
+    if (k1 < n1) r = rows[(size_t)p * K1 + k1];
+    const unsigned bal = __ballot_sync(0xffffffffu, r.accept != 0);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    int off = s_base;
+    for (int w = 0; w < warp; ++w) off += s_warp[w];
+    off += __popc(bal & ((1u << lane) - 1u));
+    if (r.accept) {
+      if (pairs) {
+        pairs[((size_t)p * K1 + off) * 2] = k1;
+        pairs[((size_t)p * K1 + off) * 2 + 1] = r.bestk;
+      }
+      if (score) score[(size_t)p * K1 + off] = r.best;
+      if (Ya) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          Ya[((size_t)p * K1 + off) * 3 + c] = xyz1[((size_t)p * K1 + k1) * 3 + c];
+          Yb[((size_t)p * K1 + off) * 3 + c] = xyz2[((size_t)p * K2 + r.bestk) * 3 + c];
+        }
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int t = s_base;
+      for (int w = 0; w < 8; ++w) t += s_warp[w];
+      s_base = t;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) n_out[p] = s_base;
+}
+
+size_t match_workspace_bytes(int cls, int P, int K1, int K2, int ND) {
+  (void)cls;
+  (void)K2;
+  (void)ND;
+  return align_up(sizeof(MatchRow) * (size_t)P * K1) + 4096;
+}
+
+int launch_match_exact(pre3_ctx* ctx, const void* dL1, const void* dL2, int cls, int P, int K1, int K2, int ND,
+                       const int32_t* dk1, const int32_t* dk2, float thresh, MatchRow* drows) {
+  Span span__(ctx, T_MATCH_EXACT);
+  if (P <= 0 || K1 <= 0) return PRE3_OK;
+  dim3 grid((K1 + MT - 1) / MT, P);
+  switch (cls) {
+    case PRE3_CLASS_DOUBLE:
+      k_match_exact<double, double><<<grid, 256, 0, ctx->stream>>>((const double*)dL1, (const double*)dL2, K1, K2, ND,
+                                                                    dk1, dk2, thresh, nullptr, nullptr, drows);
+      break;
+    case PRE3_CLASS_SINGLE:
+      k_match_exact<float, float><<<grid, 256, 0, ctx->stream>>>((const float*)dL1, (const float*)dL2, K1, K2, ND, dk1,
+                                                                  dk2, thresh, nullptr, nullptr, drows);
+      break;
+    case PRE3_CLASS_INT8:
+      k_match_exact<signed char, int><<<grid, 256, 0, ctx->stream>>>((const signed char*)dL1, (const signed char*)dL2,
+                                                                      K1, K2, ND, dk1, dk2, thresh, nullptr, nullptr,
+                                                                      drows);
+      break;
+    case PRE3_CLASS_UINT8:
+      k_match_exact<unsigned char, int><<<grid, 256, 0, ctx->stream>>>((const unsigned char*)dL1,
+                                                                        (const unsigned char*)dL2, K1, K2, ND, dk1,
+                                                                        dk2, thresh, nullptr, nullptr, drows);
+      break;
+    default:
+      return fail(ctx, PRE3_ERR_CLASS, "Unsupported numeric class");
+  }
+  count_launch(ctx);
+  PRE3_CUDA(cudaGetLastError());
+  return PRE3_OK;
+}
+
+int launch_match_rows_exact(pre3_ctx* ctx, const void* dL1, const void* dL2, int cls, int K1, int K2, int ND,
+                            const int32_t* dk2, float thresh, const int32_t* drow_list, const int32_t* drow_list_n,
+                            int list_cap, MatchRow* drows) {
+  Span span__(ctx, T_RESCORE);
+  const int blocks = 4 * ctx->sm_count;
+  if (cls == PRE3_CLASS_DOUBLE)
+    k_match_rows_exact<double, double><<<blocks, 256, 0, ctx->stream>>>((const double*)dL1, (const double*)dL2, K1, K2,
+                                                                         ND, dk2, thresh, drow_list, drow_list_n,
+                                                                         list_cap, drows);
+  else if (cls == PRE3_CLASS_SINGLE)
+    k_match_rows_exact<float, float><<<blocks, 256, 0, ctx->stream>>>((const float*)dL1, (const float*)dL2, K1, K2, ND,
+                                                                       dk2, thresh, drow_list, drow_list_n, list_cap,
+                                                                       drows);
+  else
+    return fail(ctx, PRE3_ERR_CLASS, "row recheck: class must be double or single");
+  count_launch(ctx);
+  PRE3_CUDA(cudaGetLastError());
+  return PRE3_OK;
+}
+
+int launch_match_compact(pre3_ctx* ctx, const MatchRow* drows, int P, int K1, const int32_t* dk1,
+                         int32_t* dpairs, double* dscore, int32_t* dn_out, const double* dxyz1,
+                         const double* dxyz2, int K2, double* dYa, double* dYb) {
+  Span span__(ctx, T_COMPACT);
+  if (P <= 0) return PRE3_OK;
+  k_match_compact<<<P, 256, 0, ctx->stream>>>(drows, K1, dk1, dpairs, dscore, dn_out, dxyz1, dxyz2, K2, dYa, dYb);
+  count_launch(ctx);
+  PRE3_CUDA(cudaGetLastError());
+  return PRE3_OK;
+}
+
+}  // namespace pre3

@@ -1,0 +1,1189 @@
+// ransac.cu -- stages 2-4 of the 3PRE frame-to-frame path on sm_100a:
+//   k_prep    per pair: threshold override (RANSAC_CALC_VER2.m:69-72), fp32 float4 copies of
+//             the correspondences, magnitude bounds for the fp32 error band.
+//   k_eval    one hypothesis per thread: sample set -> fp64 minimal fit (find_transform_matrix
+//             or Horn) -> fp32 support scoring over float4 correspondences tiled through
+//             shared memory -> fp64 recheck of threshold-borderline residuals, so the
+//             cardinalities are those of the fp64 reference (RANSAC_CALC_VER2.m:96-125).
+//   k_select  one block per pair: the reference's sequential loop control (adaptive stop :86,
+//             :137-140; skip on state -1 :97-99) as a prefix scan, selection (max cardinality,
+//             min ErrorSum, first index :165-175), winner mask, fp64 least-squares refit :186.
+// Compile with -fmad=false (see fit.cuh); the fp32 scorer uses explicit fmaf().
+#include "fit.cuh"
+#include "ransac.cuh"
+
+#include <cmath>
+
+namespace pre3 {
+
+constexpr int EV_THREADS = 128;
+constexpr int EV_TILE = 512;
+constexpr int EV_LIST = 1024;
+constexpr int SEL_THREADS = 256;
+constexpr int MAX_K = 8;
+
+// ------------------------------------------------------------------------------------------
+// seeded sample sets: SPEC in oracle/pre3_oracle.c (orc_sample_set), the stand-in for
+// get_rand.m:43-48 (ascending k-subset).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ULL;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+  return x ^ (x >> 31);
+}
+
+template <int KN>
+__device__ __forceinline__ void sample_set(uint64_t seed, uint32_t pair, uint32_t hyp, int N, int k_rt, int* out) {
+  const int k = KN > 0 ? KN : k_rt;
+#pragma unroll
+  for (int d = 0; d < (KN > 0 ? KN : MAX_K); ++d) {
+    if (d >= k) break;
+    const int j = N - k + d;
+    const uint64_t x = splitmix64(seed ^ ((uint64_t)pair * 0x9E3779B97F4A7C15ULL) ^
+                                  ((uint64_t)hyp * 0xD1B54A32D192ED03ULL) ^
+                                  ((uint64_t)(d + 1) * 0x8CB92BA72F3D8DD7ULL));
+    const uint32_t r = (uint32_t)(x >> 32);
+    const int t = (int)(((uint64_t)r * (uint64_t)(j + 1)) >> 32);
+    bool dup = false;
+#pragma unroll
+    for (int i = 0; i < (KN > 0 ? KN : MAX_K); ++i)
+      if (i < d && out[i] == t) dup = true;
+    int pick = dup ? j : t;
+    // sorted insert with static indexing: bubble the new value down
+    out[d] = pick;
+#pragma unroll
+    for (int i = (KN > 0 ? KN : MAX_K) - 1; i > 0; --i)
+      if (i <= d && out[i - 1] > out[i]) {
+        const int tmp = out[i - 1];
+        out[i - 1] = out[i];
+        out[i] = tmp;
+      }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_prep
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_prep(const double* __restrict__ Ya, const double* __restrict__ Yb,
+                                              const int32_t* __restrict__ n_corr, int Nmax, int method,
+                                              double thr_opt, const double* __restrict__ thr_override,
+                                              int tab_triangular, PairMeta* __restrict__ meta,
+                                              float4* __restrict__ Ya4, float4* __restrict__ Yb4) {
+  const int p = blockIdx.x;
+  int N = n_corr ? n_corr[p] : Nmax;
+  N = max(0, min(N, Nmax));
+  const double* ya = Ya + (size_t)p * Nmax * 3;
+  const double* yb = Yb + (size_t)p * Nmax * 3;
+  float y1 = 0.f, xm = 0.f;
+  double bz = INFINITY;
+  int bi = 0x7fffffff;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const double ax = ya[3 * i], ay = ya[3 * i + 1], az = ya[3 * i + 2];
+    const double bx = yb[3 * i], by = yb[3 * i + 1], bzz = yb[3 * i + 2];
+    Ya4[(size_t)p * Nmax + i] = make_float4(__double2float_rn(ax), __double2float_rn(ay), __double2float_rn(az), 0.f);
+    Yb4[(size_t)p * Nmax + i] = make_float4(__double2float_rn(bx), __double2float_rn(by), __double2float_rn(bzz), 0.f);
+    y1 = fmaxf(y1, __double2float_ru(fabs(bx) + fabs(by) + fabs(bzz)));
+    xm = fmaxf(xm, __double2float_ru(fmax(fabs(ax), fmax(fabs(ay), fabs(az)))));
+    if (bzz < bz || (bzz == bz && i < bi)) {
+      bz = bzz;
+      bi = i;
+    }
+  }
+  __shared__ float s_y1[256], s_xm[256];
+  __shared__ double s_bz[256];
+  __shared__ int s_bi[256];
+  s_y1[threadIdx.x] = y1;
+  s_xm[threadIdx.x] = xm;
+  s_bz[threadIdx.x] = bz;
+  s_bi[threadIdx.x] = bi;
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) {
+    if (threadIdx.x < off) {
+      const int o = threadIdx.x + off;
+      s_y1[threadIdx.x] = fmaxf(s_y1[threadIdx.x], s_y1[o]);
+      s_xm[threadIdx.x] = fmaxf(s_xm[threadIdx.x], s_xm[o]);
+      if (s_bz[o] < s_bz[threadIdx.x] || (s_bz[o] == s_bz[threadIdx.x] && s_bi[o] < s_bi[threadIdx.x])) {
+        s_bz[threadIdx.x] = s_bz[o];
+        s_bi[threadIdx.x] = s_bi[o];
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    double thr = thr_opt;
+    if (method == PRE3_METHOD_SVD) {
+      if (N > 0) {
+        const int j = s_bi[0] == 0x7fffffff ? 0 : s_bi[0];
+        const double x = yb[3 * j], y = yb[3 * j + 1], z = yb[3 * j + 2];
+        thr = 0.01 * sqrt((x * x + y * y) + z * z);
+      } else {
+        thr = 0.0;
+      }
+    }
+    if (thr_override) thr = *thr_override;
+    PairMeta m;
+    m.thr = thr;
+    m.thr2 = __double2float_rn(thr * thr);
+    m.y1max = s_y1[0];
+    m.xmax = s_xm[0];
+    m.N = N;
+    m.pad = tab_triangular ? (int32_t)(((long long)N * (N + 1)) / 2) : 0;
+    meta[p] = m;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_eval
+// ------------------------------------------------------------------------------------------
+// MODE 0: find_transform_matrix fit, MODE 1: Horn fit, MODE 2: (R,t) given (column-major R).
+template <int K, int MODE>
+__global__ void __launch_bounds__(EV_THREADS)
+k_eval(const PairMeta* __restrict__ meta, const double* __restrict__ Ya, const double* __restrict__ Yb,
+       const float4* __restrict__ Ya4, const float4* __restrict__ Yb4, int Nmax,
+       const int32_t* __restrict__ samples, uint64_t seed, uint32_t pair_id0, long long h0, int H,
+       const double* __restrict__ Rin, const double* __restrict__ Tin, int32_t* __restrict__ counts,
+       int8_t* __restrict__ states) {
+  __shared__ float4 sA[EV_TILE];
+  __shared__ float4 sB[EV_TILE];
+  __shared__ double sRt[EV_THREADS * 12];
+  __shared__ int sCnt[EV_THREADS];
+  __shared__ uint32_t sList[EV_LIST];
+  __shared__ int sListN;
+
+  const int p = blockIdx.y;
+  const int tid = threadIdx.x;
+  const int h = blockIdx.x * EV_THREADS + tid;
+  const PairMeta m = meta[p];
+  const int N = m.N;
+  const double* ya = Ya + (size_t)p * Nmax * 3;
+  const double* yb = Yb + (size_t)p * Nmax * 3;
+  if (tid == 0) sListN = 0;
+
+  const bool valid = (h < H) && (MODE == 2 || N >= K) && N > 0;
+  int state = 0;
+  Rigid fit;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) fit.R[i] = 0.0;
+  fit.t[0] = fit.t[1] = fit.t[2] = 0.0;
+  if (valid) {
+    if (MODE == 2) {
+      const double* r = Rin + ((size_t)p * H + h) * 9;
+      const double* t = Tin + ((size_t)p * H + h) * 3;
+#pragma unroll
+      for (int rr = 0; rr < 3; ++rr)
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) fit.R[3 * rr + cc] = r[3 * cc + rr];
+      fit.t[0] = t[0];
+      fit.t[1] = t[1];
+      fit.t[2] = t[2];
+      state = 1;
+    } else {
+      int idx[K > 0 ? K : 1];
+      if (samples) {
+        const int32_t* s = samples + ((size_t)p * H + h) * K;
+#pragma unroll
+        for (int i = 0; i < K; ++i) idx[i] = min(max(s[i], 0), N - 1);
+      } else {
+        sample_set<K>(seed, pair_id0 + (uint32_t)p, (uint32_t)(h0 + h), N, K, idx);
+      }
+      double pa[K > 0 ? K : 1][3], pb[K > 0 ? K : 1][3];
+#pragma unroll
+      for (int i = 0; i < K; ++i)
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          pa[i][r] = ya[3 * idx[i] + r];
+          pb[i][r] = yb[3 * idx[i] + r];
+        }
+      auto get = [&](int i, double* a, double* b) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          a[r] = pa[i][r];
+          b[r] = pb[i][r];
+        }
+      };
+      if (MODE == 0)
+        state = fit_kabsch<K>(K, get, fit);
+      else
+        state = fit_horn<K>(K, get, fit);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 9; ++i) sRt[tid * 12 + i] = fit.R[i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) sRt[tid * 12 + 9 + i] = fit.t[i];
+
+  const bool scored = valid && !(MODE == 0 && state == -1);
+  // fp32 copies and the certified error band
+  float r0 = __double2float_rn(fit.R[0]), r1 = __double2float_rn(fit.R[1]), r2 = __double2float_rn(fit.R[2]);
+  float r3 = __double2float_rn(fit.R[3]), r4 = __double2float_rn(fit.R[4]), r5 = __double2float_rn(fit.R[5]);
+  float r6 = __double2float_rn(fit.R[6]), r7 = __double2float_rn(fit.R[7]), r8 = __double2float_rn(fit.R[8]);
+  float t0 = __double2float_rn(fit.t[0]), t1 = __double2float_rn(fit.t[1]), t2 = __double2float_rn(fit.t[2]);
+  float thr2 = m.thr2, delta;
+  {
+    float rmax = 0.f;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) rmax = fmaxf(rmax, __double2float_ru(fabs(fit.R[i])));
+    const float tmax = fmaxf(fabsf(t0), fmaxf(fabsf(t1), fabsf(t2))) * 1.0000002f;
+    // |e32 - e| <= 12 u (Rmax*|yb|_1 + |t| + |ya|): 2u input rounding per product term, u per
+    // fma/sub rounding, generous constant; u = 2^-24.
+    const float eps = 1.001f * 12.0f * 5.9604645e-8f * (rmax * m.y1max + tmax + m.xmax);
+    const float thrf = __double2float_ru(m.thr);
+    // |r2_32 - r2| <= eps (2 sqrt(3) r + 3 eps) + 4u r2 near r = thr; doubled for slack.
+    delta = 1.01f * (2.0f * eps * (3.4641018f * thrf + 3.0f * eps) + 8.0f * 5.9604645e-8f * thr2);
+  }
+  if (!scored) {
+    thr2 = -1.0f;
+    delta = -1.0f;
+  }
+  int cnt = 0;
+  for (int base = 0; base < N; base += EV_TILE) {
+    const int tn = min(EV_TILE, N - base);
+    __syncthreads();
+    for (int i = tid; i < tn; i += EV_THREADS) {
+      sA[i] = Ya4[(size_t)p * Nmax + base + i];
+      sB[i] = Yb4[(size_t)p * Nmax + base + i];
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int i = 0; i < tn; ++i) {
+      const float4 b = sB[i];
+      const float4 a = sA[i];
+      const float ex = fmaf(r0, b.x, fmaf(r1, b.y, fmaf(r2, b.z, t0))) - a.x;
+      const float ey = fmaf(r3, b.x, fmaf(r4, b.y, fmaf(r5, b.z, t1))) - a.y;
+      const float ez = fmaf(r6, b.x, fmaf(r7, b.y, fmaf(r8, b.z, t2))) - a.z;
+      const float q = fmaf(ex, ex, fmaf(ey, ey, ez * ez));
+      const bool in = q < thr2;
+      cnt += in ? 1 : 0;
+      if (fabsf(q - thr2) <= delta) {
+        const int slot = atomicAdd(&sListN, 1);
+        if (slot < EV_LIST) sList[slot] = ((uint32_t)tid << 24) | ((in ? 1u : 0u) << 23) | (uint32_t)(base + i);
+      }
+    }
+  }
+  sCnt[tid] = scored ? cnt : -1;
+  __syncthreads();
+  const int nl = sListN;
+  if (nl > EV_LIST) {
+    // too many borderline residuals (degenerate scale): exact fp64 recount for the block
+    if (scored) {
+      int c = 0;
+      for (int i = 0; i < N; ++i)
+        c += (residual_norm(&sRt[tid * 12], &sRt[tid * 12 + 9], ya + 3 * i, yb + 3 * i) < m.thr) ? 1 : 0;
+      sCnt[tid] = c;
+    }
+  } else {
+    for (int it = tid; it < nl; it += EV_THREADS) {
+      const uint32_t item = sList[it];
+      const int hl = item >> 24;
+      const bool in32 = (item >> 23) & 1u;
+      const int mi = item & 0x7FFFFFu;
+      const bool in64 = residual_norm(&sRt[hl * 12], &sRt[hl * 12 + 9], ya + 3 * mi, yb + 3 * mi) < m.thr;
+      if (in64 != in32) atomicAdd(&sCnt[hl], in64 ? 1 : -1);
+    }
+  }
+  __syncthreads();
+  if (h < H) {
+    counts[(size_t)p * H + h] = sCnt[tid];
+    if (states) states[(size_t)p * H + h] = (int8_t)state;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// block helpers for k_select
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum(double v, double* scratch) {
+  const int tid = threadIdx.x;
+  __syncthreads();
+  scratch[tid] = v;
+  __syncthreads();
+  for (int off = SEL_THREADS / 2; off > 0; off >>= 1) {
+    if (tid < off) scratch[tid] = scratch[tid] + scratch[tid + off];
+    __syncthreads();
+  }
+  const double r = scratch[0];
+  __syncthreads();
+  return r;
+}
+
+struct SelShared {
+  double scratch[SEL_THREADS];
+  int pre_cnt[SEL_THREADS];
+  int pre_max[SEL_THREADS];
+  int i0[SEL_THREADS];
+  double tie_es[SEL_THREADS / 32];
+  int tie_s[SEL_THREADS / 32];
+  double Rt[12];
+  int stop, maxc, winner, first_rec, first_nonmax, n_iter;
+};
+
+__device__ __forceinline__ void load_sample(const int32_t* samples, uint64_t seed, uint32_t pair, long long h0,
+                                            int s, int H, int p, int N, int k, int* idx) {
+  if (samples) {
+    const int32_t* sp = samples + ((size_t)p * H + s) * k;
+    for (int i = 0; i < k; ++i) idx[i] = min(max(sp[i], 0), N - 1);
+  } else {
+    sample_set<0>(seed, pair, (uint32_t)(h0 + s), N, k, idx);
+  }
+}
+
+__device__ __forceinline__ int fit_sample(int method, const double* ya, const double* yb, const int* idx, int k,
+                                          Rigid& out) {
+  auto get = [&](int i, double* a, double* b) {
+    const int j = idx[i];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      a[r] = ya[3 * j + r];
+      b[r] = yb[3 * j + r];
+    }
+  };
+  if (method == PRE3_METHOD_SVD) return fit_kabsch<0>(k, get, out);
+  return fit_horn<0>(k, get, out);
+}
+
+// Least-squares refit over the masked correspondences by the whole block; thread 0 gets the
+// result.  Sums are formed per thread over a strided subset and then tree-reduced in a fixed
+// order (deterministic; differs from the reference's sequential sum only in rounding).
+__device__ __forceinline__ int block_refit(int method, const double* ya, const double* yb,
+                                           const uint8_t* mask, int N, double* scratch, Rigid& out) {
+  const int tid = threadIdx.x;
+  double c1[3] = {0, 0, 0}, c2[3] = {0, 0, 0};
+  double ns = 0.0;
+  for (int i = tid; i < N; i += SEL_THREADS)
+    if (mask[i]) {
+      ns += 1.0;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        c1[r] += ya[3 * i + r];
+        c2[r] += yb[3 * i + r];
+      }
+    }
+  ns = block_sum(ns, scratch);
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    c1[r] = block_sum(c1[r], scratch) / ns;
+    c2[r] = block_sum(c2[r], scratch) / ns;
+  }
+  if (method == PRE3_METHOD_SVD) {
+    double H[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = tid; i < N; i += SEL_THREADS)
+      if (mask[i]) {
+        double q1[3], q2[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          q1[r] = ya[3 * i + r] - c1[r];
+          q2[r] = yb[3 * i + r] - c2[r];
+        }
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) H[3 * r + c] = H[3 * r + c] + q2[r] * q1[c];
+      }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) H[i] = block_sum(H[i], scratch);
+    int st = 0;
+    if (tid == 0) st = kabsch_from_H(H, c1, c2, out);
+    return st;
+  } else {
+    double M[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) M[i] = 0.0;
+    for (int i = tid; i < N; i += SEL_THREADS)
+      if (mask[i]) {
+        double an[3], bn[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          an[r] = yb[3 * i + r] - c2[r];  // A = Yb (current), centroid Ca = c2
+          bn[r] = ya[3 * i + r] - c1[r];  // B = Ya (previous), centroid Cb = c1
+        }
+        horn_accumulate(M, an, bn);
+      }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) M[i] = block_sum(M[i], scratch);
+    if (tid == 0) horn_from_M(M, c2, c1, out);
+    return 1;
+  }
+}
+
+__device__ __forceinline__ void store_colmajor(double* dst, const double* Rrow) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) dst[3 * c + r] = Rrow[3 * r + c];
+}
+
+// ------------------------------------------------------------------------------------------
+// k_select
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SEL_THREADS)
+k_select(const PairMeta* __restrict__ meta, const double* __restrict__ Ya, const double* __restrict__ Yb,
+         int Nmax, const int32_t* __restrict__ samples, uint64_t seed, uint32_t pair_id0, long long h0, int H,
+         int k, int method, int max_iteration, int adaptive, const int32_t* __restrict__ tab,
+         const int32_t* __restrict__ counts, const int8_t* __restrict__ states,
+         pre3_pair_result* __restrict__ res, uint8_t* __restrict__ masks, int mask_stride,
+         uint8_t* __restrict__ mask_scratch, int32_t* __restrict__ counts_out, int8_t* __restrict__ states_out) {
+  __shared__ SelShared sh;
+  const int p = blockIdx.x;
+  const int tid = threadIdx.x;
+  const PairMeta m = meta[p];
+  const int N = m.N;
+  const double* ya = Ya + (size_t)p * Nmax * 3;
+  const double* yb = Yb + (size_t)p * Nmax * 3;
+  const int32_t* cnt = counts + (size_t)p * H;
+  const int8_t* sts = states + (size_t)p * H;
+  uint8_t* mask = masks ? masks + (size_t)p * mask_stride : mask_scratch + (size_t)p * Nmax;
+  pre3_pair_result out;
+  if (tid == 0) {
+    out.status = 0;
+    out.state = 0;
+    out.best_fit = 0;
+    out.best_sample = -1;
+    out.best_iter = 0;
+    out.n_iter = 0;
+    out.n_consumed = 0;
+    out.n_matches = N;
+    out.thr = m.thr;
+    out.error_sum = 0.0;
+    for (int i = 0; i < 9; ++i) out.R[i] = out.R_hyp[i] = 0.0;
+    for (int i = 0; i < 3; ++i) out.T[i] = out.T_hyp[i] = 0.0;
+  }
+  if (N < k || N <= 0) {  // get_rand(k, N) errors in the reference (get_rand.m:39-41)
+    if (tid == 0) {
+      out.status = 1;
+      res[p] = out;
+    }
+    for (int i = tid; i < H; i += SEL_THREADS) {
+      if (counts_out) counts_out[(size_t)p * H + i] = -1;
+      if (states_out) states_out[(size_t)p * H + i] = 0;
+    }
+    if (masks)
+      for (int i = tid; i < mask_stride; i += SEL_THREADS) mask[i] = 0;
+    return;
+  }
+  const int32_t* trow = tab ? tab + m.pad : nullptr;
+
+  // ---- 1. loop control as a prefix scan -------------------------------------------------
+  const int ipt = (H + SEL_THREADS - 1) / SEL_THREADS;
+  const int s_lo = min(H, tid * ipt), s_hi = min(H, s_lo + ipt);
+  int lc = 0, lm = 0;
+  for (int s = s_lo; s < s_hi; ++s) {
+    const bool rec = !(method == PRE3_METHOD_SVD && sts[s] == -1);
+    if (rec) {
+      ++lc;
+      lm = max(lm, cnt[s]);
+    }
+  }
+  sh.pre_cnt[tid] = lc;
+  sh.pre_max[tid] = lm;
+  if (tid == 0) {
+    sh.stop = H;
+    sh.maxc = 0;
+    sh.first_rec = 0x7fffffff;
+    sh.first_nonmax = 0x7fffffff;
+  }
+  __syncthreads();
+  if (tid == 0) {  // exclusive scan over 256 partials (tiny)
+    int ac = 0, am = 0;
+    for (int i = 0; i < SEL_THREADS; ++i) {
+      const int c = sh.pre_cnt[i], mm = sh.pre_max[i];
+      sh.pre_cnt[i] = ac;
+      sh.pre_max[i] = am;
+      ac += c;
+      am = max(am, mm);
+    }
+  }
+  __syncthreads();
+  {
+    int pc = sh.pre_cnt[tid], pm = sh.pre_max[tid];
+    int my_stop = H;
+    for (int s = s_lo; s < s_hi; ++s) {
+      const int iter = 1 + pc;
+      int nit = max_iteration;
+      if (adaptive && pm >= 5) nit = min(trow[min(pm, N)], max_iteration);
+      if (!(iter < nit)) {
+        my_stop = s;
+        break;
+      }
+      const bool rec = !(method == PRE3_METHOD_SVD && sts[s] == -1);
+      if (rec) {
+        ++pc;
+        pm = max(pm, cnt[s]);
+      }
+    }
+    if (my_stop < H) atomicMin(&sh.stop, my_stop);
+  }
+  __syncthreads();
+  const int S_end = sh.stop;  // sample sets consumed
+
+  // ---- 2. max cardinality over the recorded hypotheses -----------------------------------
+  {
+    int lmax = -1, lfirst = 0x7fffffff, nrec = 0;
+    for (int s = tid; s < S_end; s += SEL_THREADS) {
+      const bool rec = !(method == PRE3_METHOD_SVD && sts[s] == -1);
+      if (rec) {
+        lmax = max(lmax, cnt[s]);
+        lfirst = min(lfirst, s);
+        ++nrec;
+      }
+    }
+    atomicMax(&sh.maxc, lmax);
+    atomicMin(&sh.first_rec, lfirst);
+    sh.i0[tid] = nrec;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int n = 0;
+    for (int i = 0; i < SEL_THREADS; ++i) n += sh.i0[i];
+    sh.n_iter = n;
+  }
+  __syncthreads();
+  const int maxc = sh.maxc;
+  const int n_iter = sh.n_iter;
+  if (counts_out || states_out)
+    for (int s = tid; s < H; s += SEL_THREADS) {
+      const bool consumed = s < S_end;
+      const bool rec = consumed && !(method == PRE3_METHOD_SVD && sts[s] == -1);
+      if (counts_out) counts_out[(size_t)p * H + s] = rec ? cnt[s] : -1;
+      if (states_out) states_out[(size_t)p * H + s] = consumed ? sts[s] : (int8_t)0;
+    }
+  if (n_iter < 1) {  // nothing recorded: M(1).ErrorSum = [] in the reference -> error
+    if (tid == 0) {
+      out.status = 2;
+      out.n_consumed = S_end;
+      res[p] = out;
+    }
+    if (masks)
+      for (int i = tid; i < mask_stride; i += SEL_THREADS) mask[i] = 0;
+    return;
+  }
+
+  // ---- 3. ties at max cardinality: exact ErrorSum, (min ErrorSum, first index) ------------
+  const int warp = tid >> 5, lane = tid & 31;
+  double best_es = INFINITY;
+  int best_s = 0x7fffffff;
+  if (maxc > 0) {
+    // each warp walks the tie list in the same order; tie number j goes to warp j % 8
+    int tie_no = 0;
+    for (int sbase = 0; sbase < S_end; sbase += 32) {
+      const int s = sbase + lane;
+      bool is_tie = false;
+      if (s < S_end) is_tie = !(method == PRE3_METHOD_SVD && sts[s] == -1) && cnt[s] == maxc;
+      unsigned bal = __ballot_sync(0xffffffffu, is_tie);
+      while (bal) {
+        const int l = __ffs(bal) - 1;
+        bal &= bal - 1;
+        const int st = sbase + l;
+        if ((tie_no++ & (SEL_THREADS / 32 - 1)) != warp) continue;
+        int idx[MAX_K];
+        load_sample(samples, seed, pair_id0 + (uint32_t)p, h0, st, H, p, N, k, idx);
+        Rigid f;
+        fit_sample(method, ya, yb, idx, k, f);  // every lane computes the same fit
+        double es = 0.0;
+        for (int ib = 0; ib < N; ib += 32) {
+          const int i = ib + lane;
+          double nr = 0.0;
+          bool in = false;
+          if (i < N) {
+            nr = residual_norm(f.R, f.t, ya + 3 * i, yb + 3 * i);
+            in = nr < m.thr;
+          }
+          unsigned inb = __ballot_sync(0xffffffffu, in);
+          while (inb) {  // sequential sum in index order (RANSAC_CALC_VER2.m:135)
+            const int li = __ffs(inb) - 1;
+            inb &= inb - 1;
+            es = es + __shfl_sync(0xffffffffu, nr, li);
+          }
+        }
+        if (es < best_es || (es == best_es && st < best_s)) {
+          best_es = es;
+          best_s = st;
+        }
+      }
+    }
+  }
+  if (lane == 0) {
+    sh.tie_es[warp] = best_es;
+    sh.tie_s[warp] = best_s;
+  }
+  // first recorded hypothesis whose cardinality is not the maximum (its eee1 entry is 10000)
+  {
+    int lf = 0x7fffffff;
+    for (int s = tid; s < S_end; s += SEL_THREADS) {
+      const bool rec = !(method == PRE3_METHOD_SVD && sts[s] == -1);
+      if (rec && (cnt[s] != maxc || cnt[s] == 0)) lf = min(lf, s);
+    }
+    atomicMin(&sh.first_nonmax, lf);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double es = INFINITY;
+    int s = 0x7fffffff;
+    for (int w = 0; w < SEL_THREADS / 32; ++w)
+      if (sh.tie_es[w] < es || (sh.tie_es[w] == es && sh.tie_s[w] < s)) {
+        es = sh.tie_es[w];
+        s = sh.tie_s[w];
+      }
+    // [C,I] = min(eee1): entries are ErrorSum for max-cardinality hypotheses, 10000 otherwise
+    int win = s;
+    const int fn = sh.first_nonmax;
+    if (s == 0x7fffffff) {
+      win = fn;  // maxc == 0: every entry is 10000 -> I = first recorded
+    } else if (fn != 0x7fffffff) {
+      if (10000.0 < es || (10000.0 == es && fn < s)) win = fn;
+    }
+    sh.winner = win;
+  }
+  __syncthreads();
+  const int win = sh.winner;
+
+  // ---- 4. winner: hypothesis, mask, ErrorSum ---------------------------------------------
+  if (tid == 0) {
+    int idx[MAX_K];
+    load_sample(samples, seed, pair_id0 + (uint32_t)p, h0, win, H, p, N, k, idx);
+    Rigid f;
+    fit_sample(method, ya, yb, idx, k, f);
+    for (int i = 0; i < 9; ++i) sh.Rt[i] = f.R[i];
+    for (int i = 0; i < 3; ++i) sh.Rt[9 + i] = f.t[i];
+  }
+  __syncthreads();
+  for (int i = tid; i < N; i += SEL_THREADS)
+    mask[i] = residual_norm(&sh.Rt[0], &sh.Rt[9], ya + 3 * i, yb + 3 * i) < m.thr ? 1 : 0;
+  if (masks)
+    for (int i = N + tid; i < mask_stride; i += SEL_THREADS) mask[i] = 0;
+  __syncthreads();
+  if (warp == 0) {  // ErrorSum of the winner, sequential order
+    double es = 0.0;
+    for (int ib = 0; ib < N; ib += 32) {
+      const int i = ib + lane;
+      double nr = 0.0;
+      bool in = false;
+      if (i < N) {
+        in = mask[i] != 0;
+        if (in) nr = residual_norm(&sh.Rt[0], &sh.Rt[9], ya + 3 * i, yb + 3 * i);
+      }
+      unsigned inb = __ballot_sync(0xffffffffu, in);
+      while (inb) {
+        const int li = __ffs(inb) - 1;
+        inb &= inb - 1;
+        es = es + __shfl_sync(0xffffffffu, nr, li);
+      }
+    }
+    if (lane == 0) out.error_sum = es;
+  }
+
+  // ---- 5. refit on the support set --------------------------------------------------------
+  Rigid rf;
+  const int st = block_refit(method, ya, yb, mask, N, sh.scratch, rf);
+  if (tid == 0) {
+    out.state = st;
+    out.best_fit = maxc;
+    out.best_sample = win;
+    // BestFitIdx counts recorded hypotheses up to and including the winner
+    int bi = 0;
+    for (int s = 0; s <= win; ++s) bi += !(method == PRE3_METHOD_SVD && sts[s] == -1);
+    out.best_iter = bi;
+    out.n_iter = n_iter;
+    out.n_consumed = S_end;
+    store_colmajor(out.R, rf.R);
+    for (int i = 0; i < 3; ++i) out.T[i] = rf.t[i];
+    store_colmajor(out.R_hyp, &sh.Rt[0]);
+    for (int i = 0; i < 3; ++i) out.T_hyp[i] = sh.Rt[9 + i];
+    res[p] = out;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// stage-wise kernels
+// ------------------------------------------------------------------------------------------
+__global__ void k_fit_only(const double* __restrict__ Ya, const double* __restrict__ Yb, int N,
+                           const int32_t* __restrict__ samples, int k, int H, int method,
+                           double* __restrict__ R, double* __restrict__ T, int32_t* __restrict__ state) {
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= H) return;
+  int idx[MAX_K];
+  for (int i = 0; i < k; ++i) idx[i] = min(max(samples[(size_t)h * k + i], 0), N - 1);
+  Rigid f;
+  const int st = fit_sample(method, Ya, Yb, idx, k, f);
+  store_colmajor(R + (size_t)h * 9, f.R);
+  for (int i = 0; i < 3; ++i) T[(size_t)h * 3 + i] = f.t[i];
+  state[h] = st;
+}
+
+// exact fp64 scoring of given hypotheses: one warp per hypothesis; errsum in index order
+__global__ void __launch_bounds__(256) k_score_exact(const double* __restrict__ R, const double* __restrict__ T,
+                                                      int H, const double* __restrict__ Ya,
+                                                      const double* __restrict__ Yb, int N, double thr,
+                                                      int32_t* __restrict__ count, double* __restrict__ errsum,
+                                                      uint8_t* __restrict__ mask) {
+  const int h = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (h >= H) return;
+  double Rr[9], t[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) Rr[3 * r + c] = R[(size_t)h * 9 + 3 * c + r];
+  for (int i = 0; i < 3; ++i) t[i] = T[(size_t)h * 3 + i];
+  double es = 0.0;
+  int c = 0;
+  for (int ib = 0; ib < N; ib += 32) {
+    const int i = ib + lane;
+    double nr = 0.0;
+    bool in = false;
+    if (i < N) {
+      nr = residual_norm(Rr, t, Ya + 3 * i, Yb + 3 * i);
+      in = nr < thr;
+      if (mask) mask[(size_t)h * N + i] = in ? 1 : 0;
+    }
+    unsigned inb = __ballot_sync(0xffffffffu, in);
+    c += __popc(inb);
+    while (inb) {
+      const int li = __ffs(inb) - 1;
+      inb &= inb - 1;
+      es = es + __shfl_sync(0xffffffffu, nr, li);
+    }
+  }
+  if (lane == 0) {
+    if (count) count[h] = c;
+    if (errsum) errsum[h] = es;
+  }
+}
+
+// full-set fits for the find_transform_matrix / absoluteOrientationQuaternion entry points:
+// one thread, reference summation order.  out: R(9, column-major), T(3), state, s, err.
+__global__ void k_fit_all(const double* __restrict__ p1, const double* __restrict__ p2, int n, int method,
+                          int do_scale, double* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  Rigid f;
+  int st;
+  double s = 1.0, err = 0.0;
+  if (method == PRE3_METHOD_SVD) {
+    // [rot,trans,state] = find_transform_matrix(pset1 = p1, pset2 = p2)
+    auto get = [&](int i, double* a, double* b) {
+      for (int r = 0; r < 3; ++r) {
+        a[r] = p1[3 * i + r];
+        b[r] = p2[3 * i + r];
+      }
+    };
+    st = fit_kabsch<0>(n, get, f);
+  } else {
+    // [s,R,T,err] = absoluteOrientationQuaternion(A = p1, B = p2, doScale): B ~ s*R*A + T.
+    // fit_horn treats its "yb" slot as A and its "ya" slot as B.
+    auto get = [&](int i, double* a, double* b) {
+      for (int r = 0; r < 3; ++r) {
+        a[r] = p2[3 * i + r];
+        b[r] = p1[3 * i + r];
+      }
+    };
+    st = fit_horn<0>(n, get, f);
+    double Ca[3] = {0, 0, 0}, Cb[3] = {0, 0, 0};
+    for (int i = 0; i < n; ++i)
+      for (int r = 0; r < 3; ++r) {
+        Ca[r] += p1[3 * i + r];
+        Cb[r] += p2[3 * i + r];
+      }
+    for (int r = 0; r < 3; ++r) {
+      Ca[r] = Ca[r] / (double)n;
+      Cb[r] = Cb[r] / (double)n;
+    }
+    if (do_scale) {  // absoluteOrientationQuaternion.m:106-112
+      double sa = 0.0, sb = 0.0;
+      for (int i = 0; i < n; ++i) {
+        double an[3], bn[3], ran[3];
+        for (int r = 0; r < 3; ++r) {
+          an[r] = p1[3 * i + r] - Ca[r];
+          bn[r] = p2[3 * i + r] - Cb[r];
+        }
+        for (int r = 0; r < 3; ++r) ran[r] = (f.R[3 * r] * an[0] + f.R[3 * r + 1] * an[1]) + f.R[3 * r + 2] * an[2];
+        sa = sa + ((bn[0] * ran[0] + bn[1] * ran[1]) + bn[2] * ran[2]);
+        sb = sb + ((bn[0] * bn[0] + bn[1] * bn[1]) + bn[2] * bn[2]);
+      }
+      s = sb / sa;
+      for (int r = 0; r < 3; ++r)  // T = Cb - s*R*Ca (:118)
+        f.t[r] = Cb[r] - ((s * f.R[3 * r] * Ca[0] + s * f.R[3 * r + 1] * Ca[1]) + s * f.R[3 * r + 2] * Ca[2]);
+    }
+    for (int i = 0; i < n; ++i) {  // :121-127
+      double d[3];
+      for (int r = 0; r < 3; ++r)
+        d[r] = p2[3 * i + r] - (((s * f.R[3 * r] * p1[3 * i] + s * f.R[3 * r + 1] * p1[3 * i + 1]) +
+                                 s * f.R[3 * r + 2] * p1[3 * i + 2]) + f.t[r]);
+      err = err + sqrt((d[0] * d[0] + d[1] * d[1]) + d[2] * d[2]);
+    }
+  }
+  store_colmajor(out, f.R);
+  for (int i = 0; i < 3; ++i) out[9 + i] = f.t[i];
+  out[12] = (double)st;
+  out[13] = s;
+  out[14] = err;
+}
+
+// local best of a hypothesis block for the multi-GPU split: key = (count<<32) | ~id
+__global__ void __launch_bounds__(256) k_block_best(const int32_t* __restrict__ counts,
+                                                     const int8_t* __restrict__ states, int H, long long h0,
+                                                     int method, unsigned long long* __restrict__ key) {
+  unsigned long long best = 0ull;
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < H; s += gridDim.x * blockDim.x) {
+    const bool rec = !(method == PRE3_METHOD_SVD && states[s] == -1);
+    if (rec && counts[s] >= 0) {
+      const unsigned long long kk = ((unsigned long long)(uint32_t)counts[s] << 32) |
+                                    (unsigned long long)(0xFFFFFFFFu - (uint32_t)(h0 + s));
+      best = kk > best ? kk : best;
+    }
+  }
+  for (int off = 16; off > 0; off >>= 1) {
+    const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, off);
+    best = o > best ? o : best;
+  }
+  if ((threadIdx.x & 31) == 0 && best) atomicMax(key, best);
+}
+
+// ErrorSum of one hypothesis (the local winner) for the reference-exact all-gather mode
+__global__ void k_key_errsum(const PairMeta* __restrict__ meta, const double* __restrict__ Ya,
+                             const double* __restrict__ Yb, const int32_t* __restrict__ samples, uint64_t seed,
+                             uint32_t pair_id0, long long h0, int H, int k, int method,
+                             const unsigned long long* __restrict__ key, double* __restrict__ errsum) {
+  const int lane = threadIdx.x & 31;
+  const PairMeta m = meta[0];
+  const unsigned long long kk = *key;
+  if (kk == 0ull) {
+    if (lane == 0) *errsum = INFINITY;
+    return;
+  }
+  const long long gid = (long long)(0xFFFFFFFFu - (uint32_t)(kk & 0xFFFFFFFFull));
+  const int s = (int)(gid - h0);
+  int idx[MAX_K];
+  load_sample(samples, seed, pair_id0, h0, s, H, 0, m.N, k, idx);
+  Rigid f;
+  fit_sample(method, Ya, Yb, idx, k, f);
+  double es = 0.0;
+  for (int ib = 0; ib < m.N; ib += 32) {
+    const int i = ib + lane;
+    double nr = 0.0;
+    bool in = false;
+    if (i < m.N) {
+      nr = residual_norm(f.R, f.t, Ya + 3 * i, Yb + 3 * i);
+      in = nr < m.thr;
+    }
+    unsigned inb = __ballot_sync(0xffffffffu, in);
+    while (inb) {
+      const int li = __ffs(inb) - 1;
+      inb &= inb - 1;
+      es = es + __shfl_sync(0xffffffffu, nr, li);
+    }
+  }
+  if (lane == 0) *errsum = es;
+}
+
+// winner known (global id): hypothesis, mask, ErrorSum, refit -- the tail of k_select
+__global__ void __launch_bounds__(SEL_THREADS)
+k_finish(const PairMeta* __restrict__ meta, const double* __restrict__ Ya, const double* __restrict__ Yb,
+         const int32_t* __restrict__ sample_of_winner, uint64_t seed, uint32_t pair_id0, long long winner_id,
+         int k, int method, pre3_pair_result* __restrict__ res, uint8_t* __restrict__ mask) {
+  __shared__ SelShared sh;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const PairMeta m = meta[0];
+  const int N = m.N;
+  pre3_pair_result out;
+  if (tid == 0) {
+    int idx[MAX_K];
+    if (sample_of_winner)
+      for (int i = 0; i < k; ++i) idx[i] = min(max(sample_of_winner[i], 0), N - 1);
+    else
+      sample_set<0>(seed, pair_id0, (uint32_t)winner_id, N, k, idx);
+    Rigid f;
+    fit_sample(method, Ya, Yb, idx, k, f);
+    for (int i = 0; i < 9; ++i) sh.Rt[i] = f.R[i];
+    for (int i = 0; i < 3; ++i) sh.Rt[9 + i] = f.t[i];
+  }
+  __syncthreads();
+  int c = 0;
+  for (int i = tid; i < N; i += SEL_THREADS) {
+    const bool in = residual_norm(&sh.Rt[0], &sh.Rt[9], Ya + 3 * i, Yb + 3 * i) < m.thr;
+    mask[i] = in ? 1 : 0;
+    c += in ? 1 : 0;
+  }
+  const double cs = block_sum((double)c, sh.scratch);
+  double es = 0.0;
+  if (warp == 0) {
+    for (int ib = 0; ib < N; ib += 32) {
+      const int i = ib + lane;
+      double nr = 0.0;
+      bool in = false;
+      if (i < N) {
+        in = mask[i] != 0;
+        if (in) nr = residual_norm(&sh.Rt[0], &sh.Rt[9], Ya + 3 * i, Yb + 3 * i);
+      }
+      unsigned inb = __ballot_sync(0xffffffffu, in);
+      while (inb) {
+        const int li = __ffs(inb) - 1;
+        inb &= inb - 1;
+        es = es + __shfl_sync(0xffffffffu, nr, li);
+      }
+    }
+  }
+  Rigid rf;
+  const int st = block_refit(method, Ya, Yb, mask, N, sh.scratch, rf);
+  if (tid == 0) {
+    out.status = 0;
+    out.state = st;
+    out.best_fit = (int)cs;
+    out.best_sample = (int32_t)winner_id;
+    out.best_iter = 0;
+    out.n_iter = 0;
+    out.n_consumed = 0;
+    out.n_matches = N;
+    out.thr = m.thr;
+    out.error_sum = es;
+    store_colmajor(out.R, rf.R);
+    for (int i = 0; i < 3; ++i) out.T[i] = rf.t[i];
+    store_colmajor(out.R_hyp, &sh.Rt[0]);
+    for (int i = 0; i < 3; ++i) out.T_hyp[i] = sh.Rt[9 + i];
+    res[0] = out;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_threshold(const double* __restrict__ Yb, int N, double* __restrict__ thr) {
+  __shared__ double s_bz[256];
+  __shared__ int s_bi[256];
+  double bz = INFINITY;
+  int bi = 0x7fffffff;
+  for (int i = threadIdx.x; i < N; i += 256) {
+    const double z = Yb[3 * i + 2];
+    if (z < bz || (z == bz && i < bi)) {
+      bz = z;
+      bi = i;
+    }
+  }
+  s_bz[threadIdx.x] = bz;
+  s_bi[threadIdx.x] = bi;
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) {
+    if (threadIdx.x < off) {
+      const int o = threadIdx.x + off;
+      if (s_bz[o] < s_bz[threadIdx.x] || (s_bz[o] == s_bz[threadIdx.x] && s_bi[o] < s_bi[threadIdx.x])) {
+        s_bz[threadIdx.x] = s_bz[o];
+        s_bi[threadIdx.x] = s_bi[o];
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    if (N <= 0) {
+      *thr = 0.0;
+    } else {
+      const int j = s_bi[0] == 0x7fffffff ? 0 : s_bi[0];
+      const double x = Yb[3 * j], y = Yb[3 * j + 1], z = Yb[3 * j + 2];
+      *thr = 0.01 * sqrt((x * x + y * y) + z * z);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+size_t ransac_workspace_bytes(int P, int Nmax, int H) {
+  size_t b = 0;
+  b += align_up(sizeof(PairMeta) * (size_t)P);
+  b += 2 * align_up(sizeof(float4) * (size_t)P * Nmax);
+  b += align_up(sizeof(int32_t) * (size_t)P * H);
+  b += align_up((size_t)P * H);
+  b += align_up((size_t)P * Nmax);  // mask scratch
+  return b + 4096;
+}
+
+void ransac_carve(pre3_ctx* ctx, RansacBuffers& b, int H) {
+  b.meta = ws_take<PairMeta>(ctx, b.P);
+  b.Ya4 = ws_take<float4>(ctx, (size_t)b.P * b.Nmax);
+  b.Yb4 = ws_take<float4>(ctx, (size_t)b.P * b.Nmax);
+  b.counts = ws_take<int32_t>(ctx, (size_t)b.P * H);
+  b.states = ws_take<int8_t>(ctx, (size_t)b.P * H);
+}
+
+int ensure_adaptive_table(pre3_ctx* ctx, const pre3_ransac_opts& o, int Nmax) {
+  if (!o.adaptive) return PRE3_OK;
+  const int mult = o.method == PRE3_METHOD_SVD ? 5 : 1;
+  if (ctx->d_tab && ctx->tab_k == o.k && ctx->tab_mult == mult && ctx->tab_nmax >= Nmax &&
+      ctx->tab_maxit == o.max_iteration)
+    return PRE3_OK;
+  const size_t total = ((size_t)Nmax + 1) * ((size_t)Nmax + 2) / 2;
+  std::vector<int32_t> tab(total);
+  const double le = std::log(0.01);
+  for (int N = 0; N <= Nmax; ++N) {
+    int32_t* row = tab.data() + (size_t)N * (N + 1) / 2;
+    for (int c = 0; c <= N; ++c) {
+      // nIterations = mult*ceil(log(epsilon)/log(1-(card/nPoints)^k))  (RANSAC_CALC_VER2.m:139,
+      // RANSAC_CALC_VER_test.m:102), clamped to [0, MaxIteration] (the loop takes the min, :86)
+      int32_t v = o.max_iteration;
+      if (N > 0 && c >= 1) {
+        const double w = (double)c / (double)N;
+        const double d = (double)mult * std::ceil(le / std::log(1.0 - std::pow(w, (double)o.k)));
+        if (d == d) {
+          if (d < (double)o.max_iteration) v = d <= 0.0 ? 0 : (int32_t)d;
+        }
+      }
+      row[c] = v;
+    }
+  }
+  if (ctx->d_tab) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_tab);
+    ctx->d_tab = nullptr;
+  }
+  PRE3_CUDA(cudaMalloc((void**)&ctx->d_tab, total * sizeof(int32_t)));
+  PRE3_CUDA(cudaMemcpyAsync(ctx->d_tab, tab.data(), total * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  PRE3_CUDA(cudaStreamSynchronize(ctx->stream));  // tab goes out of scope
+  ctx->tab_k = o.k;
+  ctx->tab_mult = mult;
+  ctx->tab_nmax = Nmax;
+  ctx->tab_maxit = o.max_iteration;
+  return PRE3_OK;
+}
+
+int launch_prep(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts& o, int thr_given) {
+  Span span__(ctx, T_PREP);
+  if (b.P <= 0) return PRE3_OK;
+  k_prep<<<b.P, 256, 0, ctx->stream>>>(b.Ya, b.Yb, b.n_corr, b.Nmax, thr_given ? PRE3_METHOD_HORN : o.method,
+                                       o.distance_threshold, nullptr, 1, b.meta, b.Ya4, b.Yb4);
+  count_launch(ctx);
+  PRE3_CUDA(cudaGetLastError());
+  return PRE3_OK;
+}
+
+template <int MODE>
+static int launch_eval_mode(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts& o, long long h0, int H,
+                            const double* Rin, const double* Tin) {
+  Span span__(ctx, T_EVAL);
+  dim3 grid((H + EV_THREADS - 1) / EV_THREADS, b.P);
+#define PRE3_EVAL(KK)                                                                                    \
+  k_eval<KK, MODE><<<grid, EV_THREADS, 0, ctx->stream>>>(b.meta, b.Ya, b.Yb, b.Ya4, b.Yb4, b.Nmax,       \
+                                                         b.samples, o.seed, b.pair_id0, h0, H, Rin, Tin, \
+                                                         b.counts, b.states)
+  if (MODE == 2) {
+    PRE3_EVAL(1);
+  } else {
+    switch (o.k) {
+      case 3: PRE3_EVAL(3); break;
+      case 4: PRE3_EVAL(4); break;
+      case 5: PRE3_EVAL(5); break;
+      case 6: PRE3_EVAL(6); break;
+      case 7: PRE3_EVAL(7); break;
+      case 8: PRE3_EVAL(8); break;
+      default: return fail(ctx, PRE3_ERR_ARG, "minimal sample size k must be in 3..8");
+    }
+  }
+#undef PRE3_EVAL
+  count_launch(ctx);
+  PRE3_CUDA(cudaGetLastError());
+  return PRE3_OK;
+}
+
+int launch_eval(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts& o, long long h0) {
+  if (b.P <= 0 || o.H <= 0) return PRE3_OK;
+  if (o.method == PRE3_METHOD_SVD) return launch_eval_mode<0>(ctx, b, o, h0, o.H, nullptr, nullptr);
+  if (o.method == PRE3_METHOD_HORN) return launch_eval_mode<1>(ctx, b, o, h0, o.H, nullptr, nullptr);
+  return fail(ctx, PRE3_ERR_ARG, "unknown RANSAC method");
+}
+
+int launch_select(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts& o, pre3_pair_result* dres,
+                  uint8_t* dmasks, int32_t* dcounts_out, int8_t* dstates_out) {
+  Span span__(ctx, T_SELECT);
+  if (b.P <= 0) return PRE3_OK;
+  uint8_t* scratch = ws_take<uint8_t>(ctx, (size_t)b.P * b.Nmax);
+  k_select<<<b.P, SEL_THREADS, 0, ctx->stream>>>(b.meta, b.Ya, b.Yb, b.Nmax, b.samples, o.seed, b.pair_id0, 0, o.H,
+                                                 o.k, o.method, o.max_iteration, o.adaptive,
+                                                 o.adaptive ? ctx->d_tab : nullptr, b.counts, b.states, dres,
+                                                 dmasks, b.Nmax, scratch, dcounts_out, dstates_out);
+  count_launch(ctx);
+  PRE3_CUDA(cudaGetLastError());
+  return PRE3_OK;
+}
+
+int launch_fit_only(pre3_ctx* ctx, const double* dYa, const double* dYb, int N, const int32_t* dsamples, int k,
+                    int H, int method, double* dR, double* dT, int32_t* dstate) {
+  Span span__(ctx, T_OTHER);
+  if (H <= 0) return PRE3_OK;
+  k_fit_only<<<(H + 127) / 128, 128, 0, ctx->stream>>>(dYa, dYb, N, dsamples, k, H, method, dR, dT, dstate);
+  count_launch(ctx);
+  PRE3_CUDA(cudaGetLastError());
+  return PRE3_OK;
+}
+
+int launch_score_given(pre3_ctx* ctx, const double* dR, const double* dT, int H, const double* dYa,
+                       const double* dYb, int N, double thr, int32_t* dcount, double* derrsum, uint8_t* dmask) {
+  Span span__(ctx, T_OTHER);
+  if (H <= 0) return PRE3_OK;
+  // cardinalities through the production scorer (fp32 + fp64 recheck) ...
+  RansacBuffers b{};
+  b.Ya = dYa;
+  b.Yb = dYb;
+  b.n_corr = nullptr;
+  b.P = 1;
+  b.Nmax = N;
+  b.samples = nullptr;
+  b.pair_id0 = 0;
+  b.meta = ws_take<PairMeta>(ctx, 1);
+  b.Ya4 = ws_take<float4>(ctx, (size_t)N);
+  b.Yb4 = ws_take<float4>(ctx, (size_t)N);
+  b.counts = dcount;
+  b.states = nullptr;
+  pre3_ransac_opts o{};
+  o.method = PRE3_METHOD_HORN;  // threshold taken as given
+  o.distance_threshold = thr;
+  o.k = 5;
+  k_prep<<<1, 256, 0, ctx->stream>>>(b.Ya, b.Yb, nullptr, N, o.method, thr, nullptr, 0, b.meta, b.Ya4, b.Yb4);
+  count_launch(ctx);
+  PRE3_TRY(launch_eval_mode<2>(ctx, b, o, 0, H, dR, dT));
+  // ... ErrorSum and masks through the exact fp64 kernel
+  if (derrsum || dmask) {
+    k_score_exact<<<(H * 32 + 255) / 256, 256, 0, ctx->stream>>>(dR, dT, H, dYa, dYb, N, thr, nullptr, derrsum, dmask);
+    count_launch(ctx);
+  }
+  PRE3_CUDA(cudaGetLastError());
+  return PRE3_OK;
+}
+
+int launch_fit_all(pre3_ctx* ctx, const double* dp1, const double* dp2, int n, int method, int do_scale,
+                   double* dout) {
+  Span span__(ctx, T_OTHER);
+  k_fit_all<<<1, 32, 0, ctx->stream>>>(dp1, dp2, n, method, do_scale, dout);
+  count_launch(ctx);
+  PRE3_CUDA(cudaGetLastError());
+  return PRE3_OK;
+}
+
+int launch_block_best(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts& o, long long h0, int Hloc,
+                      uint64_t* dkey, double* derrsum) {
+  Span span__(ctx, T_OTHER);
+  PRE3_CUDA(cudaMemsetAsync(dkey, 0, sizeof(uint64_t), ctx->stream));
+  const int blocks = std::min(2 * ctx->sm_count, (Hloc + 255) / 256);
+  k_block_best<<<std::max(blocks, 1), 256, 0, ctx->stream>>>(b.counts, b.states, Hloc, h0, o.method,
+                                                             (unsigned long long*)dkey);
+  count_launch(ctx);
+  if (derrsum) {
+    k_key_errsum<<<1, 32, 0, ctx->stream>>>(b.meta, b.Ya, b.Yb, b.samples, o.seed, b.pair_id0, h0, Hloc, o.k,
+                                            o.method, (const unsigned long long*)dkey, derrsum);
+    count_launch(ctx);
+  }
+  PRE3_CUDA(cudaGetLastError());
+  return PRE3_OK;
+}
+
+int launch_finish(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts& o, long long winner_id,
+                  pre3_pair_result* dres, uint8_t* dmask) {
+  Span span__(ctx, T_OTHER);
+  k_finish<<<1, SEL_THREADS, 0, ctx->stream>>>(b.meta, b.Ya, b.Yb, b.samples, o.seed, b.pair_id0, winner_id, o.k,
+                                               o.method, dres, dmask);
+  count_launch(ctx);
+  PRE3_CUDA(cudaGetLastError());
+  return PRE3_OK;
+}
+
+int launch_threshold(pre3_ctx* ctx, const double* dYb, int N, double* dthr) {
+  Span span__(ctx, T_OTHER);
+  k_threshold<<<1, 256, 0, ctx->stream>>>(dYb, N, dthr);
+  count_launch(ctx);
+  PRE3_CUDA(cudaGetLastError());
+  return PRE3_OK;
+}
+
+}  // namespace pre3

@@ -1,0 +1,55 @@
+// ransac.cuh -- internal (C++) interface of the RANSAC kernels, used by capi.cu.
+#pragma once
+#include "common.cuh"
+
+namespace pre3 {
+
+// Per-pair constants produced by k_prep and consumed by the evaluation / selection kernels.
+struct PairMeta {
+  double thr;    // distance threshold (RANSAC_CALC_VER2.m:69-72 or options)
+  float thr2;    // fl32(thr*thr)
+  float y1max;   // max_i (|yb_x|+|yb_y|+|yb_z|)   -> fp32 error band of the scorer
+  float xmax;    // max_i max_j |ya_j|
+  int32_t N;     // correspondences
+  int32_t pad;
+};
+
+struct RansacBuffers {
+  const double* Ya;      // P x Nmax x 3
+  const double* Yb;
+  const int32_t* n_corr; // P
+  int P, Nmax;
+  PairMeta* meta;        // P
+  float4* Ya4;           // P x Nmax
+  float4* Yb4;
+  int32_t* counts;       // P x H
+  int8_t* states;        // P x H
+  const int32_t* samples;  // P x H x k or nullptr (seeded)
+  uint32_t pair_id0;
+};
+
+size_t ransac_workspace_bytes(int P, int Nmax, int H);
+// carve meta / float4 copies / counts / states out of the context arena
+void ransac_carve(pre3_ctx* ctx, RansacBuffers& b, int H);
+
+// thr_given != 0: use o.distance_threshold whatever the method (hypothesis-block entry points)
+int launch_prep(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts& o, int thr_given);
+int launch_eval(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts& o, long long h0);
+int launch_select(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts& o, pre3_pair_result* dres,
+                  uint8_t* dmasks, int32_t* dcounts_out, int8_t* dstates_out);
+int ensure_adaptive_table(pre3_ctx* ctx, const pre3_ransac_opts& o, int Nmax);
+
+// stage-wise entry points
+int launch_fit_only(pre3_ctx* ctx, const double* dYa, const double* dYb, int N, const int32_t* dsamples, int k,
+                    int H, int method, double* dR, double* dT, int32_t* dstate);
+int launch_score_given(pre3_ctx* ctx, const double* dR, const double* dT, int H, const double* dYa,
+                       const double* dYb, int N, double thr, int32_t* dcount, double* derrsum, uint8_t* dmask);
+int launch_fit_all(pre3_ctx* ctx, const double* dp1, const double* dp2, int n, int method, int do_scale,
+                   double* dout /* R9 colmajor, T3, state, s, err */);
+int launch_block_best(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts& o, long long h0, int Hloc,
+                      uint64_t* dkey, double* derrsum);
+int launch_finish(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts& o, long long winner_id,
+                  pre3_pair_result* dres, uint8_t* dmask);
+int launch_threshold(pre3_ctx* ctx, const double* dYb, int N, double* dthr);
+
+}  // namespace pre3

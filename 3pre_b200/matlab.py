@@ -1,0 +1,169 @@
+"""MATLAB-shaped mirror of the reference's function signatures for the hot path.
+
+Same names, argument order, shapes (128 x K descriptors, 3 x N points), 1-based indices and
+error behaviour as the reference .m / MEX files, so a test written against the reference reads
+the same against this module.  Every function forwards to libpre3.so through
+3pre_b200.api.Context -- nothing is computed in Python.  `M/` = /root/reference/matlab_code/.
+
+New OPTIONAL trailing arguments (never required): explicit sample-index sets
+(k x H, 1-based, as get_rand would have produced them), a seed, k, the adaptive-stop switch.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib as L
+from .api import Context, R2q, make_opts
+
+_ctx = None
+
+
+def context() -> Context:
+    """Lazy one-time initialisation, like a MEX file's first call
+    (M/mex_files/CorePar_Ver1/codegen/mex/corrcoef_partitioned/corrcoef_partitioned_mex.c:39-57)."""
+    global _ctx
+    if _ctx is None:
+        _ctx = Context()
+    return _ctx
+
+
+def at_exit():
+    """mexAtExit counterpart."""
+    global _ctx
+    if _ctx is not None:
+        _ctx.close()
+        _ctx = None
+
+
+class MexError(RuntimeError):
+    """mexErrMsgTxt: raised instead of longjmp-ing into the interpreter."""
+
+
+def _cols(a, rows, dtype=None, name="argument"):
+    """MATLAB rows x K matrix -> (K, rows) C-contiguous (same bytes as column-major)."""
+    a = np.asarray(a) if dtype is None else np.asarray(a, dtype)
+    if a.ndim != 2 or (rows is not None and a.shape[0] != rows):
+        raise MexError(f"{name} must be a {rows} x K matrix")
+    return np.ascontiguousarray(a.T)
+
+
+def siftmatch(L1, L2, thresh=1.5, nargout=1):
+    """matches = siftmatch(L1, L2[, thresh]);  [matches, D] = ...   (M/sift/siftmatch.m:1-12,
+    gateway M/sift/siftmatch.c:139-250).  L1: ND x K1, L2: ND x K2, same class in
+    {double, single, int8, uint8}.  matches: 2 x n double, 1-based, in k1 order."""
+    if nargout > 2:
+        raise MexError("Too many output arguments")  # siftmatch.c:156-158
+    L1 = np.asarray(L1)
+    L2 = np.asarray(L2)
+    if (L1.ndim > 2 or L2.ndim > 2 or not np.issubdtype(L1.dtype, np.number)
+            or not np.issubdtype(L2.dtype, np.number)):
+        raise MexError("L1 and L2 must be two dimensional numeric arrays")  # :160-165
+    L1 = np.atleast_2d(L1)
+    L2 = np.atleast_2d(L2)
+    if L1.shape[0] != L2.shape[0]:
+        raise MexError("L1 and L2 must have the same number of rows")  # :171-173
+    if L1.dtype != L2.dtype:
+        raise MexError("L1 and L2 must be of the same class")  # :175-178
+    if np.ndim(thresh) != 0 and np.size(thresh) != 1 or np.iscomplexobj(thresh):
+        raise MexError("THRESH should be a real scalar")  # :183-186
+    if L1.dtype not in (np.float64, np.float32, np.int8, np.uint8):
+        raise MexError("Unsupported numeric class")  # :213-215
+    thr = float(np.asarray(thresh).reshape(-1)[0])
+    pairs, score = context().siftmatch(np.ascontiguousarray(L1.T), np.ascontiguousarray(L2.T), thr)
+    matches = (pairs.T + 1).astype(np.float64)  # 1-based [k1; k2]  (:241-242)
+    if nargout == 2:
+        return matches, score
+    return matches
+
+
+def find_transform_matrix(pset1, pset2):
+    """[rot, trans, state] = find_transform_matrix(pset1, pset2)
+    (M/mex_files/RANSAC_CALCULATION/find_transform_matrix.m:2-42); pset: 3 x n."""
+    p1 = _cols(pset1, 3, np.float64, "pset1")
+    p2 = _cols(pset2, 3, np.float64, "pset2")
+    if p1.shape != p2.shape:
+        raise MexError("pset1 and pset2 must have the same size")
+    rot, tr, st = context().find_transform_matrix(p1, p2)
+    return rot, tr.reshape(3, 1), st
+
+
+def absoluteOrientationQuaternion(A, B, doScale=1):
+    """[s, R, T, err] = absoluteOrientationQuaternion(A, B, doScale)
+    (M/absoluteOrientationQuaternion.m:28-127); A, B: 3 x N, B ~ s*R*A + T.
+    doScale defaults to 1 like nargin < 3 does in the reference (:32-34)."""
+    A = np.asarray(A, np.float64)
+    B = np.asarray(B, np.float64)
+    if A.shape != B.shape:
+        raise MexError("Point sets need to have same size.")  # :41-43
+    if A.ndim != 2 or A.shape[0] != 3:
+        raise MexError("Need points of dimension 3")  # :46-48
+    if A.shape[1] < 4:
+        raise MexError("Need at least 4 point pairs")  # :51-54
+    s, R, T, err = context().horn(np.ascontiguousarray(A.T), np.ascontiguousarray(B.T), int(bool(doScale)))
+    return s, R, T.reshape(3, 1), err
+
+
+def RANSAC_CALC_VER2(Ya, Yb, options, Za=None, Zb=None, *, samples=None, seed=0, k=5, adaptive=True, H=None,
+                     method="svd"):
+    """[R, T, error, BestFit, State_RANSAC] = RANSAC_CALC_VER2(Ya, Yb, options[, Za, Zb])
+    (M/mex_files/RANSAC_CALCULATION/RANSAC_CALC_VER2.m:2-201; method='horn' gives
+    M/RANSAC_CALC_VER_test.m).  Ya, Yb: 3 x N.  options: dict / object with
+    DistanceThreshold and MaxIteration (M/SIFT_match_save.m:49-50).  `error` is returned as
+    the struct the reference ends up with (:199-201): {'ErrorSum', 'mYa', 'mYb'} (+ the
+    pass-through 'mZa', 'mZb' when Za, Zb are given, :129-130).
+    samples: k x H, 1-based (what get_rand(k, N) marks, ascending), optional."""
+    ya = _cols(Ya, 3, np.float64, "Ya")
+    yb = _cols(Yb, 3, np.float64, "Yb")
+    if ya.shape != yb.shape:
+        raise MexError("Ya and Yb must have the same size")
+    get = (lambda n: options[n]) if isinstance(options, dict) else (lambda n: getattr(options, n))
+    max_it = int(get("MaxIteration"))
+    dthr = float(get("DistanceThreshold"))
+    meth = L.METHOD_SVD if str(method).lower() == "svd" else L.METHOD_HORN
+    s0 = None
+    if samples is not None:
+        s0 = np.ascontiguousarray(np.asarray(samples).T.astype(np.int32) - 1)  # (H,k) 0-based
+        k = s0.shape[1]
+    o = make_opts(method=meth, k=k, max_iteration=max_it, adaptive=adaptive,
+                  H=(s0.shape[0] if s0 is not None else (H if H is not None else max_it)),
+                  distance_threshold=dthr, seed=seed)
+    r = context().ransac(ya, yb, s0, o)
+    if r.status == 1:
+        raise MexError("get_rand: not enough correspondences for a minimal sample")  # get_rand.m:39-41
+    if r.status == 2:
+        raise MexError("RANSAC_CALC_VER2: no hypothesis was recorded")
+    err = {"ErrorSum": r.error_sum, "mYa": np.asarray(Ya, np.float64)[:, r.mask],
+           "mYb": np.asarray(Yb, np.float64)[:, r.mask]}
+    if Za is not None and Zb is not None:
+        err["mZa"] = np.asarray(Za)[:, : len(r.mask)][:, r.mask]
+        err["mZb"] = np.asarray(Zb)[:, : len(r.mask)][:, r.mask]
+    return r.R, r.T.reshape(3, 1), err, r.best_fit, r.state
+
+
+def SIFT_match_save(DataPre, DataCurrent, options=None, *, seed=0, pair_id=0, k=5, adaptive=True):
+    """The compute of M/SIFT_match_save.m:19-53 for one pair (the .mat load/save stays with
+    the caller).  DataPre / DataCurrent: SCAN_SIFT dicts with 'Descriptor' (128 x M) and
+    'XYZ_DATA' (3 x M) (:8-14).  Returns the variables the reference saves (:79-80)."""
+    options = options or {"DistanceThreshold": 0.05, "MaxIteration": 2000}  # :49-50
+    d1 = _cols(DataPre["Descriptor"], None, None, "Descriptor")
+    d2 = _cols(DataCurrent["Descriptor"], None, None, "Descriptor")
+    x1 = _cols(DataPre["XYZ_DATA"], 3, np.float64, "XYZ_DATA")
+    x2 = _cols(DataCurrent["XYZ_DATA"], 3, np.float64, "XYZ_DATA")
+    o = make_opts(method=L.METHOD_SVD, k=k, max_iteration=int(options["MaxIteration"]), adaptive=adaptive,
+                  H=int(options["MaxIteration"]), distance_threshold=float(options["DistanceThreshold"]), seed=seed)
+    res, matches, masks = context().pairs(d1[None], d2[None], x1[None], x2[None], o, pair_id0=pair_id)
+    from .api import unpack_result
+    n = int(res["n_matches"][0])
+    r = unpack_result(res[0], masks[0, :n].astype(bool))
+    return {
+        "matches": (matches[0, :n].T + 1).astype(np.float64),
+        "R_RANSAC": r.R, "T_RANSAC": r.T.reshape(3, 1), "BestFit": r.best_fit, "State_RANSAC": r.state,
+        "status": r.status, "PositionInliers": r.mask,
+    }
+
+
+def Calculate_V_Omega_RANSAC_my_version(DataPre, DataCurrent, **kw):
+    """[T, q, R, State_RANSAC] as M/Calculate_V_Omega_RANSAC_my_version.m:9-34 returns them
+    (q = R2q(R), [w x y z] with the slamToolbox sign convention)."""
+    out = SIFT_match_save(DataPre, DataCurrent, **kw)
+    return out["T_RANSAC"], R2q(out["R_RANSAC"]).reshape(4, 1), out["R_RANSAC"], out["State_RANSAC"]

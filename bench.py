@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""bench.py -- SR4000 frame-pairs/s (match + RANSAC) on synthetic 176x144-frame-shaped pairs.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--pairs P]
+
+Workload (BASELINE.json configs[2], the one the metric "frame-pairs/s (match+RANSAC)" is quoted
+on): a whole synthetic sequence of 4096 frame pairs PER GPU -- 512 SIFT descriptors (128-d,
+class double holding float32 values) + 512 3-D points per frame, 300 planted correspondences,
+30 % outliers, 5-point RANSAC with 2000 seeded sample sets per pair, the reference's adaptive
+stop.  A step = one pass of pre3_pairs over the whole batch.  Pairs are independent: ranks get
+their own sequence, there is no data-path collective ("scaling": "weak").
+
+  value      device-resident inputs, pre3_pairs_dev, CUDA events on the launching stream
+  e2e        pre3_pairs with pinned HOST buffers: H2D of descriptors / points and D2H of the
+             results inside the timed region
+  roofline   the dominant kernel of the step, timed live with CUDA events (pre3_timing_*)
+  cpu_baseline  the reference CPU path (reference siftmatch.c from oracle/_ref when present +
+             the C restatement of RANSAC_CALC_VER2), one thread, bounded sample
+--impl reference times that CPU path with every host core (one process per core over pairs).
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+K_FEAT, N_CORR, OUTLIER, H_HYP, K_MIN, MAX_IT = 512, 300, 0.30, 2000, 5, 2000
+SEED = 3000  # 1000*cfg + index
+FLOPS_PER_EVAL = 27.0        # R*y 15, +t 3, -x 3, squares 5, sqrt 1
+WORKLOAD = "cfg3: sequence of {P} SR4000 frame pairs per GPU, 512x512 descriptors (double), 300 planted matches, " \
+           "30% outliers, k=5, 2000 sample sets, adaptive stop"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback"}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU reference arm
+# ------------------------------------------------------------------------------------------
+def _cpu_pair_worker(args):
+    """One pair through the CPU path: reference siftmatch.c (oracle/_ref) when built, else the C
+    port; then gather + the C restatement of RANSAC_CALC_VER2 (oracle/pre3_oracle.c)."""
+    seed, pair_id = args
+    from oracle import oracle as orc
+    from oracle import refmex
+    fp = _cpu_pair_data(seed)
+    t0 = time.perf_counter()
+    if refmex.available():
+        m = refmex.siftmatch(fp.desc1, fp.desc2, nout=1)[0]
+        pairs = (m.T - 1).astype(np.int32)
+    else:
+        pairs, _ = orc.siftmatch(fp.desc1, fp.desc2, 1.5)
+    Ya, Yb = fp.xyz1[pairs[:, 0]], fp.xyz2[pairs[:, 1]]
+    samples = orc.sample_sets(7, pair_id, H_HYP, len(pairs), K_MIN)
+    t1 = time.perf_counter()
+    r = orc.ransac(Ya, Yb, samples, method=0, max_iteration=MAX_IT, adaptive=True)
+    t2 = time.perf_counter()
+    return t2 - t0, t1 - t0, r.best_fit
+
+
+_PAIR_CACHE = {}
+
+
+def _cpu_pair_data(seed):
+    """Synthetic pair `seed`, generated once per process (outside the timed region)."""
+    if seed not in _PAIR_CACHE:
+        synth = importlib.import_module("3pre_b200.synth")
+        _PAIR_CACHE[seed] = synth.make_frame_pair(seed, K1=K_FEAT, K2=K_FEAT, n_corr=N_CORR, outlier_ratio=OUTLIER)
+    return _PAIR_CACHE[seed]
+
+
+def _cpu_pool_init(n):
+    for i in range(n):
+        _cpu_pair_data(SEED + i)
+    from oracle import oracle as orc
+    orc.lib()
+
+
+def cpu_kind():
+    from oracle import refmex
+    return "reference" if refmex.available() else "port"
+
+
+def cpu_baseline_single(n_pairs=24):
+    ts = [_cpu_pair_worker((SEED + i, i)) for i in range(n_pairs)]
+    total = sum(t[0] for t in ts)
+    return {
+        "value": n_pairs / total, "unit": "frame-pairs/s", "cores": 1, "kind": cpu_kind(),
+        "sample": f"{n_pairs} pairs of the workload, one thread: reference siftmatch.c (oracle/_ref) for matching "
+                  f"[{sum(t[1] for t in ts) / total:.0%} of the time] + C restatement of RANSAC_CALC_VER2 "
+                  "(MATLAB/Octave absent)" if cpu_kind() == "reference" else
+                  f"{n_pairs} pairs of the workload, one thread, C restatement (oracle/pre3_oracle.c)",
+    }
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    per_step = max(cores, 8) * 4
+    ctx = mp.get_context("fork")
+    times = []
+    with ctx.Pool(cores, initializer=_cpu_pool_init, initargs=(per_step,)) as pool:
+        for step in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            pool.map(_cpu_pair_worker, [(SEED + i, i) for i in range(per_step)], chunksize=1)
+            dt = time.perf_counter() - t0
+            if step >= args.warmup:
+                times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    value = per_step / (ms * 1e-3)
+    line = {
+        "impl": "reference", "metric": "SR4000 frame-pairs/s (match+RANSAC)", "value": value,
+        "unit": "frame-pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD.format(P=per_step) + f" [bounded sample: {per_step} pairs per step]"},
+        "cpu_baseline": {"value": value, "unit": "frame-pairs/s", "cores": cores, "kind": cpu_kind(),
+                         "sample": f"{per_step} pairs per step over {cores} processes"},
+        "e2e": {"value": value, "unit": "frame-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [c.strip() for c in ln.split(",")]))
+
+    def stop(self, t0=None, t1=None):
+        """Samples taken inside [t0, t1] (the timed region); when the region is too short for
+        three samples, every sample since start() (warm-up + timed region, same load)."""
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if len(r) >= 6 and (t0 is None or t0 - 0.02 <= t <= t1 + 0.12)]
+        window = "timed region"
+        if len(rows) < 3:
+            rows, window = [r for _, r in self.rows if len(r) >= 6], "warm-up + timed region"
+        sm = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in rows for i in range(4) if r[2 + i] == "Active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm), "window": window}
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    pre3 = importlib.import_module("3pre_b200")
+    synth = importlib.import_module("3pre_b200.synth")
+
+    P = args.pairs
+    ctx = pre3.Context(local)
+    ctx.use_torch_stream()
+    # synthetic sequence of this rank, generated on the device in slabs (bounded peak memory)
+    slabs = []
+    for s0 in range(0, P, 512):
+        n = min(512, P - s0)
+        slabs.append(synth.make_batch_torch(n, SEED + 100000 * rank + s0, dev, K1=K_FEAT, K2=K_FEAT, n_corr=N_CORR,
+                                            outlier_ratio=OUTLIER))
+    data = {k: torch.cat([s[k] for s in slabs]).contiguous() for k in ("desc1", "desc2", "xyz1", "xyz2")}
+    del slabs
+    torch.cuda.empty_cache()
+    opts = pre3.make_opts(method=0, k=K_MIN, max_iteration=MAX_IT, adaptive=True, H=H_HYP, seed=7)
+    res = torch.zeros(P, 240, dtype=torch.uint8, device=dev)
+    matches = torch.zeros(P, K_FEAT, 2, dtype=torch.int32, device=dev)
+    masks = torch.zeros(P, K_FEAT, dtype=torch.uint8, device=dev)
+
+    def step():
+        ctx.pairs_dev(data["desc1"], data["desc2"], data["xyz1"], data["xyz2"], opts, res, matches, masks,
+                      pair_id0=rank * P)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    l0 = ctx.launch_count()
+    tw0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop(tw0, time.perf_counter()) if rank == 0 else None
+    launches = ctx.launch_count() - l0
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    barrier()
+    ms_step = float(t.item()) / args.steps
+    value = world * P / (ms_step * 1e-3)
+
+    # sanity of the timed work: every pair solved, planted motion recovered
+    r = np.frombuffer(res.cpu().numpy().tobytes(), dtype=pre3.RESULT_DTYPE)
+    ok_pairs = int(((r["status"] == 0) & (r["best_fit"] > 150)).sum())
+    evals_done = float((r["n_matches"].astype(np.float64) * H_HYP).sum())          # evaluated on the GPU
+    evals_needed = float((r["n_matches"].astype(np.float64) * r["n_consumed"]).sum())  # the reference's loop
+
+    # ---- per-kernel timing (separate steps, events around every launch) -----------------
+    ctx.timing_enable(True)
+    for _ in range(2):
+        step()
+    kt = ctx.timing_read()
+    ctx.timing_enable(False)
+    per_kernel = {k: {"ms_per_step": v[0] / 2, "launches_per_step": v[1] // 2} for k, v in kt.items()}
+    tot = sum(v["ms_per_step"] for v in per_kernel.values()) or 1.0
+    for v in per_kernel.values():
+        v["share"] = v["ms_per_step"] / tot
+    dom = max(per_kernel, key=lambda k: per_kernel[k]["ms_per_step"])
+    pk = peaks()
+    fp32_peak = ctx.measure_fp32_peak()
+    desc_bytes = float(2 * P * K_FEAT * 128 * data["desc1"].element_size())
+    match_flops = 2.0 * K_FEAT * K_FEAT * 128 * P
+    rooflines = {}
+    for name, v in per_kernel.items():
+        sec = v["ms_per_step"] * 1e-3 / max(v["launches_per_step"], 1)
+        L = max(v["launches_per_step"], 1)
+        if name == "eval":
+            a = FLOPS_PER_EVAL * evals_done / L / sec / 1e12
+            rooflines[name] = {"bound": "fp32", "achieved": a, "peak": fp32_peak, "unit": "TFLOP/s",
+                               "frac": a / fp32_peak, "traffic": None,
+                               "note": "27 FLOP per hypothesis x match eval; peak = FFMA-chain microbenchmark "
+                                       "measured in this run (MEASURED_PEAKS.json has no FP32 figure)",
+                               "evals_per_s": evals_done / L / sec}
+        elif name in ("match_tc",):
+            a = match_flops / L / sec / 1e12
+            rooflines[name] = {"bound": "tensor", "achieved": a, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                               "frac": a / pk["bf16_tflops"], "traffic": None, "note": f"of {pk['source']}"}
+        elif name in ("match_exact",):
+            a = match_flops / L / sec / 1e12
+            rooflines[name] = {"bound": "fp64", "achieved": a, "peak": None, "unit": "TFLOP/s", "frac": None,
+                               "traffic": None, "note": "exact fp64 brute force (3 flop per 2 algorithmic)"}
+        elif name == "convert":
+            a = desc_bytes * 1.25 / L / sec / 1e9  # read f64 descriptors + write the f16 operand image
+            rooflines[name] = {"bound": "hbm", "achieved": a, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                               "frac": a / pk["hbm_gbs"], "traffic": None, "note": f"of {pk['source']}"}
+    roofline = dict(rooflines.get(dom, {"bound": "hbm", "achieved": None, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                        "frac": None, "traffic": None}))
+    roofline["kernel"] = dom
+
+    # ---- e2e: host buffers through pre3_pairs ---------------------------------------------
+    Pe = min(P, args.e2e_pairs)
+    host = {k: torch.empty(data[k][:Pe].shape, dtype=data[k].dtype, pin_memory=True) for k in data}
+    for k in host:
+        host[k].copy_(data[k][:Pe])
+    torch.cuda.synchronize()
+    hn = {k: v.numpy() for k, v in host.items()}
+    out = (np.zeros(Pe, pre3.RESULT_DTYPE), np.zeros((Pe, K_FEAT, 2), np.int32), np.zeros((Pe, K_FEAT), np.uint8))
+    ectx = pre3.Context(local)
+
+    def e2e_step():
+        return ectx.pairs(hn["desc1"], hn["desc2"], hn["xyz1"], hn["xyz2"], opts, pair_id0=rank * P, out=out)
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        e2e_step()
+    barrier()
+    e2e_steps = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_val = world * Pe * e2e_steps / float(te.item())
+    h2d = sum(int(hn[k].nbytes) for k in hn)
+    d2h = int(out[0].nbytes + out[1].nbytes + out[2].nbytes)
+    assert np.array_equal(out[0]["best_fit"], r["best_fit"][:Pe]), "e2e path disagrees with the device path"
+    ectx.close()
+
+    if rank == 0:
+        cpu = cpu_baseline_single()
+        line = {
+            "metric": "SR4000 frame-pairs/s (match+RANSAC)", "value": value, "unit": "frame-pairs/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD.format(P=P), "pairs_per_gpu": P, "sharding": "by frame pair",
+                       "l2": "inputs (4.3 GB of descriptors per GPU at P=4096) larger than L2",
+                       "match_engine": "tcgen05 proposal + exact rescore" if "match_tc" in per_kernel
+                       else "exact fp64 brute force"},
+            "e2e": {"value": e2e_val, "unit": "frame-pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "pairs_per_step": Pe, "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roofline,
+            "rooflines": rooflines,
+            "kernels": per_kernel,
+            "evals": {"hyp_x_match_evals_per_s": world * evals_done / (ms_step * 1e-3),
+                      "executed_per_step": evals_done, "required_by_reference_loop_per_step": evals_needed},
+            "cpu_baseline": cpu,
+            "check": {"pairs_solved": ok_pairs, "pairs": P},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs", type=int, default=4096, help="frame pairs per GPU per step")
+    ap.add_argument("--e2e-pairs", type=int, default=4096, help="frame pairs per e2e step (pinned host memory)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

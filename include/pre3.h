@@ -1,0 +1,223 @@
+/* pre3.h -- C ABI of libpre3.so: the B200 (sm_100a) drop-in for the frame-to-frame
+ * motion-estimation hot path of ahtamjidi/3PRE.
+ *
+ * Every entry point is what a MEX gateway (or any FFI) for the reference function it
+ * cites would bind: plain pointers and sizes, no MATLAB / torch types.  `M/` below is
+ * /root/reference/matlab_code/.  INTEGRATION.md shows the MEX stubs.
+ *
+ * Conventions
+ *   - All matrices use MATLAB's COLUMN-MAJOR layout: a "3 x N" point matrix is N
+ *     consecutive (x,y,z) triples, "128 x K" descriptors are K consecutive 128-vectors,
+ *     a 3x3 rotation R is stored R(1,1),R(2,1),R(3,1),R(1,2),...
+ *   - Indices crossing this ABI are 0-BASED (the gateways add 1 for MATLAB).
+ *   - Functions return PRE3_OK (0) or a negative error code; pre3_last_error() gives
+ *     the text.  Algorithmic failure is NOT an error: it is reported through
+ *     State_RANSAC / status fields exactly like the reference does
+ *     (M/mex_files/RANSAC_CALCULATION/find_transform_matrix.m:21-42).
+ *   - Host-pointer functions are synchronous (they return after the results are in the
+ *     caller's buffers).  *_dev functions take DEVICE pointers, enqueue on the context's
+ *     stream and do not synchronise.
+ *   - There is no CPU fallback: without a CUDA device every compute call fails with
+ *     PRE3_ERR_CUDA.
+ */
+#ifndef PRE3_H
+#define PRE3_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define PRE3_API __attribute__((visibility("default")))
+#else
+#define PRE3_API
+#endif
+
+#define PRE3_OK 0
+#define PRE3_ERR_ARG (-1)   /* bad argument (the reference would mexErrMsgTxt) */
+#define PRE3_ERR_CUDA (-2)  /* CUDA runtime failure / no device */
+#define PRE3_ERR_ALLOC (-3)
+#define PRE3_ERR_CLASS (-4) /* "Unsupported numeric class" (M/sift/siftmatch.c:213-215) */
+
+/* numeric classes accepted by siftmatch (M/sift/siftmatch.c:56-69,208-216) */
+#define PRE3_CLASS_DOUBLE 0
+#define PRE3_CLASS_SINGLE 1
+#define PRE3_CLASS_INT8 2
+#define PRE3_CLASS_UINT8 3
+
+/* RANSAC flavours */
+#define PRE3_METHOD_SVD 0  /* RANSAC_CALC_VER2.m: find_transform_matrix fit/refit, threshold override :69-72, x5 adaptive rule :139 */
+#define PRE3_METHOD_HORN 1 /* RANSAC_CALC_VER_test.m: absoluteOrientationQuaternion fit :71 / refit :152, options threshold, rule :102 */
+
+/* matching engines (pre3_set_match_engine) */
+#define PRE3_MATCH_AUTO 0   /* tcgen05 proposal GEMM + exact rescore when ND==128, else exact */
+#define PRE3_MATCH_EXACT 1  /* exact brute force only */
+#define PRE3_MATCH_TC 2     /* force the tensor-core path (error if the shape does not fit) */
+
+typedef struct pre3_ctx pre3_ctx;
+
+typedef struct {
+  int32_t method;            /* PRE3_METHOD_* */
+  int32_t k;                 /* minimal sample size: 5 (RANSAC_CALC_VER2.m:85), 4, or 3 */
+  int32_t max_iteration;     /* options.MaxIteration (M/SIFT_match_save.m:50: 2000) */
+  int32_t adaptive;          /* 1: reference adaptive stop (RANSAC_CALC_VER2.m:137-140); 0: fixed H */
+  int32_t H;                 /* sample sets available per pair (the loop stops when they run out) */
+  int32_t reserved;
+  double distance_threshold; /* options.DistanceThreshold; used by PRE3_METHOD_HORN only */
+  double ratio;              /* siftmatch thresh, default 1.5 on squared distances (siftmatch.c:146) */
+  uint64_t seed;             /* seeded sample sets (used when no explicit sets are supplied) */
+} pre3_ransac_opts;
+
+/* One per frame pair.  Mirrors the outputs of RANSAC_CALC_VER2.m:2 plus the counters
+ * the reference keeps in RANSAC_STAT (M/code_from_dr_ye/vodometry_dr_ye.m:13-23). */
+typedef struct {
+  int32_t status;      /* 0 ok; 1 fewer than k correspondences (get_rand would error); 2 no iteration ran */
+  int32_t state;       /* State_RANSAC of the refit: 1, 2, 0, -1 */
+  int32_t best_fit;    /* BestFit: cardinality of the winning support set */
+  int32_t best_sample; /* 0-based index of the winning sample set */
+  int32_t best_iter;   /* BestFitIdx in the reference's M(iter) numbering (1-based) */
+  int32_t n_iter;      /* length(M): hypotheses recorded */
+  int32_t n_consumed;  /* sample sets consumed (recorded + skipped on state -1) */
+  int32_t n_matches;   /* N: correspondences that entered RANSAC */
+  double thr;          /* distance threshold used */
+  double error_sum;    /* M(BestFitIdx).ErrorSum */
+  double R[9];         /* refit rotation, column-major; Ya ~ R*Yb + T */
+  double T[3];
+  double R_hyp[9];     /* winning minimal-sample hypothesis M(BestFitIdx).R (column-major) */
+  double T_hyp[3];
+} pre3_pair_result;
+
+/* ---- context ------------------------------------------------------------------- */
+/* device < 0 selects the current CUDA device.  Lazy one-time initialisation of the
+ * stream / workspace arena, as a MEX file would do on first call and undo in mexAtExit
+ * (M/mex_files/CorePar_Ver1/codegen/mex/corrcoef_partitioned/corrcoef_partitioned_mex.c:39-57). */
+PRE3_API int pre3_create(pre3_ctx **ctx, int device);
+PRE3_API void pre3_destroy(pre3_ctx *ctx);
+PRE3_API const char *pre3_last_error(const pre3_ctx *ctx);
+PRE3_API const char *pre3_version(void);
+/* Use an existing cudaStream_t (e.g. torch's current stream) for all later work. */
+PRE3_API int pre3_set_stream(pre3_ctx *ctx, void *cuda_stream);
+PRE3_API int pre3_set_match_engine(pre3_ctx *ctx, int engine);
+PRE3_API int pre3_sync(pre3_ctx *ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+PRE3_API int64_t pre3_launch_count(const pre3_ctx *ctx);
+/* Per-kernel CUDA-event timing on the context's stream (off by default; bench.py's roofline
+ * numbers).  pre3_timing_read synchronises, adds the elapsed ms and launch counts of every
+ * bracketed launch since the last read into ms[cat] / count[cat] (PRE3_TIMING_NCAT entries
+ * each, caller-zeroed) and forgets them.  pre3_timing_name(cat) names a category. */
+#define PRE3_TIMING_NCAT 9
+PRE3_API int pre3_timing_enable(pre3_ctx *ctx, int on);
+PRE3_API int pre3_timing_read(pre3_ctx *ctx, double *ms, int64_t *count);
+PRE3_API const char *pre3_timing_name(int cat);
+/* FFMA-chain microbenchmark: the measured FP32 CUDA-core peak (TFLOP/s) that the scoring
+ * kernel's roofline fraction is quoted against. */
+PRE3_API int pre3_measure_fp32_peak(pre3_ctx *ctx, double *tflops);
+
+/* ---- stage 1: siftmatch -----------------------------------------------------------
+ * Replaces compare_mx*_CLASS + mexFunction of M/sift/siftmatch.c:83-250.
+ * L1: ND x K1, L2: ND x K2, same class.  pairs: 2 x K1 capacity (k1,k2 0-based, in k1
+ * order), score: K1 capacity (best squared distance, siftmatch.c:243-245); *n_out =
+ * number of accepted pairs.  thresh is narrowed to float like the reference (:87,:205). */
+PRE3_API int pre3_siftmatch(pre3_ctx *ctx, const void *L1, const void *L2, int cls, int K1, int K2,
+                   int ND, double thresh, int32_t *pairs, double *score, int32_t *n_out);
+
+/* P independent (L1_p, L2_p) problems, each padded to K1 x K2 with the valid counts in
+ * k1_count / k2_count (NULL = all K1 / K2 valid).  pairs: P x (2 x K1), score: P x K1,
+ * n_out: P.  (find_consistent_sift_matches.m:39-65 and SIFT_match_save.m:33 in bulk.) */
+PRE3_API int pre3_siftmatch_batch(pre3_ctx *ctx, const void *L1, const void *L2, int cls, int P,
+                         int K1, int K2, int ND, const int32_t *k1_count,
+                         const int32_t *k2_count, double thresh, int32_t *pairs,
+                         double *score, int32_t *n_out);
+PRE3_API int pre3_siftmatch_batch_dev(pre3_ctx *ctx, const void *dL1, const void *dL2, int cls, int P,
+                             int K1, int K2, int ND, const int32_t *dk1_count,
+                             const int32_t *dk2_count, double thresh, int32_t *dpairs,
+                             double *dscore, int32_t *dn_out);
+
+/* ---- stage 2: minimal-sample / least-squares rigid fits ----------------------------
+ * [rot,trans,state] = find_transform_matrix(pset1,pset2)
+ * (M/mex_files/RANSAC_CALCULATION/find_transform_matrix.m:2-42).  pset: 3 x n. */
+PRE3_API int pre3_find_transform_matrix(pre3_ctx *ctx, const double *pset1, const double *pset2, int n,
+                               double *rot, double *trans, int32_t *state);
+/* [s,R,T,err] = absoluteOrientationQuaternion(A,B,doScale)
+ * (M/absoluteOrientationQuaternion.m:28-127).  n < 4 -> PRE3_ERR_ARG like :51-54. */
+PRE3_API int pre3_horn(pre3_ctx *ctx, const double *A, const double *B, int n, int do_scale, double *s,
+              double *R, double *T, double *err);
+/* H fits from sample sets: samples k x H (0-based).  Outputs 9 x H (column-major each),
+ * 3 x H, H.  method selects find_transform_matrix (Ya ~ R*Yb+T) or Horn(Yb,Ya). */
+PRE3_API int pre3_fit_batch(pre3_ctx *ctx, const double *Ya, const double *Yb, int N,
+                   const int32_t *samples, int k, int H, int method, double *R, double *T,
+                   int32_t *state);
+
+/* ---- stage 3: hypothesis support ---------------------------------------------------
+ * For each of H hypotheses (R 9 x H column-major, T 3 x H): cardinality of
+ * { i : ||R*Yb_i + T - Ya_i|| < thr } (RANSAC_CALC_VER2.m:121-125) and optionally the
+ * ErrorSum (:135) and the inlier masks (N x H bytes).  fp32 scoring with fp64 recheck
+ * of threshold-borderline residuals: results are those of the fp64 reference. */
+PRE3_API int pre3_score_batch(pre3_ctx *ctx, const double *R, const double *T, int H, const double *Ya,
+                     const double *Yb, int N, double thr, int32_t *count, double *errsum,
+                     uint8_t *mask);
+
+/* ---- stages 2-4: the RANSAC loop ---------------------------------------------------
+ * [R,T,error,BestFit,State_RANSAC] = RANSAC_CALC_VER2(Ya,Yb,options,...)
+ * (M/mex_files/RANSAC_CALCULATION/RANSAC_CALC_VER2.m:2-201; Horn flavour
+ * M/RANSAC_CALC_VER_test.m).  Ya,Yb: 3 x N.  samples: k x opts->H explicit sets
+ * (0-based) or NULL for the seeded generator.  mask: N bytes (PositionInliers of the
+ * winner) or NULL.  counts/states: opts->H entries each or NULL (per sample set:
+ * cardinality or -1 if not evaluated; find_transform_matrix state). */
+PRE3_API int pre3_ransac(pre3_ctx *ctx, const double *Ya, const double *Yb, int N,
+                const pre3_ransac_opts *opts, const int32_t *samples, pre3_pair_result *res,
+                uint8_t *mask, int32_t *counts, int8_t *states);
+
+/* P independent correspondence sets, padded to Nmax columns each; n_corr[P] valid counts.
+ * samples: P x (k x H) or NULL.  masks: P x Nmax or NULL. */
+PRE3_API int pre3_ransac_batch(pre3_ctx *ctx, const double *Ya, const double *Yb, const int32_t *n_corr,
+                      int P, int Nmax, const pre3_ransac_opts *opts, const int32_t *samples,
+                      pre3_pair_result *res, uint8_t *masks);
+PRE3_API int pre3_ransac_batch_dev(pre3_ctx *ctx, const double *dYa, const double *dYb,
+                          const int32_t *dn_corr, int P, int Nmax, const pre3_ransac_opts *opts,
+                          const int32_t *dsamples, pre3_pair_result *dres, uint8_t *dmasks);
+
+/* ---- whole frame pairs: match -> gather -> RANSAC ------------------------------------
+ * What SIFT_match_save.m:33-53 does per pair (and RANSAC_CALC_SAVE_SR4000.m /
+ * Calculate_V_Omega_RANSAC_my_version.m around it), for P pairs in one call:
+ *   matches = siftmatch(desc1_p, desc2_p); Ya = xyz1(:,matches(1,:)); Yb = xyz2(:,matches(2,:));
+ *   RANSAC_CALC_VER2(Ya, Yb, options).
+ * desc: 128 x K per pair (class cls), xyz: 3 x K per pair (double).  matches: P x (2 x K1)
+ * (0-based) or NULL; masks: P x K1 or NULL.  Sample sets are seeded (opts->seed, pair id
+ * = pair_id0 + p) because N is only known after matching. */
+PRE3_API int pre3_pairs(pre3_ctx *ctx, const void *desc1, const void *desc2, int cls, const double *xyz1,
+               const double *xyz2, int P, int K1, int K2, int ND, const int32_t *k1_count,
+               const int32_t *k2_count, const pre3_ransac_opts *opts, uint32_t pair_id0,
+               pre3_pair_result *res, int32_t *matches, uint8_t *masks);
+PRE3_API int pre3_pairs_dev(pre3_ctx *ctx, const void *ddesc1, const void *ddesc2, int cls,
+                   const double *dxyz1, const double *dxyz2, int P, int K1, int K2, int ND,
+                   const int32_t *dk1_count, const int32_t *dk2_count,
+                   const pre3_ransac_opts *opts, uint32_t pair_id0, pre3_pair_result *dres,
+                   int32_t *dmatches, uint8_t *dmasks);
+
+/* ---- hypothesis-block sharding (one large pair over several GPUs) -------
+ * Evaluates sample sets [h0, h0+Hloc) of the pair on this device and returns the local
+ * best as key = (count << 32) | (0xFFFFFFFF - global_hypothesis_id) ("first-index" mode:
+ * max count, lowest id) plus the local (count, id, errsum) triple for the
+ * reference-exact (max count, min ErrorSum, first id) all-gather mode.  The caller does
+ * the one NCCL max-reduce / all-gather, then pre3_ransac_finish on the winner's id. */
+PRE3_API int pre3_ransac_block_dev(pre3_ctx *ctx, const double *dYa, const double *dYb, int N,
+                          const pre3_ransac_opts *opts, const int32_t *dsamples, int64_t h0,
+                          int Hloc, double thr, uint64_t *dkey, double *derrsum);
+PRE3_API int pre3_ransac_finish_dev(pre3_ctx *ctx, const double *dYa, const double *dYb, int N,
+                           const pre3_ransac_opts *opts, const int32_t *dsamples_of_winner,
+                           int64_t winner_id, double thr, pre3_pair_result *dres, uint8_t *dmask);
+/* thr := 0.01*||Yb(:,argmin z)|| (RANSAC_CALC_VER2.m:69-72), computed on the device. */
+PRE3_API int pre3_distance_threshold_dev(pre3_ctx *ctx, const double *dYb, int N, double *dthr);
+
+/* R2q of slamToolbox (M/slamToolbox_11_02_18/FrameTransforms/Rotations/R2q.m:11-55), host
+ * helper used by the Calculate_V_Omega_RANSAC* shims: q = [a -b -c -d]'. */
+PRE3_API void pre3_R2q(const double *R_colmajor, double *q);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PRE3_H */

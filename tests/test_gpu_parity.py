@@ -1,0 +1,411 @@
+"""GPU parity suite (-m gpu): libpre3.so through its C ABI vs the CPU oracle on the same
+seeded inputs.  Bar: bit-exact NN indices, scores, fit states, cardinalities, inlier masks and
+selected hypothesis; refit rotation within 1e-9 rad and translation within 1e-9 m (the refit
+sums are tree-reduced on the GPU, sequential in the oracle).
+"""
+import importlib
+
+import numpy as np
+import pytest
+
+from oracle import ref_numpy as rn
+
+pytestmark = pytest.mark.gpu
+
+TOL_ROT = 1e-9  # rad
+TOL_T = 1e-9    # m
+
+
+# ------------------------------------------------------------------------------------------
+# stage 1
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["f64", "f32", "u8", "i8", "k2one", "ties", "knn"])
+@pytest.mark.parametrize("engine", [0, 1])
+def test_siftmatch_vs_reference_golden(ctx, golden, name, engine):
+    ctx.set_match_engine(engine)
+    try:
+        pairs, score = ctx.siftmatch(golden[f"{name}_L1"], golden[f"{name}_L2"], float(golden[f"{name}_thresh"]))
+    finally:
+        ctx.set_match_engine(0)
+    np.testing.assert_array_equal(pairs.T + 1, golden[f"{name}_matches"].astype(np.int64))
+    np.testing.assert_array_equal(score, golden[f"{name}_D"])
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32, np.uint8, np.int8])
+@pytest.mark.parametrize("engine", [0, 1])
+def test_siftmatch_vs_oracle(ctx, orc, synth, dtype, engine):
+    ctx.set_match_engine(engine)
+    try:
+        for seed, (K1, K2) in enumerate([(512, 512), (300, 517), (1, 40), (129, 1), (700, 2048)]):
+            fp = synth.make_frame_pair(40 + seed, K1=K1, K2=K2, n_corr=min(K1, K2) // 2)
+            d1, d2 = fp.desc1, fp.desc2
+            if dtype == np.float32:
+                d1, d2 = d1.astype(np.float32), d2.astype(np.float32)
+            elif dtype == np.uint8:
+                d1, d2 = synth.to_uint8(d1), synth.to_uint8(d2)
+            elif dtype == np.int8:
+                d1, d2 = (synth.to_uint8(d1) // 2).astype(np.int8), (synth.to_uint8(d2) // 2).astype(np.int8)
+            if K2 > 10:
+                d2[K2 - 1] = d2[3]  # exact duplicate column: first index wins, ratio test fails unless best == 0
+            pairs, score = ctx.siftmatch(d1, d2, 1.5)
+            op, os_ = orc.siftmatch(d1, d2, 1.5)
+            np.testing.assert_array_equal(pairs, op)
+            np.testing.assert_array_equal(score, os_)
+            if np.issubdtype(dtype, np.floating) and K1 >= 300:
+                assert len(pairs) >= 0.4 * min(K1, K2)  # the planted matches are found
+    finally:
+        ctx.set_match_engine(0)
+
+
+def test_siftmatch_adversarial_ratio_band(ctx, orc):
+    """Rows whose second/best ratio sits exactly at / next to the threshold, identical rows
+    (distance 0), and near-duplicates: the tensor-core proposal must hand these to the exact path."""
+    rng = np.random.default_rng(5)
+    base = np.abs(rng.normal(size=(64, 128)))
+    base /= np.linalg.norm(base, axis=1, keepdims=True)
+    L1 = base.astype(np.float32).astype(np.float64)
+    L2 = np.concatenate([L1, L1 + 1e-4 * rng.normal(size=L1.shape), L1[::-1] * (1 + 1e-7)])
+    L2 = L2.astype(np.float32).astype(np.float64)
+    for thresh in (1.5, 1.0, 1.0000001, 3.0):
+        pairs, score = ctx.siftmatch(L1, L2, thresh)
+        op, os_ = orc.siftmatch(L1, L2, thresh)
+        np.testing.assert_array_equal(pairs, op)
+        np.testing.assert_array_equal(score, os_)
+
+
+def test_siftmatch_batch_ragged(ctx, orc, synth):
+    P, K1, K2 = 5, 256, 384
+    L1 = np.zeros((P, K1, 128))
+    L2 = np.zeros((P, K2, 128))
+    k1c = np.array([256, 100, 0, 1, 255], np.int32)
+    k2c = np.array([384, 1, 50, 0, 383], np.int32)
+    for p in range(P):
+        fp = synth.make_frame_pair(70 + p, K1=K1, K2=K2, n_corr=90)
+        L1[p], L2[p] = fp.desc1, fp.desc2
+    out = ctx.siftmatch_batch(L1, L2, 1.5, k1c, k2c)
+    for p in range(P):
+        op, os_ = orc.siftmatch(L1[p, : k1c[p]], L2[p, : k2c[p]], 1.5)
+        np.testing.assert_array_equal(out[p][0], op)
+        np.testing.assert_array_equal(out[p][1], os_)
+
+
+# ------------------------------------------------------------------------------------------
+# stage 2
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("method", [0, 1])
+@pytest.mark.parametrize("k", [3, 4, 5, 8])
+def test_fit_batch_bit_exact(ctx, orc, synth, method, k):
+    c = synth.make_correspondences(11 + k, N=300, outlier_ratio=0.3)
+    samples = synth.make_samples(12 + k, 1500, 300, k)
+    # a few degenerate sets: repeated index (rank-deficient), collinear points
+    samples[0] = np.array([7] * k)
+    R, T, st = ctx.fit_batch(c.Ya, c.Yb, samples, method)
+    for h in range(len(samples)):
+        if method == 0:
+            r0, t0, s0 = orc.find_transform_matrix(c.Ya, c.Yb, samples[h])
+        else:
+            _, r0, t0, _ = orc.horn(c.Yb, c.Ya, 0, samples[h], allow_small=True)
+            s0 = 1
+        assert st[h] == s0
+        np.testing.assert_array_equal(R[h], r0)
+        np.testing.assert_array_equal(T[h], t0)
+
+
+def test_full_set_fits(ctx, orc):
+    rng = np.random.default_rng(2)
+    for n in (4, 5, 37, 1000):
+        Yb = rng.normal(size=(n, 3))
+        q = rng.normal(size=4)
+        q /= np.linalg.norm(q)
+        w, x, y, z = q
+        R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                      [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                      [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+        Ya = 1.3 * Yb @ R.T + rng.normal(size=3) + 1e-3 * rng.normal(size=(n, 3))
+        rot, tr, st = ctx.find_transform_matrix(Ya, Yb)
+        r0, t0, s0 = orc.find_transform_matrix(Ya, Yb)
+        assert st == s0
+        np.testing.assert_array_equal(rot, r0)
+        np.testing.assert_array_equal(tr, t0)
+        for do_scale in (0, 1):
+            s, Rh, Th, err = ctx.horn(Yb, Ya, do_scale)
+            s0, R0, T0, e0 = orc.horn(Yb, Ya, do_scale)
+            assert s == s0 and err == e0
+            np.testing.assert_array_equal(Rh, R0)
+            np.testing.assert_array_equal(Th, T0)
+            s1, R1, T1, e1 = rn.horn(Yb, Ya, bool(do_scale))
+            assert rn.rot_angle(Rh, R1) < TOL_ROT and np.abs(Th - T1).max() < TOL_T
+
+
+# ------------------------------------------------------------------------------------------
+# stage 3
+# ------------------------------------------------------------------------------------------
+def test_score_batch_bit_exact(ctx, orc, synth):
+    c = synth.make_correspondences(21, N=1111, outlier_ratio=0.4)
+    samples = synth.make_samples(22, 600, 1111, 5)
+    R, T, st = ctx.fit_batch(c.Ya, c.Yb, samples, 0)
+    thr = orc.distance_threshold(c.Yb)
+    cnt, es, mk = ctx.score_batch(R, T, c.Ya, c.Yb, thr)
+    for h in range(len(samples)):
+        c0, m0, e0 = orc.score(R[h], T[h], c.Ya, c.Yb, thr)
+        assert cnt[h] == c0 and es[h] == e0
+        np.testing.assert_array_equal(mk[h], m0)
+
+
+def test_score_borderline_residuals(ctx, orc):
+    """Residuals placed within a few ulps of the threshold: fp32 scoring alone would misclassify
+    them; the fp64 recheck must reproduce the reference's strict '<'."""
+    rng = np.random.default_rng(9)
+    N = 4096
+    Yb = rng.uniform(-3, 3, size=(N, 3))
+    R = np.eye(3)
+    T = np.array([0.01, -0.02, 0.03])
+    thr = 0.0125
+    u = rng.normal(size=(N, 3))
+    u /= np.linalg.norm(u, axis=1, keepdims=True)
+    scale = thr * (1 + rng.choice([-1e-15, -1e-12, -1e-9, -1e-7, 0.0, 1e-16, 1e-12, 1e-9, 1e-7], size=N))
+    Ya = Yb + T - u * scale[:, None]
+    cnt, es, mk = ctx.score_batch(R[None], T[None], Ya, Yb, thr)
+    c0, m0, e0 = orc.score(R, T, Ya, Yb, thr)
+    assert 0.2 * N < c0 < 0.8 * N
+    assert cnt[0] == c0 and es[0] == e0
+    np.testing.assert_array_equal(mk[0], m0)
+
+
+# ------------------------------------------------------------------------------------------
+# stages 2-4: the RANSAC loop (config 1: N = 300, 30 % outliers, 2000 sample sets)
+# ------------------------------------------------------------------------------------------
+def _check_ransac(g, o, N):
+    assert g.status == o.status
+    if o.status != 0:
+        return
+    assert g.thr == o.thr
+    assert (g.best_fit, g.best_sample, g.best_iter, g.n_iter, g.n_consumed) == \
+        (o.best_fit, o.best_sample, o.best_iter, o.n_iter, o.n_consumed)
+    np.testing.assert_array_equal(g.mask, o.mask)
+    assert g.error_sum == o.error_sum
+    np.testing.assert_array_equal(g.R_hyp, o.R_hyp)
+    np.testing.assert_array_equal(g.T_hyp, o.T_hyp)
+    assert g.state == o.state
+    assert rn.rot_angle(g.R, o.R) < TOL_ROT and np.abs(g.T - o.T).max() < TOL_T
+    if g.counts is not None and o.counts is not None:
+        np.testing.assert_array_equal(g.counts, o.counts)
+        np.testing.assert_array_equal(g.states[: o.n_consumed], o.states[: o.n_consumed])
+
+
+@pytest.mark.parametrize("method,k", [(0, 5), (0, 3), (1, 5), (1, 4), (1, 3)])
+@pytest.mark.parametrize("adaptive", [True, False])
+def test_ransac_config1(ctx, orc, synth, pre3, method, k, adaptive):
+    for seed in range(6):
+        c = synth.make_correspondences(1000 + seed, N=300, outlier_ratio=0.30)
+        samples = synth.make_samples(2000 + seed, 2000, 300, k)
+        opts = pre3.make_opts(method=method, k=k, max_iteration=2000, adaptive=adaptive, distance_threshold=0.012)
+        g = ctx.ransac(c.Ya, c.Yb, samples, opts)
+        o = orc.ransac(c.Ya, c.Yb, samples, method=method, max_iteration=2000, distance_threshold=0.012,
+                       adaptive=adaptive)
+        _check_ransac(g, o, 300)
+        assert rn.rot_angle(g.R, c.R) < 2e-3 and np.abs(g.T - c.t).max() < 5e-3
+
+
+def test_ransac_seeded_samples_match_oracle_generator(ctx, orc, synth, pre3):
+    c = synth.make_correspondences(77, N=257, outlier_ratio=0.5)
+    for k in (3, 5):
+        opts = pre3.make_opts(method=0, k=k, max_iteration=500, adaptive=True, H=500, seed=424242)
+        g = ctx.ransac(c.Ya, c.Yb, None, opts)
+        samples = orc.sample_sets(424242, 0, 500, 257, k)
+        o = orc.ransac(c.Ya, c.Yb, samples, method=0, max_iteration=500, adaptive=True)
+        _check_ransac(g, o, 257)
+
+
+def test_ransac_edge_cases(ctx, orc, synth, pre3):
+    c = synth.make_correspondences(5, N=120, outlier_ratio=0.2)
+    samples = synth.make_samples(6, 50, 120, 5)
+    # fewer correspondences than k
+    g = ctx.ransac(c.Ya[:4], c.Yb[:4], samples % 4, pre3.make_opts(adaptive=False))
+    assert g.status == 1
+    # MaxIteration bound, perfect data (card == N stops the loop), degenerate first sample, all outliers
+    for Ya, Yb, s, kw in [
+        (c.Ya, c.Yb, samples, dict(max_iteration=10, adaptive=False)),
+        (c.Yb @ c.R.T + c.t, c.Yb, samples, dict(adaptive=True)),
+        (np.random.default_rng(1).normal(size=(120, 3)), c.Yb, samples, dict(adaptive=True)),
+        (c.Ya, c.Yb, samples[:1], dict(max_iteration=1, adaptive=True)),  # no iteration runs -> status 2
+    ]:
+        g = ctx.ransac(Ya, Yb, s, pre3.make_opts(**kw))
+        o = orc.ransac(Ya, Yb, s, max_iteration=kw.get("max_iteration", 2000), adaptive=kw["adaptive"])
+        _check_ransac(g, o, len(Ya))
+    Yb = c.Yb.copy()
+    Yb[:5] = np.outer(np.arange(5.0), [1.0, 1.0, 1.0])
+    Ya = Yb @ c.R.T + c.t
+    s2 = samples.copy()
+    s2[0] = np.arange(5)
+    g = ctx.ransac(Ya, Yb, s2, pre3.make_opts(adaptive=False, max_iteration=20))
+    o = orc.ransac(Ya, Yb, s2, adaptive=False, max_iteration=20)
+    assert o.states[0] == -1
+    _check_ransac(g, o, 120)
+
+
+def test_ransac_batch_ragged(ctx, orc, synth, pre3):
+    P, Nmax, H, k = 9, 320, 600, 5
+    Ya = np.zeros((P, Nmax, 3))
+    Yb = np.zeros((P, Nmax, 3))
+    n = np.array([320, 300, 5, 4, 0, 17, 319, 128, 64], np.int32)
+    samples = np.zeros((P, H, k), np.int32)
+    for p in range(P):
+        c = synth.make_correspondences(300 + p, N=max(int(n[p]), 1), outlier_ratio=0.3)
+        Ya[p, : n[p]], Yb[p, : n[p]] = c.Ya[: n[p]], c.Yb[: n[p]]
+        if n[p] >= k:
+            samples[p] = synth.make_samples(400 + p, H, int(n[p]), k)
+    opts = pre3.make_opts(method=0, k=k, max_iteration=2000, adaptive=True)
+    res, masks = ctx.ransac_batch(Ya, Yb, n, samples, opts)
+    for p in range(P):
+        g = pre3.unpack_result(res[p], masks[p, : n[p]].astype(bool))
+        o = orc.ransac(Ya[p, : n[p]], Yb[p, : n[p]], samples[p], method=0, max_iteration=2000, adaptive=True)
+        _check_ransac(g, o, n[p])
+        assert not masks[p, n[p]:].any()
+
+
+# ------------------------------------------------------------------------------------------
+# whole pairs: match -> gather -> RANSAC (configs 1 / 3 shape)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cls", ["f64", "f32"])
+def test_pairs_vs_oracle(ctx, orc, synth, pre3, cls):
+    P, K = 6, 512
+    fps = [synth.make_frame_pair(900 + p, K1=K, K2=K, n_corr=300, outlier_ratio=0.30) for p in range(P)]
+    d1 = np.stack([f.desc1 for f in fps])
+    d2 = np.stack([f.desc2 for f in fps])
+    x1 = np.stack([f.xyz1 for f in fps])
+    x2 = np.stack([f.xyz2 for f in fps])
+    if cls == "f32":
+        d1, d2 = d1.astype(np.float32), d2.astype(np.float32)
+    opts = pre3.make_opts(method=0, k=5, max_iteration=2000, adaptive=True, H=2000, seed=99)
+    res, matches, masks = ctx.pairs(d1, d2, x1, x2, opts, pair_id0=1000)
+    for p in range(P):
+        # float32-valued doubles: the f32 and f64 classes give the same matches here only if the
+        # accumulation type does not change a decision; the oracle is run in the same class
+        om, o = orc.pair(d1[p].astype(np.float64), d2[p].astype(np.float64), x1[p], x2[p], 99, 1000 + p, H=2000) \
+            if cls == "f64" else (None, None)
+        n = int(res["n_matches"][p])
+        if cls == "f32":
+            op, _ = orc.siftmatch(d1[p], d2[p], 1.5)
+            np.testing.assert_array_equal(matches[p, :n], op)
+            Ya, Yb = x1[p][op[:, 0]], x2[p][op[:, 1]]
+            o = orc.ransac(Ya, Yb, orc.sample_sets(99, 1000 + p, 2000, len(op), 5), method=0, max_iteration=2000)
+        else:
+            np.testing.assert_array_equal(matches[p, :n], om)
+        g = pre3.unpack_result(res[p], masks[p, :n].astype(bool))
+        _check_ransac(g, o, n)
+        assert n >= 280 and rn.rot_angle(g.R, fps[p].R) < 2e-3 and np.abs(g.T - fps[p].t).max() < 5e-3
+
+
+def test_pairs_chunked_host_path_equals_device_path(ctx, synth, pre3):
+    """pre3_pairs (host buffers, chunked + double-buffered) == pre3_pairs_dev (resident buffers)."""
+    import torch
+    b = synth.make_batch_torch(40, 5, "cuda", K1=256, K2=256, n_corr=150)
+    opts = pre3.make_opts(method=0, k=5, max_iteration=500, adaptive=True, H=500, seed=3)
+    res_d = torch.zeros(40, 240, dtype=torch.uint8, device="cuda")
+    m_d = torch.zeros(40, 256, 2, dtype=torch.int32, device="cuda")
+    k_d = torch.zeros(40, 256, dtype=torch.uint8, device="cuda")
+    ctx.pairs_dev(b["desc1"], b["desc2"], b["xyz1"], b["xyz2"], opts, res_d, m_d, k_d, pair_id0=0)
+    ctx.sync()
+    res, matches, masks = ctx.pairs(b["desc1"].cpu().numpy(), b["desc2"].cpu().numpy(), b["xyz1"].cpu().numpy(),
+                                    b["xyz2"].cpu().numpy(), opts, pair_id0=0)
+    rd = np.frombuffer(res_d.cpu().numpy().tobytes(), dtype=pre3.RESULT_DTYPE)
+    assert rd.tobytes() == res.tobytes()
+    for p in range(40):
+        n = int(res["n_matches"][p])
+        np.testing.assert_array_equal(matches[p, :n], m_d[p, :n].cpu().numpy())
+        np.testing.assert_array_equal(masks[p, :n], k_d[p, :n].cpu().numpy())
+
+
+# ------------------------------------------------------------------------------------------
+# full-size properties (configs 2, 3, 5 shapes) -- no oracle at these sizes
+# ------------------------------------------------------------------------------------------
+def test_matching_full_size_properties(ctx, synth):
+    """2k x 2k descriptors: planted matches are found; matching L against itself returns the
+    identity with score 0; results are independent of the batch position."""
+    import torch
+    b = synth.make_batch_torch(4, 11, "cuda", K1=2048, K2=2048, n_corr=1024)
+    pairs = torch.zeros(4, 2048, 2, dtype=torch.int32, device="cuda")
+    score = torch.zeros(4, 2048, dtype=torch.float64, device="cuda")
+    n = torch.zeros(4, dtype=torch.int32, device="cuda")
+    ctx.siftmatch_batch_dev(b["desc1"], b["desc2"], pairs, score, n)
+    ctx.sync()
+    assert (n.cpu().numpy() >= 1000).all()
+    ctx.siftmatch_batch_dev(b["desc1"], b["desc1"], pairs, score, n)
+    ctx.sync()
+    assert (n.cpu().numpy() == 2048).all()
+    ar = torch.arange(2048, dtype=torch.int32, device="cuda")
+    assert (pairs[..., 0] == ar).all() and (pairs[..., 1] == ar).all() and (score == 0).all()
+
+
+def test_stress_pair_properties(ctx, synth, pre3):
+    """20k correspondences, 60 % outliers, 100k seeded hypotheses (config 5 at 1/10 of the
+    hypotheses): the winner's mask is the planted inlier set up to the noise tail, and the
+    refit recovers the planted motion."""
+    c = synth.make_correspondences(5005, N=20000, outlier_ratio=0.60)
+    opts = pre3.make_opts(method=0, k=5, max_iteration=100001, adaptive=False, H=100000, seed=1)
+    g = ctx.ransac(c.Ya, c.Yb, None, opts)
+    assert g.status == 0 and g.n_consumed == 100000  # (sets giving a reflection are skipped uncounted)
+    assert g.n_iter == int((g.states != -1).sum())
+    assert g.best_fit == g.mask.sum() == g.counts.max()
+    assert (g.mask & ~c.inlier).sum() <= 20 and (g.mask & c.inlier).sum() >= 0.8 * c.inlier.sum()
+    assert rn.rot_angle(g.R, c.R) < 1e-3 and np.abs(g.T - c.t).max() < 2e-3
+    # the winner's cardinality agrees with an independent numpy fp64 count
+    cnt, _, _, _ = rn.score(g.R_hyp, g.T_hyp, c.Ya, c.Yb, g.thr)
+    assert cnt == g.best_fit
+
+
+def test_hypothesis_block_split_equals_single_run(ctx, synth, pre3):
+    """Config-5 sharding emulated on one GPU: the blocks' keys max-reduced give the same winner
+    (max count, lowest id) as one run over all hypotheses, and finish() reproduces its result."""
+    import torch
+    c = synth.make_correspondences(31, N=5000, outlier_ratio=0.6)
+    H, G = 20000, 4
+    opts = pre3.make_opts(method=0, k=5, max_iteration=H + 1, adaptive=False, H=H, seed=17)
+    g = ctx.ransac(c.Ya, c.Yb, None, opts)
+    first = int(np.flatnonzero(g.counts == g.counts.max())[0])
+    Ya = torch.from_numpy(c.Ya).cuda()
+    Yb = torch.from_numpy(c.Yb).cuda()
+    keys = []
+    for r in range(G):
+        key = torch.zeros(1, dtype=torch.int64, device="cuda")
+        es = torch.zeros(1, dtype=torch.float64, device="cuda")
+        ctx.ransac_block_dev(Ya, Yb, opts, r * (H // G), H // G, g.thr, key, es)
+        ctx.sync()
+        keys.append(int(key.item()))
+    best = max(keys)
+    assert best >> 32 == g.counts.max() and 0xFFFFFFFF - (best & 0xFFFFFFFF) == first
+    res = torch.zeros(240, dtype=torch.uint8, device="cuda")
+    mask = torch.zeros(5000, dtype=torch.uint8, device="cuda")
+    ctx.ransac_finish_dev(Ya, Yb, opts, first, g.thr, res, mask)
+    ctx.sync()
+    r = pre3.unpack_result(np.frombuffer(res.cpu().numpy().tobytes(), dtype=pre3.RESULT_DTYPE)[0])
+    assert r.best_fit == g.counts.max() and r.best_sample == first
+    if first == g.best_sample:  # same winner as the (count, ErrorSum, first) rule -> identical outputs
+        np.testing.assert_array_equal(mask.cpu().numpy().astype(bool), g.mask)
+        np.testing.assert_array_equal(r.R, g.R)
+        np.testing.assert_array_equal(r.T, g.T)
+
+
+def test_matlab_mirror_roundtrip(ctx, orc, synth):
+    m = importlib.import_module("3pre_b200.matlab")
+    c = synth.make_correspondences(8, N=200, outlier_ratio=0.3)
+    samples = synth.make_samples(9, 800, 200, 5)
+    R, T, err, best_fit, state = m.RANSAC_CALC_VER2(c.Ya.T, c.Yb.T, {"DistanceThreshold": 0.05, "MaxIteration": 2000},
+                                                    samples=samples.T + 1)
+    o = orc.ransac(c.Ya, c.Yb, samples, method=0, max_iteration=2000)
+    assert best_fit == o.best_fit and state == o.state and T.shape == (3, 1)
+    assert err["mYa"].shape == (3, o.best_fit) and err["ErrorSum"] == o.error_sum
+    assert rn.rot_angle(R, o.R) < TOL_ROT
+    fp = synth.make_frame_pair(3, K1=300, K2=280, n_corr=150)
+    matches, D = m.siftmatch(fp.desc1.T, fp.desc2.T, nargout=2)
+    op, os_ = orc.siftmatch(fp.desc1, fp.desc2, 1.5)
+    np.testing.assert_array_equal(matches, (op.T + 1).astype(float))
+    np.testing.assert_array_equal(D, os_)
+    s, Rh, Th, e = m.absoluteOrientationQuaternion(c.Yb[:50].T, c.Ya[:50].T)  # doScale defaults to 1
+    s0, R0, T0, e0 = orc.horn(c.Yb[:50], c.Ya[:50], 1)
+    assert s == s0 and e == e0
+    Tq, q, Rr, st = m.Calculate_V_Omega_RANSAC_my_version(
+        {"Descriptor": fp.desc1.T, "XYZ_DATA": fp.xyz1.T}, {"Descriptor": fp.desc2.T, "XYZ_DATA": fp.xyz2.T})
+    assert q.shape == (4, 1) and abs(np.linalg.norm(q) - 1) < 1e-9 and st in (1, 2)
+    assert rn.rot_angle(Rr, fp.R) < 2e-3
