@@ -187,7 +187,11 @@ def _check_ransac(g, o, N):
     np.testing.assert_array_equal(g.R_hyp, o.R_hyp)
     np.testing.assert_array_equal(g.T_hyp, o.T_hyp)
     assert g.state == o.state
-    assert rn.rot_angle(g.R, o.R) < TOL_ROT and np.abs(g.T - o.T).max() < TOL_T
+    if o.state in (1, 2):
+        assert rn.rot_angle(g.R, o.R) < TOL_ROT and np.abs(g.T - o.T).max() < TOL_T
+    else:  # rot = H (not a rotation), trans = 0 (find_transform_matrix.m:35-36,:40-41)
+        np.testing.assert_allclose(g.R, o.R, rtol=0, atol=1e-12)
+        np.testing.assert_array_equal(g.T, o.T)
     if g.counts is not None and o.counts is not None:
         np.testing.assert_array_equal(g.counts, o.counts)
         np.testing.assert_array_equal(g.states[: o.n_consumed], o.states[: o.n_consumed])
