@@ -25,6 +25,7 @@ int launch_match_rows_exact(pre3_ctx* ctx, const void* dL1, const void* dL2, int
 // Tensor-core proposal (tcgen05 split-fp16 GEMM with fused top-k) + exact rescore; ND == 128,
 // classes double / single.  Rows whose candidates cannot be certified are recomputed exactly.
 bool match_tc_supported(int cls, int K1, int K2, int ND);
+size_t match_tc_workspace_bytes(int P, int K1, int K2);
 int launch_match_tc(pre3_ctx* ctx, const void* dL1, const void* dL2, int cls, int P, int K1, int K2, int ND,
                     const int32_t* dk1, const int32_t* dk2, float thresh, MatchRow* drows);
 

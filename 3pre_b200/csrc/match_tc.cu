@@ -1,9 +1,540 @@
-// match_tc.cu -- placeholder until the tcgen05 proposal kernel lands (next commit).
+// match_tc.cu -- stage 1 on the 5th-generation tensor cores (sm_100a only).
+//
+// siftmatch (M/sift/siftmatch.c:83-132) is a dense contraction: d2(k1,k2) = |a|^2 + |b|^2 - 2 a.b.
+// Three kernels:
+//   k_tc_convert   descriptors (class double / single, 128 x K column-major = K rows of 128)
+//                  -> fp16 operand image, pre-tiled in the exact shared-memory layout the UMMA
+//                  descriptors expect (128-row blocks, two 64-element K halves, 128-byte swizzle),
+//                  so that one TMA bulk copy (cp.async.bulk) lands a ready operand tile; plus
+//                  |x|^2 per descriptor (fp64 -> fp32), the pair's max |b| and a "values do not
+//                  fit fp16" flag.  HBM-bound.
+//   k_tc_gemm_top2 persistent, warp-specialised: TMA producer warp, single-thread tcgen05.mma
+//                  issuer (M128 x N128 x K16, kind::f16, fp32 accumulators in TMEM, four 128-column
+//                  accumulator slots = two row blocks x two pipeline sets), two epilogue warpgroups
+//                  that pull accumulators with tcgen05.ld and keep a running (argmin, second
+//                  smallest) of  |b|^2 - 2 a.b  per L1 row.  The distance matrix never exists
+//                  in memory.
+//   k_tc_rescore   the proposal only PROPOSES: the candidate's distance is recomputed exactly in
+//                  the reference's arithmetic (sequential `acc += delta*delta` in the class's
+//                  accumulation type, siftmatch.c:101-107), the runner-up is bracketed with a
+//                  certified error margin, and the float-cast ratio test (:122-123) is decided
+//                  only when the bracket decides it; every other row goes to the exact
+//                  brute-force kernel (match_exact.cu).  NN indices, scores and accept decisions
+//                  are therefore bit-identical to the reference.
+// Compile with -fmad=false (the exact recomputation must not contract).
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
 #include "match.cuh"
+
 namespace pre3 {
-bool match_tc_supported(int, int, int, int) { return false; }
-int launch_match_tc(pre3_ctx* ctx, const void*, const void*, int, int, int, int, int, const int32_t*, const int32_t*,
-                    float, MatchRow*) {
-  return fail(ctx, PRE3_ERR_ARG, "tensor-core matcher not built");
+
+namespace tc {
+
+constexpr int ND = 128;            // descriptor length this engine is built for
+constexpr int BLK = 128;           // rows per operand block (UMMA M and N)
+constexpr int BLK_BYTES = BLK * ND * 2;       // 32 KB: [khalf 2][row 128][128 B]
+constexpr int HALF_BYTES = BLK * 128;         // 16 KB
+constexpr int A_BUF_BYTES = 2 * BLK_BYTES;    // two row blocks
+constexpr int NSTAGE = 3;                     // B ring
+constexpr int THREADS = 384;                  // 12 warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-7 / 8-11 epilogue
+constexpr int SMEM_BYTES = 2 * A_BUF_BYTES + NSTAGE * BLK_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+struct Prop {      // per L1 row, output of the proposal GEMM
+  float second;    // second smallest of (|b|^2 - 2 a~.b~) over the pair's columns (+inf if < 2 columns)
+  int32_t idx;     // argmin column (-1 if none)
+};
+
+struct PairInfo {
+  unsigned bmax_bits;  // max |b|^2 (float bits) over the valid columns
+  int bad;             // some value is non-finite or too large for fp16
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 32 consecutive columns of 32-bit accumulators -> 32 registers per thread
+__device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, 128-byte-swizzled operand tile: 8-row groups are 1024 B apart (SBO), LBO unused (1),
+// descriptor version 1 (Blackwell), layout type 2 = SWIZZLE_128B.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::f16, A = B = F16, D = F32, both K-major, M = 128, N = 128
+constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BLK >> 3) << 17) | ((uint32_t)(BLK >> 4) << 24);
+
+// ---------------------------------------------------------------------------------------------
+// k_tc_convert: one warp per descriptor row
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load4(const double* src, double* v) {  // 32-byte aligned by construction
+  const double2 x = __ldg(reinterpret_cast<const double2*>(src));
+  const double2 y = __ldg(reinterpret_cast<const double2*>(src) + 1);
+  v[0] = x.x, v[1] = x.y, v[2] = y.x, v[3] = y.y;
+}
+__device__ __forceinline__ void load4(const float* src, double* v) {
+  const float4 x = __ldg(reinterpret_cast<const float4*>(src));
+  v[0] = x.x, v[1] = x.y, v[2] = x.z, v[3] = x.w;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_tc_convert(const T* __restrict__ L, int K, int Kp, const int32_t* __restrict__ kc, int is_b,
+             unsigned char* __restrict__ img, float* __restrict__ nrm, PairInfo* __restrict__ info) {
+  const int p = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int n = kc ? max(0, min(kc[p], K)) : K;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= Kp) return;
+  double v[4] = {0, 0, 0, 0};
+  if (row < n) load4(L + ((size_t)p * K + row) * ND + 4 * lane, v);
+  // fp16 image: block rb, K half kh, row r, 16-byte chunk c of the 128-byte row XOR-swizzled with r & 7
+  const int rb = row >> 7, r = row & 127, kh = lane >> 4, c = (lane & 15) >> 1;
+  __half2 h01 = __floats2half2_rn((float)v[0], (float)v[1]);
+  __half2 h23 = __floats2half2_rn((float)v[2], (float)v[3]);
+  uint2 packed;
+  packed.x = *reinterpret_cast<unsigned*>(&h01);
+  packed.y = *reinterpret_cast<unsigned*>(&h23);
+  unsigned char* dst = img + (size_t)p * Kp * (ND * 2) + (size_t)rb * BLK_BYTES + (size_t)kh * HALF_BYTES +
+                       (size_t)r * 128 + (size_t)((c ^ (r & 7)) << 4) + (size_t)((lane & 1) << 3);
+  *reinterpret_cast<uint2*>(dst) = packed;
+  // |x|^2 in fp64 (fixed shuffle tree), range check
+  double s = (v[0] * v[0] + v[1] * v[1]) + (v[2] * v[2] + v[3] * v[3]);
+  bool bad = false;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) bad = bad || !(fabs(v[e]) <= 60000.0);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  bad = __any_sync(0xffffffffu, bad);
+  if (lane == 0) {
+    float f = __double2float_ru(s);
+    if (row >= n) f = is_b ? INFINITY : 0.f;  // padded columns can never win
+    nrm[(size_t)p * Kp + row] = f;
+    if (row < n) {
+      if (is_b) atomicMax(&info[p].bmax_bits, __float_as_uint(f));
+      if (bad) atomicOr(&info[p].bad, 1);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_tc_gemm_top2
+// ---------------------------------------------------------------------------------------------
+struct Barriers {
+  uint64_t a_full[2], a_empty[2];
+  uint64_t b_full[NSTAGE], b_empty[NSTAGE];
+  uint64_t t_full[4], t_empty[4];  // accumulator slot = set * 2 + row block
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(THREADS, 1)
+k_tc_gemm_top2(const unsigned char* __restrict__ imgA, const unsigned char* __restrict__ imgB,
+               const float* __restrict__ nrmB, int P, int K1p, int K2p, Prop* __restrict__ prop) {
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
+  unsigned char* smem = smem_raw + (base - raw);
+  const uint32_t sA = base;                                  // 2 buffers x 64 KB
+  const uint32_t sB = base + 2 * A_BUF_BYTES;                // NSTAGE x 32 KB
+  Barriers* bars = reinterpret_cast<Barriers*>(smem + 2 * A_BUF_BYTES + NSTAGE * BLK_BYTES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int groups = (K1p / BLK + 1) / 2;  // row groups (<= 2 row blocks each) per pair
+  const int ntile = K2p / BLK;             // B tiles per pair
+  const long long nunits = (long long)P * groups;
+
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&bars->a_full[i]), 1);
+      mbar_init(smem_u32(&bars->a_empty[i]), 1);
+    }
+    for (int i = 0; i < NSTAGE; ++i) {
+      mbar_init(smem_u32(&bars->b_full[i]), 1);
+      mbar_init(smem_u32(&bars->b_empty[i]), 1);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(smem_u32(&bars->t_full[i]), 1);
+      mbar_init(smem_u32(&bars->t_empty[i]), 128);  // every thread of the epilogue warpgroup arrives
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&bars->tmem_base))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+
+  if (warp == 0) {
+    // ===== TMA producer ========================================================================
+    if (lane == 0) {
+      long long t = 0;  // B tiles issued so far
+      int uc = 0;       // units handled by this CTA so far
+      for (long long u = blockIdx.x; u < nunits; u += gridDim.x, ++uc) {
+        const int p = (int)(u / groups), g = (int)(u % groups);
+        const int nrb = min(2, K1p / BLK - 2 * g);
+        const int ab = uc & 1;
+        mbar_wait(smem_u32(&bars->a_empty[ab]), ((uc >> 1) & 1) ^ 1);
+        mbar_expect_tx(smem_u32(&bars->a_full[ab]), (uint32_t)(nrb * BLK_BYTES));
+        tma_bulk_g2s(sA + ab * A_BUF_BYTES, imgA + ((size_t)p * K1p + (size_t)g * 2 * BLK) * (ND * 2),
+                     (uint32_t)(nrb * BLK_BYTES), smem_u32(&bars->a_full[ab]));
+        for (int j = 0; j < ntile; ++j, ++t) {
+          const int st = (int)(t % NSTAGE);
+          mbar_wait(smem_u32(&bars->b_empty[st]), (uint32_t)(((t / NSTAGE) & 1) ^ 1));
+          mbar_expect_tx(smem_u32(&bars->b_full[st]), BLK_BYTES);
+          tma_bulk_g2s(sB + st * BLK_BYTES, imgB + ((size_t)p * K2p + (size_t)j * BLK) * (ND * 2), BLK_BYTES,
+                       smem_u32(&bars->b_full[st]));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread) =============================================================
+    if (lane == 0) {
+      long long t = 0;
+      int uc = 0;
+      uint32_t use0 = 0, use1 = 0, use2 = 0, use3 = 0;  // times each accumulator slot has been filled
+      for (long long u = blockIdx.x; u < nunits; u += gridDim.x, ++uc) {
+        const int g = (int)(u % groups);
+        const int nrb = min(2, K1p / BLK - 2 * g);
+        const int ab = uc & 1;
+        mbar_wait(smem_u32(&bars->a_full[ab]), (uc >> 1) & 1);
+        for (int j = 0; j < ntile; ++j, ++t) {
+          const int st = (int)(t % NSTAGE);
+          const int set = (int)(t & 1);
+          mbar_wait(smem_u32(&bars->b_full[st]), (uint32_t)((t / NSTAGE) & 1));
+          tc_fence_after();
+          for (int rb = 0; rb < nrb; ++rb) {
+            const int slot = set * 2 + rb;
+            uint32_t& use = slot == 0 ? use0 : (slot == 1 ? use1 : (slot == 2 ? use2 : use3));
+            mbar_wait(smem_u32(&bars->t_empty[slot]), (use & 1) ^ 1);
+            ++use;
+            tc_fence_after();
+            const uint32_t d = tmem + (uint32_t)(slot * BLK);
+#pragma unroll
+            for (int k = 0; k < ND / 16; ++k) {
+              const uint32_t koff = (uint32_t)((k >> 2) * HALF_BYTES + (k & 3) * 32);
+              const uint64_t da = umma_desc(sA + ab * A_BUF_BYTES + rb * BLK_BYTES + koff);
+              const uint64_t db = umma_desc(sB + st * BLK_BYTES + koff);
+              tc_mma_f16(d, da, db, IDESC, k > 0 ? 1u : 0u);
+            }
+            tc_commit(smem_u32(&bars->t_full[slot]));  // accumulator ready for the epilogue
+          }
+          tc_commit(smem_u32(&bars->b_empty[st]));  // B stage may be refilled
+        }
+        tc_commit(smem_u32(&bars->a_empty[ab]));  // A buffer may be refilled
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: warpgroup rb owns row block rb ============================================
+    const int rb = (warp - 4) >> 2;
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    long long t = 0;
+    uint32_t useA = 0, useB = 0;  // times this warpgroup has drained its slot of set 0 / set 1
+    for (long long u = blockIdx.x; u < nunits; u += gridDim.x) {
+      const int p = (int)(u / groups), g = (int)(u % groups);
+      const int nrb = min(2, K1p / BLK - 2 * g);
+      if (rb >= nrb) {
+        t += ntile;
+        continue;
+      }
+      float best = INFINITY, second = INFINITY;
+      int btile = -1, bcol = 0;
+      const float* nb = nrmB + (size_t)p * K2p;
+      for (int j = 0; j < ntile; ++j, ++t) {
+        const int set = (int)(t & 1);
+        const int slot = set * 2 + rb;
+        uint32_t& use = set == 0 ? useA : useB;
+        mbar_wait(smem_u32(&bars->t_full[slot]), use & 1);
+        ++use;
+        tc_fence_after();
+        const float best_in = best;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLK; c0 += 32) {
+          float acc[32];
+          tc_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * BLK + c0), acc);
+          const float4* nb4 = reinterpret_cast<const float4*>(nb + (size_t)j * BLK + c0);
+#pragma unroll
+          for (int i4 = 0; i4 < 8; ++i4) {
+            const float4 n4 = __ldg(nb4 + i4);
+            const float nn[4] = {n4.x, n4.y, n4.z, n4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float v = fmaf(-2.0f, acc[4 * i4 + e], nn[e]);
+              const bool lt = v < best;
+              second = lt ? best : fminf(second, v);
+              bcol = lt ? (c0 + 4 * i4 + e) : bcol;
+              best = fminf(best, v);
+            }
+          }
+        }
+        if (best < best_in) btile = j;
+        tc_fence_before();
+        mbar_arrive(smem_u32(&bars->t_empty[slot]));
+      }
+      const int row = (g * 2 + rb) * BLK + q * 32 + lane;
+      Prop o;
+      o.second = second;
+      o.idx = btile < 0 ? -1 : btile * BLK + bcol;
+      prop[(size_t)p * K1p + row] = o;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_tc_rescore: exact candidate distance + certified ratio-test decision.  One warp handles 32
+// rows at a time: coalesced loads of the row and of its candidate column, delta*delta per
+// element into shared memory, then lane r sums row r strictly in bin order.
+// ---------------------------------------------------------------------------------------------
+constexpr int RS_WARPS = 1;  // 32 x 129 products of the accumulation type = 33 KB (double)
+
+template <typename T, typename ACC>
+__global__ void __launch_bounds__(RS_WARPS * 32)
+k_tc_rescore(const T* __restrict__ L1, const T* __restrict__ L2, int K1, int K2, int K1p, int K2p,
+             const int32_t* __restrict__ k1c, const int32_t* __restrict__ k2c, float thresh,
+             const Prop* __restrict__ prop, const float* __restrict__ nrmA, const PairInfo* __restrict__ info,
+             MatchRow* __restrict__ rows, int32_t* __restrict__ row_list, int32_t* __restrict__ row_list_n) {
+  __shared__ ACC sprod[RS_WARPS][32][ND + 1];
+  const int p = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n1 = k1c ? max(0, min(k1c[p], K1)) : K1;
+  const int n2 = k2c ? max(0, min(k2c[p], K2)) : K2;
+  const int row0 = (blockIdx.x * RS_WARPS + warp) * 32;
+  if (row0 >= n1) return;
+  const PairInfo pi = info[p];
+  const int nr = min(32, n1 - row0);
+  // candidate of "my" row (lane r <-> row row0 + r)
+  Prop my;
+  my.second = INFINITY;
+  my.idx = -1;
+  if (lane < nr) my = prop[(size_t)p * K1p + row0 + lane];
+#pragma unroll 4
+  for (int r = 0; r < nr; ++r) {
+    const int idx = __shfl_sync(0xffffffffu, my.idx, r);
+    if (idx < 0 || idx >= n2) continue;
+    const T* a = L1 + ((size_t)p * K1 + row0 + r) * ND + 4 * lane;
+    const T* b = L2 + ((size_t)p * K2 + idx) * ND + 4 * lane;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const ACC d = (ACC)a[e] - (ACC)b[e];
+      sprod[warp][r][4 * lane + e] = d * d;
+    }
+  }
+  __syncwarp();
+  if (lane >= nr) return;
+  const int k1 = row0 + lane;
+  MatchRow out;
+  out.best = INFINITY;
+  out.bestk = -1;
+  out.accept = 0;
+  bool ambiguous = false;
+  if (n2 <= 0) {
+    // no column: bestk = -1 -> never accepted (siftmatch.c:123)
+  } else if (pi.bad || my.idx < 0 || my.idx >= n2 || !(thresh > 0.f)) {
+    ambiguous = true;
+  } else {
+    ACC acc = 0;
+    for (int bin = 0; bin < ND; ++bin) acc += sprod[warp][lane][bin];  // strictly in order (siftmatch.c:101-107)
+    const double d1 = (double)acc;
+    // certified margin on |(|b|^2 - 2 a~.b~ + |a|^2) - d2_exact| for every column of the pair:
+    // fp16 rounding of both operands (2^-11 relative each, 2^-25 absolute below the normal
+    // range), fp32 accumulation of 128 products, fp32 norms and epilogue, with 25 % slack.
+    const double na = (double)nrmA[(size_t)p * K1p + k1];
+    const double nbm = (double)__uint_as_float(pi.bmax_bits);
+    const double ra = sqrt(na), rbm = sqrt(nbm);
+    // (na + nbm) / 32768 also covers the reference's own rounding when it accumulates in float.
+    const double m = 1.25 * ((1.0 / 512 + 1.0 / 16384) * ra * rbm + (na + nbm) * (1.0 / 32768) +
+                             (ra + rbm) * (1.0 / 1048576));
+    const double s2 = (double)my.second + na;
+    const double L2b = s2 - m, U2b = s2 + m;  // every other column's exact distance is >= L2b; one is <= U2b
+    if (d1 < L2b) {
+      // unique exact minimum: best = d1, bestk = idx; second_best in [L2b, U2b]
+      const float lhs = __fmul_rn(thresh, (float)acc);
+      out.best = d1;
+      out.bestk = my.idx;
+      if (lhs <= (float)L2b)
+        out.accept = 1;
+      else if (lhs > (float)U2b)
+        out.accept = 0;
+      else
+        ambiguous = true;
+    } else {
+      // best >= L2b, second_best <= max(d1, U2b): rejected for sure when even that fails the test
+      const double hi = d1 > U2b ? d1 : U2b;
+      if (L2b > 0.0 && __fmul_rn(thresh, (float)L2b) > (float)hi)
+        out.accept = 0;  // rejected rows are never output: best / bestk irrelevant
+      else
+        ambiguous = true;
+    }
+  }
+  if (ambiguous) {
+    const int slot = atomicAdd(row_list_n, 1);
+    row_list[slot] = p * K1 + k1;
+  }
+  rows[(size_t)p * K1 + k1] = out;
+}
+
+}  // namespace tc
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static inline int pad128(int k) { return (k + 127) / 128 * 128; }
+
+bool match_tc_supported(int cls, int K1, int K2, int ND) {
+  return (cls == PRE3_CLASS_DOUBLE || cls == PRE3_CLASS_SINGLE) && ND == tc::ND && K1 >= 1 && K2 >= 1;
+}
+
+size_t match_tc_workspace_bytes(int P, int K1, int K2) {
+  const size_t K1p = pad128(K1), K2p = pad128(K2);
+  size_t b = 0;
+  b += align_up((size_t)P * K1p * tc::ND * 2, 1024) + 1024;
+  b += align_up((size_t)P * K2p * tc::ND * 2, 1024) + 1024;
+  b += align_up((size_t)P * K1p * 4) + align_up((size_t)P * K2p * 4);
+  b += align_up((size_t)P * K1p * sizeof(tc::Prop));
+  b += align_up((size_t)P * sizeof(tc::PairInfo));
+  b += align_up((size_t)P * K1 * 4) + 256;
+  return b + 4096;
+}
+
+int launch_match_tc(pre3_ctx* ctx, const void* dL1, const void* dL2, int cls, int P, int K1, int K2, int ND,
+                    const int32_t* dk1, const int32_t* dk2, float thresh, MatchRow* drows) {
+  using namespace tc;
+  if (!match_tc_supported(cls, K1, K2, ND)) return fail(ctx, PRE3_ERR_ARG, "tensor-core matcher: unsupported shape");
+  if (P <= 0) return PRE3_OK;
+  const int K1p = pad128(K1), K2p = pad128(K2);
+  // carve (1024-byte aligned operand images: TMA bulk copies need 16, the smem tiles 1024)
+  auto take1k = [&](size_t bytes) {
+    ctx->ws_off = align_up(ctx->ws_off, 1024);
+    return ws_take<unsigned char>(ctx, bytes);
+  };
+  unsigned char* imgA = take1k((size_t)P * K1p * ND * 2);
+  unsigned char* imgB = take1k((size_t)P * K2p * ND * 2);
+  float* nrmA = ws_take<float>(ctx, (size_t)P * K1p);
+  float* nrmB = ws_take<float>(ctx, (size_t)P * K2p);
+  Prop* prop = ws_take<Prop>(ctx, (size_t)P * K1p);
+  PairInfo* info = ws_take<PairInfo>(ctx, P);
+  int32_t* list = ws_take<int32_t>(ctx, (size_t)P * K1);
+  int32_t* list_n = ws_take<int32_t>(ctx, 64);
+  PRE3_CUDA(cudaMemsetAsync(info, 0, sizeof(PairInfo) * (size_t)P, ctx->stream));
+  PRE3_CUDA(cudaMemsetAsync(list_n, 0, sizeof(int32_t), ctx->stream));
+  {
+    Span span__(ctx, T_CONVERT);
+    const dim3 g1((K1p + 7) / 8, P), g2((K2p + 7) / 8, P);
+    if (cls == PRE3_CLASS_DOUBLE) {
+      k_tc_convert<double><<<g1, 256, 0, ctx->stream>>>((const double*)dL1, K1, K1p, dk1, 0, imgA, nrmA, info);
+      k_tc_convert<double><<<g2, 256, 0, ctx->stream>>>((const double*)dL2, K2, K2p, dk2, 1, imgB, nrmB, info);
+    } else {
+      k_tc_convert<float><<<g1, 256, 0, ctx->stream>>>((const float*)dL1, K1, K1p, dk1, 0, imgA, nrmA, info);
+      k_tc_convert<float><<<g2, 256, 0, ctx->stream>>>((const float*)dL2, K2, K2p, dk2, 1, imgB, nrmB, info);
+    }
+    count_launch(ctx, 2);
+  }
+  {
+    Span span__(ctx, T_MATCH_TC);
+    static bool attr_set = false;
+    if (!attr_set) {
+      PRE3_CUDA(cudaFuncSetAttribute(k_tc_gemm_top2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      attr_set = true;
+    }
+    const long long units = (long long)P * ((K1p / BLK + 1) / 2);
+    const int grid = (int)std::min<long long>(units, ctx->sm_count);
+    k_tc_gemm_top2<<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(imgA, imgB, nrmB, P, K1p, K2p, prop);
+    count_launch(ctx);
+  }
+  {
+    Span span__(ctx, T_RESCORE);
+    const dim3 g((K1 + RS_WARPS * 32 - 1) / (RS_WARPS * 32), P);
+    if (cls == PRE3_CLASS_DOUBLE)
+      k_tc_rescore<double, double><<<g, RS_WARPS * 32, 0, ctx->stream>>>((const double*)dL1, (const double*)dL2, K1, K2,
+                                                                          K1p, K2p, dk1, dk2, thresh, prop, nrmA, info,
+                                                                          drows, list, list_n);
+    else
+      k_tc_rescore<float, float><<<g, RS_WARPS * 32, 0, ctx->stream>>>((const float*)dL1, (const float*)dL2, K1, K2,
+                                                                        K1p, K2p, dk1, dk2, thresh, prop, nrmA, info,
+                                                                        drows, list, list_n);
+    count_launch(ctx);
+  }
+  PRE3_CUDA(cudaGetLastError());
+  if (getenv("PRE3_DEBUG")) {  // diagnostics only: how many rows fall back to the exact kernel
+    int32_t n = 0;
+    PRE3_CUDA(cudaMemcpyAsync(&n, list_n, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PRE3_CUDA(cudaStreamSynchronize(ctx->stream));
+    fprintf(stderr, "[pre3] tc matcher: P=%d K1=%d K2=%d uncertified rows %d of %lld\n", P, K1, K2, n,
+            (long long)P * K1);
+  }
+  // rows the proposal could not certify: exact brute force, one warp per row
+  return launch_match_rows_exact(ctx, dL1, dL2, cls, K1, K2, ND, dk2, thresh, list, list_n, P * K1, drows);
+}
+
 }  // namespace pre3
