@@ -96,7 +96,7 @@ int ransac_impl(pre3_ctx* ctx, const double* dYa, const double* dYb, const int32
   ransac_carve(ctx, b, o.H);
   PRE3_TRY(ensure_adaptive_table(ctx, o, Nmax));
   PRE3_TRY(launch_prep(ctx, b, o, 0));
-  PRE3_TRY(launch_eval(ctx, b, o, 0));
+  PRE3_TRY(launch_eval_waves(ctx, b, o));
   PRE3_TRY(launch_select(ctx, b, o, dres, dmasks, dcounts, dstates));
   return PRE3_OK;
 }
@@ -614,7 +614,7 @@ int pre3_ransac_block_dev(pre3_ctx* ctx, const double* dYa, const double* dYb, i
   b.pair_id0 = 0;
   ransac_carve(ctx, b, Hloc);
   PRE3_TRY(launch_prep(ctx, b, o, 1));
-  PRE3_TRY(launch_eval(ctx, b, o, h0));
+  PRE3_TRY(launch_eval(ctx, b, o, h0, 0, Hloc, nullptr));
   PRE3_TRY(launch_block_best(ctx, b, o, h0, Hloc, dkey, derrsum));
   return PRE3_OK;
 }

@@ -142,6 +142,7 @@ __global__ void __launch_bounds__(EV_THREADS)
 k_eval(const PairMeta* __restrict__ meta, const double* __restrict__ Ya, const double* __restrict__ Yb,
        const float4* __restrict__ Ya4, const float4* __restrict__ Yb4, int Nmax,
        const int32_t* __restrict__ samples, uint64_t seed, uint32_t pair_id0, long long h0, int H,
+       int hbeg, int hend, const int32_t* __restrict__ stop,
        const double* __restrict__ Rin, const double* __restrict__ Tin, int32_t* __restrict__ counts,
        int8_t* __restrict__ states) {
   __shared__ float4 sA[EV_TILE];
@@ -153,14 +154,16 @@ k_eval(const PairMeta* __restrict__ meta, const double* __restrict__ Ya, const d
 
   const int p = blockIdx.y;
   const int tid = threadIdx.x;
-  const int h = blockIdx.x * EV_THREADS + tid;
+  // the reference's loop already ended inside the sample sets evaluated by earlier waves
+  if (stop && stop[p] >= 0) return;
+  const int h = hbeg + blockIdx.x * EV_THREADS + tid;
   const PairMeta m = meta[p];
   const int N = m.N;
   const double* ya = Ya + (size_t)p * Nmax * 3;
   const double* yb = Yb + (size_t)p * Nmax * 3;
   if (tid == 0) sListN = 0;
 
-  const bool valid = (h < H) && (MODE == 2 || N >= K) && N > 0;
+  const bool valid = (h < hend) && (MODE == 2 || N >= K) && N > 0;
   int state = 0;
   Rigid fit;
 #pragma unroll
@@ -283,10 +286,74 @@ k_eval(const PairMeta* __restrict__ meta, const double* __restrict__ Ya, const d
     }
   }
   __syncthreads();
-  if (h < H) {
+  if (h < hend) {
     counts[(size_t)p * H + h] = sCnt[tid];
     if (states) states[(size_t)p * H + h] = (int8_t)state;
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_stop: one warp per pair.  Replays the reference's loop control (RANSAC_CALC_VER2.m:86,
+// :97-99, :137-140) over the first E evaluated sample sets; if the loop condition fails at some
+// s < E the pair needs no further hypotheses: stop[p] = s (k_select recomputes the same value).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_stop(const PairMeta* __restrict__ meta, const int32_t* __restrict__ counts, const int8_t* __restrict__ states,
+       int P, int H, int E, int method, int max_iteration, const int32_t* __restrict__ tab,
+       int32_t* __restrict__ stop) {
+  const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (p >= P) return;
+  if (stop[p] >= 0) return;
+  const PairMeta m = meta[p];
+  const int N = m.N;
+  const int32_t* cnt = counts + (size_t)p * H;
+  const int8_t* sts = states + (size_t)p * H;
+  const int32_t* trow = tab + m.pad;
+  const int ipt = (E + 31) / 32;
+  const int lo = min(E, lane * ipt), hi = min(E, lo + ipt);
+  int lc = 0, lm = 0;
+  for (int s = lo; s < hi; ++s) {
+    const bool rec = !(method == PRE3_METHOD_SVD && sts[s] == -1);
+    if (rec) {
+      ++lc;
+      lm = max(lm, cnt[s]);
+    }
+  }
+  // exclusive prefix (sum of recorded, max of cardinalities) over the lanes
+  int pc = lc, pm = lm;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const int c = __shfl_up_sync(0xffffffffu, pc, off);
+    const int x = __shfl_up_sync(0xffffffffu, pm, off);
+    if (lane >= off) {
+      pc += c;
+      pm = max(pm, x);
+    }
+  }
+  pc = __shfl_up_sync(0xffffffffu, pc, 1);
+  pm = __shfl_up_sync(0xffffffffu, pm, 1);
+  if (lane == 0) {
+    pc = 0;
+    pm = 0;
+  }
+  int my_stop = 0x7fffffff;
+  for (int s = lo; s < hi; ++s) {
+    int nit = max_iteration;
+    if (pm >= 5) nit = min(trow[min(pm, N)], max_iteration);
+    if (!(1 + pc < nit)) {
+      my_stop = s;
+      break;
+    }
+    const bool rec = !(method == PRE3_METHOD_SVD && sts[s] == -1);
+    if (rec) {
+      ++pc;
+      pm = max(pm, cnt[s]);
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) my_stop = min(my_stop, __shfl_xor_sync(0xffffffffu, my_stop, off));
+  if (lane == 0 && my_stop != 0x7fffffff) stop[p] = my_stop;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -988,6 +1055,7 @@ size_t ransac_workspace_bytes(int P, int Nmax, int H) {
   b += align_up(sizeof(int32_t) * (size_t)P * H);
   b += align_up((size_t)P * H);
   b += align_up((size_t)P * Nmax);  // mask scratch
+  b += align_up(sizeof(int32_t) * (size_t)P);  // stop flags
   return b + 4096;
 }
 
@@ -997,6 +1065,7 @@ void ransac_carve(pre3_ctx* ctx, RansacBuffers& b, int H) {
   b.Yb4 = ws_take<float4>(ctx, (size_t)b.P * b.Nmax);
   b.counts = ws_take<int32_t>(ctx, (size_t)b.P * H);
   b.states = ws_take<int8_t>(ctx, (size_t)b.P * H);
+  b.stop = ws_take<int32_t>(ctx, b.P);
 }
 
 int ensure_adaptive_table(pre3_ctx* ctx, const pre3_ransac_opts& o, int Nmax) {
@@ -1051,13 +1120,14 @@ int launch_prep(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts& o
 
 template <int MODE>
 static int launch_eval_mode(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts& o, long long h0, int H,
-                            const double* Rin, const double* Tin) {
+                            int hbeg, int hend, const int32_t* stop, const double* Rin, const double* Tin) {
   Span span__(ctx, T_EVAL);
-  dim3 grid((H + EV_THREADS - 1) / EV_THREADS, b.P);
+  if (hend <= hbeg) return PRE3_OK;
+  dim3 grid((hend - hbeg + EV_THREADS - 1) / EV_THREADS, b.P);
 #define PRE3_EVAL(KK)                                                                                    \
   k_eval<KK, MODE><<<grid, EV_THREADS, 0, ctx->stream>>>(b.meta, b.Ya, b.Yb, b.Ya4, b.Yb4, b.Nmax,       \
-                                                         b.samples, o.seed, b.pair_id0, h0, H, Rin, Tin, \
-                                                         b.counts, b.states)
+                                                         b.samples, o.seed, b.pair_id0, h0, H, hbeg,     \
+                                                         hend, stop, Rin, Tin, b.counts, b.states)
   if (MODE == 2) {
     PRE3_EVAL(1);
   } else {
@@ -1077,11 +1147,41 @@ static int launch_eval_mode(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ra
   return PRE3_OK;
 }
 
-int launch_eval(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts& o, long long h0) {
+int launch_eval(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts& o, long long h0, int hbeg, int hend,
+                const int32_t* stop) {
   if (b.P <= 0 || o.H <= 0) return PRE3_OK;
-  if (o.method == PRE3_METHOD_SVD) return launch_eval_mode<0>(ctx, b, o, h0, o.H, nullptr, nullptr);
-  if (o.method == PRE3_METHOD_HORN) return launch_eval_mode<1>(ctx, b, o, h0, o.H, nullptr, nullptr);
+  if (o.method == PRE3_METHOD_SVD) return launch_eval_mode<0>(ctx, b, o, h0, o.H, hbeg, hend, stop, nullptr, nullptr);
+  if (o.method == PRE3_METHOD_HORN) return launch_eval_mode<1>(ctx, b, o, h0, o.H, hbeg, hend, stop, nullptr, nullptr);
   return fail(ctx, PRE3_ERR_ARG, "unknown RANSAC method");
+}
+
+// Hypothesis evaluation in waves when the reference's adaptive stop is on: after each wave a
+// scan decides per pair whether its loop has already ended (typically within the first 256
+// sample sets at SR4000 inlier ratios); later waves skip those pairs.  Entries that are never
+// evaluated stay zeroed and lie beyond the stop index, so k_select never reads them.
+int launch_eval_waves(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts& o) {
+  if (b.P <= 0 || o.H <= 0) return PRE3_OK;
+  const int H = o.H;
+  if (!o.adaptive || H <= 384) return launch_eval(ctx, b, o, 0, 0, H, nullptr);
+  PRE3_CUDA(cudaMemsetAsync(b.counts, 0, sizeof(int32_t) * (size_t)b.P * H, ctx->stream));
+  PRE3_CUDA(cudaMemsetAsync(b.states, 0, (size_t)b.P * H, ctx->stream));
+  PRE3_CUDA(cudaMemsetAsync(b.stop, 0xFF, sizeof(int32_t) * (size_t)b.P, ctx->stream));
+  int beg = 0, width = 256;
+  while (beg < H) {
+    int end = std::min(H, beg + width);
+    if (H - end < 128) end = H;
+    PRE3_TRY(launch_eval(ctx, b, o, 0, beg, end, b.stop));
+    if (end < H) {
+      Span span__(ctx, T_SELECT);
+      k_stop<<<(b.P + 7) / 8, 256, 0, ctx->stream>>>(b.meta, b.counts, b.states, b.P, H, end, o.method,
+                                                     o.max_iteration, ctx->d_tab, b.stop);
+      count_launch(ctx);
+      PRE3_CUDA(cudaGetLastError());
+    }
+    beg = end;
+    width *= 2;
+  }
+  return PRE3_OK;
 }
 
 int launch_select(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts& o, pre3_pair_result* dres,
@@ -1132,7 +1232,7 @@ int launch_score_given(pre3_ctx* ctx, const double* dR, const double* dT, int H,
   o.k = 5;
   k_prep<<<1, 256, 0, ctx->stream>>>(b.Ya, b.Yb, nullptr, N, o.method, thr, nullptr, 0, b.meta, b.Ya4, b.Yb4);
   count_launch(ctx);
-  PRE3_TRY(launch_eval_mode<2>(ctx, b, o, 0, H, dR, dT));
+  PRE3_TRY(launch_eval_mode<2>(ctx, b, o, 0, H, 0, H, nullptr, dR, dT));
   // ... ErrorSum and masks through the exact fp64 kernel
   if (derrsum || dmask) {
     k_score_exact<<<(H * 32 + 255) / 256, 256, 0, ctx->stream>>>(dR, dT, H, dYa, dYb, N, thr, nullptr, derrsum, dmask);

@@ -24,6 +24,7 @@ struct RansacBuffers {
   float4* Yb4;
   int32_t* counts;       // P x H
   int8_t* states;        // P x H
+  int32_t* stop;         // P: sample sets consumed when the adaptive loop is known to have ended, else -1
   const int32_t* samples;  // P x H x k or nullptr (seeded)
   uint32_t pair_id0;
 };
@@ -34,7 +35,10 @@ void ransac_carve(pre3_ctx* ctx, RansacBuffers& b, int H);
 
 // thr_given != 0: use o.distance_threshold whatever the method (hypothesis-block entry points)
 int launch_prep(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts& o, int thr_given);
-int launch_eval(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts& o, long long h0);
+// sample sets [hbeg, hend) of every pair (global hypothesis id = h0 + index); pairs with stop[p] >= 0 are skipped
+int launch_eval(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts& o, long long h0, int hbeg, int hend,
+                const int32_t* stop);
+int launch_eval_waves(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts& o);
 int launch_select(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts& o, pre3_pair_result* dres,
                   uint8_t* dmasks, int32_t* dcounts_out, int8_t* dstates_out);
 int ensure_adaptive_table(pre3_ctx* ctx, const pre3_ransac_opts& o, int Nmax);
