@@ -86,5 +86,27 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+MEXDIR = os.path.join(HERE, "mex_files")
+
+
+def build_mex(force: bool = False):
+    """Compile the MEX gateways against the declarations-only shim (object files: the real
+    link against libmex / liboctinterp happens on the user's machine)."""
+    outdir = os.path.join(LIBDIR, "mex_obj")
+    os.makedirs(outdir, exist_ok=True)
+    objs = []
+    for f in sorted(os.listdir(MEXDIR)):
+        if not f.endswith(".cpp"):
+            continue
+        src, obj = os.path.join(MEXDIR, f), os.path.join(outdir, f[:-4] + ".o")
+        objs.append(obj)
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > os.path.getmtime(src):
+            continue
+        subprocess.run(["g++", "-O2", "-fPIC", "-Wall", "-c", src, "-o", obj, "-I", os.path.join(MEXDIR, "mex_shim"),
+                        "-I", MEXDIR, "-I", os.path.join(ROOT, "include")], check=True)
+    return objs
+
+
 if __name__ == "__main__":
     print(build_lib(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_mex(force="--force" in sys.argv))

@@ -38,16 +38,21 @@ constexpr int HALF_BYTES = BLK * 128;         // 16 KB
 constexpr int A_BUF_BYTES = 2 * BLK_BYTES;    // two row blocks
 constexpr int NSTAGE = 3;                     // B ring
 constexpr int THREADS = 384;                  // 12 warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-7 / 8-11 epilogue
-constexpr int SMEM_BYTES = 2 * A_BUF_BYTES + NSTAGE * BLK_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int SMEM_BYTES = 2 * A_BUF_BYTES + NSTAGE * BLK_BYTES + 256 /*barriers*/ + 4 * BLK * 4 /*norms*/;
 
+// The epilogue orders  v'(j) = |b_j|^2 + C - 2 a~.b~_j  (C = 1.0625 max_i |a_i|^2 of the pair keeps v' > 0, so
+// float bits order like unsigned integers); the low 7 bits of the key carry the column within the tile.
 struct Prop {      // per L1 row, output of the proposal GEMM
-  float second;    // second smallest of (|b|^2 - 2 a~.b~) over the pair's columns (+inf if < 2 columns)
+  float best;      // smallest v' (low 7 mantissa bits truncated)
+  float second;    // second smallest v' (+inf if < 2 columns)
   int32_t idx;     // argmin column (-1 if none)
 };
 
 struct PairInfo {
+  unsigned amax_bits;  // max |a|^2 (float bits) over the valid rows
   unsigned bmax_bits;  // max |b|^2 (float bits) over the valid columns
   int bad;             // some value is non-finite or too large for fp16
+  int pad;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -100,9 +105,9 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uin
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// 32 lanes x 32 consecutive columns of 32-bit accumulators -> 32 registers per thread
-__device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, float* v) {
-  uint32_t r[32];
+// 32 lanes x 32 consecutive columns of 32-bit accumulators -> 32 registers per thread (asynchronous:
+// the registers are valid after tc_ld_wait on them)
+__device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -113,9 +118,21 @@ __device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, float* v) {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+// waits for every outstanding tcgen05.ld of this thread; the registers are in/out operands so that no
+// use of them can be scheduled above the wait
+__device__ __forceinline__ void tc_ld_wait(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                 "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]),
+                 "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]),
+                 "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 // K-major, 128-byte-swizzled operand tile: 8-row groups are 1024 B apart (SBO), LBO unused (1),
@@ -139,43 +156,72 @@ __device__ __forceinline__ void load4(const float* src, double* v) {
   v[0] = x.x, v[1] = x.y, v[2] = x.z, v[3] = x.w;
 }
 
+constexpr int CV_ROWS = 32;  // rows per block (4 per warp)
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_tc_convert(const T* __restrict__ L, int K, int Kp, const int32_t* __restrict__ kc, int is_b,
              unsigned char* __restrict__ img, float* __restrict__ nrm, PairInfo* __restrict__ info) {
+  __shared__ float s_max[8];
+  __shared__ int s_bad[8];
   const int p = blockIdx.y;
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n = kc ? max(0, min(kc[p], K)) : K;
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= Kp) return;
-  double v[4] = {0, 0, 0, 0};
-  if (row < n) load4(L + ((size_t)p * K + row) * ND + 4 * lane, v);
-  // fp16 image: block rb, K half kh, row r, 16-byte chunk c of the 128-byte row XOR-swizzled with r & 7
-  const int rb = row >> 7, r = row & 127, kh = lane >> 4, c = (lane & 15) >> 1;
-  __half2 h01 = __floats2half2_rn((float)v[0], (float)v[1]);
-  __half2 h23 = __floats2half2_rn((float)v[2], (float)v[3]);
-  uint2 packed;
-  packed.x = *reinterpret_cast<unsigned*>(&h01);
-  packed.y = *reinterpret_cast<unsigned*>(&h23);
-  unsigned char* dst = img + (size_t)p * Kp * (ND * 2) + (size_t)rb * BLK_BYTES + (size_t)kh * HALF_BYTES +
-                       (size_t)r * 128 + (size_t)((c ^ (r & 7)) << 4) + (size_t)((lane & 1) << 3);
-  *reinterpret_cast<uint2*>(dst) = packed;
-  // |x|^2 in fp64 (fixed shuffle tree), range check
-  double s = (v[0] * v[0] + v[1] * v[1]) + (v[2] * v[2] + v[3] * v[3]);
-  bool bad = false;
+  // B norms are stored biased: |b|^2 + C with C = 1.0625 max|a|^2 (set by the A launch before this one)
+  const float bias = is_b ? 1.0625f * __uint_as_float(info[p].amax_bits) : 0.f;
+  float wmax = 0.f;
+  bool wbad = false;
+  double v[CV_ROWS / 8][4];
 #pragma unroll
-  for (int e = 0; e < 4; ++e) bad = bad || !(fabs(v[e]) <= 60000.0);
+  for (int i = 0; i < CV_ROWS / 8; ++i) {  // all loads first
+    const int row = blockIdx.x * CV_ROWS + warp * (CV_ROWS / 8) + i;
+    v[i][0] = v[i][1] = v[i][2] = v[i][3] = 0.0;
+    if (row < n) load4(L + ((size_t)p * K + row) * ND + 4 * lane, v[i]);
+  }
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-  bad = __any_sync(0xffffffffu, bad);
-  if (lane == 0) {
+  for (int i = 0; i < CV_ROWS / 8; ++i) {
+    const int row = blockIdx.x * CV_ROWS + warp * (CV_ROWS / 8) + i;
+    if (row >= Kp) break;
+    // fp16 image: block rb, K half kh, row r, 16-byte chunk c of the 128-byte row XOR-swizzled with r & 7
+    const int rb = row >> 7, r = row & 127, kh = lane >> 4, c = (lane & 15) >> 1;
+    __half2 h01 = __floats2half2_rn((float)v[i][0], (float)v[i][1]);
+    __half2 h23 = __floats2half2_rn((float)v[i][2], (float)v[i][3]);
+    uint2 packed;
+    packed.x = *reinterpret_cast<unsigned*>(&h01);
+    packed.y = *reinterpret_cast<unsigned*>(&h23);
+    unsigned char* dst = img + (size_t)p * Kp * (ND * 2) + (size_t)rb * BLK_BYTES + (size_t)kh * HALF_BYTES +
+                         (size_t)r * 128 + (size_t)((c ^ (r & 7)) << 4) + (size_t)((lane & 1) << 3);
+    *reinterpret_cast<uint2*>(dst) = packed;
+    // |x|^2 in fp64 (fixed shuffle tree), range check
+    double s = (v[i][0] * v[i][0] + v[i][1] * v[i][1]) + (v[i][2] * v[i][2] + v[i][3] * v[i][3]);
+    bool bad = false;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) bad = bad || !(fabs(v[i][e]) <= 60000.0);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    bad = __any_sync(0xffffffffu, bad);
     float f = __double2float_ru(s);
-    if (row >= n) f = is_b ? INFINITY : 0.f;  // padded columns can never win
-    nrm[(size_t)p * Kp + row] = f;
     if (row < n) {
-      if (is_b) atomicMax(&info[p].bmax_bits, __float_as_uint(f));
-      if (bad) atomicOr(&info[p].bad, 1);
+      wmax = fmaxf(wmax, f);
+      wbad = wbad || bad;
     }
+    if (lane == 0)  // padded columns can never win
+      nrm[(size_t)p * Kp + row] = (row < n) ? (is_b ? f + bias : f) : (is_b ? INFINITY : 0.f);
+  }
+  if (lane == 0) {
+    s_max[warp] = wmax;
+    s_bad[warp] = wbad ? 1 : 0;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float mx = 0.f;
+    int bd = 0;
+    for (int w = 0; w < 8; ++w) {
+      mx = fmaxf(mx, s_max[w]);
+      bd |= s_bad[w];
+    }
+    if (mx > 0.f) atomicMax(is_b ? &info[p].bmax_bits : &info[p].amax_bits, __float_as_uint(mx));
+    if (bd) atomicOr(&info[p].bad, 1);
   }
 }
 
@@ -192,13 +238,14 @@ struct Barriers {
 __global__ void __launch_bounds__(THREADS, 1)
 k_tc_gemm_top2(const unsigned char* __restrict__ imgA, const unsigned char* __restrict__ imgB,
                const float* __restrict__ nrmB, int P, int K1p, int K2p, Prop* __restrict__ prop) {
-  extern __shared__ unsigned char smem_raw[];
-  const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
-  unsigned char* smem = smem_raw + (base - raw);
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const uint32_t base = smem_u32(smem);
+  if (base & 1023u) __trap();  // SWIZZLE_128B tiles need 1024-byte alignment
   const uint32_t sA = base;                                  // 2 buffers x 64 KB
   const uint32_t sB = base + 2 * A_BUF_BYTES;                // NSTAGE x 32 KB
   Barriers* bars = reinterpret_cast<Barriers*>(smem + 2 * A_BUF_BYTES + NSTAGE * BLK_BYTES);
+  // [row block][set][128] biased column norms of the tile in flight
+  float* sNB = reinterpret_cast<float*>(smem + 2 * A_BUF_BYTES + NSTAGE * BLK_BYTES + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int groups = (K1p / BLK + 1) / 2;  // row groups (<= 2 row blocks each) per pair
@@ -302,44 +349,57 @@ k_tc_gemm_top2(const unsigned char* __restrict__ imgA, const unsigned char* __re
         t += ntile;
         continue;
       }
-      float best = INFINITY, second = INFINITY;
-      int btile = -1, bcol = 0;
+      uint32_t m1 = 0xFFFFFFFFu, m2 = 0xFFFFFFFFu;  // two smallest packed keys of this row
+      uint32_t keymask;
+      asm volatile("mov.u32 %0, 0xFFFFFF80;" : "=r"(keymask));
+      int btile = -1;
       const float* nb = nrmB + (size_t)p * K2p;
+      const int wtid = threadIdx.x - (4 + 4 * rb) * 32;  // 0..127 within the warpgroup
       for (int j = 0; j < ntile; ++j, ++t) {
         const int set = (int)(t & 1);
         const int slot = set * 2 + rb;
+        // stage the tile's (biased) column norms for broadcast reads; the global load overlaps the MMA
+        float* snb = sNB + (rb * 2 + set) * BLK;
+        snb[wtid] = __ldg(nb + (size_t)j * BLK + wtid);
+        named_bar_sync(1 + rb, 128);
         uint32_t& use = set == 0 ? useA : useB;
         mbar_wait(smem_u32(&bars->t_full[slot]), use & 1);
         ++use;
         tc_fence_after();
-        const float best_in = best;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BLK; c0 += 32) {
-          float acc[32];
-          tc_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * BLK + c0), acc);
-          const float4* nb4 = reinterpret_cast<const float4*>(nb + (size_t)j * BLK + c0);
+        const uint32_t m1_in = m1;
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * BLK);
+        uint32_t buf[2][32];
+        tc_ld_32x32(taddr, buf[0]);
+#pragma unroll
+        for (int c = 0; c < BLK / 32; ++c) {
+          tc_ld_wait(buf[c & 1]);
+          if (c + 1 < BLK / 32) tc_ld_32x32(taddr + (uint32_t)((c + 1) * 32), buf[(c + 1) & 1]);
+          const float4* nb4 = reinterpret_cast<const float4*>(snb + c * 32);
 #pragma unroll
           for (int i4 = 0; i4 < 8; ++i4) {
-            const float4 n4 = __ldg(nb4 + i4);
+            const float4 n4 = nb4[i4];
             const float nn[4] = {n4.x, n4.y, n4.z, n4.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const float v = fmaf(-2.0f, acc[4 * i4 + e], nn[e]);
-              const bool lt = v < best;
-              second = lt ? best : fminf(second, v);
-              bcol = lt ? (c0 + 4 * i4 + e) : bcol;
-              best = fminf(best, v);
+              const float v = fmaf(-2.0f, __uint_as_float(buf[c & 1][4 * i4 + e]), nn[e]);
+              uint32_t key;  // (bits & ~127) | column: one LOP3 (mask kept in a register)
+              asm("lop3.b32 %0, %1, %2, %3, 0xEA;"
+                  : "=r"(key)
+                  : "r"(__float_as_uint(v)), "r"(keymask), "r"((uint32_t)(c * 32 + 4 * i4 + e)));
+              m2 = min(m2, max(key, m1));
+              m1 = min(m1, key);
             }
           }
         }
-        if (best < best_in) btile = j;
+        if (m1 != m1_in) btile = j;
         tc_fence_before();
         mbar_arrive(smem_u32(&bars->t_empty[slot]));
       }
       const int row = (g * 2 + rb) * BLK + q * 32 + lane;
       Prop o;
-      o.second = second;
-      o.idx = btile < 0 ? -1 : btile * BLK + bcol;
+      o.best = __uint_as_float(m1 & 0xFFFFFF80u);
+      o.second = __uint_as_float(m2 & 0xFFFFFF80u);
+      o.idx = btile < 0 ? -1 : btile * BLK + (int)(m1 & 0x7Fu);
       prop[(size_t)p * K1p + row] = o;
     }
   }
@@ -356,66 +416,112 @@ k_tc_gemm_top2(const unsigned char* __restrict__ imgA, const unsigned char* __re
 // rows at a time: coalesced loads of the row and of its candidate column, delta*delta per
 // element into shared memory, then lane r sums row r strictly in bin order.
 // ---------------------------------------------------------------------------------------------
-constexpr int RS_WARPS = 1;  // 32 x 129 products of the accumulation type = 33 KB (double)
+constexpr int RS_ROWS = 16;  // rows per warp pass: 16 x 129 products of the accumulation type = 16.5 KB (double)
 
 template <typename T, typename ACC>
-__global__ void __launch_bounds__(RS_WARPS * 32)
+__device__ __forceinline__ void load_row4(const T* src, ACC* v);
+template <>
+__device__ __forceinline__ void load_row4<double, double>(const double* src, double* v) {
+  const double2 x = __ldg(reinterpret_cast<const double2*>(src));
+  const double2 y = __ldg(reinterpret_cast<const double2*>(src) + 1);
+  v[0] = x.x, v[1] = x.y, v[2] = y.x, v[3] = y.y;
+}
+template <>
+__device__ __forceinline__ void load_row4<float, float>(const float* src, float* v) {
+  const float4 x = __ldg(reinterpret_cast<const float4*>(src));
+  v[0] = x.x, v[1] = x.y, v[2] = x.z, v[3] = x.w;
+}
+
+template <typename T, typename ACC>
+__global__ void __launch_bounds__(32)
 k_tc_rescore(const T* __restrict__ L1, const T* __restrict__ L2, int K1, int K2, int K1p, int K2p,
              const int32_t* __restrict__ k1c, const int32_t* __restrict__ k2c, float thresh,
              const Prop* __restrict__ prop, const float* __restrict__ nrmA, const PairInfo* __restrict__ info,
              MatchRow* __restrict__ rows, int32_t* __restrict__ row_list, int32_t* __restrict__ row_list_n) {
-  __shared__ ACC sprod[RS_WARPS][32][ND + 1];
+  __shared__ ACC sprod[RS_ROWS][ND + 1];
   const int p = blockIdx.y;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31;
   const int n1 = k1c ? max(0, min(k1c[p], K1)) : K1;
   const int n2 = k2c ? max(0, min(k2c[p], K2)) : K2;
-  const int row0 = (blockIdx.x * RS_WARPS + warp) * 32;
+  const int row0 = blockIdx.x * RS_ROWS;
   if (row0 >= n1) return;
   const PairInfo pi = info[p];
-  const int nr = min(32, n1 - row0);
-  // candidate of "my" row (lane r <-> row row0 + r)
-  Prop my;
-  my.second = INFINITY;
-  my.idx = -1;
-  if (lane < nr) my = prop[(size_t)p * K1p + row0 + lane];
-#pragma unroll 4
-  for (int r = 0; r < nr; ++r) {
-    const int idx = __shfl_sync(0xffffffffu, my.idx, r);
-    if (idx < 0 || idx >= n2) continue;
-    const T* a = L1 + ((size_t)p * K1 + row0 + r) * ND + 4 * lane;
-    const T* b = L2 + ((size_t)p * K2 + idx) * ND + 4 * lane;
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const ACC d = (ACC)a[e] - (ACC)b[e];
-      sprod[warp][r][4 * lane + e] = d * d;
-    }
-  }
-  __syncwarp();
-  if (lane >= nr) return;
+  const int nr = min(RS_ROWS, n1 - row0);
   const int k1 = row0 + lane;
+  const bool mine = lane < nr;
+
+  // ---- what the approximate keys already decide ------------------------------------------------
+  // v'(j) = d2~(j) + C - |a|^2; |d2~(j) - d2(j)| <= m for every column j of the pair:
+  // fp16 rounding of both operands (2^-11 relative each, 2^-25 absolute below the normal range), fp32
+  // accumulation of 128 products, fp32 norms / bias / epilogue, the 7 truncated key bits, the
+  // reference's own rounding when it accumulates in float; 25 % slack on top.
+  Prop my;
+  my.best = my.second = INFINITY;
+  my.idx = -1;
+  double na = 0.0, m = 0.0, C = 0.0;
+  bool ambiguous = false, need_exact = false;
   MatchRow out;
   out.best = INFINITY;
   out.bestk = -1;
   out.accept = 0;
-  bool ambiguous = false;
-  if (n2 <= 0) {
-    // no column: bestk = -1 -> never accepted (siftmatch.c:123)
-  } else if (pi.bad || my.idx < 0 || my.idx >= n2 || !(thresh > 0.f)) {
-    ambiguous = true;
-  } else {
-    ACC acc = 0;
-    for (int bin = 0; bin < ND; ++bin) acc += sprod[warp][lane][bin];  // strictly in order (siftmatch.c:101-107)
-    const double d1 = (double)acc;
-    // certified margin on |(|b|^2 - 2 a~.b~ + |a|^2) - d2_exact| for every column of the pair:
-    // fp16 rounding of both operands (2^-11 relative each, 2^-25 absolute below the normal
-    // range), fp32 accumulation of 128 products, fp32 norms and epilogue, with 25 % slack.
-    const double na = (double)nrmA[(size_t)p * K1p + k1];
+  if (mine && n2 > 0) {
+    my = prop[(size_t)p * K1p + k1];
+    na = (double)nrmA[(size_t)p * K1p + k1];
     const double nbm = (double)__uint_as_float(pi.bmax_bits);
+    C = (double)(1.0625f * __uint_as_float(pi.amax_bits));
     const double ra = sqrt(na), rbm = sqrt(nbm);
-    // (na + nbm) / 32768 also covers the reference's own rounding when it accumulates in float.
-    const double m = 1.25 * ((1.0 / 512 + 1.0 / 16384) * ra * rbm + (na + nbm) * (1.0 / 32768) +
-                             (ra + rbm) * (1.0 / 1048576));
-    const double s2 = (double)my.second + na;
+    m = 1.25 * ((1.0 / 512 + 1.0 / 16384) * ra * rbm + (na + nbm + C) * (1.0 / 16384) + (ra + rbm) * (1.0 / 1048576));
+    if (pi.bad || my.idx < 0 || my.idx >= n2 || !(thresh > 0.f) || !(C - na > m) || !(my.best < INFINITY)) {
+      ambiguous = true;  // keys may be meaningless (range, sign) -> exact kernel
+    } else {
+      const double L1b = ((double)my.best - C + na) - m;  // exact best  >= L1b
+      const double U2b = ((double)my.second - C + na) + m;  // exact second_best <= U2b
+      if (L1b > 0.0 && __fmul_rn(thresh, (float)L1b) > (float)U2b)
+        out.accept = 0;  // ratio test fails for sure (siftmatch.c:122): row never output
+      else
+        need_exact = true;
+    }
+  }
+
+  // ---- exact distance to the candidate for the rows that may be accepted -------------------------
+  unsigned todo = __ballot_sync(0xffffffffu, need_exact);
+  while (todo) {
+    int rr[4], ii[4];
+    ACC va[4][4], vb[4][4];
+    int cnt = 0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      rr[u] = -1;
+      ii[u] = 0;
+      if (todo) {
+        rr[u] = __ffs(todo) - 1;
+        todo &= todo - 1;
+        ++cnt;
+      }
+      if (rr[u] >= 0) ii[u] = __shfl_sync(0xffffffffu, my.idx, rr[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)  // all loads of up to four rows in flight together
+      if (rr[u] >= 0) {
+        load_row4<T, ACC>(L1 + ((size_t)p * K1 + row0 + rr[u]) * ND + 4 * lane, va[u]);
+        load_row4<T, ACC>(L2 + ((size_t)p * K2 + ii[u]) * ND + 4 * lane, vb[u]);
+      }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (rr[u] >= 0) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const ACC d = va[u][e] - vb[u][e];
+          sprod[rr[u]][4 * lane + e] = d * d;
+        }
+      }
+  }
+  __syncwarp();
+  if (need_exact) {
+    ACC acc = 0;
+    for (int bin = 0; bin < ND; ++bin) acc += sprod[lane][bin];  // strictly in order (siftmatch.c:101-107)
+    const double d1 = (double)acc;
+    const double s2 = (double)my.second - C + na;
     const double L2b = s2 - m, U2b = s2 + m;  // every other column's exact distance is >= L2b; one is <= U2b
     if (d1 < L2b) {
       // unique exact minimum: best = d1, bestk = idx; second_best in [L2b, U2b]
@@ -432,11 +538,12 @@ k_tc_rescore(const T* __restrict__ L1, const T* __restrict__ L2, int K1, int K2,
       // best >= L2b, second_best <= max(d1, U2b): rejected for sure when even that fails the test
       const double hi = d1 > U2b ? d1 : U2b;
       if (L2b > 0.0 && __fmul_rn(thresh, (float)L2b) > (float)hi)
-        out.accept = 0;  // rejected rows are never output: best / bestk irrelevant
+        out.accept = 0;
       else
         ambiguous = true;
     }
   }
+  if (!mine) return;
   if (ambiguous) {
     const int slot = atomicAdd(row_list_n, 1);
     row_list[slot] = p * K1 + k1;
@@ -490,7 +597,7 @@ int launch_match_tc(pre3_ctx* ctx, const void* dL1, const void* dL2, int cls, in
   PRE3_CUDA(cudaMemsetAsync(list_n, 0, sizeof(int32_t), ctx->stream));
   {
     Span span__(ctx, T_CONVERT);
-    const dim3 g1((K1p + 7) / 8, P), g2((K2p + 7) / 8, P);
+    const dim3 g1(K1p / CV_ROWS, P), g2(K2p / CV_ROWS, P);
     if (cls == PRE3_CLASS_DOUBLE) {
       k_tc_convert<double><<<g1, 256, 0, ctx->stream>>>((const double*)dL1, K1, K1p, dk1, 0, imgA, nrmA, info);
       k_tc_convert<double><<<g2, 256, 0, ctx->stream>>>((const double*)dL2, K2, K2p, dk2, 1, imgB, nrmB, info);
@@ -514,13 +621,13 @@ int launch_match_tc(pre3_ctx* ctx, const void* dL1, const void* dL2, int cls, in
   }
   {
     Span span__(ctx, T_RESCORE);
-    const dim3 g((K1 + RS_WARPS * 32 - 1) / (RS_WARPS * 32), P);
+    const dim3 g((K1 + RS_ROWS - 1) / RS_ROWS, P);
     if (cls == PRE3_CLASS_DOUBLE)
-      k_tc_rescore<double, double><<<g, RS_WARPS * 32, 0, ctx->stream>>>((const double*)dL1, (const double*)dL2, K1, K2,
+      k_tc_rescore<double, double><<<g, 32, 0, ctx->stream>>>((const double*)dL1, (const double*)dL2, K1, K2,
                                                                           K1p, K2p, dk1, dk2, thresh, prop, nrmA, info,
                                                                           drows, list, list_n);
     else
-      k_tc_rescore<float, float><<<g, RS_WARPS * 32, 0, ctx->stream>>>((const float*)dL1, (const float*)dL2, K1, K2,
+      k_tc_rescore<float, float><<<g, 32, 0, ctx->stream>>>((const float*)dL1, (const float*)dL2, K1, K2,
                                                                         K1p, K2p, dk1, dk2, thresh, prop, nrmA, info,
                                                                         drows, list, list_n);
     count_launch(ctx);

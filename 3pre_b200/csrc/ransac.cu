@@ -759,6 +759,301 @@ k_select(const PairMeta* __restrict__ meta, const double* __restrict__ Ya, const
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// k_select_warp: the same selection as k_select with ONE WARP per pair (no block barriers), used
+// for batches of pairs.  Differences are confined to the order of the refit sums (per-lane
+// strided partial sums, then a fixed xor-butterfly), i.e. to rounding of R, T at the 1e-16 level.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v = v + __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+
+// sequential (index-order) sum of the residual norms of the inliers of (R,t): ErrorSum of
+// RANSAC_CALC_VER2.m:135; also writes the mask when asked.  Every lane returns the sum.
+__device__ __forceinline__ double warp_errsum(const double* R, const double* t, const double* ya, const double* yb,
+                                              int N, double thr, uint8_t* mask, int* count_out) {
+  const int lane = threadIdx.x & 31;
+  double es = 0.0;
+  int c = 0;
+  for (int ib = 0; ib < N; ib += 32) {
+    const int i = ib + lane;
+    double nr = 0.0;
+    bool in = false;
+    if (i < N) {
+      nr = residual_norm(R, t, ya + 3 * i, yb + 3 * i);
+      in = nr < thr;
+      if (mask) mask[i] = in ? 1 : 0;
+    }
+    unsigned inb = __ballot_sync(0xffffffffu, in);
+    c += __popc(inb);
+    while (inb) {
+      const int li = __ffs(inb) - 1;
+      inb &= inb - 1;
+      es = es + __shfl_sync(0xffffffffu, nr, li);
+    }
+  }
+  if (count_out) *count_out = c;
+  return es;
+}
+
+__device__ __forceinline__ int warp_refit(int method, const double* ya, const double* yb, const uint8_t* mask, int N,
+                                          Rigid& out) {
+  const int lane = threadIdx.x & 31;
+  double c1[3] = {0, 0, 0}, c2[3] = {0, 0, 0};
+  double ns = 0.0;
+  for (int i = lane; i < N; i += 32)
+    if (mask[i]) {
+      ns += 1.0;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        c1[r] += ya[3 * i + r];
+        c2[r] += yb[3 * i + r];
+      }
+    }
+  ns = warp_sum(ns);
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    c1[r] = warp_sum(c1[r]) / ns;
+    c2[r] = warp_sum(c2[r]) / ns;
+  }
+  if (method == PRE3_METHOD_SVD) {
+    double H[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = lane; i < N; i += 32)
+      if (mask[i]) {
+        double q1[3], q2[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          q1[r] = ya[3 * i + r] - c1[r];
+          q2[r] = yb[3 * i + r] - c2[r];
+        }
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) H[3 * r + c] = H[3 * r + c] + q2[r] * q1[c];
+      }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) H[i] = warp_sum(H[i]);
+    return kabsch_from_H(H, c1, c2, out);  // every lane computes the same result
+  } else {
+    double M[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) M[i] = 0.0;
+    for (int i = lane; i < N; i += 32)
+      if (mask[i]) {
+        double an[3], bn[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          an[r] = yb[3 * i + r] - c2[r];
+          bn[r] = ya[3 * i + r] - c1[r];
+        }
+        horn_accumulate(M, an, bn);
+      }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) M[i] = warp_sum(M[i]);
+    horn_from_M(M, c2, c1, out);
+    return 1;
+  }
+}
+
+constexpr int SELW_WARPS = 4;
+
+__global__ void __launch_bounds__(SELW_WARPS * 32)
+k_select_warp(const PairMeta* __restrict__ meta, const double* __restrict__ Ya, const double* __restrict__ Yb,
+              int P, int Nmax, const int32_t* __restrict__ samples, uint64_t seed, uint32_t pair_id0, int H, int k,
+              int method, int max_iteration, int adaptive, const int32_t* __restrict__ tab,
+              const int32_t* __restrict__ counts, const int8_t* __restrict__ states,
+              pre3_pair_result* __restrict__ res, uint8_t* __restrict__ masks, int mask_stride,
+              uint8_t* __restrict__ mask_scratch, int32_t* __restrict__ counts_out, int8_t* __restrict__ states_out) {
+  const int p = blockIdx.x * SELW_WARPS + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (p >= P) return;
+  const PairMeta m = meta[p];
+  const int N = m.N;
+  const double* ya = Ya + (size_t)p * Nmax * 3;
+  const double* yb = Yb + (size_t)p * Nmax * 3;
+  const int32_t* cnt = counts + (size_t)p * H;
+  const int8_t* sts = states + (size_t)p * H;
+  uint8_t* mask = masks ? masks + (size_t)p * mask_stride : mask_scratch + (size_t)p * Nmax;
+  pre3_pair_result* out = res + p;
+  auto init_out = [&](int status, int n_consumed) {
+    if (lane == 0) {
+      out->status = status;
+      out->state = 0;
+      out->best_fit = 0;
+      out->best_sample = -1;
+      out->best_iter = 0;
+      out->n_iter = 0;
+      out->n_consumed = n_consumed;
+      out->n_matches = N;
+      out->thr = m.thr;
+      out->error_sum = 0.0;
+      for (int i = 0; i < 9; ++i) out->R[i] = out->R_hyp[i] = 0.0;
+      for (int i = 0; i < 3; ++i) out->T[i] = out->T_hyp[i] = 0.0;
+    }
+  };
+  if (N < k || N <= 0) {  // get_rand(k, N) errors in the reference (get_rand.m:39-41)
+    init_out(1, 0);
+    for (int i = lane; i < H; i += 32) {
+      if (counts_out) counts_out[(size_t)p * H + i] = -1;
+      if (states_out) states_out[(size_t)p * H + i] = 0;
+    }
+    if (masks)
+      for (int i = lane; i < mask_stride; i += 32) mask[i] = 0;
+    return;
+  }
+  const int32_t* trow = tab ? tab + m.pad : nullptr;
+  auto recorded = [&](int s) { return !(method == PRE3_METHOD_SVD && sts[s] == -1); };
+
+  // ---- 1. loop control as a prefix scan (RANSAC_CALC_VER2.m:86, :97-99, :137-140) -----------
+  int S_end = H;
+  {
+    const int ipt = (H + 31) / 32;
+    const int lo = min(H, lane * ipt), hi = min(H, lo + ipt);
+    int lc = 0, lm = 0;
+    for (int s = lo; s < hi; ++s)
+      if (recorded(s)) {
+        ++lc;
+        lm = max(lm, cnt[s]);
+      }
+    int pc = lc, pm = lm;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int c = __shfl_up_sync(0xffffffffu, pc, off);
+      const int x = __shfl_up_sync(0xffffffffu, pm, off);
+      if (lane >= off) {
+        pc += c;
+        pm = max(pm, x);
+      }
+    }
+    pc = __shfl_up_sync(0xffffffffu, pc, 1);
+    pm = __shfl_up_sync(0xffffffffu, pm, 1);
+    if (lane == 0) {
+      pc = 0;
+      pm = 0;
+    }
+    int my_stop = H;
+    for (int s = lo; s < hi; ++s) {
+      int nit = max_iteration;
+      if (adaptive && pm >= 5) nit = min(trow[min(pm, N)], max_iteration);
+      if (!(1 + pc < nit)) {
+        my_stop = s;
+        break;
+      }
+      if (recorded(s)) {
+        ++pc;
+        pm = max(pm, cnt[s]);
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) my_stop = min(my_stop, __shfl_xor_sync(0xffffffffu, my_stop, off));
+    S_end = my_stop;
+  }
+
+  // ---- 2. max cardinality, number recorded ---------------------------------------------------
+  int maxc = -1, n_iter = 0;
+  for (int s = lane; s < S_end; s += 32)
+    if (recorded(s)) {
+      maxc = max(maxc, cnt[s]);
+      ++n_iter;
+    }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    maxc = max(maxc, __shfl_xor_sync(0xffffffffu, maxc, off));
+    n_iter += __shfl_xor_sync(0xffffffffu, n_iter, off);
+  }
+  if (counts_out || states_out)
+    for (int s = lane; s < H; s += 32) {
+      const bool consumed = s < S_end;
+      const bool rec = consumed && recorded(s);
+      if (counts_out) counts_out[(size_t)p * H + s] = rec ? cnt[s] : -1;
+      if (states_out) states_out[(size_t)p * H + s] = consumed ? sts[s] : (int8_t)0;
+    }
+  if (n_iter < 1) {  // nothing recorded: M(1).ErrorSum = [] in the reference -> error
+    init_out(2, S_end);
+    if (masks)
+      for (int i = lane; i < mask_stride; i += 32) mask[i] = 0;
+    return;
+  }
+
+  // ---- 3. selection :165-175: among max-cardinality hypotheses min ErrorSum, first on ties;
+  //         every other recorded hypothesis enters the min() with 10000 ------------------------
+  double best_es = INFINITY;
+  int best_s = 0x7fffffff, first_nonmax = 0x7fffffff, win_iter = 0;
+  {
+    int rec_before = 0;  // recorded hypotheses before the current 32-chunk
+    for (int sbase = 0; sbase < S_end; sbase += 32) {
+      const int s = sbase + lane;
+      const bool rec = s < S_end && recorded(s);
+      const bool is_tie = rec && maxc > 0 && cnt[s] == maxc;
+      const bool nonmax = rec && !is_tie;
+      const unsigned recb = __ballot_sync(0xffffffffu, rec);
+      unsigned tieb = __ballot_sync(0xffffffffu, is_tie);
+      const unsigned nmb = __ballot_sync(0xffffffffu, nonmax);
+      if (nmb && first_nonmax == 0x7fffffff) first_nonmax = sbase + __ffs(nmb) - 1;
+      while (tieb) {
+        const int l = __ffs(tieb) - 1;
+        tieb &= tieb - 1;
+        const int st = sbase + l;
+        int idx[MAX_K];
+        load_sample(samples, seed, pair_id0 + (uint32_t)p, 0, st, H, p, N, k, idx);
+        Rigid f;
+        fit_sample(method, ya, yb, idx, k, f);  // every lane computes the same fit
+        const double es = warp_errsum(f.R, f.t, ya, yb, N, m.thr, nullptr, nullptr);
+        if (es < best_es) {  // strict: first index wins ties
+          best_es = es;
+          best_s = st;
+          win_iter = rec_before + __popc(recb & ((2u << l) - 1u));
+        }
+      }
+      rec_before += __popc(recb);
+    }
+  }
+  int win = best_s;
+  if (best_s == 0x7fffffff) {
+    win = first_nonmax;  // maxc == 0: every entry is 10000 -> I = first recorded
+  } else if (first_nonmax != 0x7fffffff && (10000.0 < best_es || (10000.0 == best_es && first_nonmax < best_s))) {
+    win = first_nonmax;
+  }
+  if (win != best_s) {  // BestFitIdx of a non-tie winner: recorded hypotheses up to and including it
+    int c = 0;
+    for (int s = lane; s <= win; s += 32) c += recorded(s) ? 1 : 0;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+    win_iter = c;
+  }
+
+  // ---- 4. winner: hypothesis, mask, ErrorSum; 5. refit on the support set (:186) --------------
+  int idx[MAX_K];
+  load_sample(samples, seed, pair_id0 + (uint32_t)p, 0, win, H, p, N, k, idx);
+  Rigid f;
+  fit_sample(method, ya, yb, idx, k, f);
+  const double es = warp_errsum(f.R, f.t, ya, yb, N, m.thr, mask, nullptr);
+  if (masks)
+    for (int i = N + lane; i < mask_stride; i += 32) mask[i] = 0;
+  __syncwarp();
+  Rigid rf;
+  const int st = warp_refit(method, ya, yb, mask, N, rf);
+  if (lane == 0) {
+    out->status = 0;
+    out->state = st;
+    out->best_fit = maxc;
+    out->best_sample = win;
+    out->best_iter = win_iter;
+    out->n_iter = n_iter;
+    out->n_consumed = S_end;
+    out->n_matches = N;
+    out->thr = m.thr;
+    out->error_sum = es;
+    store_colmajor(out->R, rf.R);
+    for (int i = 0; i < 3; ++i) out->T[i] = rf.t[i];
+    store_colmajor(out->R_hyp, f.R);
+    for (int i = 0; i < 3; ++i) out->T_hyp[i] = f.t[i];
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // stage-wise kernels
 // ------------------------------------------------------------------------------------------
@@ -1189,10 +1484,16 @@ int launch_select(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts&
   Span span__(ctx, T_SELECT);
   if (b.P <= 0) return PRE3_OK;
   uint8_t* scratch = ws_take<uint8_t>(ctx, (size_t)b.P * b.Nmax);
-  k_select<<<b.P, SEL_THREADS, 0, ctx->stream>>>(b.meta, b.Ya, b.Yb, b.Nmax, b.samples, o.seed, b.pair_id0, 0, o.H,
-                                                 o.k, o.method, o.max_iteration, o.adaptive,
-                                                 o.adaptive ? ctx->d_tab : nullptr, b.counts, b.states, dres,
-                                                 dmasks, b.Nmax, scratch, dcounts_out, dstates_out);
+  if (b.P >= 32 && b.Nmax <= 4096)  // batches of pairs: one warp per pair; single big pairs: one block
+    k_select_warp<<<(b.P + SELW_WARPS - 1) / SELW_WARPS, SELW_WARPS * 32, 0, ctx->stream>>>(
+        b.meta, b.Ya, b.Yb, b.P, b.Nmax, b.samples, o.seed, b.pair_id0, o.H, o.k, o.method, o.max_iteration,
+        o.adaptive, o.adaptive ? ctx->d_tab : nullptr, b.counts, b.states, dres, dmasks, b.Nmax, scratch, dcounts_out,
+        dstates_out);
+  else
+    k_select<<<b.P, SEL_THREADS, 0, ctx->stream>>>(b.meta, b.Ya, b.Yb, b.Nmax, b.samples, o.seed, b.pair_id0, 0, o.H,
+                                                   o.k, o.method, o.max_iteration, o.adaptive,
+                                                   o.adaptive ? ctx->d_tab : nullptr, b.counts, b.states, dres,
+                                                   dmasks, b.Nmax, scratch, dcounts_out, dstates_out);
   count_launch(ctx);
   PRE3_CUDA(cudaGetLastError());
   return PRE3_OK;

@@ -297,6 +297,13 @@ def run_ours(args):
                                         "frac": None, "traffic": None}))
     roofline["kernel"] = dom
 
+    if args.profile:
+        if rank == 0:
+            print(json.dumps({"profile_run": True, "value": value, "ms_per_step": ms_step, "kernels": per_kernel,
+                              "roofline": roofline, "gpu_launches": int(launches)}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     # ---- e2e: host buffers through pre3_pairs ---------------------------------------------
     Pe = min(P, args.e2e_pairs)
     host = {k: torch.empty(data[k][:Pe].shape, dtype=data[k].dtype, pin_memory=True) for k in data}
@@ -362,6 +369,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=4096, help="frame pairs per GPU per step")
     ap.add_argument("--e2e-pairs", type=int, default=4096, help="frame pairs per e2e step (pinned host memory)")
+    ap.add_argument("--profile", action="store_true",
+                    help="short run for ncu: skips the e2e and cpu_baseline legs (their keys are null)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -72,6 +72,7 @@ void mxDestroyArray(mxArray *a);
 void mexErrMsgTxt(const char *msg);
 void mexErrMsgIdAndTxt(const char *id, const char *msg, ...);
 int mexPrintf(const char *fmt, ...);
+int mexAtExit(void (*fn)(void));
 
 /* the gateway every MEX file exports */
 void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]);

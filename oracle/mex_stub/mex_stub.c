@@ -80,6 +80,16 @@ int mexPrintf(const char *fmt, ...) {
   return r;
 }
 
+static void (*g_atexit)(void) = 0;
+int mexAtExit(void (*fn)(void)) {
+  g_atexit = fn;
+  return 0;
+}
+void stub_run_atexit(void) {
+  if (g_atexit) g_atexit();
+  g_atexit = 0;
+}
+
 mxArray *stub_wrap(int cls, size_t m, size_t n, void *data) {
   mxArray *a = (mxArray *)calloc(1, sizeof(mxArray));
   a->cls = (mxClassID)cls;

@@ -25,7 +25,7 @@ class _MxArray(C.Structure):
                 ("is_complex", C.c_int), ("owns_data", C.c_int), ("data", C.c_void_p)]
 
 
-_lib = None
+_libs = {}
 
 
 def available() -> bool:
@@ -35,29 +35,32 @@ def available() -> bool:
     return os.path.exists(_SO)
 
 
-def lib():
-    global _lib
-    if _lib is None:
-        if not available():
+def lib(so=None):
+    """The reference gateway (default) or any other siftmatch MEX gateway linked against the
+    same stub runtime (tests build the product's gateway that way to drive both identically)."""
+    path = so or _SO
+    if path not in _libs:
+        if so is None and not available():
             raise RuntimeError("oracle/_ref/libsiftmatch_ref.so not built (no /root/reference here?)")
-        _lib = C.CDLL(_SO)
-        _lib.stub_wrap.restype = C.POINTER(_MxArray)
-        _lib.stub_wrap.argtypes = [C.c_int, C.c_size_t, C.c_size_t, C.c_void_p]
-        _lib.stub_call_mex.argtypes = [C.c_int, C.POINTER(C.POINTER(_MxArray)), C.c_int, C.POINTER(C.POINTER(_MxArray))]
-        _lib.stub_last_error.restype = C.c_char_p
-        _lib.mxDestroyArray.argtypes = [C.POINTER(_MxArray)]
-    return _lib
+        L = C.CDLL(path)
+        L.stub_wrap.restype = C.POINTER(_MxArray)
+        L.stub_wrap.argtypes = [C.c_int, C.c_size_t, C.c_size_t, C.c_void_p]
+        L.stub_call_mex.argtypes = [C.c_int, C.POINTER(C.POINTER(_MxArray)), C.c_int, C.POINTER(C.POINTER(_MxArray))]
+        L.stub_last_error.restype = C.c_char_p
+        L.mxDestroyArray.argtypes = [C.POINTER(_MxArray)]
+        _libs[path] = L
+    return _libs[path]
 
 
 class MexError(RuntimeError):
     pass
 
 
-def siftmatch(L1, L2, thresh=None, nout=2, extra_args=0):
+def siftmatch(L1, L2, thresh=None, nout=2, extra_args=0, so=None):
     """Call the reference gateway: matches = siftmatch(L1, L2[, thresh]).
     L1:(K1,ND), L2:(K2,ND) numpy (== ND x K column-major).  Returns
     (matches (2,n) float64 1-BASED exactly as MATLAB sees it, D (n,) or None)."""
-    L = lib()
+    L = lib(so)
     L1 = np.ascontiguousarray(L1)
     L2 = np.ascontiguousarray(L2)
     keep = [L1, L2]

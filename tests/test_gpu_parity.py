@@ -413,3 +413,50 @@ def test_matlab_mirror_roundtrip(ctx, orc, synth):
         {"Descriptor": fp.desc1.T, "XYZ_DATA": fp.xyz1.T}, {"Descriptor": fp.desc2.T, "XYZ_DATA": fp.xyz2.T})
     assert q.shape == (4, 1) and abs(np.linalg.norm(q) - 1) < 1e-9 and st in (1, 2)
     assert rn.rot_angle(Rr, fp.R) < 2e-3
+
+
+# ------------------------------------------------------------------------------------------
+# the MEX gateway itself: 3pre_b200/mex_files/siftmatch.cpp built against the same stub mex
+# runtime the reference's siftmatch.c is driven through (oracle/mex_stub), linked to libpre3.so
+# ------------------------------------------------------------------------------------------
+def _build_gateway():
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = os.path.join(root, "tests", "_build")
+    os.makedirs(out, exist_ok=True)
+    so = os.path.join(out, "libpre3_siftmatch_gw.so")
+    libdir = os.path.join(root, "3pre_b200", "lib")
+    subprocess.run(["g++", "-O2", "-fPIC", "-shared", "-o", so,
+                    os.path.join(root, "3pre_b200", "mex_files", "siftmatch.cpp"),
+                    "-x", "c", os.path.join(root, "oracle", "mex_stub", "mex_stub.c"), "-x", "none",
+                    "-I", os.path.join(root, "oracle", "mex_stub"), "-I", os.path.join(root, "3pre_b200", "mex_files"),
+                    "-I", os.path.join(root, "include"), "-L", libdir, "-lpre3", f"-Wl,-rpath,{libdir}"], check=True)
+    return so
+
+
+def test_mex_gateway_is_a_drop_in(golden, orc, synth):
+    from oracle import refmex
+    so = _build_gateway()
+    for name in ["f64", "f32", "u8", "i8", "k2one", "ties", "knn"]:
+        m, D = refmex.siftmatch(golden[f"{name}_L1"], golden[f"{name}_L2"], float(golden[f"{name}_thresh"]), nout=2, so=so)
+        np.testing.assert_array_equal(m, golden[f"{name}_matches"])
+        np.testing.assert_array_equal(D, golden[f"{name}_D"])
+    fp = synth.make_frame_pair(123, K1=512, K2=512, n_corr=300)
+    m, D = refmex.siftmatch(fp.desc1, fp.desc2, nout=2, so=so)  # default thresh 1.5
+    if refmex.available():
+        mr, Dr = refmex.siftmatch(fp.desc1, fp.desc2, nout=2)
+        np.testing.assert_array_equal(m, mr)
+        np.testing.assert_array_equal(D, Dr)
+    op, os_ = orc.siftmatch(fp.desc1, fp.desc2, 1.5)
+    np.testing.assert_array_equal(m, (op.T + 1).astype(float))
+    # the reference's argument errors, raised through mexErrMsgTxt
+    a = np.zeros((3, 4))
+    with pytest.raises(refmex.MexError, match="same number of rows"):
+        refmex.siftmatch(a, np.zeros((3, 5)), so=so)
+    with pytest.raises(refmex.MexError, match="same class"):
+        refmex.siftmatch(a, a.astype(np.float32), so=so)
+    with pytest.raises(refmex.MexError, match="Unsupported numeric class"):
+        refmex.siftmatch(a.astype(np.int32), a.astype(np.int32), so=so)
+    with pytest.raises(refmex.MexError, match="At most three"):
+        refmex.siftmatch(a, a, 1.5, extra_args=1, so=so)
