@@ -141,6 +141,14 @@ class Context:
     def launch_count(self) -> int:
         return int(self._lib.pre3_launch_count(self._h))
 
+    def eval_schedule(self, opts: RansacOpts):
+        """Wave boundaries of the hypothesis evaluation (pre3_eval_schedule)."""
+        ends = np.zeros(40, np.int32)
+        n = self._lib.pre3_eval_schedule(C.byref(opts), _ptr(ends), 40)
+        if n < 0:
+            raise L.Pre3Error(n, "pre3_eval_schedule")
+        return ends[:n].copy()
+
     def timing_enable(self, on: bool = True):
         self._ck(self._lib.pre3_timing_enable(self._h, int(bool(on))))
 
@@ -159,9 +167,11 @@ class Context:
         return float(t[0])
 
     # ---- stage 1 ------------------------------------------------------------------------
-    def siftmatch(self, L1, L2, thresh: float = 1.5):
+    def siftmatch(self, L1, L2, thresh: float = 1.5, want_score: bool = True):
         """L1 (K1,ND), L2 (K2,ND) same dtype in {f64,f32,i8,u8}.  Returns (pairs (n,2) int32
-        0-based in k1 order, score (n,) float64) -- siftmatch.c:83-132."""
+        0-based in k1 order, score (n,) float64 | None) -- siftmatch.c:83-132.  want_score=False
+        is `matches = siftmatch(L1,L2)` (nout == 1): the library may then skip the exact
+        distance of rows whose acceptance is already certified."""
         L1, L2 = _c(L1), _c(L2)
         if L1.dtype != L2.dtype:
             raise ValueError("L1 and L2 must be of the same class")
@@ -172,11 +182,11 @@ class Context:
         K1, ND = L1.shape
         K2 = L2.shape[0]
         pairs = np.zeros((max(K1, 1), 2), np.int32)
-        score = np.zeros(max(K1, 1), np.float64)
+        score = np.zeros(max(K1, 1), np.float64) if want_score else None
         n = np.zeros(1, np.int32)
         self._ck(self._lib.pre3_siftmatch(self._h, _ptr(L1), _ptr(L2), _CLS[L1.dtype], K1, K2, ND, float(thresh),
                                           _ptr(pairs), _ptr(score), _ptr(n)))
-        return pairs[: n[0]].copy(), score[: n[0]].copy()
+        return pairs[: n[0]].copy(), (score[: n[0]].copy() if want_score else None)
 
     def siftmatch_batch(self, L1, L2, thresh: float = 1.5, k1_count=None, k2_count=None):
         """L1 (P,K1,ND), L2 (P,K2,ND).  Returns list of (pairs, score) per problem."""

@@ -55,7 +55,7 @@ size_t match_ws_bytes(int cls, int P, int K1, int K2, int ND) {
 }
 
 int match_impl(pre3_ctx* ctx, const void* dL1, const void* dL2, int cls, int P, int K1, int K2, int ND,
-               const int32_t* dk1, const int32_t* dk2, double thresh, MatchRow** rows_out) {
+               const int32_t* dk1, const int32_t* dk2, double thresh, int need_score, MatchRow** rows_out) {
   MatchRow* rows = ws_take<MatchRow>(ctx, (size_t)P * K1);
   const float th = (float)thresh;  // narrowed like the reference (siftmatch.c:87,:205)
   bool tc = false;
@@ -63,7 +63,7 @@ int match_impl(pre3_ctx* ctx, const void* dL1, const void* dL2, int cls, int P, 
   if (ctx->match_engine == PRE3_MATCH_TC && !tc)
     return fail(ctx, PRE3_ERR_ARG, "tensor-core matcher needs class double/single and ND == 128");
   if (tc)
-    PRE3_TRY(launch_match_tc(ctx, dL1, dL2, cls, P, K1, K2, ND, dk1, dk2, th, rows));
+    PRE3_TRY(launch_match_tc(ctx, dL1, dL2, cls, P, K1, K2, ND, dk1, dk2, th, need_score, rows));
   else
     PRE3_TRY(launch_match_exact(ctx, dL1, dL2, cls, P, K1, K2, ND, dk1, dk2, th, rows));
   *rows_out = rows;
@@ -197,6 +197,11 @@ int pre3_sync(pre3_ctx* ctx) {
 
 int64_t pre3_launch_count(const pre3_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+int pre3_eval_schedule(const pre3_ransac_opts* opts, int32_t* ends, int cap) {
+  if (!opts || (cap > 0 && !ends)) return PRE3_ERR_ARG;
+  return eval_wave_ends(*opts, ends, cap);
+}
+
 int pre3_timing_enable(pre3_ctx* ctx, int on) {
   if (!ctx || ctx->device < 0) return PRE3_ERR_CUDA;
   ctx->timing = on != 0;
@@ -242,7 +247,8 @@ int pre3_siftmatch_batch_dev(pre3_ctx* ctx, const void* dL1, const void* dL2, in
   if (P == 0) return PRE3_OK;
   PRE3_TRY(ws_reserve(ctx, match_ws_bytes(cls, P, K1, K2, ND)));
   MatchRow* rows = nullptr;
-  if (K1 > 0) PRE3_TRY(match_impl(ctx, dL1, dL2, cls, P, K1, K2, ND, dk1_count, dk2_count, thresh, &rows));
+  if (K1 > 0)
+    PRE3_TRY(match_impl(ctx, dL1, dL2, cls, P, K1, K2, ND, dk1_count, dk2_count, thresh, dscore != nullptr, &rows));
   PRE3_TRY(launch_match_compact(ctx, rows, P, K1, dk1_count, dpairs, dscore, dn_out, nullptr, nullptr, K2, nullptr,
                                 nullptr));
   return PRE3_OK;
@@ -273,7 +279,7 @@ int pre3_siftmatch_batch(pre3_ctx* ctx, const void* L1, const void* L2, int cls,
   if (dk1) PRE3_TRY(h2d(ctx, dk1, k1_count, 4 * (size_t)P));
   if (dk2) PRE3_TRY(h2d(ctx, dk2, k2_count, 4 * (size_t)P));
   MatchRow* rows = nullptr;
-  if (K1 > 0) PRE3_TRY(match_impl(ctx, d1, d2, cls, P, K1, K2, ND, dk1, dk2, thresh, &rows));
+  if (K1 > 0) PRE3_TRY(match_impl(ctx, d1, d2, cls, P, K1, K2, ND, dk1, dk2, thresh, score != nullptr, &rows));
   PRE3_TRY(launch_match_compact(ctx, rows, P, K1, dk1, dpairs, dscore, dn, nullptr, nullptr, K2, nullptr, nullptr));
   if (pairs) PRE3_TRY(d2h(ctx, pairs, dpairs, 8 * np));
   if (score) PRE3_TRY(d2h(ctx, score, dscore, 8 * np));
@@ -469,7 +475,7 @@ static int pairs_impl(pre3_ctx* ctx, const void* ddesc1, const void* ddesc2, int
                       const pre3_ransac_opts& o, uint32_t pair_id0, pre3_pair_result* dres, int32_t* dmatches,
                       uint8_t* dmasks) {
   MatchRow* rows = nullptr;
-  if (K1 > 0) PRE3_TRY(match_impl(ctx, ddesc1, ddesc2, cls, P, K1, K2, ND, dk1, dk2, o.ratio, &rows));
+  if (K1 > 0) PRE3_TRY(match_impl(ctx, ddesc1, ddesc2, cls, P, K1, K2, ND, dk1, dk2, o.ratio, 0, &rows));
   double* dYa = ws_take<double>(ctx, 3 * (size_t)P * K1);
   double* dYb = ws_take<double>(ctx, 3 * (size_t)P * K1);
   int32_t* dn = ws_take<int32_t>(ctx, P);

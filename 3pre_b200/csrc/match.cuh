@@ -26,8 +26,9 @@ int launch_match_rows_exact(pre3_ctx* ctx, const void* dL1, const void* dL2, int
 // classes double / single.  Rows whose candidates cannot be certified are recomputed exactly.
 bool match_tc_supported(int cls, int K1, int K2, int ND);
 size_t match_tc_workspace_bytes(int P, int K1, int K2);
+// need_score == 0: MatchRow::best may be approximate for rows whose acceptance the brackets decide.
 int launch_match_tc(pre3_ctx* ctx, const void* dL1, const void* dL2, int cls, int P, int K1, int K2, int ND,
-                    const int32_t* dk1, const int32_t* dk2, float thresh, MatchRow* drows);
+                    const int32_t* dk1, const int32_t* dk2, float thresh, int need_score, MatchRow* drows);
 
 // rows -> compact (k1,k2) list in k1 order (siftmatch.c:238-246) and, optionally, the gathered
 // correspondences Ya = xyz1(:,k1), Yb = xyz2(:,k2) (SIFT_match_save.m:53).

@@ -143,33 +143,51 @@ k_match_exact(const T* __restrict__ L1, const T* __restrict__ L2, int K1, int K2
 }
 
 // One warp per listed row: exact recomputation of rows the proposal path flagged.
-// row_list holds p*K1 + k1 entries, *row_list_n of them.
+// row_list holds p*K1 + k1 entries, *row_list_n of them.  32 columns at a time: every column is
+// loaded coalesced (a lane holds RX_ND/32 consecutive bins), the delta*delta products go to shared
+// memory, then lane c adds column c's products strictly in bin order (siftmatch.c:101-107).
+constexpr int RX_ND = 128;
 template <typename T, typename ACC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(32)
 k_match_rows_exact(const T* __restrict__ L1, const T* __restrict__ L2, int K1, int K2, int ND,
                    const int32_t* __restrict__ k2c, float thresh, const int32_t* __restrict__ row_list,
                    const int32_t* __restrict__ row_list_n, int list_cap, MatchRow* __restrict__ rows) {
-  const int lane = threadIdx.x & 31;
-  const int wpb = blockDim.x >> 5;
+  __shared__ ACC sprod[32][RX_ND + 1];
+  const int lane = threadIdx.x;
   const int n = min(*row_list_n, list_cap);
-  for (int w = blockIdx.x * wpb + (threadIdx.x >> 5); w < n; w += gridDim.x * wpb) {
+  constexpr int PER = RX_ND / 32;
+  for (int w = blockIdx.x; w < n; w += gridDim.x) {
     const int rid = row_list[w];
     const int p = rid / K1;
     const int n2 = k2c ? min(k2c[p], K2) : K2;
     const T* a = L1 + (size_t)rid * ND;
     const T* B = L2 + (size_t)p * K2 * ND;
+    ACC va[PER];
+#pragma unroll
+    for (int e = 0; e < PER; ++e) va[e] = (ACC)a[PER * lane + e];
     Top2<ACC> st;
     st.best = maxval<ACC>();
     st.second = maxval<ACC>();
     st.bestk = -1;
-    for (int k2 = lane; k2 < n2; k2 += 32) {
-      const T* b = B + (size_t)k2 * ND;
-      ACC acc = 0;
-      for (int bin = 0; bin < ND; ++bin) {
-        const ACC d = (ACC)a[bin] - (ACC)b[bin];
-        acc += d * d;
+    for (int c0 = 0; c0 < n2; c0 += 32) {
+      const int nc = min(32, n2 - c0);
+      __syncwarp();
+#pragma unroll 4
+      for (int c = 0; c < nc; ++c) {
+        const T* b = B + (size_t)(c0 + c) * ND + PER * lane;
+#pragma unroll
+        for (int e = 0; e < PER; ++e) {
+          const ACC d = va[e] - (ACC)b[e];
+          sprod[c][PER * lane + e] = d * d;
+        }
       }
-      top2_update(st, acc, k2);
+      __syncwarp();
+      if (lane < nc) {
+        ACC acc = 0;
+#pragma unroll 8
+        for (int bin = 0; bin < RX_ND; ++bin) acc += sprod[lane][bin];
+        top2_update(st, acc, c0 + lane);
+      }
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
@@ -280,13 +298,14 @@ int launch_match_rows_exact(pre3_ctx* ctx, const void* dL1, const void* dL2, int
                             const int32_t* dk2, float thresh, const int32_t* drow_list, const int32_t* drow_list_n,
                             int list_cap, MatchRow* drows) {
   Span span__(ctx, T_RESCORE);
-  const int blocks = 4 * ctx->sm_count;
+  if (ND != RX_ND) return fail(ctx, PRE3_ERR_ARG, "row recheck: ND must be 128");
+  const int blocks = 16 * ctx->sm_count;
   if (cls == PRE3_CLASS_DOUBLE)
-    k_match_rows_exact<double, double><<<blocks, 256, 0, ctx->stream>>>((const double*)dL1, (const double*)dL2, K1, K2,
+    k_match_rows_exact<double, double><<<blocks, 32, 0, ctx->stream>>>((const double*)dL1, (const double*)dL2, K1, K2,
                                                                          ND, dk2, thresh, drow_list, drow_list_n,
                                                                          list_cap, drows);
   else if (cls == PRE3_CLASS_SINGLE)
-    k_match_rows_exact<float, float><<<blocks, 256, 0, ctx->stream>>>((const float*)dL1, (const float*)dL2, K1, K2, ND,
+    k_match_rows_exact<float, float><<<blocks, 32, 0, ctx->stream>>>((const float*)dL1, (const float*)dL2, K1, K2, ND,
                                                                        dk2, thresh, drow_list, drow_list_n, list_cap,
                                                                        drows);
   else

@@ -437,7 +437,8 @@ __global__ void __launch_bounds__(32)
 k_tc_rescore(const T* __restrict__ L1, const T* __restrict__ L2, int K1, int K2, int K1p, int K2p,
              const int32_t* __restrict__ k1c, const int32_t* __restrict__ k2c, float thresh,
              const Prop* __restrict__ prop, const float* __restrict__ nrmA, const PairInfo* __restrict__ info,
-             MatchRow* __restrict__ rows, int32_t* __restrict__ row_list, int32_t* __restrict__ row_list_n) {
+             int need_score, MatchRow* __restrict__ rows, int32_t* __restrict__ row_list,
+             int32_t* __restrict__ row_list_n) {
   __shared__ ACC sprod[RS_ROWS][ND + 1];
   const int p = blockIdx.y;
   const int lane = threadIdx.x & 31;
@@ -474,12 +475,21 @@ k_tc_rescore(const T* __restrict__ L1, const T* __restrict__ L2, int K1, int K2,
     if (pi.bad || my.idx < 0 || my.idx >= n2 || !(thresh > 0.f) || !(C - na > m) || !(my.best < INFINITY)) {
       ambiguous = true;  // keys may be meaningless (range, sign) -> exact kernel
     } else {
-      const double L1b = ((double)my.best - C + na) - m;  // exact best  >= L1b
-      const double U2b = ((double)my.second - C + na) + m;  // exact second_best <= U2b
-      if (L1b > 0.0 && __fmul_rn(thresh, (float)L1b) > (float)U2b)
+      const double b1 = (double)my.best - C + na, s2 = (double)my.second - C + na;
+      const double L1b = b1 - m;  // exact best  >= L1b
+      const double U2b = s2 + m;  // exact second_best <= U2b
+      if (L1b > 0.0 && __fmul_rn(thresh, (float)L1b) > (float)U2b) {
         out.accept = 0;  // ratio test fails for sure (siftmatch.c:122): row never output
-      else
+      } else if (!need_score && b1 + m < s2 - m && __fmul_rn(thresh, (float)(b1 + m)) <= (float)(s2 - m)) {
+        // the candidate is the unique exact minimum (its distance <= b1 + m < s2 - m <= every other
+        // column's) and the test passes for every (best, second_best) in the brackets: accepted
+        // without recomputing the distance (the caller does not ask for the scores)
+        out.accept = 1;
+        out.bestk = my.idx;
+        out.best = b1;
+      } else {
         need_exact = true;
+      }
     }
   }
 
@@ -575,7 +585,7 @@ size_t match_tc_workspace_bytes(int P, int K1, int K2) {
 }
 
 int launch_match_tc(pre3_ctx* ctx, const void* dL1, const void* dL2, int cls, int P, int K1, int K2, int ND,
-                    const int32_t* dk1, const int32_t* dk2, float thresh, MatchRow* drows) {
+                    const int32_t* dk1, const int32_t* dk2, float thresh, int need_score, MatchRow* drows) {
   using namespace tc;
   if (!match_tc_supported(cls, K1, K2, ND)) return fail(ctx, PRE3_ERR_ARG, "tensor-core matcher: unsupported shape");
   if (P <= 0) return PRE3_OK;
@@ -625,11 +635,11 @@ int launch_match_tc(pre3_ctx* ctx, const void* dL1, const void* dL2, int cls, in
     if (cls == PRE3_CLASS_DOUBLE)
       k_tc_rescore<double, double><<<g, 32, 0, ctx->stream>>>((const double*)dL1, (const double*)dL2, K1, K2,
                                                                           K1p, K2p, dk1, dk2, thresh, prop, nrmA, info,
-                                                                          drows, list, list_n);
+                                                                          need_score, drows, list, list_n);
     else
       k_tc_rescore<float, float><<<g, 32, 0, ctx->stream>>>((const float*)dL1, (const float*)dL2, K1, K2,
                                                                         K1p, K2p, dk1, dk2, thresh, prop, nrmA, info,
-                                                                        drows, list, list_n);
+                                                                        need_score, drows, list, list_n);
     count_launch(ctx);
   }
   PRE3_CUDA(cudaGetLastError());

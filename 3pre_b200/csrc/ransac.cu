@@ -479,292 +479,7 @@ __device__ __forceinline__ void store_colmajor(double* dst, const double* Rrow) 
     for (int c = 0; c < 3; ++c) dst[3 * c + r] = Rrow[3 * r + c];
 }
 
-// ------------------------------------------------------------------------------------------
-// k_select
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SEL_THREADS)
-k_select(const PairMeta* __restrict__ meta, const double* __restrict__ Ya, const double* __restrict__ Yb,
-         int Nmax, const int32_t* __restrict__ samples, uint64_t seed, uint32_t pair_id0, long long h0, int H,
-         int k, int method, int max_iteration, int adaptive, const int32_t* __restrict__ tab,
-         const int32_t* __restrict__ counts, const int8_t* __restrict__ states,
-         pre3_pair_result* __restrict__ res, uint8_t* __restrict__ masks, int mask_stride,
-         uint8_t* __restrict__ mask_scratch, int32_t* __restrict__ counts_out, int8_t* __restrict__ states_out) {
-  __shared__ SelShared sh;
-  const int p = blockIdx.x;
-  const int tid = threadIdx.x;
-  const PairMeta m = meta[p];
-  const int N = m.N;
-  const double* ya = Ya + (size_t)p * Nmax * 3;
-  const double* yb = Yb + (size_t)p * Nmax * 3;
-  const int32_t* cnt = counts + (size_t)p * H;
-  const int8_t* sts = states + (size_t)p * H;
-  uint8_t* mask = masks ? masks + (size_t)p * mask_stride : mask_scratch + (size_t)p * Nmax;
-  pre3_pair_result out;
-  if (tid == 0) {
-    out.status = 0;
-    out.state = 0;
-    out.best_fit = 0;
-    out.best_sample = -1;
-    out.best_iter = 0;
-    out.n_iter = 0;
-    out.n_consumed = 0;
-    out.n_matches = N;
-    out.thr = m.thr;
-    out.error_sum = 0.0;
-    for (int i = 0; i < 9; ++i) out.R[i] = out.R_hyp[i] = 0.0;
-    for (int i = 0; i < 3; ++i) out.T[i] = out.T_hyp[i] = 0.0;
-  }
-  if (N < k || N <= 0) {  // get_rand(k, N) errors in the reference (get_rand.m:39-41)
-    if (tid == 0) {
-      out.status = 1;
-      res[p] = out;
-    }
-    for (int i = tid; i < H; i += SEL_THREADS) {
-      if (counts_out) counts_out[(size_t)p * H + i] = -1;
-      if (states_out) states_out[(size_t)p * H + i] = 0;
-    }
-    if (masks)
-      for (int i = tid; i < mask_stride; i += SEL_THREADS) mask[i] = 0;
-    return;
-  }
-  const int32_t* trow = tab ? tab + m.pad : nullptr;
-
-  // ---- 1. loop control as a prefix scan -------------------------------------------------
-  const int ipt = (H + SEL_THREADS - 1) / SEL_THREADS;
-  const int s_lo = min(H, tid * ipt), s_hi = min(H, s_lo + ipt);
-  int lc = 0, lm = 0;
-  for (int s = s_lo; s < s_hi; ++s) {
-    const bool rec = !(method == PRE3_METHOD_SVD && sts[s] == -1);
-    if (rec) {
-      ++lc;
-      lm = max(lm, cnt[s]);
-    }
-  }
-  sh.pre_cnt[tid] = lc;
-  sh.pre_max[tid] = lm;
-  if (tid == 0) {
-    sh.stop = H;
-    sh.maxc = 0;
-    sh.first_rec = 0x7fffffff;
-    sh.first_nonmax = 0x7fffffff;
-  }
-  __syncthreads();
-  if (tid == 0) {  // exclusive scan over 256 partials (tiny)
-    int ac = 0, am = 0;
-    for (int i = 0; i < SEL_THREADS; ++i) {
-      const int c = sh.pre_cnt[i], mm = sh.pre_max[i];
-      sh.pre_cnt[i] = ac;
-      sh.pre_max[i] = am;
-      ac += c;
-      am = max(am, mm);
-    }
-  }
-  __syncthreads();
-  {
-    int pc = sh.pre_cnt[tid], pm = sh.pre_max[tid];
-    int my_stop = H;
-    for (int s = s_lo; s < s_hi; ++s) {
-      const int iter = 1 + pc;
-      int nit = max_iteration;
-      if (adaptive && pm >= 5) nit = min(trow[min(pm, N)], max_iteration);
-      if (!(iter < nit)) {
-        my_stop = s;
-        break;
-      }
-      const bool rec = !(method == PRE3_METHOD_SVD && sts[s] == -1);
-      if (rec) {
-        ++pc;
-        pm = max(pm, cnt[s]);
-      }
-    }
-    if (my_stop < H) atomicMin(&sh.stop, my_stop);
-  }
-  __syncthreads();
-  const int S_end = sh.stop;  // sample sets consumed
-
-  // ---- 2. max cardinality over the recorded hypotheses -----------------------------------
-  {
-    int lmax = -1, lfirst = 0x7fffffff, nrec = 0;
-    for (int s = tid; s < S_end; s += SEL_THREADS) {
-      const bool rec = !(method == PRE3_METHOD_SVD && sts[s] == -1);
-      if (rec) {
-        lmax = max(lmax, cnt[s]);
-        lfirst = min(lfirst, s);
-        ++nrec;
-      }
-    }
-    atomicMax(&sh.maxc, lmax);
-    atomicMin(&sh.first_rec, lfirst);
-    sh.i0[tid] = nrec;
-  }
-  __syncthreads();
-  if (tid == 0) {
-    int n = 0;
-    for (int i = 0; i < SEL_THREADS; ++i) n += sh.i0[i];
-    sh.n_iter = n;
-  }
-  __syncthreads();
-  const int maxc = sh.maxc;
-  const int n_iter = sh.n_iter;
-  if (counts_out || states_out)
-    for (int s = tid; s < H; s += SEL_THREADS) {
-      const bool consumed = s < S_end;
-      const bool rec = consumed && !(method == PRE3_METHOD_SVD && sts[s] == -1);
-      if (counts_out) counts_out[(size_t)p * H + s] = rec ? cnt[s] : -1;
-      if (states_out) states_out[(size_t)p * H + s] = consumed ? sts[s] : (int8_t)0;
-    }
-  if (n_iter < 1) {  // nothing recorded: M(1).ErrorSum = [] in the reference -> error
-    if (tid == 0) {
-      out.status = 2;
-      out.n_consumed = S_end;
-      res[p] = out;
-    }
-    if (masks)
-      for (int i = tid; i < mask_stride; i += SEL_THREADS) mask[i] = 0;
-    return;
-  }
-
-  // ---- 3. ties at max cardinality: exact ErrorSum, (min ErrorSum, first index) ------------
-  const int warp = tid >> 5, lane = tid & 31;
-  double best_es = INFINITY;
-  int best_s = 0x7fffffff;
-  if (maxc > 0) {
-    // each warp walks the tie list in the same order; tie number j goes to warp j % 8
-    int tie_no = 0;
-    for (int sbase = 0; sbase < S_end; sbase += 32) {
-      const int s = sbase + lane;
-      bool is_tie = false;
-      if (s < S_end) is_tie = !(method == PRE3_METHOD_SVD && sts[s] == -1) && cnt[s] == maxc;
-      unsigned bal = __ballot_sync(0xffffffffu, is_tie);
-      while (bal) {
-        const int l = __ffs(bal) - 1;
-        bal &= bal - 1;
-        const int st = sbase + l;
-        if ((tie_no++ & (SEL_THREADS / 32 - 1)) != warp) continue;
-        int idx[MAX_K];
-        load_sample(samples, seed, pair_id0 + (uint32_t)p, h0, st, H, p, N, k, idx);
-        Rigid f;
-        fit_sample(method, ya, yb, idx, k, f);  // every lane computes the same fit
-        double es = 0.0;
-        for (int ib = 0; ib < N; ib += 32) {
-          const int i = ib + lane;
-          double nr = 0.0;
-          bool in = false;
-          if (i < N) {
-            nr = residual_norm(f.R, f.t, ya + 3 * i, yb + 3 * i);
-            in = nr < m.thr;
-          }
-          unsigned inb = __ballot_sync(0xffffffffu, in);
-          while (inb) {  // sequential sum in index order (RANSAC_CALC_VER2.m:135)
-            const int li = __ffs(inb) - 1;
-            inb &= inb - 1;
-            es = es + __shfl_sync(0xffffffffu, nr, li);
-          }
-        }
-        if (es < best_es || (es == best_es && st < best_s)) {
-          best_es = es;
-          best_s = st;
-        }
-      }
-    }
-  }
-  if (lane == 0) {
-    sh.tie_es[warp] = best_es;
-    sh.tie_s[warp] = best_s;
-  }
-  // first recorded hypothesis whose cardinality is not the maximum (its eee1 entry is 10000)
-  {
-    int lf = 0x7fffffff;
-    for (int s = tid; s < S_end; s += SEL_THREADS) {
-      const bool rec = !(method == PRE3_METHOD_SVD && sts[s] == -1);
-      if (rec && (cnt[s] != maxc || cnt[s] == 0)) lf = min(lf, s);
-    }
-    atomicMin(&sh.first_nonmax, lf);
-  }
-  __syncthreads();
-  if (tid == 0) {
-    double es = INFINITY;
-    int s = 0x7fffffff;
-    for (int w = 0; w < SEL_THREADS / 32; ++w)
-      if (sh.tie_es[w] < es || (sh.tie_es[w] == es && sh.tie_s[w] < s)) {
-        es = sh.tie_es[w];
-        s = sh.tie_s[w];
-      }
-    // [C,I] = min(eee1): entries are ErrorSum for max-cardinality hypotheses, 10000 otherwise
-    int win = s;
-    const int fn = sh.first_nonmax;
-    if (s == 0x7fffffff) {
-      win = fn;  // maxc == 0: every entry is 10000 -> I = first recorded
-    } else if (fn != 0x7fffffff) {
-      if (10000.0 < es || (10000.0 == es && fn < s)) win = fn;
-    }
-    sh.winner = win;
-  }
-  __syncthreads();
-  const int win = sh.winner;
-
-  // ---- 4. winner: hypothesis, mask, ErrorSum ---------------------------------------------
-  if (tid == 0) {
-    int idx[MAX_K];
-    load_sample(samples, seed, pair_id0 + (uint32_t)p, h0, win, H, p, N, k, idx);
-    Rigid f;
-    fit_sample(method, ya, yb, idx, k, f);
-    for (int i = 0; i < 9; ++i) sh.Rt[i] = f.R[i];
-    for (int i = 0; i < 3; ++i) sh.Rt[9 + i] = f.t[i];
-  }
-  __syncthreads();
-  for (int i = tid; i < N; i += SEL_THREADS)
-    mask[i] = residual_norm(&sh.Rt[0], &sh.Rt[9], ya + 3 * i, yb + 3 * i) < m.thr ? 1 : 0;
-  if (masks)
-    for (int i = N + tid; i < mask_stride; i += SEL_THREADS) mask[i] = 0;
-  __syncthreads();
-  if (warp == 0) {  // ErrorSum of the winner, sequential order
-    double es = 0.0;
-    for (int ib = 0; ib < N; ib += 32) {
-      const int i = ib + lane;
-      double nr = 0.0;
-      bool in = false;
-      if (i < N) {
-        in = mask[i] != 0;
-        if (in) nr = residual_norm(&sh.Rt[0], &sh.Rt[9], ya + 3 * i, yb + 3 * i);
-      }
-      unsigned inb = __ballot_sync(0xffffffffu, in);
-      while (inb) {
-        const int li = __ffs(inb) - 1;
-        inb &= inb - 1;
-        es = es + __shfl_sync(0xffffffffu, nr, li);
-      }
-    }
-    if (lane == 0) out.error_sum = es;
-  }
-
-  // ---- 5. refit on the support set --------------------------------------------------------
-  Rigid rf;
-  const int st = block_refit(method, ya, yb, mask, N, sh.scratch, rf);
-  if (tid == 0) {
-    out.state = st;
-    out.best_fit = maxc;
-    out.best_sample = win;
-    // BestFitIdx counts recorded hypotheses up to and including the winner
-    int bi = 0;
-    for (int s = 0; s <= win; ++s) bi += !(method == PRE3_METHOD_SVD && sts[s] == -1);
-    out.best_iter = bi;
-    out.n_iter = n_iter;
-    out.n_consumed = S_end;
-    store_colmajor(out.R, rf.R);
-    for (int i = 0; i < 3; ++i) out.T[i] = rf.t[i];
-    store_colmajor(out.R_hyp, &sh.Rt[0]);
-    for (int i = 0; i < 3; ++i) out.T_hyp[i] = sh.Rt[9 + i];
-    res[p] = out;
-  }
-}
-
-
-// ------------------------------------------------------------------------------------------
-// k_select_warp: the same selection as k_select with ONE WARP per pair (no block barriers), used
-// for batches of pairs.  Differences are confined to the order of the refit sums (per-lane
-// strided partial sums, then a fixed xor-butterfly), i.e. to rounding of R, T at the 1e-16 level.
-// ------------------------------------------------------------------------------------------
+// warp helpers for the selection kernels
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) v = v + __shfl_xor_sync(0xffffffffu, v, off);
@@ -858,18 +573,279 @@ __device__ __forceinline__ int warp_refit(int method, const double* ya, const do
   }
 }
 
-constexpr int SELW_WARPS = 4;
+// ------------------------------------------------------------------------------------------
+// Selection (RANSAC_CALC_VER2.m:86-175 and the refit :186) in three kernels:
+//   k_sel_scan   one block per pair (one warp for batches of pairs, 1024 threads for a single
+//                large pair): the reference's sequential loop control (:86, :97-99, :137-140) as
+//                a tiled prefix scan that stops at the first tile in which the loop ends; max
+//                cardinality; the list of hypotheses tied at that cardinality.
+//   k_sel_tie    one THREAD per tied hypothesis: minimal fit again + ErrorSum (:135), summed
+//                strictly in index order (non-inliers add an exact +0.0).
+//   k_sel_final  one warp per pair: [C,I] = min(eee1) (:165-175: min ErrorSum among the ties,
+//                10000 for every other recorded hypothesis, first index wins), winner mask,
+//                least-squares refit on the support set.
+// ------------------------------------------------------------------------------------------
+struct SelInfo {
+  int32_t status;        // 0 ok; 1 fewer than k correspondences; 2 nothing recorded
+  int32_t S_end;         // sample sets consumed
+  int32_t maxc;          // max cardinality over the recorded hypotheses
+  int32_t n_iter;        // recorded hypotheses (length(M))
+  int32_t first_nonmax;  // first recorded hypothesis that is not a tie (0x7fffffff: none)
+  int32_t n_ties;
+};
 
-__global__ void __launch_bounds__(SELW_WARPS * 32)
-k_select_warp(const PairMeta* __restrict__ meta, const double* __restrict__ Ya, const double* __restrict__ Yb,
-              int P, int Nmax, const int32_t* __restrict__ samples, uint64_t seed, uint32_t pair_id0, int H, int k,
-              int method, int max_iteration, int adaptive, const int32_t* __restrict__ tab,
-              const int32_t* __restrict__ counts, const int8_t* __restrict__ states,
-              pre3_pair_result* __restrict__ res, uint8_t* __restrict__ masks, int mask_stride,
-              uint8_t* __restrict__ mask_scratch, int32_t* __restrict__ counts_out, int8_t* __restrict__ states_out) {
-  const int p = blockIdx.x * SELW_WARPS + (threadIdx.x >> 5);
+__device__ __forceinline__ void result_init(pre3_pair_result* out, int status, int n_consumed, int N, double thr) {
+  out->status = status;
+  out->state = 0;
+  out->best_fit = 0;
+  out->best_sample = -1;
+  out->best_iter = 0;
+  out->n_iter = 0;
+  out->n_consumed = n_consumed;
+  out->n_matches = N;
+  out->thr = thr;
+  out->error_sum = 0.0;
+  for (int i = 0; i < 9; ++i) out->R[i] = out->R_hyp[i] = 0.0;
+  for (int i = 0; i < 3; ++i) out->T[i] = out->T_hyp[i] = 0.0;
+}
+
+// Block-wide EXCLUSIVE scan of (sum, max) over one value per thread (identity 0, 0); also
+// returns the block totals.  NT threads, NT a multiple of 32 (NT == 32: pure warp shuffles).
+template <int NT>
+__device__ __forceinline__ void block_exscan_cm(int c, int m, int& ex_c, int& ex_m, int& tot_c, int& tot_m,
+                                                int* s_c, int* s_m) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const int cc = __shfl_up_sync(0xffffffffu, c, off);
+    const int mm = __shfl_up_sync(0xffffffffu, m, off);
+    if (lane >= off) {
+      c += cc;
+      m = max(m, mm);
+    }
+  }
+  ex_c = __shfl_up_sync(0xffffffffu, c, 1);
+  ex_m = __shfl_up_sync(0xffffffffu, m, 1);
+  if (lane == 0) {
+    ex_c = 0;
+    ex_m = 0;
+  }
+  if (NT == 32) {
+    tot_c = __shfl_sync(0xffffffffu, c, 31);
+    tot_m = __shfl_sync(0xffffffffu, m, 31);
+    return;
+  }
+  __syncthreads();  // s_c / s_m may still be read from the previous call
+  if (lane == 31) {
+    s_c[warp] = c;
+    s_m[warp] = m;
+  }
+  __syncthreads();
+  int bc = 0, bm = 0, tc = 0, tm = 0;
+  for (int w = 0; w < NT / 32; ++w) {
+    const int wc = s_c[w], wm = s_m[w];
+    if (w < warp) {
+      bc += wc;
+      bm = max(bm, wm);
+    }
+    tc += wc;
+    tm = max(tm, wm);
+  }
+  ex_c += bc;
+  ex_m = max(ex_m, bm);
+  tot_c = tc;
+  tot_m = tm;
+}
+
+template <int NT>
+__device__ __forceinline__ int block_min_int(int v, int* s_v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, off));
+  if (NT == 32) return v;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_v[threadIdx.x >> 5] = v;
+  __syncthreads();
+  int r = 0x7fffffff;
+  for (int w = 0; w < NT / 32; ++w) r = min(r, s_v[w]);
+  return r;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT)
+k_sel_scan(const PairMeta* __restrict__ meta, int Nmax, int H, int k, int method, int max_iteration, int adaptive,
+           const int32_t* __restrict__ tab, const int32_t* __restrict__ counts, const int8_t* __restrict__ states,
+           pre3_pair_result* __restrict__ res, uint8_t* __restrict__ masks, int mask_stride,
+           int32_t* __restrict__ counts_out, int8_t* __restrict__ states_out, SelInfo* __restrict__ info,
+           int2* __restrict__ ties, int* __restrict__ tie_total) {
+  __shared__ int s_a[32], s_b[32], s_base, s_pc, s_pm;
+  const int p = blockIdx.x;
+  const int tid = threadIdx.x;
+  const PairMeta m = meta[p];
+  const int N = m.N;
+  const int32_t* cnt = counts + (size_t)p * H;
+  const int8_t* sts = states + (size_t)p * H;
+  uint8_t* mask = masks ? masks + (size_t)p * mask_stride : nullptr;
+  SelInfo si;
+  si.status = 0;
+  si.S_end = 0;
+  si.maxc = 0;
+  si.n_iter = 0;
+  si.first_nonmax = 0x7fffffff;
+  si.n_ties = 0;
+  if (N < k || N <= 0) {  // get_rand(k, N) errors in the reference (get_rand.m:39-41)
+    if (tid == 0) {
+      result_init(res + p, 1, 0, N, m.thr);
+      si.status = 1;
+      info[p] = si;
+    }
+    for (int i = tid; i < H; i += NT) {
+      if (counts_out) counts_out[(size_t)p * H + i] = -1;
+      if (states_out) states_out[(size_t)p * H + i] = 0;
+    }
+    if (mask)
+      for (int i = tid; i < mask_stride; i += NT) mask[i] = 0;
+    return;
+  }
+  const int32_t* trow = tab ? tab + m.pad : nullptr;
+
+  // ---- 1. loop control, tile by tile; also yields max cardinality and length(M) at the stop ----
+  int S_end = H, maxc = 0, n_iter = 0;
+  {
+    int car_c = 0, car_m = 0;  // recorded count / max cardinality before the current tile
+    bool stopped = false;
+    for (int base = 0; base < H; base += NT) {
+      const int s = base + tid;
+      const bool rec = s < H && !(method == PRE3_METHOD_SVD && sts[s] == -1);
+      int ec, em, tot_c, tot_m;
+      block_exscan_cm<NT>(rec ? 1 : 0, rec ? cnt[s] : 0, ec, em, tot_c, tot_m, s_a, s_b);
+      const int pc = car_c + ec, pm = max(car_m, em);
+      int nit = max_iteration;
+      if (adaptive && pm >= 5) nit = min(trow[min(pm, N)], max_iteration);
+      const bool stop_here = s < H && !(1 + pc < nit);
+      const int first = block_min_int<NT>(stop_here ? s : 0x7fffffff, s_a);
+      if (first != 0x7fffffff) {
+        // values at the stop index = recorded count / max cardinality over s < first
+        if (s == first) {
+          s_pc = pc;
+          s_pm = pm;
+        }
+        __syncthreads();
+        n_iter = s_pc;
+        maxc = s_pm;
+        S_end = first;
+        stopped = true;
+        break;
+      }
+      car_c += tot_c;
+      car_m = max(car_m, tot_m);
+      if (NT != 32) __syncthreads();
+    }
+    if (!stopped) {
+      n_iter = car_c;
+      maxc = car_m;
+    }
+  }
+  if (counts_out || states_out)
+    for (int s = tid; s < H; s += NT) {
+      const bool consumed = s < S_end;
+      const bool rec = consumed && !(method == PRE3_METHOD_SVD && sts[s] == -1);
+      if (counts_out) counts_out[(size_t)p * H + s] = rec ? cnt[s] : -1;
+      if (states_out) states_out[(size_t)p * H + s] = consumed ? sts[s] : (int8_t)0;
+    }
+  si.S_end = S_end;
+  si.maxc = maxc;
+  si.n_iter = n_iter;
+  if (n_iter < 1) {  // nothing recorded: M(1).ErrorSum = [] in the reference -> error
+    if (tid == 0) {
+      result_init(res + p, 2, S_end, N, m.thr);
+      si.status = 2;
+      info[p] = si;
+    }
+    if (mask)
+      for (int i = tid; i < mask_stride; i += NT) mask[i] = 0;
+    return;
+  }
+
+  // ---- 2. ties at max cardinality -> global list; first recorded non-tie ------------------------
+  int first_nonmax = 0x7fffffff, n_ties = 0;
+  for (int base = 0; base < S_end; base += NT) {
+    const int s = base + tid;
+    const bool rec = s < S_end && !(method == PRE3_METHOD_SVD && sts[s] == -1);
+    const bool is_tie = rec && maxc > 0 && cnt[s] == maxc;
+    if (rec && !is_tie) first_nonmax = min(first_nonmax, s);
+    const unsigned bal = __ballot_sync(0xffffffffu, is_tie);
+    int tile_ties;
+    int my_off = __popc(bal & ((1u << (tid & 31)) - 1u));
+    if (NT == 32) {
+      tile_ties = __popc(bal);
+    } else {
+      __syncthreads();
+      if ((tid & 31) == 0) s_a[tid >> 5] = __popc(bal);
+      __syncthreads();
+      tile_ties = 0;
+      for (int w = 0; w < NT / 32; ++w) {
+        if (w < (tid >> 5)) my_off += s_a[w];
+        tile_ties += s_a[w];
+      }
+    }
+    if (tile_ties > 0) {
+      if (tid == 0) s_base = atomicAdd(tie_total, tile_ties);
+      if (NT == 32) __syncwarp(); else __syncthreads();
+      const int tb = s_base;
+      if (is_tie) ties[tb + my_off] = make_int2(p, s);
+      if (NT == 32) __syncwarp(); else __syncthreads();
+    }
+    n_ties += tile_ties;
+  }
+  first_nonmax = block_min_int<NT>(first_nonmax, s_a);
+  if (tid == 0) {
+    si.first_nonmax = first_nonmax;
+    si.n_ties = n_ties;
+    info[p] = si;
+  }
+}
+
+constexpr int TIE_THREADS = 128;
+
+__global__ void __launch_bounds__(TIE_THREADS)
+k_sel_tie(const PairMeta* __restrict__ meta, const double* __restrict__ Ya, const double* __restrict__ Yb, int Nmax,
+          const int32_t* __restrict__ samples, uint64_t seed, uint32_t pair_id0, int H, int k, int method,
+          const int2* __restrict__ ties, const int* __restrict__ tie_total, int cap, double* __restrict__ es_out) {
+  const int total = min(*tie_total, cap);
+  for (int t = blockIdx.x * TIE_THREADS + threadIdx.x; t < total; t += gridDim.x * TIE_THREADS) {
+    const int2 ps = ties[t];
+    const int p = ps.x, s = ps.y;
+    const PairMeta m = meta[p];
+    const int N = m.N;
+    const double* ya = Ya + (size_t)p * Nmax * 3;
+    const double* yb = Yb + (size_t)p * Nmax * 3;
+    int idx[MAX_K];
+    load_sample(samples, seed, pair_id0 + (uint32_t)p, 0, s, H, p, N, k, idx);
+    Rigid f;
+    fit_sample(method, ya, yb, idx, k, f);
+    double es = 0.0;
+#pragma unroll 2
+    for (int i = 0; i < N; ++i) {
+      const double nr = residual_norm(f.R, f.t, ya + 3 * i, yb + 3 * i);
+      es = es + (nr < m.thr ? nr : 0.0);  // sum(normResidu(inliers)) in index order (:135); + 0.0 is exact
+    }
+    es_out[(size_t)p * H + s] = es;
+  }
+}
+
+constexpr int SELF_WARPS = 4;
+
+__global__ void __launch_bounds__(SELF_WARPS * 32)
+k_sel_final(const PairMeta* __restrict__ meta, const double* __restrict__ Ya, const double* __restrict__ Yb, int P,
+            int Nmax, const int32_t* __restrict__ samples, uint64_t seed, uint32_t pair_id0, int H, int k, int method,
+            const int32_t* __restrict__ counts, const int8_t* __restrict__ states, const SelInfo* __restrict__ info,
+            const double* __restrict__ es_in, pre3_pair_result* __restrict__ res, uint8_t* __restrict__ masks,
+            int mask_stride, uint8_t* __restrict__ mask_scratch) {
+  const int p = blockIdx.x * SELF_WARPS + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (p >= P) return;
+  const SelInfo si = info[p];
+  if (si.status != 0) return;  // result already written by k_sel_scan
   const PairMeta m = meta[p];
   const int N = m.N;
   const double* ya = Ya + (size_t)p * Nmax * 3;
@@ -877,173 +853,69 @@ k_select_warp(const PairMeta* __restrict__ meta, const double* __restrict__ Ya, 
   const int32_t* cnt = counts + (size_t)p * H;
   const int8_t* sts = states + (size_t)p * H;
   uint8_t* mask = masks ? masks + (size_t)p * mask_stride : mask_scratch + (size_t)p * Nmax;
-  pre3_pair_result* out = res + p;
-  auto init_out = [&](int status, int n_consumed) {
-    if (lane == 0) {
-      out->status = status;
-      out->state = 0;
-      out->best_fit = 0;
-      out->best_sample = -1;
-      out->best_iter = 0;
-      out->n_iter = 0;
-      out->n_consumed = n_consumed;
-      out->n_matches = N;
-      out->thr = m.thr;
-      out->error_sum = 0.0;
-      for (int i = 0; i < 9; ++i) out->R[i] = out->R_hyp[i] = 0.0;
-      for (int i = 0; i < 3; ++i) out->T[i] = out->T_hyp[i] = 0.0;
-    }
-  };
-  if (N < k || N <= 0) {  // get_rand(k, N) errors in the reference (get_rand.m:39-41)
-    init_out(1, 0);
-    for (int i = lane; i < H; i += 32) {
-      if (counts_out) counts_out[(size_t)p * H + i] = -1;
-      if (states_out) states_out[(size_t)p * H + i] = 0;
-    }
-    if (masks)
-      for (int i = lane; i < mask_stride; i += 32) mask[i] = 0;
-    return;
-  }
-  const int32_t* trow = tab ? tab + m.pad : nullptr;
   auto recorded = [&](int s) { return !(method == PRE3_METHOD_SVD && sts[s] == -1); };
 
-  // ---- 1. loop control as a prefix scan (RANSAC_CALC_VER2.m:86, :97-99, :137-140) -----------
-  int S_end = H;
-  {
-    const int ipt = (H + 31) / 32;
-    const int lo = min(H, lane * ipt), hi = min(H, lo + ipt);
-    int lc = 0, lm = 0;
-    for (int s = lo; s < hi; ++s)
-      if (recorded(s)) {
-        ++lc;
-        lm = max(lm, cnt[s]);
-      }
-    int pc = lc, pm = lm;
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-      const int c = __shfl_up_sync(0xffffffffu, pc, off);
-      const int x = __shfl_up_sync(0xffffffffu, pm, off);
-      if (lane >= off) {
-        pc += c;
-        pm = max(pm, x);
-      }
-    }
-    pc = __shfl_up_sync(0xffffffffu, pc, 1);
-    pm = __shfl_up_sync(0xffffffffu, pm, 1);
-    if (lane == 0) {
-      pc = 0;
-      pm = 0;
-    }
-    int my_stop = H;
-    for (int s = lo; s < hi; ++s) {
-      int nit = max_iteration;
-      if (adaptive && pm >= 5) nit = min(trow[min(pm, N)], max_iteration);
-      if (!(1 + pc < nit)) {
-        my_stop = s;
-        break;
-      }
-      if (recorded(s)) {
-        ++pc;
-        pm = max(pm, cnt[s]);
-      }
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) my_stop = min(my_stop, __shfl_xor_sync(0xffffffffu, my_stop, off));
-    S_end = my_stop;
-  }
-
-  // ---- 2. max cardinality, number recorded ---------------------------------------------------
-  int maxc = -1, n_iter = 0;
-  for (int s = lane; s < S_end; s += 32)
-    if (recorded(s)) {
-      maxc = max(maxc, cnt[s]);
-      ++n_iter;
-    }
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
-    maxc = max(maxc, __shfl_xor_sync(0xffffffffu, maxc, off));
-    n_iter += __shfl_xor_sync(0xffffffffu, n_iter, off);
-  }
-  if (counts_out || states_out)
-    for (int s = lane; s < H; s += 32) {
-      const bool consumed = s < S_end;
-      const bool rec = consumed && recorded(s);
-      if (counts_out) counts_out[(size_t)p * H + s] = rec ? cnt[s] : -1;
-      if (states_out) states_out[(size_t)p * H + s] = consumed ? sts[s] : (int8_t)0;
-    }
-  if (n_iter < 1) {  // nothing recorded: M(1).ErrorSum = [] in the reference -> error
-    init_out(2, S_end);
-    if (masks)
-      for (int i = lane; i < mask_stride; i += 32) mask[i] = 0;
-    return;
-  }
-
-  // ---- 3. selection :165-175: among max-cardinality hypotheses min ErrorSum, first on ties;
-  //         every other recorded hypothesis enters the min() with 10000 ------------------------
+  // ---- min ErrorSum over the ties, first index on equal sums -------------------------------------
   double best_es = INFINITY;
-  int best_s = 0x7fffffff, first_nonmax = 0x7fffffff, win_iter = 0;
-  {
-    int rec_before = 0;  // recorded hypotheses before the current 32-chunk
-    for (int sbase = 0; sbase < S_end; sbase += 32) {
-      const int s = sbase + lane;
-      const bool rec = s < S_end && recorded(s);
-      const bool is_tie = rec && maxc > 0 && cnt[s] == maxc;
-      const bool nonmax = rec && !is_tie;
-      const unsigned recb = __ballot_sync(0xffffffffu, rec);
-      unsigned tieb = __ballot_sync(0xffffffffu, is_tie);
-      const unsigned nmb = __ballot_sync(0xffffffffu, nonmax);
-      if (nmb && first_nonmax == 0x7fffffff) first_nonmax = sbase + __ffs(nmb) - 1;
-      while (tieb) {
-        const int l = __ffs(tieb) - 1;
-        tieb &= tieb - 1;
-        const int st = sbase + l;
-        int idx[MAX_K];
-        load_sample(samples, seed, pair_id0 + (uint32_t)p, 0, st, H, p, N, k, idx);
-        Rigid f;
-        fit_sample(method, ya, yb, idx, k, f);  // every lane computes the same fit
-        const double es = warp_errsum(f.R, f.t, ya, yb, N, m.thr, nullptr, nullptr);
-        if (es < best_es) {  // strict: first index wins ties
+  int best_s = 0x7fffffff;
+  if (si.n_ties > 0) {
+    for (int s = lane; s < si.S_end; s += 32)
+      if (recorded(s) && cnt[s] == si.maxc) {
+        const double es = es_in[(size_t)p * H + s];
+        if (es < best_es) {  // ascending s within a lane: strict < keeps the first
           best_es = es;
-          best_s = st;
-          win_iter = rec_before + __popc(recb & ((2u << l) - 1u));
+          best_s = s;
         }
       }
-      rec_before += __popc(recb);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const double oe = __shfl_xor_sync(0xffffffffu, best_es, off);
+      const int os = __shfl_xor_sync(0xffffffffu, best_s, off);
+      if (oe < best_es || (oe == best_es && os < best_s)) {
+        best_es = oe;
+        best_s = os;
+      }
     }
   }
   int win = best_s;
+  const int fn = si.first_nonmax;
   if (best_s == 0x7fffffff) {
-    win = first_nonmax;  // maxc == 0: every entry is 10000 -> I = first recorded
-  } else if (first_nonmax != 0x7fffffff && (10000.0 < best_es || (10000.0 == best_es && first_nonmax < best_s))) {
-    win = first_nonmax;
+    win = fn;  // maxc == 0: every entry of eee1 is 10000 -> I = first recorded
+  } else if (fn != 0x7fffffff && (10000.0 < best_es || (10000.0 == best_es && fn < best_s))) {
+    win = fn;
   }
-  if (win != best_s) {  // BestFitIdx of a non-tie winner: recorded hypotheses up to and including it
-    int c = 0;
-    for (int s = lane; s <= win; s += 32) c += recorded(s) ? 1 : 0;
+  // BestFitIdx: recorded hypotheses up to and including the winner
+  int win_iter = 0;
+  for (int s = lane; s <= win; s += 32) win_iter += recorded(s) ? 1 : 0;
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
-    win_iter = c;
-  }
+  for (int off = 16; off > 0; off >>= 1) win_iter += __shfl_xor_sync(0xffffffffu, win_iter, off);
 
-  // ---- 4. winner: hypothesis, mask, ErrorSum; 5. refit on the support set (:186) --------------
+  // ---- winner: hypothesis, mask, ErrorSum; refit on the support set (:186) --------------------------
   int idx[MAX_K];
   load_sample(samples, seed, pair_id0 + (uint32_t)p, 0, win, H, p, N, k, idx);
   Rigid f;
-  fit_sample(method, ya, yb, idx, k, f);
-  const double es = warp_errsum(f.R, f.t, ya, yb, N, m.thr, mask, nullptr);
+  fit_sample(method, ya, yb, idx, k, f);  // every lane computes the same fit
+  double es;
+  if (win == best_s) {
+    es = best_es;
+    for (int i = lane; i < N; i += 32) mask[i] = residual_norm(f.R, f.t, ya + 3 * i, yb + 3 * i) < m.thr ? 1 : 0;
+  } else {
+    es = warp_errsum(f.R, f.t, ya, yb, N, m.thr, mask, nullptr);
+  }
   if (masks)
     for (int i = N + lane; i < mask_stride; i += 32) mask[i] = 0;
   __syncwarp();
   Rigid rf;
   const int st = warp_refit(method, ya, yb, mask, N, rf);
   if (lane == 0) {
+    pre3_pair_result* out = res + p;
     out->status = 0;
     out->state = st;
-    out->best_fit = maxc;
+    out->best_fit = si.maxc;
     out->best_sample = win;
     out->best_iter = win_iter;
-    out->n_iter = n_iter;
-    out->n_consumed = S_end;
+    out->n_iter = si.n_iter;
+    out->n_consumed = si.S_end;
     out->n_matches = N;
     out->thr = m.thr;
     out->error_sum = es;
@@ -1053,7 +925,6 @@ k_select_warp(const PairMeta* __restrict__ meta, const double* __restrict__ Ya, 
     for (int i = 0; i < 3; ++i) out->T_hyp[i] = f.t[i];
   }
 }
-
 // ------------------------------------------------------------------------------------------
 // stage-wise kernels
 // ------------------------------------------------------------------------------------------
@@ -1350,6 +1221,7 @@ size_t ransac_workspace_bytes(int P, int Nmax, int H) {
   b += align_up(sizeof(int32_t) * (size_t)P * H);
   b += align_up((size_t)P * H);
   b += align_up((size_t)P * Nmax);  // mask scratch
+  b += align_up(sizeof(SelInfo) * (size_t)P) + 2 * align_up(8 * (size_t)P * (H > 0 ? H : 1)) + 512;  // selection
   b += align_up(sizeof(int32_t) * (size_t)P);  // stop flags
   return b + 4096;
 }
@@ -1454,17 +1326,39 @@ int launch_eval(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts& o
 // scan decides per pair whether its loop has already ended (typically within the first 256
 // sample sets at SR4000 inlier ratios); later waves skip those pairs.  Entries that are never
 // evaluated stay zeroed and lie beyond the stop index, so k_select never reads them.
-int launch_eval_waves(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts& o) {
-  if (b.P <= 0 || o.H <= 0) return PRE3_OK;
+// Wave boundaries of launch_eval_waves: ends[i] = number of sample sets evaluated after wave i.
+int eval_wave_ends(const pre3_ransac_opts& o, int32_t* ends, int cap) {
   const int H = o.H;
-  if (!o.adaptive || H <= 384) return launch_eval(ctx, b, o, 0, 0, H, nullptr);
-  PRE3_CUDA(cudaMemsetAsync(b.counts, 0, sizeof(int32_t) * (size_t)b.P * H, ctx->stream));
-  PRE3_CUDA(cudaMemsetAsync(b.states, 0, (size_t)b.P * H, ctx->stream));
-  PRE3_CUDA(cudaMemsetAsync(b.stop, 0xFF, sizeof(int32_t) * (size_t)b.P, ctx->stream));
+  int n = 0;
+  if (H <= 0) return 0;
+  if (!o.adaptive || H <= 384) {
+    if (n < cap) ends[n] = H;
+    return 1;
+  }
   int beg = 0, width = 256;
   while (beg < H) {
     int end = std::min(H, beg + width);
     if (H - end < 128) end = H;
+    if (n < cap) ends[n] = end;
+    ++n;
+    beg = end;
+    width *= 2;
+  }
+  return n;
+}
+
+int launch_eval_waves(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts& o) {
+  if (b.P <= 0 || o.H <= 0) return PRE3_OK;
+  const int H = o.H;
+  int32_t ends[40];
+  const int nw = eval_wave_ends(o, ends, 40);
+  if (nw <= 1) return launch_eval(ctx, b, o, 0, 0, H, nullptr);
+  PRE3_CUDA(cudaMemsetAsync(b.counts, 0, sizeof(int32_t) * (size_t)b.P * H, ctx->stream));
+  PRE3_CUDA(cudaMemsetAsync(b.states, 0, (size_t)b.P * H, ctx->stream));
+  PRE3_CUDA(cudaMemsetAsync(b.stop, 0xFF, sizeof(int32_t) * (size_t)b.P, ctx->stream));
+  int beg = 0;
+  for (int w = 0; w < nw; ++w) {
+    const int end = ends[w];
     PRE3_TRY(launch_eval(ctx, b, o, 0, beg, end, b.stop));
     if (end < H) {
       Span span__(ctx, T_SELECT);
@@ -1474,7 +1368,6 @@ int launch_eval_waves(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_o
       PRE3_CUDA(cudaGetLastError());
     }
     beg = end;
-    width *= 2;
   }
   return PRE3_OK;
 }
@@ -1483,18 +1376,30 @@ int launch_select(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts&
                   uint8_t* dmasks, int32_t* dcounts_out, int8_t* dstates_out) {
   Span span__(ctx, T_SELECT);
   if (b.P <= 0) return PRE3_OK;
+  const size_t PH = (size_t)b.P * std::max(o.H, 1);
   uint8_t* scratch = ws_take<uint8_t>(ctx, (size_t)b.P * b.Nmax);
-  if (b.P >= 32 && b.Nmax <= 4096)  // batches of pairs: one warp per pair; single big pairs: one block
-    k_select_warp<<<(b.P + SELW_WARPS - 1) / SELW_WARPS, SELW_WARPS * 32, 0, ctx->stream>>>(
-        b.meta, b.Ya, b.Yb, b.P, b.Nmax, b.samples, o.seed, b.pair_id0, o.H, o.k, o.method, o.max_iteration,
-        o.adaptive, o.adaptive ? ctx->d_tab : nullptr, b.counts, b.states, dres, dmasks, b.Nmax, scratch, dcounts_out,
-        dstates_out);
+  SelInfo* info = ws_take<SelInfo>(ctx, b.P);
+  double* es = ws_take<double>(ctx, PH);
+  int2* ties = ws_take<int2>(ctx, PH);
+  int* tie_total = ws_take<int>(ctx, 64);
+  if (PH >= ((size_t)1 << 31)) return fail(ctx, PRE3_ERR_ARG, "pairs x sample sets must stay below 2^31");
+  PRE3_CUDA(cudaMemsetAsync(tie_total, 0, sizeof(int), ctx->stream));
+  const int32_t* tab = o.adaptive ? ctx->d_tab : nullptr;
+  if (b.P >= 64)  // batches of pairs: one warp per pair; few (large) pairs: 1024 threads each
+    k_sel_scan<32><<<b.P, 32, 0, ctx->stream>>>(b.meta, b.Nmax, o.H, o.k, o.method, o.max_iteration, o.adaptive, tab,
+                                                b.counts, b.states, dres, dmasks, b.Nmax, dcounts_out, dstates_out,
+                                                info, ties, tie_total);
   else
-    k_select<<<b.P, SEL_THREADS, 0, ctx->stream>>>(b.meta, b.Ya, b.Yb, b.Nmax, b.samples, o.seed, b.pair_id0, 0, o.H,
-                                                   o.k, o.method, o.max_iteration, o.adaptive,
-                                                   o.adaptive ? ctx->d_tab : nullptr, b.counts, b.states, dres,
-                                                   dmasks, b.Nmax, scratch, dcounts_out, dstates_out);
-  count_launch(ctx);
+    k_sel_scan<1024><<<b.P, 1024, 0, ctx->stream>>>(b.meta, b.Nmax, o.H, o.k, o.method, o.max_iteration, o.adaptive,
+                                                    tab, b.counts, b.states, dres, dmasks, b.Nmax, dcounts_out,
+                                                    dstates_out, info, ties, tie_total);
+  const int tie_blocks = (int)std::min<size_t>((PH + TIE_THREADS - 1) / TIE_THREADS, (size_t)ctx->sm_count * 8);
+  k_sel_tie<<<tie_blocks, TIE_THREADS, 0, ctx->stream>>>(b.meta, b.Ya, b.Yb, b.Nmax, b.samples, o.seed, b.pair_id0, o.H,
+                                                         o.k, o.method, ties, tie_total, (int)PH, es);
+  k_sel_final<<<(b.P + SELF_WARPS - 1) / SELF_WARPS, SELF_WARPS * 32, 0, ctx->stream>>>(
+      b.meta, b.Ya, b.Yb, b.P, b.Nmax, b.samples, o.seed, b.pair_id0, o.H, o.k, o.method, b.counts, b.states, info, es,
+      dres, dmasks, b.Nmax, scratch);
+  count_launch(ctx, 3);
   PRE3_CUDA(cudaGetLastError());
   return PRE3_OK;
 }

@@ -39,6 +39,7 @@ int launch_prep(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts& o
 int launch_eval(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts& o, long long h0, int hbeg, int hend,
                 const int32_t* stop);
 int launch_eval_waves(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts& o);
+int eval_wave_ends(const pre3_ransac_opts& o, int32_t* ends, int cap);
 int launch_select(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts& o, pre3_pair_result* dres,
                   uint8_t* dmasks, int32_t* dcounts_out, int8_t* dstates_out);
 int ensure_adaptive_table(pre3_ctx* ctx, const pre3_ransac_opts& o, int Nmax);

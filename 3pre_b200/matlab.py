@@ -69,7 +69,8 @@ def siftmatch(L1, L2, thresh=1.5, nargout=1):
     if L1.dtype not in (np.float64, np.float32, np.int8, np.uint8):
         raise MexError("Unsupported numeric class")  # :213-215
     thr = float(np.asarray(thresh).reshape(-1)[0])
-    pairs, score = context().siftmatch(np.ascontiguousarray(L1.T), np.ascontiguousarray(L2.T), thr)
+    pairs, score = context().siftmatch(np.ascontiguousarray(L1.T), np.ascontiguousarray(L2.T), thr,
+                                       want_score=nargout == 2)
     matches = (pairs.T + 1).astype(np.float64)  # 1-based [k1; k2]  (:241-242)
     if nargout == 2:
         return matches, score

@@ -104,6 +104,12 @@ PRE3_API int pre3_set_match_engine(pre3_ctx *ctx, int engine);
 PRE3_API int pre3_sync(pre3_ctx *ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 PRE3_API int64_t pre3_launch_count(const pre3_ctx *ctx);
+/* With the adaptive stop on, the batch entry points evaluate the sample sets of a pair in waves
+ * and skip the later waves of pairs whose loop (RANSAC_CALC_VER2.m:86) has already ended.
+ * Writes the wave boundaries (sample sets evaluated after wave i) into ends[0..cap) and returns the
+ * number of waves: a pair that consumed n sets had ends[min{i : n < ends[i]}] (or H) sets evaluated.
+ * bench.py derives the executed hypothesis x match evaluations from this. */
+PRE3_API int pre3_eval_schedule(const pre3_ransac_opts *opts, int32_t *ends, int cap);
 /* Per-kernel CUDA-event timing on the context's stream (off by default; bench.py's roofline
  * numbers).  pre3_timing_read synchronises, adds the elapsed ms and launch counts of every
  * bracketed launch since the last read into ms[cat] / count[cat] (PRE3_TIMING_NCAT entries
