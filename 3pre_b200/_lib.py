@@ -15,7 +15,7 @@ OK, ERR_ARG, ERR_CUDA, ERR_ALLOC, ERR_CLASS = 0, -1, -2, -3, -4
 CLASS_DOUBLE, CLASS_SINGLE, CLASS_INT8, CLASS_UINT8 = 0, 1, 2, 3
 METHOD_SVD, METHOD_HORN = 0, 1
 MATCH_AUTO, MATCH_EXACT, MATCH_TC = 0, 1, 2
-TIMING_NCAT = 9
+TIMING_NCAT = 12
 
 
 class RansacOpts(C.Structure):
@@ -53,6 +53,23 @@ class PairResult(C.Structure):
     ]
 
 
+class Cam(C.Structure):
+    """pre3_cam"""
+    _fields_ = [("f", C.c_double), ("Cx", C.c_double), ("Cy", C.c_double), ("k1", C.c_double), ("k2", C.c_double)]
+
+
+class EkfOpts(C.Structure):
+    """pre3_ekf_opts"""
+    _fields_ = [("n_hyp_init", C.c_int32), ("H", C.c_int32), ("adaptive", C.c_int32), ("reserved", C.c_int32),
+                ("seed", C.c_uint64)]
+
+
+class EkfResult(C.Structure):
+    """pre3_ekf_result (32 bytes)"""
+    _fields_ = [("status", C.c_int32), ("n_evaluated", C.c_int32), ("best_hyp", C.c_int32),
+                ("max_support", C.c_int32), ("num_ic", C.c_int32), ("m", C.c_int32), ("n_hyp", C.c_double)]
+
+
 # name -> (restype, argtypes); every symbol include/pre3.h declares
 _VP, _I, _D, _I64, _U32, _U64 = C.c_void_p, C.c_int, C.c_double, C.c_int64, C.c_uint32, C.c_uint64
 _OPTS = C.POINTER(RansacOpts)
@@ -86,6 +103,13 @@ SYMBOLS = {
     "pre3_ransac_finish_dev": (_I, [_VP, _VP, _VP, _I, _OPTS, _VP, _I64, _D, _VP, _VP]),
     "pre3_distance_threshold_dev": (_I, [_VP, _VP, _I, _VP]),
     "pre3_R2q": (None, [_VP, _VP]),
+    "pre3_ekf_support": (_I, [_VP, _VP, _I, _I, C.POINTER(Cam), _VP, _VP, _I, _VP, _I, _D, _VP, _VP, _VP]),
+    "pre3_ransac_hypotheses_batch": (_I, [_VP, _I, _I, _I, _VP, _VP, _D, C.POINTER(Cam), _VP, _VP, _VP, _VP, _VP, _VP,
+                                          _VP, _VP, _VP, _VP, C.POINTER(EkfOpts), _U32, _VP, _VP, _VP]),
+    "pre3_ransac_hypotheses_batch_dev": (_I, [_VP, _I, _I, _I, _VP, _VP, _D, C.POINTER(Cam), _VP, _VP, _VP, _VP, _VP,
+                                              _VP, _VP, _VP, _VP, _VP, C.POINTER(EkfOpts), _U32, _VP, _VP, _VP]),
+    "pre3_ekf_eval_schedule": (_I, [C.POINTER(EkfOpts), _VP, _I]),
+    "pre3_measure_fp64_peak": (_I, [_VP, _VP]),
 }
 
 _lib = None

@@ -16,7 +16,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _lib as L
-from ._lib import Pre3Error, RansacOpts, PairResult
+from ._lib import Pre3Error, RansacOpts, PairResult, Cam, EkfOpts, EkfResult
 
 _CLS = {
     np.dtype(np.float64): L.CLASS_DOUBLE,
@@ -31,6 +31,9 @@ RESULT_DTYPE = np.dtype(
      ("R", "<f8", (9,)), ("T", "<f8", (3,)), ("R_hyp", "<f8", (9,)), ("T_hyp", "<f8", (3,))]
 )
 assert RESULT_DTYPE.itemsize == C.sizeof(PairResult) == 240
+EKF_RESULT_DTYPE = np.dtype([("status", "<i4"), ("n_evaluated", "<i4"), ("best_hyp", "<i4"), ("max_support", "<i4"),
+                             ("num_ic", "<i4"), ("m", "<i4"), ("n_hyp", "<f8")])
+assert EKF_RESULT_DTYPE.itemsize == C.sizeof(EkfResult) == 32
 
 
 def _ptr(a):
@@ -51,6 +54,18 @@ def make_opts(method=L.METHOD_SVD, k=5, max_iteration=2000, adaptive=True, H=200
     plus the explicit knobs the reference hard-codes (k: RANSAC_CALC_VER2.m:85)."""
     return RansacOpts(int(method), int(k), int(max_iteration), int(bool(adaptive)), int(H), 0,
                       float(distance_threshold), float(ratio), int(seed))
+
+
+def make_cam(cam) -> Cam:
+    """cam struct fields used on the path (M/initialize_cam.m:64-76); accepts a dict or a Cam."""
+    if isinstance(cam, Cam):
+        return cam
+    return Cam(float(cam["f"]), float(cam["Cx"]), float(cam["Cy"]), float(cam["k1"]), float(cam["k2"]))
+
+
+def make_ekf_opts(n_hyp_init=1000, H=1000, adaptive=True, seed=0) -> EkfOpts:
+    """n_hyp_init: ransac_hypotheses.m:35; H: selections available; adaptive: the stop rule :77-80."""
+    return EkfOpts(int(n_hyp_init), int(H), int(bool(adaptive)), 0, int(seed))
 
 
 @dataclass
@@ -159,6 +174,18 @@ class Context:
         self._ck(self._lib.pre3_timing_read(self._h, _ptr(ms), _ptr(cnt)))
         return {self._lib.pre3_timing_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(L.TIMING_NCAT)
                 if cnt[i]}
+
+    def measure_fp64_peak(self) -> float:
+        v = C.c_double(0.0)
+        self._ck(self._lib.pre3_measure_fp64_peak(self._h, C.byref(v)))
+        return v.value
+
+    def ekf_eval_schedule(self, opts: EkfOpts):
+        ends = np.zeros(40, np.int32)
+        n = self._lib.pre3_ekf_eval_schedule(C.byref(opts), _ptr(ends), 40)
+        if n < 0:
+            raise Pre3Error(n, "pre3_ekf_eval_schedule")
+        return ends[:n].copy()
 
     def measure_fp32_peak(self) -> float:
         """FFMA-chain microbenchmark, TFLOP/s (the scoring roofline's denominator)."""
@@ -318,6 +345,69 @@ class Context:
                                       _ptr(k1c), _ptr(k2c), C.byref(o), int(pair_id0), _ptr(res), _ptr(matches),
                                       _ptr(masks)))
         return res[:P], (matches[:P] if matches is not None else None), (masks[:P] if masks is not None else None)
+
+    # ---- config 4: 1-point-RANSAC EKF hypotheses -------------------------------------------
+    def ekf_support(self, xi, cam, pattern, z_id, z_euc, threshold):
+        """compute_hypothesis_support_fast.m:27-116 for B states.  xi (B,n) [= n x B column-major];
+        pattern (n,4) 0/1; z_id (n_id,2), z_euc (n_euc,2) [= 2 x n column-major].
+        Returns support (B,) int32, li_id (B,n_id) bool, li_euc (B,n_euc) bool."""
+        xi = _c(np.atleast_2d(xi), np.float64)
+        B, n = xi.shape
+        pat = _c(np.asarray(pattern, np.float64).T)  # column-major n x 4
+        if pat.shape != (4, n):
+            raise ValueError("state_vector_pattern must be n x 4")
+        zi, ze = _c(z_id, np.float64).reshape(-1, 2), _c(z_euc, np.float64).reshape(-1, 2)
+        n_id, n_euc = len(zi), len(ze)
+        sup = np.zeros(max(B, 1), np.int32)
+        li = np.zeros((max(B, 1), max(n_id, 1)), np.uint8)
+        le = np.zeros((max(B, 1), max(n_euc, 1)), np.uint8)
+        c = make_cam(cam)
+        self._ck(self._lib.pre3_ekf_support(self._h, _ptr(xi), n, B, C.byref(c), _ptr(pat), _ptr(zi), n_id, _ptr(ze),
+                                            n_euc, float(threshold), _ptr(sup), _ptr(li), _ptr(le)))
+        return sup[:B], li.reshape(-1)[:B * n_id].reshape(B, n_id).astype(bool), \
+            le.reshape(-1)[:B * n_euc].reshape(B, n_euc).astype(bool)
+
+    def ransac_hypotheses_batch(self, frames: dict, sel=None, opts: EkfOpts | None = None, frame_id0=0,
+                                want_supports=False, **kw):
+        """ransac_hypotheses.m:27-85 for Fr frames.  `frames`: dict of numpy arrays with a leading
+        frame axis -- x (Fr,n), P (Fr,n,n) column-major per frame, type/pos (Fr,F) int32,
+        has_z/ic/li0 (Fr,F) uint8, z/h (Fr,F,2), Hcam (Fr,F,13,2), Hfeat (Fr,F,6,2), R (Fr,F,2,2), plus
+        scalars std_z and cam (3pre_b200.synth_ekf layout).  sel: (Fr,H,3) int32 or None (seeded).
+        Returns (results (Fr,) EKF_RESULT_DTYPE, li_inlier (Fr,F) uint8, supports (Fr,H) | None)."""
+        x, P = _c(frames["x"], np.float64), _c(frames["P"], np.float64)
+        Fr, n = x.shape
+        F = np.asarray(frames["type"]).shape[1]
+        o = opts or make_ekf_opts(**kw)
+        if sel is not None:
+            sel = _c(sel, np.int32)
+            if sel.shape != (Fr, o.H, 3):
+                raise ValueError("sel must be (Fr, H, 3)")
+        ty, po = _c(frames["type"], np.int32), _c(frames["pos"], np.int32)
+        hz, ic = _c(frames["has_z"], np.uint8), _c(frames["ic"], np.uint8)
+        li = _c(frames["li0"], np.uint8).copy()
+        z, h = _c(frames["z"], np.float64), _c(frames["h"], np.float64)
+        Hc, Hf, R = _c(frames["Hcam"], np.float64), _c(frames["Hfeat"], np.float64), _c(frames["R"], np.float64)
+        res = np.zeros(max(Fr, 1), EKF_RESULT_DTYPE)
+        sup = np.zeros((max(Fr, 1), max(o.H, 1)), np.int32) if want_supports else None
+        c = make_cam(frames["cam"])
+        self._ck(self._lib.pre3_ransac_hypotheses_batch(
+            self._h, Fr, n, F, _ptr(x), _ptr(P), float(frames["std_z"]), C.byref(c), _ptr(ty), _ptr(po), _ptr(hz),
+            _ptr(ic), _ptr(z), _ptr(h), _ptr(Hc), _ptr(Hf), _ptr(R), _ptr(sel), C.byref(o), int(frame_id0), _ptr(li),
+            _ptr(res), _ptr(sup)))
+        return res[:Fr], li[:Fr], (sup[:Fr] if sup is not None else None)
+
+    def ransac_hypotheses_batch_dev(self, frames: dict, opts: EkfOpts, li_inlier, res, sel=None, supports=None,
+                                    frame_id0=0):
+        """Same on CUDA tensors (3pre_b200.synth_ekf.make_ekf_frames(device='cuda') layout);
+        res: uint8 (Fr,32); li_inlier: uint8 (Fr,F) in/out.  Stream-ordered, no sync."""
+        Fr, n = frames["x"].shape
+        F = frames["type"].shape[1]
+        c = make_cam(frames["cam"])
+        self._ck(self._lib.pre3_ransac_hypotheses_batch_dev(
+            self._h, Fr, n, F, _ptr(frames["x"]), _ptr(frames["P"]), float(frames["std_z"]), C.byref(c),
+            _ptr(frames["type"]), _ptr(frames["pos"]), _ptr(frames["has_z"]), _ptr(frames["ic"]), _ptr(frames["z"]),
+            _ptr(frames["h"]), _ptr(frames["Hcam"]), _ptr(frames["Hfeat"]), _ptr(frames["R"]), _ptr(sel),
+            C.byref(opts), int(frame_id0), _ptr(li_inlier), _ptr(res), _ptr(supports)))
 
     # ---- device-pointer entry points (torch CUDA tensors, stream-ordered, no sync) --------
     def pairs_dev(self, desc1, desc2, xyz1, xyz2, opts: RansacOpts, res, matches=None, masks=None, pair_id0=0,

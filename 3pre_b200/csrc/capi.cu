@@ -158,6 +158,7 @@ void pre3_destroy(pre3_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->d_tab) cudaFree(ctx->d_tab);
+    if (ctx->d_ekf_tab) cudaFree(ctx->d_ekf_tab);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     for (void* p : ctx->aux) cudaFree(p);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
@@ -224,7 +225,8 @@ int pre3_timing_read(pre3_ctx* ctx, double* ms, int64_t* count) {
 
 const char* pre3_timing_name(int cat) {
   static const char* names[T_NCAT] = {"convert", "match_tc", "match_exact", "rescore", "compact",
-                                      "prep",    "eval",     "select",      "other"};
+                                      "prep",    "eval",     "select",      "other",   "ekf_gain",
+                                      "ekf_score", "ekf_select"};
   return (cat >= 0 && cat < T_NCAT) ? names[cat] : "?";
 }
 

@@ -11,7 +11,7 @@
 
 namespace pre3 {
 // per-kernel timing categories (pre3_timing_*): bench.py's roofline numbers come from here
-enum TimeCat { T_CONVERT = 0, T_MATCH_TC, T_MATCH_EXACT, T_RESCORE, T_COMPACT, T_PREP, T_EVAL, T_SELECT, T_OTHER, T_NCAT };
+enum TimeCat { T_CONVERT = 0, T_MATCH_TC, T_MATCH_EXACT, T_RESCORE, T_COMPACT, T_PREP, T_EVAL, T_SELECT, T_OTHER, T_EKF_GAIN, T_EKF_SCORE, T_EKF_SELECT, T_NCAT };
 struct TimedSpan {
   int cat;
   cudaEvent_t a, b;
@@ -34,6 +34,9 @@ struct pre3_ctx {
   // cached adaptive-iteration tables, keyed by (k, mult, Nmax, max_iteration)
   int tab_k = -1, tab_mult = -1, tab_nmax = -1, tab_maxit = -1;
   int32_t* d_tab = nullptr;       // triangular: row N starts at N*(N+1)/2, entries c = 0..N
+  // cached n_hyp table of the EKF path: (F+1) x (F+1) doubles, row num_ic, column support
+  double* d_ekf_tab = nullptr;
+  int ekf_tab_F = -1;
   // pinned staging for small results
   void* h_pin = nullptr;
   size_t h_pin_cap = 0;

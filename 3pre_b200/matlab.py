@@ -168,3 +168,117 @@ def Calculate_V_Omega_RANSAC_my_version(DataPre, DataCurrent, **kw):
     (q = R2q(R), [w x y z] with the slamToolbox sign convention)."""
     out = SIFT_match_save(DataPre, DataCurrent, **kw)
     return out["T_RANSAC"], R2q(out["R_RANSAC"]).reshape(4, 1), out["R_RANSAC"], out["State_RANSAC"]
+
+
+# ---------------------------------------------------------------------------------------
+# config 4: the 1-point-RANSAC EKF hypothesis path
+# ---------------------------------------------------------------------------------------
+StatData = {}  # the reference's global (M/ransac_hypotheses.m:34,84-85)
+
+
+def compute_hypothesis_support_fast(xi, cam, state_vector_pattern, z_id, z_euc, threshold):
+    """[hypothesis_support, positions_li_inliers_id, positions_li_inliers_euc] =
+    compute_hypothesis_support_fast(xi, cam, state_vector_pattern, z_id, z_euc, threshold)
+    (M/compute_hypothesis_support_fast.m:27-116).  xi: n x 1; pattern: n x 4; z_id: 2 x n_id or [];
+    z_euc: 2 x n_euc or [].  Empty measurement sets give [] masks (:73-77,:112-116)."""
+    xi = np.asarray(xi, np.float64).reshape(-1)
+    z_id = np.asarray(z_id, np.float64)
+    z_euc = np.asarray(z_euc, np.float64)
+    zi = np.ascontiguousarray(z_id.T) if z_id.size else np.zeros((0, 2))
+    ze = np.ascontiguousarray(z_euc.T) if z_euc.size else np.zeros((0, 2))
+    try:
+        sup, li, le = context().ekf_support(xi[None, :], cam, state_vector_pattern, zi, ze, float(threshold))
+    except L.Pre3Error as e:
+        if e.code == L.ERR_ARG:
+            raise MexError(str(e)) from None
+        raise
+    return int(sup[0]), (li[0] if z_id.size else np.zeros(0, bool)), (le[0] if z_euc.size else np.zeros(0, bool))
+
+
+def _field(obj, name):
+    return obj[name] if isinstance(obj, dict) else getattr(obj, name)
+
+
+def features_to_frame(filter, features_info, cam):
+    """Unmarshal (filter, features_info, cam) the way ransac_hypotheses_mex.cpp does: per-feature
+    type / state offset (generate_state_vector_pattern.m:30-51), measurement flags, z, h, the
+    camera and feature blocks of H (calculate_Hi_inverse_depth_my_version.m:44-49 -- any other
+    non-zero of H is an error) and R.  Returns the frames dict Context.ransac_hypotheses_batch takes."""
+    x = np.asarray(_field(filter, "x_k_km1"), np.float64).reshape(-1)
+    P = np.asarray(_field(filter, "p_k_km1"), np.float64)
+    n, F = len(x), len(features_info)
+    if P.shape != (n, n):
+        raise MexError("p_k_km1 must be n x n")
+    ty, pos = np.zeros(F, np.int32), np.zeros(F, np.int32)
+    hz, ic, li = np.zeros(F, np.uint8), np.zeros(F, np.uint8), np.zeros(F, np.uint8)
+    z, h = np.zeros((F, 2)), np.zeros((F, 2))
+    Hc, Hf, R = np.zeros((F, 13, 2)), np.zeros((F, 6, 2)), np.zeros((F, 2, 2))
+    p = 13
+    for i, fi in enumerate(features_info):
+        t = str(_field(fi, "type"))
+        if t == "inversedepth":
+            ty[i], nf = 0, 6
+        elif t == "cartesian":
+            ty[i], nf = 1, 3
+        else:
+            raise MexError("feature type must be 'inversedepth' or 'cartesian'")
+        pos[i] = p
+        p += nf
+        zi = np.asarray(_field(fi, "z"), np.float64).reshape(-1)
+        hz[i] = zi.size > 0
+        ic[i] = bool(_field(fi, "individually_compatible"))
+        li[i] = bool(fi.get("low_innovation_inlier", 0)) if isinstance(fi, dict) else bool(getattr(fi, "low_innovation_inlier", 0))
+        if ic[i] or hz[i]:
+            if zi.size:
+                z[i] = zi[:2]
+            h[i] = np.asarray(_field(fi, "h"), np.float64).reshape(-1)[:2]
+            Hi = np.asarray(_field(fi, "H"), np.float64)
+            if Hi.shape != (2, n):
+                raise MexError("features_info(i).H must be 2 x n")
+            rest = Hi.copy()
+            rest[:, :13] = 0
+            rest[:, pos[i]:pos[i] + nf] = 0
+            if np.any(rest != 0):
+                raise MexError("pre3:ekf: H has non-zeros outside the camera and the feature's own block")
+            Hc[i] = Hi[:, :13].T
+            Hf[i, :nf] = Hi[:, pos[i]:pos[i] + nf].T
+            R[i] = np.asarray(_field(fi, "R"), np.float64).T
+    if p != n:
+        raise MexError("state size does not match the features (13 + 6 n_id + 3 n_euc)")
+    return dict(x=x[None], P=np.ascontiguousarray(P.T)[None], type=ty[None], pos=pos[None], has_z=hz[None], ic=ic[None],
+                li0=li[None], z=z[None], h=h[None], Hcam=Hc[None], Hfeat=Hf[None], R=R[None],
+                std_z=float(_field(filter, "std_z")), cam=cam, n=n, F=F)
+
+
+def ransac_hypotheses(filter, features_info, cam, *, selections=None, seed=0, n_hyp=1000, adaptive=True):
+    """features_info = ransac_hypotheses(filter, features_info, cam)  (M/ransac_hypotheses.m:27-85).
+    filter: dict / object with x_k_km1, p_k_km1, std_z (what get_x_k_km1 / get_p_k_km1 / get_std_z
+    return); features_info: list of dicts (fields h, z, H, R, type, individually_compatible);
+    cam: dict with f, Cx, Cy, k1, k2.  Returns a copy of features_info with low_innovation_inlier
+    set like set_as_most_supported_hypothesis.m:32-53 and fills StatData (:84-85).
+    selections (optional): 3 x H matrix of 1-based feature positions, one column per hypothesis,
+    as select_random_match.m:58 would have returned them."""
+    from .api import make_ekf_opts
+    fr = features_to_frame(filter, features_info, cam)
+    sel = None
+    H = int(n_hyp)
+    if selections is not None:
+        s = np.asarray(selections)
+        H = s.shape[1]
+        sel = np.zeros((1, H, 3), np.int32)
+        sel[0, :, :s.shape[0]] = s.T.astype(np.int32) - 1
+    o = make_ekf_opts(n_hyp_init=n_hyp, H=H, adaptive=adaptive, seed=seed)
+    res, li, _ = context().ransac_hypotheses_batch(fr, sel, o)
+    if res["status"][0] == 1:
+        raise MexError("select_random_match: Index exceeds matrix dimensions (no individually compatible match)")
+    if res["status"][0] == 3:
+        raise MexError("an individually compatible feature has no measurement z")
+    out = []
+    for i, fi in enumerate(features_info):
+        g = dict(fi) if isinstance(fi, dict) else dict(vars(fi))
+        if fr["has_z"][0, i] and res["best_hyp"][0] >= 0:
+            g["low_innovation_inlier"] = int(li[0, i])
+        out.append(g)
+    StatData["RANSAC_ITER"] = float(res["n_hyp"][0])
+    StatData["RANSAC_HYP_SUPPORT"] = int(res["max_support"][0])
+    return out

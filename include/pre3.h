@@ -114,7 +114,7 @@ PRE3_API int pre3_eval_schedule(const pre3_ransac_opts *opts, int32_t *ends, int
  * numbers).  pre3_timing_read synchronises, adds the elapsed ms and launch counts of every
  * bracketed launch since the last read into ms[cat] / count[cat] (PRE3_TIMING_NCAT entries
  * each, caller-zeroed) and forgets them.  pre3_timing_name(cat) names a category. */
-#define PRE3_TIMING_NCAT 9
+#define PRE3_TIMING_NCAT 12
 PRE3_API int pre3_timing_enable(pre3_ctx *ctx, int on);
 PRE3_API int pre3_timing_read(pre3_ctx *ctx, double *ms, int64_t *count);
 PRE3_API const char *pre3_timing_name(int cat);
@@ -218,6 +218,74 @@ PRE3_API int pre3_ransac_finish_dev(pre3_ctx *ctx, const double *dYa, const doub
                            int64_t winner_id, double thr, pre3_pair_result *dres, uint8_t *dmask);
 /* thr := 0.01*||Yb(:,argmin z)|| (RANSAC_CALC_VER2.m:69-72), computed on the device. */
 PRE3_API int pre3_distance_threshold_dev(pre3_ctx *ctx, const double *dYb, int N, double *dthr);
+
+/* ---- config 4: 1-point-RANSAC EKF hypotheses --------------------------------------------
+ * ransac_hypotheses (M/ransac_hypotheses.m:27-85) and compute_hypothesis_support_fast
+ * (M/compute_hypothesis_support_fast.m:27-116).  fp64 throughout; sin/cos and inv(S) follow the
+ * fixed-order algorithms specified in oracle/pre3_oracle_ekf.c. */
+typedef struct {
+  double f, Cx, Cy, k1, k2; /* cam.f, cam.Cx, cam.Cy, cam.k1, cam.k2 (M/initialize_cam.m:64-76) */
+} pre3_cam;
+
+typedef struct {
+  int32_t n_hyp_init; /* 1000 (ransac_hypotheses.m:35) */
+  int32_t H;          /* match selections available per frame (the loop also ends when they run out) */
+  int32_t adaptive;   /* 1: the reference's stop rule (:77-80); 0: evaluate all H, first maximum wins */
+  int32_t reserved;
+  uint64_t seed;      /* seeded selections (used when none are supplied) */
+} pre3_ekf_opts;
+
+typedef struct {
+  int32_t status;      /* 0 ok; 1 no individually compatible match (select_random_match.m:50 errors);
+                          3 an individually compatible feature has no measurement z */
+  int32_t n_evaluated; /* hypotheses the reference's loop evaluates */
+  int32_t best_hyp;    /* 0-based index of the most supported hypothesis, -1 if none had support */
+  int32_t max_support; /* StatData.RANSAC_HYP_SUPPORT (:85) */
+  int32_t num_ic;      /* individually compatible matches */
+  int32_t m;           /* matches per hypothesis: 3 if num_ic > 3 else 1 (select_random_match.m:47-51) */
+  double n_hyp;        /* StatData.RANSAC_ITER (:84): the final n_hyp */
+} pre3_ekf_result;
+
+/* [support, li_id, li_euc] = compute_hypothesis_support_fast(xi, cam, pattern, z_id, z_euc, thr) for B
+ * hypothesised states at once (B = 1 is the reference call).  xi: n x B; pattern: n x 4 (the 0/1
+ * matrix of generate_state_vector_pattern.m:29-51); z_id: 2 x n_id; z_euc: 2 x n_euc;
+ * support: B; li_id: n_id x B bytes; li_euc: n_euc x B bytes (either may be NULL). */
+PRE3_API int pre3_ekf_support(pre3_ctx *ctx, const double *xi, int n, int B, const pre3_cam *cam,
+                     const double *pattern, const double *z_id, int n_id, const double *z_euc,
+                     int n_euc, double threshold, int32_t *support, uint8_t *li_id, uint8_t *li_euc);
+
+/* features_info = ransac_hypotheses(filter, features_info, cam) for Fr frames that share the state
+ * size n and the feature count F.  Per frame (all column-major, frames consecutive):
+ *   x n (get_x_k_km1), P n x n (get_p_k_km1); std_z = get_std_z(filter) (the threshold, :33);
+ *   per feature i of features_info: type (0 'inversedepth', 1 'cartesian'), pos (0-based offset of
+ *   its states in x), has_z (~isempty(z)), ic (individually_compatible), z 2, h 2,
+ *   Hcam 2 x 13 = H(:,1:13), Hfeat 2 x 6 = H(:,pos+1:pos+6) (cartesian: first 3 columns; H has no
+ *   other non-zeros, M/calculate_Hi_inverse_depth_my_version.m:44-49), R 2 x 2.
+ *   sel: H x 3 supplied match selections per frame (0-based feature indices in the order
+ *   select_random_match.m:58 returns them; only the first m are read) or NULL (seeded, frame id =
+ *   frame_id0 + frame).
+ * Outputs: li_inlier Fr x F bytes IN/OUT (low_innovation_inlier: written for features with z when a
+ * hypothesis had support, untouched otherwise, set_as_most_supported_hypothesis.m:32-53); res Fr;
+ * supports Fr x H (support of every hypothesis the loop evaluated, -1 beyond) or NULL. */
+PRE3_API int pre3_ransac_hypotheses_batch(pre3_ctx *ctx, int Fr, int n, int F, const double *x, const double *P,
+                                 double std_z, const pre3_cam *cam, const int32_t *type,
+                                 const int32_t *pos, const uint8_t *has_z, const uint8_t *ic,
+                                 const double *z, const double *h, const double *Hcam,
+                                 const double *Hfeat, const double *R, const int32_t *sel,
+                                 const pre3_ekf_opts *opts, uint32_t frame_id0, uint8_t *li_inlier,
+                                 pre3_ekf_result *res, int32_t *supports);
+PRE3_API int pre3_ransac_hypotheses_batch_dev(pre3_ctx *ctx, int Fr, int n, int F, const double *dx,
+                                     const double *dP, double std_z, const pre3_cam *cam,
+                                     const int32_t *dtype, const int32_t *dpos, const uint8_t *dhas_z,
+                                     const uint8_t *dic, const double *dz, const double *dh,
+                                     const double *dHcam, const double *dHfeat, const double *dR,
+                                     const int32_t *dsel, const pre3_ekf_opts *opts,
+                                     uint32_t frame_id0, uint8_t *dli_inlier, pre3_ekf_result *dres,
+                                     int32_t *dsupports);
+/* Wave boundaries of the hypothesis evaluation (like pre3_eval_schedule). */
+PRE3_API int pre3_ekf_eval_schedule(const pre3_ekf_opts *opts, int32_t *ends, int cap);
+/* DFMA-chain microbenchmark: measured FP64 CUDA-core peak (TFLOP/s), the roofline of the EKF kernels. */
+PRE3_API int pre3_measure_fp64_peak(pre3_ctx *ctx, double *tflops);
 
 /* R2q of slamToolbox (M/slamToolbox_11_02_18/FrameTransforms/Rotations/R2q.m:11-55), host
  * helper used by the Calculate_V_Omega_RANSAC* shims: q = [a -b -c -d]'. */

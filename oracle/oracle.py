@@ -233,3 +233,100 @@ def R2q(R):
     q = np.zeros(4)
     lib().orc_R2q(_p(r, C.c_double), _p(q, C.c_double))
     return q
+
+
+# ---------------------------------------------------------------------------------------
+# config 4: 1-point-RANSAC EKF hypotheses (oracle/pre3_oracle_ekf.c)
+# ---------------------------------------------------------------------------------------
+class EkfCam(C.Structure):
+    _fields_ = [("f", C.c_double), ("Cx", C.c_double), ("Cy", C.c_double), ("k1", C.c_double), ("k2", C.c_double)]
+
+
+class EkfResult(C.Structure):
+    _fields_ = [("status", C.c_int32), ("n_evaluated", C.c_int32), ("best_hyp", C.c_int32),
+                ("max_support", C.c_int32), ("num_ic", C.c_int32), ("m", C.c_int32), ("n_hyp", C.c_double)]
+
+
+def _cam(cam):
+    return EkfCam(cam["f"], cam["Cx"], cam["Cy"], cam["k1"], cam["k2"])
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def sincos(x):
+    """orc_sincos: the specified sin / cos pair (stand-in for MATLAB's in M/m.m:32-34)."""
+    s, c = C.c_double(), C.c_double()
+    lib().orc_sincos(C.c_double(float(x)), C.byref(s), C.byref(c))
+    return s.value, c.value
+
+
+def ekf_nhyp(support, num_ic):
+    f = lib().orc_ekf_nhyp
+    f.restype = C.c_double
+    return f(int(support), int(num_ic))
+
+
+def ekf_select(seed, frame, hyp, num_ic, m):
+    out = np.zeros(3, np.int32)
+    lib().orc_ekf_select(C.c_uint64(seed), C.c_uint32(frame), C.c_uint32(hyp), int(num_ic), int(m), _p(out, C.c_int32))
+    return out[:m].copy()
+
+
+def ekf_update(fr, sel):
+    """xi = x + K (zi - hi) for the matches `sel` (M/ransac_hypotheses.m:51-63).  fr: synth_ekf.EkfFrame."""
+    sel = _i32(sel)
+    xi = np.zeros(fr.n)
+    Pc = np.ascontiguousarray(fr.P.T)  # column-major
+    lib().orc_ekf_update(_p(_f64(fr.x), C.c_double), _p(Pc, C.c_double), fr.n, _p(_i32(fr.pos), C.c_int32),
+                         _p(_i32(fr.type), C.c_int32), _p(_f64(fr.z), C.c_double), _p(_f64(fr.h), C.c_double),
+                         _p(_f64(fr.Hcam), C.c_double), _p(_f64(fr.Hfeat), C.c_double), _p(_f64(fr.R), C.c_double),
+                         _p(sel, C.c_int32), len(sel), _p(xi, C.c_double))
+    return xi
+
+
+def pattern_to_lists(pattern):
+    """logical pattern columns (generate_state_vector_pattern.m:29-51) -> 0-based index lists."""
+    pattern = np.asarray(pattern)
+    return [_i32(np.flatnonzero(pattern[:, c])) for c in range(4)]
+
+
+def ekf_support(xi, cam, pattern, z_id, z_euc, threshold):
+    """compute_hypothesis_support_fast.m:27-116.  z_id (n_id,2), z_euc (n_euc,2) [= 2 x n column-major].
+    Returns support, li_id (bool), li_euc (bool), residuals."""
+    ir, ia, irho, ixyz = pattern_to_lists(pattern)
+    z_id, z_euc = _f64(z_id).reshape(-1, 2), _f64(z_euc).reshape(-1, 2)
+    n_id, n_euc = len(z_id), len(z_euc)
+    li_id, li_euc = np.zeros(n_id + 1, np.uint8), np.zeros(n_euc + 1, np.uint8)
+    res = np.zeros(n_id + n_euc + 1)
+    c = _cam(cam)
+    sup = lib().orc_ekf_support(_p(_f64(xi), C.c_double), C.byref(c), _p(ir, C.c_int32), _p(ia, C.c_int32),
+                                _p(irho, C.c_int32), _p(z_id, C.c_double), n_id, _p(ixyz, C.c_int32),
+                                _p(z_euc, C.c_double), n_euc, C.c_double(threshold), _p(li_id, C.c_uint8),
+                                _p(li_euc, C.c_uint8), _p(res, C.c_double))
+    return sup, li_id[:n_id].astype(bool), li_euc[:n_euc].astype(bool), res[:n_id + n_euc].copy()
+
+
+def ransac_hypotheses(fr, sel=None, H=1000, n_hyp_init=1000, seed=0, frame_id=0, adaptive=True):
+    """ransac_hypotheses.m:27-85 on one synth_ekf.EkfFrame.  sel: (H,3) 0-based feature indices or None
+    (seeded).  Returns dict(li, n_hyp, max_support, best_hyp, n_evaluated, supports, status, m, num_ic)."""
+    if sel is not None:
+        sel = _i32(sel)
+        H = len(sel)
+    li = np.ascontiguousarray(fr.li0, dtype=np.uint8).copy()
+    out = EkfResult()
+    supports = np.full(max(H, 1), -1, np.int32)
+    c = _cam(fr.cam)
+    Pc = np.ascontiguousarray(fr.P.T)
+    hz, ic = np.ascontiguousarray(fr.has_z, np.uint8), np.ascontiguousarray(fr.ic, np.uint8)
+    lib().orc_ransac_hypotheses(_p(_f64(fr.x), C.c_double), _p(Pc, C.c_double), fr.n, C.c_double(fr.std_z), C.byref(c),
+                                fr.F, _p(_i32(fr.type), C.c_int32), _p(_i32(fr.pos), C.c_int32), _p(hz, C.c_uint8),
+                                _p(ic, C.c_uint8), _p(_f64(fr.z), C.c_double), _p(_f64(fr.h), C.c_double),
+                                _p(_f64(fr.Hcam), C.c_double), _p(_f64(fr.Hfeat), C.c_double), _p(_f64(fr.R), C.c_double),
+                                _p(sel, C.c_int32) if sel is not None else None, int(H), int(n_hyp_init),
+                                int(bool(adaptive)), C.c_uint64(seed), C.c_uint32(frame_id), _p(li, C.c_uint8), C.byref(out),
+                                _p(supports, C.c_int32))
+    return dict(li=li, n_hyp=out.n_hyp, max_support=out.max_support, best_hyp=out.best_hyp,
+                n_evaluated=out.n_evaluated, supports=supports[:out.n_evaluated].copy(), status=out.status, m=out.m,
+                num_ic=out.num_ic)

@@ -1,0 +1,160 @@
+"""Independent numpy / LAPACK restatement of the 1-point-RANSAC EKF hypothesis path ("oracle A").
+
+TEST INFRASTRUCTURE ONLY.  Written separately from oracle/pre3_oracle_ekf.c: dense H rows,
+numpy sin / cos, numpy.linalg.inv and BLAS products the way the MATLAB reference uses its
+built-ins, MATLAB-shaped arrays (column vectors, n x 4 logical pattern).  Checks the C oracle
+and the CUDA kernels to tolerance (states to 1e-9) and the supports / masks wherever no residual
+lies within 1e-9 px of its threshold.  `M/` = /root/reference/matlab_code/.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def m(a):
+    """M/m.m:32-34."""
+    theta, phi = a[0], a[1]
+    cphi = np.cos(phi)
+    return np.vstack([cphi * np.sin(theta), -np.sin(phi), cphi * np.cos(theta)])
+
+
+def q2r(q):
+    """M/q2r.m:29-36."""
+    r, x, y, z = q
+    return np.array([[r * r + x * x - y * y - z * z, 2 * (x * y - r * z), 2 * (z * x + r * y)],
+                     [2 * (x * y + r * z), r * r - x * x + y * y - z * z, 2 * (y * z - r * x)],
+                     [2 * (z * x - r * y), 2 * (y * z + r * x), r * r - x * x - y * y + z * z]])
+
+
+def distort_fm(uv, cam):
+    """M/distort_fm_my_version.m:44-61."""
+    xu = (uv[0] - cam["Cx"]) / cam["f"]
+    yu = (uv[1] - cam["Cy"]) / cam["f"]
+    ru = np.sqrt(xu * xu + yu * yu)
+    D = 1 + cam["k1"] * ru ** 2 + cam["k2"] * ru ** 4
+    return np.vstack([xu * D * cam["f"] + cam["Cx"], yu * D * cam["f"] + cam["Cy"]])
+
+
+def generate_state_vector_pattern(types, has_z, z, n):
+    """M/generate_state_vector_pattern.m:27-53.  types: 0 inverse depth / 1 cartesian; z: (F,2)."""
+    pattern = np.zeros((n, 4))
+    position = 13  # 0-based 14
+    z_id, z_euc = [], []
+    for i, t in enumerate(types):
+        if t == 0:
+            if has_z[i]:
+                pattern[position:position + 3, 0] = 1
+                pattern[position + 3:position + 5, 1] = 1
+                pattern[position + 5, 2] = 1
+                z_id.append(z[i])
+            position += 6
+        else:
+            if has_z[i]:
+                pattern[position:position + 3, 3] = 1
+                z_euc.append(z[i])
+            position += 3
+    z_id = np.array(z_id, float).reshape(-1, 2).T
+    z_euc = np.array(z_euc, float).reshape(-1, 2).T
+    return pattern, z_id, z_euc
+
+
+def compute_hypothesis_support_fast(xi, cam, pattern, z_id, z_euc, threshold, return_residuals=False):
+    """M/compute_hypothesis_support_fast.m:27-116.  z_id: 2 x n_id, z_euc: 2 x n_euc."""
+    xi = np.asarray(xi, float).ravel()
+    support = 0
+    li_id = np.zeros(0, bool)
+    li_euc = np.zeros(0, bool)
+    res_all = []
+    rotcw = q2r(xi[3:7]).T
+    if z_id.size:
+        n_id = z_id.shape[1]
+        ri = xi[pattern[:, 0].astype(bool)].reshape(n_id, 3).T
+        ang = xi[pattern[:, 1].astype(bool)].reshape(n_id, 2).T
+        rho = xi[pattern[:, 2].astype(bool)]
+        mi = m(ang)
+        d = (ri - xi[0:3, None]) * rho[None, :]
+        hc = rotcw @ (d + mi)
+        hn = hc[0:2] / hc[2]
+        h_image = cam["f"] * hn + np.array([[cam["Cx"]], [cam["Cy"]]])
+        nu = z_id - distort_fm(h_image, cam)
+        residuals = np.sqrt(nu[0] ** 2 + nu[1] ** 2)
+        li_id = residuals < (np.nanmin(residuals) + threshold if np.isfinite(residuals).any() else np.nan)
+        support += int(li_id.sum())
+        res_all.append(residuals)
+    if z_euc.size:
+        n_euc = z_euc.shape[1]
+        xyz = xi[pattern[:, 3].astype(bool)].reshape(n_euc, 3).T
+        hc = rotcw @ (xyz - xi[0:3, None])
+        hn = hc[0:2] / hc[2]
+        h_image = cam["f"] * hn + np.array([[cam["Cx"]], [cam["Cy"]]])
+        nu = z_euc - distort_fm(h_image, cam)
+        residuals = np.sqrt(nu[0] ** 2 + nu[1] ** 2)
+        li_euc = residuals < threshold
+        support += int(li_euc.sum())
+        res_all.append(residuals)
+    if return_residuals:
+        return support, li_id, li_euc, (np.concatenate(res_all) if res_all else np.zeros(0))
+    return support, li_id, li_euc
+
+
+def dense_H(fr, i):
+    """features_info(i).H as the full 2 x n matrix (M/calculate_Hi_inverse_depth_my_version.m:44-49)."""
+    H = np.zeros((2, fr.n))
+    H[:, 0:13] = fr.Hcam[i].T      # stored (13, 2) = 2 x 13 column-major
+    nf = 6 if fr.type[i] == 0 else 3
+    H[:, fr.pos[i]:fr.pos[i] + nf] = fr.Hfeat[i].T[:, :nf]
+    return H
+
+
+def hypothesis_state(fr, sel):
+    """M/ransac_hypotheses.m:51-63 for the matches `sel` (0-based feature indices)."""
+    hi = np.concatenate([fr.h[i] for i in sel])
+    zi = np.concatenate([fr.z[i] for i in sel])
+    Hi = np.vstack([dense_H(fr, i) for i in sel])
+    R = np.zeros((2 * len(sel), 2 * len(sel)))
+    for a, i in enumerate(sel):
+        R[2 * a:2 * a + 2, 2 * a:2 * a + 2] = fr.R[i].T  # stored column-major
+    S = Hi @ fr.P @ Hi.T + R
+    K = fr.P @ Hi.T @ np.linalg.inv(S)
+    return fr.x + K @ (zi - hi)
+
+
+def n_hyp_rule(support, num_ic):
+    """M/ransac_hypotheses.m:77-78 with MATLAB's complex log for negative arguments."""
+    epsilon = 1 - support / num_ic
+    a = 1 - (1 - epsilon)
+    with np.errstate(divide="ignore"):
+        v = np.log(complex(1 - 0.99)) / np.log(complex(a)) if a != 0 else complex(0.0)
+    return float(np.ceil(v.real))
+
+
+def ransac_hypotheses(fr, sel, n_hyp_init=1000):
+    """M/ransac_hypotheses.m:27-85.  sel: (H, 3) supplied selections (0-based feature indices)."""
+    pattern, z_id, z_euc = generate_state_vector_pattern(fr.type, fr.has_z, fr.z, fr.n)
+    num_ic = int(fr.ic.sum())
+    if num_ic == 0:
+        raise IndexError("select_random_match: no individually compatible match")
+    mm = 3 if num_ic > 3 else 1
+    n_hyp = float(n_hyp_init)
+    max_support = 0
+    li = fr.li0.copy()
+    best = -1
+    supports = []
+    id_feats = [i for i in range(fr.F) if fr.has_z[i] and fr.type[i] == 0]
+    euc_feats = [i for i in range(fr.F) if fr.has_z[i] and fr.type[i] == 1]
+    for i in range(min(n_hyp_init, len(sel))):
+        if n_hyp == 0:
+            break
+        xi = hypothesis_state(fr, list(sel[i][:mm]))
+        sup, li_id, li_euc = compute_hypothesis_support_fast(xi, fr.cam, pattern, z_id, z_euc, fr.std_z)
+        supports.append(sup)
+        if sup > max_support:
+            max_support = sup
+            best = i
+            li[id_feats] = li_id
+            li[euc_feats] = li_euc
+            n_hyp = n_hyp_rule(sup, num_ic)
+        if n_hyp <= mm:
+            break
+    return dict(li=li, n_hyp=n_hyp, max_support=max_support, best_hyp=best, supports=np.array(supports),
+                n_evaluated=len(supports), m=mm, num_ic=num_ic)
