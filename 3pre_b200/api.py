@@ -451,6 +451,14 @@ class Context:
                                                  _ptr(samples), int(h0), int(Hloc), float(thr), _ptr(key),
                                                  _ptr(errsum)))
 
+    def ransac_block_select_dev(self, Ya, Yb, opts: RansacOpts, h0: int, Hloc: int, thr: float, res, mask=None,
+                                samples=None):
+        """Reference-exact local winner of hypotheses [h0, h0+Hloc): res uint8 (240,) tensor
+        (best_sample is local: add h0), mask uint8 (N,) | None."""
+        self._ck(self._lib.pre3_ransac_block_select_dev(self._h, _ptr(Ya), _ptr(Yb), Ya.shape[0], C.byref(opts),
+                                                        _ptr(samples), int(h0), int(Hloc), float(thr), _ptr(res),
+                                                        _ptr(mask)))
+
     def ransac_finish_dev(self, Ya, Yb, opts: RansacOpts, winner_id: int, thr: float, res, mask=None,
                           sample_of_winner=None):
         self._ck(self._lib.pre3_ransac_finish_dev(self._h, _ptr(Ya), _ptr(Yb), Ya.shape[0], C.byref(opts),

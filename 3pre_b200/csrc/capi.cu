@@ -627,6 +627,37 @@ int pre3_ransac_block_dev(pre3_ctx* ctx, const double* dYa, const double* dYb, i
   return PRE3_OK;
 }
 
+// Reference-exact local selection over one hypothesis block: evaluate [h0, h0+Hloc), then the full
+// (max cardinality, min ErrorSum, first index) rule + mask + refit, as if the block were the whole run.
+int pre3_ransac_block_select_dev(pre3_ctx* ctx, const double* dYa, const double* dYb, int N,
+                                 const pre3_ransac_opts* opts, const int32_t* dsamples, int64_t h0, int Hloc,
+                                 double thr, pre3_pair_result* dres, uint8_t* dmask) {
+  PRE3_LIVE();
+  PRE3_TRY(check_opts(ctx, opts));
+  PRE3_NEED(dYa && dYb && dres, "null pointer");
+  PRE3_NEED(N >= 1 && Hloc >= 0 && h0 >= 0, "bad sizes");
+  pre3_ransac_opts o = *opts;
+  o.H = Hloc;
+  o.adaptive = 0;
+  o.max_iteration = Hloc + 1;  // the loop runs over every sample set of the block
+  o.distance_threshold = thr;
+  PRE3_TRY(ws_reserve(ctx, ransac_ws_bytes(1, N, Hloc)));
+  RansacBuffers b{};
+  b.Ya = dYa;
+  b.Yb = dYb;
+  b.n_corr = nullptr;
+  b.P = 1;
+  b.Nmax = N;
+  b.samples = dsamples;
+  b.pair_id0 = 0;
+  b.h0 = h0;
+  ransac_carve(ctx, b, Hloc);
+  PRE3_TRY(launch_prep(ctx, b, o, 1));
+  PRE3_TRY(launch_eval(ctx, b, o, h0, 0, Hloc, nullptr));
+  PRE3_TRY(launch_select(ctx, b, o, dres, dmask, nullptr, nullptr));
+  return PRE3_OK;
+}
+
 int pre3_ransac_finish_dev(pre3_ctx* ctx, const double* dYa, const double* dYb, int N, const pre3_ransac_opts* opts,
                            const int32_t* dsamples_of_winner, int64_t winner_id, double thr, pre3_pair_result* dres,
                            uint8_t* dmask) {

@@ -809,8 +809,9 @@ constexpr int TIE_THREADS = 128;
 
 __global__ void __launch_bounds__(TIE_THREADS)
 k_sel_tie(const PairMeta* __restrict__ meta, const double* __restrict__ Ya, const double* __restrict__ Yb, int Nmax,
-          const int32_t* __restrict__ samples, uint64_t seed, uint32_t pair_id0, int H, int k, int method,
-          const int2* __restrict__ ties, const int* __restrict__ tie_total, int cap, double* __restrict__ es_out) {
+          const int32_t* __restrict__ samples, uint64_t seed, uint32_t pair_id0, long long h0, int H, int k,
+          int method, const int2* __restrict__ ties, const int* __restrict__ tie_total, int cap,
+          double* __restrict__ es_out) {
   const int total = min(*tie_total, cap);
   for (int t = blockIdx.x * TIE_THREADS + threadIdx.x; t < total; t += gridDim.x * TIE_THREADS) {
     const int2 ps = ties[t];
@@ -820,7 +821,7 @@ k_sel_tie(const PairMeta* __restrict__ meta, const double* __restrict__ Ya, cons
     const double* ya = Ya + (size_t)p * Nmax * 3;
     const double* yb = Yb + (size_t)p * Nmax * 3;
     int idx[MAX_K];
-    load_sample(samples, seed, pair_id0 + (uint32_t)p, 0, s, H, p, N, k, idx);
+    load_sample(samples, seed, pair_id0 + (uint32_t)p, h0, s, H, p, N, k, idx);
     Rigid f;
     fit_sample(method, ya, yb, idx, k, f);
     double es = 0.0;
@@ -837,8 +838,9 @@ constexpr int SELF_WARPS = 4;
 
 __global__ void __launch_bounds__(SELF_WARPS * 32)
 k_sel_final(const PairMeta* __restrict__ meta, const double* __restrict__ Ya, const double* __restrict__ Yb, int P,
-            int Nmax, const int32_t* __restrict__ samples, uint64_t seed, uint32_t pair_id0, int H, int k, int method,
-            const int32_t* __restrict__ counts, const int8_t* __restrict__ states, const SelInfo* __restrict__ info,
+            int Nmax, const int32_t* __restrict__ samples, uint64_t seed, uint32_t pair_id0, long long h0, int H, int k,
+            int method, const int32_t* __restrict__ counts, const int8_t* __restrict__ states,
+            const SelInfo* __restrict__ info,
             const double* __restrict__ es_in, pre3_pair_result* __restrict__ res, uint8_t* __restrict__ masks,
             int mask_stride, uint8_t* __restrict__ mask_scratch) {
   const int p = blockIdx.x * SELF_WARPS + (threadIdx.x >> 5);
@@ -892,7 +894,7 @@ k_sel_final(const PairMeta* __restrict__ meta, const double* __restrict__ Ya, co
 
   // ---- winner: hypothesis, mask, ErrorSum; refit on the support set (:186) --------------------------
   int idx[MAX_K];
-  load_sample(samples, seed, pair_id0 + (uint32_t)p, 0, win, H, p, N, k, idx);
+  load_sample(samples, seed, pair_id0 + (uint32_t)p, h0, win, H, p, N, k, idx);
   Rigid f;
   fit_sample(method, ya, yb, idx, k, f);  // every lane computes the same fit
   double es;
@@ -1394,11 +1396,11 @@ int launch_select(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts&
                                                     tab, b.counts, b.states, dres, dmasks, b.Nmax, dcounts_out,
                                                     dstates_out, info, ties, tie_total);
   const int tie_blocks = (int)std::min<size_t>((PH + TIE_THREADS - 1) / TIE_THREADS, (size_t)ctx->sm_count * 8);
-  k_sel_tie<<<tie_blocks, TIE_THREADS, 0, ctx->stream>>>(b.meta, b.Ya, b.Yb, b.Nmax, b.samples, o.seed, b.pair_id0, o.H,
-                                                         o.k, o.method, ties, tie_total, (int)PH, es);
+  k_sel_tie<<<tie_blocks, TIE_THREADS, 0, ctx->stream>>>(b.meta, b.Ya, b.Yb, b.Nmax, b.samples, o.seed, b.pair_id0, b.h0,
+                                                         o.H, o.k, o.method, ties, tie_total, (int)PH, es);
   k_sel_final<<<(b.P + SELF_WARPS - 1) / SELF_WARPS, SELF_WARPS * 32, 0, ctx->stream>>>(
-      b.meta, b.Ya, b.Yb, b.P, b.Nmax, b.samples, o.seed, b.pair_id0, o.H, o.k, o.method, b.counts, b.states, info, es,
-      dres, dmasks, b.Nmax, scratch);
+      b.meta, b.Ya, b.Yb, b.P, b.Nmax, b.samples, o.seed, b.pair_id0, b.h0, o.H, o.k, o.method, b.counts, b.states, info,
+      es, dres, dmasks, b.Nmax, scratch);
   count_launch(ctx, 3);
   PRE3_CUDA(cudaGetLastError());
   return PRE3_OK;

@@ -27,6 +27,7 @@ struct RansacBuffers {
   int32_t* stop;         // P: sample sets consumed when the adaptive loop is known to have ended, else -1
   const int32_t* samples;  // P x H x k or nullptr (seeded)
   uint32_t pair_id0;
+  long long h0 = 0;      // global id of local sample set 0 (hypothesis-block sharding); selection kernels only
 };
 
 size_t ransac_workspace_bytes(int P, int Nmax, int H);

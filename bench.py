@@ -181,6 +181,194 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm), "window": window}
 
 
+
+# ------------------------------------------------------------------------------------------
+# the other BASELINE.json configs, measured briefly next to the headline workload
+# ------------------------------------------------------------------------------------------
+def _time_steps(fn, steps, warmup):
+    import torch
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def _kernel_times(ctx, fn, reps=2):
+    ctx.timing_enable(True)
+    for _ in range(reps):
+        fn()
+    kt = ctx.timing_read()
+    ctx.timing_enable(False)
+    return {k: {"ms_per_step": v[0] / reps, "launches_per_step": v[1] // reps} for k, v in kt.items()}
+
+
+def bench_cfg2(ctx, pre3, synth, dev, rank, P=256, K=2048, steps=5, warmup=2):
+    """configs[1]: SIFT descriptor matching 2k x 2k 128-d, batch of 256 pairs, ratio test, one GPU."""
+    import torch
+    slabs = [synth.make_batch_torch(32, 2000 + 100000 * rank + s0, dev, K1=K, K2=K, n_corr=K // 2)
+             for s0 in range(0, P, 32)]
+    d1 = torch.cat([s["desc1"] for s in slabs]).contiguous()
+    d2 = torch.cat([s["desc2"] for s in slabs]).contiguous()
+    del slabs
+    pairs = torch.zeros(P, K, 2, dtype=torch.int32, device=dev)
+    n_out = torch.zeros(P, dtype=torch.int32, device=dev)
+
+    def step():
+        ctx.siftmatch_batch_dev(d1, d2, pairs, None, n_out, 1.5)
+
+    ms = _time_steps(step, steps, warmup)
+    kt = _kernel_times(ctx, step)
+    flops = 2.0 * K * K * 128 * P
+    pk = peaks()
+    gemm = kt.get("match_tc", {}).get("ms_per_step", 0.0)
+    out = {"workload": f"cfg2: siftmatch {K}x{K}x128 (double), batch of {P} pairs, ratio 1.5",
+           "pairs_per_s": P / (ms * 1e-3), "ms_per_step": ms,
+           "tflops_whole_step": flops / (ms * 1e-3) / 1e12,
+           "accepted_matches_per_pair": float(n_out.float().mean().item()), "kernels": kt}
+    if gemm > 0:
+        a = flops / (gemm * 1e-3) / 1e12
+        out["roofline"] = {"kernel": "match_tc", "bound": "tensor", "achieved": a, "peak": pk["bf16_tflops"],
+                           "unit": "TFLOP/s", "frac": a / pk["bf16_tflops"], "traffic": None,
+                           "note": f"algorithmic 2*K1*K2*128 per pair; peak {pk['source']}"}
+    del d1, d2
+    torch.cuda.empty_cache()
+    return out
+
+
+EKF_FLOPS_PER_EVAL = 600.0   # DESIGN.md: K-form state update 468 + sin/cos 72 + projection/distortion 60 (mul and add counted apart)
+
+
+def bench_cfg4(ctx, pre3, dev, rank, Fr=256, n_id=200, H=1000, steps=3, warmup=1):
+    """configs[3]: 1-point-RANSAC EKF hypothesis support, 200 inverse-depth features (n = 1213)."""
+    import torch
+    se = importlib.import_module("3pre_b200.synth_ekf")
+    parts = [se.make_ekf_frames(64, 4000 + 100000 * rank + f0, device=dev, n_id=n_id, outlier_ratio=0.2)
+             for f0 in range(0, Fr, 64)]
+    b = {k: (torch.cat([p[k] for p in parts]).contiguous() if hasattr(parts[0][k], "shape") else parts[0][k])
+         for k in parts[0]}
+    del parts
+    b["cam"] = dict(se.CAM)
+    li = torch.zeros(Fr, b["F"], dtype=torch.uint8, device=dev)
+    res = torch.zeros(Fr, 32, dtype=torch.uint8, device=dev)
+    out = {"workload": f"cfg4: ransac_hypotheses on {Fr} resident EKF frames (of the 10k-frame config), {n_id} "
+                       f"inverse-depth features, n = {b['n']}, {H} seeded match triples per frame, thr = 1 px, 20% outliers"}
+    fp64_peak = ctx.measure_fp64_peak()
+    for name, adaptive in (("adaptive", True), ("fixed_H", False)):
+        o = pre3.make_ekf_opts(H=H, adaptive=adaptive, seed=11)
+
+        def step():
+            ctx.ransac_hypotheses_batch_dev(b, o, li, res)
+
+        ms = _time_steps(step, steps, warmup)
+        kt = _kernel_times(ctx, step, reps=1)
+        r = np.frombuffer(res.cpu().numpy().tobytes(), dtype=pre3.EKF_RESULT_DTYPE)
+        ends = ctx.ekf_eval_schedule(o)
+        done = ends[np.minimum(np.searchsorted(ends, np.maximum(r["n_evaluated"], 1) - 1, side="right"), len(ends) - 1)]
+        evals = float((done.astype(np.float64) * n_id).sum())
+        sc = kt.get("ekf_score", {}).get("ms_per_step", 0.0)
+        gn = kt.get("ekf_gain", {}).get("ms_per_step", 0.0)
+        o_ = {"frames_per_s": Fr / (ms * 1e-3), "ms_per_step": ms, "hyp_x_feature_evals_per_s": evals / (ms * 1e-3),
+              "hypotheses_evaluated_per_frame": float(done.mean()),
+              "hypotheses_needed_by_reference_loop_per_frame": float(r["n_evaluated"].mean()),
+              "mean_support": float(r["max_support"].mean()), "kernels": kt}
+        if sc > 0:
+            a = EKF_FLOPS_PER_EVAL * evals / (sc * 1e-3) / 1e12
+            o_["roofline_score"] = {"kernel": "ekf_score", "bound": "fp64", "achieved": a, "peak": fp64_peak,
+                                    "unit": "TFLOP/s", "frac": a / fp64_peak if fp64_peak else None, "traffic": None,
+                                    "note": "600 fp64 ops per hypothesis x feature eval; peak = DFMA-chain microbenchmark "
+                                            "of this run (counts 2 per FMA; the path may not fuse, so 0.5 is its ceiling)"}
+        if gn > 0:
+            byt = Fr * (b["n"] * b["n"] * 8.0 + b["F"] * 2 * b["n"] * 8.0)
+            a = byt / (gn * 1e-3) / 1e9
+            pk = peaks()
+            o_["roofline_gain"] = {"kernel": "ekf_gain", "bound": "hbm", "achieved": a, "peak": pk["hbm_gbs"],
+                                   "unit": "GB/s", "frac": a / pk["hbm_gbs"], "traffic": None,
+                                   "note": "reads P (n*n*8 B) once, writes G (F*2*n*8 B) per frame"}
+        out[name] = o_
+    del b
+    torch.cuda.empty_cache()
+    return out
+
+
+def bench_cfg5(ctx, pre3, synth, dev, rank, world, N=20000, H=1000000, steps=3, warmup=1):
+    """configs[4]: one pair, 20k correspondences x 1M hypotheses, 60% outliers, hypotheses split over
+    the ranks, ONE NCCL max-reduce of (inlier count, hypothesis id)."""
+    import torch
+    import torch.distributed as dist
+    pd = importlib.import_module("3pre_b200.dist")
+    c = synth.make_correspondences(5000, N=N, outlier_ratio=0.6)
+    Ya, Yb = torch.from_numpy(c.Ya).to(dev), torch.from_numpy(c.Yb).to(dev)
+    if world > 1:  # replicate the correspondences (480 KB) from rank 0
+        dist.broadcast(Ya, 0)
+        dist.broadcast(Yb, 0)
+    opts = pre3.make_opts(method=0, k=5, max_iteration=H + 1, adaptive=False, H=H, seed=5)
+    out = {"workload": f"cfg5: one pair, {N} correspondences x {H} hypotheses (k=5, fixed H, 60% outliers), "
+                       f"hypothesis blocks over {world} GPU(s)", "scaling": "strong"}
+    for mode in ("first", "reference"):
+        def step():
+            return pd.ransac_hypothesis_split(ctx, Ya, Yb, opts, mode=mode, want_mask=False)
+
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            rec, _ = step()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        out[mode] = {"ms_per_solve": ms, "hyp_x_match_evals_per_s": float(N) * H / (ms * 1e-3),
+                     "best_fit": int(rec["best_fit"]), "best_sample": int(rec["best_sample"]),
+                     "collective": "all_reduce(MAX) of one u64 key" if mode == "first"
+                     else "all_gather of 16 B per rank (count, id, ErrorSum)"}
+    # the scoring kernel alone, on this rank's block (fp32 CUDA-core roofline at large N)
+    h0, h1 = pd.split_range(H, rank, world)
+    key = torch.zeros(1, dtype=torch.int64, device=dev)
+    thr = torch.zeros(1, dtype=torch.float64, device=dev)
+    ctx.distance_threshold_dev(Yb, thr)
+    ctx.sync()
+    kt = _kernel_times(ctx, lambda: ctx.ransac_block_dev(Ya, Yb, opts, h0, h1 - h0, float(thr.item()), key), reps=2)
+    ev = kt.get("eval", {}).get("ms_per_step", 0.0)
+    if ev > 0:
+        fp32_peak = ctx.measure_fp32_peak()
+        a = FLOPS_PER_EVAL * float(N) * (h1 - h0) / (ev * 1e-3) / 1e12
+        out["roofline"] = {"kernel": "eval (k_eval<5,0>)", "bound": "fp32", "achieved": a, "peak": fp32_peak,
+                           "unit": "TFLOP/s", "frac": a / fp32_peak, "traffic": None,
+                           "evals_per_s": float(N) * (h1 - h0) / (ev * 1e-3),
+                           "note": "27 FLOP per hypothesis x match eval; the fp64 5-point fits run in the same kernel; "
+                                   "peak = FFMA-chain microbenchmark of this run"}
+    out["kernels"] = kt
+    return out
+
+
+def other_workloads(ctx, pre3, synth, dev, rank, world):
+    out = {}
+    jobs = [("cfg5", lambda: bench_cfg5(ctx, pre3, synth, dev, rank, world))]
+    if rank == 0:  # single-GPU configs: measured on rank 0 only (the other ranks wait at the next barrier)
+        jobs = [("cfg2", lambda: bench_cfg2(ctx, pre3, synth, dev, rank)),
+                ("cfg4", lambda: bench_cfg4(ctx, pre3, dev, rank))] + jobs
+    # cfg5 involves every rank: run it first everywhere so that no rank waits inside a collective
+    jobs.sort(key=lambda j: j[0] != "cfg5")
+    for name, fn in jobs:
+        try:
+            out[name] = fn()
+        except Exception as e:  # a secondary workload must not take the headline line down
+            out[name] = {"error": f"{type(e).__name__}: {e}"}
+    return out
+
+
 # ------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------
@@ -338,6 +526,12 @@ def run_ours(args):
     assert np.array_equal(out[0]["best_fit"], r["best_fit"][:Pe]), "e2e path disagrees with the device path"
     ectx.close()
 
+    others = None
+    if not args.no_other:
+        del data, host, hn, res, matches, masks
+        torch.cuda.empty_cache()
+        others = other_workloads(ctx, pre3, synth, dev, rank, world)
+        barrier()
     if rank == 0:
         cpu = cpu_baseline_single()
         line = {
@@ -359,6 +553,7 @@ def run_ours(args):
                       "executed_per_step": evals_done, "required_by_reference_loop_per_step": evals_needed},
             "cpu_baseline": cpu,
             "check": {"pairs_solved": ok_pairs, "pairs": P},
+            "other_workloads": others,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -373,6 +568,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=4096, help="frame pairs per GPU per step")
     ap.add_argument("--e2e-pairs", type=int, default=4096, help="frame pairs per e2e step (pinned host memory)")
+    ap.add_argument("--no-other", action="store_true", help="skip the short cfg2 / cfg4 / cfg5 measurements")
     ap.add_argument("--profile", action="store_true",
                     help="short run for ncu: skips the e2e and cpu_baseline legs (their keys are null)")
     args = ap.parse_args()

@@ -213,6 +213,14 @@ PRE3_API int pre3_pairs_dev(pre3_ctx *ctx, const void *ddesc1, const void *ddesc
 PRE3_API int pre3_ransac_block_dev(pre3_ctx *ctx, const double *dYa, const double *dYb, int N,
                           const pre3_ransac_opts *opts, const int32_t *dsamples, int64_t h0,
                           int Hloc, double thr, uint64_t *dkey, double *derrsum);
+/* Reference-exact mode of the split: the block's own winner under the full rule of
+ * RANSAC_CALC_VER2.m:165-175 (max cardinality, then min ErrorSum, then first index) with its mask and
+ * refit; res->best_sample is LOCAL (add h0).  The caller all-gathers (best_fit, h0 + best_sample,
+ * error_sum) -- 16 bytes per rank -- and every rank picks the same global winner; the owning rank
+ * already holds R, T and the mask. */
+PRE3_API int pre3_ransac_block_select_dev(pre3_ctx *ctx, const double *dYa, const double *dYb, int N,
+                                 const pre3_ransac_opts *opts, const int32_t *dsamples, int64_t h0,
+                                 int Hloc, double thr, pre3_pair_result *dres, uint8_t *dmask);
 PRE3_API int pre3_ransac_finish_dev(pre3_ctx *ctx, const double *dYa, const double *dYb, int N,
                            const pre3_ransac_opts *opts, const int32_t *dsamples_of_winner,
                            int64_t winner_id, double thr, pre3_pair_result *dres, uint8_t *dmask);

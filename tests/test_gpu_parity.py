@@ -400,6 +400,47 @@ def test_hypothesis_block_split_equals_single_run(ctx, synth, pre3):
         np.testing.assert_allclose(r.T, g.T, rtol=0, atol=1e-13)
 
 
+@pytest.mark.parametrize("supplied", [False, True])
+def test_hypothesis_block_split_reference_mode(ctx, orc, synth, pre3, supplied):
+    """Reference-exact mode of the split: every block's own (max count, min ErrorSum, first id) winner,
+    16 bytes per block exchanged, same pick everywhere == the single run; the owning block already
+    holds the mask and refit.  Also through dist.ransac_hypothesis_split without a process group."""
+    import torch
+    pd = importlib.import_module("3pre_b200.dist")
+    N, H, G = 600, 4000, 4   # small N -> many hypotheses tie on the cardinality
+    c = synth.make_correspondences(33, N=N, outlier_ratio=0.5, noise=0.0005)
+    opts = pre3.make_opts(method=0, k=5, max_iteration=H + 1, adaptive=False, H=H, seed=23)
+    samples = orc.sample_sets(23, 0, H, N, 5) if supplied else None
+    g = ctx.ransac(c.Ya, c.Yb, samples, opts)
+    Ya, Yb = torch.from_numpy(c.Ya).cuda(), torch.from_numpy(c.Yb).cuda()
+    ds = torch.from_numpy(samples).cuda() if supplied else None
+    counts, ids, ess, recs, masks = [], [], [], [], []
+    for r in range(G):
+        h0, h1 = pd.split_range(H, r, G)
+        res = torch.zeros(240, dtype=torch.uint8, device="cuda")
+        mask = torch.zeros(N, dtype=torch.uint8, device="cuda")
+        ctx.ransac_block_select_dev(Ya, Yb, opts, h0, h1 - h0, g.thr, res, mask,
+                                    samples=ds[h0:h1].contiguous() if supplied else None)
+        ctx.sync()
+        rec = np.frombuffer(res.cpu().numpy().tobytes(), dtype=pre3.RESULT_DTYPE)[0]
+        assert rec["status"] == 0
+        counts.append(int(rec["best_fit"])); ids.append(h0 + int(rec["best_sample"])); ess.append(float(rec["error_sum"]))
+        recs.append(rec); masks.append(mask.cpu().numpy().astype(bool))
+    w = pd.pick_reference(counts, ids, ess)
+    assert (counts[w], ids[w], ess[w]) == (g.best_fit, g.best_sample, g.error_sum)
+    np.testing.assert_array_equal(masks[w], g.mask)
+    r = pre3.unpack_result(recs[w])
+    np.testing.assert_array_equal(r.R, g.R)
+    np.testing.assert_array_equal(r.T, g.T)
+    assert r.state == g.state
+    # the driver with world size 1 (no process group): both modes
+    rec, m = pd.ransac_hypothesis_split(ctx, Ya, Yb, opts, samples=ds, mode="reference")
+    assert (rec["best_fit"], rec["best_sample"], rec["error_sum"]) == (g.best_fit, g.best_sample, g.error_sum)
+    np.testing.assert_array_equal(m.astype(bool), g.mask)
+    rec, m = pd.ransac_hypothesis_split(ctx, Ya, Yb, opts, samples=ds, mode="first")
+    assert rec["best_fit"] == g.counts.max() and rec["best_sample"] == int(np.flatnonzero(g.counts == g.counts.max())[0])
+
+
 def test_matlab_mirror_roundtrip(ctx, orc, synth):
     m = importlib.import_module("3pre_b200.matlab")
     c = synth.make_correspondences(8, N=200, outlier_ratio=0.3)
