@@ -138,7 +138,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "frame-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------
@@ -491,8 +491,8 @@ def run_ours(args):
 
     if args.profile:
         if rank == 0:
-            print(json.dumps({"profile_run": True, "value": value, "ms_per_step": ms_step, "kernels": per_kernel,
-                              "roofline": roofline, "gpu_launches": int(launches)}), flush=True)
+            emit({"profile_run": True, "value": value, "ms_per_step": ms_step, "kernels": per_kernel,
+                  "roofline": roofline, "gpu_launches": int(launches)})
         if world > 1:
             dist.destroy_process_group()
         return
@@ -555,12 +555,30 @@ def run_ours(args):
             "check": {"pairs_solved": ok_pairs, "pairs": P},
             "other_workloads": others,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The ONE JSON line goes to the real stdout; everything else a library prints (NCCL's version
+    banner, warnings) was redirected to stderr in main()."""
+    txt = json.dumps(line) + "\n"
+    if _REAL_STDOUT is None:
+        sys.stdout.write(txt)
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, txt.encode())
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)  # stray prints of native libraries (NCCL banner) must not precede the JSON line
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
