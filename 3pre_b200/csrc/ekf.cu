@@ -214,6 +214,7 @@ __global__ void __launch_bounds__(GAIN_THREADS)
 k_ekf_gain(int n, int F, const double* __restrict__ P, const int32_t* __restrict__ type, const int32_t* __restrict__ pos,
            const double* __restrict__ Hcam, const double* __restrict__ Hfeat, const FrameIdx* __restrict__ idx,
            const int32_t* __restrict__ ic_list, double* __restrict__ G) {
+  // blockIdx.z strides over the IC features so that a few frames still fill the machine
   const int frame = blockIdx.y;
   const FrameIdx fi = idx[frame];
   if (fi.status != 0) return;
@@ -226,7 +227,7 @@ k_ekf_gain(int n, int F, const double* __restrict__ P, const int32_t* __restrict
     pc0[k] = v0 ? Pc[(size_t)k * n + e0] : 0.0;
     pc1[k] = v1 ? Pc[(size_t)k * n + e1] : 0.0;
   }
-  for (int r = 0; r < fi.num_ic; ++r) {
+  for (int r = blockIdx.z; r < fi.num_ic; r += gridDim.z) {
     const int f = ic_list[(size_t)frame * F + r];
     const size_t ff = (size_t)frame * F + f;
     const int nf = type[ff] == 0 ? 6 : 3, p = pos[ff];
@@ -324,184 +325,250 @@ struct ScoreArgs {
   uint8_t* li;          // FINAL: Fr x F
 };
 
-struct ScoreShared {
+// What the scoring threads need from one hypothesis: written by k_ekf_hyp, read by k_ekf_score.
+struct HypRec {
+  double Sinv[36];  // inv(Hi*P*Hi' + R), row-major d x d
+  double innov[6];  // zi - hi
+  double cam[7];    // updated camera position + quaternion
+  double Rw[9];     // q2r of the updated quaternion
+  int32_t sel[3];   // the selected features
+  int32_t d;        // 2 m
+};
+
+struct SetupShared {  // per warp
   double H[3][2][19];
   double W[6][32];
   double aug[6][12];
-  double Sinv[36];
-  double innov[6];
-  double cam[7];
-  double Rw[9];
-  double red[32];
-  size_t goff[6];
-  int ired[32];
   int sel[3], nf[3], pos[3];
 };
 
-template <bool FINAL>
-__global__ void __launch_bounds__(256) k_ekf_score(const ScoreArgs A) {
-  extern __shared__ double s_res[];  // one residual per measured feature
-  __shared__ ScoreShared sh;
-  const int frame = blockIdx.y;
-  const int tid = threadIdx.x, lane = tid & 31;
+// xi[e] = x[e] + sum_j K[e][j]*innov[j],  K[e][j] = sum_c G[e][c]*Sinv[c][j]  (ransac_hypotheses.m:62-63)
+__device__ __forceinline__ double updated_state(const double* __restrict__ x, const double* __restrict__ G,
+                                                const size_t* goff, const double* Sinv, const double* innov, int d,
+                                                int e) {
+  double g[6], dx = 0.0;
+#pragma unroll
+  for (int c = 0; c < 6; ++c) g[c] = c < d ? __ldg(G + goff[c] + e) : 0.0;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    if (j < d) {
+      double k = g[0] * Sinv[j];
+#pragma unroll
+      for (int c = 1; c < 6; ++c)
+        if (c < d) k = k + g[c] * Sinv[c * d + j];
+      const double term = k * innov[j];
+      dx = j == 0 ? term : dx + term;
+    }
+  }
+  return x[e] + dx;
+}
+
+constexpr int HYP_WARPS = 4;
+
+// One WARP per (frame, hypothesis): the m selected matches, S = Hi*P*Hi' + R from the P sub-blocks,
+// inv(S) by a cooperative Gauss-Jordan, the innovation and the updated camera states.
+// grid.x covers the hypotheses [hbeg, hend) of every frame (or, with best != nullptr, the winner of
+// every frame); rec is indexed [frame * rec_stride + (hyp - hbeg)].
+__global__ void __launch_bounds__(HYP_WARPS * 32)
+k_ekf_hyp(const ScoreArgs A, int Fr, HypRec* __restrict__ rec, int rec_stride, int use_best) {
+  __shared__ SetupShared shs[HYP_WARPS];
+  const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+  const int per_frame = use_best ? 1 : (A.hend - A.hbeg);
+  const long long w = (long long)blockIdx.x * HYP_WARPS + wl;
+  if (w >= (long long)Fr * per_frame) return;
+  const int frame = (int)(w / per_frame), slot = (int)(w % per_frame);
   const FrameIdx fi = A.idx[frame];
   if (fi.status != 0) return;
   int hyp;
-  if (FINAL) {
+  if (use_best) {
     hyp = A.best[frame];
     if (hyp < 0) return;
   } else {
-    hyp = A.hbeg + blockIdx.x;
-    if (hyp >= A.hend) return;
+    hyp = A.hbeg + slot;
     if (A.stop && A.stop[frame] >= 0) return;
   }
+  SetupShared& sh = shs[wl];
   const int n = A.n, F = A.F, m = fi.m, d = 2 * m;
   const size_t fF = (size_t)frame * F;
   const double* Pc = A.P + (size_t)frame * n * n;
   const double* x = A.x + (size_t)frame * n;
+  HypRec* out = rec + (size_t)frame * rec_stride + slot;
 
-  if (tid < 32) {
-    // ---- the m selected matches (select_random_match.m:47-58) --------------------------------
-    {
-      int rk[3] = {0, 0, 0};
-      if (!A.sel) select_ranks(A.seed, A.frame_id0 + (uint32_t)frame, (uint32_t)hyp, fi.num_ic, m, rk);
-      if (lane < m) {
-        int f;
-        if (A.sel)
-          f = min(max(A.sel[((size_t)frame * A.H + hyp) * 3 + lane], 0), F - 1);
-        else
-          f = A.ic_list[fF + rk[lane]];
-        sh.sel[lane] = f;
-        sh.nf[lane] = A.type[fF + f] == 0 ? 6 : 3;
-        sh.pos[lane] = A.pos[fF + f];
-        sh.goff[2 * lane] = ((fF + f) * 2) * (size_t)n;
-        sh.goff[2 * lane + 1] = ((fF + f) * 2 + 1) * (size_t)n;
-      }
+  // ---- the m selected matches (select_random_match.m:47-58) ----------------------------------
+  {
+    int rk[3] = {0, 0, 0};
+    if (!A.sel) select_ranks(A.seed, A.frame_id0 + (uint32_t)frame, (uint32_t)hyp, fi.num_ic, m, rk);
+    if (lane < m) {
+      int f;
+      if (A.sel)
+        f = min(max(A.sel[((size_t)frame * A.H + hyp) * 3 + lane], 0), F - 1);
+      else
+        f = A.ic_list[fF + rk[lane]];
+      sh.sel[lane] = f;
+      sh.nf[lane] = A.type[fF + f] == 0 ? 6 : 3;
+      sh.pos[lane] = A.pos[fF + f];
     }
-    __syncwarp();
-    // ---- H rows of the selected features: 13 camera + nf feature columns ----------------------
-    for (int i = lane; i < m * 2 * 19; i += 32) {
-      const int a = i / 38, c = (i / 19) & 1, t = i % 19;
-      const size_t ff = fF + sh.sel[a];
-      double v = 0.0;
-      if (t < 13)
-        v = A.Hcam[ff * 26 + 2 * t + c];
-      else if (t - 13 < sh.nf[a])
-        v = A.Hfeat[ff * 12 + 2 * (t - 13) + c];
-      sh.H[a][c][t] = v;
-    }
-    __syncwarp();
-    // ---- W = Hi*P at the columns any selected H touches (lane = column) ------------------------
-    {
-      int k = -1;
-      if (lane < 13) {
-        k = lane;
-      } else {
-        int off = lane - 13;
-        for (int b = 0; b < m; ++b) {
-          if (off < sh.nf[b]) {
-            k = sh.pos[b] + off;
-            break;
-          }
-          off -= sh.nf[b];
+  }
+  __syncwarp();
+  // ---- H rows of the selected features: 13 camera + nf feature columns --------------------------
+  for (int i = lane; i < m * 2 * 19; i += 32) {
+    const int a = i / 38, c = (i / 19) & 1, t = i % 19;
+    const size_t ff = fF + sh.sel[a];
+    double v = 0.0;
+    if (t < 13)
+      v = A.Hcam[ff * 26 + 2 * t + c];
+    else if (t - 13 < sh.nf[a])
+      v = A.Hfeat[ff * 12 + 2 * (t - 13) + c];
+    sh.H[a][c][t] = v;
+  }
+  __syncwarp();
+  // ---- W = Hi*P at the columns any selected H touches (lane = column) ----------------------------
+  {
+    int k = -1;
+    if (lane < 13) {
+      k = lane;
+    } else {
+      int off = lane - 13;
+      for (int b = 0; b < m; ++b) {
+        if (off < sh.nf[b]) {
+          k = sh.pos[b] + off;
+          break;
         }
+        off -= sh.nf[b];
       }
-      if (k >= 0) {
-        for (int a = 0; a < m; ++a) {
-          const int nta = 13 + sh.nf[a], pa = sh.pos[a];
-          double w0 = 0.0, w1 = 0.0;
-          for (int ta = 0; ta < nta; ++ta) {
-            const int kk = ta < 13 ? ta : pa + (ta - 13);
-            const double pv = Pc[(size_t)k * n + kk];
-            const double t0 = sh.H[a][0][ta] * pv, t1 = sh.H[a][1][ta] * pv;
-            w0 = ta == 0 ? t0 : w0 + t0;
-            w1 = ta == 0 ? t1 : w1 + t1;
-          }
-          sh.W[2 * a][lane] = w0;
-          sh.W[2 * a + 1][lane] = w1;
+    }
+    if (k >= 0) {
+      for (int a = 0; a < m; ++a) {
+        const int nta = 13 + sh.nf[a], pa = sh.pos[a];
+        double w0 = 0.0, w1 = 0.0;
+        for (int ta = 0; ta < nta; ++ta) {
+          const int kk = ta < 13 ? ta : pa + (ta - 13);
+          const double pv = Pc[(size_t)k * n + kk];
+          const double t0 = sh.H[a][0][ta] * pv, t1 = sh.H[a][1][ta] * pv;
+          w0 = ta == 0 ? t0 : w0 + t0;
+          w1 = ta == 0 ? t1 : w1 + t1;
         }
+        sh.W[2 * a][lane] = w0;
+        sh.W[2 * a + 1][lane] = w1;
+      }
+    }
+  }
+  __syncwarp();
+  // ---- S = W*Hi' + R, augmented with the identity ----------------------------------------------
+  for (int i = lane; i < d * d; i += 32) {
+    const int r = i / d, sc = i % d, a = r >> 1, ca = r & 1, b = sc >> 1, cb = sc & 1;
+    int offb = 0;
+    for (int bb = 0; bb < b; ++bb) offb += sh.nf[bb];
+    const int ntb = 13 + sh.nf[b];
+    double acc = 0.0;
+    for (int tb = 0; tb < ntb; ++tb) {
+      const int col = tb < 13 ? tb : 13 + offb + (tb - 13);
+      const double term = sh.W[r][col] * sh.H[b][cb][tb];
+      acc = tb == 0 ? term : acc + term;
+    }
+    const double rblk = (a == b) ? A.R[(fF + sh.sel[a]) * 4 + 2 * cb + ca] : 0.0;
+    sh.aug[r][sc] = acc + rblk;
+    sh.aug[r][d + sc] = (r == sc) ? 1.0 : 0.0;
+  }
+  __syncwarp();
+  // ---- inv(S): Gauss-Jordan with partial pivoting, lane = column of [S | I] ------------------------
+  for (int col = 0; col < d; ++col) {
+    int pr = col;
+    double best = fabs(sh.aug[col][col]);
+    for (int r = col + 1; r < d; ++r) {
+      const double v = fabs(sh.aug[r][col]);
+      if (v > best) {
+        best = v;
+        pr = r;
       }
     }
     __syncwarp();
-    // ---- S = W*Hi' + R, augmented with the identity ------------------------------------------
-    for (int i = lane; i < d * d; i += 32) {
-      const int r = i / d, s = i % d, a = r >> 1, ca = r & 1, b = s >> 1, cb = s & 1;
-      int offb = 0;
-      for (int bb = 0; bb < b; ++bb) offb += sh.nf[bb];
-      const int ntb = 13 + sh.nf[b];
-      double acc = 0.0;
-      for (int tb = 0; tb < ntb; ++tb) {
-        const int col = tb < 13 ? tb : 13 + offb + (tb - 13);
-        const double term = sh.W[r][col] * sh.H[b][cb][tb];
-        acc = tb == 0 ? term : acc + term;
-      }
-      const double rblk = (a == b) ? A.R[(fF + sh.sel[a]) * 4 + 2 * cb + ca] : 0.0;
-      sh.aug[r][s] = acc + rblk;
-      sh.aug[r][d + s] = (r == s) ? 1.0 : 0.0;
+    if (pr != col && lane < 2 * d) {
+      const double t = sh.aug[col][lane];
+      sh.aug[col][lane] = sh.aug[pr][lane];
+      sh.aug[pr][lane] = t;
     }
     __syncwarp();
-    // ---- inv(S): Gauss-Jordan with partial pivoting, lane = column of [S | I] --------------------
-    for (int col = 0; col < d; ++col) {
-      int pr = col;
-      double best = fabs(sh.aug[col][col]);
-      for (int r = col + 1; r < d; ++r) {
-        const double v = fabs(sh.aug[r][col]);
-        if (v > best) {
-          best = v;
-          pr = r;
-        }
-      }
-      __syncwarp();
-      if (pr != col && lane < 2 * d) {
-        const double t = sh.aug[col][lane];
-        sh.aug[col][lane] = sh.aug[pr][lane];
-        sh.aug[pr][lane] = t;
-      }
-      __syncwarp();
-      const double piv = sh.aug[col][col];
-      double fr[6];
+    const double piv = sh.aug[col][col];
+    double fr[6];
 #pragma unroll
-      for (int r = 0; r < 6; ++r) fr[r] = r < d ? sh.aug[r][col] : 0.0;
-      __syncwarp();
-      if (lane < 2 * d) {
-        const double v = sh.aug[col][lane] / piv;
-        sh.aug[col][lane] = v;
+    for (int r = 0; r < 6; ++r) fr[r] = r < d ? sh.aug[r][col] : 0.0;
+    __syncwarp();
+    if (lane < 2 * d) {
+      const double v = sh.aug[col][lane] / piv;
+      sh.aug[col][lane] = v;
 #pragma unroll
-        for (int r = 0; r < 6; ++r)
-          if (r < d && r != col) sh.aug[r][lane] = sh.aug[r][lane] - fr[r] * v;
-      }
-      __syncwarp();
-    }
-    for (int i = lane; i < d * d; i += 32) sh.Sinv[i] = sh.aug[i / d][d + (i % d)];
-    if (lane < d) {
-      const size_t ff = fF + sh.sel[lane >> 1];
-      sh.innov[lane] = A.z[ff * 2 + (lane & 1)] - A.h[ff * 2 + (lane & 1)];
+      for (int r = 0; r < 6; ++r)
+        if (r < d && r != col) sh.aug[r][lane] = sh.aug[r][lane] - fr[r] * v;
     }
     __syncwarp();
   }
-  __syncthreads();
+  // Sinv / innovation live in the first rows of W from here on (W is no longer needed)
+  double* Sinv = &sh.W[0][0];
+  double* innov = &sh.W[2][0];
+  double* cam = &sh.W[3][0];
+  for (int i = lane; i < d * d; i += 32) Sinv[i] = sh.aug[i / d][d + (i % d)];
+  if (lane < d) {
+    const size_t ff = fF + sh.sel[lane >> 1];
+    innov[lane] = A.z[ff * 2 + (lane & 1)] - A.h[ff * 2 + (lane & 1)];
+  }
+  __syncwarp();
+  size_t goff[6];
+#pragma unroll
+  for (int c = 0; c < 6; ++c) goff[c] = c < d ? ((fF + sh.sel[c >> 1]) * 2 + (c & 1)) * (size_t)n : 0;
+  if (lane < 7) cam[lane] = updated_state(x, A.G, goff, Sinv, innov, d, lane);
+  __syncwarp();
+  for (int i = lane; i < 36; i += 32) out->Sinv[i] = i < d * d ? Sinv[i] : 0.0;
+  if (lane < 6) out->innov[lane] = lane < d ? innov[lane] : 0.0;
+  if (lane < 7) out->cam[lane] = cam[lane];
+  if (lane < 3) out->sel[lane] = lane < m ? sh.sel[lane] : 0;
+  if (lane == 0) {
+    double Rw[9];
+    q2r(&cam[3], Rw);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) out->Rw[i] = Rw[i];
+    out->d = d;
+  }
+}
 
-  // xi[e] = x[e] + sum_j K[e][j]*innov[j],  K[e][j] = sum_c G[e][c]*Sinv[c][j]  (ransac_hypotheses.m:62-63)
-  auto updated = [&](int e) -> double {
-    double g[6], dx = 0.0;
-#pragma unroll
-    for (int c = 0; c < 6; ++c) g[c] = c < d ? __ldg(A.G + sh.goff[c] + e) : 0.0;
-#pragma unroll
-    for (int j = 0; j < 6; ++j) {
-      if (j < d) {
-        double k = g[0] * sh.Sinv[j];
-#pragma unroll
-        for (int c = 1; c < 6; ++c)
-          if (c < d) k = k + g[c] * sh.Sinv[c * d + j];
-        const double term = k * sh.innov[j];
-        dx = j == 0 ? term : dx + term;
-      }
-    }
-    return x[e] + dx;
-  };
-  if (tid < 7) sh.cam[tid] = updated(tid);
+struct ScoreShared {
+  HypRec rec;
+  double red[32];
+  size_t goff[6];
+  int ired[32];
+};
+
+// One block per (frame, hypothesis), one thread per measured feature.
+template <bool FINAL>
+__global__ void __launch_bounds__(256) k_ekf_score(const ScoreArgs A, const HypRec* __restrict__ rec, int rec_stride) {
+  extern __shared__ double s_res[];  // one residual per measured feature
+  __shared__ ScoreShared sh;
+  const int frame = blockIdx.y;
+  const int tid = threadIdx.x;
+  const FrameIdx fi = A.idx[frame];
+  if (fi.status != 0) return;
+  int hyp, slot;
+  if (FINAL) {
+    hyp = A.best[frame];
+    slot = 0;
+    if (hyp < 0) return;
+  } else {
+    slot = blockIdx.x;
+    hyp = A.hbeg + slot;
+    if (hyp >= A.hend) return;
+    if (A.stop && A.stop[frame] >= 0) return;
+  }
+  const int n = A.n, F = A.F;
+  const size_t fF = (size_t)frame * F;
+  const double* x = A.x + (size_t)frame * n;
+  {
+    const double* src = reinterpret_cast<const double*>(rec + (size_t)frame * rec_stride + slot);
+    double* dst = reinterpret_cast<double*>(&sh.rec);
+    for (int i = tid; i < (int)(sizeof(HypRec) / sizeof(double)); i += blockDim.x) dst[i] = src[i];
+  }
   __syncthreads();
-  if (tid == 0) q2r(&sh.cam[3], sh.Rw);
+  const int d = sh.rec.d;
+  if (tid < 6) sh.goff[tid] = tid < d ? ((fF + sh.rec.sel[tid >> 1]) * 2 + (tid & 1)) * (size_t)n : 0;
   __syncthreads();
 
   // ---- one thread per measured feature ---------------------------------------------------------
@@ -511,8 +578,9 @@ __global__ void __launch_bounds__(256) k_ekf_score(const ScoreArgs A) {
     const int ty = A.type[fF + f], p = A.pos[fF + f];
     double s[6];
 #pragma unroll
-    for (int t = 0; t < 6; ++t) s[t] = (t < 3 || ty == 0) ? updated(p + t) : 0.0;
-    const double r = feature_residual(ty, s, sh.cam, sh.Rw, A.cam, A.z[(fF + f) * 2], A.z[(fF + f) * 2 + 1]);
+    for (int t = 0; t < 6; ++t)
+      s[t] = (t < 3 || ty == 0) ? updated_state(x, A.G, sh.goff, sh.rec.Sinv, sh.rec.innov, d, p + t) : 0.0;
+    const double r = feature_residual(ty, s, sh.rec.cam, sh.rec.Rw, A.cam, A.z[(fF + f) * 2], A.z[(fF + f) * 2 + 1]);
     s_res[j] = r;
     if (ty == 0) lmin = nanmin2(lmin, r);
   }
@@ -737,6 +805,7 @@ static size_t ekf_ws_bytes(int C, int n, int F, int H) {
   b += align_up(8 * (size_t)C * F * 2 * n);
   b += align_up(4 * (size_t)C * std::max(H, 1));
   b += 2 * align_up(4 * (size_t)C);
+  b += align_up(sizeof(HypRec) * (size_t)C * std::max(H, 1));  // hypothesis records of the widest wave (<= H)
   return b + 8192;
 }
 
@@ -765,6 +834,9 @@ static int ekf_impl(pre3_ctx* ctx, int Fr, int n, int F, const double* dx, const
     int32_t* sup = ws_take<int32_t>(ctx, (size_t)nc * std::max(H, 1));
     int32_t* stop = ws_take<int32_t>(ctx, nc);
     int32_t* best = ws_take<int32_t>(ctx, nc);
+    int maxw = 1;
+    for (int w = 0, beg = 0; w < nw; beg = ends[w], ++w) maxw = std::max(maxw, ends[w] - beg);
+    HypRec* rec = ws_take<HypRec>(ctx, (size_t)nc * maxw);
     const size_t fo = (size_t)c0;
     {
       Span span__(ctx, T_EKF_SELECT);
@@ -773,7 +845,10 @@ static int ekf_impl(pre3_ctx* ctx, int Fr, int n, int F, const double* dx, const
     }
     {
       Span span__(ctx, T_EKF_GAIN);
-      const dim3 grid((n + 2 * GAIN_THREADS - 1) / (2 * GAIN_THREADS), nc);
+      const int gx = (n + 2 * GAIN_THREADS - 1) / (2 * GAIN_THREADS);
+      const int want = 8 * ctx->sm_count;  // resident blocks to hide the dependent column loads
+      const int gz = std::max(1, std::min(std::min(F, 64), (want + gx * nc - 1) / (gx * nc)));
+      const dim3 grid(gx, nc, gz);
       k_ekf_gain<<<grid, GAIN_THREADS, 0, ctx->stream>>>(n, F, dP + fo * n * n, dtype + fo * F, dpos + fo * F,
                                                          dHcam + fo * F * 26, dHfeat + fo * F * 12, idx, ic_list, G);
       count_launch(ctx);
@@ -813,8 +888,10 @@ static int ekf_impl(pre3_ctx* ctx, int Fr, int n, int F, const double* dx, const
         Span span__(ctx, T_EKF_SCORE);
         a.hbeg = beg;
         a.hend = end;
-        k_ekf_score<false><<<dim3(end - beg, nc), bs, smem, ctx->stream>>>(a);
-        count_launch(ctx);
+        const long long warps = (long long)nc * (end - beg);
+        k_ekf_hyp<<<(unsigned)((warps + HYP_WARPS - 1) / HYP_WARPS), HYP_WARPS * 32, 0, ctx->stream>>>(a, nc, rec, maxw, 0);
+        k_ekf_score<false><<<dim3(end - beg, nc), bs, smem, ctx->stream>>>(a, rec, maxw);
+        count_launch(ctx, 2);
       }
       if (end < limit) {
         Span span__(ctx, T_EKF_SELECT);
@@ -835,8 +912,9 @@ static int ekf_impl(pre3_ctx* ctx, int Fr, int n, int F, const double* dx, const
       Span span__(ctx, T_EKF_SCORE);
       a.hbeg = 0;
       a.hend = 1;
-      k_ekf_score<true><<<dim3(1, nc), bs, smem, ctx->stream>>>(a);
-      count_launch(ctx);
+      k_ekf_hyp<<<(nc + HYP_WARPS - 1) / HYP_WARPS, HYP_WARPS * 32, 0, ctx->stream>>>(a, nc, rec, maxw, 1);
+      k_ekf_score<true><<<dim3(1, nc), bs, smem, ctx->stream>>>(a, rec, maxw);
+      count_launch(ctx, 2);
     }
     PRE3_CUDA(cudaGetLastError());
   }

@@ -676,7 +676,7 @@ k_sel_scan(const PairMeta* __restrict__ meta, int Nmax, int H, int k, int method
            const int32_t* __restrict__ tab, const int32_t* __restrict__ counts, const int8_t* __restrict__ states,
            pre3_pair_result* __restrict__ res, uint8_t* __restrict__ masks, int mask_stride,
            int32_t* __restrict__ counts_out, int8_t* __restrict__ states_out, SelInfo* __restrict__ info,
-           int2* __restrict__ ties, int* __restrict__ tie_total) {
+           int2* __restrict__ ties, int* __restrict__ tie_total, int32_t* __restrict__ pair_ties) {
   __shared__ int s_a[32], s_b[32], s_base, s_pc, s_pm;
   const int p = blockIdx.x;
   const int tid = threadIdx.x;
@@ -792,7 +792,10 @@ k_sel_scan(const PairMeta* __restrict__ meta, int Nmax, int H, int k, int method
       if (tid == 0) s_base = atomicAdd(tie_total, tile_ties);
       if (NT == 32) __syncwarp(); else __syncthreads();
       const int tb = s_base;
-      if (is_tie) ties[tb + my_off] = make_int2(p, s);
+      if (is_tie) {
+        ties[tb + my_off] = make_int2(p, s);
+        pair_ties[(size_t)p * H + n_ties + my_off] = s;  // this pair's ties in ascending order
+      }
       if (NT == 32) __syncwarp(); else __syncthreads();
     }
     n_ties += tile_ties;
@@ -807,11 +810,55 @@ k_sel_scan(const PairMeta* __restrict__ meta, int Nmax, int H, int k, int method
 
 constexpr int TIE_THREADS = 128;
 
+// sum of v over the 32 lanes strictly in lane order, continued from acc (every lane returns it)
+__device__ __forceinline__ double warp_ordered_add(double acc, double v) {
+#pragma unroll
+  for (int l = 0; l < 32; ++l) acc = acc + __shfl_sync(0xffffffffu, v, l);
+  return acc;
+}
+
+// One WARP per tied hypothesis: minimal fit again (every lane, same result), the residual norms of
+// 32 correspondences at a time, summed strictly in index order (non-inliers add an exact +0.0).
 __global__ void __launch_bounds__(TIE_THREADS)
 k_sel_tie(const PairMeta* __restrict__ meta, const double* __restrict__ Ya, const double* __restrict__ Yb, int Nmax,
           const int32_t* __restrict__ samples, uint64_t seed, uint32_t pair_id0, long long h0, int H, int k,
           int method, const int2* __restrict__ ties, const int* __restrict__ tie_total, int cap,
           double* __restrict__ es_out) {
+  const int total = min(*tie_total, cap);
+  const int lane = threadIdx.x & 31;
+  const int wpb = TIE_THREADS / 32;
+  for (int t = blockIdx.x * wpb + (threadIdx.x >> 5); t < total; t += gridDim.x * wpb) {
+    const int2 ps = ties[t];
+    const int p = ps.x, s = ps.y;
+    const PairMeta m = meta[p];
+    const int N = m.N;
+    const double* ya = Ya + (size_t)p * Nmax * 3;
+    const double* yb = Yb + (size_t)p * Nmax * 3;
+    int idx[MAX_K];
+    load_sample(samples, seed, pair_id0 + (uint32_t)p, h0, s, H, p, N, k, idx);
+    Rigid f;
+    fit_sample(method, ya, yb, idx, k, f);
+    double es = 0.0;
+    for (int ib = 0; ib < N; ib += 32) {
+      const int i = ib + lane;
+      double v = 0.0;
+      if (i < N) {
+        const double nr = residual_norm(f.R, f.t, ya + 3 * i, yb + 3 * i);
+        v = nr < m.thr ? nr : 0.0;  // sum(normResidu(inliers)) in index order (:135)
+      }
+      es = warp_ordered_add(es, v);
+    }
+    if (lane == 0) es_out[(size_t)p * H + s] = es;
+  }
+}
+
+// One THREAD per tied hypothesis (small N: the ties of a pair sit next to each other in the list, so
+// the lanes of a warp read the same few correspondences); loads of 4 correspondences in flight.
+__global__ void __launch_bounds__(TIE_THREADS)
+k_sel_tie_thread(const PairMeta* __restrict__ meta, const double* __restrict__ Ya, const double* __restrict__ Yb,
+                 int Nmax, const int32_t* __restrict__ samples, uint64_t seed, uint32_t pair_id0, long long h0, int H,
+                 int k, int method, const int2* __restrict__ ties, const int* __restrict__ tie_total, int cap,
+                 double* __restrict__ es_out) {
   const int total = min(*tie_total, cap);
   for (int t = blockIdx.x * TIE_THREADS + threadIdx.x; t < total; t += gridDim.x * TIE_THREADS) {
     const int2 ps = ties[t];
@@ -825,26 +872,41 @@ k_sel_tie(const PairMeta* __restrict__ meta, const double* __restrict__ Ya, cons
     Rigid f;
     fit_sample(method, ya, yb, idx, k, f);
     double es = 0.0;
-#pragma unroll 2
-    for (int i = 0; i < N; ++i) {
+    int i = 0;
+    for (; i + 4 <= N; i += 4) {
+      double a[12], b[12];
+#pragma unroll
+      for (int u = 0; u < 12; ++u) {
+        a[u] = __ldg(ya + 3 * i + u);
+        b[u] = __ldg(yb + 3 * i + u);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const double nr = residual_norm(f.R, f.t, a + 3 * u, b + 3 * u);
+        es = es + (nr < m.thr ? nr : 0.0);  // sum(normResidu(inliers)) in index order (:135); + 0.0 is exact
+      }
+    }
+    for (; i < N; ++i) {
       const double nr = residual_norm(f.R, f.t, ya + 3 * i, yb + 3 * i);
-      es = es + (nr < m.thr ? nr : 0.0);  // sum(normResidu(inliers)) in index order (:135); + 0.0 is exact
+      es = es + (nr < m.thr ? nr : 0.0);
     }
     es_out[(size_t)p * H + s] = es;
   }
 }
 
-constexpr int SELF_WARPS = 4;
-
-__global__ void __launch_bounds__(SELF_WARPS * 32)
+// NT threads per pair: 32 (one warp, batches of pairs) or 512 (a few large pairs).
+template <int NT>
+__global__ void __launch_bounds__(NT)
 k_sel_final(const PairMeta* __restrict__ meta, const double* __restrict__ Ya, const double* __restrict__ Yb, int P,
             int Nmax, const int32_t* __restrict__ samples, uint64_t seed, uint32_t pair_id0, long long h0, int H, int k,
             int method, const int32_t* __restrict__ counts, const int8_t* __restrict__ states,
-            const SelInfo* __restrict__ info,
-            const double* __restrict__ es_in, pre3_pair_result* __restrict__ res, uint8_t* __restrict__ masks,
-            int mask_stride, uint8_t* __restrict__ mask_scratch) {
-  const int p = blockIdx.x * SELF_WARPS + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
+            const SelInfo* __restrict__ info, const int32_t* __restrict__ pair_ties, const double* __restrict__ es_in,
+            pre3_pair_result* __restrict__ res, uint8_t* __restrict__ masks, int mask_stride,
+            uint8_t* __restrict__ mask_scratch) {
+  __shared__ double s_es[32];
+  __shared__ int s_i[32];
+  const int p = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (p >= P) return;
   const SelInfo si = info[p];
   if (si.status != 0) return;  // result already written by k_sel_scan
@@ -852,32 +914,44 @@ k_sel_final(const PairMeta* __restrict__ meta, const double* __restrict__ Ya, co
   const int N = m.N;
   const double* ya = Ya + (size_t)p * Nmax * 3;
   const double* yb = Yb + (size_t)p * Nmax * 3;
-  const int32_t* cnt = counts + (size_t)p * H;
   const int8_t* sts = states + (size_t)p * H;
   uint8_t* mask = masks ? masks + (size_t)p * mask_stride : mask_scratch + (size_t)p * Nmax;
   auto recorded = [&](int s) { return !(method == PRE3_METHOD_SVD && sts[s] == -1); };
 
-  // ---- min ErrorSum over the ties, first index on equal sums -------------------------------------
+  // ---- min ErrorSum over this pair's ties (listed in ascending s), first index on equal sums --------
   double best_es = INFINITY;
   int best_s = 0x7fffffff;
-  if (si.n_ties > 0) {
-    for (int s = lane; s < si.S_end; s += 32)
-      if (recorded(s) && cnt[s] == si.maxc) {
-        const double es = es_in[(size_t)p * H + s];
-        if (es < best_es) {  // ascending s within a lane: strict < keeps the first
-          best_es = es;
-          best_s = s;
-        }
-      }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      const double oe = __shfl_xor_sync(0xffffffffu, best_es, off);
-      const int os = __shfl_xor_sync(0xffffffffu, best_s, off);
-      if (oe < best_es || (oe == best_es && os < best_s)) {
-        best_es = oe;
-        best_s = os;
-      }
+  for (int j = tid; j < si.n_ties; j += NT) {
+    const int s = pair_ties[(size_t)p * H + j];
+    const double es = es_in[(size_t)p * H + s];
+    if (es < best_es) {  // ascending s within a thread: strict < keeps the first
+      best_es = es;
+      best_s = s;
     }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const double oe = __shfl_xor_sync(0xffffffffu, best_es, off);
+    const int os = __shfl_xor_sync(0xffffffffu, best_s, off);
+    if (oe < best_es || (oe == best_es && os < best_s)) {
+      best_es = oe;
+      best_s = os;
+    }
+  }
+  if (NT > 32) {
+    if (lane == 0) {
+      s_es[warp] = best_es;
+      s_i[warp] = best_s;
+    }
+    __syncthreads();
+    best_es = s_es[0];
+    best_s = s_i[0];
+    for (int w = 1; w < NT / 32; ++w)
+      if (s_es[w] < best_es || (s_es[w] == best_es && s_i[w] < best_s)) {
+        best_es = s_es[w];
+        best_s = s_i[w];
+      }
+    __syncthreads();
   }
   int win = best_s;
   const int fn = si.first_nonmax;
@@ -888,25 +962,29 @@ k_sel_final(const PairMeta* __restrict__ meta, const double* __restrict__ Ya, co
   }
   // BestFitIdx: recorded hypotheses up to and including the winner
   int win_iter = 0;
-  for (int s = lane; s <= win; s += 32) win_iter += recorded(s) ? 1 : 0;
+  for (int s = tid; s <= win; s += NT) win_iter += recorded(s) ? 1 : 0;
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) win_iter += __shfl_xor_sync(0xffffffffu, win_iter, off);
+  if (NT > 32) {
+    if (lane == 0) s_i[warp] = win_iter;
+    __syncthreads();
+    win_iter = 0;
+    for (int w = 0; w < NT / 32; ++w) win_iter += s_i[w];
+    __syncthreads();
+  }
 
   // ---- winner: hypothesis, mask, ErrorSum; refit on the support set (:186) --------------------------
   int idx[MAX_K];
   load_sample(samples, seed, pair_id0 + (uint32_t)p, h0, win, H, p, N, k, idx);
   Rigid f;
-  fit_sample(method, ya, yb, idx, k, f);  // every lane computes the same fit
-  double es;
-  if (win == best_s) {
-    es = best_es;
-    for (int i = lane; i < N; i += 32) mask[i] = residual_norm(f.R, f.t, ya + 3 * i, yb + 3 * i) < m.thr ? 1 : 0;
-  } else {
-    es = warp_errsum(f.R, f.t, ya, yb, N, m.thr, mask, nullptr);
-  }
+  fit_sample(method, ya, yb, idx, k, f);  // every thread computes the same fit
+  for (int i = tid; i < N; i += NT) mask[i] = residual_norm(f.R, f.t, ya + 3 * i, yb + 3 * i) < m.thr ? 1 : 0;
   if (masks)
-    for (int i = N + lane; i < mask_stride; i += 32) mask[i] = 0;
-  __syncwarp();
+    for (int i = N + tid; i < mask_stride; i += NT) mask[i] = 0;
+  if (NT > 32) __syncthreads(); else __syncwarp();
+  if (warp != 0) return;
+  double es = best_es;
+  if (win != best_s) es = warp_errsum(f.R, f.t, ya, yb, N, m.thr, nullptr, nullptr);
   Rigid rf;
   const int st = warp_refit(method, ya, yb, mask, N, rf);
   if (lane == 0) {
@@ -1223,7 +1301,7 @@ size_t ransac_workspace_bytes(int P, int Nmax, int H) {
   b += align_up(sizeof(int32_t) * (size_t)P * H);
   b += align_up((size_t)P * H);
   b += align_up((size_t)P * Nmax);  // mask scratch
-  b += align_up(sizeof(SelInfo) * (size_t)P) + 2 * align_up(8 * (size_t)P * (H > 0 ? H : 1)) + 512;  // selection
+  b += align_up(sizeof(SelInfo) * (size_t)P) + 3 * align_up(8 * (size_t)P * (H > 0 ? H : 1)) + 512;  // selection
   b += align_up(sizeof(int32_t) * (size_t)P);  // stop flags
   return b + 4096;
 }
@@ -1383,24 +1461,38 @@ int launch_select(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts&
   SelInfo* info = ws_take<SelInfo>(ctx, b.P);
   double* es = ws_take<double>(ctx, PH);
   int2* ties = ws_take<int2>(ctx, PH);
+  int32_t* pair_ties = ws_take<int32_t>(ctx, PH);
   int* tie_total = ws_take<int>(ctx, 64);
   if (PH >= ((size_t)1 << 31)) return fail(ctx, PRE3_ERR_ARG, "pairs x sample sets must stay below 2^31");
   PRE3_CUDA(cudaMemsetAsync(tie_total, 0, sizeof(int), ctx->stream));
   const int32_t* tab = o.adaptive ? ctx->d_tab : nullptr;
-  if (b.P >= 64)  // batches of pairs: one warp per pair; few (large) pairs: 1024 threads each
+  const bool many = b.P >= 64;  // batches of pairs: one warp per pair; few (large) pairs: 1024 threads each
+  if (many)
     k_sel_scan<32><<<b.P, 32, 0, ctx->stream>>>(b.meta, b.Nmax, o.H, o.k, o.method, o.max_iteration, o.adaptive, tab,
                                                 b.counts, b.states, dres, dmasks, b.Nmax, dcounts_out, dstates_out,
-                                                info, ties, tie_total);
+                                                info, ties, tie_total, pair_ties);
   else
     k_sel_scan<1024><<<b.P, 1024, 0, ctx->stream>>>(b.meta, b.Nmax, o.H, o.k, o.method, o.max_iteration, o.adaptive,
                                                     tab, b.counts, b.states, dres, dmasks, b.Nmax, dcounts_out,
-                                                    dstates_out, info, ties, tie_total);
-  const int tie_blocks = (int)std::min<size_t>((PH + TIE_THREADS - 1) / TIE_THREADS, (size_t)ctx->sm_count * 8);
-  k_sel_tie<<<tie_blocks, TIE_THREADS, 0, ctx->stream>>>(b.meta, b.Ya, b.Yb, b.Nmax, b.samples, o.seed, b.pair_id0, b.h0,
-                                                         o.H, o.k, o.method, ties, tie_total, (int)PH, es);
-  k_sel_final<<<(b.P + SELF_WARPS - 1) / SELF_WARPS, SELF_WARPS * 32, 0, ctx->stream>>>(
-      b.meta, b.Ya, b.Yb, b.P, b.Nmax, b.samples, o.seed, b.pair_id0, b.h0, o.H, o.k, o.method, b.counts, b.states, info,
-      es, dres, dmasks, b.Nmax, scratch);
+                                                    dstates_out, info, ties, tie_total, pair_ties);
+  const size_t tie_warps = TIE_THREADS / 32;
+  const int tie_blocks = (int)std::min<size_t>((PH + tie_warps - 1) / tie_warps, (size_t)ctx->sm_count * 16);
+  if (b.Nmax <= 2048) {  // thread per tie; the ordered sum of a long residual list wants a warp per tie
+    const int tb = (int)std::min<size_t>((PH + TIE_THREADS - 1) / TIE_THREADS, (size_t)ctx->sm_count * 8);
+    k_sel_tie_thread<<<tb, TIE_THREADS, 0, ctx->stream>>>(b.meta, b.Ya, b.Yb, b.Nmax, b.samples, o.seed, b.pair_id0,
+                                                          b.h0, o.H, o.k, o.method, ties, tie_total, (int)PH, es);
+  } else {
+    k_sel_tie<<<tie_blocks, TIE_THREADS, 0, ctx->stream>>>(b.meta, b.Ya, b.Yb, b.Nmax, b.samples, o.seed, b.pair_id0,
+                                                           b.h0, o.H, o.k, o.method, ties, tie_total, (int)PH, es);
+  }
+  if (many)
+    k_sel_final<32><<<b.P, 32, 0, ctx->stream>>>(b.meta, b.Ya, b.Yb, b.P, b.Nmax, b.samples, o.seed, b.pair_id0, b.h0,
+                                                 o.H, o.k, o.method, b.counts, b.states, info, pair_ties, es, dres,
+                                                 dmasks, b.Nmax, scratch);
+  else
+    k_sel_final<512><<<b.P, 512, 0, ctx->stream>>>(b.meta, b.Ya, b.Yb, b.P, b.Nmax, b.samples, o.seed, b.pair_id0,
+                                                     b.h0, o.H, o.k, o.method, b.counts, b.states, info, pair_ties, es,
+                                                     dres, dmasks, b.Nmax, scratch);
   count_launch(ctx, 3);
   PRE3_CUDA(cudaGetLastError());
   return PRE3_OK;

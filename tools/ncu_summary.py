@@ -2,7 +2,7 @@
 """Condense an `ncu --set full` report and/or a launch list into the small text files kept
 under profiles/ (the .ncu-rep itself stays in gpurun_out/, which is scratch).
 
-    python tools/ncu_summary.py --rep gpurun_out/X.ncu-rep --launches gpurun_out/X_launches.csv \
+    python tools/ncu_summary.py --rep gpurun_out/X.ncu-rep|X_raw.csv --launches gpurun_out/X_launches.csv \
         --out profiles/r01_X
 
 writes <out>_kernels.csv (one row per profiled launch: duration, registers, occupancy, DRAM
@@ -43,7 +43,10 @@ METRICS = [
 
 
 def raw_rows(rep):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    if rep.endswith(".csv"):  # already exported on the GPU box (`ncu -i X.ncu-rep --page raw --csv`)
+        out = open(rep).read()
+    else:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     return rows[0], rows[1], rows[2:]
 
@@ -73,6 +76,9 @@ def kernels_table(rep, path):
 
 def launches_table(src, path):
     lines = [l for l in open(src) if not l.startswith("==")]
+    if lines and not lines[0].startswith('"ID"'):  # filtered list: put the header line first
+        hdr = [l for l in lines if l.startswith('"ID"')]
+        lines = hdr[:1] + [l for l in lines if not l.startswith('"ID"')]
     rows = list(csv.DictReader(lines))
     tot = collections.OrderedDict()
     with open(path, "w", newline="") as f:
