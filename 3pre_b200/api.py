@@ -156,6 +156,12 @@ class Context:
     def launch_count(self) -> int:
         return int(self._lib.pre3_launch_count(self._h))
 
+    def transfer_bytes(self):
+        """(host->device, device->host) bytes moved by pairs() so far."""
+        a, b = C.c_int64(0), C.c_int64(0)
+        self._ck(self._lib.pre3_transfer_bytes(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def eval_schedule(self, opts: RansacOpts):
         """Wave boundaries of the hypothesis evaluation (pre3_eval_schedule)."""
         ends = np.zeros(40, np.int32)

@@ -34,7 +34,8 @@ def _nvcc() -> str:
 
 
 def sources():
-    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+    """.cu: CUDA translation units; .cpp: host-only helpers (g++ through nvcc, no device code)."""
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cpp")))
 
 
 def _deps():
@@ -62,12 +63,15 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
     hdr_t = max(os.path.getmtime(d) for d in _deps() if not d.endswith(".cu"))
     objs, procs = [], []
     for src in sources():
-        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        obj = os.path.join(objdir, os.path.splitext(os.path.basename(src))[0] + ".o")
         objs.append(obj)
         if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), hdr_t):
             continue
-        cmd = [nvcc, *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-c", src, "-o", obj]
-        if verbose:
+        if src.endswith(".cpp"):
+            cmd = ["g++", "-O3", "-std=c++17", "-fPIC", "-fvisibility=hidden", "-c", src, "-o", obj]
+        else:
+            cmd = [nvcc, *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-c", src, "-o", obj]
+        if verbose and not src.endswith(".cpp"):
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
@@ -81,7 +85,7 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
     if failed:
         raise RuntimeError("libpre3 build failed")
     link = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
-            "-Xcompiler", "-fPIC", "-cudart", "static"]
+            "-Xcompiler", "-fPIC", "-cudart", "static", "-lpthread"]
     subprocess.run(link, check=True)
     return LIB
 

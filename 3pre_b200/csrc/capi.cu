@@ -3,7 +3,10 @@
 //
 // Every compute entry point fails with PRE3_ERR_CUDA when there is no CUDA device: there is
 // no CPU fallback by design (the CPU restatement lives in oracle/ and is test-only).
+#include <chrono>
+#include <cstdlib>
 #include <cstring>
+#include <thread>
 
 #include "common.cuh"
 #include "match.cuh"
@@ -159,6 +162,10 @@ void pre3_destroy(pre3_ctx* ctx) {
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->d_tab) cudaFree(ctx->d_tab);
     if (ctx->d_ekf_tab) cudaFree(ctx->d_ekf_tab);
+    for (int i = 0; i < 2; ++i) {
+      if (ctx->h_stage[i]) cudaFreeHost(ctx->h_stage[i]);
+      if (ctx->ev_stage_done[i]) cudaEventDestroy(ctx->ev_stage_done[i]);
+    }
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     for (void* p : ctx->aux) cudaFree(p);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
@@ -169,6 +176,7 @@ void pre3_destroy(pre3_ctx* ctx) {
     }
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   }
+  if (ctx->pool) host_pool_destroy(ctx->pool);
   delete ctx;
 }
 
@@ -197,6 +205,13 @@ int pre3_sync(pre3_ctx* ctx) {
 }
 
 int64_t pre3_launch_count(const pre3_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int pre3_transfer_bytes(const pre3_ctx* ctx, int64_t* h2d, int64_t* d2h) {
+  if (!ctx) return PRE3_ERR_ARG;
+  if (h2d) *h2d = ctx->h2d_bytes;
+  if (d2h) *d2h = ctx->d2h_bytes;
+  return PRE3_OK;
+}
 
 int pre3_eval_schedule(const pre3_ransac_opts* opts, int32_t* ends, int cap) {
   if (!opts || (cap > 0 && !ends)) return PRE3_ERR_ARG;
@@ -502,7 +517,32 @@ int pre3_pairs_dev(pre3_ctx* ctx, const void* ddesc1, const void* ddesc2, int cl
 
 // Host buffers: the P pairs are cut into chunks that are staged on a second stream while the
 // previous chunk computes (double-buffered device staging), so that for whole-sequence runs the
-// PCIe copy of the descriptors -- 1 MB per 512x512 pair in class double -- overlaps the kernels.
+// PCIe copy of the descriptors overlaps the kernels.  Class-double descriptors (1 MB per 512x512
+// pair) are narrowed to float into pinned staging by the host pool when every value survives the
+// round trip (hostconv.cpp): half the PCIe bytes, same arithmetic on the device.
+static int ensure_host_stage(pre3_ctx* ctx, size_t bytes_per_slot) {
+  if (ctx->host_f32 < 0) {
+    const char* e = getenv("PRE3_HOST_F32");
+    const unsigned hw = std::thread::hardware_concurrency();
+    ctx->host_f32 = e ? (atoi(e) != 0) : (hw >= 4);
+    if (ctx->host_f32) ctx->pool = host_pool_create((int)std::min<unsigned>(hw > 1 ? hw - 1 : 1, 15));
+  }
+  if (!ctx->host_f32) return PRE3_OK;
+  if (ctx->h_stage_cap < bytes_per_slot) {
+    for (int i = 0; i < 2; ++i) {
+      if (ctx->h_stage[i]) {
+        cudaStreamSynchronize(ctx->copy_stream ? ctx->copy_stream : ctx->stream);
+        cudaFreeHost(ctx->h_stage[i]);
+        ctx->h_stage[i] = nullptr;
+      }
+      PRE3_CUDA(cudaHostAlloc((void**)&ctx->h_stage[i], bytes_per_slot, cudaHostAllocDefault));
+      if (!ctx->ev_stage_done[i]) PRE3_CUDA(cudaEventCreateWithFlags(&ctx->ev_stage_done[i], cudaEventDisableTiming));
+    }
+    ctx->h_stage_cap = bytes_per_slot;
+  }
+  return PRE3_OK;
+}
+
 int pre3_pairs(pre3_ctx* ctx, const void* desc1, const void* desc2, int cls, const double* xyz1, const double* xyz2,
                int P, int K1, int K2, int ND, const int32_t* k1_count, const int32_t* k2_count,
                const pre3_ransac_opts* opts, uint32_t pair_id0, pre3_pair_result* res, int32_t* matches,
@@ -552,14 +592,67 @@ int pre3_pairs(pre3_ctx* ctx, const void* desc1, const void* desc2, int cls, con
   }
   PRE3_TRY(ensure_copy_stream(ctx));
   PRE3_TRY(ws_reserve(ctx, pairs_ws_bytes(cls, C, K1, K2, ND, opts->H)));
+  const size_t n1 = (size_t)K1 * ND, n2 = (size_t)K2 * ND;  // descriptor values per pair
+  bool narrow = cls == PRE3_CLASS_DOUBLE && ND > 0;
+  if (narrow) {
+    PRE3_TRY(ensure_host_stage(ctx, 4 * (n1 + n2) * (size_t)C));
+    narrow = ctx->host_f32 == 1;
+  }
+  // results come back through pinned staging: a device->host copy into pageable user memory would block
+  // the host until the chunk's kernels have finished and serialise the whole pipeline
+  const size_t rb_res = sizeof(pre3_pair_result) * (size_t)P, rb_m = matches ? 8 * (size_t)K1 * P : 0,
+               rb_k = masks ? (size_t)K1 * P : 0;
+  if (ctx->h_pin_cap < rb_res + rb_m + rb_k) {
+    if (ctx->h_pin) {
+      cudaStreamSynchronize(ctx->stream);
+      cudaFreeHost(ctx->h_pin);
+      ctx->h_pin = nullptr;
+      ctx->h_pin_cap = 0;
+    }
+    PRE3_CUDA(cudaHostAlloc(&ctx->h_pin, rb_res + rb_m + rb_k, cudaHostAllocDefault));
+    ctx->h_pin_cap = rb_res + rb_m + rb_k;
+  }
+  char* hp_res = (char*)ctx->h_pin;
+  char* hp_m = hp_res + rb_res;
+  char* hp_k = hp_m + rb_m;
+  int chunk_cls[2] = {cls, cls};
+  const int raw_every = getenv("PRE3_HOST_F32_RAW_EVERY") ? atoi(getenv("PRE3_HOST_F32_RAW_EVERY")) : 5;
   cudaStream_t cs = ctx->copy_stream;
+  double t_conv = 0.0, t_wait = 0.0, t_enq = 0.0, t_stage = 0.0;  // PRE3_DEBUG diagnostics
+  auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   auto stage_in = [&](int c) -> int {
     const int s = c & 1;
     const int p0 = c * C, n = std::min(C, P - p0);
-    // the slot may still be read by the compute of chunk c-2 / written back by its D2H
+    bool as_f32 = false;
+    // every raw_every-th chunk crosses as doubles: the host pool (~75 GB/s of doubles on a 16-core host)
+    // and the PCIe link (~54 GB/s) then finish together instead of the link waiting for the pool
+    if (narrow && !(raw_every > 0 && c % raw_every == raw_every - 1)) {
+      // the pinned slot is free once the H2D of chunk c-2 has finished
+      const double ta = now();
+      if (c >= 2) PRE3_CUDA(cudaEventSynchronize(ctx->ev_stage_done[s]));
+      const double tb = now();
+      float* f1 = (float*)ctx->h_stage[s];
+      float* f2 = f1 + n1 * (size_t)C;
+      as_f32 = host_narrow(ctx->pool, (const double*)desc1 + (size_t)p0 * n1, f1, n1 * n) &&
+               host_narrow(ctx->pool, (const double*)desc2 + (size_t)p0 * n2, f2, n2 * n);
+      t_wait += tb - ta;
+      t_conv += now() - tb;
+    }
+    chunk_cls[s] = as_f32 ? PRE3_CLASS_DOUBLE_F32 : cls;
+    ctx->h2d_bytes += (int64_t)((as_f32 ? 4 * (n1 + n2) : pb1 + pb2) * n + 24 * ((size_t)K1 + K2) * n +
+                                (k1_count ? 4 * (size_t)n : 0) + (k2_count ? 4 * (size_t)n : 0));
+    // the device slot may still be read by the compute of chunk c-2 / written back by its D2H
     PRE3_CUDA(cudaStreamWaitEvent(cs, ctx->ev_slot_free[s], 0));
-    PRE3_CUDA(cudaMemcpyAsync(slot[s].d1, (const char*)desc1 + (size_t)p0 * pb1, pb1 * n, cudaMemcpyHostToDevice, cs));
-    PRE3_CUDA(cudaMemcpyAsync(slot[s].d2, (const char*)desc2 + (size_t)p0 * pb2, pb2 * n, cudaMemcpyHostToDevice, cs));
+    if (as_f32) {
+      const float* f1 = (const float*)ctx->h_stage[s];
+      PRE3_CUDA(cudaMemcpyAsync(slot[s].d1, f1, 4 * n1 * n, cudaMemcpyHostToDevice, cs));
+      PRE3_CUDA(cudaMemcpyAsync(slot[s].d2, f1 + n1 * (size_t)C, 4 * n2 * n, cudaMemcpyHostToDevice, cs));
+      PRE3_CUDA(cudaEventRecord(ctx->ev_stage_done[s], cs));
+    } else {
+      PRE3_CUDA(cudaMemcpyAsync(slot[s].d1, (const char*)desc1 + (size_t)p0 * pb1, pb1 * n, cudaMemcpyHostToDevice, cs));
+      PRE3_CUDA(cudaMemcpyAsync(slot[s].d2, (const char*)desc2 + (size_t)p0 * pb2, pb2 * n, cudaMemcpyHostToDevice, cs));
+      if (narrow) PRE3_CUDA(cudaEventRecord(ctx->ev_stage_done[s], cs));  // keeps the slot's event current
+    }
     PRE3_CUDA(cudaMemcpyAsync(slot[s].x1, xyz1 + 3 * (size_t)p0 * K1, 24 * (size_t)K1 * n, cudaMemcpyHostToDevice, cs));
     PRE3_CUDA(cudaMemcpyAsync(slot[s].x2, xyz2 + 3 * (size_t)p0 * K2, 24 * (size_t)K2 * n, cudaMemcpyHostToDevice, cs));
     if (k1_count) PRE3_CUDA(cudaMemcpyAsync(slot[s].k1, k1_count + p0, 4 * (size_t)n, cudaMemcpyHostToDevice, cs));
@@ -574,20 +667,35 @@ int pre3_pairs(pre3_ctx* ctx, const void* desc1, const void* desc2, int cls, con
   for (int c = 0; c < nchunks; ++c) {
     const int s = c & 1;
     const int p0 = c * C, n = std::min(C, P - p0);
-    if (c + 1 < nchunks) PRE3_TRY(stage_in(c + 1));
+    // enqueue the compute of chunk c first: the host then narrows chunk c+1 while the copy engine moves
+    // chunk c (already enqueued) and the SMs work on it
+    const double tq0 = now();
     PRE3_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_slot_full[s], 0));
     ctx->ws_off = 0;  // arena reused by every chunk (stream order keeps it safe)
-    PRE3_TRY(pairs_impl(ctx, slot[s].d1, slot[s].d2, cls, slot[s].x1, slot[s].x2, n, K1, K2, ND,
+    PRE3_TRY(pairs_impl(ctx, slot[s].d1, slot[s].d2, chunk_cls[s], slot[s].x1, slot[s].x2, n, K1, K2, ND,
                         k1_count ? slot[s].k1 : nullptr, k2_count ? slot[s].k2 : nullptr, *opts,
                         pair_id0 + (uint32_t)p0, slot[s].r, matches ? slot[s].m : nullptr,
                         masks ? slot[s].msk : nullptr));
-    PRE3_TRY(d2h(ctx, res + p0, slot[s].r, sizeof(pre3_pair_result) * (size_t)n));
-    if (matches) PRE3_TRY(d2h(ctx, matches + 2 * (size_t)p0 * K1, slot[s].m, 8 * (size_t)K1 * n));
-    if (masks) PRE3_TRY(d2h(ctx, masks + (size_t)p0 * K1, slot[s].msk, (size_t)K1 * n));
+    PRE3_TRY(d2h(ctx, hp_res + sizeof(pre3_pair_result) * (size_t)p0, slot[s].r, sizeof(pre3_pair_result) * (size_t)n));
+    if (matches) PRE3_TRY(d2h(ctx, hp_m + 8 * (size_t)p0 * K1, slot[s].m, 8 * (size_t)K1 * n));
+    if (masks) PRE3_TRY(d2h(ctx, hp_k + (size_t)p0 * K1, slot[s].msk, (size_t)K1 * n));
+    ctx->d2h_bytes += (int64_t)(sizeof(pre3_pair_result) * (size_t)n + (matches ? 8 * (size_t)K1 * n : 0) +
+                                (masks ? (size_t)K1 * n : 0));
     PRE3_CUDA(cudaEventRecord(ctx->ev_slot_free[s], ctx->stream));
+    const double tq1 = now();
+    t_enq += tq1 - tq0;
+    if (c + 1 < nchunks) PRE3_TRY(stage_in(c + 1));
+    t_stage += now() - tq1;
   }
+  const double t_sync0 = now();
   PRE3_CUDA(cudaStreamSynchronize(ctx->stream));
   PRE3_CUDA(cudaStreamSynchronize(cs));
+  memcpy(res, hp_res, rb_res);
+  if (matches) memcpy(matches, hp_m, rb_m);
+  if (masks) memcpy(masks, hp_k, rb_k);
+  if (getenv("PRE3_DEBUG"))
+    fprintf(stderr, "[pre3] pairs: P=%d chunks=%d narrow=%d host narrowing %.1f ms, staging waits %.1f ms, enqueue compute %.1f ms, stage_in %.1f ms, final sync %.1f ms\n",
+            P, nchunks, (int)narrow, t_conv * 1e3, t_wait * 1e3, t_enq * 1e3, t_stage * 1e3, (now() - t_sync0) * 1e3);
   return PRE3_OK;
 }
 

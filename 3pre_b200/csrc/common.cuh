@@ -9,7 +9,17 @@
 
 #include "../../include/pre3.h"
 
+// Internal storage class of the host-pointer batch entry points: values of class double that were
+// narrowed to float for the PCIe transfer (every value survives the round trip, hostconv.cpp); the
+// arithmetic stays that of PRE3_CLASS_DOUBLE (double accumulation).
+#define PRE3_CLASS_DOUBLE_F32 100
+
 namespace pre3 {
+class HostPool;
+HostPool* host_pool_create(int threads);
+void host_pool_destroy(HostPool* p);
+int host_pool_size(const HostPool* p);
+bool host_narrow(HostPool* pool, const double* s, float* d, size_t n);
 // per-kernel timing categories (pre3_timing_*): bench.py's roofline numbers come from here
 enum TimeCat { T_CONVERT = 0, T_MATCH_TC, T_MATCH_EXACT, T_RESCORE, T_COMPACT, T_PREP, T_EVAL, T_SELECT, T_OTHER, T_EKF_GAIN, T_EKF_SCORE, T_EKF_SELECT, T_NCAT };
 struct TimedSpan {
@@ -25,6 +35,7 @@ struct pre3_ctx {
   int match_engine = PRE3_MATCH_AUTO;
   int sm_count = 148;
   int64_t launches = 0;
+  int64_t h2d_bytes = 0, d2h_bytes = 0;  // moved by the host-pointer whole-pair entry point (bench.py's e2e)
   std::string err;
   // growable device workspace (bump allocator, reset per API call)
   char* ws = nullptr;
@@ -48,6 +59,13 @@ struct pre3_ctx {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_slot_full[2] = {nullptr, nullptr};
   cudaEvent_t ev_slot_free[2] = {nullptr, nullptr};
+  // host-side narrowing of double descriptors for the transfer (hostconv.cpp): pool, pinned float
+  // staging (two slots), "H2D of this slot has finished" events
+  pre3::HostPool* pool = nullptr;
+  int host_f32 = -1;  // -1 undecided, 0 off, 1 on
+  char* h_stage[2] = {nullptr, nullptr};
+  size_t h_stage_cap = 0;
+  cudaEvent_t ev_stage_done[2] = {nullptr, nullptr};
   // optional per-launch CUDA-event timing (off by default)
   bool timing = false;
   std::vector<pre3::TimedSpan> spans;

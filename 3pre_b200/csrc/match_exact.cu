@@ -276,6 +276,10 @@ int launch_match_exact(pre3_ctx* ctx, const void* dL1, const void* dL2, int cls,
       k_match_exact<float, float><<<grid, 256, 0, ctx->stream>>>((const float*)dL1, (const float*)dL2, K1, K2, ND, dk1,
                                                                   dk2, thresh, nullptr, nullptr, drows);
       break;
+    case PRE3_CLASS_DOUBLE_F32:  // class double stored as float: double arithmetic
+      k_match_exact<float, double><<<grid, 256, 0, ctx->stream>>>((const float*)dL1, (const float*)dL2, K1, K2, ND, dk1,
+                                                                   dk2, thresh, nullptr, nullptr, drows);
+      break;
     case PRE3_CLASS_INT8:
       k_match_exact<signed char, int><<<grid, 256, 0, ctx->stream>>>((const signed char*)dL1, (const signed char*)dL2,
                                                                       K1, K2, ND, dk1, dk2, thresh, nullptr, nullptr,
@@ -308,6 +312,10 @@ int launch_match_rows_exact(pre3_ctx* ctx, const void* dL1, const void* dL2, int
     k_match_rows_exact<float, float><<<blocks, 32, 0, ctx->stream>>>((const float*)dL1, (const float*)dL2, K1, K2, ND,
                                                                        dk2, thresh, drow_list, drow_list_n, list_cap,
                                                                        drows);
+  else if (cls == PRE3_CLASS_DOUBLE_F32)
+    k_match_rows_exact<float, double><<<blocks, 32, 0, ctx->stream>>>((const float*)dL1, (const float*)dL2, K1, K2, ND,
+                                                                        dk2, thresh, drow_list, drow_list_n, list_cap,
+                                                                        drows);
   else
     return fail(ctx, PRE3_ERR_CLASS, "row recheck: class must be double or single");
   count_launch(ctx);

@@ -431,6 +431,11 @@ __device__ __forceinline__ void load_row4<float, float>(const float* src, float*
   const float4 x = __ldg(reinterpret_cast<const float4*>(src));
   v[0] = x.x, v[1] = x.y, v[2] = x.z, v[3] = x.w;
 }
+template <>
+__device__ __forceinline__ void load_row4<float, double>(const float* src, double* v) {
+  const float4 x = __ldg(reinterpret_cast<const float4*>(src));
+  v[0] = x.x, v[1] = x.y, v[2] = x.z, v[3] = x.w;
+}
 
 template <typename T, typename ACC>
 __global__ void __launch_bounds__(32)
@@ -569,7 +574,8 @@ k_tc_rescore(const T* __restrict__ L1, const T* __restrict__ L2, int K1, int K2,
 static inline int pad128(int k) { return (k + 127) / 128 * 128; }
 
 bool match_tc_supported(int cls, int K1, int K2, int ND) {
-  return (cls == PRE3_CLASS_DOUBLE || cls == PRE3_CLASS_SINGLE) && ND == tc::ND && K1 >= 1 && K2 >= 1;
+  return (cls == PRE3_CLASS_DOUBLE || cls == PRE3_CLASS_SINGLE || cls == PRE3_CLASS_DOUBLE_F32) && ND == tc::ND &&
+         K1 >= 1 && K2 >= 1;
 }
 
 size_t match_tc_workspace_bytes(int P, int K1, int K2) {
@@ -636,6 +642,10 @@ int launch_match_tc(pre3_ctx* ctx, const void* dL1, const void* dL2, int cls, in
       k_tc_rescore<double, double><<<g, 32, 0, ctx->stream>>>((const double*)dL1, (const double*)dL2, K1, K2,
                                                                           K1p, K2p, dk1, dk2, thresh, prop, nrmA, info,
                                                                           need_score, drows, list, list_n);
+    else if (cls == PRE3_CLASS_DOUBLE_F32)
+      k_tc_rescore<float, double><<<g, 32, 0, ctx->stream>>>((const float*)dL1, (const float*)dL2, K1, K2,
+                                                                         K1p, K2p, dk1, dk2, thresh, prop, nrmA, info,
+                                                                         need_score, drows, list, list_n);
     else
       k_tc_rescore<float, float><<<g, 32, 0, ctx->stream>>>((const float*)dL1, (const float*)dL2, K1, K2,
                                                                         K1p, K2p, dk1, dk2, thresh, prop, nrmA, info,
@@ -643,7 +653,7 @@ int launch_match_tc(pre3_ctx* ctx, const void* dL1, const void* dL2, int cls, in
     count_launch(ctx);
   }
   PRE3_CUDA(cudaGetLastError());
-  if (getenv("PRE3_DEBUG")) {  // diagnostics only: how many rows fall back to the exact kernel
+  if (getenv("PRE3_DEBUG") && atoi(getenv("PRE3_DEBUG")) >= 2) {  // diagnostics only: how many rows fall back to the exact kernel
     int32_t n = 0;
     PRE3_CUDA(cudaMemcpyAsync(&n, list_n, 4, cudaMemcpyDeviceToHost, ctx->stream));
     PRE3_CUDA(cudaStreamSynchronize(ctx->stream));

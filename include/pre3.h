@@ -104,6 +104,11 @@ PRE3_API int pre3_set_match_engine(pre3_ctx *ctx, int engine);
 PRE3_API int pre3_sync(pre3_ctx *ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 PRE3_API int64_t pre3_launch_count(const pre3_ctx *ctx);
+/* bytes pre3_pairs has moved over PCIe so far (host -> device, device -> host): bench.py's e2e figures.
+ * Class-double descriptors whose values all survive (double)(float)x == x -- the reference's descriptors
+ * are floats stored in a double matrix, M/sift/siftdescriptor.c:500-527 -- cross as float and are widened
+ * on the device (same arithmetic); PRE3_HOST_F32=0 in the environment turns that off. */
+PRE3_API int pre3_transfer_bytes(const pre3_ctx *ctx, int64_t *h2d, int64_t *d2h);
 /* With the adaptive stop on, the batch entry points evaluate the sample sets of a pair in waves
  * and skip the later waves of pairs whose loop (RANSAC_CALC_VER2.m:86) has already ended.
  * Writes the wave boundaries (sample sets evaluated after wave i) into ends[0..cap) and returns the

@@ -329,6 +329,34 @@ def test_pairs_chunked_host_path_equals_device_path(ctx, synth, pre3):
 # ------------------------------------------------------------------------------------------
 # full-size properties (configs 2, 3, 5 shapes) -- no oracle at these sizes
 # ------------------------------------------------------------------------------------------
+def test_pairs_host_narrowing_is_lossless_and_falls_back(ctx, synth, pre3):
+    """Host path: float-exact double descriptors cross PCIe as float (half the bytes), others as double;
+    either way the results equal the device path bit for bit."""
+    import torch
+    P, K = 6, 256
+    b = synth.make_batch_torch(P, 910, "cuda", K1=K, K2=K, n_corr=150)
+    opts = pre3.make_opts(H=500, seed=3)
+    for exact in (True, False):
+        d1, d2 = b["desc1"].clone(), b["desc2"].clone()
+        if not exact:  # full double precision in one value of pair 3
+            d1[3, 7, 5] += 1e-13
+        res = torch.zeros(P, 240, dtype=torch.uint8, device="cuda")
+        m = torch.zeros(P, K, 2, dtype=torch.int32, device="cuda")
+        ctx.pairs_dev(d1, d2, b["xyz1"], b["xyz2"], opts, res, m)
+        ctx.sync()
+        dev = np.frombuffer(res.cpu().numpy().tobytes(), dtype=pre3.RESULT_DTYPE)
+        t0 = ctx.transfer_bytes()[0]
+        hres, hm, _ = ctx.pairs(d1.cpu().numpy(), d2.cpu().numpy(), b["xyz1"].cpu().numpy(), b["xyz2"].cpu().numpy(), opts)
+        moved = ctx.transfer_bytes()[0] - t0
+        assert hres.tobytes() == dev.tobytes()
+        md = m.cpu().numpy()
+        for p in range(P):  # entries beyond the pair's match count are not written
+            n = int(dev["n_matches"][p])
+            np.testing.assert_array_equal(hm[p, :n], md[p, :n])
+        desc_bytes = 2 * P * K * 128 * 8
+        assert moved < 0.6 * desc_bytes if exact else moved > desc_bytes
+
+
 def test_matching_full_size_properties(ctx, synth):
     """2k x 2k descriptors: planted matches are found; matching L against itself returns the
     identity with score 0; results are independent of the batch position."""
