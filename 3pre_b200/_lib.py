@@ -88,6 +88,7 @@ SYMBOLS = {
     "pre3_timing_read": (_I, [_VP, _VP, _VP]),
     "pre3_timing_name": (C.c_char_p, [_I]),
     "pre3_measure_fp32_peak": (_I, [_VP, _VP]),
+    "pre3_measure_fp32_peak_mode": (_I, [_VP, _I, _VP]),
     "pre3_siftmatch": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _D, _VP, _VP, _VP]),
     "pre3_siftmatch_batch": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _I, _VP, _VP, _D, _VP, _VP, _VP]),
     "pre3_siftmatch_batch_dev": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _I, _VP, _VP, _D, _VP, _VP, _VP]),

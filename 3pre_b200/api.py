@@ -193,6 +193,11 @@ class Context:
             raise Pre3Error(n, "pre3_ekf_eval_schedule")
         return ends[:n].copy()
 
+    def measure_fp32_peak_3reg(self) -> float:
+        v = C.c_double(0.0)
+        self._ck(self._lib.pre3_measure_fp32_peak_mode(self._h, 1, C.byref(v)))
+        return v.value
+
     def measure_fp32_peak(self) -> float:
         """FFMA-chain microbenchmark, TFLOP/s (the scoring roofline's denominator)."""
         t = np.zeros(1)

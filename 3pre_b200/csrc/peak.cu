@@ -25,6 +25,39 @@ __global__ void __launch_bounds__(256) k_fp32_peak(float* out, int iters, float 
   if (s == 123.456f) out[0] = s;  // never true; keeps the chains alive
 }
 
+// Same chains with all three FFMA sources in registers (the form a scorer with per-thread hypotheses and
+// per-match operands needs): the multiplier / addend come from memory, so ptxas cannot use the constant-bank
+// or immediate forms.
+__global__ void __launch_bounds__(256) k_fp32_peak_3reg(float* out, int iters, const float* __restrict__ ab) {
+  float x0 = threadIdx.x, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f,
+        x7 = x0 + 7.f;
+  const float a0 = ab[threadIdx.x & 7], b0 = ab[8 + (threadIdx.x & 7)], a1 = ab[16 + (threadIdx.x & 3)],
+              b1 = ab[24 + (threadIdx.x & 3)];
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      x0 = fmaf(x0, a0, b0);
+      x1 = fmaf(x1, a1, b1);
+      x2 = fmaf(x2, a0, b1);
+      x3 = fmaf(x3, a1, b0);
+      x4 = fmaf(x4, b0, a0);
+      x5 = fmaf(x5, b1, a1);
+      x6 = fmaf(x6, b0, a1);
+      x7 = fmaf(x7, b1, a0);
+      x0 = fmaf(x0, a1, b1);
+      x1 = fmaf(x1, a0, b0);
+      x2 = fmaf(x2, a1, b0);
+      x3 = fmaf(x3, a0, b1);
+      x4 = fmaf(x4, b1, a1);
+      x5 = fmaf(x5, b0, a0);
+      x6 = fmaf(x6, b1, a0);
+      x7 = fmaf(x7, b0, a1);
+    }
+  }
+  const float s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+  if (s == 123.456f) out[0] = s;
+}
+
 // FP64 DFMA chains: the denominator of the EKF kernels' roofline.
 __global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, double a, double b) {
   double x0 = threadIdx.x, x1 = x0 + 1.0, x2 = x0 + 2.0, x3 = x0 + 3.0, x4 = x0 + 4.0, x5 = x0 + 5.0, x6 = x0 + 6.0,
@@ -76,12 +109,17 @@ extern "C" int pre3_measure_fp64_peak(pre3_ctx* ctx, double* tflops) {
   return PRE3_OK;
 }
 
-extern "C" int pre3_measure_fp32_peak(pre3_ctx* ctx, double* tflops) {
+// mode 0: constant-bank operands (the classic peak); mode 1: three register operands
+extern "C" int pre3_measure_fp32_peak_mode(pre3_ctx* ctx, int mode, double* tflops) {
   using namespace pre3;
   if (!ctx || ctx->device < 0 || !tflops) return PRE3_ERR_CUDA;
   PRE3_CUDA(cudaSetDevice(ctx->device));
-  PRE3_TRY(ws_reserve(ctx, 4096));
+  PRE3_TRY(ws_reserve(ctx, 8192));
   float* out = ws_take<float>(ctx, 16);
+  float* ab = ws_take<float>(ctx, 32);
+  float hab[32];
+  for (int i = 0; i < 32; ++i) hab[i] = (i & 8) ? 0.001f + 1e-6f * i : 0.999f - 1e-6f * i;
+  PRE3_CUDA(cudaMemcpyAsync(ab, hab, sizeof hab, cudaMemcpyHostToDevice, ctx->stream));
   const int blocks = ctx->sm_count * 8, iters = 4096;
   cudaEvent_t a, b;
   PRE3_CUDA(cudaEventCreate(&a));
@@ -89,7 +127,10 @@ extern "C" int pre3_measure_fp32_peak(pre3_ctx* ctx, double* tflops) {
   double best = 0.0;
   for (int rep = 0; rep < 5; ++rep) {
     PRE3_CUDA(cudaEventRecord(a, ctx->stream));
-    k_fp32_peak<<<blocks, 256, 0, ctx->stream>>>(out, iters, 0.999f, 0.001f);
+    if (mode == 0)
+      k_fp32_peak<<<blocks, 256, 0, ctx->stream>>>(out, iters, 0.999f, 0.001f);
+    else
+      k_fp32_peak_3reg<<<blocks, 256, 0, ctx->stream>>>(out, iters, ab);
     PRE3_CUDA(cudaEventRecord(b, ctx->stream));
     PRE3_CUDA(cudaEventSynchronize(b));
     float ms = 0.f;
@@ -102,4 +143,8 @@ extern "C" int pre3_measure_fp32_peak(pre3_ctx* ctx, double* tflops) {
   cudaEventDestroy(b);
   *tflops = best;
   return PRE3_OK;
+}
+
+extern "C" int pre3_measure_fp32_peak(pre3_ctx* ctx, double* tflops) {
+  return pre3_measure_fp32_peak_mode(ctx, 0, tflops);
 }

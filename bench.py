@@ -343,9 +343,11 @@ def bench_cfg5(ctx, pre3, synth, dev, rank, world, N=20000, H=1000000, steps=3, 
     ev = kt.get("eval", {}).get("ms_per_step", 0.0)
     if ev > 0:
         fp32_peak = ctx.measure_fp32_peak()
+        fp32_peak_3reg = ctx.measure_fp32_peak_3reg()
         a = FLOPS_PER_EVAL * float(N) * (h1 - h0) / (ev * 1e-3) / 1e12
         out["roofline"] = {"kernel": "eval (k_eval<5,0>)", "bound": "fp32", "achieved": a, "peak": fp32_peak,
                            "unit": "TFLOP/s", "frac": a / fp32_peak, "traffic": None,
+                           "peak_register_operands": fp32_peak_3reg, "frac_of_register_operand_peak": a / fp32_peak_3reg,
                            "evals_per_s": float(N) * (h1 - h0) / (ev * 1e-3),
                            "note": "27 FLOP per hypothesis x match eval; the fp64 5-point fits run in the same kernel; "
                                    "peak = FFMA-chain microbenchmark of this run"}
@@ -459,6 +461,7 @@ def run_ours(args):
     dom = max(per_kernel, key=lambda k: per_kernel[k]["ms_per_step"])
     pk = peaks()
     fp32_peak = ctx.measure_fp32_peak()
+    fp32_peak_3reg = ctx.measure_fp32_peak_3reg()
     desc_bytes = float(2 * P * K_FEAT * 128 * data["desc1"].element_size())
     match_flops = 2.0 * K_FEAT * K_FEAT * 128 * P
     rooflines = {}
@@ -472,7 +475,11 @@ def run_ours(args):
                                "note": "27 FLOP per hypothesis x match eval over the evaluations executed (the fp64 "
                                        "minimal fits run in the same kernel and are not counted); peak = FFMA-chain "
                                        "microbenchmark measured in this run (MEASURED_PEAKS.json has no FP32 figure)",
-                               "evals_per_s": evals_done / L / sec}
+                               "evals_per_s": evals_done / L / sec,
+                               "peak_register_operands": fp32_peak_3reg, "frac_of_register_operand_peak": a / fp32_peak_3reg,
+                               "note2": "peak_register_operands = the same FFMA chains with all three sources in registers "
+                                        "(hypothesis in registers x correspondence from shared memory): the issue rate this "
+                                        "kernel's FFMAs can reach"}
         elif name in ("match_tc",):
             a = match_flops / L / sec / 1e12
             rooflines[name] = {"bound": "tensor", "achieved": a, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",

@@ -126,6 +126,9 @@ PRE3_API const char *pre3_timing_name(int cat);
 /* FFMA-chain microbenchmark: the measured FP32 CUDA-core peak (TFLOP/s) that the scoring
  * kernel's roofline fraction is quoted against. */
 PRE3_API int pre3_measure_fp32_peak(pre3_ctx *ctx, double *tflops);
+/* mode 0: FFMA with constant-bank operands (= pre3_measure_fp32_peak); mode 1: all three sources in registers,
+ * the form the scorer's inner loop needs (per-thread hypothesis x per-match operand). */
+PRE3_API int pre3_measure_fp32_peak_mode(pre3_ctx *ctx, int mode, double *tflops);
 
 /* ---- stage 1: siftmatch -----------------------------------------------------------
  * Replaces compare_mx*_CLASS + mexFunction of M/sift/siftmatch.c:83-250.
