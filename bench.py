@@ -355,12 +355,71 @@ def bench_cfg5(ctx, pre3, synth, dev, rank, world, N=20000, H=1000000, steps=3, 
     return out
 
 
+def bench_cfg1(ctx, pre3, synth, dev):
+    """configs[0]: one synthetic SR4000 frame pair (~300 matches, 30% outliers), 2000 hypotheses: a LATENCY
+    number on the GPU (one pair cannot fill the machine); k=5 (RANSAC_CALC_VER2.m:85) and k=3 (BASELINE wording)."""
+    import torch
+    fp = synth.make_frame_pair(1000, K1=512, K2=512, n_corr=300, outlier_ratio=0.30)
+    h = {k: np.ascontiguousarray(getattr(fp, k))[None] for k in ("desc1", "desc2", "xyz1", "xyz2")}
+    d = {k: torch.from_numpy(v).to(dev) for k, v in h.items()}
+    res = torch.zeros(1, 240, dtype=torch.uint8, device=dev)
+    out = {"workload": "cfg1: one SR4000 frame pair, 512x512 descriptors -> ~300 matches, 30% outliers, 2000 sample "
+                       "sets, adaptive stop (latency; match + RANSAC + refit)"}
+    for k in (5, 3):
+        opts = pre3.make_opts(method=0, k=k, max_iteration=2000, adaptive=True, H=2000, seed=7)
+        ms_dev = _time_steps(lambda: ctx.pairs_dev(d["desc1"], d["desc2"], d["xyz1"], d["xyz2"], opts, res), 20, 3)
+        t0 = time.perf_counter()
+        for _ in range(20):
+            r, _, _ = ctx.pairs(h["desc1"], h["desc2"], h["xyz1"], h["xyz2"], opts)
+        ms_host = (time.perf_counter() - t0) / 20 * 1e3
+        out[f"k{k}"] = {"ms_per_pair_device_resident": ms_dev, "ms_per_pair_host_buffers": ms_host,
+                        "best_fit": int(r["best_fit"][0]), "n_matches": int(r["n_matches"][0]),
+                        "sample_sets_consumed": int(r["n_consumed"][0])}
+    return out
+
+
+def cpu_other_baselines(synth):
+    """The CPU path (one thread) on bounded samples of cfg2 / cfg4 / cfg5, for the report."""
+    from oracle import oracle as orc
+    from oracle import refmex
+    out = {}
+    fp = synth.make_frame_pair(2000, K1=2048, K2=2048, n_corr=1024)
+    t0 = time.perf_counter()
+    if refmex.available():
+        refmex.siftmatch(fp.desc1, fp.desc2, nout=1)
+    else:
+        orc.siftmatch(fp.desc1, fp.desc2, 1.5)
+    dt = time.perf_counter() - t0
+    out["cfg2"] = {"pairs_per_s": 1.0 / dt, "cores": 1, "kind": cpu_kind(), "sample": "1 pair 2048x2048x128 (double)"}
+    se = importlib.import_module("3pre_b200.synth_ekf")
+    b = se.make_ekf_frames(2, 4000, n_id=200, outlier_ratio=0.2)
+    t0 = time.perf_counter()
+    ne = 0
+    for f in range(2):
+        ne += orc.ransac_hypotheses(se.frame(b, f), None, H=1000, seed=11, frame_id=f)["n_evaluated"]
+    dt = time.perf_counter() - t0
+    out["cfg4"] = {"frames_per_s": 2.0 / dt, "hyp_x_feature_evals_per_s": ne * 200 / dt, "cores": 1, "kind": "port",
+                   "sample": f"2 frames, adaptive stop ({ne} hypotheses evaluated), C restatement (oracle/pre3_oracle_ekf.c)"}
+    c = synth.make_correspondences(5000, N=20000, outlier_ratio=0.6)
+    smp = orc.sample_sets(5, 0, 200, 20000, 5)
+    t0 = time.perf_counter()
+    orc.ransac(c.Ya, c.Yb, smp, method=0, max_iteration=201, adaptive=False)
+    dt = time.perf_counter() - t0
+    out["cfg5"] = {"hyp_x_match_evals_per_s": 200 * 20000 / dt, "cores": 1, "kind": "port",
+                   "ms_per_solve_extrapolated": dt / 200 * 1e6 * 1e3,
+                   "sample": "200 of the 1M hypotheses, extrapolated linearly (the literal reference stores a support "
+                             "set per hypothesis, infeasible at 1M)"}
+    return out
+
+
 def other_workloads(ctx, pre3, synth, dev, rank, world):
     out = {}
     jobs = [("cfg5", lambda: bench_cfg5(ctx, pre3, synth, dev, rank, world))]
     if rank == 0:  # single-GPU configs: measured on rank 0 only (the other ranks wait at the next barrier)
-        jobs = [("cfg2", lambda: bench_cfg2(ctx, pre3, synth, dev, rank)),
-                ("cfg4", lambda: bench_cfg4(ctx, pre3, dev, rank))] + jobs
+        jobs = [("cfg1", lambda: bench_cfg1(ctx, pre3, synth, dev)),
+                ("cfg2", lambda: bench_cfg2(ctx, pre3, synth, dev, rank)),
+                ("cfg4", lambda: bench_cfg4(ctx, pre3, dev, rank)),
+                ("cpu", lambda: cpu_other_baselines(synth))] + jobs
     # cfg5 involves every rank: run it first everywhere so that no rank waits inside a collective
     jobs.sort(key=lambda j: j[0] != "cfg5")
     for name, fn in jobs:
