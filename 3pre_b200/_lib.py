@@ -113,6 +113,7 @@ SYMBOLS = {
                                               _VP, _VP, _VP, _VP, _VP, C.POINTER(EkfOpts), _U32, _VP, _VP, _VP]),
     "pre3_ekf_eval_schedule": (_I, [C.POINTER(EkfOpts), _VP, _I]),
     "pre3_measure_fp64_peak": (_I, [_VP, _VP]),
+    "pre3_measure_tmem_read": (_I, [_VP, _VP]),
 }
 
 _lib = None

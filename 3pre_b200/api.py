@@ -181,6 +181,12 @@ class Context:
         return {self._lib.pre3_timing_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(L.TIMING_NCAT)
                 if cnt[i]}
 
+    def measure_tmem_read(self) -> float:
+        """GB/s of tcgen05.ld over the whole chip."""
+        v = C.c_double(0.0)
+        self._ck(self._lib.pre3_measure_tmem_read(self._h, C.byref(v)))
+        return v.value
+
     def measure_fp64_peak(self) -> float:
         v = C.c_double(0.0)
         self._ck(self._lib.pre3_measure_fp64_peak(self._h, C.byref(v)))

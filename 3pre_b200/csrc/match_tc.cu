@@ -235,6 +235,12 @@ struct Barriers {
   uint32_t tmem_base;
 };
 
+// EXP selects an ablation of the pipeline (PRE3_TC_EXP in the environment, tools/match_bench.py; 0 = the product;
+// the others produce no usable proposal and only exist to time the halves of the kernel):
+//   1  TMA + MMA only: the epilogue waits for and releases the accumulators without reading them
+//   2  TMA + epilogue only: the issuer commits without issuing tcgen05.mma
+//   4  TMA only          5  MMA only (no B loads, no epilogue)
+template <int EXP>
 __global__ void __launch_bounds__(THREADS, 1)
 k_tc_gemm_top2(const unsigned char* __restrict__ imgA, const unsigned char* __restrict__ imgB,
                const float* __restrict__ nrmB, int P, int K1p, int K2p, Prop* __restrict__ prop) {
@@ -291,6 +297,7 @@ k_tc_gemm_top2(const unsigned char* __restrict__ imgA, const unsigned char* __re
         tma_bulk_g2s(sA + ab * A_BUF_BYTES, imgA + ((size_t)p * K1p + (size_t)g * 2 * BLK) * (ND * 2),
                      (uint32_t)(nrb * BLK_BYTES), smem_u32(&bars->a_full[ab]));
         for (int j = 0; j < ntile; ++j, ++t) {
+          if (EXP == 5) continue;
           const int st = (int)(t % NSTAGE);
           mbar_wait(smem_u32(&bars->b_empty[st]), (uint32_t)(((t / NSTAGE) & 1) ^ 1));
           mbar_expect_tx(smem_u32(&bars->b_full[st]), BLK_BYTES);
@@ -313,7 +320,7 @@ k_tc_gemm_top2(const unsigned char* __restrict__ imgA, const unsigned char* __re
         for (int j = 0; j < ntile; ++j, ++t) {
           const int st = (int)(t % NSTAGE);
           const int set = (int)(t & 1);
-          mbar_wait(smem_u32(&bars->b_full[st]), (uint32_t)((t / NSTAGE) & 1));
+          if (EXP != 5) mbar_wait(smem_u32(&bars->b_full[st]), (uint32_t)((t / NSTAGE) & 1));
           tc_fence_after();
           for (int rb = 0; rb < nrb; ++rb) {
             const int slot = set * 2 + rb;
@@ -327,11 +334,11 @@ k_tc_gemm_top2(const unsigned char* __restrict__ imgA, const unsigned char* __re
               const uint32_t koff = (uint32_t)((k >> 2) * HALF_BYTES + (k & 3) * 32);
               const uint64_t da = umma_desc(sA + ab * A_BUF_BYTES + rb * BLK_BYTES + koff);
               const uint64_t db = umma_desc(sB + st * BLK_BYTES + koff);
-              tc_mma_f16(d, da, db, IDESC, k > 0 ? 1u : 0u);
+              if (EXP != 2 && EXP != 4) tc_mma_f16(d, da, db, IDESC, k > 0 ? 1u : 0u);
             }
             tc_commit(smem_u32(&bars->t_full[slot]));  // accumulator ready for the epilogue
           }
-          tc_commit(smem_u32(&bars->b_empty[st]));  // B stage may be refilled
+          if (EXP != 5) tc_commit(smem_u32(&bars->b_empty[st]));  // B stage may be refilled
         }
         tc_commit(smem_u32(&bars->a_empty[ab]));  // A buffer may be refilled
       }
@@ -369,9 +376,10 @@ k_tc_gemm_top2(const unsigned char* __restrict__ imgA, const unsigned char* __re
         const uint32_t m1_in = m1;
         const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * BLK);
         uint32_t buf[2][32];
-        tc_ld_32x32(taddr, buf[0]);
+        if (EXP != 1 && EXP != 4 && EXP != 5) tc_ld_32x32(taddr, buf[0]);
 #pragma unroll
         for (int c = 0; c < BLK / 32; ++c) {
+          if (EXP == 1 || EXP == 4 || EXP == 5) break;
           tc_ld_wait(buf[c & 1]);
           if (c + 1 < BLK / 32) tc_ld_32x32(taddr + (uint32_t)((c + 1) * 32), buf[(c + 1) & 1]);
           const float4* nb4 = reinterpret_cast<const float4*>(snb + c * 32);
@@ -627,12 +635,26 @@ int launch_match_tc(pre3_ctx* ctx, const void* dL1, const void* dL2, int cls, in
     Span span__(ctx, T_MATCH_TC);
     static bool attr_set = false;
     if (!attr_set) {
-      PRE3_CUDA(cudaFuncSetAttribute(k_tc_gemm_top2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      PRE3_CUDA(cudaFuncSetAttribute(k_tc_gemm_top2<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      PRE3_CUDA(cudaFuncSetAttribute(k_tc_gemm_top2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      PRE3_CUDA(cudaFuncSetAttribute(k_tc_gemm_top2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      PRE3_CUDA(cudaFuncSetAttribute(k_tc_gemm_top2<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      PRE3_CUDA(cudaFuncSetAttribute(k_tc_gemm_top2<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
       attr_set = true;
     }
     const long long units = (long long)P * ((K1p / BLK + 1) / 2);
     const int grid = (int)std::min<long long>(units, ctx->sm_count);
-    k_tc_gemm_top2<<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(imgA, imgB, nrmB, P, K1p, K2p, prop);
+    static const int exp_mode = getenv("PRE3_TC_EXP") ? atoi(getenv("PRE3_TC_EXP")) : 0;
+    if (exp_mode == 1)
+      k_tc_gemm_top2<1><<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(imgA, imgB, nrmB, P, K1p, K2p, prop);
+    else if (exp_mode == 2)
+      k_tc_gemm_top2<2><<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(imgA, imgB, nrmB, P, K1p, K2p, prop);
+    else if (exp_mode == 4)
+      k_tc_gemm_top2<4><<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(imgA, imgB, nrmB, P, K1p, K2p, prop);
+    else if (exp_mode == 5)
+      k_tc_gemm_top2<5><<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(imgA, imgB, nrmB, P, K1p, K2p, prop);
+    else
+      k_tc_gemm_top2<0><<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(imgA, imgB, nrmB, P, K1p, K2p, prop);
     count_launch(ctx);
   }
   {

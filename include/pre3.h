@@ -300,6 +300,9 @@ PRE3_API int pre3_ransac_hypotheses_batch_dev(pre3_ctx *ctx, int Fr, int n, int 
                                      int32_t *dsupports);
 /* Wave boundaries of the hypothesis evaluation (like pre3_eval_schedule). */
 PRE3_API int pre3_ekf_eval_schedule(const pre3_ekf_opts *opts, int32_t *ends, int cap);
+/* tcgen05.ld sweep: measured TMEM -> register read rate (GB/s, whole chip), the bound of the matching GEMM's
+ * epilogue (every fp32 accumulator is read once: 4 B of TMEM per 2*128 flops). */
+PRE3_API int pre3_measure_tmem_read(pre3_ctx *ctx, double *gbs);
 /* DFMA-chain microbenchmark: measured FP64 CUDA-core peak (TFLOP/s), the roofline of the EKF kernels. */
 PRE3_API int pre3_measure_fp64_peak(pre3_ctx *ctx, double *tflops);
 
