@@ -551,6 +551,16 @@ def run_ours(args):
             a = desc_bytes * 1.25 / L / sec / 1e9  # read f64 descriptors + write the f16 operand image
             rooflines[name] = {"bound": "hbm", "achieved": a, "peak": pk["hbm_gbs"], "unit": "GB/s",
                                "frac": a / pk["hbm_gbs"], "traffic": None, "note": f"of {pk['source']}"}
+    # traffic: DRAM bytes per launch measured by ncu (profiles/r01_traffic.json: bytes per pair at the same
+    # per-pair shape), scaled to the pairs one launch processes here
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath):
+        tr = json.load(open(tpath))["per_pair_bytes"]
+        for name in rooflines:
+            if name in tr:
+                rooflines[name]["traffic"] = tr[name]["bytes"] * P * tr[name].get("launches_per_timed_span", 1)
+                rooflines[name]["traffic_note"] = "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch " \
+                                                  "(profiles/r01_f_kernels.csv, per pair) x pairs per launch"
     roofline = dict(rooflines.get(dom, {"bound": "hbm", "achieved": None, "peak": pk["hbm_gbs"], "unit": "GB/s",
                                         "frac": None, "traffic": None}))
     roofline["kernel"] = dom
