@@ -8,11 +8,12 @@
 //   k_ekf_index   per frame: IC list, measured-feature list, m (select_random_match.m:47-51).
 //   k_ekf_gain    G = P*H' for every individually compatible feature of the frame (n x 2 each):
 //                 P is streamed once (HBM bound); every hypothesis then gathers its 2m columns.
-//   k_ekf_score   one block per (frame, hypothesis).  Warp 0: S = Hi*P*Hi' + R from the P
-//                 sub-blocks, inv(S) by a cooperative Gauss-Jordan, innovation, the updated camera
-//                 states.  Then one thread per measured feature: the 6 (3) updated feature states
-//                 xi = x + K (zi - hi) in the reference's K-form, projection, distortion, residual;
-//                 block min (the `min(residuals) + threshold` rule, :70) and count.
+//   k_ekf_hyp     one warp per (frame, hypothesis): S = Hi*P*Hi' + R from the P sub-blocks, inv(S)
+//                 by a cooperative Gauss-Jordan, innovation, the updated camera states -> a 480-byte
+//                 record per hypothesis.
+//   k_ekf_score   one block per (frame, hypothesis), one thread per measured feature: the 6 (3)
+//                 updated feature states xi = x + K (zi - hi) in the reference's K-form, projection,
+//                 distortion, residual; block min (the `min(residuals) + threshold` rule, :70) and count.
 //   k_ekf_stop / k_ekf_pick  the reference's sequential loop control (:40-46,:74-80) replayed
 //                 over the supports (hypotheses are evaluated in waves; frames whose loop has
 //                 ended skip the later waves), first-maximum selection.
