@@ -329,10 +329,12 @@ def test_pairs_chunked_host_path_equals_device_path(ctx, synth, pre3):
 # ------------------------------------------------------------------------------------------
 # full-size properties (configs 2, 3, 5 shapes) -- no oracle at these sizes
 # ------------------------------------------------------------------------------------------
-def test_pairs_host_narrowing_is_lossless_and_falls_back(ctx, synth, pre3):
+def test_pairs_host_narrowing_is_lossless_and_falls_back(synth, pre3, monkeypatch):
     """Host path: float-exact double descriptors cross PCIe as float (half the bytes), others as double;
     either way the results equal the device path bit for bit."""
     import torch
+    monkeypatch.setenv("PRE3_HOST_F32", "1")  # the default depends on the host's core count per rank
+    ctx = pre3.Context(0)
     P, K = 6, 256
     b = synth.make_batch_torch(P, 910, "cuda", K1=K, K2=K, n_corr=150)
     opts = pre3.make_opts(H=500, seed=3)
@@ -355,6 +357,7 @@ def test_pairs_host_narrowing_is_lossless_and_falls_back(ctx, synth, pre3):
             np.testing.assert_array_equal(hm[p, :n], md[p, :n])
         desc_bytes = 2 * P * K * 128 * 8
         assert moved < 0.6 * desc_bytes if exact else moved > desc_bytes
+    ctx.close()
 
 
 def test_matching_full_size_properties(ctx, synth):
