@@ -522,14 +522,16 @@ int pre3_pairs_dev(pre3_ctx* ctx, const void* ddesc1, const void* ddesc2, int cl
 // round trip (hostconv.cpp): half the PCIe bytes, same arithmetic on the device.
 static int ensure_host_stage(pre3_ctx* ctx, size_t bytes_per_slot) {
   if (ctx->host_f32 < 0) {
-    // The pool needs the host's cores: with several ranks on one host (LOCAL_WORLD_SIZE, set by torchrun) each
-    // GPU has its own PCIe link but the ranks share the cores, and sending doubles is faster than narrowing
-    // them with a quarter of the machine.  PRE3_HOST_F32=0/1 overrides.
+    // Narrowing trades host memory traffic (read 8 B + write 4 B + DMA 4 B per value instead of DMA 8 B) for PCIe
+    // bytes: it pays while ONE link is the bottleneck (measured on a 16-core host: 50 k -> 63 k pairs/s).  With
+    // several ranks on one host (LOCAL_WORLD_SIZE, set by torchrun) every GPU has its own link and the shared host
+    // memory becomes the limit (measured at 2 ranks: 89 k pairs/s narrowed vs 2 x 50 k raw), so it is switched off.
+    // PRE3_HOST_F32=0/1 overrides.
     const char* e = getenv("PRE3_HOST_F32");
     const char* lws = getenv("LOCAL_WORLD_SIZE");
     const unsigned ranks = lws && atoi(lws) > 0 ? (unsigned)atoi(lws) : 1u;
-    const unsigned hw = std::thread::hardware_concurrency() / ranks;
-    ctx->host_f32 = e ? (atoi(e) != 0) : (hw >= 12);
+    const unsigned hw = std::thread::hardware_concurrency();
+    ctx->host_f32 = e ? (atoi(e) != 0) : (ranks == 1 && hw >= 8);
     if (ctx->host_f32) ctx->pool = host_pool_create((int)std::min<unsigned>(hw > 1 ? hw - 1 : 1, 15));
   }
   if (!ctx->host_f32) return PRE3_OK;

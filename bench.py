@@ -623,8 +623,10 @@ def run_ours(args):
                        else "exact fp64 brute force"},
             "e2e": {"value": e2e_val, "unit": "frame-pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "pairs_per_step": Pe, "steps": e2e_steps, "host_input_bytes_per_step": host_in,
-                    "note": "pre3_pairs on pinned host buffers (class double); descriptors whose values survive "
-                            "(double)(float)x == x are narrowed by a host thread pool and cross PCIe as float"},
+                    "note": "pre3_pairs on pinned host buffers (class double). With one rank per host, descriptors whose "
+                            "values survive (double)(float)x == x are narrowed by a host thread pool and cross PCIe as "
+                            "float (h2d_bytes_per_step < host_input_bytes_per_step); with several ranks per host they "
+                            "cross as doubles (every GPU has its own link, the host memory is shared)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline,
