@@ -37,7 +37,11 @@ constexpr int BLK_BYTES = BLK * ND * 2;       // 32 KB: [khalf 2][row 128][128 B
 constexpr int HALF_BYTES = BLK * 128;         // 16 KB
 constexpr int A_BUF_BYTES = 2 * BLK_BYTES;    // two row blocks
 constexpr int NSTAGE = 3;                     // B ring
-constexpr int THREADS = 384;                  // 12 warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-7 / 8-11 epilogue
+constexpr int THREADS = 352;                  // 11 warps: 0-3 / 4-7 epilogue, 8 TMA, 9 MMA, 10 TMEM alloc
+// The issuing warps carry the HIGHEST warp ids of their SM sub-partitions (warp id mod 4): the scheduler serves the
+// highest ready warp id first, so the single-thread TMA / MMA issuers are not starved by the compute-heavy
+// epilogue warps they share a sub-partition with.
+constexpr int W_EPI0 = 0, W_TMA = 8, W_MMA = 9, W_ALLOC = 10;
 constexpr int SMEM_BYTES = 2 * A_BUF_BYTES + NSTAGE * BLK_BYTES + 256 /*barriers*/ + 4 * BLK * 4 /*norms*/;
 
 // The epilogue orders  v'(j) = |b_j|^2 + C - 2 a~.b~_j  (C = 1.0625 max_i |a_i|^2 of the pair keeps v' > 0, so
@@ -258,7 +262,7 @@ k_tc_gemm_top2(const unsigned char* __restrict__ imgA, const unsigned char* __re
   const int ntile = K2p / BLK;             // B tiles per pair
   const long long nunits = (long long)P * groups;
 
-  if (warp == 1 && lane == 0) {
+  if (warp == W_MMA && lane == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&bars->a_full[i]), 1);
       mbar_init(smem_u32(&bars->a_empty[i]), 1);
@@ -273,7 +277,7 @@ k_tc_gemm_top2(const unsigned char* __restrict__ imgA, const unsigned char* __re
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 2) {
+  if (warp == W_ALLOC) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&bars->tmem_base))
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -283,7 +287,7 @@ k_tc_gemm_top2(const unsigned char* __restrict__ imgA, const unsigned char* __re
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
 
-  if (warp == 0) {
+  if (warp == W_TMA) {
     // ===== TMA producer ========================================================================
     if (lane == 0) {
       long long t = 0;  // B tiles issued so far
@@ -306,7 +310,7 @@ k_tc_gemm_top2(const unsigned char* __restrict__ imgA, const unsigned char* __re
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == W_MMA) {
     // ===== MMA issuer (one thread) =============================================================
     if (lane == 0) {
       long long t = 0;
@@ -343,9 +347,9 @@ k_tc_gemm_top2(const unsigned char* __restrict__ imgA, const unsigned char* __re
         tc_commit(smem_u32(&bars->a_empty[ab]));  // A buffer may be refilled
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp < W_TMA) {
     // ===== epilogue: warpgroup rb owns row block rb ============================================
-    const int rb = (warp - 4) >> 2;
+    const int rb = (warp - W_EPI0) >> 2;
     const int q = warp & 3;  // TMEM lane quarter this warp may read
     long long t = 0;
     uint32_t useA = 0, useB = 0;  // times this warpgroup has drained its slot of set 0 / set 1
@@ -361,13 +365,17 @@ k_tc_gemm_top2(const unsigned char* __restrict__ imgA, const unsigned char* __re
       asm volatile("mov.u32 %0, 0xFFFFFF80;" : "=r"(keymask));
       int btile = -1;
       const float* nb = nrmB + (size_t)p * K2p;
-      const int wtid = threadIdx.x - (4 + 4 * rb) * 32;  // 0..127 within the warpgroup
+      const int wtid = threadIdx.x - (W_EPI0 + 4 * rb) * 32;  // 0..127 within the warpgroup
+      // the column norm of the NEXT tile is fetched one tile ahead: its global-load latency (exposed, it cost a
+      // quarter of the epilogue's time) hides behind the current tile's selection
+      float nb_next = __ldg(nb + wtid);
       for (int j = 0; j < ntile; ++j, ++t) {
         const int set = (int)(t & 1);
         const int slot = set * 2 + rb;
-        // stage the tile's (biased) column norms for broadcast reads; the global load overlaps the MMA
+        // stage the tile's (biased) column norms for broadcast reads
         float* snb = sNB + (rb * 2 + set) * BLK;
-        snb[wtid] = __ldg(nb + (size_t)j * BLK + wtid);
+        snb[wtid] = nb_next;
+        if (j + 1 < ntile) nb_next = __ldg(nb + (size_t)(j + 1) * BLK + wtid);
         named_bar_sync(1 + rb, 128);
         uint32_t& use = set == 0 ? useA : useB;
         mbar_wait(smem_u32(&bars->t_full[slot]), use & 1);
@@ -413,7 +421,7 @@ k_tc_gemm_top2(const unsigned char* __restrict__ imgA, const unsigned char* __re
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == W_ALLOC) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
   }
@@ -633,28 +641,27 @@ int launch_match_tc(pre3_ctx* ctx, const void* dL1, const void* dL2, int cls, in
   }
   {
     Span span__(ctx, T_MATCH_TC);
-    static bool attr_set = false;
-    if (!attr_set) {
-      PRE3_CUDA(cudaFuncSetAttribute(k_tc_gemm_top2<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-      PRE3_CUDA(cudaFuncSetAttribute(k_tc_gemm_top2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-      PRE3_CUDA(cudaFuncSetAttribute(k_tc_gemm_top2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-      PRE3_CUDA(cudaFuncSetAttribute(k_tc_gemm_top2<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-      PRE3_CUDA(cudaFuncSetAttribute(k_tc_gemm_top2<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-      attr_set = true;
-    }
     const long long units = (long long)P * ((K1p / BLK + 1) / 2);
     const int grid = (int)std::min<long long>(units, ctx->sm_count);
     static const int exp_mode = getenv("PRE3_TC_EXP") ? atoi(getenv("PRE3_TC_EXP")) : 0;
-    if (exp_mode == 1)
-      k_tc_gemm_top2<1><<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(imgA, imgB, nrmB, P, K1p, K2p, prop);
-    else if (exp_mode == 2)
-      k_tc_gemm_top2<2><<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(imgA, imgB, nrmB, P, K1p, K2p, prop);
-    else if (exp_mode == 4)
-      k_tc_gemm_top2<4><<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(imgA, imgB, nrmB, P, K1p, K2p, prop);
-    else if (exp_mode == 5)
-      k_tc_gemm_top2<5><<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(imgA, imgB, nrmB, P, K1p, K2p, prop);
-    else
-      k_tc_gemm_top2<0><<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(imgA, imgB, nrmB, P, K1p, K2p, prop);
+#define PRE3_GEMM(E)                                                                                             \
+  do {                                                                                                           \
+    static bool attr_done = false;                                                                               \
+    if (!attr_done) {                                                                                            \
+      PRE3_CUDA(cudaFuncSetAttribute(k_tc_gemm_top2<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); \
+      attr_done = true;                                                                                          \
+    }                                                                                                            \
+    k_tc_gemm_top2<E><<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(imgA, imgB, nrmB, P, K1p, K2p, prop);           \
+  } while (0)
+    switch (exp_mode) {
+      case 0: PRE3_GEMM(0); break;
+      case 1: PRE3_GEMM(1); break;
+      case 2: PRE3_GEMM(2); break;
+      case 4: PRE3_GEMM(4); break;
+      case 5: PRE3_GEMM(5); break;
+      default: return fail(ctx, PRE3_ERR_ARG, "PRE3_TC_EXP: ablation not built");
+    }
+#undef PRE3_GEMM
     count_launch(ctx);
   }
   {
