@@ -109,6 +109,18 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uin
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// A operand in tensor memory (ablation only)
+__device__ __forceinline__ void tc_mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // 32 lanes x 32 consecutive columns of 32-bit accumulators -> 32 registers per thread (asynchronous:
 // the registers are valid after tc_ld_wait on them)
 __device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -244,6 +256,7 @@ struct Barriers {
 //   1  TMA + MMA only: the epilogue waits for and releases the accumulators without reading them
 //   2  TMA + epilogue only: the issuer commits without issuing tcgen05.mma
 //   4  TMA only          5  MMA only (no B loads, no epilogue)
+//   6  MMA only, N = 256 per instruction (half as many)      7  MMA only, A operand read from tensor memory
 template <int EXP>
 __global__ void __launch_bounds__(THREADS, 1)
 k_tc_gemm_top2(const unsigned char* __restrict__ imgA, const unsigned char* __restrict__ imgB,
@@ -301,7 +314,7 @@ k_tc_gemm_top2(const unsigned char* __restrict__ imgA, const unsigned char* __re
         tma_bulk_g2s(sA + ab * A_BUF_BYTES, imgA + ((size_t)p * K1p + (size_t)g * 2 * BLK) * (ND * 2),
                      (uint32_t)(nrb * BLK_BYTES), smem_u32(&bars->a_full[ab]));
         for (int j = 0; j < ntile; ++j, ++t) {
-          if (EXP == 5) continue;
+          if (EXP >= 5) continue;
           const int st = (int)(t % NSTAGE);
           mbar_wait(smem_u32(&bars->b_empty[st]), (uint32_t)(((t / NSTAGE) & 1) ^ 1));
           mbar_expect_tx(smem_u32(&bars->b_full[st]), BLK_BYTES);
@@ -324,7 +337,7 @@ k_tc_gemm_top2(const unsigned char* __restrict__ imgA, const unsigned char* __re
         for (int j = 0; j < ntile; ++j, ++t) {
           const int st = (int)(t % NSTAGE);
           const int set = (int)(t & 1);
-          if (EXP != 5) mbar_wait(smem_u32(&bars->b_full[st]), (uint32_t)((t / NSTAGE) & 1));
+          if (EXP < 5) mbar_wait(smem_u32(&bars->b_full[st]), (uint32_t)((t / NSTAGE) & 1));
           tc_fence_after();
           for (int rb = 0; rb < nrb; ++rb) {
             const int slot = set * 2 + rb;
@@ -338,11 +351,19 @@ k_tc_gemm_top2(const unsigned char* __restrict__ imgA, const unsigned char* __re
               const uint32_t koff = (uint32_t)((k >> 2) * HALF_BYTES + (k & 3) * 32);
               const uint64_t da = umma_desc(sA + ab * A_BUF_BYTES + rb * BLK_BYTES + koff);
               const uint64_t db = umma_desc(sB + st * BLK_BYTES + koff);
-              if (EXP != 2 && EXP != 4) tc_mma_f16(d, da, db, IDESC, k > 0 ? 1u : 0u);
+              if (EXP == 6) {  // timing only: one N = 256 instruction per two tiles (operands are garbage)
+                if ((t & 1) == 0)
+                  tc_mma_f16(tmem + (uint32_t)(rb * 2 * BLK), da, umma_desc(sB + koff),
+                             (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(BLK >> 4) << 24), k > 0 ? 1u : 0u);
+              } else if (EXP == 7) {
+                tc_mma_f16_ts(d, tmem + (uint32_t)(448 + k * 8), db, IDESC, k > 0 ? 1u : 0u);
+              } else if (EXP != 2 && EXP != 4) {
+                tc_mma_f16(d, da, db, IDESC, k > 0 ? 1u : 0u);
+              }
             }
             tc_commit(smem_u32(&bars->t_full[slot]));  // accumulator ready for the epilogue
           }
-          if (EXP != 5) tc_commit(smem_u32(&bars->b_empty[st]));  // B stage may be refilled
+          if (EXP < 5) tc_commit(smem_u32(&bars->b_empty[st]));  // B stage may be refilled
         }
         tc_commit(smem_u32(&bars->a_empty[ab]));  // A buffer may be refilled
       }
@@ -384,10 +405,10 @@ k_tc_gemm_top2(const unsigned char* __restrict__ imgA, const unsigned char* __re
         const uint32_t m1_in = m1;
         const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * BLK);
         uint32_t buf[2][32];
-        if (EXP != 1 && EXP != 4 && EXP != 5) tc_ld_32x32(taddr, buf[0]);
+        if (EXP != 1 && EXP < 4) tc_ld_32x32(taddr, buf[0]);
 #pragma unroll
         for (int c = 0; c < BLK / 32; ++c) {
-          if (EXP == 1 || EXP == 4 || EXP == 5) break;
+          if (EXP == 1 || EXP >= 4) break;
           tc_ld_wait(buf[c & 1]);
           if (c + 1 < BLK / 32) tc_ld_32x32(taddr + (uint32_t)((c + 1) * 32), buf[(c + 1) & 1]);
           const float4* nb4 = reinterpret_cast<const float4*>(snb + c * 32);
@@ -659,6 +680,8 @@ int launch_match_tc(pre3_ctx* ctx, const void* dL1, const void* dL2, int cls, in
       case 2: PRE3_GEMM(2); break;
       case 4: PRE3_GEMM(4); break;
       case 5: PRE3_GEMM(5); break;
+      case 6: PRE3_GEMM(6); break;
+      case 7: PRE3_GEMM(7); break;
       default: return fail(ctx, PRE3_ERR_ARG, "PRE3_TC_EXP: ablation not built");
     }
 #undef PRE3_GEMM
