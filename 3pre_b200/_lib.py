@@ -101,6 +101,8 @@ SYMBOLS = {
     "pre3_ransac_batch_dev": (_I, [_VP, _VP, _VP, _VP, _I, _I, _OPTS, _VP, _VP, _VP]),
     "pre3_pairs": (_I, [_VP, _VP, _VP, _I, _VP, _VP, _I, _I, _I, _I, _VP, _VP, _OPTS, _U32, _VP, _VP, _VP]),
     "pre3_pairs_dev": (_I, [_VP, _VP, _VP, _I, _VP, _VP, _I, _I, _I, _I, _VP, _VP, _OPTS, _U32, _VP, _VP, _VP]),
+    "pre3_sequence": (_I, [_VP, _VP, _I, _VP, _I, _I, _I, _VP, _OPTS, _U32, _VP, _VP, _VP]),
+    "pre3_sequence_dev": (_I, [_VP, _VP, _I, _VP, _I, _I, _I, _VP, _OPTS, _U32, _VP, _VP, _VP]),
     "pre3_ransac_block_dev": (_I, [_VP, _VP, _VP, _I, _OPTS, _VP, _I64, _I, _D, _VP, _VP]),
     "pre3_ransac_block_select_dev": (_I, [_VP, _VP, _VP, _I, _OPTS, _VP, _I64, _I, _D, _VP, _VP]),
     "pre3_ransac_finish_dev": (_I, [_VP, _VP, _VP, _I, _OPTS, _VP, _I64, _D, _VP, _VP]),

@@ -363,6 +363,40 @@ class Context:
                                       _ptr(masks)))
         return res[:P], (matches[:P] if matches is not None else None), (masks[:P] if masks is not None else None)
 
+    def sequence(self, desc, xyz, opts: RansacOpts | None = None, pair_id0=0, k_count=None, want_matches=True,
+                 want_masks=True, out=None, **kw):
+        """F consecutive frames -> F-1 pairs (frame p, frame p+1).  desc (F,K,128), xyz (F,K,3) host arrays.
+        Same returns as pairs() with F-1 entries."""
+        d = _c(desc)
+        if d.dtype not in _CLS:
+            raise ValueError("Unsupported numeric class")
+        x = _c(xyz, np.float64)
+        F, K, ND = d.shape
+        P = max(F - 1, 0)
+        o = opts or make_opts(**kw)
+        kc = None if k_count is None else _c(k_count, np.int32)
+        if out is not None:
+            res, matches, masks = out
+        else:
+            res = np.zeros(max(P, 1), RESULT_DTYPE)
+            matches = np.zeros((max(P, 1), max(K, 1), 2), np.int32) if want_matches else None
+            masks = np.zeros((max(P, 1), max(K, 1)), np.uint8) if want_masks else None
+        self._ck(self._lib.pre3_sequence(self._h, _ptr(d), _CLS[d.dtype], _ptr(x), F, K, ND, _ptr(kc), C.byref(o),
+                                         int(pair_id0), _ptr(res), _ptr(matches), _ptr(masks)))
+        return res[:P], (matches[:P] if matches is not None else None), (masks[:P] if masks is not None else None)
+
+    def sequence_dev(self, desc, xyz, opts: RansacOpts, res, matches=None, masks=None, pair_id0=0, k_count=None):
+        """CUDA tensors: desc (F,K,128), xyz (F,K,3) f64; res uint8 (F-1,240); matches int32 (F-1,K,2) | None;
+        masks uint8 (F-1,K) | None."""
+        import torch
+        cls = {torch.float64: L.CLASS_DOUBLE, torch.float32: L.CLASS_SINGLE, torch.int8: L.CLASS_INT8,
+               torch.uint8: L.CLASS_UINT8}[desc.dtype]
+        F, K, ND = desc.shape
+        for t in (desc, xyz, res):
+            assert t.is_cuda and t.is_contiguous()
+        self._ck(self._lib.pre3_sequence_dev(self._h, _ptr(desc), cls, _ptr(xyz), F, K, ND, _ptr(k_count),
+                                             C.byref(opts), int(pair_id0), _ptr(res), _ptr(matches), _ptr(masks)))
+
     # ---- config 4: 1-point-RANSAC EKF hypotheses -------------------------------------------
     def ekf_support(self, xi, cam, pattern, z_id, z_euc, threshold):
         """compute_hypothesis_support_fast.m:27-116 for B states.  xi (B,n) [= n x B column-major];

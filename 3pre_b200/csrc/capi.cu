@@ -65,10 +65,16 @@ int match_impl(pre3_ctx* ctx, const void* dL1, const void* dL2, int cls, int P, 
   if (ctx->match_engine != PRE3_MATCH_EXACT) tc = match_tc_supported(cls, K1, K2, ND);
   if (ctx->match_engine == PRE3_MATCH_TC && !tc)
     return fail(ctx, PRE3_ERR_ARG, "tensor-core matcher needs class double/single and ND == 128");
-  if (tc)
+  if (tc) {
     PRE3_TRY(launch_match_tc(ctx, dL1, dL2, cls, P, K1, K2, ND, dk1, dk2, th, need_score, rows));
-  else
+  } else {
+    if (!dL2) {  // sequence mode: pair p = (set p, set p + 1) of dL1
+      const size_t esz = cls == PRE3_CLASS_DOUBLE_F32 ? 4 : class_size(cls);
+      dL2 = (const char*)dL1 + (size_t)K1 * ND * esz;
+      if (dk1) dk2 = dk1 + 1;
+    }
     PRE3_TRY(launch_match_exact(ctx, dL1, dL2, cls, P, K1, K2, ND, dk1, dk2, th, rows));
+  }
   *rows_out = rows;
   return PRE3_OK;
 }
@@ -493,6 +499,10 @@ static int pairs_impl(pre3_ctx* ctx, const void* ddesc1, const void* ddesc2, int
                       uint8_t* dmasks) {
   MatchRow* rows = nullptr;
   if (K1 > 0) PRE3_TRY(match_impl(ctx, ddesc1, ddesc2, cls, P, K1, K2, ND, dk1, dk2, o.ratio, 0, &rows));
+  if (!ddesc2) {  // sequence mode: frame p + 1 is the "current" frame of pair p
+    dxyz2 = dxyz1 + 3 * (size_t)K1;
+    if (dk1) dk2 = dk1 + 1;
+  }
   double* dYa = ws_take<double>(ctx, 3 * (size_t)P * K1);
   double* dYb = ws_take<double>(ctx, 3 * (size_t)P * K1);
   int32_t* dn = ws_take<int32_t>(ctx, P);
@@ -512,6 +522,22 @@ int pre3_pairs_dev(pre3_ctx* ctx, const void* ddesc1, const void* ddesc2, int cl
   if (P == 0) return PRE3_OK;
   PRE3_TRY(ws_reserve(ctx, pairs_ws_bytes(cls, P, K1, K2, ND, opts->H)));
   return pairs_impl(ctx, ddesc1, ddesc2, cls, dxyz1, dxyz2, P, K1, K2, ND, dk1_count, dk2_count, *opts, pair_id0, dres,
+                    dmatches, dmasks);
+}
+
+// A SEQUENCE of F frames = F - 1 consecutive pairs (frame p, frame p + 1): what the reference's whole-sequence
+// loops run (find_consistent_sift_matches.m:22-32: RANSAC_CALC_SAVE_SR4000(i, i+1) for every i).  Every frame's
+// descriptors are converted once instead of twice.
+int pre3_sequence_dev(pre3_ctx* ctx, const void* ddesc, int cls, const double* dxyz, int F, int K, int ND,
+                      const int32_t* dk_count, const pre3_ransac_opts* opts, uint32_t pair_id0, pre3_pair_result* dres,
+                      int32_t* dmatches, uint8_t* dmasks) {
+  PRE3_LIVE();
+  PRE3_TRY(check_match_args(ctx, ddesc, ddesc, cls, F, K, K, ND));
+  PRE3_TRY(check_opts(ctx, opts));
+  PRE3_NEED(F <= 1 || (dres && dxyz), "null pointer");
+  if (F <= 1) return PRE3_OK;
+  PRE3_TRY(ws_reserve(ctx, pairs_ws_bytes(cls, F, K, K, ND, opts->H)));
+  return pairs_impl(ctx, ddesc, nullptr, cls, dxyz, nullptr, F - 1, K, K, ND, dk_count, nullptr, *opts, pair_id0, dres,
                     dmatches, dmasks);
 }
 
@@ -550,15 +576,18 @@ static int ensure_host_stage(pre3_ctx* ctx, size_t bytes_per_slot) {
   return PRE3_OK;
 }
 
-int pre3_pairs(pre3_ctx* ctx, const void* desc1, const void* desc2, int cls, const double* xyz1, const double* xyz2,
-               int P, int K1, int K2, int ND, const int32_t* k1_count, const int32_t* k2_count,
-               const pre3_ransac_opts* opts, uint32_t pair_id0, pre3_pair_result* res, int32_t* matches,
-               uint8_t* masks) {
+// seq: desc1 / xyz1 / k1_count hold P + 1 frames, pair p = (frame p, frame p + 1); desc2 / xyz2 / k2_count unused.
+// A chunk of n pairs then stages n + 1 frames (the boundary frame is sent twice, once per chunk).
+static int pairs_host(pre3_ctx* ctx, const void* desc1, const void* desc2, int cls, const double* xyz1,
+                      const double* xyz2, int P, int K1, int K2, int ND, const int32_t* k1_count,
+                      const int32_t* k2_count, const pre3_ransac_opts* opts, uint32_t pair_id0, pre3_pair_result* res,
+                      int32_t* matches, uint8_t* masks, bool seq) {
   PRE3_LIVE();
-  PRE3_TRY(check_match_args(ctx, desc1, desc2, cls, P, K1, K2, ND));
+  PRE3_TRY(check_match_args(ctx, desc1, seq ? desc1 : desc2, cls, P, K1, K2, ND));
   PRE3_TRY(check_opts(ctx, opts));
-  PRE3_NEED(res && xyz1 && xyz2, "null pointer");
+  PRE3_NEED(res && xyz1 && (seq || xyz2), "null pointer");
   if (P == 0) return PRE3_OK;
+  const int X = seq ? 1 : 0;  // extra frame per chunk on the "1" side
   const size_t es = class_size(cls);
   const size_t pb1 = (size_t)K1 * ND * es, pb2 = (size_t)K2 * ND * es;  // per pair
   const size_t per_pair_in = pb1 + pb2 + 24 * ((size_t)K1 + K2) + 8;
@@ -574,8 +603,8 @@ int pre3_pairs(pre3_ctx* ctx, const void* desc1, const void* desc2, int cls, con
     int32_t* m;
     uint8_t* msk;
   } slot[2];
-  const size_t slot_bytes = align_up(pb1 * C) + align_up(pb2 * C) + align_up(24 * (size_t)K1 * C) +
-                            align_up(24 * (size_t)K2 * C) + 2 * align_up(4 * (size_t)C) +
+  const size_t slot_bytes = align_up(pb1 * (C + 1)) + align_up(pb2 * C) + align_up(24 * (size_t)K1 * (C + 1)) +
+                            align_up(24 * (size_t)K2 * C) + 2 * align_up(4 * (size_t)(C + 1)) +
                             align_up(sizeof(pre3_pair_result) * (size_t)C) + align_up(8 * (size_t)K1 * C) +
                             align_up((size_t)K1 * C) + 4096;
   PRE3_TRY(aux_reserve(ctx, 0, 2 * slot_bytes));
@@ -587,22 +616,22 @@ int pre3_pairs(pre3_ctx* ctx, const void* desc1, const void* desc2, int cls, con
       off += align_up(bytes);
       return p;
     };
-    slot[s].d1 = take(pb1 * C);
+    slot[s].d1 = take(pb1 * (C + 1));
     slot[s].d2 = take(pb2 * C);
-    slot[s].x1 = (double*)take(24 * (size_t)K1 * C);
+    slot[s].x1 = (double*)take(24 * (size_t)K1 * (C + 1));
     slot[s].x2 = (double*)take(24 * (size_t)K2 * C);
-    slot[s].k1 = (int32_t*)take(4 * (size_t)C);
-    slot[s].k2 = (int32_t*)take(4 * (size_t)C);
+    slot[s].k1 = (int32_t*)take(4 * (size_t)(C + 1));
+    slot[s].k2 = (int32_t*)take(4 * (size_t)(C + 1));
     slot[s].r = (pre3_pair_result*)take(sizeof(pre3_pair_result) * (size_t)C);
     slot[s].m = (int32_t*)take(8 * (size_t)K1 * C);
     slot[s].msk = (uint8_t*)take((size_t)K1 * C);
   }
   PRE3_TRY(ensure_copy_stream(ctx));
-  PRE3_TRY(ws_reserve(ctx, pairs_ws_bytes(cls, C, K1, K2, ND, opts->H)));
+  PRE3_TRY(ws_reserve(ctx, pairs_ws_bytes(cls, C + 1, K1, K2, ND, opts->H)));
   const size_t n1 = (size_t)K1 * ND, n2 = (size_t)K2 * ND;  // descriptor values per pair
   bool narrow = cls == PRE3_CLASS_DOUBLE && ND > 0;
   if (narrow) {
-    PRE3_TRY(ensure_host_stage(ctx, 4 * (n1 + n2) * (size_t)C));
+    PRE3_TRY(ensure_host_stage(ctx, 4 * (n1 + n2) * (size_t)(C + 1)));
     narrow = ctx->host_f32 == 1;
   }
   // results come back through pinned staging: a device->host copy into pageable user memory would block
@@ -639,31 +668,35 @@ int pre3_pairs(pre3_ctx* ctx, const void* desc1, const void* desc2, int cls, con
       if (c >= 2) PRE3_CUDA(cudaEventSynchronize(ctx->ev_stage_done[s]));
       const double tb = now();
       float* f1 = (float*)ctx->h_stage[s];
-      float* f2 = f1 + n1 * (size_t)C;
-      as_f32 = host_narrow(ctx->pool, (const double*)desc1 + (size_t)p0 * n1, f1, n1 * n) &&
-               host_narrow(ctx->pool, (const double*)desc2 + (size_t)p0 * n2, f2, n2 * n);
+      float* f2 = f1 + n1 * (size_t)(C + 1);
+      as_f32 = host_narrow(ctx->pool, (const double*)desc1 + (size_t)p0 * n1, f1, n1 * (n + X)) &&
+               (seq || host_narrow(ctx->pool, (const double*)desc2 + (size_t)p0 * n2, f2, n2 * n));
       t_wait += tb - ta;
       t_conv += now() - tb;
     }
     chunk_cls[s] = as_f32 ? PRE3_CLASS_DOUBLE_F32 : cls;
-    ctx->h2d_bytes += (int64_t)((as_f32 ? 4 * (n1 + n2) : pb1 + pb2) * n + 24 * ((size_t)K1 + K2) * n +
-                                (k1_count ? 4 * (size_t)n : 0) + (k2_count ? 4 * (size_t)n : 0));
+    ctx->h2d_bytes += (int64_t)((as_f32 ? 4 * n1 : pb1) * (n + X) + (seq ? 0 : (as_f32 ? 4 * n2 : pb2) * n) +
+                                24 * (size_t)K1 * (n + X) + (seq ? 0 : 24 * (size_t)K2 * n) +
+                                (k1_count ? 4 * (size_t)(n + X) : 0) + (!seq && k2_count ? 4 * (size_t)n : 0));
     // the device slot may still be read by the compute of chunk c-2 / written back by its D2H
     PRE3_CUDA(cudaStreamWaitEvent(cs, ctx->ev_slot_free[s], 0));
     if (as_f32) {
       const float* f1 = (const float*)ctx->h_stage[s];
-      PRE3_CUDA(cudaMemcpyAsync(slot[s].d1, f1, 4 * n1 * n, cudaMemcpyHostToDevice, cs));
-      PRE3_CUDA(cudaMemcpyAsync(slot[s].d2, f1 + n1 * (size_t)C, 4 * n2 * n, cudaMemcpyHostToDevice, cs));
+      PRE3_CUDA(cudaMemcpyAsync(slot[s].d1, f1, 4 * n1 * (n + X), cudaMemcpyHostToDevice, cs));
+      if (!seq)
+        PRE3_CUDA(cudaMemcpyAsync(slot[s].d2, f1 + n1 * (size_t)(C + 1), 4 * n2 * n, cudaMemcpyHostToDevice, cs));
       PRE3_CUDA(cudaEventRecord(ctx->ev_stage_done[s], cs));
     } else {
-      PRE3_CUDA(cudaMemcpyAsync(slot[s].d1, (const char*)desc1 + (size_t)p0 * pb1, pb1 * n, cudaMemcpyHostToDevice, cs));
-      PRE3_CUDA(cudaMemcpyAsync(slot[s].d2, (const char*)desc2 + (size_t)p0 * pb2, pb2 * n, cudaMemcpyHostToDevice, cs));
+      PRE3_CUDA(cudaMemcpyAsync(slot[s].d1, (const char*)desc1 + (size_t)p0 * pb1, pb1 * (n + X), cudaMemcpyHostToDevice, cs));
+      if (!seq)
+        PRE3_CUDA(cudaMemcpyAsync(slot[s].d2, (const char*)desc2 + (size_t)p0 * pb2, pb2 * n, cudaMemcpyHostToDevice, cs));
       if (narrow) PRE3_CUDA(cudaEventRecord(ctx->ev_stage_done[s], cs));  // keeps the slot's event current
     }
-    PRE3_CUDA(cudaMemcpyAsync(slot[s].x1, xyz1 + 3 * (size_t)p0 * K1, 24 * (size_t)K1 * n, cudaMemcpyHostToDevice, cs));
-    PRE3_CUDA(cudaMemcpyAsync(slot[s].x2, xyz2 + 3 * (size_t)p0 * K2, 24 * (size_t)K2 * n, cudaMemcpyHostToDevice, cs));
-    if (k1_count) PRE3_CUDA(cudaMemcpyAsync(slot[s].k1, k1_count + p0, 4 * (size_t)n, cudaMemcpyHostToDevice, cs));
-    if (k2_count) PRE3_CUDA(cudaMemcpyAsync(slot[s].k2, k2_count + p0, 4 * (size_t)n, cudaMemcpyHostToDevice, cs));
+    PRE3_CUDA(cudaMemcpyAsync(slot[s].x1, xyz1 + 3 * (size_t)p0 * K1, 24 * (size_t)K1 * (n + X), cudaMemcpyHostToDevice, cs));
+    if (!seq)
+      PRE3_CUDA(cudaMemcpyAsync(slot[s].x2, xyz2 + 3 * (size_t)p0 * K2, 24 * (size_t)K2 * n, cudaMemcpyHostToDevice, cs));
+    if (k1_count) PRE3_CUDA(cudaMemcpyAsync(slot[s].k1, k1_count + p0, 4 * (size_t)(n + X), cudaMemcpyHostToDevice, cs));
+    if (!seq && k2_count) PRE3_CUDA(cudaMemcpyAsync(slot[s].k2, k2_count + p0, 4 * (size_t)n, cudaMemcpyHostToDevice, cs));
     PRE3_CUDA(cudaEventRecord(ctx->ev_slot_full[s], cs));
     return PRE3_OK;
   };
@@ -679,8 +712,8 @@ int pre3_pairs(pre3_ctx* ctx, const void* desc1, const void* desc2, int cls, con
     const double tq0 = now();
     PRE3_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_slot_full[s], 0));
     ctx->ws_off = 0;  // arena reused by every chunk (stream order keeps it safe)
-    PRE3_TRY(pairs_impl(ctx, slot[s].d1, slot[s].d2, chunk_cls[s], slot[s].x1, slot[s].x2, n, K1, K2, ND,
-                        k1_count ? slot[s].k1 : nullptr, k2_count ? slot[s].k2 : nullptr, *opts,
+    PRE3_TRY(pairs_impl(ctx, slot[s].d1, seq ? nullptr : slot[s].d2, chunk_cls[s], slot[s].x1, seq ? nullptr : slot[s].x2,
+                        n, K1, K2, ND, k1_count ? slot[s].k1 : nullptr, !seq && k2_count ? slot[s].k2 : nullptr, *opts,
                         pair_id0 + (uint32_t)p0, slot[s].r, matches ? slot[s].m : nullptr,
                         masks ? slot[s].msk : nullptr));
     PRE3_TRY(d2h(ctx, hp_res + sizeof(pre3_pair_result) * (size_t)p0, slot[s].r, sizeof(pre3_pair_result) * (size_t)n));
@@ -704,6 +737,23 @@ int pre3_pairs(pre3_ctx* ctx, const void* desc1, const void* desc2, int cls, con
     fprintf(stderr, "[pre3] pairs: P=%d chunks=%d narrow=%d host narrowing %.1f ms, staging waits %.1f ms, enqueue compute %.1f ms, stage_in %.1f ms, final sync %.1f ms\n",
             P, nchunks, (int)narrow, t_conv * 1e3, t_wait * 1e3, t_enq * 1e3, t_stage * 1e3, (now() - t_sync0) * 1e3);
   return PRE3_OK;
+}
+
+int pre3_pairs(pre3_ctx* ctx, const void* desc1, const void* desc2, int cls, const double* xyz1, const double* xyz2,
+               int P, int K1, int K2, int ND, const int32_t* k1_count, const int32_t* k2_count,
+               const pre3_ransac_opts* opts, uint32_t pair_id0, pre3_pair_result* res, int32_t* matches,
+               uint8_t* masks) {
+  if (ctx && !(desc2 || (size_t)P * K2 * ND == 0)) return fail(ctx, PRE3_ERR_ARG, "descriptor pointer missing");
+  return pairs_host(ctx, desc1, desc2, cls, xyz1, xyz2, P, K1, K2, ND, k1_count, k2_count, opts, pair_id0, res, matches,
+                    masks, false);
+}
+
+int pre3_sequence(pre3_ctx* ctx, const void* desc, int cls, const double* xyz, int F, int K, int ND,
+                  const int32_t* k_count, const pre3_ransac_opts* opts, uint32_t pair_id0, pre3_pair_result* res,
+                  int32_t* matches, uint8_t* masks) {
+  if (F <= 1) return ctx ? PRE3_OK : PRE3_ERR_ARG;
+  return pairs_host(ctx, desc, nullptr, cls, xyz, nullptr, F - 1, K, K, ND, k_count, nullptr, opts, pair_id0, res,
+                    matches, masks, true);
 }
 
 // ================================================================================================

@@ -174,17 +174,24 @@ __device__ __forceinline__ void load4(const float* src, double* v) {
 
 constexpr int CV_ROWS = 32;  // rows per block (4 per warp)
 
+struct FrameInfo {       // per converted descriptor set ("frame")
+  unsigned max_bits;     // max |x|^2 (float bits) over the valid rows
+  int bad;               // some value is non-finite or too large for fp16
+};
+
+// One launch converts `gridDim.y` descriptor sets.  Norms are stored RAW (|x|^2 rounded up to float, +inf for
+// padded rows, which therefore can never win as columns); the bias that keeps the keys positive is added by the
+// GEMM epilogue, so one converted set can serve as the A operand of one pair and the B operand of another
+// (consecutive frames of a sequence).
 template <typename T>
 __global__ void __launch_bounds__(256)
-k_tc_convert(const T* __restrict__ L, int K, int Kp, const int32_t* __restrict__ kc, int is_b,
-             unsigned char* __restrict__ img, float* __restrict__ nrm, PairInfo* __restrict__ info) {
+k_tc_convert(const T* __restrict__ L, int K, int Kp, const int32_t* __restrict__ kc, unsigned char* __restrict__ img,
+             float* __restrict__ nrm, FrameInfo* __restrict__ finfo) {
   __shared__ float s_max[8];
   __shared__ int s_bad[8];
   const int p = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n = kc ? max(0, min(kc[p], K)) : K;
-  // B norms are stored biased: |b|^2 + C with C = 1.0625 max|a|^2 (set by the A launch before this one)
-  const float bias = is_b ? 1.0625f * __uint_as_float(info[p].amax_bits) : 0.f;
   float wmax = 0.f;
   bool wbad = false;
   double v[CV_ROWS / 8][4];
@@ -209,20 +216,19 @@ k_tc_convert(const T* __restrict__ L, int K, int Kp, const int32_t* __restrict__
                          (size_t)r * 128 + (size_t)((c ^ (r & 7)) << 4) + (size_t)((lane & 1) << 3);
     *reinterpret_cast<uint2*>(dst) = packed;
     // |x|^2 in fp64 (fixed shuffle tree), range check
-    double s = (v[i][0] * v[i][0] + v[i][1] * v[i][1]) + (v[i][2] * v[i][2] + v[i][3] * v[i][3]);
+    double sq = (v[i][0] * v[i][0] + v[i][1] * v[i][1]) + (v[i][2] * v[i][2] + v[i][3] * v[i][3]);
     bool bad = false;
 #pragma unroll
     for (int e = 0; e < 4; ++e) bad = bad || !(fabs(v[i][e]) <= 60000.0);
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    for (int off = 16; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
     bad = __any_sync(0xffffffffu, bad);
-    float f = __double2float_ru(s);
+    float f = __double2float_ru(sq);
     if (row < n) {
       wmax = fmaxf(wmax, f);
       wbad = wbad || bad;
     }
-    if (lane == 0)  // padded columns can never win
-      nrm[(size_t)p * Kp + row] = (row < n) ? (is_b ? f + bias : f) : (is_b ? INFINITY : 0.f);
+    if (lane == 0) nrm[(size_t)p * Kp + row] = (row < n) ? f : INFINITY;
   }
   if (lane == 0) {
     s_max[warp] = wmax;
@@ -236,9 +242,22 @@ k_tc_convert(const T* __restrict__ L, int K, int Kp, const int32_t* __restrict__
       mx = fmaxf(mx, s_max[w]);
       bd |= s_bad[w];
     }
-    if (mx > 0.f) atomicMax(is_b ? &info[p].bmax_bits : &info[p].amax_bits, __float_as_uint(mx));
-    if (bd) atomicOr(&info[p].bad, 1);
+    if (mx > 0.f) atomicMax(&finfo[p].max_bits, __float_as_uint(mx));
+    if (bd) atomicOr(&finfo[p].bad, 1);
   }
+}
+
+// per pair: bounds of its two descriptor sets (fa[p], fb[p])
+__global__ void k_tc_pair_info(int P, const FrameInfo* __restrict__ fa, const FrameInfo* __restrict__ fb,
+                               PairInfo* __restrict__ info) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  PairInfo o;
+  o.amax_bits = fa[p].max_bits;
+  o.bmax_bits = fb[p].max_bits;
+  o.bad = fa[p].bad | fb[p].bad;
+  o.pad = 0;
+  info[p] = o;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -260,7 +279,8 @@ struct Barriers {
 template <int EXP>
 __global__ void __launch_bounds__(THREADS, 1)
 k_tc_gemm_top2(const unsigned char* __restrict__ imgA, const unsigned char* __restrict__ imgB,
-               const float* __restrict__ nrmB, int P, int K1p, int K2p, Prop* __restrict__ prop) {
+               const float* __restrict__ nrmB, const PairInfo* __restrict__ pinfo, int P, int K1p, int K2p,
+               Prop* __restrict__ prop) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t base = smem_u32(smem);
   if (base & 1023u) __trap();  // SWIZZLE_128B tiles need 1024-byte alignment
@@ -390,12 +410,15 @@ k_tc_gemm_top2(const unsigned char* __restrict__ imgA, const unsigned char* __re
       // the column norm of the NEXT tile is fetched one tile ahead: its global-load latency (exposed, it cost a
       // quarter of the epilogue's time) hides behind the current tile's selection
       float nb_next = __ldg(nb + wtid);
+      // C = 1.0625 max_i |a_i|^2 of the pair: keeps every v' = |b|^2 + C - 2 a.b positive, so float bits order
+      // like unsigned integers (k_tc_rescore subtracts the same C)
+      const float bias = 1.0625f * __uint_as_float(pinfo[p].amax_bits);
       for (int j = 0; j < ntile; ++j, ++t) {
         const int set = (int)(t & 1);
         const int slot = set * 2 + rb;
         // stage the tile's (biased) column norms for broadcast reads
         float* snb = sNB + (rb * 2 + set) * BLK;
-        snb[wtid] = nb_next;
+        snb[wtid] = nb_next + bias;
         if (j + 1 < ntile) nb_next = __ldg(nb + (size_t)(j + 1) * BLK + wtid);
         named_bar_sync(1 + rb, 128);
         uint32_t& use = set == 0 ? useA : useB;
@@ -618,11 +641,11 @@ bool match_tc_supported(int cls, int K1, int K2, int ND) {
 size_t match_tc_workspace_bytes(int P, int K1, int K2) {
   const size_t K1p = pad128(K1), K2p = pad128(K2);
   size_t b = 0;
-  b += align_up((size_t)P * K1p * tc::ND * 2, 1024) + 1024;
+  b += align_up((size_t)(P + 1) * K1p * tc::ND * 2, 1024) + 1024;
   b += align_up((size_t)P * K2p * tc::ND * 2, 1024) + 1024;
-  b += align_up((size_t)P * K1p * 4) + align_up((size_t)P * K2p * 4);
+  b += align_up((size_t)(P + 1) * K1p * 4) + align_up((size_t)P * K2p * 4);
   b += align_up((size_t)P * K1p * sizeof(tc::Prop));
-  b += align_up((size_t)P * sizeof(tc::PairInfo));
+  b += align_up((size_t)P * sizeof(tc::PairInfo)) + 2 * align_up((size_t)(P + 1) * sizeof(tc::FrameInfo));
   b += align_up((size_t)P * K1 * 4) + 256;
   return b + 4096;
 }
@@ -633,32 +656,47 @@ int launch_match_tc(pre3_ctx* ctx, const void* dL1, const void* dL2, int cls, in
   if (!match_tc_supported(cls, K1, K2, ND)) return fail(ctx, PRE3_ERR_ARG, "tensor-core matcher: unsupported shape");
   if (P <= 0) return PRE3_OK;
   const int K1p = pad128(K1), K2p = pad128(K2);
+  // dL2 == nullptr: SEQUENCE mode.  dL1 holds P + 1 descriptor sets (consecutive frames); pair p matches set p
+  // against set p + 1.  Every set is converted once and serves as the A operand of pair p and the B operand of
+  // pair p - 1: half the conversion traffic of 2 P independent sets.
+  const bool seq = dL2 == nullptr;
+  if (seq && K1 != K2) return fail(ctx, PRE3_ERR_ARG, "sequence mode needs the same descriptor count per frame");
+  const int FA = seq ? P + 1 : P;  // descriptor sets behind dL1
   // carve (1024-byte aligned operand images: TMA bulk copies need 16, the smem tiles 1024)
   auto take1k = [&](size_t bytes) {
     ctx->ws_off = align_up(ctx->ws_off, 1024);
     return ws_take<unsigned char>(ctx, bytes);
   };
-  unsigned char* imgA = take1k((size_t)P * K1p * ND * 2);
-  unsigned char* imgB = take1k((size_t)P * K2p * ND * 2);
-  float* nrmA = ws_take<float>(ctx, (size_t)P * K1p);
-  float* nrmB = ws_take<float>(ctx, (size_t)P * K2p);
+  const size_t set_bytes = (size_t)K1p * ND * 2;
+  unsigned char* imgA = take1k((size_t)FA * set_bytes);
+  unsigned char* imgB = seq ? imgA + set_bytes : take1k((size_t)P * K2p * ND * 2);
+  float* nrmA = ws_take<float>(ctx, (size_t)FA * K1p);
+  float* nrmB = seq ? nrmA + K1p : ws_take<float>(ctx, (size_t)P * K2p);
   Prop* prop = ws_take<Prop>(ctx, (size_t)P * K1p);
   PairInfo* info = ws_take<PairInfo>(ctx, P);
+  FrameInfo* fa = ws_take<FrameInfo>(ctx, (size_t)FA);
+  FrameInfo* fb = seq ? fa + 1 : ws_take<FrameInfo>(ctx, (size_t)P);
   int32_t* list = ws_take<int32_t>(ctx, (size_t)P * K1);
   int32_t* list_n = ws_take<int32_t>(ctx, 64);
-  PRE3_CUDA(cudaMemsetAsync(info, 0, sizeof(PairInfo) * (size_t)P, ctx->stream));
+  PRE3_CUDA(cudaMemsetAsync(fa, 0, sizeof(FrameInfo) * (size_t)FA, ctx->stream));
+  if (!seq) PRE3_CUDA(cudaMemsetAsync(fb, 0, sizeof(FrameInfo) * (size_t)P, ctx->stream));
   PRE3_CUDA(cudaMemsetAsync(list_n, 0, sizeof(int32_t), ctx->stream));
+  if (seq) {
+    dL2 = (const char*)dL1 + (size_t)K1 * ND * (cls == PRE3_CLASS_DOUBLE ? 8 : 4);
+    if (dk1) dk2 = dk1 + 1;
+  }
   {
     Span span__(ctx, T_CONVERT);
-    const dim3 g1(K1p / CV_ROWS, P), g2(K2p / CV_ROWS, P);
+    const dim3 g1(K1p / CV_ROWS, FA), g2(K2p / CV_ROWS, P);
     if (cls == PRE3_CLASS_DOUBLE) {
-      k_tc_convert<double><<<g1, 256, 0, ctx->stream>>>((const double*)dL1, K1, K1p, dk1, 0, imgA, nrmA, info);
-      k_tc_convert<double><<<g2, 256, 0, ctx->stream>>>((const double*)dL2, K2, K2p, dk2, 1, imgB, nrmB, info);
+      k_tc_convert<double><<<g1, 256, 0, ctx->stream>>>((const double*)dL1, K1, K1p, dk1, imgA, nrmA, fa);
+      if (!seq) k_tc_convert<double><<<g2, 256, 0, ctx->stream>>>((const double*)dL2, K2, K2p, dk2, imgB, nrmB, fb);
     } else {
-      k_tc_convert<float><<<g1, 256, 0, ctx->stream>>>((const float*)dL1, K1, K1p, dk1, 0, imgA, nrmA, info);
-      k_tc_convert<float><<<g2, 256, 0, ctx->stream>>>((const float*)dL2, K2, K2p, dk2, 1, imgB, nrmB, info);
+      k_tc_convert<float><<<g1, 256, 0, ctx->stream>>>((const float*)dL1, K1, K1p, dk1, imgA, nrmA, fa);
+      if (!seq) k_tc_convert<float><<<g2, 256, 0, ctx->stream>>>((const float*)dL2, K2, K2p, dk2, imgB, nrmB, fb);
     }
-    count_launch(ctx, 2);
+    k_tc_pair_info<<<(P + 255) / 256, 256, 0, ctx->stream>>>(P, fa, fb, info);
+    count_launch(ctx, seq ? 2 : 3);
   }
   {
     Span span__(ctx, T_MATCH_TC);
@@ -672,7 +710,7 @@ int launch_match_tc(pre3_ctx* ctx, const void* dL1, const void* dL2, int cls, in
       PRE3_CUDA(cudaFuncSetAttribute(k_tc_gemm_top2<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); \
       attr_done = true;                                                                                          \
     }                                                                                                            \
-    k_tc_gemm_top2<E><<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(imgA, imgB, nrmB, P, K1p, K2p, prop);           \
+    k_tc_gemm_top2<E><<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(imgA, imgB, nrmB, info, P, K1p, K2p, prop);           \
   } while (0)
     switch (exp_mode) {
       case 0: PRE3_GEMM(0); break;

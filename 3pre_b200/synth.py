@@ -177,3 +177,59 @@ def make_batch_torch(P, seed, device, K1=512, K2=512, n_corr=300, outlier_ratio=
     if dtype == "float64":
         d1, d2 = d1.to(f64), d2.to(f64)
     return dict(desc1=d1.contiguous(), desc2=d2.contiguous(), xyz1=xyz1.contiguous(), xyz2=xyz2.contiguous(), R=R, t=t)
+
+
+def make_sequence_torch(F, seed, device, K=512, n_corr=300, outlier_ratio=0.30, noise=0.002, desc_noise=0.02,
+                        dtype="float64"):
+    """F consecutive synthetic SR4000 frames (desc (F,K,128), xyz (F,K,3)): frame f+1 re-observes n_corr random
+    features of frame f (descriptor + N(0, desc_noise^2) before normalisation, 3-D point moved by the rigid
+    motion of the step, a fraction replaced by unrelated points = outliers); its other K - n_corr features are
+    new.  Same distributions as make_batch_torch, which draws the two frames of every pair independently.
+    Returns dict desc, xyz, R (F-1,3,3), t (F-1,3) with xyz[f] ~ R[f] * xyz[f+1] + t[f] on the inliers."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(int(seed))
+    f64 = torch.float64
+    P = F - 1
+
+    def scene(*shape):
+        u = torch.rand(*shape, device=device, generator=g, dtype=f64) * (W - 1)
+        v = torch.rand(*shape, device=device, generator=g, dtype=f64) * (H_IMG - 1)
+        z = torch.rand(*shape, device=device, generator=g, dtype=f64) * 4.2 + 0.8
+        return torch.stack([-(u - CX) * z / F_PX, -(v - CY) * z / F_PX, z], dim=-1)
+
+    axis = torch.randn(P, 3, device=device, generator=g, dtype=f64)
+    axis = axis / axis.norm(dim=1, keepdim=True)
+    ang = torch.rand(P, device=device, generator=g, dtype=f64) * np.deg2rad(5.0)
+    Kx = torch.zeros(P, 3, 3, device=device, dtype=f64)
+    Kx[:, 0, 1], Kx[:, 0, 2] = -axis[:, 2], axis[:, 1]
+    Kx[:, 1, 0], Kx[:, 1, 2] = axis[:, 2], -axis[:, 0]
+    Kx[:, 2, 0], Kx[:, 2, 1] = -axis[:, 1], axis[:, 0]
+    eye = torch.eye(3, device=device, dtype=f64).expand(P, 3, 3)
+    R = eye + torch.sin(ang)[:, None, None] * Kx + (1 - torch.cos(ang))[:, None, None] * (Kx @ Kx)
+    t = torch.randn(P, 3, device=device, generator=g, dtype=f64)
+    t = t * (torch.rand(P, 1, device=device, generator=g, dtype=f64) * 0.10) / t.norm(dim=1, keepdim=True)
+
+    raw = torch.randn(F, K, 128, device=device, generator=g, dtype=torch.float32).abs()
+    xyz = scene(F, K)
+    i_prev = torch.rand(P, K, device=device, generator=g).argsort(dim=1)[:, :n_corr]   # features of frame f
+    i_next = torch.rand(P, K, device=device, generator=g).argsort(dim=1)[:, :n_corr]   # their slots in frame f+1
+    pert = desc_noise * torch.randn(P, n_corr, 128, device=device, generator=g, dtype=torch.float32)
+    pnoise = noise * torch.randn(P, n_corr, 3, device=device, generator=g, dtype=f64)
+    n_out = int(round(outlier_ratio * n_corr))
+    outl = scene(P, max(n_out, 1))
+    Rt = R.transpose(1, 2)
+    for f in range(P):  # frame f+1 depends on frame f
+        src = raw[f, i_prev[f]]
+        raw[f + 1, i_next[f]] = (src + pert[f]).abs()
+        ya = xyz[f, i_prev[f]]                       # previous-frame points
+        yb = (ya - t[f]) @ R[f] + pnoise[f]          # R^T (ya - t): the same points seen from frame f+1
+        if n_out > 0:
+            yb[:n_out] = outl[f, :n_out]
+        xyz[f + 1, i_next[f]] = yb
+    d = raw / raw.norm(dim=-1, keepdim=True)
+    d = d.clamp(max=0.2)
+    d = (d / d.norm(dim=-1, keepdim=True)).to(torch.float32)
+    if dtype == "float64":
+        d = d.to(f64)
+    return dict(desc=d.contiguous(), xyz=xyz.contiguous(), R=R, t=t)

@@ -212,6 +212,19 @@ PRE3_API int pre3_pairs_dev(pre3_ctx *ctx, const void *ddesc1, const void *ddesc
                    const pre3_ransac_opts *opts, uint32_t pair_id0, pre3_pair_result *dres,
                    int32_t *dmatches, uint8_t *dmasks);
 
+/* A SEQUENCE of F frames = F - 1 consecutive pairs (frame p, frame p + 1), the way the reference's
+ * whole-sequence loops call the pair driver (M/find_consistent_sift_matches.m:22-32:
+ * RANSAC_CALC_SAVE_SR4000(i, i + 1) for every i; M/Test_RANSAC_dead_reckoning.m).  Same results as pre3_pairs
+ * on (desc[p], desc[p+1]), but every frame's descriptors cross PCIe and are converted for the tensor cores once
+ * instead of twice.  desc: F x (128 x K), xyz: F x (3 x K), k_count: F or NULL; res / matches / masks: F - 1
+ * entries (pair p uses seeded sample sets of pair id pair_id0 + p). */
+PRE3_API int pre3_sequence(pre3_ctx *ctx, const void *desc, int cls, const double *xyz, int F, int K, int ND,
+                  const int32_t *k_count, const pre3_ransac_opts *opts, uint32_t pair_id0,
+                  pre3_pair_result *res, int32_t *matches, uint8_t *masks);
+PRE3_API int pre3_sequence_dev(pre3_ctx *ctx, const void *ddesc, int cls, const double *dxyz, int F, int K, int ND,
+                      const int32_t *dk_count, const pre3_ransac_opts *opts, uint32_t pair_id0,
+                      pre3_pair_result *dres, int32_t *dmatches, uint8_t *dmasks);
+
 /* ---- hypothesis-block sharding (one large pair over several GPUs) -------
  * Evaluates sample sets [h0, h0+Hloc) of the pair on this device and returns the local
  * best as key = (count << 32) | (0xFFFFFFFF - global_hypothesis_id) ("first-index" mode:

@@ -360,6 +360,57 @@ def test_pairs_host_narrowing_is_lossless_and_falls_back(synth, pre3, monkeypatc
     ctx.close()
 
 
+@pytest.mark.parametrize("cls", ["f64", "f32", "u8"])
+@pytest.mark.parametrize("engine", [0, 1])
+def test_sequence_equals_pairs(ctx, orc, synth, pre3, cls, engine):
+    """F consecutive frames through pre3_sequence(_dev) == the F-1 pairs (frame p, frame p+1) through pre3_pairs_dev
+    (bit for bit: records, matches, masks), ragged frame sizes included; pair 0 also against the oracle."""
+    import torch
+    F, K = 9, 200  # K not a multiple of 128; 8 pairs
+    sq = synth.make_sequence_torch(F, 77, "cuda", K=K, n_corr=120)
+    desc, xyz = sq["desc"], sq["xyz"]
+    if cls == "f32":
+        desc = desc.to(torch.float32)
+    elif cls == "u8":
+        desc = torch.clamp(torch.floor(512.0 * desc + 0.5), 0, 255).to(torch.uint8)
+    kc = torch.tensor([K, K - 3, K, K - 17, K, K, K - 1, K, K], dtype=torch.int32, device="cuda")
+    opts = pre3.make_opts(H=400, seed=9)
+    ctx.set_match_engine(engine)
+    try:
+        P = F - 1
+        r1 = torch.zeros(P, 240, dtype=torch.uint8, device="cuda")
+        m1 = torch.zeros(P, K, 2, dtype=torch.int32, device="cuda")
+        k1 = torch.zeros(P, K, dtype=torch.uint8, device="cuda")
+        ctx.pairs_dev(desc[:-1].contiguous(), desc[1:].contiguous(), xyz[:-1].contiguous(), xyz[1:].contiguous(), opts,
+                      r1, m1, k1, pair_id0=5, k1_count=kc[:-1].contiguous(), k2_count=kc[1:].contiguous())
+        r2 = torch.zeros(P, 240, dtype=torch.uint8, device="cuda")
+        m2 = torch.zeros(P, K, 2, dtype=torch.int32, device="cuda")
+        k2 = torch.zeros(P, K, dtype=torch.uint8, device="cuda")
+        ctx.sequence_dev(desc, xyz, opts, r2, m2, k2, pair_id0=5, k_count=kc)
+        ctx.sync()
+        a = np.frombuffer(r1.cpu().numpy().tobytes(), dtype=pre3.RESULT_DTYPE)
+        b = np.frombuffer(r2.cpu().numpy().tobytes(), dtype=pre3.RESULT_DTYPE)
+        assert a.tobytes() == b.tobytes() and (a["status"] == 0).all() and (a["best_fit"] > 40).all()
+        hres, hm, hk = ctx.sequence(desc.cpu().numpy(), xyz.cpu().numpy(), opts, pair_id0=5, k_count=kc.cpu().numpy())
+        assert hres.tobytes() == a.tobytes()
+        for p in range(P):
+            n = int(a["n_matches"][p])
+            np.testing.assert_array_equal(m1[p, :n].cpu().numpy(), m2[p, :n].cpu().numpy())
+            np.testing.assert_array_equal(hm[p, :n], m2[p, :n].cpu().numpy())
+            np.testing.assert_array_equal(k1[p, :n].cpu().numpy(), k2[p, :n].cpu().numpy())
+            np.testing.assert_array_equal(hk[p, :n], k2[p, :n].cpu().numpy())
+        if cls == "f64":
+            d0, d1 = desc[0].cpu().numpy(), desc[1, : K - 3].cpu().numpy()
+            om, o = orc.pair(d0, d1, xyz[0].cpu().numpy(), xyz[1, : K - 3].cpu().numpy(), 9, 5, H=400)
+            np.testing.assert_array_equal(hm[0, : len(om)], om)
+            assert (o.best_fit, o.best_sample) == (a["best_fit"][0], a["best_sample"][0])
+        # a single frame has no pair
+        res0, _, _ = ctx.sequence(desc[:1].cpu().numpy(), xyz[:1].cpu().numpy(), opts)
+        assert len(res0) == 0
+    finally:
+        ctx.set_match_engine(0)
+
+
 def test_matching_full_size_properties(ctx, synth):
     """2k x 2k descriptors: planted matches are found; matching L against itself returns the
     identity with score 0; results are independent of the batch position."""
