@@ -38,8 +38,8 @@ if ROOT not in sys.path:
 K_FEAT, N_CORR, OUTLIER, H_HYP, K_MIN, MAX_IT = 512, 300, 0.30, 2000, 5, 2000
 SEED = 3000  # 1000*cfg + index
 FLOPS_PER_EVAL = 27.0        # R*y 15, +t 3, -x 3, squares 5, sqrt 1
-WORKLOAD = "cfg3: sequence of {P} SR4000 frame pairs per GPU, 512x512 descriptors (double), 300 planted matches, " \
-           "30% outliers, k=5, 2000 sample sets, adaptive stop"
+WORKLOAD = "cfg3: sequence of {P}+1 consecutive SR4000 frames = {P} frame pairs per GPU, 512 descriptors (double) per " \
+           "frame, 300 re-observed features per step, 30% outliers, k=5, 2000 sample sets, adaptive stop"
 
 
 def peaks():
@@ -102,7 +102,8 @@ def cpu_baseline_single(n_pairs=24):
     total = sum(t[0] for t in ts)
     return {
         "value": n_pairs / total, "unit": "frame-pairs/s", "cores": 1, "kind": cpu_kind(),
-        "sample": f"{n_pairs} pairs of the workload, one thread: reference siftmatch.c (oracle/_ref) for matching "
+        "sample": f"{n_pairs} pairs of the workload's shape (512x512 descriptors, ~300 matches), one thread: "
+                  f"reference siftmatch.c (oracle/_ref) for matching "
                   f"[{sum(t[1] for t in ts) / total:.0%} of the time] + C restatement of RANSAC_CALC_VER2 "
                   "(MATLAB/Octave absent)" if cpu_kind() == "reference" else
                   f"{n_pairs} pairs of the workload, one thread, C restatement (oracle/pre3_oracle.c)",
@@ -450,14 +451,10 @@ def run_ours(args):
     P = args.pairs
     ctx = pre3.Context(local)
     ctx.use_torch_stream()
-    # synthetic sequence of this rank, generated on the device in slabs (bounded peak memory)
-    slabs = []
-    for s0 in range(0, P, 512):
-        n = min(512, P - s0)
-        slabs.append(synth.make_batch_torch(n, SEED + 100000 * rank + s0, dev, K1=K_FEAT, K2=K_FEAT, n_corr=N_CORR,
-                                            outlier_ratio=OUTLIER))
-    data = {k: torch.cat([s[k] for s in slabs]).contiguous() for k in ("desc1", "desc2", "xyz1", "xyz2")}
-    del slabs
+    # synthetic sequence of this rank: P + 1 consecutive frames, generated on the device
+    sq = synth.make_sequence_torch(P + 1, SEED + 100000 * rank, dev, K=K_FEAT, n_corr=N_CORR, outlier_ratio=OUTLIER)
+    data = {"desc": sq["desc"], "xyz": sq["xyz"]}
+    del sq
     torch.cuda.empty_cache()
     opts = pre3.make_opts(method=0, k=K_MIN, max_iteration=MAX_IT, adaptive=True, H=H_HYP, seed=7)
     res = torch.zeros(P, 240, dtype=torch.uint8, device=dev)
@@ -465,8 +462,7 @@ def run_ours(args):
     masks = torch.zeros(P, K_FEAT, dtype=torch.uint8, device=dev)
 
     def step():
-        ctx.pairs_dev(data["desc1"], data["desc2"], data["xyz1"], data["xyz2"], opts, res, matches, masks,
-                      pair_id0=rank * P)
+        ctx.sequence_dev(data["desc"], data["xyz"], opts, res, matches, masks, pair_id0=rank * P)
 
     def barrier():
         if world > 1:
@@ -521,7 +517,7 @@ def run_ours(args):
     pk = peaks()
     fp32_peak = ctx.measure_fp32_peak()
     fp32_peak_3reg = ctx.measure_fp32_peak_3reg()
-    desc_bytes = float(2 * P * K_FEAT * 128 * data["desc1"].element_size())
+    desc_bytes = float((P + 1) * K_FEAT * 128 * data["desc"].element_size())  # every frame is converted once
     match_flops = 2.0 * K_FEAT * K_FEAT * 128 * P
     rooflines = {}
     for name, v in per_kernel.items():
@@ -558,7 +554,8 @@ def run_ours(args):
         tr = json.load(open(tpath))["per_pair_bytes"]
         for name in rooflines:
             if name in tr:
-                rooflines[name]["traffic"] = tr[name]["bytes"] * P * tr[name].get("launches_per_timed_span", 1)
+                units = (P + 1) if name == "convert" else P  # convert: bytes per descriptor set (frame)
+                rooflines[name]["traffic"] = tr[name]["bytes"] * units
                 rooflines[name]["traffic_note"] = "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch " \
                                                   "(profiles/r01_f_kernels.csv, per pair) x pairs per launch"
     roofline = dict(rooflines.get(dom, {"bound": "hbm", "achieved": None, "peak": pk["hbm_gbs"], "unit": "GB/s",
@@ -574,16 +571,16 @@ def run_ours(args):
         return
     # ---- e2e: host buffers through pre3_pairs ---------------------------------------------
     Pe = min(P, args.e2e_pairs)
-    host = {k: torch.empty(data[k][:Pe].shape, dtype=data[k].dtype, pin_memory=True) for k in data}
+    host = {k: torch.empty(data[k][:Pe + 1].shape, dtype=data[k].dtype, pin_memory=True) for k in data}
     for k in host:
-        host[k].copy_(data[k][:Pe])
+        host[k].copy_(data[k][:Pe + 1])
     torch.cuda.synchronize()
     hn = {k: v.numpy() for k, v in host.items()}
     out = (np.zeros(Pe, pre3.RESULT_DTYPE), np.zeros((Pe, K_FEAT, 2), np.int32), np.zeros((Pe, K_FEAT), np.uint8))
     ectx = pre3.Context(local)
 
     def e2e_step():
-        return ectx.pairs(hn["desc1"], hn["desc2"], hn["xyz1"], hn["xyz2"], opts, pair_id0=rank * P, out=out)
+        return ectx.sequence(hn["desc"], hn["xyz"], opts, pair_id0=rank * P, out=out)
 
     for _ in range(max(1, min(args.warmup, 2))):
         e2e_step()
@@ -618,12 +615,13 @@ def run_ours(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD.format(P=P), "pairs_per_gpu": P, "sharding": "by frame pair",
-                       "l2": "inputs (4.3 GB of descriptors per GPU at P=4096) larger than L2",
+                       "api": "pre3_sequence_dev (value) / pre3_sequence (e2e): pair p = (frame p, frame p+1)",
+                       "l2": "inputs (2.1 GB of descriptors per GPU at P=4096) larger than L2",
                        "match_engine": "tcgen05 proposal + exact rescore" if "match_tc" in per_kernel
                        else "exact fp64 brute force"},
             "e2e": {"value": e2e_val, "unit": "frame-pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "pairs_per_step": Pe, "steps": e2e_steps, "host_input_bytes_per_step": host_in,
-                    "note": "pre3_pairs on pinned host buffers (class double). With one rank per host, descriptors whose "
+                    "note": "pre3_sequence on pinned host buffers (class double). With one rank per host, descriptors whose "
                             "values survive (double)(float)x == x are narrowed by a host thread pool and cross PCIe as "
                             "float (h2d_bytes_per_step < host_input_bytes_per_step); with several ranks per host they "
                             "cross as doubles (every GPU has its own link, the host memory is shared)"},
