@@ -13,6 +13,7 @@
 #include "ransac.cuh"
 
 #include <cmath>
+#include <cstdlib>
 
 namespace pre3 {
 
@@ -852,45 +853,53 @@ k_sel_tie(const PairMeta* __restrict__ meta, const double* __restrict__ Ya, cons
   }
 }
 
-// One THREAD per tied hypothesis (small N: the ties of a pair sit next to each other in the list, so
-// the lanes of a warp read the same few correspondences); loads of 4 correspondences in flight.
+// FOUR lanes per tied hypothesis (small N): the lanes of a quad take every fourth correspondence and the
+// ordered sum is rebuilt with width-4 shuffles (four adds per four correspondences, in index order).  Four
+// times the warps of the thread-per-tie form for the same ties: the kernel is latency bound (sqrt / dependent
+// adds), not throughput bound.
+template <int G>
 __global__ void __launch_bounds__(TIE_THREADS)
-k_sel_tie_thread(const PairMeta* __restrict__ meta, const double* __restrict__ Ya, const double* __restrict__ Yb,
-                 int Nmax, const int32_t* __restrict__ samples, uint64_t seed, uint32_t pair_id0, long long h0, int H,
-                 int k, int method, const int2* __restrict__ ties, const int* __restrict__ tie_total, int cap,
-                 double* __restrict__ es_out) {
+k_sel_tie_quad(const PairMeta* __restrict__ meta, const double* __restrict__ Ya, const double* __restrict__ Yb,
+               int Nmax, const int32_t* __restrict__ samples, uint64_t seed, uint32_t pair_id0, long long h0, int H,
+               int k, int method, const int2* __restrict__ ties, const int* __restrict__ tie_total, int cap,
+               double* __restrict__ es_out) {
   const int total = min(*tie_total, cap);
-  for (int t = blockIdx.x * TIE_THREADS + threadIdx.x; t < total; t += gridDim.x * TIE_THREADS) {
-    const int2 ps = ties[t];
+  const int sub = threadIdx.x & (G - 1);
+  const int quads = (gridDim.x * TIE_THREADS) / G;
+  const int rounds = (total + quads - 1) / quads;  // every thread runs the same number of rounds (full-warp shuffles)
+  for (int rd = 0; rd < rounds; ++rd) {
+    const int t = rd * quads + ((blockIdx.x * TIE_THREADS + threadIdx.x) / G);
+    const bool live = t < total;
+    if (!__any_sync(0xffffffffu, live)) continue;  // warp-uniform: nothing to do for this warp in this round
+    const int2 ps = ties[live ? t : 0];
     const int p = ps.x, s = ps.y;
     const PairMeta m = meta[p];
-    const int N = m.N;
+    const int N = live ? m.N : 0;
     const double* ya = Ya + (size_t)p * Nmax * 3;
     const double* yb = Yb + (size_t)p * Nmax * 3;
     int idx[MAX_K];
-    load_sample(samples, seed, pair_id0 + (uint32_t)p, h0, s, H, p, N, k, idx);
+    load_sample(samples, seed, pair_id0 + (uint32_t)p, h0, s, H, p, max(m.N, 1), k, idx);
     Rigid f;
     fit_sample(method, ya, yb, idx, k, f);
+    const int Nw = __reduce_max_sync(0xffffffffu, N);
     double es = 0.0;
-    int i = 0;
-    for (; i + 4 <= N; i += 4) {
-      double a[12], b[12];
-#pragma unroll
-      for (int u = 0; u < 12; ++u) {
-        a[u] = __ldg(ya + 3 * i + u);
-        b[u] = __ldg(yb + 3 * i + u);
+    for (int ib = 0; ib < Nw; ib += 2 * G) {
+      double v0 = 0.0, v1 = 0.0;
+      const int i0 = ib + sub, i1 = ib + G + sub;
+      if (i0 < N) {
+        const double nr = residual_norm(f.R, f.t, ya + 3 * i0, yb + 3 * i0);
+        v0 = nr < m.thr ? nr : 0.0;  // sum(normResidu(inliers)) in index order (:135); + 0.0 is exact
+      }
+      if (i1 < N) {
+        const double nr = residual_norm(f.R, f.t, ya + 3 * i1, yb + 3 * i1);
+        v1 = nr < m.thr ? nr : 0.0;
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const double nr = residual_norm(f.R, f.t, a + 3 * u, b + 3 * u);
-        es = es + (nr < m.thr ? nr : 0.0);  // sum(normResidu(inliers)) in index order (:135); + 0.0 is exact
-      }
+      for (int l = 0; l < G; ++l) es = es + __shfl_sync(0xffffffffu, v0, l, G);
+#pragma unroll
+      for (int l = 0; l < G; ++l) es = es + __shfl_sync(0xffffffffu, v1, l, G);
     }
-    for (; i < N; ++i) {
-      const double nr = residual_norm(f.R, f.t, ya + 3 * i, yb + 3 * i);
-      es = es + (nr < m.thr ? nr : 0.0);
-    }
-    es_out[(size_t)p * H + s] = es;
+    if (live && sub == 0) es_out[(size_t)p * H + s] = es;
   }
 }
 
@@ -1478,9 +1487,10 @@ int launch_select(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts&
   const size_t tie_warps = TIE_THREADS / 32;
   const int tie_blocks = (int)std::min<size_t>((PH + tie_warps - 1) / tie_warps, (size_t)ctx->sm_count * 16);
   if (b.Nmax <= 2048) {  // thread per tie; the ordered sum of a long residual list wants a warp per tie
-    const int tb = (int)std::min<size_t>((PH + TIE_THREADS - 1) / TIE_THREADS, (size_t)ctx->sm_count * 8);
-    k_sel_tie_thread<<<tb, TIE_THREADS, 0, ctx->stream>>>(b.meta, b.Ya, b.Yb, b.Nmax, b.samples, o.seed, b.pair_id0,
-                                                          b.h0, o.H, o.k, o.method, ties, tie_total, (int)PH, es);
+    // 4 lanes per tie measured best (select 0.34 -> 0.27 ms per 4096 pairs; 8 lanes 0.28, 16 lanes 0.31)
+    const int tb = (int)std::min<size_t>((4 * PH + TIE_THREADS - 1) / TIE_THREADS, (size_t)ctx->sm_count * 16);
+    k_sel_tie_quad<4><<<tb, TIE_THREADS, 0, ctx->stream>>>(b.meta, b.Ya, b.Yb, b.Nmax, b.samples, o.seed, b.pair_id0,
+                                                           b.h0, o.H, o.k, o.method, ties, tie_total, (int)PH, es);
   } else {
     k_sel_tie<<<tie_blocks, TIE_THREADS, 0, ctx->stream>>>(b.meta, b.Ya, b.Yb, b.Nmax, b.samples, o.seed, b.pair_id0,
                                                            b.h0, o.H, o.k, o.method, ties, tie_total, (int)PH, es);
