@@ -497,21 +497,16 @@ __device__ __forceinline__ void load_row4<float, double>(const float* src, doubl
   v[0] = x.x, v[1] = x.y, v[2] = x.z, v[3] = x.w;
 }
 
+constexpr int RS_GROUPS = 4;  // 16-row groups per (one-warp) block: 4x fewer blocks to schedule
+
 template <typename T, typename ACC>
-__global__ void __launch_bounds__(32)
-k_tc_rescore(const T* __restrict__ L1, const T* __restrict__ L2, int K1, int K2, int K1p, int K2p,
-             const int32_t* __restrict__ k1c, const int32_t* __restrict__ k2c, float thresh,
-             const Prop* __restrict__ prop, const float* __restrict__ nrmA, const PairInfo* __restrict__ info,
-             int need_score, MatchRow* __restrict__ rows, int32_t* __restrict__ row_list,
-             int32_t* __restrict__ row_list_n) {
-  __shared__ ACC sprod[RS_ROWS][ND + 1];
-  const int p = blockIdx.y;
+__device__ __forceinline__ void rescore_group(ACC (*sprod)[ND + 1], int p, int row0, int n1, int n2,
+                                              const T* __restrict__ L1, const T* __restrict__ L2, int K1, int K2,
+                                              int K1p, float thresh, const Prop* __restrict__ prop,
+                                              const float* __restrict__ nrmA, const PairInfo& pi, int need_score,
+                                              MatchRow* __restrict__ rows, int32_t* __restrict__ row_list,
+                                              int32_t* __restrict__ row_list_n) {
   const int lane = threadIdx.x & 31;
-  const int n1 = k1c ? max(0, min(k1c[p], K1)) : K1;
-  const int n2 = k2c ? max(0, min(k2c[p], K2)) : K2;
-  const int row0 = blockIdx.x * RS_ROWS;
-  if (row0 >= n1) return;
-  const PairInfo pi = info[p];
   const int nr = min(RS_ROWS, n1 - row0);
   const int k1 = row0 + lane;
   const bool mine = lane < nr;
@@ -626,6 +621,27 @@ k_tc_rescore(const T* __restrict__ L1, const T* __restrict__ L2, int K1, int K2,
   rows[(size_t)p * K1 + k1] = out;
 }
 
+template <typename T, typename ACC>
+__global__ void __launch_bounds__(32)
+k_tc_rescore(const T* __restrict__ L1, const T* __restrict__ L2, int K1, int K2, int K1p, int K2p,
+             const int32_t* __restrict__ k1c, const int32_t* __restrict__ k2c, float thresh,
+             const Prop* __restrict__ prop, const float* __restrict__ nrmA, const PairInfo* __restrict__ info,
+             int need_score, MatchRow* __restrict__ rows, int32_t* __restrict__ row_list,
+             int32_t* __restrict__ row_list_n) {
+  __shared__ ACC sprod[RS_ROWS][ND + 1];
+  const int p = blockIdx.y;
+  const int n1 = k1c ? max(0, min(k1c[p], K1)) : K1;
+  const int n2 = k2c ? max(0, min(k2c[p], K2)) : K2;
+  const PairInfo pi = info[p];
+  for (int grp = 0; grp < RS_GROUPS; ++grp) {
+    const int row0 = (blockIdx.x * RS_GROUPS + grp) * RS_ROWS;
+    if (row0 >= n1) return;
+    rescore_group<T, ACC>(sprod, p, row0, n1, n2, L1, L2, K1, K2, K1p, thresh, prop, nrmA, pi, need_score, rows, row_list,
+                          row_list_n);
+    __syncwarp();  // sprod is reused by the next group
+  }
+}
+
 }  // namespace tc
 
 // ---------------------------------------------------------------------------------------------
@@ -727,7 +743,7 @@ int launch_match_tc(pre3_ctx* ctx, const void* dL1, const void* dL2, int cls, in
   }
   {
     Span span__(ctx, T_RESCORE);
-    const dim3 g((K1 + RS_ROWS - 1) / RS_ROWS, P);
+    const dim3 g((K1 + RS_ROWS * RS_GROUPS - 1) / (RS_ROWS * RS_GROUPS), P);
     if (cls == PRE3_CLASS_DOUBLE)
       k_tc_rescore<double, double><<<g, 32, 0, ctx->stream>>>((const double*)dL1, (const double*)dL2, K1, K2,
                                                                           K1p, K2p, dk1, dk2, thresh, prop, nrmA, info,
