@@ -557,7 +557,7 @@ def run_ours(args):
                 units = (P + 1) if name == "convert" else P  # convert: bytes per descriptor set (frame)
                 rooflines[name]["traffic"] = tr[name]["bytes"] * units
                 rooflines[name]["traffic_note"] = "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch " \
-                                                  "(profiles/r01_f_kernels.csv, per pair) x pairs per launch"
+                                                  "(profiles/r01_i_kernels.csv, per pair) x pairs per launch"
     roofline = dict(rooflines.get(dom, {"bound": "hbm", "achieved": None, "peak": pk["hbm_gbs"], "unit": "GB/s",
                                         "frac": None, "traffic": None}))
     roofline["kernel"] = dom

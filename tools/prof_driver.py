@@ -27,11 +27,11 @@ def main():
     ctx.use_torch_stream()
     if "cfg3" in which:
         P = 1024
-        d = synth.make_batch_torch(P, 3000, dev)
+        d = synth.make_sequence_torch(P + 1, 3000, dev)
         opts = pre3.make_opts(method=0, k=5, max_iteration=2000, adaptive=True, H=2000, seed=7)
         res = torch.zeros(P, 240, dtype=torch.uint8, device=dev)
         for _ in range(2):
-            ctx.pairs_dev(d["desc1"], d["desc2"], d["xyz1"], d["xyz2"], opts, res)
+            ctx.sequence_dev(d["desc"], d["xyz"], opts, res)   # the headline path of bench.py
         ctx.sync()
         del d
     if "cfg2" in which:
