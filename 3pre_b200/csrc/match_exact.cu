@@ -142,52 +142,45 @@ k_match_exact(const T* __restrict__ L1, const T* __restrict__ L2, int K1, int K2
   (void)row_list_n;
 }
 
-// One warp per listed row: exact recomputation of rows the proposal path flagged.
-// row_list holds p*K1 + k1 entries, *row_list_n of them.  32 columns at a time: every column is
-// loaded coalesced (a lane holds RX_ND/32 consecutive bins), the delta*delta products go to shared
-// memory, then lane c adds column c's products strictly in bin order (siftmatch.c:101-107).
 constexpr int RX_ND = 128;
+// Exact recomputation of the rows the proposal path flagged (row_list holds p*K1 + k1 entries, *row_list_n of
+// them), one BLOCK per row: thread = column (strided by the block size), 128 sequential `acc += delta*delta`
+// per column in registers (strictly in bin order, siftmatch.c:101-107), the A row in shared memory.  The rows the proposal
+// cannot certify are few (a handful per thousand pairs), so what matters is the latency of ONE row: a warp per row
+// needs ~100 us for 512 columns, a 256-thread block a few.
+constexpr int RXB_THREADS = 256;
+
 template <typename T, typename ACC>
-__global__ void __launch_bounds__(32)
-k_match_rows_exact(const T* __restrict__ L1, const T* __restrict__ L2, int K1, int K2, int ND,
-                   const int32_t* __restrict__ k2c, float thresh, const int32_t* __restrict__ row_list,
-                   const int32_t* __restrict__ row_list_n, int list_cap, MatchRow* __restrict__ rows) {
-  __shared__ ACC sprod[32][RX_ND + 1];
-  const int lane = threadIdx.x;
+__global__ void __launch_bounds__(RXB_THREADS)
+k_match_rows_exact_blk(const T* __restrict__ L1, const T* __restrict__ L2, int K1, int K2, int ND,
+                       const int32_t* __restrict__ k2c, float thresh, const int32_t* __restrict__ row_list,
+                       const int32_t* __restrict__ row_list_n, int list_cap, MatchRow* __restrict__ rows) {
+  __shared__ ACC sa[RX_ND];
+  __shared__ Top2<ACC> sred[RXB_THREADS / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = min(*row_list_n, list_cap);
-  constexpr int PER = RX_ND / 32;
   for (int w = blockIdx.x; w < n; w += gridDim.x) {
     const int rid = row_list[w];
     const int p = rid / K1;
     const int n2 = k2c ? min(k2c[p], K2) : K2;
     const T* a = L1 + (size_t)rid * ND;
     const T* B = L2 + (size_t)p * K2 * ND;
-    ACC va[PER];
-#pragma unroll
-    for (int e = 0; e < PER; ++e) va[e] = (ACC)a[PER * lane + e];
+    __syncthreads();  // sa / sred of the previous row are no longer read
+    for (int e = tid; e < RX_ND; e += RXB_THREADS) sa[e] = (ACC)a[e];
+    __syncthreads();
     Top2<ACC> st;
     st.best = maxval<ACC>();
     st.second = maxval<ACC>();
     st.bestk = -1;
-    for (int c0 = 0; c0 < n2; c0 += 32) {
-      const int nc = min(32, n2 - c0);
-      __syncwarp();
-#pragma unroll 4
-      for (int c = 0; c < nc; ++c) {
-        const T* b = B + (size_t)(c0 + c) * ND + PER * lane;
-#pragma unroll
-        for (int e = 0; e < PER; ++e) {
-          const ACC d = va[e] - (ACC)b[e];
-          sprod[c][PER * lane + e] = d * d;
-        }
-      }
-      __syncwarp();
-      if (lane < nc) {
-        ACC acc = 0;
+    for (int c = tid; c < n2; c += RXB_THREADS) {  // ascending columns per thread: top2_update keeps the first minimum
+      const T* b = B + (size_t)c * ND;
+      ACC acc = 0;
 #pragma unroll 8
-        for (int bin = 0; bin < RX_ND; ++bin) acc += sprod[lane][bin];
-        top2_update(st, acc, c0 + lane);
+      for (int e = 0; e < RX_ND; ++e) {
+        const ACC d = sa[e] - (ACC)b[e];
+        acc += d * d;  // strictly in bin order (siftmatch.c:101-107)
       }
+      top2_update(st, acc, c);
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
@@ -197,12 +190,16 @@ k_match_rows_exact(const T* __restrict__ L1, const T* __restrict__ L2, int K1, i
       o.bestk = __shfl_xor_sync(0xffffffffu, st.bestk, off);
       top2_merge(st, o);
     }
-    if (lane == 0) {
-      MatchRow r;
-      r.best = (double)st.best;
-      r.bestk = st.bestk;
-      r.accept = (__fmul_rn(thresh, (float)st.best) <= (float)st.second && st.bestk != -1) ? 1 : 0;
-      rows[rid] = r;
+    if (lane == 0) sred[warp] = st;
+    __syncthreads();
+    if (tid == 0) {
+      Top2<ACC> r = sred[0];
+      for (int i = 1; i < RXB_THREADS / 32; ++i) top2_merge(r, sred[i]);
+      MatchRow o;
+      o.best = (double)r.best;
+      o.bestk = r.bestk;
+      o.accept = (__fmul_rn(thresh, (float)r.best) <= (float)r.second && r.bestk != -1) ? 1 : 0;
+      rows[rid] = o;
     }
   }
 }
@@ -303,19 +300,16 @@ int launch_match_rows_exact(pre3_ctx* ctx, const void* dL1, const void* dL2, int
                             int list_cap, MatchRow* drows) {
   Span span__(ctx, T_RESCORE);
   if (ND != RX_ND) return fail(ctx, PRE3_ERR_ARG, "row recheck: ND must be 128");
-  const int blocks = 16 * ctx->sm_count;
+  const int blocks = 4 * ctx->sm_count;
   if (cls == PRE3_CLASS_DOUBLE)
-    k_match_rows_exact<double, double><<<blocks, 32, 0, ctx->stream>>>((const double*)dL1, (const double*)dL2, K1, K2,
-                                                                         ND, dk2, thresh, drow_list, drow_list_n,
-                                                                         list_cap, drows);
+    k_match_rows_exact_blk<double, double><<<blocks, RXB_THREADS, 0, ctx->stream>>>(
+        (const double*)dL1, (const double*)dL2, K1, K2, ND, dk2, thresh, drow_list, drow_list_n, list_cap, drows);
   else if (cls == PRE3_CLASS_SINGLE)
-    k_match_rows_exact<float, float><<<blocks, 32, 0, ctx->stream>>>((const float*)dL1, (const float*)dL2, K1, K2, ND,
-                                                                       dk2, thresh, drow_list, drow_list_n, list_cap,
-                                                                       drows);
+    k_match_rows_exact_blk<float, float><<<blocks, RXB_THREADS, 0, ctx->stream>>>(
+        (const float*)dL1, (const float*)dL2, K1, K2, ND, dk2, thresh, drow_list, drow_list_n, list_cap, drows);
   else if (cls == PRE3_CLASS_DOUBLE_F32)
-    k_match_rows_exact<float, double><<<blocks, 32, 0, ctx->stream>>>((const float*)dL1, (const float*)dL2, K1, K2, ND,
-                                                                        dk2, thresh, drow_list, drow_list_n, list_cap,
-                                                                        drows);
+    k_match_rows_exact_blk<float, double><<<blocks, RXB_THREADS, 0, ctx->stream>>>(
+        (const float*)dL1, (const float*)dL2, K1, K2, ND, dk2, thresh, drow_list, drow_list_n, list_cap, drows);
   else
     return fail(ctx, PRE3_ERR_CLASS, "row recheck: class must be double or single");
   count_launch(ctx);
