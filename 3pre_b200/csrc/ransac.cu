@@ -249,20 +249,37 @@ k_eval(const PairMeta* __restrict__ meta, const double* __restrict__ Ya, const d
       sB[i] = Yb4[(size_t)p * Nmax + base + i];
     }
     __syncthreads();
-#pragma unroll 4
-    for (int i = 0; i < tn; ++i) {
+    auto resid2 = [&](int i) {
       const float4 b = sB[i];
       const float4 a = sA[i];
       const float ex = fmaf(r0, b.x, fmaf(r1, b.y, fmaf(r2, b.z, t0))) - a.x;
       const float ey = fmaf(r3, b.x, fmaf(r4, b.y, fmaf(r5, b.z, t1))) - a.y;
       const float ez = fmaf(r6, b.x, fmaf(r7, b.y, fmaf(r8, b.z, t2))) - a.z;
-      const float q = fmaf(ex, ex, fmaf(ey, ey, ez * ez));
-      const bool in = q < thr2;
-      cnt += in ? 1 : 0;
-      if (fabsf(q - thr2) <= delta) {
-        const int slot = atomicAdd(&sListN, 1);
-        if (slot < EV_LIST) sList[slot] = ((uint32_t)tid << 24) | ((in ? 1u : 0u) << 23) | (uint32_t)(base + i);
+      return fmaf(ex, ex, fmaf(ey, ey, ez * ez));
+    };
+    auto queue = [&](float q, int i) {  // threshold-borderline residual: fp64 recheck after the loop
+      const int slot = atomicAdd(&sListN, 1);
+      if (slot < EV_LIST) sList[slot] = ((uint32_t)tid << 24) | ((q < thr2 ? 1u : 0u) << 23) | (uint32_t)(base + i);
+    };
+    // four correspondences per trip, ONE (rarely taken) branch for their borderline tests: the hot loop carries
+    // no per-eval divergence bookkeeping
+    int i = 0;
+    for (; i + 4 <= tn; i += 4) {
+      const float q0 = resid2(i), q1 = resid2(i + 1), q2 = resid2(i + 2), q3 = resid2(i + 3);
+      cnt += (q0 < thr2 ? 1 : 0) + (q1 < thr2 ? 1 : 0) + (q2 < thr2 ? 1 : 0) + (q3 < thr2 ? 1 : 0);
+      const bool b0 = fabsf(q0 - thr2) <= delta, b1 = fabsf(q1 - thr2) <= delta, b2 = fabsf(q2 - thr2) <= delta,
+                 b3 = fabsf(q3 - thr2) <= delta;
+      if (b0 | b1 | b2 | b3) {
+        if (b0) queue(q0, i);
+        if (b1) queue(q1, i + 1);
+        if (b2) queue(q2, i + 2);
+        if (b3) queue(q3, i + 3);
       }
+    }
+    for (; i < tn; ++i) {
+      const float q = resid2(i);
+      cnt += q < thr2 ? 1 : 0;
+      if (fabsf(q - thr2) <= delta) queue(q, i);
     }
   }
   sCnt[tid] = scored ? cnt : -1;
