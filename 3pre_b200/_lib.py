@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libpre3.so")
 
 OK, ERR_ARG, ERR_CUDA, ERR_ALLOC, ERR_CLASS = 0, -1, -2, -3, -4
 CLASS_DOUBLE, CLASS_SINGLE, CLASS_INT8, CLASS_UINT8 = 0, 1, 2, 3
-METHOD_SVD, METHOD_HORN = 0, 1
+METHOD_SVD, METHOD_HORN, METHOD_DR_YE = 0, 1, 2
 MATCH_AUTO, MATCH_EXACT, MATCH_TC = 0, 1, 2
 TIMING_NCAT = 12
 
@@ -51,6 +51,12 @@ class PairResult(C.Structure):
         ("R_hyp", C.c_double * 9),
         ("T_hyp", C.c_double * 3),
     ]
+
+
+class DrYeStat(C.Structure):
+    """pre3_dr_ye_stat (32 bytes)"""
+    _fields_ = [("error_mean", C.c_double), ("error_std", C.c_double), ("dist", C.c_double),
+                ("n_iteration_ransac", C.c_int32), ("n_loops", C.c_int32)]
 
 
 class Cam(C.Structure):
@@ -99,6 +105,8 @@ SYMBOLS = {
     "pre3_ransac": (_I, [_VP, _VP, _VP, _I, _OPTS, _VP, _VP, _VP, _VP, _VP]),
     "pre3_ransac_batch": (_I, [_VP, _VP, _VP, _VP, _I, _I, _OPTS, _VP, _VP, _VP]),
     "pre3_ransac_batch_dev": (_I, [_VP, _VP, _VP, _VP, _I, _I, _OPTS, _VP, _VP, _VP]),
+    "pre3_vodometry_dr_ye_batch": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, _OPTS, _VP, _VP, _VP, _VP, _VP]),
+    "pre3_vodometry_dr_ye_batch_dev": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, _OPTS, _VP, _U32, _VP, _VP, _VP, _VP]),
     "pre3_pairs": (_I, [_VP, _VP, _VP, _I, _VP, _VP, _I, _I, _I, _I, _VP, _VP, _OPTS, _U32, _VP, _VP, _VP]),
     "pre3_pairs_dev": (_I, [_VP, _VP, _VP, _I, _VP, _VP, _I, _I, _I, _I, _VP, _VP, _OPTS, _U32, _VP, _VP, _VP]),
     "pre3_sequence": (_I, [_VP, _VP, _I, _VP, _I, _I, _I, _VP, _OPTS, _U32, _VP, _VP, _VP]),

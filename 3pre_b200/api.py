@@ -16,7 +16,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _lib as L
-from ._lib import Pre3Error, RansacOpts, PairResult, Cam, EkfOpts, EkfResult
+from ._lib import Pre3Error, RansacOpts, PairResult, Cam, EkfOpts, EkfResult, DrYeStat
 
 _CLS = {
     np.dtype(np.float64): L.CLASS_DOUBLE,
@@ -34,6 +34,9 @@ assert RESULT_DTYPE.itemsize == C.sizeof(PairResult) == 240
 EKF_RESULT_DTYPE = np.dtype([("status", "<i4"), ("n_evaluated", "<i4"), ("best_hyp", "<i4"), ("max_support", "<i4"),
                              ("num_ic", "<i4"), ("m", "<i4"), ("n_hyp", "<f8")])
 assert EKF_RESULT_DTYPE.itemsize == C.sizeof(EkfResult) == 32
+DR_YE_STAT_DTYPE = np.dtype([("error_mean", "<f8"), ("error_std", "<f8"), ("dist", "<f8"),
+                             ("n_iteration_ransac", "<i4"), ("n_loops", "<i4")])
+assert DR_YE_STAT_DTYPE.itemsize == C.sizeof(DrYeStat) == 32
 
 
 def _ptr(a):
@@ -335,6 +338,46 @@ class Context:
         self._ck(self._lib.pre3_ransac_batch(self._h, _ptr(ya), _ptr(yb), _ptr(nc), P, Nmax, C.byref(o), _ptr(s),
                                              _ptr(res), _ptr(masks)))
         return res[:P], (masks[:P, :Nmax] if masks is not None else None)
+
+    # ---- code_from_dr_ye variant ---------------------------------------------------------
+    def vodometry_dr_ye_batch(self, Ya, Yb, n_corr=None, match=None, samples=None, opts: RansacOpts | None = None,
+                              want_masks=True, want_counts=False, **kw):
+        """RANSAC part of vodometry_dr_ye.m:147-220 for P match sets.  Ya = pset1, Yb = pset2 (P,Nmax,3);
+        match (P,Nmax,2) feature ids or None; samples (P,H,4) draws (0-based) or None (seeded sampler).
+        Returns (results RESULT_DTYPE (P,), masks (P,Nmax) | None, stat DR_YE_STAT_DTYPE (P,), counts (P,H) | None)."""
+        ya, yb = _c(Ya, np.float64), _c(Yb, np.float64)
+        P, Nmax = ya.shape[0], ya.shape[1]
+        kw.setdefault("k", 4)
+        kw.setdefault("max_iteration", 700)
+        kw.setdefault("H", 700)
+        o = opts or make_opts(method=L.METHOD_DR_YE, **kw)
+        s = None
+        if samples is not None:
+            s = _c(samples, np.int32)
+            if s.ndim != 3 or s.shape[2] != 4:
+                raise ValueError("samples must be (P, H, 4)")
+            o.H = int(s.shape[1])
+        mt = None if match is None else _c(match, np.int32)
+        nc = None if n_corr is None else _c(n_corr, np.int32)
+        res = np.zeros(max(P, 1), RESULT_DTYPE)
+        stat = np.zeros(max(P, 1), DR_YE_STAT_DTYPE)
+        masks = np.zeros((max(P, 1), max(Nmax, 1)), np.uint8) if want_masks else None
+        counts = np.zeros((max(P, 1), max(int(o.H), 1)), np.int32) if want_counts else None
+        self._ck(self._lib.pre3_vodometry_dr_ye_batch(self._h, _ptr(ya), _ptr(yb), _ptr(nc), _ptr(mt), P, Nmax,
+                                                      C.byref(o), _ptr(s), _ptr(res), _ptr(masks), _ptr(stat),
+                                                      _ptr(counts)))
+        return (res[:P], masks[:P, :Nmax] if masks is not None else None, stat[:P],
+                counts[:P, :int(o.H)] if counts is not None else None)
+
+    def vodometry_dr_ye_batch_dev(self, Ya, Yb, opts: RansacOpts, res, n_corr=None, match=None, samples=None,
+                                  masks=None, stat=None, counts=None, pair_id0=0):
+        """CUDA tensors: Ya, Yb (P,Nmax,3) f64; res uint8 (P,240); n_corr int32 (P,) | None; match int32
+        (P,Nmax,2) | None; samples int32 (P,H,4) | None; masks uint8 (P,Nmax) | None; stat uint8 (P,32) | None;
+        counts int32 (P,H) | None.  Asynchronous on the context's stream."""
+        P, Nmax = int(Ya.shape[0]), int(Ya.shape[1])
+        self._ck(self._lib.pre3_vodometry_dr_ye_batch_dev(self._h, _ptr(Ya), _ptr(Yb), _ptr(n_corr), _ptr(match), P,
+                                                          Nmax, C.byref(opts), _ptr(samples), int(pair_id0),
+                                                          _ptr(res), _ptr(masks), _ptr(stat), _ptr(counts)))
 
     # ---- whole pairs --------------------------------------------------------------------
     def pairs(self, desc1, desc2, xyz1, xyz2, opts: RansacOpts | None = None, pair_id0=0, k1_count=None,

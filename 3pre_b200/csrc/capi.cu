@@ -45,8 +45,10 @@ int d2h(pre3_ctx* ctx, void* h, const void* d, size_t bytes) {
 
 int check_opts(pre3_ctx* ctx, const pre3_ransac_opts* o) {
   PRE3_NEED(o != nullptr, "options missing");
-  PRE3_NEED(o->method == PRE3_METHOD_SVD || o->method == PRE3_METHOD_HORN, "unknown RANSAC method");
+  PRE3_NEED(o->method == PRE3_METHOD_SVD || o->method == PRE3_METHOD_HORN || o->method == PRE3_METHOD_DR_YE,
+            "unknown RANSAC method");
   PRE3_NEED(o->k >= 3 && o->k <= 8, "minimal sample size k must be in 3..8");
+  PRE3_NEED(o->method != PRE3_METHOD_DR_YE || o->k == 4, "the dr_ye variant draws 4 matches per hypothesis");
   PRE3_NEED(o->H >= 0, "H must be >= 0");
   PRE3_NEED(o->max_iteration >= 0, "MaxIteration must be >= 0");
   return PRE3_OK;
@@ -93,7 +95,8 @@ size_t ransac_ws_bytes(int P, int Nmax, int H) { return ransac_workspace_bytes(P
 
 int ransac_impl(pre3_ctx* ctx, const double* dYa, const double* dYb, const int32_t* dn_corr, int P, int Nmax,
                 const pre3_ransac_opts& o, const int32_t* dsamples, uint32_t pair_id0, pre3_pair_result* dres,
-                uint8_t* dmasks, int32_t* dcounts, int8_t* dstates) {
+                uint8_t* dmasks, int32_t* dcounts, int8_t* dstates, const int32_t* dmatch = nullptr,
+                pre3_dr_ye_stat* dstat = nullptr) {
   RansacBuffers b{};
   b.Ya = dYa;
   b.Yb = dYb;
@@ -103,6 +106,10 @@ int ransac_impl(pre3_ctx* ctx, const double* dYa, const double* dYb, const int32
   b.samples = dsamples;
   b.pair_id0 = pair_id0;
   ransac_carve(ctx, b, o.H);
+  if (o.method == PRE3_METHOD_DR_YE) {
+    if (dstates) return fail(ctx, PRE3_ERR_ARG, "per-hypothesis states are not reported by the dr_ye variant");
+    return launch_dr_ye(ctx, b, o, dmatch, dres, dmasks, dstat, dcounts);
+  }
   PRE3_TRY(ensure_adaptive_table(ctx, o, Nmax));
   PRE3_TRY(launch_prep(ctx, b, o, 0));
   PRE3_TRY(launch_eval_waves(ctx, b, o));
@@ -486,6 +493,72 @@ int pre3_ransac(pre3_ctx* ctx, const double* Ya, const double* Yb, int N, const 
 }
 
 // ================================================================================================
+// code_from_dr_ye variant
+// ================================================================================================
+int pre3_vodometry_dr_ye_batch_dev(pre3_ctx* ctx, const double* dYa, const double* dYb, const int32_t* dn_corr,
+                                   const int32_t* dmatch, int P, int Nmax, const pre3_ransac_opts* opts,
+                                   const int32_t* dsamples, uint32_t pair_id0, pre3_pair_result* dres,
+                                   uint8_t* dmasks, pre3_dr_ye_stat* dstat, int32_t* dcounts) {
+  PRE3_LIVE();
+  PRE3_NEED(opts != nullptr, "options missing");
+  pre3_ransac_opts o = *opts;
+  o.method = PRE3_METHOD_DR_YE;
+  PRE3_TRY(check_opts(ctx, &o));
+  PRE3_NEED(P >= 0 && Nmax >= 0, "bad sizes");
+  PRE3_NEED(dres != nullptr, "result pointer missing");
+  if (P == 0) return PRE3_OK;
+  PRE3_TRY(ws_reserve(ctx, ransac_ws_bytes(P, Nmax, o.H)));
+  return ransac_impl(ctx, dYa, dYb, dn_corr, P, Nmax, o, dsamples, pair_id0, dres, dmasks, dcounts, nullptr, dmatch,
+                     dstat);
+}
+
+int pre3_vodometry_dr_ye_batch(pre3_ctx* ctx, const double* Ya, const double* Yb, const int32_t* n_corr,
+                               const int32_t* match, int P, int Nmax, const pre3_ransac_opts* opts,
+                               const int32_t* samples, pre3_pair_result* res, uint8_t* masks, pre3_dr_ye_stat* stat,
+                               int32_t* counts) {
+  PRE3_LIVE();
+  PRE3_NEED(opts != nullptr, "options missing");
+  pre3_ransac_opts o = *opts;
+  o.method = PRE3_METHOD_DR_YE;
+  PRE3_TRY(check_opts(ctx, &o));
+  PRE3_NEED(P >= 0 && Nmax >= 0, "bad sizes");
+  PRE3_NEED(res != nullptr, "result pointer missing");
+  PRE3_NEED((Ya && Yb) || (size_t)P * Nmax == 0, "null correspondences");
+  if (P == 0) return PRE3_OK;
+  const int H = o.H;
+  const size_t pb = 3 * (size_t)P * Nmax * 8;
+  const size_t sb = samples ? 16 * (size_t)P * H : 0;
+  const size_t mtb = match ? 8 * (size_t)P * Nmax : 0;
+  const size_t rb = sizeof(pre3_pair_result) * (size_t)P;
+  const size_t mb = masks ? (size_t)P * Nmax : 0;
+  const size_t cb = counts ? 4 * (size_t)P * H : 0;
+  const size_t stb = stat ? sizeof(pre3_dr_ye_stat) * (size_t)P : 0;
+  PRE3_TRY(ws_reserve(ctx, ransac_ws_bytes(P, Nmax, H) + 2 * align_up(pb) + align_up(sb) + align_up(mtb) + align_up(rb) +
+                               align_up(mb) + align_up(cb) + align_up(stb) + align_up(4 * (size_t)P) + 8192));
+  double* dYa = ws_take<double>(ctx, 3 * (size_t)P * Nmax);
+  double* dYb = ws_take<double>(ctx, 3 * (size_t)P * Nmax);
+  int32_t* ds = samples ? ws_take<int32_t>(ctx, 4 * (size_t)P * H) : nullptr;
+  int32_t* dmt = match ? ws_take<int32_t>(ctx, 2 * (size_t)P * Nmax) : nullptr;
+  int32_t* dn = n_corr ? ws_take<int32_t>(ctx, P) : nullptr;
+  pre3_pair_result* dres = ws_take<pre3_pair_result>(ctx, P);
+  uint8_t* dm = masks ? ws_take<uint8_t>(ctx, mb) : nullptr;
+  int32_t* dc = counts ? ws_take<int32_t>(ctx, (size_t)P * H) : nullptr;
+  pre3_dr_ye_stat* dst = stat ? ws_take<pre3_dr_ye_stat>(ctx, P) : nullptr;
+  PRE3_TRY(h2d(ctx, dYa, Ya, pb));
+  PRE3_TRY(h2d(ctx, dYb, Yb, pb));
+  if (ds) PRE3_TRY(h2d(ctx, ds, samples, sb));
+  if (dmt) PRE3_TRY(h2d(ctx, dmt, match, mtb));
+  if (dn) PRE3_TRY(h2d(ctx, dn, n_corr, 4 * (size_t)P));
+  PRE3_TRY(ransac_impl(ctx, dYa, dYb, dn, P, Nmax, o, ds, 0, dres, dm, dc, nullptr, dmt, dst));
+  PRE3_TRY(d2h(ctx, res, dres, rb));
+  if (masks) PRE3_TRY(d2h(ctx, masks, dm, mb));
+  if (counts) PRE3_TRY(d2h(ctx, counts, dc, cb));
+  if (stat) PRE3_TRY(d2h(ctx, stat, dst, stb));
+  PRE3_CUDA(cudaStreamSynchronize(ctx->stream));
+  return PRE3_OK;
+}
+
+// ================================================================================================
 // whole frame pairs
 // ================================================================================================
 static size_t pairs_ws_bytes(int cls, int P, int K1, int K2, int ND, int H) {
@@ -508,7 +581,7 @@ static int pairs_impl(pre3_ctx* ctx, const void* ddesc1, const void* ddesc2, int
   int32_t* dn = ws_take<int32_t>(ctx, P);
   int32_t* dpairs = dmatches ? dmatches : ws_take<int32_t>(ctx, 2 * (size_t)P * K1);
   PRE3_TRY(launch_match_compact(ctx, rows, P, K1, dk1, dpairs, nullptr, dn, dxyz1, dxyz2, K2, dYa, dYb));
-  return ransac_impl(ctx, dYa, dYb, dn, P, K1, o, nullptr, pair_id0, dres, dmasks, nullptr, nullptr);
+  return ransac_impl(ctx, dYa, dYb, dn, P, K1, o, nullptr, pair_id0, dres, dmasks, nullptr, nullptr, dpairs);
 }
 
 int pre3_pairs_dev(pre3_ctx* ctx, const void* ddesc1, const void* ddesc2, int cls, const double* dxyz1,

@@ -71,8 +71,9 @@ __device__ __forceinline__ double det3(const double* m) {
 
 // Tail of find_transform_matrix once H (row-major), ct1, ct2 are known (:17-42).
 // Returns state; fills out (rot row-major, trans).
+// threshold: 1e-11 (find_transform_matrix.m:20) or 1e-14 (code_from_dr_ye/find_transform_matrix_dr_ye.m:19).
 __device__ __forceinline__ int kabsch_from_H(const double* H, const double* ct1, const double* ct2,
-                                             Rigid& out) {
+                                             Rigid& out, double threshold = 0.00000000001) {
   bool finite = true;
 #pragma unroll
   for (int i = 0; i < 9; ++i) finite = finite && isfinite(H[i]);
@@ -85,7 +86,7 @@ __device__ __forceinline__ int kabsch_from_H(const double* H, const double* ct1,
     svd3_cols(A, V, sig);
 #pragma unroll
     for (int j = 0; j < 3; ++j)
-      if (sig[j] < 0.00000000001) {
+      if (sig[j] < threshold) {
         ++nsmall;
         jsmall = j;
       }
@@ -150,7 +151,7 @@ __device__ __forceinline__ int kabsch_from_H(const double* H, const double* ct1,
 // time (loops unroll, points live in registers); KN == 0 uses the runtime n.  Either way
 // the arithmetic sequence is the one of find_transform_matrix.m:11-15.
 template <int KN, typename Get>
-__device__ __forceinline__ int fit_kabsch(int n_rt, Get get, Rigid& out) {
+__device__ __forceinline__ int fit_kabsch(int n_rt, Get get, Rigid& out, double threshold = 0.00000000001) {
   const int n = KN > 0 ? KN : n_rt;
   double ct1[3] = {0, 0, 0}, ct2[3] = {0, 0, 0};
 #pragma unroll
@@ -183,7 +184,7 @@ __device__ __forceinline__ int fit_kabsch(int n_rt, Get get, Rigid& out) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) H[3 * r + c] = H[3 * r + c] + q2[r] * q1[c];
   }
-  return kabsch_from_H(H, ct1, ct2, out);
+  return kabsch_from_H(H, ct1, ct2, out, threshold);
 }
 
 // Cyclic Jacobi on the symmetric 4x4 m (row-major, upper triangle authoritative);
@@ -349,6 +350,19 @@ __device__ __forceinline__ double residual_norm(const double* R, const double* t
     r[k] = y0 - ya[k];
   }
   return sqrt((r[0] * r[0] + r[1] * r[1]) + r[2] * r[2]);
+}
+
+// Squared distance d_diff of M/code_from_dr_ye/ransac_dr_ye.m:61-68 (sum of squares from 0.0, no sqrt).
+__device__ __forceinline__ double residual_sq(const double* R, const double* t, const double* ya,
+                                              const double* yb) {
+  double d = 0.0;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const double y0 = ((R[3 * k] * yb[0] + R[3 * k + 1] * yb[1]) + R[3 * k + 2] * yb[2]) + t[k];
+    const double e = y0 - ya[k];
+    d = d + e * e;
+  }
+  return d;
 }
 
 }  // namespace pre3

@@ -137,7 +137,17 @@ __global__ void __launch_bounds__(256) k_prep(const double* __restrict__ Ya, con
 // ------------------------------------------------------------------------------------------
 // k_eval
 // ------------------------------------------------------------------------------------------
-// MODE 0: find_transform_matrix fit, MODE 1: Horn fit, MODE 2: (R,t) given (column-major R).
+// MODE 0: find_transform_matrix fit, MODE 1: Horn fit, MODE 2: (R,t) given (column-major R),
+// MODE 3: the code_from_dr_ye variant (ransac_dr_ye.m:59-70): find_transform_matrix fit on the sample in the
+//         order given, EVERY hypothesis scored (rot = H, trans = 0 when the fit fails), and the threshold
+//         meta.thr bounds the SQUARED distance (meta.thr2 = fl32(thr)).
+template <int MODE>
+__device__ __forceinline__ bool exact_inlier(const double* R, const double* t, const double* ya, const double* yb,
+                                             double thr) {
+  if (MODE == 3) return residual_sq(R, t, ya, yb) < thr;
+  return residual_norm(R, t, ya, yb) < thr;
+}
+
 template <int K, int MODE>
 __global__ void __launch_bounds__(EV_THREADS)
 k_eval(const PairMeta* __restrict__ meta, const double* __restrict__ Ya, const double* __restrict__ Yb,
@@ -206,7 +216,7 @@ k_eval(const PairMeta* __restrict__ meta, const double* __restrict__ Ya, const d
           b[r] = pb[i][r];
         }
       };
-      if (MODE == 0)
+      if (MODE == 0 || MODE == 3)
         state = fit_kabsch<K>(K, get, fit);
       else
         state = fit_horn<K>(K, get, fit);
@@ -232,7 +242,7 @@ k_eval(const PairMeta* __restrict__ meta, const double* __restrict__ Ya, const d
     // |e32 - e| <= 12 u (Rmax*|yb|_1 + |t| + |ya|): 2u input rounding per product term, u per
     // fma/sub rounding, generous constant; u = 2^-24.
     const float eps = 1.001f * 12.0f * 5.9604645e-8f * (rmax * m.y1max + tmax + m.xmax);
-    const float thrf = __double2float_ru(m.thr);
+    const float thrf = MODE == 3 ? __fsqrt_ru(__double2float_ru(m.thr)) : __double2float_ru(m.thr);
     // |r2_32 - r2| <= eps (2 sqrt(3) r + 3 eps) + 4u r2 near r = thr; doubled for slack.
     delta = 1.01f * (2.0f * eps * (3.4641018f * thrf + 3.0f * eps) + 8.0f * 5.9604645e-8f * thr2);
   }
@@ -290,7 +300,7 @@ k_eval(const PairMeta* __restrict__ meta, const double* __restrict__ Ya, const d
     if (scored) {
       int c = 0;
       for (int i = 0; i < N; ++i)
-        c += (residual_norm(&sRt[tid * 12], &sRt[tid * 12 + 9], ya + 3 * i, yb + 3 * i) < m.thr) ? 1 : 0;
+        c += exact_inlier<MODE>(&sRt[tid * 12], &sRt[tid * 12 + 9], ya + 3 * i, yb + 3 * i, m.thr) ? 1 : 0;
       sCnt[tid] = c;
     }
   } else {
@@ -299,7 +309,7 @@ k_eval(const PairMeta* __restrict__ meta, const double* __restrict__ Ya, const d
       const int hl = item >> 24;
       const bool in32 = (item >> 23) & 1u;
       const int mi = item & 0x7FFFFFu;
-      const bool in64 = residual_norm(&sRt[hl * 12], &sRt[hl * 12 + 9], ya + 3 * mi, yb + 3 * mi) < m.thr;
+      const bool in64 = exact_inlier<MODE>(&sRt[hl * 12], &sRt[hl * 12 + 9], ya + 3 * mi, yb + 3 * mi, m.thr);
       if (in64 != in32) atomicAdd(&sCnt[hl], in64 ? 1 : -1);
     }
   }
@@ -430,7 +440,8 @@ __device__ __forceinline__ int fit_sample(int method, const double* ya, const do
 // result.  Sums are formed per thread over a strided subset and then tree-reduced in a fixed
 // order (deterministic; differs from the reference's sequential sum only in rounding).
 __device__ __forceinline__ int block_refit(int method, const double* ya, const double* yb,
-                                           const uint8_t* mask, int N, double* scratch, Rigid& out) {
+                                           const uint8_t* mask, int N, double* scratch, Rigid& out,
+                                           double threshold = 0.00000000001) {
   const int tid = threadIdx.x;
   double c1[3] = {0, 0, 0}, c2[3] = {0, 0, 0};
   double ns = 0.0;
@@ -467,7 +478,7 @@ __device__ __forceinline__ int block_refit(int method, const double* ya, const d
 #pragma unroll
     for (int i = 0; i < 9; ++i) H[i] = block_sum(H[i], scratch);
     int st = 0;
-    if (tid == 0) st = kabsch_from_H(H, c1, c2, out);
+    if (tid == 0) st = kabsch_from_H(H, c1, c2, out, threshold);
     return st;
   } else {
     double M[16];
@@ -1317,6 +1328,294 @@ __global__ void __launch_bounds__(256) k_threshold(const double* __restrict__ Yb
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// The code_from_dr_ye variant: M/code_from_dr_ye/vodometry_dr_ye.m:147-220 with
+// ransac_dr_ye.m as the loop body.  Specification: oracle/pre3_oracle_dr_ye.c.
+//   k_dy_prep    per pair: dist / threshold on the squared distance (ransac_dr_ye.m:20-23,70), fp32 copies
+//   k_dy_sample  per hypothesis: the reference's 4-match sampler (:28-48) on a seeded uniform stream
+//   k_eval<4,3>  fit + support of every hypothesis (:59-71)
+//   k_dy_select  per pair: first maximum of cnum (vodometry_dr_ye.m:184), support set, refit with the
+//                1e-14 variant (:211), mean / std of the residual norms (:212-215), nIterationRansac (:216)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_dy_prep(const double* __restrict__ Ya, const double* __restrict__ Yb,
+                                                 const int32_t* __restrict__ n_corr, int Nmax,
+                                                 PairMeta* __restrict__ meta, float4* __restrict__ Ya4,
+                                                 float4* __restrict__ Yb4) {
+  const int p = blockIdx.x;
+  int N = n_corr ? n_corr[p] : Nmax;
+  N = max(0, min(N, Nmax));
+  const double* ya = Ya + (size_t)p * Nmax * 3;
+  const double* yb = Yb + (size_t)p * Nmax * 3;
+  float y1 = 0.f, xm = 0.f;
+  double bz = INFINITY;
+  int any = 0;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const double ax = ya[3 * i], ay = ya[3 * i + 1], az = ya[3 * i + 2];
+    const double bx = yb[3 * i], by = yb[3 * i + 1], bzz = yb[3 * i + 2];
+    Ya4[(size_t)p * Nmax + i] = make_float4(__double2float_rn(ax), __double2float_rn(ay), __double2float_rn(az), 0.f);
+    Yb4[(size_t)p * Nmax + i] = make_float4(__double2float_rn(bx), __double2float_rn(by), __double2float_rn(bzz), 0.f);
+    y1 = fmaxf(y1, __double2float_ru(fabs(bx) + fabs(by) + fabs(bzz)));
+    xm = fmaxf(xm, __double2float_ru(fmax(fabs(ax), fmax(fabs(ay), fabs(az)))));
+    const double nrm = sqrt((bzz * bzz + by * by) + bx * bx);  // :20
+    if (nrm > 0.4) {  // :21
+      if (!any || bzz < bz) bz = bzz;
+      any = 1;
+    }
+  }
+  __shared__ float s_y1[256], s_xm[256];
+  __shared__ double s_bz[256];
+  __shared__ int s_i[256];
+  s_y1[threadIdx.x] = y1;
+  s_xm[threadIdx.x] = xm;
+  s_bz[threadIdx.x] = bz;
+  s_i[threadIdx.x] = any;
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) {
+    if (threadIdx.x < off) {
+      const int o = threadIdx.x + off;
+      s_y1[threadIdx.x] = fmaxf(s_y1[threadIdx.x], s_y1[o]);
+      s_xm[threadIdx.x] = fmaxf(s_xm[threadIdx.x], s_xm[o]);
+      if (s_i[o] && (!s_i[threadIdx.x] || s_bz[o] < s_bz[threadIdx.x])) s_bz[threadIdx.x] = s_bz[o];
+      s_i[threadIdx.x] |= s_i[o];
+    }
+    __syncthreads();
+  }
+  const double minZ = s_bz[0];
+  const int have = s_i[0];
+  y1 = s_y1[0];
+  xm = s_xm[0];
+  __syncthreads();
+  // pmZ = find(pset2(3,:) == minZ) over ALL points; the first one (:22-23)
+  int first = 0x7fffffff;
+  if (have)
+    for (int i = threadIdx.x; i < N; i += blockDim.x)
+      if (yb[3 * i + 2] == minZ) {
+        first = i;
+        break;
+      }
+  s_i[threadIdx.x] = first;
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) {
+    if (threadIdx.x < off) s_i[threadIdx.x] = min(s_i[threadIdx.x], s_i[threadIdx.x + off]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    PairMeta m;
+    const int j = s_i[0];
+    if (have && j != 0x7fffffff) {
+      const double x = yb[3 * j], y = yb[3 * j + 1], z = yb[3 * j + 2];
+      m.thr = 0.001 * sqrt((x * x + y * y) + z * z);  // :23, :70
+    } else {
+      m.thr = -1.0;  // no point farther than 0.4 m: the reference errors at :22 (status 5)
+    }
+    m.thr2 = __double2float_rn(m.thr);
+    m.y1max = y1;
+    m.xmax = xm;
+    m.N = N;
+    m.pad = (int32_t)(((long long)N * (N + 1)) / 2);
+    meta[p] = m;
+  }
+}
+
+constexpr int DY_MAX_DRAWS = 1000;
+
+__device__ __forceinline__ int dy_draw(uint64_t seed, uint32_t pair, uint32_t hyp, int j, int pnum) {
+  const uint64_t x = splitmix64(seed ^ ((uint64_t)pair * 0x9E3779B97F4A7C15ULL) ^
+                                ((uint64_t)hyp * 0xD1B54A32D192ED03ULL) ^
+                                ((uint64_t)(j + 1) * 0x8CB92BA72F3D8DD7ULL));
+  const double u = (double)(x >> 11) * 0x1.0p-53;
+  return (int)round((double)(pnum - 1) * u + 1.0) - 1;  // round((pnum-1)*rand+1), 0-based
+}
+
+// one thread per (pair, hypothesis): num_rs(1..4) of ransac_dr_ye.m:28-48, 0-based, in draw order
+__global__ void __launch_bounds__(256) k_dy_sample(const PairMeta* __restrict__ meta,
+                                                   const int32_t* __restrict__ match, int Nmax, uint64_t seed,
+                                                   uint32_t pair_id0, int H, int32_t* __restrict__ samples) {
+  const int p = blockIdx.y;
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= H) return;
+  const int N = meta[p].N;
+  int4 out = make_int4(0, 0, 0, 0);
+  if (N >= 4) {
+    const int32_t* mt = match ? match + 2 * (size_t)p * Nmax : nullptr;
+    auto M1 = [&](int i) { return mt ? mt[2 * i] : i; };
+    auto M2 = [&](int i) { return mt ? mt[2 * i + 1] : i; };
+    const uint32_t pr = pair_id0 + (uint32_t)p;
+    int j = 0;
+    int n1 = dy_draw(seed, pr, h, j++, N), n2 = dy_draw(seed, pr, h, j++, N);
+    int n3 = dy_draw(seed, pr, h, j++, N), n4 = dy_draw(seed, pr, h, j++, N);
+    // :33-35: all three flags come from the FIRST draws
+    bool d1 = M1(n1) == M1(n2) || M2(n1) == M2(n2);
+    bool d2 = M1(n1) == M1(n3) || M1(n2) == M1(n3) || M2(n1) == M2(n3) || M2(n2) == M2(n3);
+    bool d3 = M1(n1) == M1(n4) || M1(n2) == M2(n4) || M1(n3) == M1(n4) || M2(n1) == M1(n4) || M2(n2) == M2(n4) ||
+              M2(n3) == M2(n4);
+    while ((n2 == n1 || d1) && j < DY_MAX_DRAWS) {
+      n2 = dy_draw(seed, pr, h, j++, N);
+      d1 = M1(n1) == M1(n2) || M2(n1) == M2(n2);
+    }
+    while ((n3 == n1 || n3 == n2 || d2) && j < DY_MAX_DRAWS) {
+      n3 = dy_draw(seed, pr, h, j++, N);
+      d2 = M1(n1) == M1(n3) || M1(n2) == M1(n3) || M2(n1) == M2(n3) || M2(n2) == M2(n3);
+    }
+    while ((n4 == n1 || n4 == n2 || n4 == n3 || d3) && j < DY_MAX_DRAWS) {
+      n4 = dy_draw(seed, pr, h, j++, N);
+      d3 = M1(n1) == M1(n4) || M1(n2) == M2(n4) || M1(n3) == M1(n4) || M2(n1) == M1(n4) || M2(n2) == M2(n4) ||
+           M2(n3) == M2(n4);
+    }
+    out = make_int4(n1, n2, n3, n4);
+  }
+  reinterpret_cast<int4*>(samples)[(size_t)p * H + h] = out;
+}
+
+__device__ __forceinline__ int dy_rst(int pnum, int max_iteration) {  // min(700, nchoosek(pnum,4)) (:162)
+  if (pnum < 4) return 0;
+  const double c = ((double)pnum * (pnum - 1) / 2.0) * ((double)(pnum - 2) * (pnum - 3) / 12.0);
+  return c < (double)max_iteration ? (int)c : max_iteration;
+}
+
+struct DySelShared {
+  double scratch[SEL_THREADS];
+  unsigned long long key[SEL_THREADS / 32];
+  double Rt[12];
+  int st;
+};
+
+__global__ void __launch_bounds__(SEL_THREADS)
+k_dy_select(const PairMeta* __restrict__ meta, const double* __restrict__ Ya, const double* __restrict__ Yb, int Nmax,
+            const int32_t* __restrict__ samples, int H, int max_iteration, const int32_t* __restrict__ tab,
+            const int32_t* __restrict__ counts, pre3_pair_result* __restrict__ res, uint8_t* __restrict__ masks,
+            uint8_t* __restrict__ mask_scratch, pre3_dr_ye_stat* __restrict__ stat,
+            int32_t* __restrict__ counts_out) {
+  __shared__ DySelShared sh;
+  const int p = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const PairMeta m = meta[p];
+  const int N = m.N;
+  const double* ya = Ya + (size_t)p * Nmax * 3;
+  const double* yb = Yb + (size_t)p * Nmax * 3;
+  uint8_t* mask = masks ? masks + (size_t)p * Nmax : mask_scratch + (size_t)p * Nmax;
+  const int32_t* cnt = counts + (size_t)p * H;
+  const int rst = dy_rst(N, max_iteration);
+  const int L = min(rst, H);
+  int status = 0;
+  if (N < 4) status = 1;
+  else if (m.thr < 0.0) status = 5;
+  if (counts_out)
+    for (int s = tid; s < H; s += SEL_THREADS) counts_out[(size_t)p * H + s] = (status == 0 && s < L) ? cnt[s] : -1;
+  if (masks)
+    for (int i = tid; i < Nmax; i += SEL_THREADS) mask[i] = 0;
+  pre3_dr_ye_stat sd;
+  sd.error_mean = sd.error_std = 0.0;
+  sd.dist = status == 0 ? m.thr / 0.001 : 0.0;
+  sd.n_iteration_ransac = 0;
+  sd.n_loops = status == 0 ? L : 0;
+  if (status != 0) {
+    if (tid == 0) {
+      result_init(res + p, status, 0, N, status == 1 ? 0.0 : m.thr);
+      if (stat) stat[p] = sd;
+    }
+    return;
+  }
+  // first maximum of tmp_cnum(1..L): max over the key (count << 32 | ~index)
+  unsigned long long key = 0ull;
+  for (int s = tid; s < L; s += SEL_THREADS) {
+    const unsigned long long k = ((unsigned long long)(uint32_t)cnt[s] << 32) | (uint32_t)(0xFFFFFFFFu - (uint32_t)s);
+    key = k > key ? k : key;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const unsigned long long o = __shfl_xor_sync(0xffffffffu, key, off);
+    key = o > key ? o : key;
+  }
+  if (lane == 0) sh.key[warp] = key;
+  __syncthreads();
+  key = sh.key[0];
+  for (int w = 1; w < SEL_THREADS / 32; ++w) key = sh.key[w] > key ? sh.key[w] : key;
+  const int maxc = L > 0 ? (int)(key >> 32) : 0;
+  const int win = L > 0 ? (int)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFu)) : -1;
+  // nIterations after the last update (:175-178) depends on the final maxCNUM only; never updated if it stays 0
+  int nit = rst;
+  if (maxc > 0) nit = min(rst, tab[m.pad + min(maxc, N)]);
+  sd.n_iteration_ransac = nit;
+  if (maxc < 3) {  // :187-194 "no consensus found, ransac fails"
+    if (tid == 0) {
+      result_init(res + p, 4, L, N, m.thr);
+      res[p].best_fit = maxc;
+      res[p].best_sample = win;
+      res[p].best_iter = win + 1;
+      res[p].n_iter = nit;
+      if (stat) stat[p] = sd;
+    }
+    return;
+  }
+  // winner: fit again (every thread, same result), support set
+  int idx[4];
+  {
+    const int32_t* sp = samples + ((size_t)p * H + win) * 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) idx[i] = min(max(sp[i], 0), N - 1);
+  }
+  Rigid f;
+  {
+    auto get = [&](int i, double* a, double* b) {
+      const int j = idx[i];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        a[r] = ya[3 * j + r];
+        b[r] = yb[3 * j + r];
+      }
+    };
+    fit_kabsch<4>(4, get, f);
+  }
+  for (int i = tid; i < N; i += SEL_THREADS) mask[i] = residual_sq(f.R, f.t, ya + 3 * i, yb + 3 * i) < m.thr ? 1 : 0;
+  __syncthreads();
+  // refit with find_transform_matrix_dr_ye (threshold 1e-14, :211)
+  Rigid rf;
+  const int st = block_refit(PRE3_METHOD_SVD, ya, yb, mask, N, sh.scratch, rf, 0.00000000000001);
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) sh.Rt[i] = rf.R[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) sh.Rt[9 + i] = rf.t[i];
+    sh.st = st;
+  }
+  __syncthreads();
+  // ErrorRANSAC_Norm over the support set: mean, std (n - 1) (:212-215)
+  double sum = 0.0;
+  for (int i = tid; i < N; i += SEL_THREADS)
+    if (mask[i]) sum += residual_norm(sh.Rt, sh.Rt + 9, ya + 3 * i, yb + 3 * i);
+  sum = block_sum(sum, sh.scratch);
+  const double mean = sum / (double)maxc;
+  double ss = 0.0;
+  for (int i = tid; i < N; i += SEL_THREADS)
+    if (mask[i]) {
+      const double d = residual_norm(sh.Rt, sh.Rt + 9, ya + 3 * i, yb + 3 * i) - mean;
+      ss += d * d;
+    }
+  ss = block_sum(ss, sh.scratch);
+  if (tid == 0) {
+    pre3_pair_result* out = res + p;
+    out->status = 0;
+    out->state = sh.st;
+    out->best_fit = maxc;
+    out->best_sample = win;
+    out->best_iter = win + 1;
+    out->n_iter = nit;
+    out->n_consumed = L;
+    out->n_matches = N;
+    out->thr = m.thr;
+    out->error_sum = sum;
+    store_colmajor(out->R, sh.Rt);
+    for (int i = 0; i < 3; ++i) out->T[i] = sh.Rt[9 + i];
+    store_colmajor(out->R_hyp, f.R);
+    for (int i = 0; i < 3; ++i) out->T_hyp[i] = f.t[i];
+    sd.error_mean = mean;
+    sd.error_std = maxc > 1 ? sqrt(ss / (double)(maxc - 1)) : 0.0;
+    if (stat) stat[p] = sd;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
@@ -1343,7 +1642,7 @@ void ransac_carve(pre3_ctx* ctx, RansacBuffers& b, int H) {
 
 int ensure_adaptive_table(pre3_ctx* ctx, const pre3_ransac_opts& o, int Nmax) {
   if (!o.adaptive) return PRE3_OK;
-  const int mult = o.method == PRE3_METHOD_SVD ? 5 : 1;
+  const int mult = o.method == PRE3_METHOD_HORN ? 1 : 5;  // x5: RANSAC_CALC_VER2.m:139, vodometry_dr_ye.m:177
   if (ctx->d_tab && ctx->tab_k == o.k && ctx->tab_mult == mult && ctx->tab_nmax >= Nmax &&
       ctx->tab_maxit == o.max_iteration)
     return PRE3_OK;
@@ -1403,6 +1702,8 @@ static int launch_eval_mode(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ra
                                                          hend, stop, Rin, Tin, b.counts, b.states)
   if (MODE == 2) {
     PRE3_EVAL(1);
+  } else if (MODE == 3) {
+    PRE3_EVAL(4);
   } else {
     switch (o.k) {
       case 3: PRE3_EVAL(3); break;
@@ -1522,6 +1823,46 @@ int launch_select(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts&
                                                      dres, dmasks, b.Nmax, scratch);
   count_launch(ctx, 3);
   PRE3_CUDA(cudaGetLastError());
+  return PRE3_OK;
+}
+
+// The code_from_dr_ye variant on device buffers.  The selection scratch of the VER2 path (3 x 8 P H bytes) is
+// not needed here; its first 16 P H bytes hold the seeded sample sets.
+int launch_dr_ye(pre3_ctx* ctx, RansacBuffers& b, const pre3_ransac_opts& o, const int32_t* dmatch,
+                 pre3_pair_result* dres, uint8_t* dmasks, pre3_dr_ye_stat* dstat, int32_t* dcounts_out) {
+  if (b.P <= 0) return PRE3_OK;
+  if (o.k != 4) return fail(ctx, PRE3_ERR_ARG, "the dr_ye variant draws 4 matches per hypothesis (ransac_dr_ye.m:28)");
+  const int H = std::max(o.H, 0);
+  const size_t PH = (size_t)b.P * std::max(H, 1);
+  if (PH >= ((size_t)1 << 31)) return fail(ctx, PRE3_ERR_ARG, "pairs x sample sets must stay below 2^31");
+  uint8_t* scratch = ws_take<uint8_t>(ctx, (size_t)b.P * b.Nmax);
+  int32_t* gen = ws_take<int32_t>(ctx, 4 * PH);
+  pre3_ransac_opts oa = o;
+  oa.adaptive = 1;
+  PRE3_TRY(ensure_adaptive_table(ctx, oa, b.Nmax));
+  {
+    Span span__(ctx, T_PREP);
+    k_dy_prep<<<b.P, 256, 0, ctx->stream>>>(b.Ya, b.Yb, b.n_corr, b.Nmax, b.meta, b.Ya4, b.Yb4);
+    count_launch(ctx);
+    if (!b.samples && H > 0) {
+      k_dy_sample<<<dim3((H + 255) / 256, b.P), 256, 0, ctx->stream>>>(b.meta, dmatch, b.Nmax, o.seed, b.pair_id0, H,
+                                                                      gen);
+      count_launch(ctx);
+      b.samples = gen;
+    }
+    PRE3_CUDA(cudaGetLastError());
+  }
+  // every pair runs min(700, nchoosek(pnum,4)) <= max_iteration iterations: the sets beyond are never read
+  const int Hrun = std::min(H, o.max_iteration);
+  if (Hrun > 0) PRE3_TRY(launch_eval_mode<3>(ctx, b, o, 0, H, 0, Hrun, nullptr, nullptr, nullptr));
+  {
+    Span span__(ctx, T_SELECT);
+    k_dy_select<<<b.P, SEL_THREADS, 0, ctx->stream>>>(b.meta, b.Ya, b.Yb, b.Nmax, b.samples, H, o.max_iteration,
+                                                      ctx->d_tab, b.counts, dres, dmasks, scratch, dstat,
+                                                      dcounts_out);
+    count_launch(ctx);
+    PRE3_CUDA(cudaGetLastError());
+  }
   return PRE3_OK;
 }
 

@@ -43,6 +43,10 @@ int launch_eval_waves(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_o
 int eval_wave_ends(const pre3_ransac_opts& o, int32_t* ends, int cap);
 int launch_select(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts& o, pre3_pair_result* dres,
                   uint8_t* dmasks, int32_t* dcounts_out, int8_t* dstates_out);
+// M/code_from_dr_ye variant (vodometry_dr_ye.m:147-220); dmatch: P x Nmax x 2 match ids or nullptr; b.samples:
+// P x H x 4 explicit sets or nullptr (seeded sampler of ransac_dr_ye.m:28-48)
+int launch_dr_ye(pre3_ctx* ctx, RansacBuffers& b, const pre3_ransac_opts& o, const int32_t* dmatch,
+                 pre3_pair_result* dres, uint8_t* dmasks, pre3_dr_ye_stat* dstat, int32_t* dcounts_out);
 int ensure_adaptive_table(pre3_ctx* ctx, const pre3_ransac_opts& o, int Nmax);
 
 // stage-wise entry points

@@ -171,6 +171,110 @@ def Calculate_V_Omega_RANSAC_my_version(DataPre, DataCurrent, **kw):
 
 
 # ---------------------------------------------------------------------------------------
+# the code_from_dr_ye variant: what the live EKF calls (M/fv.m:47)
+# ---------------------------------------------------------------------------------------
+def _mround(v):
+    """MATLAB round() for the positive pixel coordinates used here (half away from zero)."""
+    return np.floor(np.asarray(v, np.float64) + 0.5).astype(np.int64)
+
+
+def confidence_filtering(frm, des, confidence_map):
+    """[frm, des] = confidence_filtering(frm, des, confidence_map)
+    (M/code_from_dr_ye/confidence_filtering.m:1-13): drop features whose pixel confidence is below half the
+    maximum.  Host-side index bookkeeping (K <= a few hundred lookups), no device work."""
+    frm = np.asarray(frm, np.float64)
+    cm = np.asarray(confidence_map)
+    keep = cm[_mround(frm[1]) - 1, _mround(frm[0]) - 1] >= 0.5 * cm.max()
+    return frm[:, keep], np.asarray(des)[:, keep]
+
+
+def _pset(frm, idx, x, y, z):
+    """pset(:,i) = [-x(ROW,COL); -y(ROW,COL); z(ROW,COL)] at the rounded frame position of feature idx(i)
+    (M/code_from_dr_ye/ransac_dr_ye.m:13-19, vodometry_dr_ye.m:204-210)."""
+    col = _mround(frm[0, idx]) - 1
+    row = _mround(frm[1, idx]) - 1
+    return np.stack([-np.asarray(x, np.float64)[row, col], -np.asarray(y, np.float64)[row, col],
+                     np.asarray(z, np.float64)[row, col]])
+
+
+def R2e(R):
+    """e = [roll; pitch; yaw] (M/slamToolbox_11_02_18/FrameTransforms/Rotations/R2e.m:31-35)."""
+    R = np.asarray(R, np.float64)
+    return np.array([np.arctan2(R[2, 1], R[2, 2]), np.arcsin(-R[2, 0]), np.arctan2(R[1, 0], R[0, 0])])
+
+
+def vodometry_dr_ye(Data1, Data2, *, confidence_map=False, samples=None, seed=0, pair_id=0, max_iteration=700):
+    """[rot, phi, theta, psi, trans, error, pnum, op_num, sta, op_pset1, op_pset2, RANSAC_STAT] =
+    vodometry_dr_ye(file1, file2) (M/code_from_dr_ye/vodometry_dr_ye.m:5-247) from the point where the two frames
+    have been read and SIFT has run (:31,:67,:114,:116 stay with the caller: file I/O and SIFT extraction are not
+    on this path).  Data: dict with 'frm' (4 x K as sift() returns it, 0-based pixel positions; :73-74 add 1),
+    'des' (128 x K), 'x', 'y', 'z' (144 x 176 maps) and optionally 'confidence_map'.
+    Descriptor matching (:139), the RANSAC iterations (:162-183 with ransac_dr_ye.m as the body), selection (:184),
+    the refit (:211) and the residual statistics (:212-215) run in libpre3.so.
+    samples: 4 x H, 1-based draws num_rs(1..4) per iteration (optional; else the seeded sampler)."""
+    ctx = context()
+    frm1 = np.array(Data1["frm"], np.float64)
+    frm2 = np.array(Data2["frm"], np.float64)
+    des1, des2 = np.asarray(Data1["des"]), np.asarray(Data2["des"])
+    stat = {"nFeatures1": frm1.shape[1], "nFeatures2": frm2.shape[1], "nMatches": 0, "nIterationRansac": 0,
+            "InlierRatio": 0, "nSupport": 0, "ErrorMean": 0, "ErrorStd": 0, "SolutionState": 0}
+    frm1[:2] += 1  # :73-74
+    frm2[:2] += 1  # :119-121
+    if confidence_map:  # myCONFIG.FLAGS.CONFIDENCE_MAP (:80-82, :123-125)
+        frm1, des1 = confidence_filtering(frm1, des1, Data1["confidence_map"])
+        frm2, des2 = confidence_filtering(frm2, des2, Data2["confidence_map"])
+    stat["nF1_Confidence_Filtered"], stat["nF2_Confidence_Filtered"] = frm1.shape[1], frm2.shape[1]
+    match = siftmatch(des1, des2)  # :139
+    pnum = match.shape[1]
+    stat["nMatches"] = pnum
+    fail = (np.zeros((3, 3)), 0.0, 0.0, 0.0, 0.0)
+    if pnum < 4:  # :152-160
+        stat["SolutionState"] = 4
+        return (*fail, 1, pnum, 0, 0, np.zeros((3, 0)), np.zeros((3, 0)), stat)
+    m0 = match.astype(np.int64) - 1
+    pset1 = _pset(frm1, m0[0], Data1["x"], Data1["y"], Data1["z"])
+    pset2 = _pset(frm2, m0[1], Data2["x"], Data2["y"], Data2["z"])
+    s0 = None
+    if samples is not None:
+        s0 = np.ascontiguousarray(np.asarray(samples).T.astype(np.int32) - 1)[None]  # (1,H,4) 0-based
+    res, masks, st, _ = ctx.vodometry_dr_ye_batch(np.ascontiguousarray(pset1.T)[None], np.ascontiguousarray(pset2.T)[None],
+                                                  match=np.ascontiguousarray(m0.T.astype(np.int32))[None], samples=s0,
+                                                  max_iteration=max_iteration,
+                                                  H=(s0.shape[1] if s0 is not None else max_iteration), seed=seed)
+    r, st = res[0], st[0]
+    if r["status"] == 5:
+        raise MexError("ransac_dr_ye: no point farther than 0.4 m (min of an empty set, ransac_dr_ye.m:21-22)")
+    stat["nIterationRansac"] = int(st["n_iteration_ransac"])
+    op_num = int(r["best_fit"])
+    if r["status"] == 4:  # :187-194
+        stat["SolutionState"] = 4
+        return (*fail, 0, pnum, op_num, 0, np.zeros((3, 0)), np.zeros((3, 0)), stat)
+    mask = masks[0, :pnum].astype(bool)
+    op_pset1, op_pset2 = pset1[:, mask], pset2[:, mask]
+    rot = np.array(r["R"]).reshape(3, 3).T.copy()
+    trans = np.array(r["T"]).reshape(3, 1)
+    sta = int(r["state"])
+    stat.update(nSupport=op_num, ErrorMean=float(st["error_mean"]), ErrorStd=float(st["error_std"]), SolutionState=sta,
+                GoodFrames1=frm1[:, m0[0, mask]], GoodDescriptor1=des1[:, m0[0, mask]],
+                GoodFrames2=frm2[:, m0[1, mask]], GoodDescriptor2=des2[:, m0[1, mask]],
+                InlierRatio=op_num / pnum * 100)
+    if sta < 1:  # :230-235
+        return rot, 0.0, 0.0, 0.0, 0.0, 2, pnum, op_num, sta, op_pset1, op_pset2, stat
+    e = R2e(rot)  # :237-240
+    return rot, e[0], e[1], e[2], trans, 0, pnum, op_num, sta, op_pset1, op_pset2, stat
+
+
+def Calculate_V_Omega_RANSAC_dr_ye(Data1, Data2, **kw):
+    """[T, q, R, sta, RANSAC_STAT] = Calculate_V_Omega_RANSAC_dr_ye(stepPre, stepCurrent)
+    (M/code_from_dr_ye/Calculate_V_Omega_RANSAC_dr_ye.m:19-50; the result cache :12-32 stays with the caller)."""
+    rot, _, _, _, trans, _, _, _, sta, _, _, stat = vodometry_dr_ye(Data1, Data2, **kw)
+    if sta != 1:  # :41-44
+        R = np.eye(3)
+        return np.zeros((3, 1)), R2q(R).reshape(4, 1), R, sta, stat
+    return trans, R2q(rot).reshape(4, 1), rot, sta, stat
+
+
+# ---------------------------------------------------------------------------------------
 # config 4: the 1-point-RANSAC EKF hypothesis path
 # ---------------------------------------------------------------------------------------
 StatData = {}  # the reference's global (M/ransac_hypotheses.m:34,84-85)

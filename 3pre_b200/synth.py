@@ -85,6 +85,14 @@ def make_samples(seed, H, N, k):
     return np.sort(idx, axis=1).astype(np.int32)
 
 
+def make_draws(seed, H, N, k=4):
+    """Draws (H,k) int32, 0-based, k distinct indices per row in DRAW order (not sorted) -- what
+    num_rs(1..4) of M/code_from_dr_ye/ransac_dr_ye.m:28-48 holds once its re-draw loops have ended."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    keys = rng.random((H, N))
+    return np.argsort(keys, axis=1)[:, :k].astype(np.int32)
+
+
 @dataclass
 class FramePair:
     desc1: np.ndarray  # (K1,128) float64 (float32-valued)  previous frame

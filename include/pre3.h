@@ -51,6 +51,9 @@ extern "C" {
 /* RANSAC flavours */
 #define PRE3_METHOD_SVD 0  /* RANSAC_CALC_VER2.m: find_transform_matrix fit/refit, threshold override :69-72, x5 adaptive rule :139 */
 #define PRE3_METHOD_HORN 1 /* RANSAC_CALC_VER_test.m: absoluteOrientationQuaternion fit :71 / refit :152, options threshold, rule :102 */
+#define PRE3_METHOD_DR_YE 2 /* code_from_dr_ye/vodometry_dr_ye.m:147-220 + ransac_dr_ye.m: 4 matches per hypothesis in draw order,
+                               squared-distance bound 0.001*dist, every hypothesis scored, min(MaxIteration=700, C(n,4))
+                               iterations, first maximum wins, refit with find_transform_matrix_dr_ye (1e-14) */
 
 /* matching engines (pre3_set_match_engine) */
 #define PRE3_MATCH_AUTO 0   /* tcgen05 proposal GEMM + exact rescore when ND==128, else exact */
@@ -194,7 +197,44 @@ PRE3_API int pre3_ransac_batch_dev(pre3_ctx *ctx, const double *dYa, const doubl
                           const int32_t *dn_corr, int P, int Nmax, const pre3_ransac_opts *opts,
                           const int32_t *dsamples, pre3_pair_result *dres, uint8_t *dmasks);
 
+/* ---- the code_from_dr_ye variant ---------------------------------
+ * The RANSAC part of [rot,phi,theta,psi,trans,error,pnum,op_num,sta,op_pset1,op_pset2,RANSAC_STAT] =
+ * vodometry_dr_ye(file1,file2) (M/code_from_dr_ye/vodometry_dr_ye.m:147-220, loop body ransac_dr_ye.m:20-71),
+ * the variant the live EKF calls (M/fv.m:47 -> Calculate_V_Omega_RANSAC_dr_ye.m:19-22), for P match sets.
+ * Ya = pset1 (frame 1), Yb = pset2 (frame 2): pset1 ~ rot*pset2 + trans; opts->method is taken as
+ * PRE3_METHOD_DR_YE, opts->k must be 4, opts->max_iteration = 700 reproduces :162.
+ * match: P x (2 x Nmax) feature ids [k1;k2] of every match (what siftmatch returned; only compared for
+ * equality by the sampler, ransac_dr_ye.m:33-48) or NULL (match i = [i;i]).
+ * samples: P x (4 x H) explicit draws num_rs(1..4) (0-based, draw order) or NULL: the reference's sampler
+ * run on a seeded uniform stream (opts->seed, pair id).
+ * pre3_pair_result fields in this mode: status 0 ok / 1 pnum < 4 (:152) / 4 no consensus, op_num < 3 (:187) /
+ * 5 no point farther than 0.4 m (ransac_dr_ye.m:21-22 raises an error); state = sta of the refit (:211);
+ * best_fit = op_num; best_sample = rs_ind - 1; n_consumed = iterations executed; n_iter =
+ * RANSAC_STAT.nIterationRansac (:216); thr = 0.001*dist (bound on the SQUARED distance, ransac_dr_ye.m:70);
+ * error_sum = sum of the residual norms over the support set after the refit (:212-213).
+ * masks: P x Nmax (support set of the winner) or NULL; stat: P or NULL; counts: P x H (tmp_cnum, -1 beyond
+ * the executed iterations) or NULL. */
+typedef struct {
+  double error_mean;          /* RANSAC_STAT.ErrorMean (:214) */
+  double error_std;           /* RANSAC_STAT.ErrorStd  (:215, normalised by n - 1) */
+  double dist;                /* ransac_dr_ye.m:23 */
+  int32_t n_iteration_ransac; /* RANSAC_STAT.nIterationRansac (:216) */
+  int32_t n_loops;            /* iterations executed: min(700, nchoosek(pnum,4), H) */
+} pre3_dr_ye_stat;
+
+PRE3_API int pre3_vodometry_dr_ye_batch(pre3_ctx *ctx, const double *Ya, const double *Yb, const int32_t *n_corr,
+                               const int32_t *match, int P, int Nmax, const pre3_ransac_opts *opts,
+                               const int32_t *samples, pre3_pair_result *res, uint8_t *masks,
+                               pre3_dr_ye_stat *stat, int32_t *counts);
+PRE3_API int pre3_vodometry_dr_ye_batch_dev(pre3_ctx *ctx, const double *dYa, const double *dYb,
+                                   const int32_t *dn_corr, const int32_t *dmatch, int P, int Nmax,
+                                   const pre3_ransac_opts *opts, const int32_t *dsamples, uint32_t pair_id0,
+                                   pre3_pair_result *dres, uint8_t *dmasks, pre3_dr_ye_stat *dstat,
+                                   int32_t *dcounts);
+
 /* ---- whole frame pairs: match -> gather -> RANSAC ------------------------------------
+ * (opts->method = PRE3_METHOD_DR_YE runs the variant above on the matches of every pair: match ids =
+ * the siftmatch output, seeded sampler.)
  * What SIFT_match_save.m:33-53 does per pair (and RANSAC_CALC_SAVE_SR4000.m /
  * Calculate_V_Omega_RANSAC_my_version.m around it), for P pairs in one call:
  *   matches = siftmatch(desc1_p, desc2_p); Ya = xyz1(:,matches(1,:)); Yb = xyz2(:,matches(2,:));

@@ -228,6 +228,99 @@ def pair(desc1, desc2, xyz1, xyz2, seed, pair_id, H=2000, ratio=1.5, method=0, k
     return pairs[:n].copy(), _unpack(res, mask[:n].astype(bool))
 
 
+# ---------------------------------------------------------------------------------------------------
+# code_from_dr_ye variant (oracle/pre3_oracle_dr_ye.c)
+# ---------------------------------------------------------------------------------------------------
+class DrYeResult(C.Structure):
+    _fields_ = [("status", C.c_int32), ("state", C.c_int32), ("op_num", C.c_int32), ("best_sample", C.c_int32),
+                ("n_loops", C.c_int32), ("n_iteration_ransac", C.c_int32), ("pnum", C.c_int32), ("pad", C.c_int32),
+                ("thr", C.c_double), ("error_sum", C.c_double), ("error_mean", C.c_double), ("error_std", C.c_double),
+                ("R", C.c_double * 9), ("T", C.c_double * 3), ("R_hyp", C.c_double * 9), ("T_hyp", C.c_double * 3)]
+
+
+@dataclass
+class DrYe:
+    status: int
+    state: int
+    op_num: int
+    best_sample: int
+    n_loops: int
+    n_iteration_ransac: int
+    pnum: int
+    thr: float
+    error_sum: float
+    error_mean: float
+    error_std: float
+    R: np.ndarray
+    T: np.ndarray
+    R_hyp: np.ndarray
+    T_hyp: np.ndarray
+    mask: np.ndarray
+    counts: np.ndarray
+
+
+def dr_ye_sample(seed, pair, hyp, match, pnum):
+    """ransac_dr_ye.m:28-48 on the seeded stream.  match (pnum,2) int32 or None.  Returns 4 0-based indices."""
+    out = np.zeros(4, np.int32)
+    mt = None if match is None else np.ascontiguousarray(match, np.int32)
+    L = lib()
+    L.orc_dr_ye_sample.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(C.c_int32), C.c_int,
+                                   C.POINTER(C.c_int32)]
+    L.orc_dr_ye_sample.restype = None
+    L.orc_dr_ye_sample(int(seed), int(pair), int(hyp), _p(mt, C.c_int32) if mt is not None else None, int(pnum),
+                       _p(out, C.c_int32))
+    return out
+
+
+def dr_ye_sample_stream(stream, match, n_sets):
+    """The sampler on a recorded uniform stream; returns (sets (n_sets,4) 0-based, uniforms consumed)."""
+    u = _f64(stream)
+    mt = np.ascontiguousarray(match, np.int32)
+    out = np.zeros((n_sets, 4), np.int32)
+    L = lib()
+    L.orc_dr_ye_sample_stream.argtypes = [C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_int32), C.c_int, C.c_int,
+                                          C.POINTER(C.c_int32)]
+    L.orc_dr_ye_sample_stream.restype = C.c_int
+    used = L.orc_dr_ye_sample_stream(_p(u, C.c_double), u.size, _p(mt, C.c_int32), mt.shape[0], int(n_sets),
+                                     _p(out, C.c_int32))
+    return out, int(used)
+
+
+def dr_ye_dist(Yb):
+    yb = _f64(Yb)
+    L = lib()
+    L.orc_dr_ye_dist.argtypes = [C.POINTER(C.c_double), C.c_int]
+    L.orc_dr_ye_dist.restype = C.c_double
+    return float(L.orc_dr_ye_dist(_p(yb, C.c_double), yb.shape[0]))
+
+
+def vodometry_dr_ye(Ya, Yb, match=None, samples=None, max_iteration=700, H=700, seed=0, pair=0):
+    """RANSAC part of vodometry_dr_ye.m:147-220.  Ya = pset1, Yb = pset2 (N,3); match (N,2) | None;
+    samples (H,4) 0-based draws | None (seeded)."""
+    ya, yb = _f64(Ya), _f64(Yb)
+    N = ya.shape[0]
+    sm = None
+    if samples is not None:
+        sm = np.ascontiguousarray(samples, np.int32)
+        H = sm.shape[0]
+    mt = None if match is None else np.ascontiguousarray(match, np.int32)
+    res = DrYeResult()
+    mask = np.zeros(max(N, 1), np.uint8)
+    counts = np.zeros(max(H, 1), np.int32)
+    L = lib()
+    L.orc_vodometry_dr_ye.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int32), C.c_int,
+                                      C.c_int, C.c_int, C.POINTER(C.c_int32), C.c_uint64, C.c_uint32,
+                                      C.POINTER(DrYeResult), C.POINTER(C.c_uint8), C.POINTER(C.c_int32)]
+    L.orc_vodometry_dr_ye.restype = None
+    L.orc_vodometry_dr_ye(_p(ya, C.c_double), _p(yb, C.c_double), _p(mt, C.c_int32) if mt is not None else None, N,
+                          int(max_iteration), int(H), _p(sm, C.c_int32) if sm is not None else None, int(seed),
+                          int(pair), C.byref(res), _p(mask, C.c_uint8), _p(counts, C.c_int32))
+    return DrYe(res.status, res.state, res.op_num, res.best_sample, res.n_loops, res.n_iteration_ransac, res.pnum,
+                res.thr, res.error_sum, res.error_mean, res.error_std, np.array(res.R).reshape(3, 3),
+                np.array(res.T), np.array(res.R_hyp).reshape(3, 3), np.array(res.T_hyp), mask[:N].astype(bool),
+                counts[:H].copy())
+
+
 def R2q(R):
     r = _f64(R).reshape(9)
     q = np.zeros(4)

@@ -149,9 +149,21 @@ static double orc_det3(double m[3][3]) {
  *   - two or three sigma_j < 1e-11: state -1 (MATLAB: 1 or -1 by the same luck).
  *   - any non-finite entry: state 0 (round(mdet) is neither 1 nor -1, :38-42).
  */
+ORC_API int orc_find_transform_thr(const double *pset1, const double *pset2,
+                                   const int32_t *idx, int pnum, double threshold,
+                                   double *rot, double *trans);
+
 ORC_API int orc_find_transform(const double *pset1, const double *pset2,
                                const int32_t *idx, int pnum, double *rot,
                                double *trans) {
+  return orc_find_transform_thr(pset1, pset2, idx, pnum, 0.00000000001 /* :20 */, rot, trans);
+}
+
+/* threshold: 1e-11 in find_transform_matrix.m:20, 1e-14 in
+ * M/code_from_dr_ye/find_transform_matrix_dr_ye.m:19 (the only difference between the two files) */
+ORC_API int orc_find_transform_thr(const double *pset1, const double *pset2,
+                                   const int32_t *idx, int pnum, double threshold,
+                                   double *rot, double *trans) {
   double H[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
   double ct1[3] = {0, 0, 0}, ct2[3] = {0, 0, 0};
   for (int i = 0; i < pnum; ++i) { /* sum(pset,2) :11 */
@@ -187,7 +199,6 @@ ORC_API int orc_find_transform(const double *pset1, const double *pset2,
   int nsmall = 0, jsmall = -1;
   if (finite) {
     orc_svd3_cols(A, V, sig);
-    const double threshold = 0.00000000001; /* :20 */
     for (int j = 0; j < 3; ++j)
       if (sig[j] < threshold) {
         ++nsmall;

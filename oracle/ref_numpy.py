@@ -11,8 +11,9 @@ from __future__ import annotations
 import numpy as np
 
 
-def find_transform_matrix(pset1, pset2):
-    """M/mex_files/RANSAC_CALCULATION/find_transform_matrix.m:9-42 (pset1 ~ rot*pset2 + trans)."""
+def find_transform_matrix(pset1, pset2, threshold=1e-11):
+    """M/mex_files/RANSAC_CALCULATION/find_transform_matrix.m:9-42 (pset1 ~ rot*pset2 + trans);
+    threshold=1e-14 is M/code_from_dr_ye/find_transform_matrix_dr_ye.m."""
     p1 = np.asarray(pset1, float).T  # 3 x n
     p2 = np.asarray(pset2, float).T
     n = p2.shape[1]
@@ -30,7 +31,7 @@ def find_transform_matrix(pset1, pset2):
         rot = Xq
         return rot, ct1 - rot @ ct2, 1
     if round(mdet) == -1:
-        zn = np.nonzero(sv < 1e-11)[0]
+        zn = np.nonzero(sv < threshold)[0]
         if zn.size == 1:
             V[:, zn] = -V[:, zn]
             rot = V @ U.T
@@ -130,6 +131,84 @@ def ransac_ver2(Ya, Yb, samples, max_iteration=2000, adaptive=True, method=0, di
         _, R, T, _ = horn(Yb[mask], Ya[mask], False)
         st = 1
     return dict(R=R, T=T, state=st, best_fit=int(mx), best_sample=hs, mask=mask, n_iter=len(rec), thr=thr, error_sum=es[best])
+
+
+def dr_ye_sampler(match, rand):
+    """M/code_from_dr_ye/ransac_dr_ye.m:28-48, line by line.  match: (pnum,2) feature ids; rand(): a callable
+    returning the next uniform of the stream.  Returns the four 0-based match indices in draw order."""
+    m = np.asarray(match).T  # 2 x pnum, as in the reference
+    pnum = m.shape[1]
+
+    def draw():
+        v = (pnum - 1) * rand() + 1
+        return int(np.floor(v + 0.5)) - 1  # MATLAB round (half away from zero, v > 0), 0-based
+
+    n = [draw() for _ in range(4)]
+    d1 = (m[0, n[0]] == m[0, n[1]]) or (m[1, n[0]] == m[1, n[1]])
+    d2 = ((m[0, n[0]] == m[0, n[2]]) or (m[0, n[1]] == m[0, n[2]]) or (m[1, n[0]] == m[1, n[2]])
+          or (m[1, n[1]] == m[1, n[2]]))
+    d3 = ((m[0, n[0]] == m[0, n[3]]) or (m[0, n[1]] == m[1, n[3]]) or (m[0, n[2]] == m[0, n[3]])
+          or (m[1, n[0]] == m[0, n[3]]) or (m[1, n[1]] == m[1, n[3]]) or (m[1, n[2]] == m[1, n[3]]))
+    while n[1] == n[0] or d1:
+        n[1] = draw()
+        d1 = (m[0, n[0]] == m[0, n[1]]) or (m[1, n[0]] == m[1, n[1]])
+    while n[2] == n[0] or n[2] == n[1] or d2:
+        n[2] = draw()
+        d2 = ((m[0, n[0]] == m[0, n[2]]) or (m[0, n[1]] == m[0, n[2]]) or (m[1, n[0]] == m[1, n[2]])
+              or (m[1, n[1]] == m[1, n[2]]))
+    while n[3] == n[0] or n[3] == n[1] or n[3] == n[2] or d3:
+        n[3] = draw()
+        d3 = ((m[0, n[0]] == m[0, n[3]]) or (m[0, n[1]] == m[1, n[3]]) or (m[0, n[2]] == m[0, n[3]])
+              or (m[1, n[0]] == m[0, n[3]]) or (m[1, n[1]] == m[1, n[3]]) or (m[1, n[2]] == m[1, n[3]]))
+    return n
+
+
+def vodometry_dr_ye(Ya, Yb, samples, max_iteration=700):
+    """RANSAC part of M/code_from_dr_ye/vodometry_dr_ye.m:147-220 with ransac_dr_ye.m:20-71 as the loop body;
+    Ya = pset1, Yb = pset2 (N,3); samples (H,4) supplied draws.  LAPACK svd for the fits.  Returns a dict."""
+    from math import comb
+    Ya = np.asarray(Ya, float)
+    Yb = np.asarray(Yb, float)
+    pnum = Ya.shape[0]
+    out = {"status": 0, "op_num": 0, "best_sample": -1}
+    if pnum < 4:
+        out["status"] = 1
+        return out
+    nrm = np.sqrt(Yb[:, 2] ** 2 + Yb[:, 1] ** 2 + Yb[:, 0] ** 2)
+    far = nrm > 0.4
+    if not far.any():
+        out["status"] = 5
+        return out
+    minZ = Yb[far, 2].min()
+    j = np.nonzero(Yb[:, 2] == minZ)[0][0]
+    dist = np.sqrt(Yb[j, 0] ** 2 + Yb[j, 1] ** 2 + Yb[j, 2] ** 2)
+    rst = min(max_iteration, comb(pnum, 4))
+    L = min(rst, len(samples))
+    cnums = np.full(len(samples), -1, np.int64)
+    maxc, nit = 0, rst
+    for i in range(L):
+        s = np.asarray(samples[i])
+        rot, trans, _ = find_transform_matrix(Ya[s], Yb[s])
+        d = ((Yb @ rot.T + trans - Ya) ** 2).sum(1)
+        cnums[i] = int((d < 0.001 * dist).sum())
+        if cnums[i] > maxc:
+            maxc = cnums[i]
+            with np.errstate(divide="ignore"):
+                nit = 5 * np.ceil(np.log(0.01) / np.log(1 - (maxc / pnum) ** 4))
+    best = int(np.argmax(cnums[:L])) if L else -1
+    out.update(counts=cnums, best_sample=best, op_num=int(cnums[best]) if L else 0, thr=0.001 * dist, dist=dist,
+               n_loops=L, n_iteration_ransac=int(min(rst, nit)))
+    if out["op_num"] < 3:
+        out["status"] = 4
+        return out
+    s = np.asarray(samples[best])
+    rot, trans, _ = find_transform_matrix(Ya[s], Yb[s])
+    mask = ((Yb @ rot.T + trans - Ya) ** 2).sum(1) < 0.001 * dist
+    R, T, sta = find_transform_matrix(Ya[mask], Yb[mask], threshold=1e-14)
+    en = np.sqrt(((Yb[mask] @ R.T + T - Ya[mask]) ** 2).sum(1))
+    out.update(mask=mask, R=R, T=T, state=sta, R_hyp=rot, T_hyp=trans, error_mean=en.mean(),
+               error_std=en.std(ddof=1) if en.size > 1 else 0.0)
+    return out
 
 
 def rot_angle(Ra, Rb):

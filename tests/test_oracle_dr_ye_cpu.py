@@ -1,0 +1,132 @@
+"""CPU suite: the oracle of the code_from_dr_ye variant (oracle/pre3_oracle_dr_ye.c).
+
+PARITY UNPINNED: the reference holds no vectors for this path.  The C restatement (Jacobi fits, the
+operation order the CUDA kernels share) is checked against the independent numpy / LAPACK restatement
+(oracle/ref_numpy.py, committed as tests/golden/dr_ye.npz by tests/golden/make_golden_dr_ye.py), against
+planted motion, and on the loop / sampler semantics read off the .m files.
+`M/` = /root/reference/matlab_code/.
+"""
+import importlib
+import os
+from math import comb
+
+import numpy as np
+import pytest
+
+from oracle import ref_numpy as rn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(ROOT, "tests", "golden", "dr_ye.npz"))
+
+
+@pytest.mark.parametrize("name", ["a", "b", "c", "d"])
+def test_oracle_vs_golden(orc, gold, name):
+    Ya, Yb, draws = gold[f"{name}_Ya"], gold[f"{name}_Yb"], gold[f"{name}_draws"]
+    r = orc.vodometry_dr_ye(Ya, Yb, samples=draws, max_iteration=700)
+    status, op_num, best, n_loops, nit, state = gold[f"{name}_scalars"]
+    assert (r.status, r.op_num, r.best_sample, r.n_loops, r.n_iteration_ransac) == (status, op_num, best, n_loops, nit)
+    np.testing.assert_array_equal(r.counts, gold[f"{name}_counts"])  # tmp_cnum of every iteration
+    np.testing.assert_array_equal(r.mask, gold[f"{name}_mask"])
+    thr, mean, std = gold[f"{name}_stats"]
+    assert abs(r.thr - thr) < 1e-15 and abs(r.error_mean - mean) < 1e-9 and abs(r.error_std - std) < 1e-9
+    assert rn.rot_angle(r.R, gold[f"{name}_R"]) < 1e-9 and np.abs(r.T - gold[f"{name}_T"]).max() < 1e-9
+    assert r.state == state == 1
+
+
+def test_sampler_vs_golden_stream(orc, gold):
+    # ransac_dr_ye.m:28-48 incl. its mixed-row comparisons and stale duplicate flags, on recorded uniforms
+    sets, used = orc.dr_ye_sample_stream(gold["sampler_stream"], gold["sampler_match"], 200)
+    np.testing.assert_array_equal(sets, gold["sampler_sets"])
+    assert used == gold["sampler_stream"].size
+    m = gold["sampler_match"]
+    # the first two picks never share a feature (:37-40); later slots may, through the stale flags (:33-35)
+    assert (m[sets[:, 0], 0] != m[sets[:, 1], 0]).all() and (m[sets[:, 0], 1] != m[sets[:, 1], 1]).all()
+    assert (sets[:, 0] != sets[:, 1]).all() and (sets[:, 2] != sets[:, 0]).all() and (sets[:, 3] != sets[:, 2]).all()
+
+
+def test_seeded_sampler_is_a_pure_function(orc):
+    a = [orc.dr_ye_sample(9, 3, h, None, 50) for h in range(64)]
+    b = [orc.dr_ye_sample(9, 3, h, None, 50) for h in range(64)]
+    np.testing.assert_array_equal(a, b)
+    a = np.array(a)
+    assert a.min() >= 0 and a.max() < 50 and len({tuple(x) for x in a}) > 60
+    for row in a:  # identity match ids: the duplicate tests reduce to distinct indices
+        assert len(set(row)) == 4
+
+
+def test_threshold_rule(orc):
+    # ransac_dr_ye.m:20-23: min z over points FARTHER than 0.4 m, then the first point (any) with that z
+    Yb = np.array([[0.0, 0.0, 0.1],     # closer than 0.4 m: ignored by the min
+                   [3.0, 0.0, 0.9],     # not eligible? norm 3.13 > 0.4, z = 0.9
+                   [0.0, 0.0, 0.5],     # eligible, z = 0.5 -> minZ
+                   [2.0, 0.0, 0.5]])    # same z, later index
+    assert orc.dr_ye_dist(Yb) == 0.5
+    Yb2 = Yb.copy()
+    Yb2[0] = [0.0, 0.3, 0.5]            # closer than 0.4 m but z == minZ and first -> pmZ(1) picks it (:22)
+    assert abs(orc.dr_ye_dist(Yb2) - np.sqrt(0.3 ** 2 + 0.5 ** 2)) < 1e-16
+    assert orc.dr_ye_dist(Yb[:1]) < 0   # nothing farther than 0.4 m: the reference errors
+
+
+def test_loop_semantics(orc):
+    synth = importlib.import_module("3pre_b200.synth")
+    c = synth.make_correspondences(11, N=100, outlier_ratio=0.3)
+    draws = synth.make_draws(12, 900, 100)
+    r = orc.vodometry_dr_ye(c.Ya, c.Yb, samples=draws)
+    # `for i=1:min(rst,nIterations)` evaluates its range once: all min(700, C(n,4)) iterations run
+    # (vodometry_dr_ye.m:162-165) although nIterations drops (:175-178); the drop is only REPORTED (:216)
+    assert r.n_loops == 700 and (r.counts[:700] >= 0).all() and (r.counts[700:] == -1).all()
+    w = r.op_num / 100
+    assert r.n_iteration_ransac == min(700, int(5 * np.ceil(np.log(0.01) / np.log(1 - w ** 4)))) < 700
+    # first maximum wins (:184)
+    assert r.best_sample == int(np.argmax(r.counts[:700])) and r.op_num == r.counts[:700].max()
+    # small match sets: nchoosek(pnum,4) bounds the loop
+    r = orc.vodometry_dr_ye(c.Ya[:6], c.Yb[:6], samples=draws % 6)
+    assert r.n_loops == comb(6, 4) == 15
+    assert orc.vodometry_dr_ye(c.Ya[:3], c.Yb[:3], samples=draws % 3).status == 1     # :152-160
+    # perfect data: maxCNUM == pnum -> log(0) -> nIterations = 0 reported, loop still runs
+    Ya = c.Yb @ c.R.T + c.t
+    r = orc.vodometry_dr_ye(Ya, c.Yb, samples=draws)
+    assert r.op_num == 100 and r.n_iteration_ransac == 0 and r.n_loops == 700 and r.best_sample == 0
+    # no consensus: unrelated point sets -> fewer than 3 supporters... use tiny sets so that it is certain
+    rng = np.random.default_rng(3)
+    A, B = rng.normal(size=(5, 3)) * 5 + [0, 0, 8], rng.normal(size=(5, 3)) * 5 + [0, 0, 8]
+    r = orc.vodometry_dr_ye(A, B, samples=draws % 5)
+    assert r.status in (0, 4) and (r.status == 4) == (r.op_num < 3)
+    # nothing farther than 0.4 m
+    assert orc.vodometry_dr_ye(c.Ya * 0.01, c.Yb * 0.01, samples=draws).status == 5
+
+
+def test_every_hypothesis_is_scored_and_draw_order_is_kept(orc):
+    synth = importlib.import_module("3pre_b200.synth")
+    c = synth.make_correspondences(21, N=60, outlier_ratio=0.2)
+    Yb = c.Yb.copy()
+    Yb[:4] = np.outer(np.arange(4.0), [1.0, 1.0, 1.0]) + [0, 0, 2]   # collinear sample -> fit fails
+    Ya = Yb @ c.R.T + c.t
+    draws = synth.make_draws(22, 50, 60)
+    draws[0] = [0, 1, 2, 3]
+    r = orc.vodometry_dr_ye(Ya, Yb, samples=draws)
+    # RANSAC_CALC_VER2 skips a failed fit (:97-99); ransac_dr_ye scores it with rot = H, trans = 0 (:59-70)
+    assert r.counts[0] >= 0
+    g = rn.vodometry_dr_ye(Ya, Yb, draws)
+    np.testing.assert_array_equal(r.counts[1:50], g["counts"][1:50])
+    # the sample is used in draw order; a permuted sample is the same set of points -> same support
+    d2 = draws.copy()
+    d2[:, :] = d2[:, ::-1]
+    r2 = orc.vodometry_dr_ye(Ya, Yb, samples=d2)
+    assert (r2.counts[1:50] == r.counts[1:50]).mean() > 0.9
+
+
+def test_planted_motion(orc):
+    synth = importlib.import_module("3pre_b200.synth")
+    for seed in range(4):
+        c = synth.make_correspondences(3000 + seed, N=300, outlier_ratio=0.3)
+        match = np.stack([np.arange(300), np.random.default_rng(seed).permutation(300)], 1).astype(np.int32)
+        r = orc.vodometry_dr_ye(c.Ya, c.Yb, match=match, seed=5, pair=seed)
+        assert r.status == 0 and r.state == 1
+        assert rn.rot_angle(r.R, c.R) < 2e-3 and np.abs(r.T - c.t).max() < 5e-3
+        assert (r.mask & ~c.inlier).sum() <= 3 and (r.mask & c.inlier).sum() >= 0.9 * c.inlier.sum()
+        assert 0 < r.error_mean < 0.01 and 0 < r.error_std < 0.01
