@@ -356,6 +356,49 @@ def bench_cfg5(ctx, pre3, synth, dev, rank, world, N=20000, H=1000000, steps=3, 
     return out
 
 
+def bench_dr_ye(ctx, pre3, synth, dev, rank, P=1024, steps=5, warmup=2):
+    """the code_from_dr_ye variant (vodometry_dr_ye.m) on a cfg3-shaped sequence: match +
+    700 four-match hypotheses per pair, every one scored (no early stop: the reference's for-range is fixed),
+    first-max selection, refit, residual statistics."""
+    import torch
+    L = importlib.import_module("3pre_b200._lib")
+    sq = synth.make_sequence_torch(P + 1, 8100 + 100000 * rank, dev, K=K_FEAT, n_corr=N_CORR, outlier_ratio=OUTLIER)
+    opts = pre3.make_opts(method=L.METHOD_DR_YE, k=4, max_iteration=700, adaptive=False, H=700, seed=7)
+    res = torch.zeros(P, 240, dtype=torch.uint8, device=dev)
+    masks = torch.zeros(P, K_FEAT, dtype=torch.uint8, device=dev)
+
+    def step():
+        ctx.sequence_dev(sq["desc"], sq["xyz"], opts, res, None, masks, pair_id0=0)
+
+    ms = _time_steps(step, steps, warmup)
+    kt = _kernel_times(ctx, step)
+    rec = np.frombuffer(res.cpu().numpy().tobytes(), dtype=pre3.RESULT_DTYPE)
+    evals = float((rec["n_consumed"].astype(np.int64) * rec["n_matches"]).sum())
+    out = {"workload": f"code_from_dr_ye variant: sequence of {P}+1 frames, {K_FEAT} descriptors per frame, 700 "
+                       "four-match hypotheses per pair, all scored (vodometry_dr_ye.m:162-183)",
+           "pairs_per_s": P / (ms * 1e-3), "ms_per_step": ms, "kernels": kt,
+           "pairs_solved": int((rec["status"] == 0).sum()), "mean_support": float(rec["best_fit"].mean()),
+           "hyp_x_match_evals_per_s": evals / (ms * 1e-3)}
+    ev = kt.get("eval", {}).get("ms_per_step", 0.0)
+    if ev > 0:
+        a = 27.0 * evals / (ev * 1e-3) / 1e12
+        out["roofline"] = {"kernel": "eval", "bound": "fp32", "achieved": a, "unit": "TFLOP/s",
+                           "note": "27 FLOP per hypothesis x match eval (the fp64 4-point fits run in the same kernel)"}
+    if rank == 0:
+        from oracle import oracle as orc
+        fps = [synth.make_frame_pair(8200 + i, K1=K_FEAT, K2=K_FEAT, n_corr=N_CORR, outlier_ratio=OUTLIER) for i in range(3)]
+        t0 = time.perf_counter()
+        for i, f in enumerate(fps):
+            pairs, _ = orc.siftmatch(f.desc1, f.desc2, 1.5)
+            orc.vodometry_dr_ye(f.xyz1[pairs[:, 0]], f.xyz2[pairs[:, 1]], match=pairs, seed=7, pair=i)
+        dt = time.perf_counter() - t0
+        out["cpu"] = {"pairs_per_s": 3 / dt, "cores": 1, "kind": "port",
+                      "sample": "3 pairs: C restatement of siftmatch + vodometry_dr_ye (oracle/), one thread"}
+    del sq
+    torch.cuda.empty_cache()
+    return out
+
+
 def bench_cfg1(ctx, pre3, synth, dev):
     """configs[0]: one synthetic SR4000 frame pair (~300 matches, 30% outliers), 2000 hypotheses: a LATENCY
     number on the GPU (one pair cannot fill the machine); k=5 (RANSAC_CALC_VER2.m:85) and k=3 (BASELINE wording)."""
@@ -420,6 +463,7 @@ def other_workloads(ctx, pre3, synth, dev, rank, world):
         jobs = [("cfg1", lambda: bench_cfg1(ctx, pre3, synth, dev)),
                 ("cfg2", lambda: bench_cfg2(ctx, pre3, synth, dev, rank)),
                 ("cfg4", lambda: bench_cfg4(ctx, pre3, dev, rank)),
+                ("dr_ye", lambda: bench_dr_ye(ctx, pre3, synth, dev, rank)),
                 ("cpu", lambda: cpu_other_baselines(synth))] + jobs
     # cfg5 involves every rank: run it first everywhere so that no rank waits inside a collective
     jobs.sort(key=lambda j: j[0] != "cfg5")

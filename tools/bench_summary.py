@@ -21,6 +21,9 @@ if "cfg4" in o and "error" not in o["cfg4"]:
         print("cfg4", m, round(c["frames_per_s"]), "frames/s", {k: round(v["ms_per_step"], 3) for k, v in c["kernels"].items()})
 if "cfg1" in o and "error" not in o["cfg1"]:
     print("cfg1 ms/pair", {k: round(v["ms_per_pair_device_resident"], 4) for k, v in o["cfg1"].items() if isinstance(v, dict)})
+if "dr_ye" in o and "error" not in o["dr_ye"]:
+    c = o["dr_ye"]
+    print("dr_ye", round(c["pairs_per_s"]), "pairs/s", {k: round(v["ms_per_step"], 3) for k, v in c["kernels"].items()})
 for k, v in o.items():
     if isinstance(v, dict) and "error" in v:
         print("ERROR in", k, v["error"])
