@@ -15,7 +15,7 @@ OK, ERR_ARG, ERR_CUDA, ERR_ALLOC, ERR_CLASS = 0, -1, -2, -3, -4
 CLASS_DOUBLE, CLASS_SINGLE, CLASS_INT8, CLASS_UINT8 = 0, 1, 2, 3
 METHOD_SVD, METHOD_HORN, METHOD_DR_YE = 0, 1, 2
 MATCH_AUTO, MATCH_EXACT, MATCH_TC = 0, 1, 2
-TIMING_NCAT = 12
+TIMING_NCAT = 13
 
 
 class RansacOpts(C.Structure):
@@ -57,6 +57,12 @@ class DrYeStat(C.Structure):
     """pre3_dr_ye_stat (32 bytes)"""
     _fields_ = [("error_mean", C.c_double), ("error_std", C.c_double), ("dist", C.c_double),
                 ("n_iteration_ransac", C.c_int32), ("n_loops", C.c_int32)]
+
+
+class FrameOpts(C.Structure):
+    """pre3_frame_opts (24 bytes)"""
+    _fields_ = [("sigma", C.c_double), ("boundary", C.c_int32), ("mode", C.c_int32), ("rows", C.c_int32),
+                ("use_confidence", C.c_int32)]
 
 
 class Cam(C.Structure):
@@ -105,6 +111,12 @@ SYMBOLS = {
     "pre3_ransac": (_I, [_VP, _VP, _VP, _I, _OPTS, _VP, _VP, _VP, _VP, _VP]),
     "pre3_ransac_batch": (_I, [_VP, _VP, _VP, _VP, _I, _I, _OPTS, _VP, _VP, _VP]),
     "pre3_ransac_batch_dev": (_I, [_VP, _VP, _VP, _VP, _I, _I, _OPTS, _VP, _VP, _VP]),
+    "pre3_read_xyz_sr4000_batch": (_I, [_VP, _VP, _I, C.POINTER(FrameOpts), _VP, _VP, _VP, _VP]),
+    "pre3_read_xyz_sr4000_batch_dev": (_I, [_VP, _VP, _I, C.POINTER(FrameOpts), _VP, _VP, _VP, _VP]),
+    "pre3_features_xyz_batch": (_I, [_VP, _VP, _I, C.POINTER(FrameOpts), _VP, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP,
+                                     _VP, _I, _I, _VP, _VP, _VP]),
+    "pre3_features_xyz_batch_dev": (_I, [_VP, _VP, _I, C.POINTER(FrameOpts), _VP, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP,
+                                         _VP, _I, _I, _VP, _VP, _VP, _VP]),
     "pre3_vodometry_dr_ye_batch": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, _OPTS, _VP, _VP, _VP, _VP, _VP]),
     "pre3_vodometry_dr_ye_batch_dev": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, _OPTS, _VP, _U32, _VP, _VP, _VP, _VP]),
     "pre3_pairs": (_I, [_VP, _VP, _VP, _I, _VP, _VP, _I, _I, _I, _I, _VP, _VP, _OPTS, _U32, _VP, _VP, _VP]),

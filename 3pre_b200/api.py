@@ -16,7 +16,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _lib as L
-from ._lib import Pre3Error, RansacOpts, PairResult, Cam, EkfOpts, EkfResult, DrYeStat
+from ._lib import Pre3Error, RansacOpts, PairResult, Cam, EkfOpts, EkfResult, DrYeStat, FrameOpts
 
 _CLS = {
     np.dtype(np.float64): L.CLASS_DOUBLE,
@@ -49,6 +49,12 @@ def _ptr(a):
 
 def _c(a, dtype=None):
     return np.ascontiguousarray(a, dtype=dtype)
+
+
+def make_frame_opts(sigma=2.0, boundary=0, mode=0, rows=720, use_confidence=1) -> FrameOpts:
+    """Defaults = M/read_xyz_sr4000.m:8-21 + M/inittialize_depth_my_version.m; the code_from_dr_ye flavour is
+    sigma=1, boundary=1 ('replicate'), mode=1."""
+    return FrameOpts(float(sigma), int(boundary), int(mode), int(rows), int(bool(use_confidence)))
 
 
 def make_opts(method=L.METHOD_SVD, k=5, max_iteration=2000, adaptive=True, H=2000, distance_threshold=0.05,
@@ -338,6 +344,71 @@ class Context:
         self._ck(self._lib.pre3_ransac_batch(self._h, _ptr(ya), _ptr(yb), _ptr(nc), P, Nmax, C.byref(o), _ptr(s),
                                              _ptr(res), _ptr(masks)))
         return res[:P], (masks[:P, :Nmax] if masks is not None else None)
+
+    # ---- frames -> per-feature 3-D points ---------------------------
+    def read_xyz_sr4000_batch(self, sr, opts: FrameOpts | None = None, **kw):
+        """sr (F,176,rows) float64 = F column-major rows x 176 sr_data matrices.  Returns x, y, z (F,176,144)
+        (= 144 x 176 column-major maps) and max_conf (F,)."""
+        sr = _c(sr, np.float64)
+        F, cols, rows = sr.shape
+        if cols != 176:
+            raise ValueError("sr must be (F, 176, rows)")
+        o = opts or make_frame_opts(rows=rows, **kw)
+        x, y, z = (np.zeros((max(F, 1), 176, 144)) for _ in range(3))
+        mc = np.zeros(max(F, 1))
+        self._ck(self._lib.pre3_read_xyz_sr4000_batch(self._h, _ptr(sr), F, C.byref(o), _ptr(x), _ptr(y), _ptr(z),
+                                                      _ptr(mc)))
+        return x[:F], y[:F], z[:F], mc[:F]
+
+    def read_xyz_sr4000_batch_dev(self, sr, opts: FrameOpts, x, y, z, max_conf=None):
+        """CUDA tensors: sr (F,176,rows) f64; x, y, z (F,176,144) f64 (or all None: only max_conf); max_conf (F,)."""
+        self._ck(self._lib.pre3_read_xyz_sr4000_batch_dev(self._h, _ptr(sr), int(sr.shape[0]), C.byref(opts), _ptr(x),
+                                                          _ptr(y), _ptr(z), _ptr(max_conf)))
+
+    def features_xyz_batch(self, sr, frames, desc=None, k_count=None, opts: FrameOpts | None = None, **kw):
+        """SIFT_extract_save.m:75-88 for F frames.  sr (F,176,rows); frames (F,K,ld) with the 0-based sift (x, y) in
+        the first two entries of a feature; desc (F,K,ND) or None.  Returns a dict: xyz_all (F,K,3), keep (F,K) bool,
+        n_keep (F,), idx_remain (F,K), xyz (F,K,3) compacted, frames_out (F,K,ld), desc_out (F,K,ND) | None, n_oob."""
+        sr, fr = _c(sr, np.float64), _c(frames, np.float64)
+        F, cols, rows = sr.shape
+        _, K, ld = fr.shape
+        o = opts or make_frame_opts(rows=rows, **kw)
+        d = None
+        cls, ND = 0, 0
+        if desc is not None:
+            d = _c(desc)
+            if d.dtype not in _CLS:
+                raise ValueError("Unsupported numeric class")
+            cls, ND = _CLS[d.dtype], int(d.shape[2])
+        kc = None if k_count is None else _c(k_count, np.int32)
+        Fm, Km = max(F, 1), max(K, 1)
+        out = {"xyz_all": np.zeros((Fm, Km, 3)), "keep": np.zeros((Fm, Km), np.uint8), "n_keep": np.zeros(Fm, np.int32),
+               "idx_remain": np.zeros((Fm, Km), np.int32), "xyz": np.zeros((Fm, Km, 3)),
+               "frames_out": np.zeros((Fm, Km, ld)), "desc_out": None if d is None else np.zeros_like(d)}
+        oob = np.zeros(1, np.int32)
+        self._ck(self._lib.pre3_features_xyz_batch(self._h, _ptr(sr), F, C.byref(o), _ptr(fr), ld, K, _ptr(kc),
+                                                   _ptr(out["xyz_all"]), _ptr(out["keep"]), _ptr(out["n_keep"]),
+                                                   _ptr(out["idx_remain"]), _ptr(out["xyz"]), _ptr(d), cls, ND,
+                                                   _ptr(out["desc_out"]), _ptr(out["frames_out"]), _ptr(oob)))
+        out["keep"] = out["keep"].astype(bool)
+        out["n_oob"] = int(oob[0])
+        return out
+
+    def features_xyz_batch_dev(self, sr, opts: FrameOpts, frames, xyz=None, n_keep=None, idx_remain=None, xyz_all=None,
+                               keep=None, desc_in=None, desc_out=None, frames_out=None, k_count=None, n_oob=None):
+        """CUDA tensors (see features_xyz_batch for shapes).  Asynchronous on the context's stream."""
+        import torch
+        F, K, ld = (int(v) for v in frames.shape)
+        cls, ND = 0, 0
+        if desc_in is not None:
+            cls = {torch.float64: L.CLASS_DOUBLE, torch.float32: L.CLASS_SINGLE, torch.int8: L.CLASS_INT8,
+                   torch.uint8: L.CLASS_UINT8}[desc_in.dtype]
+            ND = int(desc_in.shape[2])
+        self._ck(self._lib.pre3_features_xyz_batch_dev(self._h, _ptr(sr), F, C.byref(opts), _ptr(frames), ld, K,
+                                                       _ptr(k_count), _ptr(xyz_all), _ptr(keep), _ptr(n_keep),
+                                                       _ptr(idx_remain), _ptr(xyz), _ptr(desc_in), cls, ND,
+                                                       _ptr(desc_out), _ptr(frames if frames_out is not None else None),
+                                                       _ptr(frames_out), _ptr(n_oob)))
 
     # ---- code_from_dr_ye variant ---------------------------------------------------------
     def vodometry_dr_ye_batch(self, Ya, Yb, n_corr=None, match=None, samples=None, opts: RansacOpts | None = None,

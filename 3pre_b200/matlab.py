@@ -13,7 +13,7 @@ from __future__ import annotations
 import numpy as np
 
 from . import _lib as L
-from .api import Context, R2q, make_opts
+from .api import Context, R2q, make_opts, make_frame_opts
 
 _ctx = None
 
@@ -168,6 +168,70 @@ def Calculate_V_Omega_RANSAC_my_version(DataPre, DataCurrent, **kw):
     (q = R2q(R), [w x y z] with the slamToolbox sign convention)."""
     out = SIFT_match_save(DataPre, DataCurrent, **kw)
     return out["T_RANSAC"], R2q(out["R_RANSAC"]).reshape(4, 1), out["R_RANSAC"], out["State_RANSAC"]
+
+
+# ---------------------------------------------------------------------------------------
+# the step before the path (SURVEY.md 8f rank 2): SR4000 frame -> filtered maps -> per-feature 3-D points
+# ---------------------------------------------------------------------------------------
+def _sr(sr_data):
+    """rows x 176 MATLAB matrix -> (1,176,rows) C-contiguous (same bytes as column-major)."""
+    a = np.asarray(sr_data, np.float64)
+    if a.ndim != 2 or a.shape[1] < 176 or a.shape[0] not in (576, 720, 721):
+        raise MexError("sr_data must be a 576/720/721 x 176 matrix (load of d1_%04d.dat)")
+    return np.ascontiguousarray(a[:, :176].T)[None]
+
+
+def read_xyz_sr4000(sr_data):
+    """[x, y, z, confidence_map] = read_xyz_sr4000(prefix, k) from the matrix `load` returned (:3): z, x, y =
+    imfilter(., fspecial('gaussian',[3 3],2), 'same') (M/read_xyz_sr4000.m:8-21); confidence_map raw (:26) or []."""
+    a = np.asarray(sr_data, np.float64)
+    x, y, z, _ = context().read_xyz_sr4000_batch(_sr(a), sigma=2.0, boundary=0)
+    cm = a[576:720, :176].copy() if a.shape[0] >= 720 else np.zeros((0, 0))
+    return x[0].T.copy(), y[0].T.copy(), z[0].T.copy(), cm
+
+
+def read_sr4000_data_dr_ye(sr_data):
+    """[x, y, z, confidence_map] of M/code_from_dr_ye/read_sr4000_data_dr_ye.m:8,27-36,88-90 (sigma 1, 'replicate');
+    the amplitude-image output img1 (:11-25,42,70) feeds SIFT extraction and is not produced here."""
+    a = np.asarray(sr_data, np.float64)
+    x, y, z, _ = context().read_xyz_sr4000_batch(_sr(a), sigma=1.0, boundary=1, mode=1)
+    cm = a[576:720, :176].copy() if a.shape[0] >= 720 else np.zeros((0, 0))
+    return x[0].T.copy(), y[0].T.copy(), z[0].T.copy(), cm
+
+
+def SIFT_extract_save(sr_data, frames, descriptors, idxScan=0):
+    """The data part of M/SIFT_extract_save.m:44-88 for one scan, from the point where sift_vedal has returned
+    (frames 4 x N with 0-based positions, descriptors 128 x N): SCAN_SIFT with Descriptor_RAW, SCALE_ORIENT_POS_RAW
+    (positions + 1, :55-56), Descriptor, SCALE_ORIENT_POS, XYZ_DATA of the features that have valid 3-D data
+    (inittialize_depth_my_version.m:40-85).  Image reading, SIFT extraction and the .mat save stay with the caller."""
+    fr = _cols(frames, None, np.float64, "frames")
+    de = _cols(descriptors, None, None, "descriptors")
+    out = context().features_xyz_batch(_sr(sr_data), fr[None], desc=de[None], sigma=2.0, boundary=0, mode=0)
+    if out["n_oob"]:
+        raise MexError("Index exceeds matrix dimensions (inittialize_depth_my_version.m:40)")
+    n = int(out["n_keep"][0])
+    raw = np.array(frames, np.float64)
+    raw[:2] += 1
+    pos = out["frames_out"][0, :n].T.copy()
+    pos[:2] += 1
+    return {"idxScan": idxScan, "Descriptor_RAW": np.asarray(descriptors), "SCALE_ORIENT_POS_RAW": raw,
+            "Descriptor": out["desc_out"][0, :n].T.copy(), "SCALE_ORIENT_POS": pos,
+            "XYZ_DATA": out["xyz"][0, :n].T.copy(), "idxRemain": out["idx_remain"][0, :n] + 1}
+
+
+def inittialize_depth_my_version(uvd, sr_data):
+    """[initial_rho, Feature3d_in_code_coordinate] = inittialize_depth_my_version(uvd, step)
+    (M/inittialize_depth_my_version.m:1-92) for ONE feature; uvd = [u; v] 1-based (column, row) as the callers pass
+    it (SIFT_extract_save.m:77), the frame given as its sr_data matrix instead of a step number.  Empty outputs
+    (None) when the reference returns []."""
+    fr = np.array([[float(uvd[0]) - 1.0, float(uvd[1]) - 1.0]])
+    out = context().features_xyz_batch(_sr(sr_data), fr[None], sigma=2.0, boundary=0, mode=0)
+    if out["n_oob"]:
+        raise MexError("Index exceeds matrix dimensions (inittialize_depth_my_version.m:40)")
+    if not out["keep"][0, 0]:
+        return None, None
+    p = out["xyz_all"][0, 0]
+    return 1.0 / np.sqrt(p @ p), p.copy()
 
 
 # ---------------------------------------------------------------------------------------

@@ -241,3 +241,42 @@ def make_sequence_torch(F, seed, device, K=512, n_corr=300, outlier_ratio=0.30, 
     if dtype == "float64":
         d = d.to(f64)
     return dict(desc=d.contiguous(), xyz=xyz.contiguous(), R=R, t=t)
+
+
+def make_sr_frames(seed, F, K, rows=720, n_nan=300, n_near=200, n_lowconf=2000):
+    """Synthetic SR4000 frames as `load('d1_%04d.dat')` returns them (M/read_xyz_sr4000.m:3,10-12,26): F matrices of
+    rows x 176 doubles [z; x; y; amplitude; confidence(; time stamp)], returned as (F,176,rows) C-contiguous (= column-
+    major rows x 176), plus sift-style frames (F,K,4): 0-based (x, y), scale, orientation.  Some pixels are NaN, some
+    closer than 0.4 m, some of low confidence; some features sit exactly on .5 positions (round half away)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    sr = np.zeros((F, rows, 176))
+    for f in range(F):
+        u, v = np.meshgrid(np.arange(176.0), np.arange(144.0))
+        z = 2.5 + 1.5 * np.sin(u / 40.0 + f) * np.cos(v / 30.0) + rng.normal(scale=0.01, size=(144, 176))
+        x = -(u - 91.69) * z / 250.577
+        y = -(v - 72.27) * z / 250.577
+        pix = rng.permutation(144 * 176)
+        near = pix[:n_near]
+        z.flat[near] *= 0.05
+        x.flat[near] *= 0.05
+        y.flat[near] *= 0.05
+        nan = pix[n_near:n_near + n_nan]
+        x.flat[nan] = np.nan
+        z.flat[nan[::3]] = np.nan
+        sr[f, 0:144], sr[f, 144:288], sr[f, 288:432] = z, x, y
+        sr[f, 432:576] = rng.uniform(0, 20000, size=(144, 176))
+        if rows >= 720:
+            cm = rng.uniform(20000, 65535, size=(144, 176))
+            cm.flat[pix[n_near + n_nan:n_near + n_nan + n_lowconf]] = rng.uniform(0, 30000, n_lowconf)
+            sr[f, 576:720] = cm
+        if rows == 721:
+            sr[f, 720, 0] = 1000.0 + f
+    frames = np.zeros((F, K, 4))
+    frames[:, :, 0] = rng.uniform(0.0, 175.0, size=(F, K))
+    frames[:, :, 1] = rng.uniform(0.0, 143.0, size=(F, K))
+    half = rng.random((F, K)) < 0.1
+    frames[:, :, 0] = np.where(half, np.floor(frames[:, :, 0]) + 0.5, frames[:, :, 0]).clip(0, 174.5)
+    frames[:, :, 1] = np.where(half, np.floor(frames[:, :, 1]) + 0.5, frames[:, :, 1]).clip(0, 142.5)
+    frames[:, :, 2] = rng.uniform(1, 4, size=(F, K))
+    frames[:, :, 3] = rng.uniform(-np.pi, np.pi, size=(F, K))
+    return np.ascontiguousarray(sr.transpose(0, 2, 1)), frames

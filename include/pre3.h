@@ -122,7 +122,7 @@ PRE3_API int pre3_eval_schedule(const pre3_ransac_opts *opts, int32_t *ends, int
  * numbers).  pre3_timing_read synchronises, adds the elapsed ms and launch counts of every
  * bracketed launch since the last read into ms[cat] / count[cat] (PRE3_TIMING_NCAT entries
  * each, caller-zeroed) and forgets them.  pre3_timing_name(cat) names a category. */
-#define PRE3_TIMING_NCAT 12
+#define PRE3_TIMING_NCAT 13
 PRE3_API int pre3_timing_enable(pre3_ctx *ctx, int on);
 PRE3_API int pre3_timing_read(pre3_ctx *ctx, double *ms, int64_t *count);
 PRE3_API const char *pre3_timing_name(int cat);
@@ -196,6 +196,47 @@ PRE3_API int pre3_ransac_batch(pre3_ctx *ctx, const double *Ya, const double *Yb
 PRE3_API int pre3_ransac_batch_dev(pre3_ctx *ctx, const double *dYa, const double *dYb,
                           const int32_t *dn_corr, int P, int Nmax, const pre3_ransac_opts *opts,
                           const int32_t *dsamples, pre3_pair_result *dres, uint8_t *dmasks);
+
+/* ---- SR4000 frame batches -> per-feature 3-D points ----------------
+ * The step before the matching path: what SIFT_extract_save.m:75-88 does per frame through
+ * read_xyz_sr4000.m:8-21 (3 x 3 Gaussian smoothing of the x, y, z maps) and
+ * inittialize_depth_my_version.m:16,40-85 (x(round(v),round(u)) lookup, rejection of NaN / closer than 0.4 m /
+ * confidence <= max/2, [-x,-y,z]); and its code_from_dr_ye flavour (read_sr4000_data_dr_ye.m:8,88-90: sigma 1,
+ * 'replicate'; confidence_filtering.m:1-13; the lookup of ransac_dr_ye.m:13-19).
+ * sr_data: F frames, each the rows x 176 column-major double matrix `load('d1_%04d.dat')` returns: rows 1:144 z,
+ * 145:288 x, 289:432 y, 433:576 amplitude, 577:720 confidence (rows >= 720), row 721 time stamp. */
+typedef struct {
+  double sigma;           /* fspecial('gaussian',[3 3],sigma): 2 (read_xyz_sr4000.m:8), 1 (read_sr4000_data_dr_ye.m:8) */
+  int32_t boundary;       /* 0 zero padding (imfilter(...,'same'), read_xyz_sr4000.m:15-21); 1 'replicate' (dr_ye :88-90) */
+  int32_t mode;           /* 0 inittialize_depth_my_version.m rejection rules; 1 dr_ye: confidence_filtering.m only */
+  int32_t rows;           /* rows of sr_data per frame: 576, 720 or 721 */
+  int32_t use_confidence; /* mode 1: myCONFIG.FLAGS.CONFIDENCE_MAP (vodometry_dr_ye.m:80-82) */
+} pre3_frame_opts;
+
+/* [x,y,z,confidence_map] = read_xyz_sr4000(prefix, k) for F frames already loaded: the filtered maps, F x (144 x 176)
+ * column-major each; max_conf: F values of max(confidence_map(:)) (NaN when rows < 720) or NULL. */
+PRE3_API int pre3_read_xyz_sr4000_batch(pre3_ctx *ctx, const double *sr_data, int F, const pre3_frame_opts *opts,
+                               double *x, double *y, double *z, double *max_conf);
+PRE3_API int pre3_read_xyz_sr4000_batch_dev(pre3_ctx *ctx, const double *dsr_data, int F,
+                                   const pre3_frame_opts *opts, double *dx, double *dy, double *dz,
+                                   double *dmax_conf);
+/* The per-feature loop of SIFT_extract_save.m:75-88, fused with the smoothing (the stencil is evaluated only at
+ * the pixels the features round to).  frames: F x (frame_ld x K), rows 1:2 = the 0-based (x, y) sift returns (:55-56
+ * add 1); k_count: valid features per frame or NULL.  Outputs (any may be NULL): xyz_all F x (3 x K) with NaN columns
+ * for rejected features (xyz_data of :80-83); keep F x K; n_keep F; idx_remain F x K (0-based idxRemain, -1 beyond
+ * n_keep); xyz F x (3 x K) compacted XYZ_DATA (:88); desc_out = Descriptor(:, idxRemain) (:86, class cls, ND rows,
+ * zero beyond n_keep); frames_out = SCALE_ORIENT_POS(:, idxRemain) (:87); n_oob: features whose rounded position lies
+ * outside the 144 x 176 image (the reference raises an index error; they are rejected here). */
+PRE3_API int pre3_features_xyz_batch(pre3_ctx *ctx, const double *sr_data, int F, const pre3_frame_opts *opts,
+                            const double *frames, int frame_ld, int K, const int32_t *k_count, double *xyz_all,
+                            uint8_t *keep, int32_t *n_keep, int32_t *idx_remain, double *xyz,
+                            const void *desc_in, int cls, int ND, void *desc_out, double *frames_out,
+                            int32_t *n_oob);
+PRE3_API int pre3_features_xyz_batch_dev(pre3_ctx *ctx, const double *dsr_data, int F, const pre3_frame_opts *opts,
+                                const double *dframes, int frame_ld, int K, const int32_t *dk_count,
+                                double *dxyz_all, uint8_t *dkeep, int32_t *dn_keep, int32_t *didx_remain,
+                                double *dxyz, const void *ddesc_in, int cls, int ND, void *ddesc_out,
+                                const double *dframes_in, double *dframes_out, int32_t *dn_oob);
 
 /* ---- the code_from_dr_ye variant ---------------------------------
  * The RANSAC part of [rot,phi,theta,psi,trans,error,pnum,op_num,sta,op_pset1,op_pset2,RANSAC_STAT] =

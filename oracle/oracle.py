@@ -321,6 +321,59 @@ def vodometry_dr_ye(Ya, Yb, match=None, samples=None, max_iteration=700, H=700, 
                 counts[:H].copy())
 
 
+# ---------------------------------------------------------------------------------------------------
+# frames -> per-feature 3-D points (oracle/pre3_oracle_frames.c)
+# ---------------------------------------------------------------------------------------------------
+def gaussian3(sigma):
+    h = np.zeros(9)
+    L = lib()
+    L.orc_gaussian3.argtypes = [C.c_double, C.POINTER(C.c_double)]
+    L.orc_gaussian3.restype = None
+    L.orc_gaussian3(float(sigma), _p(h, C.c_double))
+    return h.reshape(3, 3).T  # h[dr+1, dc+1]
+
+
+def read_xyz(sr, sigma=2.0, boundary=0):
+    """sr: (176, rows) C-contiguous = the rows x 176 column-major sr_data.  Returns x, y, z as (176,144) arrays
+    (= 144 x 176 column-major)."""
+    sr = _f64(sr)
+    rows = sr.shape[1]
+    x, y, z = (np.zeros((176, 144)) for _ in range(3))
+    L = lib()
+    L.orc_read_xyz.argtypes = [C.POINTER(C.c_double), C.c_int, C.c_double, C.c_int] + [C.POINTER(C.c_double)] * 3
+    L.orc_read_xyz.restype = None
+    L.orc_read_xyz(_p(sr, C.c_double), rows, float(sigma), int(boundary), _p(x, C.c_double), _p(y, C.c_double),
+                   _p(z, C.c_double))
+    return x, y, z
+
+
+def max_confidence(sr):
+    sr = _f64(sr)
+    L = lib()
+    L.orc_max_confidence.argtypes = [C.POINTER(C.c_double), C.c_int]
+    L.orc_max_confidence.restype = C.c_double
+    return float(L.orc_max_confidence(_p(sr, C.c_double), sr.shape[1]))
+
+
+def features_xyz(sr, frames, sigma=2.0, boundary=0, mode=0, use_conf=1):
+    """sr: (176, rows); frames: (K, frame_ld).  Returns (xyz_all (K,3), keep (K,) bool, idx_remain (n,), n_oob)."""
+    sr, fr = _f64(sr), _f64(frames)
+    K, ld = fr.shape
+    xyz = np.zeros((max(K, 1), 3))
+    keep = np.zeros(max(K, 1), np.uint8)
+    idx = np.zeros(max(K, 1), np.int32)
+    oob = C.c_int32(0)
+    L = lib()
+    L.orc_features_xyz.argtypes = [C.POINTER(C.c_double), C.c_int, C.c_double, C.c_int, C.c_int, C.c_int,
+                                   C.POINTER(C.c_double), C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint8),
+                                   C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    L.orc_features_xyz.restype = C.c_int
+    n = L.orc_features_xyz(_p(sr, C.c_double), sr.shape[1], float(sigma), int(boundary), int(mode), int(use_conf),
+                           _p(fr, C.c_double), ld, K, _p(xyz, C.c_double), _p(keep, C.c_uint8), _p(idx, C.c_int32),
+                           C.byref(oob))
+    return xyz[:K], keep[:K].astype(bool), idx[:n].copy(), int(oob.value)
+
+
 def R2q(R):
     r = _f64(R).reshape(9)
     q = np.zeros(4)

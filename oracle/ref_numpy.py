@@ -211,6 +211,52 @@ def vodometry_dr_ye(Ya, Yb, samples, max_iteration=700):
     return out
 
 
+def fspecial_gaussian3(sigma):
+    """fspecial('gaussian', [3 3], sigma) (Image Processing Toolbox)."""
+    xx, yy = np.meshgrid(np.arange(-1, 2), np.arange(-1, 2))
+    h = np.exp(-(xx * xx + yy * yy) / (2.0 * sigma * sigma))
+    h[h < np.finfo(float).eps * h.max()] = 0
+    return h / h.sum()
+
+
+def read_xyz_sr4000(sr_data, sigma=2.0, boundary="same"):
+    """M/read_xyz_sr4000.m:8-26 (sigma 2, imfilter 'same' = zero padding) or
+    M/code_from_dr_ye/read_sr4000_data_dr_ye.m:8,27-36,88-90 (sigma 1, 'replicate') on the rows x 176 matrix
+    `load` returned.  scipy.ndimage.correlate stands for imfilter.  Returns x, y, z, confidence_map (or None)."""
+    from scipy import ndimage
+    sr = np.asarray(sr_data, float)
+    G = fspecial_gaussian3(sigma)
+    mode = {"same": "constant", "replicate": "nearest"}[boundary]
+    z = ndimage.correlate(sr[0:144, :176], G, mode=mode, cval=0.0)
+    x = ndimage.correlate(sr[144:288, :176], G, mode=mode, cval=0.0)
+    y = ndimage.correlate(sr[288:432, :176], G, mode=mode, cval=0.0)
+    cm = sr[576:720, :176] if sr.shape[0] >= 720 else None
+    return x, y, z, cm
+
+
+def sift_extract_xyz(sr_data, frames):
+    """The per-feature loop of M/SIFT_extract_save.m:55-56,75-88 with M/inittialize_depth_my_version.m:16,31-85.
+    frames: 4 x K as sift returns them (0-based x, y).  Returns (xyz_data 3 x K with NaN columns, idxRemain 0-based)."""
+    x, y, z, cm = read_xyz_sr4000(sr_data, 2.0, "same")
+    fr = np.array(frames, float)
+    fr[:2] += 1
+    mc = np.nanmax(cm) if cm is not None else None
+    out = np.full((3, fr.shape[1]), np.nan)
+    remain = []
+    for i in range(fr.shape[1]):
+        r = int(np.floor(fr[1, i] + 0.5)) - 1
+        c = int(np.floor(fr[0, i] + 0.5)) - 1
+        xf, yf, zf = x[r, c], y[r, c], z[r, c]
+        if np.isnan(xf):
+            continue
+        df = np.sqrt(xf ** 2 + yf ** 2 + zf ** 2)
+        if df < 0.4 or (cm is not None and cm[r, c] <= 0.5 * mc):
+            continue
+        out[:, i] = [-xf, -yf, zf]
+        remain.append(i)
+    return out, np.array(remain, int)
+
+
 def rot_angle(Ra, Rb):
     """Geodesic distance between two rotations, radians."""
     D = np.asarray(Ra) @ np.asarray(Rb).T
