@@ -77,71 +77,94 @@ __device__ __forceinline__ double stencil(const double* __restrict__ map, int ld
   return acc;
 }
 
-__global__ void __launch_bounds__(256) k_conf_max(const double* __restrict__ sr, int rows, int F,
-                                                  double* __restrict__ max_conf) {
+// 288 threads: thread = (row, column parity); every column is one contiguous 1152-byte read
+__global__ void __launch_bounds__(2 * FR_ROWS) k_conf_max(const double* __restrict__ sr, int rows, int F,
+                                                          double* __restrict__ max_conf) {
   const int f = blockIdx.x;
   const double* cm = sr + (size_t)f * rows * FR_COLS + 4 * FR_ROWS;
+  const int r = threadIdx.x % FR_ROWS, c0 = threadIdx.x / FR_ROWS;
   double m = -INFINITY;
   bool any = false;
-  for (int i = threadIdx.x; i < FR_PIX; i += 256) {
-    const int r = i % FR_ROWS, c = i / FR_ROWS;
-    const double v = cm[(size_t)c * rows + r];
+#pragma unroll 8
+  for (int c = c0; c < FR_COLS; c += 2) {
+    const double v = __ldg(cm + (size_t)c * rows + r);
     if (v == v) {  // max ignores NaN
       m = any ? fmax(m, v) : v;
       any = true;
     }
   }
-  __shared__ double s_m[256];
-  __shared__ int s_a[256];
+  __shared__ double s_m[2 * FR_ROWS];
+  __shared__ int s_a[2 * FR_ROWS];
   s_m[threadIdx.x] = m;
   s_a[threadIdx.x] = any;
   __syncthreads();
-  for (int off = 128; off > 0; off >>= 1) {
-    if (threadIdx.x < off && s_a[threadIdx.x + off]) {
-      s_m[threadIdx.x] = s_a[threadIdx.x] ? fmax(s_m[threadIdx.x], s_m[threadIdx.x + off]) : s_m[threadIdx.x + off];
-      s_a[threadIdx.x] = 1;
+  if (threadIdx.x < 32) {
+    for (int i = threadIdx.x + 32; i < 2 * FR_ROWS; i += 32)
+      if (s_a[i]) {
+        m = any ? fmax(m, s_m[i]) : s_m[i];
+        any = true;
+      }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const double om = __shfl_xor_sync(0xffffffffu, m, off);
+      const int oa = __shfl_xor_sync(0xffffffffu, (int)any, off);
+      if (oa) {
+        m = any ? fmax(m, om) : om;
+        any = true;
+      }
     }
-    __syncthreads();
+    if (threadIdx.x == 0) max_conf[f] = any ? m : NAN;  // all-NaN map: max is NaN
   }
-  if (threadIdx.x == 0) max_conf[f] = s_a[0] ? s_m[0] : NAN;  // all-NaN map: max is NaN
 }
 
-// grid (cols tiles, 3 maps, F); block 144 threads = one thread per row, 16 columns per block: the 18 x 146 halo
-// tile is staged in shared memory with coalesced column reads (144 contiguous doubles per column)
-constexpr int SM_TC = 16;
+// grid (column tiles, 3 maps, F); block 144 threads = one thread per image row marching along SM_TC columns with
+// a 3 x 3 register window: three loads per output (the row above / below come out of L1: the neighbouring threads
+// read the same 128-byte lines), no shared memory, no barrier.  Reads and writes are 1152-byte contiguous columns.
+constexpr int SM_TC = 44;  // 176 = 4 x 44: one halo column per 44
 template <int BOUNDARY>
 __global__ void __launch_bounds__(FR_ROWS) k_smooth_maps(const double* __restrict__ sr, int rows, Taps t,
                                                          double* __restrict__ ox, double* __restrict__ oy,
                                                          double* __restrict__ oz) {
-  __shared__ double tile[SM_TC + 2][FR_ROWS + 2];
   const int f = blockIdx.z, which = blockIdx.y, c0 = blockIdx.x * SM_TC;
   // sr_data rows: z 0..143, x 144..287, y 288..431 (read_xyz_sr4000.m:10-12)
   const double* map = sr + (size_t)f * rows * FR_COLS + (which == 0 ? FR_ROWS : which == 1 ? 2 * FR_ROWS : 0);
   double* out = (which == 0 ? ox : which == 1 ? oy : oz) + (size_t)f * FR_PIX;
   const int r = threadIdx.x;
-  for (int j = 0; j < SM_TC + 2; ++j) {
-    int cc = c0 + j - 1;
-    for (int i = r; i < FR_ROWS + 2; i += FR_ROWS) {
-      int rr = i - 1;
-      double v;
-      if (BOUNDARY == 1) {
-        v = map[(size_t)min(max(cc, 0), FR_COLS - 1) * rows + min(max(rr, 0), FR_ROWS - 1)];
-      } else {
-        v = (rr >= 0 && rr < FR_ROWS && cc >= 0 && cc < FR_COLS) ? map[(size_t)cc * rows + rr] : 0.0;
-      }
-      tile[j][i] = v;
-    }
+  int rr[3];
+  bool rin[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const int q = r + d - 1;
+    rin[d] = q >= 0 && q < FR_ROWS;
+    rr[d] = min(max(q, 0), FR_ROWS - 1);
   }
-  __syncthreads();
+  auto load_col = [&](int c, double* v) {
+    const bool cin = c >= 0 && c < FR_COLS;
+    const double* col = map + (size_t)min(max(c, 0), FR_COLS - 1) * rows;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const double x = __ldg(col + rr[d]);
+      v[d] = (BOUNDARY == 1 || (cin && rin[d])) ? x : 0.0;
+    }
+  };
+  double w[3][3];  // w[column slot][row offset]: columns c-1, c, c+1
+  load_col(c0 - 1, w[0]);
+  load_col(c0, w[1]);
+#pragma unroll 4
   for (int j = 0; j < SM_TC; ++j) {
     const int c = c0 + j;
-    if (c >= FR_COLS) break;
+    load_col(c + 1, w[2]);
     double acc = 0.0;
 #pragma unroll
-    for (int dc = -1; dc <= 1; ++dc)
+    for (int dc = 0; dc < 3; ++dc)
 #pragma unroll
-      for (int dr = -1; dr <= 1; ++dr) acc = acc + t.h[(dr + 1) + 3 * (dc + 1)] * tile[j + 1 + dc][r + 1 + dr];
+      for (int dr = 0; dr < 3; ++dr) acc = acc + t.h[dr + 3 * dc] * w[dc][dr];
     out[(size_t)c * FR_ROWS + r] = acc;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      w[0][d] = w[1][d];
+      w[1][d] = w[2][d];
+    }
   }
 }
 
@@ -303,11 +326,11 @@ int smooth_impl(pre3_ctx* ctx, const double* dsr, int F, const pre3_frame_opts& 
   Span span__(ctx, T_FRAMES);
   const Taps t = gaussian3(o.sigma);
   if (dmaxc && o.rows >= 720) {
-    k_conf_max<<<F, 256, 0, ctx->stream>>>(dsr, o.rows, F, dmaxc);
+    k_conf_max<<<F, 2 * FR_ROWS, 0, ctx->stream>>>(dsr, o.rows, F, dmaxc);
     count_launch(ctx);
   }
   if (dx && dy && dz) {
-    dim3 grid((FR_COLS + SM_TC - 1) / SM_TC, 3, F);
+    dim3 grid(FR_COLS / SM_TC, 3, F);
     if (o.boundary == 1)
       k_smooth_maps<1><<<grid, FR_ROWS, 0, ctx->stream>>>(dsr, o.rows, t, dx, dy, dz);
     else
@@ -329,7 +352,7 @@ int features_impl(pre3_ctx* ctx, const double* dsr, int F, const pre3_frame_opts
   int32_t* idx = didx ? didx : ws_take<int32_t>(ctx, (size_t)F * K);
   if (dn_oob) PRE3_CUDA(cudaMemsetAsync(dn_oob, 0, sizeof(int32_t), ctx->stream));
   if (o.rows >= 720) {
-    k_conf_max<<<F, 256, 0, ctx->stream>>>(dsr, o.rows, F, dmaxc);
+    k_conf_max<<<F, 2 * FR_ROWS, 0, ctx->stream>>>(dsr, o.rows, F, dmaxc);
     count_launch(ctx);
   }
   if (o.boundary == 1)

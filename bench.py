@@ -399,6 +399,49 @@ def bench_dr_ye(ctx, pre3, synth, dev, rank, P=1024, steps=5, warmup=2):
     return out
 
 
+def bench_frames(ctx, pre3, dev, F=2048, K=512, steps=5, warmup=2):
+    """SR4000 frame batches -> per-feature 3-D points (read_xyz_sr4000.m + the loop of
+    SIFT_extract_save.m:75-88).  Two forms: the full filtered maps (what read_xyz_sr4000 returns) and the fused
+    per-feature lookup + compaction the matching path actually needs."""
+    import torch
+    g = torch.Generator(device=dev).manual_seed(77)
+    sr = torch.empty(F, 176, 720, dtype=torch.float64, device=dev)
+    sr[:, :, 0:144] = 2.5 + torch.rand(F, 176, 144, generator=g, device=dev, dtype=torch.float64)
+    sr[:, :, 144:432] = torch.rand(F, 176, 288, generator=g, device=dev, dtype=torch.float64) * 2 - 1
+    sr[:, :, 432:720] = torch.rand(F, 176, 288, generator=g, device=dev, dtype=torch.float64) * 60000
+    fr = torch.zeros(F, K, 4, dtype=torch.float64, device=dev)
+    fr[:, :, 0] = torch.rand(F, K, generator=g, device=dev, dtype=torch.float64) * 175
+    fr[:, :, 1] = torch.rand(F, K, generator=g, device=dev, dtype=torch.float64) * 143
+    desc = torch.rand(F, K, 128, generator=g, device=dev, dtype=torch.float64)
+    o = pre3.make_frame_opts()
+    x, y, z = (torch.empty(F, 176, 144, dtype=torch.float64, device=dev) for _ in range(3))
+    mc = torch.empty(F, dtype=torch.float64, device=dev)
+    xyz = torch.empty(F, K, 3, dtype=torch.float64, device=dev)
+    nk = torch.empty(F, dtype=torch.int32, device=dev)
+    dout = torch.empty_like(desc)
+    pk = peaks()
+    out = {"workload": f"{F} SR4000 frames (720 x 176 doubles each), {K} features per frame"}
+    ms = _time_steps(lambda: ctx.read_xyz_sr4000_batch_dev(sr, o, x, y, z, mc), steps, warmup)
+    b = F * (7 * 144 * 176 * 8.0)   # read z, x, y + confidence, write z, x, y
+    out["maps"] = {"ms_per_step": ms, "frames_per_s": F / (ms * 1e-3),
+                   "roofline": {"bound": "hbm", "achieved": b / (ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                "frac": b / (ms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": None,
+                                "note": "algorithmic bytes: 3 maps in + 3 maps out + confidence map = 1.42 MB per frame"}}
+    ms = _time_steps(lambda: ctx.features_xyz_batch_dev(sr, o, fr, xyz=xyz, n_keep=nk, desc_in=desc, desc_out=dout),
+                     steps, warmup)
+    kept = float(nk.float().sum().item())
+    b = F * (144 * 176 * 8.0 + K * (27 * 8 + 8 + 32 + 24 + 1024)) + kept * 1024
+    out["fused_features"] = {"ms_per_step": ms, "frames_per_s": F / (ms * 1e-3), "mean_kept": float(nk.float().mean().item()),
+                             "roofline": {"bound": "hbm", "achieved": b / (ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"],
+                                          "unit": "GB/s", "frac": b / (ms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": None,
+                                          "note": "algorithmic bytes per frame: confidence map 203 KB + per feature 27 "
+                                                  "stencil taps, frame entry, point, 1 KB of compacted descriptor "
+                                                  "written, and 1 KB read per surviving feature"}}
+    del sr, fr, desc, x, y, z, dout
+    torch.cuda.empty_cache()
+    return out
+
+
 def bench_cfg1(ctx, pre3, synth, dev):
     """configs[0]: one synthetic SR4000 frame pair (~300 matches, 30% outliers), 2000 hypotheses: a LATENCY
     number on the GPU (one pair cannot fill the machine); k=5 (RANSAC_CALC_VER2.m:85) and k=3 (BASELINE wording)."""
@@ -464,6 +507,7 @@ def other_workloads(ctx, pre3, synth, dev, rank, world):
                 ("cfg2", lambda: bench_cfg2(ctx, pre3, synth, dev, rank)),
                 ("cfg4", lambda: bench_cfg4(ctx, pre3, dev, rank)),
                 ("dr_ye", lambda: bench_dr_ye(ctx, pre3, synth, dev, rank)),
+                ("frames", lambda: bench_frames(ctx, pre3, dev)),
                 ("cpu", lambda: cpu_other_baselines(synth))] + jobs
     # cfg5 involves every rank: run it first everywhere so that no rank waits inside a collective
     jobs.sort(key=lambda j: j[0] != "cfg5")

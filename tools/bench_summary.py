@@ -24,6 +24,11 @@ if "cfg1" in o and "error" not in o["cfg1"]:
 if "dr_ye" in o and "error" not in o["dr_ye"]:
     c = o["dr_ye"]
     print("dr_ye", round(c["pairs_per_s"]), "pairs/s", {k: round(v["ms_per_step"], 3) for k, v in c["kernels"].items()})
+if "frames" in o and "error" not in o["frames"]:
+    c = o["frames"]
+    print("frames maps", round(c["maps"]["frames_per_s"]), "frames/s, HBM frac", round(c["maps"]["roofline"]["frac"], 3),
+          "| fused", round(c["fused_features"]["frames_per_s"]), "frames/s, HBM frac",
+          round(c["fused_features"]["roofline"]["frac"], 3))
 for k, v in o.items():
     if isinstance(v, dict) and "error" in v:
         print("ERROR in", k, v["error"])

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Short single-GPU pass over every kernel family, for ncu (launch list / --set full):
 
-    python tools/prof_driver.py [cfg3] [cfg2] [cfg4] [cfg5]      (default: all four)
+    python tools/prof_driver.py [cfg3] [cfg2] [cfg4] [cfg5] [dr_ye] [frames]      (default: all)
 
 Sizes are cut down so that ~40 replays per launch stay cheap; shapes per unit are the
 BASELINE.json ones (512x512 / 2048x2048 descriptors, N=300 / 20000 correspondences, n=1213)."""
@@ -21,7 +21,7 @@ pd = importlib.import_module("3pre_b200.dist")
 
 
 def main():
-    which = sys.argv[1:] or ["cfg3", "cfg2", "cfg4", "cfg5"]
+    which = sys.argv[1:] or ["cfg3", "cfg2", "cfg4", "cfg5", "dr_ye", "frames"]
     dev = torch.device("cuda", 0)
     ctx = pre3.Context(0)
     ctx.use_torch_stream()
@@ -61,6 +61,32 @@ def main():
         for mode in ("first", "reference"):
             rec, _ = pd.ransac_hypothesis_split(ctx, Ya, Yb, opts, mode=mode, want_mask=False)
         print("cfg5", int(rec["best_fit"]), int(rec["best_sample"]))
+    if "dr_ye" in which:   # the code_from_dr_ye variant on the cfg3 shape
+        L = importlib.import_module("3pre_b200._lib")
+        P = 512
+        d = synth.make_sequence_torch(P + 1, 8100, dev)
+        opts = pre3.make_opts(method=L.METHOD_DR_YE, k=4, max_iteration=700, adaptive=False, H=700, seed=7)
+        res = torch.zeros(P, 240, dtype=torch.uint8, device=dev)
+        for _ in range(2):
+            ctx.sequence_dev(d["desc"], d["xyz"], opts, res)
+        ctx.sync()
+        del d
+    if "frames" in which:  # frames -> filtered maps / fused per-feature lookup + compaction
+        F, K = 512, 512
+        g = torch.Generator(device=dev).manual_seed(1)
+        sr = torch.rand(F, 176, 720, generator=g, device=dev, dtype=torch.float64) + 1.0
+        fr = torch.rand(F, K, 4, generator=g, device=dev, dtype=torch.float64) * 140
+        desc = torch.rand(F, K, 128, generator=g, device=dev, dtype=torch.float64)
+        o = pre3.make_frame_opts()
+        x, y, z = (torch.empty(F, 176, 144, dtype=torch.float64, device=dev) for _ in range(3))
+        mc = torch.empty(F, dtype=torch.float64, device=dev)
+        xyz = torch.empty(F, K, 3, dtype=torch.float64, device=dev)
+        nk = torch.empty(F, dtype=torch.int32, device=dev)
+        dout = torch.empty_like(desc)
+        for _ in range(2):
+            ctx.read_xyz_sr4000_batch_dev(sr, o, x, y, z, mc)
+            ctx.features_xyz_batch_dev(sr, o, fr, xyz=xyz, n_keep=nk, desc_in=desc, desc_out=dout)
+        ctx.sync()
     ctx.sync()
     print("launches", ctx.launch_count())
     ctx.close()
