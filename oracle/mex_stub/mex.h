@@ -69,6 +69,15 @@ void *mxCalloc(size_t n, size_t sz);
 void mxFree(void *p);
 mxArray *mxCreateDoubleMatrix(size_t m, size_t n, mxComplexity c);
 void mxDestroyArray(mxArray *a);
+/* additions for the product's own gateways (3pre_b200/mex_files/*.cpp): scalars and 1 x 1 structs */
+typedef size_t mwIndex;
+int mxIsEmpty(const mxArray *a);
+size_t mxGetNumberOfElements(const mxArray *a);
+mxArray *mxCreateDoubleScalar(double v);
+int mxIsStruct(const mxArray *a);
+mxArray *mxCreateStructMatrix(size_t m, size_t n, int nfields, const char **names);
+void mxSetField(mxArray *a, mwIndex i, const char *name, mxArray *v);
+mxArray *mxGetField(const mxArray *a, mwIndex i, const char *name);
 void mexErrMsgTxt(const char *msg);
 void mexErrMsgIdAndTxt(const char *id, const char *msg, ...);
 int mexPrintf(const char *fmt, ...);

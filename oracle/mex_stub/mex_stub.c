@@ -54,10 +54,67 @@ mxArray *mxCreateDoubleMatrix(size_t m, size_t n, mxComplexity c) {
   return a;
 }
 
+/* 1 x 1 structs: data -> stub_struct {nfields, names[], vals[]} */
+typedef struct {
+  int nfields;
+  const char **names;
+  mxArray **vals;
+} stub_struct;
+
 void mxDestroyArray(mxArray *a) {
   if (!a) return;
+  if (a->cls == mxSTRUCT_CLASS && a->data) {
+    stub_struct *s = (stub_struct *)a->data;
+    for (int i = 0; i < s->nfields; ++i) mxDestroyArray(s->vals[i]);
+    free(s->names);
+    free(s->vals);
+    free(s);
+    free(a);
+    return;
+  }
   if (a->owns_data) free(a->data);
   free(a);
+}
+
+int mxIsEmpty(const mxArray *a) { return a->m * a->n == 0; }
+size_t mxGetNumberOfElements(const mxArray *a) { return a->m * a->n; }
+mxArray *mxCreateDoubleScalar(double v) {
+  mxArray *a = mxCreateDoubleMatrix(1, 1, mxREAL);
+  ((double *)a->data)[0] = v;
+  return a;
+}
+int mxIsStruct(const mxArray *a) { return a->cls == mxSTRUCT_CLASS; }
+mxArray *mxCreateStructMatrix(size_t m, size_t n, int nfields, const char **names) {
+  mxArray *a = (mxArray *)calloc(1, sizeof(mxArray));
+  stub_struct *s = (stub_struct *)calloc(1, sizeof(stub_struct));
+  s->nfields = nfields;
+  s->names = (const char **)calloc((size_t)(nfields ? nfields : 1), sizeof(char *));
+  s->vals = (mxArray **)calloc((size_t)(nfields ? nfields : 1), sizeof(mxArray *));
+  for (int i = 0; i < nfields; ++i) s->names[i] = names[i];
+  a->cls = mxSTRUCT_CLASS;
+  a->m = m;
+  a->n = n;
+  a->ndim = 2;
+  a->owns_data = 0;
+  a->data = s;
+  return a;
+}
+void mxSetField(mxArray *a, mwIndex i, const char *name, mxArray *v) {
+  (void)i;
+  stub_struct *s = (stub_struct *)a->data;
+  for (int k = 0; k < s->nfields; ++k)
+    if (strcmp(s->names[k], name) == 0) {
+      mxDestroyArray(s->vals[k]);
+      s->vals[k] = v;
+    }
+}
+mxArray *mxGetField(const mxArray *a, mwIndex i, const char *name) {
+  (void)i;
+  if (a->cls != mxSTRUCT_CLASS) return 0;
+  stub_struct *s = (stub_struct *)a->data;
+  for (int k = 0; k < s->nfields; ++k)
+    if (strcmp(s->names[k], name) == 0) return s->vals[k];
+  return 0;
 }
 
 void mexErrMsgTxt(const char *msg) {

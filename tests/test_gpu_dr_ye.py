@@ -207,3 +207,61 @@ def test_device_entry_is_stream_ordered(ctx, pre3, orc, synth):
     for p in range(0, P, 7):
         g = orc.vodometry_dr_ye(cs[p].Ya, cs[p].Yb, seed=2, pair=1000 + p)
         _check(g, rec[p], mk[p], st[p], None, N)
+
+
+def test_mex_gateway_vodometry_dr_ye(orc, synth):
+    """3pre_b200/mex_files/vodometry_dr_ye_mex.cpp linked against the stub MEX runtime that also drives the
+    reference's own siftmatch.c gateway (oracle/mex_stub): called through mexFunction with mxArrays."""
+    import ctypes as C
+    import subprocess
+    from oracle import refmex
+    root = ROOT
+    out = os.path.join(root, "tests", "_build")
+    os.makedirs(out, exist_ok=True)
+    so = os.path.join(out, "libpre3_vodometry_dr_ye_gw.so")
+    libdir = os.path.join(root, "3pre_b200", "lib")
+    subprocess.run(["g++", "-O2", "-fPIC", "-shared", "-o", so,
+                    os.path.join(root, "3pre_b200", "mex_files", "vodometry_dr_ye_mex.cpp"),
+                    "-x", "c", os.path.join(root, "oracle", "mex_stub", "mex_stub.c"), "-x", "none",
+                    "-I", os.path.join(root, "oracle", "mex_stub"), "-I", os.path.join(root, "3pre_b200", "mex_files"),
+                    "-I", os.path.join(root, "include"), "-L", libdir, "-lpre3", f"-Wl,-rpath,{libdir}"], check=True)
+    L = refmex.lib(so)
+    c = synth.make_correspondences(4900, N=150, outlier_ratio=0.3)
+    match = np.stack([np.arange(150) + 1, np.random.default_rng(4).permutation(150) + 1], 1).astype(np.float64)
+    draws = synth.make_draws(4901, 700, 150)
+
+    def call(args, nout):
+        keep = [np.ascontiguousarray(a, np.float64) for a in args]
+        ins = [L.stub_wrap(6, a.shape[1] if a.ndim == 2 else 1, a.shape[0], a.ctypes.data) for a in keep]
+        in_arr = (C.POINTER(refmex._MxArray) * len(ins))(*ins)
+        out_arr = (C.POINTER(refmex._MxArray) * nout)()
+        rc = L.stub_call_mex(nout, out_arr, len(ins), in_arr)
+        for a in ins:
+            L.mxDestroyArray(a)
+        if rc != 0:
+            raise refmex.MexError(L.stub_last_error().decode())
+        res = []
+        for i in range(nout):
+            m = out_arr[i].contents
+            res.append(np.ctypeslib.as_array(C.cast(m.data, C.POINTER(C.c_double)), shape=(m.n, m.m)).copy().T
+                       if m.cls == 6 and m.m * m.n else np.zeros((m.m, m.n)))
+            L.mxDestroyArray(out_arr[i])
+        return res
+
+    # arrays are passed as (columns, rows) C-contiguous = MATLAB column-major rows x columns
+    rot, trans, sta, op_num, good = call([c.Ya, c.Yb, match, (draws + 1).astype(np.float64)], 5)
+    o = orc.vodometry_dr_ye(c.Ya, c.Yb, samples=draws)
+    assert sta[0, 0] == o.state == 1 and op_num[0, 0] == o.op_num
+    np.testing.assert_array_equal(good.ravel().astype(int) - 1, np.flatnonzero(o.mask))
+    assert rn.rot_angle(rot, o.R) < 1e-9 and np.abs(trans.ravel() - o.T).max() < 1e-9
+    # seeded form: a scalar in place of the draws
+    rot2, _, sta2, op2 = call([c.Ya, c.Yb, match, np.array([[5.0]])], 4)
+    o2 = orc.vodometry_dr_ye(c.Ya, c.Yb, match=match.astype(np.int32), seed=5, pair=0)
+    assert op2[0, 0] == o2.op_num and rn.rot_angle(rot2, o2.R) < 1e-9
+    with pytest.raises(refmex.MexError, match="same size"):
+        call([c.Ya, c.Yb[:10], match], 1)
+    with pytest.raises(refmex.MexError, match="required"):
+        call([c.Ya, c.Yb], 1)
+    # fewer than 4 matches: SolutionState 4, no error (vodometry_dr_ye.m:152-160)
+    _, _, sta3, op3 = call([c.Ya[:3], c.Yb[:3], match[:3]], 4)
+    assert sta3[0, 0] == 4 and op3[0, 0] == 0
