@@ -15,7 +15,7 @@ OK, ERR_ARG, ERR_CUDA, ERR_ALLOC, ERR_CLASS = 0, -1, -2, -3, -4
 CLASS_DOUBLE, CLASS_SINGLE, CLASS_INT8, CLASS_UINT8 = 0, 1, 2, 3
 METHOD_SVD, METHOD_HORN, METHOD_DR_YE = 0, 1, 2
 MATCH_AUTO, MATCH_EXACT, MATCH_TC = 0, 1, 2
-TIMING_NCAT = 13
+TIMING_NCAT = 14
 
 
 class RansacOpts(C.Structure):
@@ -111,6 +111,9 @@ SYMBOLS = {
     "pre3_ransac": (_I, [_VP, _VP, _VP, _I, _OPTS, _VP, _VP, _VP, _VP, _VP]),
     "pre3_ransac_batch": (_I, [_VP, _VP, _VP, _VP, _I, _I, _OPTS, _VP, _VP, _VP]),
     "pre3_ransac_batch_dev": (_I, [_VP, _VP, _VP, _VP, _I, _I, _OPTS, _VP, _VP, _VP]),
+    "pre3_ekf_update_batch": (_I, [_VP, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _D, _VP, _VP, _VP]),
+    "pre3_ekf_update_batch_dev": (_I, [_VP, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _D, _VP, _VP, _VP]),
+    "pre3_ekf_rescue_hi_inliers_batch_dev": (_I, [_VP, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "pre3_read_xyz_sr4000_batch": (_I, [_VP, _VP, _I, C.POINTER(FrameOpts), _VP, _VP, _VP, _VP]),
     "pre3_read_xyz_sr4000_batch_dev": (_I, [_VP, _VP, _I, C.POINTER(FrameOpts), _VP, _VP, _VP, _VP]),
     "pre3_features_xyz_batch": (_I, [_VP, _VP, _I, C.POINTER(FrameOpts), _VP, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP,

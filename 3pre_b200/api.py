@@ -574,6 +574,47 @@ class Context:
             _ptr(frames["h"]), _ptr(frames["Hcam"]), _ptr(frames["Hfeat"]), _ptr(frames["R"]), _ptr(sel),
             C.byref(opts), int(frame_id0), _ptr(li_inlier), _ptr(res), _ptr(supports)))
 
+    # ---- EKF partial updates (first part) ------------------------------
+    def ekf_update_batch(self, frames: dict, sel, r_diag=1.0, x=None, P=None):
+        """update.m:27-56 with z, h, H stacked from the features flagged in sel (Fr,F) uint8 and R = r_diag * eye:
+        ekf_update_li_inliers.m / ekf_update_hi_inliers.m.  `frames` as in ransac_hypotheses_batch; x / P override
+        frames['x'] / frames['P'] (the hi-inlier update runs on x_k_k / p_k_k).  Returns (x_k_k (Fr,n), p_k_k (Fr,n,n)
+        column-major per frame, m (Fr,) rows of the stacked system)."""
+        x = _c(frames["x"] if x is None else x, np.float64)
+        P = _c(frames["P"] if P is None else P, np.float64)
+        Fr, n = x.shape
+        F = np.asarray(frames["type"]).shape[1]
+        sel = _c(sel, np.uint8)
+        ty, po = _c(frames["type"], np.int32), _c(frames["pos"], np.int32)
+        z, h = _c(frames["z"], np.float64), _c(frames["h"], np.float64)
+        Hc, Hf = _c(frames["Hcam"], np.float64), _c(frames["Hfeat"], np.float64)
+        xo, Po, m = np.zeros_like(x), np.zeros_like(P), np.zeros(max(Fr, 1), np.int32)
+        self._ck(self._lib.pre3_ekf_update_batch(self._h, Fr, n, F, _ptr(x), _ptr(P), _ptr(ty), _ptr(po), _ptr(sel),
+                                                 _ptr(z), _ptr(h), _ptr(Hc), _ptr(Hf), float(r_diag), _ptr(xo), _ptr(Po),
+                                                 _ptr(m)))
+        return xo, Po, m[:Fr]
+
+    def ekf_update_batch_dev(self, frames: dict, sel, x_out, P_out, r_diag=1.0, x=None, P=None, m_out=None):
+        """Same on CUDA tensors (make_ekf_frames(device='cuda') layout); stream-ordered, no sync."""
+        x = frames["x"] if x is None else x
+        P = frames["P"] if P is None else P
+        Fr, n = x.shape
+        F = frames["type"].shape[1]
+        self._ck(self._lib.pre3_ekf_update_batch_dev(self._h, Fr, n, F, _ptr(x), _ptr(P), _ptr(frames["type"]),
+                                                     _ptr(frames["pos"]), _ptr(sel), _ptr(frames["z"]),
+                                                     _ptr(frames["h"]), _ptr(frames["Hcam"]), _ptr(frames["Hfeat"]),
+                                                     float(r_diag), _ptr(x_out), _ptr(P_out), _ptr(m_out)))
+
+    def ekf_rescue_hi_inliers_batch_dev(self, frames: dict, P_kk, li, hi, h=None, Hcam=None, Hfeat=None):
+        """rescue_hi_inliers.m:35-46 on CUDA tensors: hi (Fr,F) uint8 is written where ic == 1 and li == 0.
+        h / Hcam / Hfeat: the measurements re-predicted at x_k_k (default: the frames' own)."""
+        Fr, F = frames["type"].shape
+        n = frames["x"].shape[1]
+        self._ck(self._lib.pre3_ekf_rescue_hi_inliers_batch_dev(
+            self._h, Fr, n, F, _ptr(P_kk), _ptr(frames["type"]), _ptr(frames["pos"]), _ptr(frames["ic"]), _ptr(li),
+            _ptr(frames["z"]), _ptr(frames["h"] if h is None else h), _ptr(frames["Hcam"] if Hcam is None else Hcam),
+            _ptr(frames["Hfeat"] if Hfeat is None else Hfeat), _ptr(hi)))
+
     # ---- device-pointer entry points (torch CUDA tensors, stream-ordered, no sync) --------
     def pairs_dev(self, desc1, desc2, xyz1, xyz2, opts: RansacOpts, res, matches=None, masks=None, pair_id0=0,
                   k1_count=None, k2_count=None):

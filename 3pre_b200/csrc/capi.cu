@@ -254,7 +254,7 @@ int pre3_timing_read(pre3_ctx* ctx, double* ms, int64_t* count) {
 const char* pre3_timing_name(int cat) {
   static const char* names[T_NCAT] = {"convert", "match_tc", "match_exact", "rescore", "compact",
                                       "prep",    "eval",     "select",      "other",   "ekf_gain",
-                                      "ekf_score", "ekf_select", "frames"};
+                                      "ekf_score", "ekf_select", "frames", "ekf_update"};
   return (cat >= 0 && cat < T_NCAT) ? names[cat] : "?";
 }
 

@@ -1,0 +1,612 @@
+// ekf_update.cu -- the EKF partial updates around ransac_hypotheses (first part).
+//
+// Reference:
+//   M/update.m:27-56                                 S = H P H' + R;  K = P H' inv(S);  x + K (z - h);  P - K S K';
+//                                                    0.5 P + 0.5 P';  quaternion normalisation Jacobian; q / |q|
+//   M/@ekf_filter/ekf_update_li_inliers.m:15-29      z, h, H stacked from the low-innovation inliers, R = eye
+//   M/@ekf_filter/ekf_update_hi_inliers.m:18-32      the same from the high-innovation inliers, on x_k_k / p_k_k
+//   M/@ekf_filter/rescue_hi_inliers.m:35-46          nu' inv(H p_k_k H') nu < 5.9915
+//   M/normJac.m:1-16
+// Checker: oracle/ref_numpy_ekf.py (update, ekf_update_inliers, rescue_hi_inliers) -- dense numpy / LAPACK.  This is a
+// floating-point path (dense fp64 linear algebra): results are specified to a tolerance (1e-9 relative to max|P|), not
+// bit for bit, so the kernels use fused multiply-adds (explicit fma(): the translation unit is compiled -fmad=false).
+//
+// Per frame, with n states (cfg4: 1213) and m = 2 x (flagged features) stacked rows (cfg4: ~320):
+//   k_upd_index   flagged features in feature order, m
+//   k_upd_G       G = P H'            n x m   19 structural non-zeros of H per row (13 camera + 6 feature columns)
+//   k_upd_S       S = H G + I         m x m
+//   k_upd_inv     inv(S)              in-place Gauss-Jordan with partial pivoting, one block per frame   2 m^3 FLOP
+//   k_dgemm       K = G inv(S)        n x m x m  |  T = K S   n x m x m  |  P' = P - T K'   n x n x m    (2 n^2 m FLOP: the bulk)
+//   k_upd_x       x + K (z - h)
+//   k_upd_sym     0.5 P' + 0.5 P''    tiled transpose
+//   k_upd_quat    rows / columns 4:7 through normJac, q / |q|
+// Everything is column-major like MATLAB.
+#include <cmath>
+
+#include "common.cuh"
+
+namespace pre3 {
+namespace {
+
+struct UpdDims {
+  int n, F, Mmax;  // Mmax = 2 F
+};
+
+// ---- flagged features in order ----------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_upd_index(const uint8_t* __restrict__ sel, int F, int32_t* __restrict__ idx,
+                                                   int32_t* __restrict__ m_out) {
+  __shared__ int s_w[8];
+  __shared__ int s_base;
+  const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  for (int i0 = 0; i0 < F; i0 += 256) {
+    const int i = i0 + tid;
+    const bool on = i < F && sel[(size_t)f * F + i] == 1;
+    const unsigned bal = __ballot_sync(0xffffffffu, on);
+    if (lane == 0) s_w[warp] = __popc(bal);
+    __syncthreads();
+    int off = s_base + __popc(bal & ((1u << lane) - 1u)), tot = 0;
+    for (int w = 0; w < 8; ++w) {
+      if (w < warp) off += s_w[w];
+      tot += s_w[w];
+    }
+    if (on) idx[(size_t)f * F + off] = i;
+    __syncthreads();
+    if (tid == 0) s_base += tot;
+    __syncthreads();
+  }
+  if (tid == 0) m_out[f] = 2 * s_base;
+}
+
+// column c of H row (feature i, component a): cols 0..12 camera, then pos .. pos+5 (cartesian: 3)
+__device__ __forceinline__ int h_col(int t, int pos) { return t < 13 ? t : pos + (t - 13); }
+__device__ __forceinline__ double h_val(int t, int a, const double* __restrict__ hc, const double* __restrict__ hf) {
+  return t < 13 ? hc[2 * t + a] : hf[2 * (t - 13) + a];  // 2 x 13 / 2 x 6 column-major blocks
+}
+
+// G(:, 2 j + a) = sum_t P(:, col_t) H(a, col_t): grid (row tiles, m columns, frames)
+__global__ void __launch_bounds__(256)
+k_upd_G(const double* __restrict__ P, UpdDims d, const int32_t* __restrict__ idx, const int32_t* __restrict__ mf,
+        const int32_t* __restrict__ type, const int32_t* __restrict__ pos, const double* __restrict__ Hcam,
+        const double* __restrict__ Hfeat, double* __restrict__ G) {
+  const int f = blockIdx.z, col = blockIdx.y;
+  if (col >= mf[f]) return;
+  const int i = idx[(size_t)f * d.F + (col >> 1)], a = col & 1;
+  const int r = blockIdx.x * 256 + threadIdx.x;
+  if (r >= d.n) return;
+  const size_t fi = (size_t)f * d.F + i;
+  const double* hc = Hcam + fi * 26;
+  const double* hf = Hfeat + fi * 12;
+  const int ps = pos[fi], nz = 13 + (type[fi] == 0 ? 6 : 3);
+  const double* Pf = P + (size_t)f * d.n * d.n;
+  double acc = 0.0;
+  for (int t = 0; t < nz; ++t) acc = fma(Pf[(size_t)h_col(t, ps) * d.n + r], h_val(t, a, hc, hf), acc);
+  G[((size_t)f * d.Mmax + col) * d.n + r] = acc;
+}
+
+// S(ra, cb) = sum_t H(ra, col_t) G(col_t, cb) + (ra == cb); grid (m tiles, m, frames)
+__global__ void __launch_bounds__(128)
+k_upd_S(const double* __restrict__ G, UpdDims d, const int32_t* __restrict__ idx, const int32_t* __restrict__ mf,
+        const int32_t* __restrict__ type, const int32_t* __restrict__ pos, const double* __restrict__ Hcam,
+        const double* __restrict__ Hfeat, double r_diag, double* __restrict__ S) {
+  const int f = blockIdx.z, cb = blockIdx.y, m = mf[f];
+  const int ra = blockIdx.x * 128 + threadIdx.x;
+  if (cb >= m || ra >= m) return;
+  const int i = idx[(size_t)f * d.F + (ra >> 1)], a = ra & 1;
+  const size_t fi = (size_t)f * d.F + i;
+  const double* hc = Hcam + fi * 26;
+  const double* hf = Hfeat + fi * 12;
+  const int ps = pos[fi], nz = 13 + (type[fi] == 0 ? 6 : 3);
+  const double* g = G + ((size_t)f * d.Mmax + cb) * d.n;
+  double acc = 0.0;
+  for (int t = 0; t < nz; ++t) acc = fma(h_val(t, a, hc, hf), g[h_col(t, ps)], acc);
+  S[((size_t)f * d.Mmax + cb) * d.Mmax + ra] = acc + (ra == cb ? r_diag : 0.0);
+}
+
+// In-place Gauss-Jordan inversion with partial pivoting, one block per frame.  A: m x m column-major, ld = Mmax.
+constexpr int INV_THREADS = 1024;
+__global__ void __launch_bounds__(INV_THREADS)
+k_upd_inv(double* __restrict__ Sinv, int Mmax, const int32_t* __restrict__ mf, int32_t* __restrict__ piv_ws,
+          int32_t* __restrict__ singular) {
+  extern __shared__ double sm[];  // rowk[Mmax], colk[Mmax]
+  double* rowk = sm;
+  double* colk = sm + Mmax;
+  __shared__ double s_v[32];
+  __shared__ int s_i[32];
+  __shared__ int s_p;
+  const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int m = mf[f];
+  double* A = Sinv + (size_t)f * Mmax * Mmax;
+  int32_t* piv = piv_ws + (size_t)f * Mmax;
+  for (int k = 0; k < m; ++k) {
+    // pivot: first maximum of |A(r, k)|, r >= k
+    double bv = -1.0;
+    int bi = 0x7fffffff;
+    for (int r = k + tid; r < m; r += INV_THREADS) {
+      const double v = fabs(A[(size_t)k * Mmax + r]);
+      if (v > bv) {
+        bv = v;
+        bi = r;
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+      if (ov > bv || (ov == bv && oi < bi)) {
+        bv = ov;
+        bi = oi;
+      }
+    }
+    if (lane == 0) {
+      s_v[warp] = bv;
+      s_i[warp] = bi;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double v = s_v[0];
+      int p = s_i[0];
+      for (int w = 1; w < INV_THREADS / 32; ++w)
+        if (s_v[w] > v || (s_v[w] == v && s_i[w] < p)) {
+          v = s_v[w];
+          p = s_i[w];
+        }
+      if (p == 0x7fffffff) p = k;  // a column of NaNs: no pivot found
+      s_p = p;
+      piv[k] = p;
+      if (!(v > 0.0)) *singular = 1;
+    }
+    __syncthreads();
+    const int p = s_p;
+    // swap rows k and p, and stage row k (after the swap) and column k (after the swap)
+    for (int j = tid; j < m; j += INV_THREADS) {
+      double ak = A[(size_t)j * Mmax + k];
+      if (p != k) {
+        const double ap = A[(size_t)j * Mmax + p];
+        A[(size_t)j * Mmax + p] = ak;
+        ak = ap;
+      }
+      rowk[j] = ak;
+    }
+    __syncthreads();
+    for (int r = tid; r < m; r += INV_THREADS) {
+      double v = A[(size_t)k * Mmax + r];
+      if (r == k) v = rowk[k];
+      else if (r == p) v = A[(size_t)k * Mmax + p];  // already swapped in place by the loop above (j == k wrote it)
+      colk[r] = v;
+    }
+    __syncthreads();
+    const double dinv = 1.0 / rowk[k];
+    // A(k, j) = rowk(j) * d (j != k), A(k,k) = d;  A(i, j) -= colk(i) * rowk(j) * d (i != k, j != k);  A(i, k) = -colk(i) * d
+    for (int j = warp; j < m; j += INV_THREADS / 32) {  // 32 x 32 thread grid: lanes along rows (coalesced)
+      const double rj = rowk[j] * dinv;
+      double* col = A + (size_t)j * Mmax;
+      for (int i = lane; i < m; i += 32) {
+        double v;
+        if (i == k) {
+          v = j == k ? dinv : rj;
+        } else if (j == k) {
+          v = -colk[i] * dinv;
+        } else {
+          v = fma(-colk[i], rj, col[i]);
+        }
+        col[i] = v;
+      }
+    }
+    __syncthreads();
+  }
+  // undo the row exchanges: columns in reverse order
+  for (int k = m - 1; k >= 0; --k) {
+    const int p = piv[k];
+    if (p != k)
+      for (int r = tid; r < m; r += INV_THREADS) {
+        const double a = A[(size_t)k * Mmax + r], b = A[(size_t)p * Mmax + r];
+        A[(size_t)k * Mmax + r] = b;
+        A[(size_t)p * Mmax + r] = a;
+      }
+    __syncthreads();
+  }
+}
+
+// ---- fp64 GEMM, column-major:  C = A B  (TRANSB 0)  or  C = D - A B'  (TRANSB 1) -------------------
+//   A: M x Kd (lda), B: Kd x N (ldb) or N x Kd (ldb) when transposed, per-frame Kd = mf[f] (and N = mf[f] when NFROMM).
+// 64 x 64 tile per 256-thread block, 16-deep k slices through shared memory, 4 x 4 outputs per thread with rows
+// tx + 16 i (conflict-free 128-byte smem reads, coalesced stores) and columns ty + 16 j (broadcast reads).
+constexpr int GM = 64, GN = 64, GK = 16;
+template <int TRANSB>
+__global__ void __launch_bounds__(256)
+k_dgemm(const double* __restrict__ A, int lda, size_t strideA, const double* __restrict__ B, int ldb, size_t strideB,
+        double* __restrict__ C, int ldc, size_t strideC, const double* __restrict__ D, int ldd, size_t strideD, int M,
+        int N, const int32_t* __restrict__ mf, int n_from_m) {
+  __shared__ double As[GK][GM];
+  __shared__ double Bs[GK][GN + 1];
+  const int f = blockIdx.z;
+  const int Kd = mf[f];
+  if (n_from_m) N = Kd;
+  const int m0 = blockIdx.x * GM, n0 = blockIdx.y * GN;
+  if (m0 >= M || n0 >= N) return;
+  A += (size_t)f * strideA;
+  B += (size_t)f * strideB;
+  C += (size_t)f * strideC;
+  if (D) D += (size_t)f * strideD;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  double acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+  for (int k0 = 0; k0 < Kd; k0 += GK) {
+    // A tile: 64 rows x 16 k, contiguous along rows
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int mm = tid & 63, kk = (tid >> 6) + 4 * it;
+      const int gr = m0 + mm, gk = k0 + kk;
+      As[kk][mm] = (gr < M && gk < Kd) ? A[(size_t)gk * lda + gr] : 0.0;
+    }
+    if (TRANSB) {  // B(k, j) = Bp[k * ldb + j]: contiguous along j
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int jj = tid & 63, kk = (tid >> 6) + 4 * it;
+        const int gj = n0 + jj, gk = k0 + kk;
+        Bs[kk][jj] = (gj < N && gk < Kd) ? B[(size_t)gk * ldb + gj] : 0.0;
+      }
+    } else {  // B(k, j) = Bp[j * ldb + k]: contiguous along k
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int kk = tid & 15, jj = (tid >> 4) + 16 * it;
+        const int gj = n0 + jj, gk = k0 + kk;
+        Bs[kk][jj] = (gj < N && gk < Kd) ? B[(size_t)gj * ldb + gk] : 0.0;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < GK; ++kk) {
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][tx + 16 * i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][ty + 16 * j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int gc = n0 + ty + 16 * j;
+    if (gc >= N) continue;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int gr = m0 + tx + 16 * i;
+      if (gr >= M) continue;
+      const double v = acc[i][j];
+      C[(size_t)gc * ldc + gr] = TRANSB ? D[(size_t)gc * ldd + gr] - v : v;
+    }
+  }
+}
+
+// x_out = x + K (z - h) over the flagged features (m == 0: x_out = x)
+__global__ void __launch_bounds__(256)
+k_upd_x(const double* __restrict__ x, const double* __restrict__ K, UpdDims d, const int32_t* __restrict__ idx,
+        const int32_t* __restrict__ mf, const double* __restrict__ z, const double* __restrict__ h,
+        double* __restrict__ x_out) {
+  extern __shared__ double s_d[];  // z - h, m entries
+  const int f = blockIdx.y, m = mf[f];
+  for (int j = threadIdx.x; j < m; j += 256) {
+    const size_t fi = (size_t)f * d.F + idx[(size_t)f * d.F + (j >> 1)];
+    s_d[j] = z[fi * 2 + (j & 1)] - h[fi * 2 + (j & 1)];
+  }
+  __syncthreads();
+  const int r = blockIdx.x * 256 + threadIdx.x;
+  if (r >= d.n) return;
+  const double* Kf = K + (size_t)f * d.Mmax * d.n;
+  double acc = 0.0;
+  for (int j = 0; j < m; ++j) acc = fma(Kf[(size_t)j * d.n + r], s_d[j], acc);
+  x_out[(size_t)f * d.n + r] = x[(size_t)f * d.n + r] + acc;
+}
+
+// P_out = 0.5 P' + 0.5 P''  (m == 0: P_out = P_in untouched: update.m:52-53); 32 x 32 tiles
+__global__ void __launch_bounds__(256)
+k_upd_sym(const double* __restrict__ Pp, const double* __restrict__ Pin, int n, const int32_t* __restrict__ mf,
+          double* __restrict__ Pout) {
+  __shared__ double t[32][33];
+  const int f = blockIdx.z;
+  const size_t base = (size_t)f * n * n;
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  if (mf[f] == 0) {
+    for (int j = ty; j < 32; j += 8) {
+      const int r = r0 + tx, c = c0 + j;
+      if (r < n && c < n) Pout[base + (size_t)c * n + r] = Pin[base + (size_t)c * n + r];
+    }
+    return;
+  }
+  for (int j = ty; j < 32; j += 8) {  // transposed block: rows c0.., columns r0..
+    const int r = c0 + tx, c = r0 + j;
+    t[j][tx] = (r < n && c < n) ? Pp[base + (size_t)c * n + r] : 0.0;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int r = r0 + tx, c = c0 + j;
+    if (r < n && c < n) Pout[base + (size_t)c * n + r] = 0.5 * Pp[base + (size_t)c * n + r] + 0.5 * t[tx][j];
+  }
+}
+
+// rows / columns 4:7 (0-based 3..6) through Jnorm = normJac(x_k_k(4:7)) (update.m:42-46), then q / |q| (:48)
+__global__ void __launch_bounds__(256)
+k_upd_quat(double* __restrict__ P, double* __restrict__ x, int n, const int32_t* __restrict__ mf) {
+  __shared__ double J[16];
+  __shared__ double q44[16], tmp[16];
+  const int f = blockIdx.x;
+  if (mf[f] == 0) return;
+  double* Pf = P + (size_t)f * n * n;
+  double* xf = x + (size_t)f * n;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    const double r = xf[3], a = xf[4], b = xf[5], c = xf[6];
+    const double s2 = ((r * r + a * a) + b * b) + c * c;
+    const double sc = 1.0 / (s2 * sqrt(s2));  // ^(-3/2)
+    const double M[16] = {a * a + b * b + c * c, -r * a, -r * b, -r * c,   // row 0
+                          -a * r, r * r + b * b + c * c, -a * b, -a * c,   // row 1
+                          -b * r, -b * a, r * r + a * a + c * c, -b * c,   // row 2
+                          -c * r, -c * a, -c * b, r * r + a * a + b * b};  // row 3
+    for (int i = 0; i < 16; ++i) J[i] = sc * M[i];  // J[4 * row + col]
+  }
+  if (tid < 16) q44[tid] = Pf[(size_t)(3 + (tid >> 2)) * n + 3 + (tid & 3)];  // q44[4 * col + row]
+  __syncthreads();
+  // columns 3..6 for the rows outside the quaternion: p(r, 4:7) * Jnorm'  and the mirrored rows Jnorm * p(4:7, c)
+  for (int r = tid; r < n; r += 256) {
+    if (r >= 3 && r < 7) continue;
+    double v[4], o[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) v[b] = Pf[(size_t)(3 + b) * n + r];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      double acc = 0.0;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc = fma(v[b], J[4 * a + b], acc);
+      o[a] = acc;
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      Pf[(size_t)(3 + a) * n + r] = o[a];  // column block
+      Pf[(size_t)r * n + 3 + a] = o[a];    // row block (P is symmetric after k_upd_sym)
+    }
+  }
+  // 4 x 4 block: (Jnorm * p44) * Jnorm'
+  if (tid < 16) {
+    const int a = tid >> 2, c = tid & 3;  // tmp(a, c) = sum_b J(a, b) p44(b, c)
+    double acc = 0.0;
+    for (int b = 0; b < 4; ++b) acc = fma(J[4 * a + b], q44[4 * c + b], acc);
+    tmp[4 * a + c] = acc;
+  }
+  __syncthreads();
+  if (tid < 16) {
+    const int a = tid >> 2, c = tid & 3;  // out(a, c) = sum_b tmp(a, b) J(c, b)
+    double acc = 0.0;
+    for (int b = 0; b < 4; ++b) acc = fma(tmp[4 * a + b], J[4 * c + b], acc);
+    Pf[(size_t)(3 + c) * n + 3 + a] = acc;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const double nq = sqrt(((xf[3] * xf[3] + xf[4] * xf[4]) + xf[5] * xf[5]) + xf[6] * xf[6]);
+    for (int i = 3; i < 7; ++i) xf[i] = xf[i] / nq;
+  }
+}
+
+// rescue_hi_inliers.m:35-46: one thread per feature
+__global__ void __launch_bounds__(128)
+k_upd_rescue(const double* __restrict__ P, int n, int F, const int32_t* __restrict__ type,
+             const int32_t* __restrict__ pos, const uint8_t* __restrict__ ic, const uint8_t* __restrict__ li,
+             const double* __restrict__ z, const double* __restrict__ h, const double* __restrict__ Hcam,
+             const double* __restrict__ Hfeat, double chi2, uint8_t* __restrict__ hi) {
+  const int f = blockIdx.y, i = blockIdx.x * 128 + threadIdx.x;
+  if (i >= F) return;
+  const size_t fi = (size_t)f * F + i;
+  if (!(ic[fi] == 1 && li[fi] == 0)) return;  // the reference leaves high_innovation_inlier untouched
+  const double* Pf = P + (size_t)f * n * n;
+  const double* hc = Hcam + fi * 26;
+  const double* hf = Hfeat + fi * 12;
+  const int ps = pos[fi], nz = 13 + (type[fi] == 0 ? 6 : 3);
+  double s00 = 0.0, s01 = 0.0, s10 = 0.0, s11 = 0.0;
+  for (int t = 0; t < nz; ++t) {  // (H P)(a, col_t) then times H'
+    double g0 = 0.0, g1 = 0.0;
+    const int ct = h_col(t, ps);
+    for (int u = 0; u < nz; ++u) {
+      const double p = Pf[(size_t)ct * n + h_col(u, ps)];
+      g0 = fma(h_val(u, 0, hc, hf), p, g0);
+      g1 = fma(h_val(u, 1, hc, hf), p, g1);
+    }
+    const double h0 = h_val(t, 0, hc, hf), h1 = h_val(t, 1, hc, hf);
+    s00 = fma(g0, h0, s00);
+    s01 = fma(g0, h1, s01);
+    s10 = fma(g1, h0, s10);
+    s11 = fma(g1, h1, s11);
+  }
+  const double det = s00 * s11 - s01 * s10;
+  const double n0 = z[fi * 2] - h[fi * 2], n1 = z[fi * 2 + 1] - h[fi * 2 + 1];
+  // nu' inv(S) nu with inv(S) = [s11 -s01; -s10 s00] / det
+  const double q = (n0 * (s11 * n0 - s01 * n1) + n1 * (s00 * n1 - s10 * n0)) / det;
+  hi[fi] = q < chi2 ? 1 : 0;
+}
+
+#define UPD_LIVE()                                                                                         \
+  do {                                                                                                     \
+    if (!ctx) return PRE3_ERR_ARG;                                                                         \
+    if (ctx->device < 0) return fail(ctx, PRE3_ERR_CUDA, "no CUDA device (libpre3 has no CPU fallback)"); \
+    PRE3_CUDA(cudaSetDevice(ctx->device));                                                                 \
+  } while (0)
+
+size_t upd_ws_per_frame(int n, int F) {
+  const size_t M = 2 * (size_t)F;
+  return 3 * align_up(8 * (size_t)n * M) + 2 * align_up(8 * M * M) + align_up(8 * (size_t)n * n) + align_up(4 * (size_t)F) +
+         align_up(4 * M) + 512;
+}
+
+int frames_per_chunk(int Fr, int n, int F) {
+  const size_t budget = (size_t)2 << 30;
+  const size_t per = upd_ws_per_frame(n, F);
+  return (int)std::max<size_t>(1, std::min<size_t>((size_t)Fr, budget / per));
+}
+
+int update_chunk(pre3_ctx* ctx, int C, int n, int F, const double* dx, const double* dP, const int32_t* dtype,
+                 const int32_t* dpos, const uint8_t* dsel, const double* dz, const double* dh, const double* dHcam,
+                 const double* dHfeat, double r_diag, double* dx_out, double* dP_out, int32_t* dm_out) {
+  Span span__(ctx, T_EKF_UPDATE);
+  const UpdDims d{n, F, 2 * F};
+  const size_t M = (size_t)d.Mmax;
+  double* G = ws_take<double>(ctx, (size_t)C * n * M);
+  double* K = ws_take<double>(ctx, (size_t)C * n * M);
+  double* T = ws_take<double>(ctx, (size_t)C * n * M);
+  double* S = ws_take<double>(ctx, (size_t)C * M * M);
+  double* Si = ws_take<double>(ctx, (size_t)C * M * M);
+  double* Pp = ws_take<double>(ctx, (size_t)C * n * n);
+  int32_t* idx = ws_take<int32_t>(ctx, (size_t)C * F);
+  int32_t* piv = ws_take<int32_t>(ctx, (size_t)C * M);
+  int32_t* mf = dm_out ? dm_out : ws_take<int32_t>(ctx, C);
+  int32_t* sing = ws_take<int32_t>(ctx, 1);
+  cudaStream_t st = ctx->stream;
+  PRE3_CUDA(cudaMemsetAsync(sing, 0, 4, st));
+  k_upd_index<<<C, 256, 0, st>>>(dsel, F, idx, mf);
+  k_upd_G<<<dim3((n + 255) / 256, d.Mmax, C), 256, 0, st>>>(dP, d, idx, mf, dtype, dpos, dHcam, dHfeat, G);
+  k_upd_S<<<dim3((d.Mmax + 127) / 128, d.Mmax, C), 128, 0, st>>>(G, d, idx, mf, dtype, dpos, dHcam, dHfeat, r_diag, S);
+  PRE3_CUDA(cudaMemcpyAsync(Si, S, 8 * (size_t)C * M * M, cudaMemcpyDeviceToDevice, st));
+  k_upd_inv<<<C, INV_THREADS, 2 * M * sizeof(double), st>>>(Si, d.Mmax, mf, piv, sing);
+  const dim3 g1((n + GM - 1) / GM, (d.Mmax + GN - 1) / GN, C), g2((n + GM - 1) / GM, (n + GN - 1) / GN, C);
+  // K = G inv(S);  T = K S;  P' = P - T K'
+  k_dgemm<0><<<g1, 256, 0, st>>>(G, n, (size_t)n * M, Si, d.Mmax, M * M, K, n, (size_t)n * M, nullptr, 0, 0, n, 0, mf, 1);
+  k_dgemm<0><<<g1, 256, 0, st>>>(K, n, (size_t)n * M, S, d.Mmax, M * M, T, n, (size_t)n * M, nullptr, 0, 0, n, 0, mf, 1);
+  k_dgemm<1><<<g2, 256, 0, st>>>(T, n, (size_t)n * M, K, n, (size_t)n * M, Pp, n, (size_t)n * n, dP, n, (size_t)n * n, n, n,
+                                 mf, 0);
+  k_upd_x<<<dim3((n + 255) / 256, C), 256, M * sizeof(double), st>>>(dx, K, d, idx, mf, dz, dh, dx_out);
+  k_upd_sym<<<dim3((n + 31) / 32, (n + 31) / 32, C), 256, 0, st>>>(Pp, dP, n, mf, dP_out);
+  k_upd_quat<<<C, 256, 0, st>>>(dP_out, dx_out, n, mf);
+  count_launch(ctx, 10);
+  PRE3_CUDA(cudaGetLastError());
+  return PRE3_OK;
+}
+
+int update_impl(pre3_ctx* ctx, int Fr, int n, int F, const double* dx, const double* dP, const int32_t* dtype,
+                const int32_t* dpos, const uint8_t* dsel, const double* dz, const double* dh, const double* dHcam,
+                const double* dHfeat, double r_diag, double* dx_out, double* dP_out, int32_t* dm_out) {
+  const int C = frames_per_chunk(Fr, n, F);
+  for (int f0 = 0; f0 < Fr; f0 += C) {
+    const int c = std::min(C, Fr - f0);
+    ctx->ws_off = 0;  // the chunks reuse the arena in stream order
+    const size_t fF = (size_t)f0 * F;
+    PRE3_TRY(update_chunk(ctx, c, n, F, dx + (size_t)f0 * n, dP + (size_t)f0 * n * n, dtype + fF, dpos + fF, dsel + fF,
+                          dz + 2 * fF, dh + 2 * fF, dHcam + 26 * fF, dHfeat + 12 * fF, r_diag, dx_out + (size_t)f0 * n,
+                          dP_out + (size_t)f0 * n * n, dm_out ? dm_out + f0 : nullptr));
+  }
+  return PRE3_OK;
+}
+
+int check_upd(pre3_ctx* ctx, int Fr, int n, int F) {
+  if (Fr < 0 || n < 13 || F < 0) return fail(ctx, PRE3_ERR_ARG, "bad sizes (n >= 13: the camera states)");
+  if (2 * (size_t)F * 2 * sizeof(double) > 200 * 1024)
+    return fail(ctx, PRE3_ERR_ARG, "too many features per frame for the inversion kernel's shared memory");
+  return PRE3_OK;
+}
+
+}  // namespace
+}  // namespace pre3
+
+using namespace pre3;
+
+extern "C" {
+
+int pre3_ekf_update_batch_dev(pre3_ctx* ctx, int Fr, int n, int F, const double* dx, const double* dP,
+                              const int32_t* dtype, const int32_t* dpos, const uint8_t* dsel, const double* dz,
+                              const double* dh, const double* dHcam, const double* dHfeat, double r_diag,
+                              double* dx_out, double* dP_out, int32_t* dm_out) {
+  UPD_LIVE();
+  PRE3_TRY(check_upd(ctx, Fr, n, F));
+  if (Fr == 0) return PRE3_OK;
+  if (!dx || !dP || !dsel || !dx_out || !dP_out || (F > 0 && (!dtype || !dpos || !dz || !dh || !dHcam || !dHfeat)))
+    return fail(ctx, PRE3_ERR_ARG, "null pointer");
+  if (dP_out == dP) return fail(ctx, PRE3_ERR_ARG, "p_k_k must not alias the input covariance");
+  static bool attr_done = false;
+  if (!attr_done) {
+    PRE3_CUDA(cudaFuncSetAttribute(k_upd_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_done = true;
+  }
+  const int C = frames_per_chunk(Fr, n, F);
+  PRE3_TRY(ws_reserve(ctx, (size_t)C * upd_ws_per_frame(n, F) + 8192));
+  return update_impl(ctx, Fr, n, F, dx, dP, dtype, dpos, dsel, dz, dh, dHcam, dHfeat, r_diag, dx_out, dP_out, dm_out);
+}
+
+int pre3_ekf_update_batch(pre3_ctx* ctx, int Fr, int n, int F, const double* x, const double* P, const int32_t* type,
+                          const int32_t* pos, const uint8_t* sel, const double* z, const double* h, const double* Hcam,
+                          const double* Hfeat, double r_diag, double* x_out, double* P_out, int32_t* m_out) {
+  UPD_LIVE();
+  PRE3_TRY(check_upd(ctx, Fr, n, F));
+  if (Fr == 0) return PRE3_OK;
+  if (!x || !P || !sel || !x_out || !P_out || (F > 0 && (!type || !pos || !z || !h || !Hcam || !Hfeat)))
+    return fail(ctx, PRE3_ERR_ARG, "null pointer");
+  // staged through cudaMalloc'd buffers (a covariance batch can exceed the arena's sensible size); one sync at the end
+  const size_t xb = 8 * (size_t)Fr * n, pb = 8 * (size_t)Fr * n * n, fF = (size_t)Fr * F;
+  char* buf = nullptr;
+  const size_t total = 2 * align_up(xb) + 2 * align_up(pb) + 2 * align_up(4 * fF) + align_up(fF) + 2 * align_up(16 * fF) +
+                       align_up(208 * fF) + align_up(96 * fF) + align_up(4 * (size_t)Fr) + 4096;
+  cudaError_t e = cudaMalloc((void**)&buf, total);
+  if (e != cudaSuccess) return fail(ctx, PRE3_ERR_ALLOC, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    char* p = buf + off;
+    off += align_up(bytes);
+    return p;
+  };
+  double* dx = (double*)take(xb);
+  double* dxo = (double*)take(xb);
+  double* dP = (double*)take(pb);
+  double* dPo = (double*)take(pb);
+  int32_t* dty = (int32_t*)take(4 * fF);
+  int32_t* dps = (int32_t*)take(4 * fF);
+  uint8_t* dsl = (uint8_t*)take(fF);
+  double* dzz = (double*)take(16 * fF);
+  double* dhh = (double*)take(16 * fF);
+  double* dHc = (double*)take(208 * fF);
+  double* dHf = (double*)take(96 * fF);
+  int32_t* dm = (int32_t*)take(4 * (size_t)Fr);
+  cudaStream_t st = ctx->stream;
+  int rc = PRE3_OK;
+  auto up = [&](void* d, const void* hptr, size_t b) {
+    if (b && rc == PRE3_OK && cudaMemcpyAsync(d, hptr, b, cudaMemcpyHostToDevice, st) != cudaSuccess)
+      rc = fail(ctx, PRE3_ERR_CUDA, "cudaMemcpyAsync (host to device)");
+  };
+  up(dx, x, xb); up(dP, P, pb); up(dty, type, 4 * fF); up(dps, pos, 4 * fF); up(dsl, sel, fF);
+  up(dzz, z, 16 * fF); up(dhh, h, 16 * fF); up(dHc, Hcam, 208 * fF); up(dHf, Hfeat, 96 * fF);
+  if (rc == PRE3_OK)
+    rc = pre3_ekf_update_batch_dev(ctx, Fr, n, F, dx, dP, dty, dps, dsl, dzz, dhh, dHc, dHf, r_diag, dxo, dPo, dm);
+  if (rc == PRE3_OK) {
+    cudaMemcpyAsync(x_out, dxo, xb, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(P_out, dPo, pb, cudaMemcpyDeviceToHost, st);
+    if (m_out) cudaMemcpyAsync(m_out, dm, 4 * (size_t)Fr, cudaMemcpyDeviceToHost, st);
+  }
+  const cudaError_t se = cudaStreamSynchronize(st);
+  cudaFree(buf);
+  if (rc == PRE3_OK && se != cudaSuccess) return fail(ctx, PRE3_ERR_CUDA, cudaGetErrorString(se));
+  return rc;
+}
+
+int pre3_ekf_rescue_hi_inliers_batch_dev(pre3_ctx* ctx, int Fr, int n, int F, const double* dP_kk,
+                                         const int32_t* dtype, const int32_t* dpos, const uint8_t* dic,
+                                         const uint8_t* dli, const double* dz, const double* dh, const double* dHcam,
+                                         const double* dHfeat, uint8_t* dhi) {
+  UPD_LIVE();
+  PRE3_TRY(check_upd(ctx, Fr, n, F));
+  if (Fr == 0 || F == 0) return PRE3_OK;
+  if (!dP_kk || !dtype || !dpos || !dic || !dli || !dz || !dh || !dHcam || !dHfeat || !dhi)
+    return fail(ctx, PRE3_ERR_ARG, "null pointer");
+  Span span__(ctx, T_EKF_UPDATE);
+  k_upd_rescue<<<dim3((F + 127) / 128, Fr), 128, 0, ctx->stream>>>(dP_kk, n, F, dtype, dpos, dic, dli, dz, dh, dHcam,
+                                                                  dHfeat, 5.9915, dhi);
+  count_launch(ctx);
+  PRE3_CUDA(cudaGetLastError());
+  return PRE3_OK;
+}
+
+}  // extern "C"

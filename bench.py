@@ -442,6 +442,33 @@ def bench_frames(ctx, pre3, dev, F=2048, K=512, steps=5, warmup=2):
     return out
 
 
+def bench_ekf_update(ctx, pre3, dev, Fr=64, n_id=200, steps=3, warmup=1):
+    """SURVEY.md 8f rank 3 (first part): update.m on the low-innovation inliers of cfg4-shaped frames (n = 1213,
+    ~160 of 200 features flagged -> m ~ 320 stacked rows): dense fp64 linear algebra, 2 n^2 m FLOP for the
+    covariance update alone."""
+    import torch
+    se = importlib.import_module("3pre_b200.synth_ekf")
+    b = se.make_ekf_frames(Fr, 4000, device=dev, n_id=n_id, outlier_ratio=0.2)
+    sel = (~b["outlier"]).to(torch.uint8)
+    xo, Po = torch.empty_like(b["x"]), torch.empty_like(b["P"])
+    mo = torch.zeros(Fr, dtype=torch.int32, device=dev)
+
+    def step():
+        ctx.ekf_update_batch_dev(b, sel, xo, Po, m_out=mo)
+
+    ms = _time_steps(step, steps, warmup)
+    n = b["n"]
+    m = mo.double()
+    # K = G inv(S): 2 n m^2; T = K S: 2 n m^2; P - T K': 2 n^2 m; inversion 2 m^3; G, S: 38 (n + m) m
+    flops = float((4 * n * m * m + 2 * n * n * m + 2 * m ** 3 + 38 * (n + m) * m).sum().item())
+    out = {"workload": f"update.m on {Fr} frames, n = {n}, mean stacked rows m = {float(m.mean().item()):.0f}",
+           "frames_per_s": Fr / (ms * 1e-3), "ms_per_step": ms, "fp64_tflops": flops / (ms * 1e-3) / 1e12,
+           "kernels": _kernel_times(ctx, step, reps=1)}
+    del b, xo, Po
+    torch.cuda.empty_cache()
+    return out
+
+
 def bench_cfg1(ctx, pre3, synth, dev):
     """configs[0]: one synthetic SR4000 frame pair (~300 matches, 30% outliers), 2000 hypotheses: a LATENCY
     number on the GPU (one pair cannot fill the machine); k=5 (RANSAC_CALC_VER2.m:85) and k=3 (BASELINE wording)."""
@@ -508,6 +535,7 @@ def other_workloads(ctx, pre3, synth, dev, rank, world):
                 ("cfg4", lambda: bench_cfg4(ctx, pre3, dev, rank)),
                 ("dr_ye", lambda: bench_dr_ye(ctx, pre3, synth, dev, rank)),
                 ("frames", lambda: bench_frames(ctx, pre3, dev)),
+                ("ekf_update", lambda: bench_ekf_update(ctx, pre3, dev)),
                 ("cpu", lambda: cpu_other_baselines(synth))] + jobs
     # cfg5 involves every rank: run it first everywhere so that no rank waits inside a collective
     jobs.sort(key=lambda j: j[0] != "cfg5")

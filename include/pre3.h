@@ -122,7 +122,7 @@ PRE3_API int pre3_eval_schedule(const pre3_ransac_opts *opts, int32_t *ends, int
  * numbers).  pre3_timing_read synchronises, adds the elapsed ms and launch counts of every
  * bracketed launch since the last read into ms[cat] / count[cat] (PRE3_TIMING_NCAT entries
  * each, caller-zeroed) and forgets them.  pre3_timing_name(cat) names a category. */
-#define PRE3_TIMING_NCAT 13
+#define PRE3_TIMING_NCAT 14
 PRE3_API int pre3_timing_enable(pre3_ctx *ctx, int on);
 PRE3_API int pre3_timing_read(pre3_ctx *ctx, double *ms, int64_t *count);
 PRE3_API const char *pre3_timing_name(int cat);
@@ -196,6 +196,31 @@ PRE3_API int pre3_ransac_batch(pre3_ctx *ctx, const double *Ya, const double *Yb
 PRE3_API int pre3_ransac_batch_dev(pre3_ctx *ctx, const double *dYa, const double *dYb,
                           const int32_t *dn_corr, int P, int Nmax, const pre3_ransac_opts *opts,
                           const int32_t *dsamples, pre3_pair_result *dres, uint8_t *dmasks);
+
+/* ---- EKF partial updates around ransac_hypotheses (first part) -----
+ * [x_k_k, p_k_k] = update(x, p, H, R, z, h) (M/update.m:27-56) for Fr frames, with z, h, H stacked from the features
+ * whose flag sel is 1, in feature order, and R = r_diag * eye -- what ekf_update_li_inliers.m:15-29 (sel =
+ * low_innovation_inlier, x / P = x_k_km1 / p_k_km1) and ekf_update_hi_inliers.m:18-32 (sel = high_innovation_inlier,
+ * x / P = x_k_k / p_k_k) do with r_diag = 1.  Feature arrays as in pre3_ransac_hypotheses_batch (type, pos, z, h,
+ * Hcam 2 x 13, Hfeat 2 x 6 per feature).  Outputs: x_out Fr x n, P_out Fr x (n x n) (must not alias P), m_out Fr
+ * (rows of the stacked system; 0: the frame is copied through unchanged, update.m:50-54) or NULL.
+ * Dense fp64 linear algebra: results agree with the reference arithmetic to rounding (tests: 1e-9 of max|P|). */
+PRE3_API int pre3_ekf_update_batch(pre3_ctx *ctx, int Fr, int n, int F, const double *x, const double *P,
+                          const int32_t *type, const int32_t *pos, const uint8_t *sel, const double *z,
+                          const double *h, const double *Hcam, const double *Hfeat, double r_diag, double *x_out,
+                          double *P_out, int32_t *m_out);
+PRE3_API int pre3_ekf_update_batch_dev(pre3_ctx *ctx, int Fr, int n, int F, const double *dx, const double *dP,
+                              const int32_t *dtype, const int32_t *dpos, const uint8_t *dsel, const double *dz,
+                              const double *dh, const double *dHcam, const double *dHfeat, double r_diag,
+                              double *dx_out, double *dP_out, int32_t *dm_out);
+/* The test of rescue_hi_inliers.m:35-46 on device buffers: for features with ic == 1 and li == 0,
+ * hi = (nu' * inv(H p_k_k H') * nu < 5.9915), nu = z - h; other entries of hi are left untouched.  h, Hcam, Hfeat
+ * are the measurements re-predicted at x_k_k (:32-33: predict_camera_measurements / calculate_derivatives stay with
+ * the caller). */
+PRE3_API int pre3_ekf_rescue_hi_inliers_batch_dev(pre3_ctx *ctx, int Fr, int n, int F, const double *dP_kk,
+                                         const int32_t *dtype, const int32_t *dpos, const uint8_t *dic,
+                                         const uint8_t *dli, const double *dz, const double *dh,
+                                         const double *dHcam, const double *dHfeat, uint8_t *dhi);
 
 /* ---- SR4000 frame batches -> per-feature 3-D points ----------------
  * The step before the matching path: what SIFT_extract_save.m:75-88 does per frame through

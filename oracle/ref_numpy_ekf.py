@@ -158,3 +158,67 @@ def ransac_hypotheses(fr, sel, n_hyp_init=1000):
             break
     return dict(li=li, n_hyp=n_hyp, max_support=max_support, best_hyp=best, supports=np.array(supports),
                 n_evaluated=len(supports), m=mm, num_ic=num_ic)
+
+
+# ---------------------------------------------------------------------------------------------------
+# SURVEY.md 8f rank 3 (first part): the EKF partial updates around ransac_hypotheses
+# ---------------------------------------------------------------------------------------------------
+def normJac(q):
+    """M/normJac.m:1-16."""
+    r, x, y, z = q
+    return (r * r + x * x + y * y + z * z) ** (-1.5) * np.array(
+        [[x * x + y * y + z * z, -r * x, -r * y, -r * z],
+         [-x * r, r * r + y * y + z * z, -x * y, -x * z],
+         [-y * r, -y * x, r * r + x * x + z * z, -y * z],
+         [-z * r, -z * x, -z * y, r * r + x * x + y * y]])
+
+
+def update(x_km1_k, p_km1_k, H, R, z, h):
+    """[x_k_k, p_k_k, K] = update(x_km1_k, p_km1_k, H, R, z, h)   (M/update.m:27-56), dense numpy / LAPACK."""
+    if len(z) == 0:
+        return x_km1_k.copy(), p_km1_k.copy(), 0
+    S = H @ p_km1_k @ H.T + R
+    K = p_km1_k @ H.T @ np.linalg.inv(S)
+    x = x_km1_k + K @ (z - h)
+    p = p_km1_k - K @ S @ K.T
+    p = 0.5 * p + 0.5 * p.T
+    J = normJac(x[3:7])
+    n = p.shape[0]
+    p = np.block([[p[0:3, 0:3], p[0:3, 3:7] @ J.T, p[0:3, 7:n]],
+                  [J @ p[3:7, 0:3], J @ p[3:7, 3:7] @ J.T, J @ p[3:7, 7:n]],
+                  [p[7:n, 0:3], p[7:n, 3:7] @ J.T, p[7:n, 7:n]]])
+    x = x.copy()
+    x[3:7] = x[3:7] / np.linalg.norm(x[3:7])
+    return x, p, K
+
+
+def ekf_update_inliers(fr, flags, x=None, P=None):
+    """M/@ekf_filter/ekf_update_li_inliers.m:15-29 (flags = low_innovation_inlier, x/P = x_k_km1/p_k_km1) and
+    ekf_update_hi_inliers.m:18-32 (flags = high_innovation_inlier, x/P = x_k_k/p_k_k): stack z, h, H of the flagged
+    features in feature order, R = eye, update()."""
+    x = fr.x if x is None else x
+    P = fr.P if P is None else P
+    sel = [i for i in range(fr.F) if flags[i] == 1]
+    if not sel:
+        return update(x, P, np.zeros((0, fr.n)), np.zeros((0, 0)), np.zeros(0), np.zeros(0))[:2]
+    z = np.concatenate([fr.z[i] for i in sel])
+    h = np.concatenate([fr.h[i] for i in sel])
+    H = np.vstack([dense_H(fr, i) for i in sel])
+    xk, pk, _ = update(x, P, H, np.eye(len(z)), z, h)
+    return xk, pk
+
+
+def rescue_hi_inliers(fr, p_k_k, li, h=None):
+    """The test of M/@ekf_filter/rescue_hi_inliers.m:35-46 for features that are individually compatible but not
+    low-innovation inliers: nu' * inv(H p_k_k H') * nu < chi2inv(0.95, 2) = 5.9915.  (The re-prediction of h and H at
+    x_k_k, :32-33, is the caller's; pass the re-predicted h, or None for fr.h.)  Returns the high_innovation_inlier
+    flags (-1 where the reference leaves the field untouched)."""
+    h = fr.h if h is None else h
+    out = np.full(fr.F, -1, np.int32)
+    for i in range(fr.F):
+        if fr.ic[i] == 1 and li[i] == 0:
+            Hi = dense_H(fr, i)
+            Si = Hi @ p_k_k @ Hi.T
+            nu = fr.z[i] - h[i]
+            out[i] = 1 if nu @ np.linalg.inv(Si) @ nu < 5.9915 else 0
+    return out
