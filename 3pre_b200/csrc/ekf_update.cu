@@ -15,7 +15,7 @@
 //   k_upd_index   flagged features in feature order, m
 //   k_upd_G       G = P H'            n x m   19 structural non-zeros of H per row (13 camera + 6 feature columns)
 //   k_upd_S       S = H G + I         m x m
-//   k_upd_inv     inv(S)              in-place Gauss-Jordan with partial pivoting, one block per frame   2 m^3 FLOP
+//   k_inv_panel / k_inv_update   inv(S): in-place blocked Gauss-Jordan (S is symmetric positive definite)   2 m^3 FLOP
 //   k_dgemm       K = G inv(S)        n x m x m  |  T = K S   n x m x m  |  P' = P - T K'   n x n x m    (2 n^2 m FLOP: the bulk)
 //   k_upd_x       x + K (z - h)
 //   k_upd_sym     0.5 P' + 0.5 P''    tiled transpose
@@ -104,108 +104,119 @@ k_upd_S(const double* __restrict__ G, UpdDims d, const int32_t* __restrict__ idx
   S[((size_t)f * d.Mmax + cb) * d.Mmax + ra] = acc + (ra == cb ? r_diag : 0.0);
 }
 
-// In-place Gauss-Jordan inversion with partial pivoting, one block per frame.  A: m x m column-major, ld = Mmax.
-constexpr int INV_THREADS = 1024;
-__global__ void __launch_bounds__(INV_THREADS)
-k_upd_inv(double* __restrict__ Sinv, int Mmax, const int32_t* __restrict__ mf, int32_t* __restrict__ piv_ws,
-          int32_t* __restrict__ singular) {
-  extern __shared__ double sm[];  // rowk[Mmax], colk[Mmax]
-  double* rowk = sm;
-  double* colk = sm + Mmax;
-  __shared__ double s_v[32];
-  __shared__ int s_i[32];
-  __shared__ int s_p;
-  const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+// In-place BLOCKED Gauss-Jordan inversion of S = H P H' + r I (symmetric positive definite: no pivoting needed), block
+// size 32.  Per block step kb the matrix is read and written once (the scalar algorithm did that once per COLUMN:
+// 11.4 ms per 64 frames at m = 323, bound by the L2 bandwidth of the one SM that owned the frame; blocked: see DESIGN.md):
+//   k_inv_panel   one block per frame: Dinv = inv(A_kk) in shared memory; Cc = A(:, kb) saved; row panel
+//                 A_kj <- Dinv A_kj (also kept in Rp); A_kk <- Dinv
+//   k_inv_update  64 x 64 tiles over all frames: A_ij <- A_ij - Cc_i Rp_j (i, j outside kb);  A_ik <- -Cc_i Dinv
+// A: m x m column-major, ld = Mmax.  Side buffers per frame: Di 32 x 32, Cc Mmax x 32, Rp 32 x Mmax.
+constexpr int IB = 32;
+__global__ void __launch_bounds__(1024)
+k_inv_panel(double* __restrict__ Sinv, int Mmax, const int32_t* __restrict__ mf, int k0, double* __restrict__ Di,
+            double* __restrict__ Cc, double* __restrict__ Rp) {
+  __shared__ double D[IB][IB + 1];
+  const int f = blockIdx.x, tid = threadIdx.x;
   const int m = mf[f];
+  if (k0 >= m) return;
+  const int bs = min(IB, m - k0);
   double* A = Sinv + (size_t)f * Mmax * Mmax;
-  int32_t* piv = piv_ws + (size_t)f * Mmax;
-  for (int k = 0; k < m; ++k) {
-    // pivot: first maximum of |A(r, k)|, r >= k
-    double bv = -1.0;
-    int bi = 0x7fffffff;
-    for (int r = k + tid; r < m; r += INV_THREADS) {
-      const double v = fabs(A[(size_t)k * Mmax + r]);
-      if (v > bv) {
-        bv = v;
-        bi = r;
-      }
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-      if (ov > bv || (ov == bv && oi < bi)) {
-        bv = ov;
-        bi = oi;
-      }
-    }
-    if (lane == 0) {
-      s_v[warp] = bv;
-      s_i[warp] = bi;
-    }
+  double* di = Di + (size_t)f * IB * IB;
+  double* cc = Cc + (size_t)f * Mmax * IB;
+  double* rp = Rp + (size_t)f * IB * Mmax;
+  const int ti = tid & 31, tj = tid >> 5;  // element (ti, tj) of the diagonal block
+  D[ti][tj] = (ti < bs && tj < bs) ? A[(size_t)(k0 + tj) * Mmax + k0 + ti] : (ti == tj ? 1.0 : 0.0);
+  for (int e = tid; e < m * bs; e += 1024) {  // Cc(i, c) = A(i, k0 + c) before anything is overwritten
+    const int i = e % m, c = e / m;
+    cc[(size_t)c * Mmax + i] = A[(size_t)(k0 + c) * Mmax + i];
+  }
+  __syncthreads();
+  for (int k = 0; k < IB; ++k) {  // unpivoted in-place Gauss-Jordan on the 32 x 32 block (identity padding)
+    const double dinv = 1.0 / D[k][k];
+    const double rkj = D[k][tj], cik = D[ti][k], old = D[ti][tj];
     __syncthreads();
-    if (tid == 0) {
-      double v = s_v[0];
-      int p = s_i[0];
-      for (int w = 1; w < INV_THREADS / 32; ++w)
-        if (s_v[w] > v || (s_v[w] == v && s_i[w] < p)) {
-          v = s_v[w];
-          p = s_i[w];
-        }
-      if (p == 0x7fffffff) p = k;  // a column of NaNs: no pivot found
-      s_p = p;
-      piv[k] = p;
-      if (!(v > 0.0)) *singular = 1;
-    }
-    __syncthreads();
-    const int p = s_p;
-    // swap rows k and p, and stage row k (after the swap) and column k (after the swap)
-    for (int j = tid; j < m; j += INV_THREADS) {
-      double ak = A[(size_t)j * Mmax + k];
-      if (p != k) {
-        const double ap = A[(size_t)j * Mmax + p];
-        A[(size_t)j * Mmax + p] = ak;
-        ak = ap;
-      }
-      rowk[j] = ak;
-    }
-    __syncthreads();
-    for (int r = tid; r < m; r += INV_THREADS) {
-      double v = A[(size_t)k * Mmax + r];
-      if (r == k) v = rowk[k];
-      else if (r == p) v = A[(size_t)k * Mmax + p];  // already swapped in place by the loop above (j == k wrote it)
-      colk[r] = v;
-    }
-    __syncthreads();
-    const double dinv = 1.0 / rowk[k];
-    // A(k, j) = rowk(j) * d (j != k), A(k,k) = d;  A(i, j) -= colk(i) * rowk(j) * d (i != k, j != k);  A(i, k) = -colk(i) * d
-    for (int j = warp; j < m; j += INV_THREADS / 32) {  // 32 x 32 thread grid: lanes along rows (coalesced)
-      const double rj = rowk[j] * dinv;
-      double* col = A + (size_t)j * Mmax;
-      for (int i = lane; i < m; i += 32) {
-        double v;
-        if (i == k) {
-          v = j == k ? dinv : rj;
-        } else if (j == k) {
-          v = -colk[i] * dinv;
-        } else {
-          v = fma(-colk[i], rj, col[i]);
-        }
-        col[i] = v;
-      }
-    }
+    double v;
+    if (ti == k) v = tj == k ? dinv : rkj * dinv;
+    else if (tj == k) v = -cik * dinv;
+    else v = fma(-cik, rkj * dinv, old);
+    D[ti][tj] = v;
     __syncthreads();
   }
-  // undo the row exchanges: columns in reverse order
-  for (int k = m - 1; k >= 0; --k) {
-    const int p = piv[k];
-    if (p != k)
-      for (int r = tid; r < m; r += INV_THREADS) {
-        const double a = A[(size_t)k * Mmax + r], b = A[(size_t)p * Mmax + r];
-        A[(size_t)k * Mmax + r] = b;
-        A[(size_t)p * Mmax + r] = a;
-      }
-    __syncthreads();
+  di[tj * IB + ti] = D[ti][tj];
+  if (ti < bs && tj < bs) A[(size_t)(k0 + tj) * Mmax + k0 + ti] = D[ti][tj];
+  // row panel: Rp(r, j) = sum_c Dinv(r, c) A(k0 + c, j), j outside the pivot block
+  for (int e = tid; e < m * IB; e += 1024) {
+    const int r = e & (IB - 1), j = e >> 5;
+    if (r >= bs || (j >= k0 && j < k0 + bs)) continue;
+    double acc = 0.0;
+    for (int c = 0; c < bs; ++c) acc = fma(D[r][c], A[(size_t)j * Mmax + k0 + c], acc);
+    rp[(size_t)j * IB + r] = acc;
+  }
+  __syncthreads();
+  for (int e = tid; e < m * IB; e += 1024) {  // second pass: the panel is written only after every read of it
+    const int r = e & (IB - 1), j = e >> 5;
+    if (r >= bs || (j >= k0 && j < k0 + bs)) continue;
+    A[(size_t)j * Mmax + k0 + r] = rp[(size_t)j * IB + r];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_inv_update(double* __restrict__ Sinv, int Mmax, const int32_t* __restrict__ mf, int k0,
+             const double* __restrict__ Di, const double* __restrict__ Cc, const double* __restrict__ Rp) {
+  __shared__ double Cs[IB][64];      // Cs[c][i]
+  __shared__ double Bs[IB][64 + 1];  // Bs[c][j]: Rp(c, j), or Dinv(c, j - k0) inside the pivot block's columns
+  const int f = blockIdx.z;
+  const int m = mf[f];
+  if (k0 >= m) return;
+  const int bs = min(IB, m - k0);
+  const int i0 = blockIdx.x * 64, j0 = blockIdx.y * 64;
+  if (i0 >= m || j0 >= m) return;
+  double* A = Sinv + (size_t)f * Mmax * Mmax;
+  const double* di = Di + (size_t)f * IB * IB;
+  const double* cc = Cc + (size_t)f * Mmax * IB;
+  const double* rp = Rp + (size_t)f * IB * Mmax;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  for (int e = tid; e < IB * 64; e += 256) {
+    const int ii = e & 63, c = e >> 6;
+    Cs[c][ii] = (c < bs && i0 + ii < m) ? cc[(size_t)c * Mmax + i0 + ii] : 0.0;
+  }
+  for (int e = tid; e < IB * 64; e += 256) {
+    const int c = e & (IB - 1), jj = e >> 5;
+    const int j = j0 + jj;
+    double v = 0.0;
+    if (c < bs && j < m) v = (j >= k0 && j < k0 + bs) ? di[(j - k0) * IB + c] : rp[(size_t)j * IB + c];
+    Bs[c][jj] = v;
+  }
+  __syncthreads();
+  double acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+#pragma unroll 8
+  for (int c = 0; c < IB; ++c) {
+    double av[4], bv[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) av[a] = Cs[c][tx + 16 * a];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) bv[b] = Bs[c][ty + 16 * b];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
+  }
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    const int j = j0 + ty + 16 * b;
+    if (j >= m) continue;
+    const bool jpiv = j >= k0 && j < k0 + bs;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int i = i0 + tx + 16 * a;
+      if (i >= m || (i >= k0 && i < k0 + bs)) continue;  // the pivot block's rows are final (k_inv_panel)
+      double* p = A + (size_t)j * Mmax + i;
+      *p = jpiv ? -acc[a][b] : *p - acc[a][b];
+    }
   }
 }
 
@@ -443,7 +454,7 @@ k_upd_rescue(const double* __restrict__ P, int n, int F, const int32_t* __restri
 size_t upd_ws_per_frame(int n, int F) {
   const size_t M = 2 * (size_t)F;
   return 3 * align_up(8 * (size_t)n * M) + 2 * align_up(8 * M * M) + align_up(8 * (size_t)n * n) + align_up(4 * (size_t)F) +
-         align_up(4 * M) + 512;
+         align_up(8 * IB * IB) + 2 * align_up(8 * M * IB) + 1024;
 }
 
 int frames_per_chunk(int Fr, int n, int F) {
@@ -465,16 +476,19 @@ int update_chunk(pre3_ctx* ctx, int C, int n, int F, const double* dx, const dou
   double* Si = ws_take<double>(ctx, (size_t)C * M * M);
   double* Pp = ws_take<double>(ctx, (size_t)C * n * n);
   int32_t* idx = ws_take<int32_t>(ctx, (size_t)C * F);
-  int32_t* piv = ws_take<int32_t>(ctx, (size_t)C * M);
+  double* Di = ws_take<double>(ctx, (size_t)C * IB * IB);
+  double* Cc = ws_take<double>(ctx, (size_t)C * M * IB);
+  double* Rp = ws_take<double>(ctx, (size_t)C * M * IB);
   int32_t* mf = dm_out ? dm_out : ws_take<int32_t>(ctx, C);
-  int32_t* sing = ws_take<int32_t>(ctx, 1);
   cudaStream_t st = ctx->stream;
-  PRE3_CUDA(cudaMemsetAsync(sing, 0, 4, st));
   k_upd_index<<<C, 256, 0, st>>>(dsel, F, idx, mf);
   k_upd_G<<<dim3((n + 255) / 256, d.Mmax, C), 256, 0, st>>>(dP, d, idx, mf, dtype, dpos, dHcam, dHfeat, G);
   k_upd_S<<<dim3((d.Mmax + 127) / 128, d.Mmax, C), 128, 0, st>>>(G, d, idx, mf, dtype, dpos, dHcam, dHfeat, r_diag, S);
   PRE3_CUDA(cudaMemcpyAsync(Si, S, 8 * (size_t)C * M * M, cudaMemcpyDeviceToDevice, st));
-  k_upd_inv<<<C, INV_THREADS, 2 * M * sizeof(double), st>>>(Si, d.Mmax, mf, piv, sing);
+  for (int k0 = 0; k0 < d.Mmax; k0 += IB) {  // frames whose m <= k0 return at once
+    k_inv_panel<<<C, 1024, 0, st>>>(Si, d.Mmax, mf, k0, Di, Cc, Rp);
+    k_inv_update<<<dim3((d.Mmax + 63) / 64, (d.Mmax + 63) / 64, C), 256, 0, st>>>(Si, d.Mmax, mf, k0, Di, Cc, Rp);
+  }
   const dim3 g1((n + GM - 1) / GM, (d.Mmax + GN - 1) / GN, C), g2((n + GM - 1) / GM, (n + GN - 1) / GN, C);
   // K = G inv(S);  T = K S;  P' = P - T K'
   k_dgemm<0><<<g1, 256, 0, st>>>(G, n, (size_t)n * M, Si, d.Mmax, M * M, K, n, (size_t)n * M, nullptr, 0, 0, n, 0, mf, 1);
@@ -484,7 +498,7 @@ int update_chunk(pre3_ctx* ctx, int C, int n, int F, const double* dx, const dou
   k_upd_x<<<dim3((n + 255) / 256, C), 256, M * sizeof(double), st>>>(dx, K, d, idx, mf, dz, dh, dx_out);
   k_upd_sym<<<dim3((n + 31) / 32, (n + 31) / 32, C), 256, 0, st>>>(Pp, dP, n, mf, dP_out);
   k_upd_quat<<<C, 256, 0, st>>>(dP_out, dx_out, n, mf);
-  count_launch(ctx, 10);
+  count_launch(ctx, 9 + 2 * ((d.Mmax + IB - 1) / IB));
   PRE3_CUDA(cudaGetLastError());
   return PRE3_OK;
 }
@@ -506,8 +520,6 @@ int update_impl(pre3_ctx* ctx, int Fr, int n, int F, const double* dx, const dou
 
 int check_upd(pre3_ctx* ctx, int Fr, int n, int F) {
   if (Fr < 0 || n < 13 || F < 0) return fail(ctx, PRE3_ERR_ARG, "bad sizes (n >= 13: the camera states)");
-  if (2 * (size_t)F * 2 * sizeof(double) > 200 * 1024)
-    return fail(ctx, PRE3_ERR_ARG, "too many features per frame for the inversion kernel's shared memory");
   return PRE3_OK;
 }
 
@@ -528,11 +540,6 @@ int pre3_ekf_update_batch_dev(pre3_ctx* ctx, int Fr, int n, int F, const double*
   if (!dx || !dP || !dsel || !dx_out || !dP_out || (F > 0 && (!dtype || !dpos || !dz || !dh || !dHcam || !dHfeat)))
     return fail(ctx, PRE3_ERR_ARG, "null pointer");
   if (dP_out == dP) return fail(ctx, PRE3_ERR_ARG, "p_k_k must not alias the input covariance");
-  static bool attr_done = false;
-  if (!attr_done) {
-    PRE3_CUDA(cudaFuncSetAttribute(k_upd_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_done = true;
-  }
   const int C = frames_per_chunk(Fr, n, F);
   PRE3_TRY(ws_reserve(ctx, (size_t)C * upd_ws_per_frame(n, F) + 8192));
   return update_impl(ctx, Fr, n, F, dx, dP, dtype, dpos, dsel, dz, dh, dHcam, dHfeat, r_diag, dx_out, dP_out, dm_out);
