@@ -16,9 +16,9 @@
 //   k_upd_G       G = P H'            n x m   19 structural non-zeros of H per row (13 camera + 6 feature columns)
 //   k_upd_S       S = H G + I         m x m
 //   k_inv_panel / k_inv_update   inv(S): in-place blocked Gauss-Jordan (S is symmetric positive definite)   2 m^3 FLOP
-//   k_dgemm       K = G inv(S)        n x m x m  |  T = K S   n x m x m  |  P' = P - T K'   n x n x m    (2 n^2 m FLOP: the bulk)
+//   k_dgemm       K = G inv(S)        n x m x m
+//   k_dsyrk_update  0.5 (P + P') - G K'   lower tiles + mirrored write (K S K' = G K' is symmetric)   n^2 m FLOP: the bulk
 //   k_upd_x       x + K (z - h)
-//   k_upd_sym     0.5 P' + 0.5 P''    tiled transpose
 //   k_upd_quat    rows / columns 4:7 through normJac, q / |q|
 // Everything is column-major like MATLAB.
 #include <cmath>
@@ -299,6 +299,91 @@ k_dgemm(const double* __restrict__ A, int lda, size_t strideA, const double* __r
   }
 }
 
+// P_out = 0.5 (P + P') - G K'   (update.m:37-38 with K S = P H' = G).  G K' is symmetric (= K S K'), so only the tiles
+// on and below the diagonal are computed; the symmetrisation of :38 is the epilogue (the mirrored tile is staged through
+// shared memory so that both writes are coalesced).  m == 0: P_out = P (update.m:52-53).
+__global__ void __launch_bounds__(256)
+k_dsyrk_update(const double* __restrict__ G, const double* __restrict__ K, size_t strideGK, const double* __restrict__ Pin,
+               double* __restrict__ Pout, int n, const int32_t* __restrict__ mf) {
+  __shared__ double smem[64 * 65];
+  double(*As)[GM] = reinterpret_cast<double(*)[GM]>(smem);            // [GK][GM]
+  double(*Bs)[GN] = reinterpret_cast<double(*)[GN]>(smem + GK * GM);  // [GK][GN]
+  double(*Tt)[65] = reinterpret_cast<double(*)[65]>(smem);            // epilogue: [64][65]
+  const int f = blockIdx.z;
+  const int Kd = mf[f];
+  const int i0 = blockIdx.x * GM, j0 = blockIdx.y * GN;
+  if (j0 > i0 || i0 >= n) return;
+  G += (size_t)f * strideGK;
+  K += (size_t)f * strideGK;
+  Pin += (size_t)f * n * n;
+  Pout += (size_t)f * n * n;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const bool diag = i0 == j0;
+  if (Kd == 0) {  // copy through, both triangles
+    for (int e = tid; e < 64 * 64; e += 256) {
+      const int ii = e & 63, jj = e >> 6;
+      const int i = i0 + ii, j = j0 + jj;
+      if (i < n && j < n) {
+        Pout[(size_t)j * n + i] = Pin[(size_t)j * n + i];
+        if (!diag) Pout[(size_t)i * n + j] = Pin[(size_t)i * n + j];
+      }
+    }
+    return;
+  }
+  double acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+  for (int k0 = 0; k0 < Kd; k0 += GK) {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int mm = tid & 63, kk = (tid >> 6) + 4 * it;
+      const int gk = k0 + kk;
+      As[kk][mm] = (i0 + mm < n && gk < Kd) ? G[(size_t)gk * n + i0 + mm] : 0.0;
+      Bs[kk][mm] = (j0 + mm < n && gk < Kd) ? K[(size_t)gk * n + j0 + mm] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < GK; ++kk) {
+      double av[4], bv[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) av[a] = As[kk][tx + 16 * a];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) bv[b] = Bs[kk][ty + 16 * b];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
+    }
+    __syncthreads();
+  }
+  // mirrored input tile: Tt[ii][jj] = P(j0 + jj, i0 + ii)
+  for (int e = tid; e < 64 * 64; e += 256) {
+    const int jj = e & 63, ii = e >> 6;
+    Tt[ii][jj] = (i0 + ii < n && j0 + jj < n) ? Pin[(size_t)(i0 + ii) * n + j0 + jj] : 0.0;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    const int jj = ty + 16 * b, j = j0 + jj;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int ii = tx + 16 * a, i = i0 + ii;
+      if (i >= n || j >= n || (diag && ii < jj)) continue;
+      const double v = (0.5 * Pin[(size_t)j * n + i] + 0.5 * Tt[ii][jj]) - acc[a][b];
+      Pout[(size_t)j * n + i] = v;
+      Tt[ii][jj] = v;
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < 64 * 64; e += 256) {  // mirror: P_out(j, i) = P_out(i, j)
+    const int jj = e & 63, ii = e >> 6;
+    if (i0 + ii >= n || j0 + jj >= n || (diag && ii <= jj)) continue;
+    Pout[(size_t)(i0 + ii) * n + j0 + jj] = Tt[ii][jj];
+  }
+}
+
 // x_out = x + K (z - h) over the flagged features (m == 0: x_out = x)
 __global__ void __launch_bounds__(256)
 k_upd_x(const double* __restrict__ x, const double* __restrict__ K, UpdDims d, const int32_t* __restrict__ idx,
@@ -317,33 +402,6 @@ k_upd_x(const double* __restrict__ x, const double* __restrict__ K, UpdDims d, c
   double acc = 0.0;
   for (int j = 0; j < m; ++j) acc = fma(Kf[(size_t)j * d.n + r], s_d[j], acc);
   x_out[(size_t)f * d.n + r] = x[(size_t)f * d.n + r] + acc;
-}
-
-// P_out = 0.5 P' + 0.5 P''  (m == 0: P_out = P_in untouched: update.m:52-53); 32 x 32 tiles
-__global__ void __launch_bounds__(256)
-k_upd_sym(const double* __restrict__ Pp, const double* __restrict__ Pin, int n, const int32_t* __restrict__ mf,
-          double* __restrict__ Pout) {
-  __shared__ double t[32][33];
-  const int f = blockIdx.z;
-  const size_t base = (size_t)f * n * n;
-  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  if (mf[f] == 0) {
-    for (int j = ty; j < 32; j += 8) {
-      const int r = r0 + tx, c = c0 + j;
-      if (r < n && c < n) Pout[base + (size_t)c * n + r] = Pin[base + (size_t)c * n + r];
-    }
-    return;
-  }
-  for (int j = ty; j < 32; j += 8) {  // transposed block: rows c0.., columns r0..
-    const int r = c0 + tx, c = r0 + j;
-    t[j][tx] = (r < n && c < n) ? Pp[base + (size_t)c * n + r] : 0.0;
-  }
-  __syncthreads();
-  for (int j = ty; j < 32; j += 8) {
-    const int r = r0 + tx, c = c0 + j;
-    if (r < n && c < n) Pout[base + (size_t)c * n + r] = 0.5 * Pp[base + (size_t)c * n + r] + 0.5 * t[tx][j];
-  }
 }
 
 // rows / columns 4:7 (0-based 3..6) through Jnorm = normJac(x_k_k(4:7)) (update.m:42-46), then q / |q| (:48)
@@ -453,7 +511,7 @@ k_upd_rescue(const double* __restrict__ P, int n, int F, const int32_t* __restri
 
 size_t upd_ws_per_frame(int n, int F) {
   const size_t M = 2 * (size_t)F;
-  return 3 * align_up(8 * (size_t)n * M) + 2 * align_up(8 * M * M) + align_up(8 * (size_t)n * n) + align_up(4 * (size_t)F) +
+  return 2 * align_up(8 * (size_t)n * M) + 2 * align_up(8 * M * M) + align_up(4 * (size_t)F) +
          align_up(8 * IB * IB) + 2 * align_up(8 * M * IB) + 1024;
 }
 
@@ -471,10 +529,8 @@ int update_chunk(pre3_ctx* ctx, int C, int n, int F, const double* dx, const dou
   const size_t M = (size_t)d.Mmax;
   double* G = ws_take<double>(ctx, (size_t)C * n * M);
   double* K = ws_take<double>(ctx, (size_t)C * n * M);
-  double* T = ws_take<double>(ctx, (size_t)C * n * M);
   double* S = ws_take<double>(ctx, (size_t)C * M * M);
   double* Si = ws_take<double>(ctx, (size_t)C * M * M);
-  double* Pp = ws_take<double>(ctx, (size_t)C * n * n);
   int32_t* idx = ws_take<int32_t>(ctx, (size_t)C * F);
   double* Di = ws_take<double>(ctx, (size_t)C * IB * IB);
   double* Cc = ws_take<double>(ctx, (size_t)C * M * IB);
@@ -490,15 +546,13 @@ int update_chunk(pre3_ctx* ctx, int C, int n, int F, const double* dx, const dou
     k_inv_update<<<dim3((d.Mmax + 63) / 64, (d.Mmax + 63) / 64, C), 256, 0, st>>>(Si, d.Mmax, mf, k0, Di, Cc, Rp);
   }
   const dim3 g1((n + GM - 1) / GM, (d.Mmax + GN - 1) / GN, C), g2((n + GM - 1) / GM, (n + GN - 1) / GN, C);
-  // K = G inv(S);  T = K S;  P' = P - T K'
+  // K = G inv(S);  P_out = 0.5 (P + P') - G K'   (K S K' = G K': K S = P H' = G by construction, so the reference's
+  // second n x m x m product is not repeated; the difference is rounding x cond(S), far inside the tolerance)
   k_dgemm<0><<<g1, 256, 0, st>>>(G, n, (size_t)n * M, Si, d.Mmax, M * M, K, n, (size_t)n * M, nullptr, 0, 0, n, 0, mf, 1);
-  k_dgemm<0><<<g1, 256, 0, st>>>(K, n, (size_t)n * M, S, d.Mmax, M * M, T, n, (size_t)n * M, nullptr, 0, 0, n, 0, mf, 1);
-  k_dgemm<1><<<g2, 256, 0, st>>>(T, n, (size_t)n * M, K, n, (size_t)n * M, Pp, n, (size_t)n * n, dP, n, (size_t)n * n, n, n,
-                                 mf, 0);
+  k_dsyrk_update<<<g2, 256, 0, st>>>(G, K, (size_t)n * M, dP, dP_out, n, mf);
   k_upd_x<<<dim3((n + 255) / 256, C), 256, M * sizeof(double), st>>>(dx, K, d, idx, mf, dz, dh, dx_out);
-  k_upd_sym<<<dim3((n + 31) / 32, (n + 31) / 32, C), 256, 0, st>>>(Pp, dP, n, mf, dP_out);
   k_upd_quat<<<C, 256, 0, st>>>(dP_out, dx_out, n, mf);
-  count_launch(ctx, 9 + 2 * ((d.Mmax + IB - 1) / IB));
+  count_launch(ctx, 7 + 2 * ((d.Mmax + IB - 1) / IB));
   PRE3_CUDA(cudaGetLastError());
   return PRE3_OK;
 }

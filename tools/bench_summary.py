@@ -29,6 +29,10 @@ if "frames" in o and "error" not in o["frames"]:
     print("frames maps", round(c["maps"]["frames_per_s"]), "frames/s, HBM frac", round(c["maps"]["roofline"]["frac"], 3),
           "| fused", round(c["fused_features"]["frames_per_s"]), "frames/s, HBM frac",
           round(c["fused_features"]["roofline"]["frac"], 3))
+if "ekf_update" in o and "error" not in o["ekf_update"]:
+    c = o["ekf_update"]
+    print("ekf_update", round(c["frames_per_s"]), "frames/s", round(c["fp64_tflops_executed"], 2), "TFLOP/s fp64 executed |",
+          "cpu", c.get("cpu"))
 for k, v in o.items():
     if isinstance(v, dict) and "error" in v:
         print("ERROR in", k, v["error"])
