@@ -22,6 +22,7 @@
 //   k_upd_quat    rows / columns 4:7 through normJac, q / |q|
 // Everything is column-major like MATLAB.
 #include <cmath>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -107,31 +108,25 @@ k_upd_S(const double* __restrict__ G, UpdDims d, const int32_t* __restrict__ idx
 // In-place BLOCKED Gauss-Jordan inversion of S = H P H' + r I (symmetric positive definite: no pivoting needed), block
 // size 32.  Per block step kb the matrix is read and written once (the scalar algorithm did that once per COLUMN:
 // 11.4 ms per 64 frames at m = 323, bound by the L2 bandwidth of the one SM that owned the frame; blocked: see DESIGN.md):
-//   k_inv_panel   one block per frame: Dinv = inv(A_kk) in shared memory; Cc = A(:, kb) saved; row panel
-//                 A_kj <- Dinv A_kj (also kept in Rp); A_kk <- Dinv
+//   k_inv_diag    one block per frame: Dinv = inv(A_kk) in shared memory
+//   k_inv_panel   64-wide slabs over all frames: Cc = A(:, kb) saved; row panel A_kj <- Dinv A_kj (also kept in Rp);
+//                 A_kk <- Dinv
 //   k_inv_update  64 x 64 tiles over all frames: A_ij <- A_ij - Cc_i Rp_j (i, j outside kb);  A_ik <- -Cc_i Dinv
 // A: m x m column-major, ld = Mmax.  Side buffers per frame: Di 32 x 32, Cc Mmax x 32, Rp 32 x Mmax.
 constexpr int IB = 32;
+// step 1: one block per frame, the 32 x 32 pivot block only
 __global__ void __launch_bounds__(1024)
-k_inv_panel(double* __restrict__ Sinv, int Mmax, const int32_t* __restrict__ mf, int k0, double* __restrict__ Di,
-            double* __restrict__ Cc, double* __restrict__ Rp) {
+k_inv_diag(double* __restrict__ Sinv, int Mmax, const int32_t* __restrict__ mf, int k0, double* __restrict__ Di) {
   __shared__ double D[IB][IB + 1];
   const int f = blockIdx.x, tid = threadIdx.x;
   const int m = mf[f];
   if (k0 >= m) return;
   const int bs = min(IB, m - k0);
   double* A = Sinv + (size_t)f * Mmax * Mmax;
-  double* di = Di + (size_t)f * IB * IB;
-  double* cc = Cc + (size_t)f * Mmax * IB;
-  double* rp = Rp + (size_t)f * IB * Mmax;
   const int ti = tid & 31, tj = tid >> 5;  // element (ti, tj) of the diagonal block
   D[ti][tj] = (ti < bs && tj < bs) ? A[(size_t)(k0 + tj) * Mmax + k0 + ti] : (ti == tj ? 1.0 : 0.0);
-  for (int e = tid; e < m * bs; e += 1024) {  // Cc(i, c) = A(i, k0 + c) before anything is overwritten
-    const int i = e % m, c = e / m;
-    cc[(size_t)c * Mmax + i] = A[(size_t)(k0 + c) * Mmax + i];
-  }
   __syncthreads();
-  for (int k = 0; k < IB; ++k) {  // unpivoted in-place Gauss-Jordan on the 32 x 32 block (identity padding)
+  for (int k = 0; k < IB; ++k) {  // unpivoted in-place Gauss-Jordan (identity padding beyond bs)
     const double dinv = 1.0 / D[k][k];
     const double rkj = D[k][tj], cik = D[ti][k], old = D[ti][tj];
     __syncthreads();
@@ -142,21 +137,52 @@ k_inv_panel(double* __restrict__ Sinv, int Mmax, const int32_t* __restrict__ mf,
     D[ti][tj] = v;
     __syncthreads();
   }
-  di[tj * IB + ti] = D[ti][tj];
-  if (ti < bs && tj < bs) A[(size_t)(k0 + tj) * Mmax + k0 + ti] = D[ti][tj];
-  // row panel: Rp(r, j) = sum_c Dinv(r, c) A(k0 + c, j), j outside the pivot block
-  for (int e = tid; e < m * IB; e += 1024) {
-    const int r = e & (IB - 1), j = e >> 5;
-    if (r >= bs || (j >= k0 && j < k0 + bs)) continue;
-    double acc = 0.0;
-    for (int c = 0; c < bs; ++c) acc = fma(D[r][c], A[(size_t)j * Mmax + k0 + c], acc);
-    rp[(size_t)j * IB + r] = acc;
+  Di[(size_t)f * IB * IB + tj * IB + ti] = D[ti][tj];
+}
+
+// step 2: grid (64-wide slabs, frames): slab t saves Cc(i, :) = A(i, kb) for its rows i and forms the row panel
+// Rp(:, j) = Dinv A(kb, j) for its columns j (written back to A as well: only this block touches A(kb, j) here);
+// the slab that holds the pivot block writes A_kk = Dinv last.
+__global__ void __launch_bounds__(256)
+k_inv_panel(double* __restrict__ Sinv, int Mmax, const int32_t* __restrict__ mf, int k0, const double* __restrict__ Di,
+            double* __restrict__ Cc, double* __restrict__ Rp) {
+  __shared__ double Dv[IB][IB + 1];  // Dv[r][c] = Dinv(r, c)
+  __shared__ double Ak[IB][64 + 1];  // Ak[c][jj] = A(k0 + c, j0 + jj), old
+  const int f = blockIdx.y, tid = threadIdx.x;
+  const int m = mf[f];
+  if (k0 >= m) return;
+  const int bs = min(IB, m - k0);
+  const int t0 = blockIdx.x * 64;
+  if (t0 >= m) return;
+  double* A = Sinv + (size_t)f * Mmax * Mmax;
+  const double* di = Di + (size_t)f * IB * IB;
+  double* cc = Cc + (size_t)f * Mmax * IB;
+  double* rp = Rp + (size_t)f * IB * Mmax;
+  for (int e = tid; e < IB * IB; e += 256) Dv[e & 31][e >> 5] = di[e];
+  for (int e = tid; e < IB * 64; e += 256) {  // column panel rows t0 .. t0+63, coalesced along rows
+    const int ii = e & 63, c = e >> 6;
+    if (c < bs && t0 + ii < m) cc[(size_t)c * Mmax + t0 + ii] = A[(size_t)(k0 + c) * Mmax + t0 + ii];
+  }
+  for (int e = tid; e < IB * 64; e += 256) {  // old row panel columns t0 .. t0+63, contiguous along c
+    const int c = e & 31, jj = e >> 5;
+    Ak[c][jj] = (c < bs && t0 + jj < m) ? A[(size_t)(t0 + jj) * Mmax + k0 + c] : 0.0;
   }
   __syncthreads();
-  for (int e = tid; e < m * IB; e += 1024) {  // second pass: the panel is written only after every read of it
-    const int r = e & (IB - 1), j = e >> 5;
-    if (r >= bs || (j >= k0 && j < k0 + bs)) continue;
-    A[(size_t)j * Mmax + k0 + r] = rp[(size_t)j * IB + r];
+  for (int e = tid; e < IB * 64; e += 256) {
+    const int r = e & 31, jj = e >> 5;
+    const int j = t0 + jj;
+    if (r >= bs || j >= m) continue;
+    double v;
+    if (j >= k0 && j < k0 + bs) {
+      v = Dv[r][j - k0];  // A_kk <- Dinv
+    } else {
+      double acc = 0.0;
+#pragma unroll 8
+      for (int c = 0; c < IB; ++c) acc = fma(Dv[r][c], Ak[c][jj], acc);
+      v = acc;
+      rp[(size_t)j * IB + r] = acc;
+    }
+    A[(size_t)j * Mmax + k0 + r] = v;
   }
 }
 
@@ -518,13 +544,21 @@ size_t upd_ws_per_frame(int n, int F) {
 int frames_per_chunk(int Fr, int n, int F) {
   const size_t budget = (size_t)2 << 30;
   const size_t per = upd_ws_per_frame(n, F);
-  return (int)std::max<size_t>(1, std::min<size_t>((size_t)Fr, budget / per));
+  size_t c = std::max<size_t>(1, std::min<size_t>((size_t)Fr, budget / per));
+  if (const char* e = getenv("PRE3_UPD_CHUNK")) c = std::max<size_t>(1, std::min<size_t>(c, (size_t)atoi(e)));  // tests
+  return (int)c;
 }
 
 int update_chunk(pre3_ctx* ctx, int C, int n, int F, const double* dx, const double* dP, const int32_t* dtype,
                  const int32_t* dpos, const uint8_t* dsel, const double* dz, const double* dh, const double* dHcam,
                  const double* dHfeat, double r_diag, double* dx_out, double* dP_out, int32_t* dm_out) {
   Span span__(ctx, T_EKF_UPDATE);
+  if (F == 0) {  // nothing can be flagged: every frame is copied through (update.m:50-54)
+    PRE3_CUDA(cudaMemcpyAsync(dx_out, dx, 8 * (size_t)C * n, cudaMemcpyDeviceToDevice, ctx->stream));
+    PRE3_CUDA(cudaMemcpyAsync(dP_out, dP, 8 * (size_t)C * n * n, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (dm_out) PRE3_CUDA(cudaMemsetAsync(dm_out, 0, 4 * (size_t)C, ctx->stream));
+    return PRE3_OK;
+  }
   const UpdDims d{n, F, 2 * F};
   const size_t M = (size_t)d.Mmax;
   double* G = ws_take<double>(ctx, (size_t)C * n * M);
@@ -542,7 +576,8 @@ int update_chunk(pre3_ctx* ctx, int C, int n, int F, const double* dx, const dou
   k_upd_S<<<dim3((d.Mmax + 127) / 128, d.Mmax, C), 128, 0, st>>>(G, d, idx, mf, dtype, dpos, dHcam, dHfeat, r_diag, S);
   PRE3_CUDA(cudaMemcpyAsync(Si, S, 8 * (size_t)C * M * M, cudaMemcpyDeviceToDevice, st));
   for (int k0 = 0; k0 < d.Mmax; k0 += IB) {  // frames whose m <= k0 return at once
-    k_inv_panel<<<C, 1024, 0, st>>>(Si, d.Mmax, mf, k0, Di, Cc, Rp);
+    k_inv_diag<<<C, 1024, 0, st>>>(Si, d.Mmax, mf, k0, Di);
+    k_inv_panel<<<dim3((d.Mmax + 63) / 64, C), 256, 0, st>>>(Si, d.Mmax, mf, k0, Di, Cc, Rp);
     k_inv_update<<<dim3((d.Mmax + 63) / 64, (d.Mmax + 63) / 64, C), 256, 0, st>>>(Si, d.Mmax, mf, k0, Di, Cc, Rp);
   }
   const dim3 g1((n + GM - 1) / GM, (d.Mmax + GN - 1) / GN, C), g2((n + GM - 1) / GM, (n + GN - 1) / GN, C);
@@ -552,7 +587,7 @@ int update_chunk(pre3_ctx* ctx, int C, int n, int F, const double* dx, const dou
   k_dsyrk_update<<<g2, 256, 0, st>>>(G, K, (size_t)n * M, dP, dP_out, n, mf);
   k_upd_x<<<dim3((n + 255) / 256, C), 256, M * sizeof(double), st>>>(dx, K, d, idx, mf, dz, dh, dx_out);
   k_upd_quat<<<C, 256, 0, st>>>(dP_out, dx_out, n, mf);
-  count_launch(ctx, 7 + 2 * ((d.Mmax + IB - 1) / IB));
+  count_launch(ctx, 7 + 3 * ((d.Mmax + IB - 1) / IB));
   PRE3_CUDA(cudaGetLastError());
   return PRE3_OK;
 }

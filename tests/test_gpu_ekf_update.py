@@ -94,6 +94,23 @@ def test_full_size_frame(ctx):
     assert m.min() > 250
 
 
+def test_chunked_batches_and_degenerate_sizes(pre3, monkeypatch):
+    """Batches larger than the workspace budget run in chunks (forced here: 2 frames per chunk); no features at all."""
+    monkeypatch.setenv("PRE3_UPD_CHUNK", "2")
+    Fr = 5
+    b = se.make_ekf_frames(Fr, 91, n_id=10, n_euc=4)
+    fb = se.batch_to_numpy(b)
+    flags = (~fb["outlier"]).astype(np.uint8)
+    with pre3.Context(0) as c2:
+        xo, Po, m = c2.ekf_update_batch(fb, flags)
+        for f in range(Fr):
+            _check_update(se.frame(b, f), flags[f], xo[f], Po[f], m[f])
+        empty = {k: (v[:, :0] if isinstance(v, np.ndarray) and v.ndim >= 2 and k not in ("x", "P") else v)
+                 for k, v in fb.items()}
+        xo, Po, m = c2.ekf_update_batch(empty, np.zeros((Fr, 0), np.uint8))
+        assert (m == 0).all() and np.array_equal(xo, fb["x"]) and np.array_equal(Po, fb["P"])
+
+
 def test_argument_errors(ctx, pre3):
     b = se.batch_to_numpy(se.make_ekf_frames(1, 1, n_id=4))
     with pytest.raises(pre3.Pre3Error):

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Short single-GPU pass over every kernel family, for ncu (launch list / --set full):
 
-    python tools/prof_driver.py [cfg3] [cfg2] [cfg4] [cfg5] [dr_ye] [frames]      (default: all)
+    python tools/prof_driver.py [cfg3] [cfg2] [cfg4] [cfg5] [dr_ye] [frames] [ekf_update]      (default: all)
 
 Sizes are cut down so that ~40 replays per launch stay cheap; shapes per unit are the
 BASELINE.json ones (512x512 / 2048x2048 descriptors, N=300 / 20000 correspondences, n=1213)."""
@@ -21,7 +21,7 @@ pd = importlib.import_module("3pre_b200.dist")
 
 
 def main():
-    which = sys.argv[1:] or ["cfg3", "cfg2", "cfg4", "cfg5", "dr_ye", "frames"]
+    which = sys.argv[1:] or ["cfg3", "cfg2", "cfg4", "cfg5", "dr_ye", "frames", "ekf_update"]
     dev = torch.device("cuda", 0)
     ctx = pre3.Context(0)
     ctx.use_torch_stream()
@@ -86,6 +86,14 @@ def main():
         for _ in range(2):
             ctx.read_xyz_sr4000_batch_dev(sr, o, x, y, z, mc)
             ctx.features_xyz_batch_dev(sr, o, fr, xyz=xyz, n_keep=nk, desc_in=desc, desc_out=dout)
+        ctx.sync()
+    if "ekf_update" in which:  # update.m on cfg4-shaped frames (n = 1213, m ~ 320)
+        Fr = 16
+        b = se.make_ekf_frames(Fr, 4000, device=dev, n_id=200, outlier_ratio=0.2)
+        sel = (~b["outlier"]).to(torch.uint8)
+        xo, Po = torch.empty_like(b["x"]), torch.empty_like(b["P"])
+        torch.cuda.synchronize()
+        ctx.ekf_update_batch_dev(b, sel, xo, Po)
         ctx.sync()
     ctx.sync()
     print("launches", ctx.launch_count())
