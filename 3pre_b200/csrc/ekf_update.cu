@@ -66,24 +66,64 @@ __device__ __forceinline__ double h_val(int t, int a, const double* __restrict__
   return t < 13 ? hc[2 * t + a] : hf[2 * (t - 13) + a];  // 2 x 13 / 2 x 6 column-major blocks
 }
 
-// G(:, 2 j + a) = sum_t P(:, col_t) H(a, col_t): grid (row tiles, m columns, frames)
+// G = P H': thread = state row r, marching over the frame's flagged features.  The 13 camera columns of P(r, :) stay in
+// registers for the whole march, the six feature columns are read once per feature and serve both measurement rows:
+// 6 loads + 2 stores per feature instead of 38 loads.  H blocks of 32 features at a time are staged in shared memory.
+constexpr int GF = 32;
 __global__ void __launch_bounds__(256)
 k_upd_G(const double* __restrict__ P, UpdDims d, const int32_t* __restrict__ idx, const int32_t* __restrict__ mf,
         const int32_t* __restrict__ type, const int32_t* __restrict__ pos, const double* __restrict__ Hcam,
         const double* __restrict__ Hfeat, double* __restrict__ G) {
-  const int f = blockIdx.z, col = blockIdx.y;
-  if (col >= mf[f]) return;
-  const int i = idx[(size_t)f * d.F + (col >> 1)], a = col & 1;
+  __shared__ double s_hc[GF][26];
+  __shared__ double s_hf[GF][12];
+  __shared__ int s_pos[GF], s_nf[GF];
+  const int f = blockIdx.y;
+  const int Lall = mf[f] >> 1;
+  // gridDim.z blocks share the features of a frame (more blocks when few frames are in flight)
+  const int per = (Lall + gridDim.z - 1) / gridDim.z;
+  const int jbeg = blockIdx.z * per, L = min(Lall, jbeg + per);
+  if (jbeg >= L) return;
   const int r = blockIdx.x * 256 + threadIdx.x;
-  if (r >= d.n) return;
-  const size_t fi = (size_t)f * d.F + i;
-  const double* hc = Hcam + fi * 26;
-  const double* hf = Hfeat + fi * 12;
-  const int ps = pos[fi], nz = 13 + (type[fi] == 0 ? 6 : 3);
+  const bool live = r < d.n;
   const double* Pf = P + (size_t)f * d.n * d.n;
-  double acc = 0.0;
-  for (int t = 0; t < nz; ++t) acc = fma(Pf[(size_t)h_col(t, ps) * d.n + r], h_val(t, a, hc, hf), acc);
-  G[((size_t)f * d.Mmax + col) * d.n + r] = acc;
+  double* Gf = G + (size_t)f * d.Mmax * d.n;
+  double pc[13];
+#pragma unroll
+  for (int t = 0; t < 13; ++t) pc[t] = live ? Pf[(size_t)t * d.n + r] : 0.0;
+  for (int j0 = jbeg; j0 < L; j0 += GF) {
+    const int nj = min(GF, L - j0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < nj * 38; e += 256) {
+      const int jj = e / 38, q = e - jj * 38;
+      const size_t fi = (size_t)f * d.F + idx[(size_t)f * d.F + j0 + jj];
+      if (q < 26) s_hc[jj][q] = Hcam[fi * 26 + q];
+      else s_hf[jj][q - 26] = Hfeat[fi * 12 + (q - 26)];
+    }
+    for (int jj = threadIdx.x; jj < nj; jj += 256) {
+      const size_t fi = (size_t)f * d.F + idx[(size_t)f * d.F + j0 + jj];
+      s_pos[jj] = pos[fi];
+      s_nf[jj] = type[fi] == 0 ? 6 : 3;
+    }
+    __syncthreads();
+    if (!live) continue;
+    for (int jj = 0; jj < nj; ++jj) {
+      double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+      for (int t = 0; t < 13; ++t) {
+        a0 = fma(pc[t], s_hc[jj][2 * t], a0);
+        a1 = fma(pc[t], s_hc[jj][2 * t + 1], a1);
+      }
+      const double* pcol = Pf + (size_t)s_pos[jj] * d.n + r;
+      const int nf = s_nf[jj];
+      for (int u = 0; u < nf; ++u) {
+        const double pv = pcol[(size_t)u * d.n];
+        a0 = fma(pv, s_hf[jj][2 * u], a0);
+        a1 = fma(pv, s_hf[jj][2 * u + 1], a1);
+      }
+      Gf[(size_t)(2 * (j0 + jj)) * d.n + r] = a0;
+      Gf[(size_t)(2 * (j0 + jj) + 1) * d.n + r] = a1;
+    }
+  }
 }
 
 // S(ra, cb) = sum_t H(ra, col_t) G(col_t, cb) + (ra == cb); grid (m tiles, m, frames)
@@ -572,7 +612,9 @@ int update_chunk(pre3_ctx* ctx, int C, int n, int F, const double* dx, const dou
   int32_t* mf = dm_out ? dm_out : ws_take<int32_t>(ctx, C);
   cudaStream_t st = ctx->stream;
   k_upd_index<<<C, 256, 0, st>>>(dsel, F, idx, mf);
-  k_upd_G<<<dim3((n + 255) / 256, d.Mmax, C), 256, 0, st>>>(dP, d, idx, mf, dtype, dpos, dHcam, dHfeat, G);
+  const int gx = (n + 255) / 256;
+  const int gz = std::max(1, std::min(16, (4 * ctx->sm_count + gx * C - 1) / (gx * C)));
+  k_upd_G<<<dim3(gx, C, gz), 256, 0, st>>>(dP, d, idx, mf, dtype, dpos, dHcam, dHfeat, G);
   k_upd_S<<<dim3((d.Mmax + 127) / 128, d.Mmax, C), 128, 0, st>>>(G, d, idx, mf, dtype, dpos, dHcam, dHfeat, r_diag, S);
   PRE3_CUDA(cudaMemcpyAsync(Si, S, 8 * (size_t)C * M * M, cudaMemcpyDeviceToDevice, st));
   for (int k0 = 0; k0 < d.Mmax; k0 += IB) {  // frames whose m <= k0 return at once
