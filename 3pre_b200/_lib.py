@@ -113,6 +113,8 @@ SYMBOLS = {
     "pre3_ransac_batch_dev": (_I, [_VP, _VP, _VP, _VP, _I, _I, _OPTS, _VP, _VP, _VP]),
     "pre3_ekf_update_batch": (_I, [_VP, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _D, _VP, _VP, _VP]),
     "pre3_ekf_update_batch_dev": (_I, [_VP, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _D, _VP, _VP, _VP]),
+    "pre3_ekf_update_dense": (_I, [_VP, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "pre3_ekf_update_dense_dev": (_I, [_VP, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "pre3_ekf_rescue_hi_inliers_batch_dev": (_I, [_VP, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "pre3_read_xyz_sr4000_batch": (_I, [_VP, _VP, _I, C.POINTER(FrameOpts), _VP, _VP, _VP, _VP]),
     "pre3_read_xyz_sr4000_batch_dev": (_I, [_VP, _VP, _I, C.POINTER(FrameOpts), _VP, _VP, _VP, _VP]),

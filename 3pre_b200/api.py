@@ -605,6 +605,22 @@ class Context:
                                                      _ptr(frames["h"]), _ptr(frames["Hcam"]), _ptr(frames["Hfeat"]),
                                                      float(r_diag), _ptr(x_out), _ptr(P_out), _ptr(m_out)))
 
+    def ekf_update_dense(self, x, P, H, R, z, h):
+        """[x_k_k, p_k_k, K] = update(x, p, H, R, z, h) (update.m:27-56) with dense numpy matrices in their mathematical
+        orientation: P (n,n), H (m,n), R (m,m).  Returns (x_k_k (n,), p_k_k (n,n), K (n,m))."""
+        x = _c(np.asarray(x, np.float64).ravel())
+        n = x.size
+        z = _c(np.asarray(z, np.float64).ravel())
+        h = _c(np.asarray(h, np.float64).ravel())
+        m = z.size
+        Pc = _c(np.asarray(P, np.float64).T)        # column-major
+        Hc = _c(np.asarray(H, np.float64).reshape(m, n).T)
+        Rc = _c(np.asarray(R, np.float64).reshape(m, m).T)
+        xo, Po, Ko = np.zeros(n), np.zeros((n, n)), np.zeros((max(m, 1), n))
+        self._ck(self._lib.pre3_ekf_update_dense(self._h, n, m, _ptr(x), _ptr(Pc), _ptr(Hc), _ptr(Rc), _ptr(z), _ptr(h),
+                                                 _ptr(xo), _ptr(Po), _ptr(Ko)))
+        return xo, Po.T.copy(), Ko[:m].T.copy()
+
     def ekf_rescue_hi_inliers_batch_dev(self, frames: dict, P_kk, li, hi, h=None, Hcam=None, Hfeat=None):
         """rescue_hi_inliers.m:35-46 on CUDA tensors: hi (Fr,F) uint8 is written where ic == 1 and li == 0.
         h / Hcam / Hfeat: the measurements re-predicted at x_k_k (default: the frames' own)."""

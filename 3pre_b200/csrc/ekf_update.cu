@@ -286,8 +286,9 @@ k_inv_update(double* __restrict__ Sinv, int Mmax, const int32_t* __restrict__ mf
   }
 }
 
-// ---- fp64 GEMM, column-major:  C = A B  (TRANSB 0)  or  C = D - A B'  (TRANSB 1) -------------------
-//   A: M x Kd (lda), B: Kd x N (ldb) or N x Kd (ldb) when transposed, per-frame Kd = mf[f] (and N = mf[f] when NFROMM).
+// ---- fp64 GEMM, column-major:  C = [D +] A B  (TRANSB 0)  or  C = [D +] A B'  (TRANSB 1) ------------
+//   A: M x Kd (lda), B: Kd x N (ldb) or N x Kd (ldb) when transposed; Kd = mf[f] per frame (and N = mf[f] when
+//   n_from_m), or kd_fixed when mf is null.
 // 64 x 64 tile per 256-thread block, 16-deep k slices through shared memory, 4 x 4 outputs per thread with rows
 // tx + 16 i (conflict-free 128-byte smem reads, coalesced stores) and columns ty + 16 j (broadcast reads).
 constexpr int GM = 64, GN = 64, GK = 16;
@@ -295,11 +296,11 @@ template <int TRANSB>
 __global__ void __launch_bounds__(256)
 k_dgemm(const double* __restrict__ A, int lda, size_t strideA, const double* __restrict__ B, int ldb, size_t strideB,
         double* __restrict__ C, int ldc, size_t strideC, const double* __restrict__ D, int ldd, size_t strideD, int M,
-        int N, const int32_t* __restrict__ mf, int n_from_m) {
+        int N, const int32_t* __restrict__ mf, int n_from_m, int kd_fixed) {
   __shared__ double As[GK][GM];
   __shared__ double Bs[GK][GN + 1];
   const int f = blockIdx.z;
-  const int Kd = mf[f];
+  const int Kd = mf ? mf[f] : kd_fixed;
   if (n_from_m) N = Kd;
   const int m0 = blockIdx.x * GM, n0 = blockIdx.y * GN;
   if (m0 >= M || n0 >= N) return;
@@ -360,7 +361,7 @@ k_dgemm(const double* __restrict__ A, int lda, size_t strideA, const double* __r
       const int gr = m0 + tx + 16 * i;
       if (gr >= M) continue;
       const double v = acc[i][j];
-      C[(size_t)gc * ldc + gr] = TRANSB ? D[(size_t)gc * ldd + gr] - v : v;
+      C[(size_t)gc * ldc + gr] = D ? D[(size_t)gc * ldd + gr] + v : v;
     }
   }
 }
@@ -625,7 +626,7 @@ int update_chunk(pre3_ctx* ctx, int C, int n, int F, const double* dx, const dou
   const dim3 g1((n + GM - 1) / GM, (d.Mmax + GN - 1) / GN, C), g2((n + GM - 1) / GM, (n + GN - 1) / GN, C);
   // K = G inv(S);  P_out = 0.5 (P + P') - G K'   (K S K' = G K': K S = P H' = G by construction, so the reference's
   // second n x m x m product is not repeated; the difference is rounding x cond(S), far inside the tolerance)
-  k_dgemm<0><<<g1, 256, 0, st>>>(G, n, (size_t)n * M, Si, d.Mmax, M * M, K, n, (size_t)n * M, nullptr, 0, 0, n, 0, mf, 1);
+  k_dgemm<0><<<g1, 256, 0, st>>>(G, n, (size_t)n * M, Si, d.Mmax, M * M, K, n, (size_t)n * M, nullptr, 0, 0, n, 0, mf, 1, 0);
   k_dsyrk_update<<<g2, 256, 0, st>>>(G, K, (size_t)n * M, dP, dP_out, n, mf);
   k_upd_x<<<dim3((n + 255) / 256, C), 256, M * sizeof(double), st>>>(dx, K, d, idx, mf, dz, dh, dx_out);
   k_upd_quat<<<C, 256, 0, st>>>(dP_out, dx_out, n, mf);
@@ -646,6 +647,66 @@ int update_impl(pre3_ctx* ctx, int Fr, int n, int F, const double* dx, const dou
                           dz + 2 * fF, dh + 2 * fF, dHcam + 26 * fF, dHfeat + 12 * fF, r_diag, dx_out + (size_t)f0 * n,
                           dP_out + (size_t)f0 * n * n, dm_out ? dm_out + f0 : nullptr));
   }
+  return PRE3_OK;
+}
+
+// ---- update.m with H and R given as dense matrices (the function's own signature) ------------------
+__global__ void k_set_int(int32_t* p, int v) { *p = v; }
+
+__global__ void __launch_bounds__(256)
+k_upd_x_dense(const double* __restrict__ x, const double* __restrict__ K, int n, int m, const double* __restrict__ z,
+              const double* __restrict__ h, double* __restrict__ x_out) {
+  extern __shared__ double s_d[];
+  for (int j = threadIdx.x; j < m; j += 256) s_d[j] = z[j] - h[j];
+  __syncthreads();
+  const int r = blockIdx.x * 256 + threadIdx.x;
+  if (r >= n) return;
+  double acc = 0.0;
+  for (int j = 0; j < m; ++j) acc = fma(K[(size_t)j * n + r], s_d[j], acc);
+  x_out[r] = x[r] + acc;
+}
+
+size_t dense_ws_bytes(int n, int m) {
+  const size_t M = (size_t)std::max(m, 1);
+  return 2 * align_up(8 * (size_t)n * M) + 2 * align_up(8 * M * M) + align_up(8 * IB * IB) + 2 * align_up(8 * M * IB) + 4096;
+}
+
+int update_dense_impl(pre3_ctx* ctx, int n, int m, const double* dx, const double* dP, const double* dH,
+                      const double* dR, const double* dz, const double* dh, double* dx_out, double* dP_out,
+                      double* dK_out) {
+  Span span__(ctx, T_EKF_UPDATE);
+  cudaStream_t st = ctx->stream;
+  if (m == 0) {  // update.m:50-54
+    PRE3_CUDA(cudaMemcpyAsync(dx_out, dx, 8 * (size_t)n, cudaMemcpyDeviceToDevice, st));
+    PRE3_CUDA(cudaMemcpyAsync(dP_out, dP, 8 * (size_t)n * n, cudaMemcpyDeviceToDevice, st));
+    return PRE3_OK;
+  }
+  const size_t M = (size_t)m;
+  double* G = ws_take<double>(ctx, (size_t)n * M);
+  double* K = dK_out ? dK_out : ws_take<double>(ctx, (size_t)n * M);
+  double* S = ws_take<double>(ctx, M * M);
+  double* Si = ws_take<double>(ctx, M * M);
+  double* Di = ws_take<double>(ctx, IB * IB);
+  double* Cc = ws_take<double>(ctx, M * IB);
+  double* Rp = ws_take<double>(ctx, M * IB);
+  int32_t* mf = ws_take<int32_t>(ctx, 1);
+  k_set_int<<<1, 1, 0, st>>>(mf, m);
+  const dim3 gnm((n + GM - 1) / GM, (m + GN - 1) / GN, 1), gmm((m + GM - 1) / GM, (m + GN - 1) / GN, 1);
+  // G = P H'  (n x n x m);  S = H G + R  (m x n x m)
+  k_dgemm<1><<<gnm, 256, 0, st>>>(dP, n, 0, dH, m, 0, G, n, 0, nullptr, 0, 0, n, m, nullptr, 0, n);
+  k_dgemm<0><<<gmm, 256, 0, st>>>(dH, m, 0, G, n, 0, S, m, 0, dR, m, 0, m, m, nullptr, 0, n);
+  PRE3_CUDA(cudaMemcpyAsync(Si, S, 8 * M * M, cudaMemcpyDeviceToDevice, st));
+  for (int k0 = 0; k0 < m; k0 += IB) {
+    k_inv_diag<<<1, 1024, 0, st>>>(Si, m, mf, k0, Di);
+    k_inv_panel<<<dim3((m + 63) / 64, 1), 256, 0, st>>>(Si, m, mf, k0, Di, Cc, Rp);
+    k_inv_update<<<dim3((m + 63) / 64, (m + 63) / 64, 1), 256, 0, st>>>(Si, m, mf, k0, Di, Cc, Rp);
+  }
+  k_dgemm<0><<<gnm, 256, 0, st>>>(G, n, 0, Si, m, 0, K, n, 0, nullptr, 0, 0, n, m, nullptr, 0, m);
+  k_dsyrk_update<<<dim3((n + GM - 1) / GM, (n + GN - 1) / GN, 1), 256, 0, st>>>(G, K, 0, dP, dP_out, n, mf);
+  k_upd_x_dense<<<(n + 255) / 256, 256, M * sizeof(double), st>>>(dx, K, n, m, dz, dh, dx_out);
+  k_upd_quat<<<1, 256, 0, st>>>(dP_out, dx_out, n, mf);
+  count_launch(ctx, 7 + 3 * ((m + IB - 1) / IB));
+  PRE3_CUDA(cudaGetLastError());
   return PRE3_OK;
 }
 
@@ -728,6 +789,54 @@ int pre3_ekf_update_batch(pre3_ctx* ctx, int Fr, int n, int F, const double* x, 
   cudaFree(buf);
   if (rc == PRE3_OK && se != cudaSuccess) return fail(ctx, PRE3_ERR_CUDA, cudaGetErrorString(se));
   return rc;
+}
+
+int pre3_ekf_update_dense_dev(pre3_ctx* ctx, int n, int m, const double* dx, const double* dP, const double* dH,
+                              const double* dR, const double* dz, const double* dh, double* dx_out, double* dP_out,
+                              double* dK_out) {
+  UPD_LIVE();
+  if (n < 7 || m < 0) return fail(ctx, PRE3_ERR_ARG, "bad sizes (n >= 7: the quaternion lives in x(4:7))");
+  if (!dx || !dP || !dx_out || !dP_out || (m > 0 && (!dH || !dR || !dz || !dh))) return fail(ctx, PRE3_ERR_ARG, "null pointer");
+  if (dP_out == dP) return fail(ctx, PRE3_ERR_ARG, "p_k_k must not alias the input covariance");
+  if ((size_t)m * sizeof(double) > 48 * 1024) return fail(ctx, PRE3_ERR_ARG, "more than 6144 stacked rows");
+  PRE3_TRY(ws_reserve(ctx, dense_ws_bytes(n, m)));
+  return update_dense_impl(ctx, n, m, dx, dP, dH, dR, dz, dh, dx_out, dP_out, dK_out);
+}
+
+int pre3_ekf_update_dense(pre3_ctx* ctx, int n, int m, const double* x, const double* P, const double* H,
+                          const double* R, const double* z, const double* h, double* x_out, double* P_out,
+                          double* K_out) {
+  UPD_LIVE();
+  if (n < 7 || m < 0) return fail(ctx, PRE3_ERR_ARG, "bad sizes (n >= 7: the quaternion lives in x(4:7))");
+  if (!x || !P || !x_out || !P_out || (m > 0 && (!H || !R || !z || !h))) return fail(ctx, PRE3_ERR_ARG, "null pointer");
+  if ((size_t)m * sizeof(double) > 48 * 1024) return fail(ctx, PRE3_ERR_ARG, "more than 6144 stacked rows");
+  const size_t nb = 8 * (size_t)n, pb = 8 * (size_t)n * n, hb = 8 * (size_t)m * n, rb = 8 * (size_t)m * m, zb = 8 * (size_t)m;
+  PRE3_TRY(ws_reserve(ctx, dense_ws_bytes(n, m) + 2 * align_up(nb) + 2 * align_up(pb) + 2 * align_up(hb) + align_up(rb) +
+                               2 * align_up(zb) + 8192));
+  double* dx = ws_take<double>(ctx, n);
+  double* dxo = ws_take<double>(ctx, n);
+  double* dP = ws_take<double>(ctx, (size_t)n * n);
+  double* dPo = ws_take<double>(ctx, (size_t)n * n);
+  double* dH = ws_take<double>(ctx, (size_t)std::max(m, 1) * n);
+  double* dK = ws_take<double>(ctx, (size_t)std::max(m, 1) * n);
+  double* dR = ws_take<double>(ctx, (size_t)std::max(m, 1) * std::max(m, 1));
+  double* dz = ws_take<double>(ctx, std::max(m, 1));
+  double* dh = ws_take<double>(ctx, std::max(m, 1));
+  cudaStream_t st = ctx->stream;
+  PRE3_CUDA(cudaMemcpyAsync(dx, x, nb, cudaMemcpyHostToDevice, st));
+  PRE3_CUDA(cudaMemcpyAsync(dP, P, pb, cudaMemcpyHostToDevice, st));
+  if (m > 0) {
+    PRE3_CUDA(cudaMemcpyAsync(dH, H, hb, cudaMemcpyHostToDevice, st));
+    PRE3_CUDA(cudaMemcpyAsync(dR, R, rb, cudaMemcpyHostToDevice, st));
+    PRE3_CUDA(cudaMemcpyAsync(dz, z, zb, cudaMemcpyHostToDevice, st));
+    PRE3_CUDA(cudaMemcpyAsync(dh, h, zb, cudaMemcpyHostToDevice, st));
+  }
+  PRE3_TRY(update_dense_impl(ctx, n, m, dx, dP, dH, dR, dz, dh, dxo, dPo, dK));
+  PRE3_CUDA(cudaMemcpyAsync(x_out, dxo, nb, cudaMemcpyDeviceToHost, st));
+  PRE3_CUDA(cudaMemcpyAsync(P_out, dPo, pb, cudaMemcpyDeviceToHost, st));
+  if (K_out && m > 0) PRE3_CUDA(cudaMemcpyAsync(K_out, dK, hb, cudaMemcpyDeviceToHost, st));
+  PRE3_CUDA(cudaStreamSynchronize(st));
+  return PRE3_OK;
 }
 
 int pre3_ekf_rescue_hi_inliers_batch_dev(pre3_ctx* ctx, int Fr, int n, int F, const double* dP_kk,

@@ -171,6 +171,22 @@ def Calculate_V_Omega_RANSAC_my_version(DataPre, DataCurrent, **kw):
 
 
 # ---------------------------------------------------------------------------------------
+# the step after the path (SURVEY.md 8f rank 3): the EKF partial updates
+# ---------------------------------------------------------------------------------------
+def update(x_km1_k, p_km1_k, H, R, z, h):
+    """[x_k_k, p_k_k, K] = update(x_km1_k, p_km1_k, H, R, z, h)   (M/update.m:27-56).  H may be a scipy sparse
+    matrix (the reference stacks sparse 2 x n blocks); K = 0 when z is empty (:54)."""
+    if hasattr(H, "toarray"):
+        H = H.toarray()
+    z = np.asarray(z, np.float64).ravel()
+    x = np.asarray(x_km1_k, np.float64)
+    if z.size == 0:
+        return x.copy(), np.array(p_km1_k, np.float64), 0
+    xo, Po, K = context().ekf_update_dense(x.ravel(), p_km1_k, H, R, z, np.asarray(h, np.float64).ravel())
+    return xo.reshape(x.shape), Po, K
+
+
+# ---------------------------------------------------------------------------------------
 # the step before the path (SURVEY.md 8f rank 2): SR4000 frame -> filtered maps -> per-feature 3-D points
 # ---------------------------------------------------------------------------------------
 def _sr(sr_data):

@@ -26,6 +26,9 @@ int mxIsNumeric(const mxArray *a);
 int mxIsComplex(const mxArray *a);
 int mxIsStruct(const mxArray *a);
 int mxIsEmpty(const mxArray *a);
+int mxIsSparse(const mxArray *a);
+mwIndex *mxGetIr(const mxArray *a);
+mwIndex *mxGetJc(const mxArray *a);
 mwSize mxGetNumberOfDimensions(const mxArray *a);
 size_t mxGetM(const mxArray *a);
 size_t mxGetN(const mxArray *a);

@@ -213,6 +213,15 @@ PRE3_API int pre3_ekf_update_batch_dev(pre3_ctx *ctx, int Fr, int n, int F, cons
                               const int32_t *dtype, const int32_t *dpos, const uint8_t *dsel, const double *dz,
                               const double *dh, const double *dHcam, const double *dHfeat, double r_diag,
                               double *dx_out, double *dP_out, int32_t *dm_out);
+/* [x_k_k, p_k_k, K] = update(x_km1_k, p_km1_k, H, R, z, h) with the function's own signature (M/update.m:27): H m x n
+ * and R m x m dense column-major (a sparse MATLAB H is expanded by the gateway), n >= 7.  K_out: n x m or NULL.
+ * m == 0: x and P are copied through (:50-54; the reference returns K = 0). */
+PRE3_API int pre3_ekf_update_dense(pre3_ctx *ctx, int n, int m, const double *x, const double *P, const double *H,
+                          const double *R, const double *z, const double *h, double *x_out, double *P_out,
+                          double *K_out);
+PRE3_API int pre3_ekf_update_dense_dev(pre3_ctx *ctx, int n, int m, const double *dx, const double *dP,
+                              const double *dH, const double *dR, const double *dz, const double *dh,
+                              double *dx_out, double *dP_out, double *dK_out);
 /* The test of rescue_hi_inliers.m:35-46 on device buffers: for features with ic == 1 and li == 0,
  * hi = (nu' * inv(H p_k_k H') * nu < 5.9915), nu = z - h; other entries of hi are left untouched.  h, Hcam, Hfeat
  * are the measurements re-predicted at x_k_k (:32-33: predict_camera_measurements / calculate_derivatives stay with

@@ -72,6 +72,9 @@ void mxDestroyArray(mxArray *a);
 /* additions for the product's own gateways (3pre_b200/mex_files/*.cpp): scalars and 1 x 1 structs */
 typedef size_t mwIndex;
 int mxIsEmpty(const mxArray *a);
+int mxIsSparse(const mxArray *a); /* always 0: the stub has no sparse arrays */
+mwIndex *mxGetIr(const mxArray *a);
+mwIndex *mxGetJc(const mxArray *a);
 size_t mxGetNumberOfElements(const mxArray *a);
 mxArray *mxCreateDoubleScalar(double v);
 int mxIsStruct(const mxArray *a);

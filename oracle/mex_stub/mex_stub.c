@@ -77,6 +77,9 @@ void mxDestroyArray(mxArray *a) {
 }
 
 int mxIsEmpty(const mxArray *a) { return a->m * a->n == 0; }
+int mxIsSparse(const mxArray *a) { (void)a; return 0; }
+mwIndex *mxGetIr(const mxArray *a) { (void)a; return 0; }
+mwIndex *mxGetJc(const mxArray *a) { (void)a; return 0; }
 size_t mxGetNumberOfElements(const mxArray *a) { return a->m * a->n; }
 mxArray *mxCreateDoubleScalar(double v) {
   mxArray *a = mxCreateDoubleMatrix(1, 1, mxREAL);

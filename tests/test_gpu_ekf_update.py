@@ -115,3 +115,78 @@ def test_argument_errors(ctx, pre3):
     b = se.batch_to_numpy(se.make_ekf_frames(1, 1, n_id=4))
     with pytest.raises(pre3.Pre3Error):
         ctx.ekf_update_batch(b, np.zeros((1, 4), np.uint8), x=np.zeros((1, 5)), P=np.zeros((1, 5, 5)))
+
+
+def test_update_with_the_functions_own_signature(ctx):
+    """[x, p, K] = update(x, p, H, R, z, h) with dense H and a general R (M/update.m:27), through the mirror."""
+    ml = importlib.import_module("3pre_b200.matlab")
+    b = se.make_ekf_frames(1, 55, n_id=25, n_euc=4, interleave=True)
+    fr = se.frame(b, 0)
+    sel = [i for i in range(fr.F) if not fr.outlier[i]]
+    H = np.vstack([rne.dense_H(fr, i) for i in sel])
+    z = np.concatenate([fr.z[i] for i in sel]); h = np.concatenate([fr.h[i] for i in sel])
+    rng = np.random.default_rng(1)
+    A = rng.normal(size=(len(z), len(z))) * 0.1
+    R = np.eye(len(z)) * 1.5 + A @ A.T                       # a general SPD measurement covariance
+    gx, gP, gK = rne.update(fr.x, fr.P, H, R, z, h)
+    x, P, K = ml.update(fr.x.reshape(-1, 1), fr.P, H, R, z.reshape(-1, 1), h.reshape(-1, 1))
+    assert x.shape == (fr.n, 1) and np.abs(x.ravel() - gx).max() < TOL
+    assert np.abs(P - gP).max() <= TOL * np.abs(gP).max() and np.abs(K - gK).max() <= TOL * np.abs(gK).max()
+    from scipy import sparse
+    x2, P2, _ = ml.update(fr.x, fr.P, sparse.csr_matrix(H), R, z, h)
+    assert np.array_equal(x2, x.ravel()) and np.array_equal(P2, P)
+    x0, P0, K0 = ml.update(fr.x, fr.P, np.zeros((0, fr.n)), np.zeros((0, 0)), np.zeros(0), np.zeros(0))
+    assert np.array_equal(x0, fr.x) and np.array_equal(P0, fr.P) and K0 == 0
+
+
+def test_mex_gateway_update_shadows_update_m():
+    """3pre_b200/mex_files/update.cpp linked against the stub MEX runtime (oracle/mex_stub) and called through
+    mexFunction with mxArrays: the drop-in for M/update.m itself."""
+    import ctypes as C
+    import os
+    import subprocess
+    from oracle import refmex
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = os.path.join(root, "tests", "_build")
+    os.makedirs(out, exist_ok=True)
+    so = os.path.join(out, "libpre3_update_gw.so")
+    libdir = os.path.join(root, "3pre_b200", "lib")
+    subprocess.run(["g++", "-O2", "-fPIC", "-shared", "-o", so, os.path.join(root, "3pre_b200", "mex_files", "update.cpp"),
+                    "-x", "c", os.path.join(root, "oracle", "mex_stub", "mex_stub.c"), "-x", "none",
+                    "-I", os.path.join(root, "oracle", "mex_stub"), "-I", os.path.join(root, "3pre_b200", "mex_files"),
+                    "-I", os.path.join(root, "include"), "-L", libdir, "-lpre3", f"-Wl,-rpath,{libdir}"], check=True)
+    L = refmex.lib(so)
+
+    def call(args, nout):   # args: MATLAB matrices (rows, cols); passed column-major
+        keep = [np.ascontiguousarray(np.atleast_2d(a).T, np.float64) for a in args]
+        ins = [L.stub_wrap(6, k.shape[1], k.shape[0], k.ctypes.data) for k in keep]
+        in_arr = (C.POINTER(refmex._MxArray) * len(ins))(*ins)
+        out_arr = (C.POINTER(refmex._MxArray) * nout)()
+        rc = L.stub_call_mex(nout, out_arr, len(ins), in_arr)
+        for a in ins:
+            L.mxDestroyArray(a)
+        if rc != 0:
+            raise refmex.MexError(L.stub_last_error().decode())
+        res = []
+        for i in range(nout):
+            m = out_arr[i].contents
+            res.append(np.ctypeslib.as_array(C.cast(m.data, C.POINTER(C.c_double)), shape=(m.n, m.m)).copy().T)
+            L.mxDestroyArray(out_arr[i])
+        return res
+
+    b = se.make_ekf_frames(1, 56, n_id=12)
+    fr = se.frame(b, 0)
+    sel = [i for i in range(fr.F) if not fr.outlier[i]]
+    H = np.vstack([rne.dense_H(fr, i) for i in sel])
+    z = np.concatenate([fr.z[i] for i in sel]); h = np.concatenate([fr.h[i] for i in sel])
+    x, P, K = call([fr.x.reshape(-1, 1), fr.P, H, np.eye(len(z)), z.reshape(-1, 1), h.reshape(-1, 1)], 3)
+    gx, gP, gK = rne.update(fr.x, fr.P, H, np.eye(len(z)), z, h)
+    assert x.shape == (fr.n, 1) and np.abs(x.ravel() - gx).max() < TOL
+    assert np.abs(P - gP).max() <= TOL * np.abs(gP).max() and np.abs(K - gK).max() <= TOL * np.abs(gK).max()
+    # empty measurement vector: copied through, K = 0 (update.m:50-54)
+    x0, P0, K0 = call([fr.x.reshape(-1, 1), fr.P, np.zeros((0, fr.n)), np.zeros((0, 0)), np.zeros((0, 1)), np.zeros((0, 1))], 3)
+    assert np.array_equal(x0.ravel(), fr.x) and np.array_equal(P0, fr.P) and K0.ravel()[0] == 0
+    with pytest.raises(refmex.MexError, match="six inputs"):
+        call([fr.x.reshape(-1, 1), fr.P], 1)
+    with pytest.raises(refmex.MexError, match="H must be"):
+        call([fr.x.reshape(-1, 1), fr.P, H[:, :5], np.eye(len(z)), z.reshape(-1, 1), h.reshape(-1, 1)], 1)
