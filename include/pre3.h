@@ -188,8 +188,9 @@ PRE3_API int pre3_ransac(pre3_ctx *ctx, const double *Ya, const double *Yb, int 
                 const pre3_ransac_opts *opts, const int32_t *samples, pre3_pair_result *res,
                 uint8_t *mask, int32_t *counts, int8_t *states);
 
-/* P independent correspondence sets, padded to Nmax columns each; n_corr[P] valid counts.
- * samples: P x (k x H) or NULL.  masks: P x Nmax or NULL. */
+/* RANSAC_CALC_VER2 (M/mex_files/RANSAC_CALCULATION/RANSAC_CALC_VER2.m:2-201) for P independent correspondence sets at
+ * once -- the pairs M/find_consistent_sift_matches.m:22-32 loops over --, padded to Nmax columns each; n_corr[P] valid
+ * counts.  samples: P x (k x H) or NULL.  masks: P x Nmax or NULL. */
 PRE3_API int pre3_ransac_batch(pre3_ctx *ctx, const double *Ya, const double *Yb, const int32_t *n_corr,
                       int P, int Nmax, const pre3_ransac_opts *opts, const int32_t *samples,
                       pre3_pair_result *res, uint8_t *masks);

@@ -42,6 +42,30 @@ def test_library_exports_every_declared_symbol(pre3):
     assert b"sm_100a" in lib.pre3_version()
 
 
+def test_every_entry_point_cites_the_reference_interface_it_replaces():
+    """include/pre3.h: the comment block in front of every PRE3_API declaration (or of the group it belongs to) names
+    a reference file (M/...: .m / .c) with line numbers, or is plumbing (context, timing, measurement helpers)."""
+    src = open(HEADER).read()
+    plumbing = ("create", "destroy", "last_error", "version", "set_stream", "set_match_engine", "sync", "launch_count",
+                "transfer_bytes", "timing", "measure", "eval_schedule")
+    # split at blank lines that precede a comment opener: one chunk = comment block + its declarations
+    chunks = re.split(r"\n\s*\n(?=/\*)", src)
+    cited = set()
+    for ch in chunks:
+        names = re.findall(r"PRE3_API\s+[\w\s\*]+?\b(pre3_\w+)\s*\(", ch)
+        if names and re.search(r"\.(m|c|prj)\b[^\n]*?:\d+|\.(m|c):\d+", ch):
+            cited.update(names)
+    missing = [s for s in declared_symbols() if s not in cited and not any(k in s for k in plumbing)]
+    assert not missing, missing
+
+
+def test_struct_layouts_of_the_later_additions(pre3):
+    L = pre3._lib
+    assert C.sizeof(L.DrYeStat) == 32 and pre3.DR_YE_STAT_DTYPE.itemsize == 32
+    assert C.sizeof(L.FrameOpts) == 24 and L.FrameOpts.rows.offset == 16
+    assert L.TIMING_NCAT == int(re.search(r"#define PRE3_TIMING_NCAT (\d+)", open(HEADER).read()).group(1))
+
+
 def test_library_is_sm100a_only():
     so = os.path.join(ROOT, "3pre_b200", "lib", "libpre3.so")
     out = subprocess.run(["cuobjdump", "-lelf", so], capture_output=True, text=True).stdout
