@@ -149,7 +149,7 @@ __device__ __forceinline__ bool exact_inlier(const double* R, const double* t, c
 }
 
 template <int K, int MODE>
-__global__ void __launch_bounds__(EV_THREADS)
+__global__ void __launch_bounds__(EV_THREADS, 6)
 k_eval(const PairMeta* __restrict__ meta, const double* __restrict__ Ya, const double* __restrict__ Yb,
        const float4* __restrict__ Ya4, const float4* __restrict__ Yb4, int Nmax,
        const int32_t* __restrict__ samples, uint64_t seed, uint32_t pair_id0, long long h0, int H,
