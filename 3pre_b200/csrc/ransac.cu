@@ -1742,6 +1742,10 @@ int eval_wave_ends(const pre3_ransac_opts& o, int32_t* ends, int cap) {
     if (n < cap) ends[n] = H;
     return 1;
   }
+  // The reference's loop ends after 5*ceil(log(0.01)/log(1-w^k)) recorded hypotheses once a sample whose support is the
+  // fraction w of the matches has been seen: ~215 at the SR4000 shapes of the bench (w ~ 0.63, k = 5).  First wave 256,
+  // then doubling (measured: a 192-wide first wave sends most pairs into a second wave, eval 0.44 -> 0.60 ms; finer
+  // waves 256/384/512/... measured equal or slower).
   int beg = 0, width = 256;
   while (beg < H) {
     int end = std::min(H, beg + width);
