@@ -592,3 +592,29 @@ def test_mex_gateway_is_a_drop_in(golden, orc, synth):
         refmex.siftmatch(a.astype(np.int32), a.astype(np.int32), so=so)
     with pytest.raises(refmex.MexError, match="At most three"):
         refmex.siftmatch(a, a, 1.5, extra_args=1, so=so)
+
+
+def test_process_sequence_from_cached_sift_results(ctx, pre3, orc, synth, tmp_path):
+    """The loop of find_consistent_sift_matches.m:22-32 over a folder of SIFT_result%04d.mat files (3pre_b200/formats.py):
+    ragged feature counts per frame, one pre3_sequence call, RANSAC5_step files written as Calculate_V_Omega_RANSAC_my_version
+    reads them."""
+    import importlib
+    fm = importlib.import_module("3pre_b200.formats")
+    folder = str(tmp_path) + "/"
+    frames = []
+    base = synth.make_frame_pair(7700, K1=200, K2=200, n_corr=120)
+    perm = np.random.default_rng(5).permutation(200)[:150]      # frame 2 re-observes frame 0's features, moved rigidly
+    seq = [(base.desc1, base.xyz1), (base.desc2[:180], base.xyz2[:180]),
+           (base.desc1[perm], base.xyz1[perm] @ base.R + np.array([0.02, -0.01, 0.03]))]
+    for k, (d, x) in enumerate(seq):
+        fm.save_sift_result(fm.sift_result_path(folder, 10 + k), {"idxScan": 10 + k, "Descriptor": d.T, "XYZ_DATA": x.T})
+    o = pre3.make_opts(max_iteration=300, H=300, seed=4)
+    res, matches, masks = fm.process_sequence(ctx, folder, 10, 12, opts=o)
+    for p in range(2):
+        om, g = orc.pair(seq[p][0], seq[p + 1][0], seq[p][1], seq[p + 1][1], 4, p, H=300, max_iteration=300)
+        n = int(res["n_matches"][p])
+        np.testing.assert_array_equal(matches[p, :n], om)
+        assert (res["status"][p], res["best_fit"][p], res["best_sample"][p], res["state"][p]) == \
+            (g.status, g.best_fit, g.best_sample, g.state), (p, res[p], g)
+        T, R, st = fm.load_ransac_step(fm.ransac_step_path(folder, 10 + p, 11 + p))
+        assert st == g.state and np.abs(R - g.R).max() < 1e-9 and np.abs(T.ravel() - g.T).max() < 1e-9
