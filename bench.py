@@ -503,9 +503,14 @@ def bench_cfg1(ctx, pre3, synth, dev):
         for _ in range(20):
             r, _, _ = ctx.pairs(h["desc1"], h["desc2"], h["xyz1"], h["xyz2"], opts)
         ms_host = (time.perf_counter() - t0) / 20 * 1e3
+        # fixed H (adaptive stop off): all 2000 sample sets are evaluated -> hypothesis x match evals/s of ONE pair
+        fopts = pre3.make_opts(method=0, k=k, max_iteration=2001, adaptive=False, H=2000, seed=7)
+        ms_fix = _time_steps(lambda: ctx.pairs_dev(d["desc1"], d["desc2"], d["xyz1"], d["xyz2"], fopts, res), 20, 3)
         out[f"k{k}"] = {"ms_per_pair_device_resident": ms_dev, "ms_per_pair_host_buffers": ms_host,
                         "best_fit": int(r["best_fit"][0]), "n_matches": int(r["n_matches"][0]),
-                        "sample_sets_consumed": int(r["n_consumed"][0])}
+                        "sample_sets_consumed": int(r["n_consumed"][0]),
+                        "fixed_H": {"ms_per_pair_device_resident": ms_fix,
+                                    "hyp_x_match_evals_per_s": 2000.0 * int(r["n_matches"][0]) / (ms_fix * 1e-3)}}
     return out
 
 
