@@ -130,3 +130,35 @@ def test_planted_motion(orc):
         assert rn.rot_angle(r.R, c.R) < 2e-3 and np.abs(r.T - c.t).max() < 5e-3
         assert (r.mask & ~c.inlier).sum() <= 3 and (r.mask & c.inlier).sum() >= 0.9 * c.inlier.sum()
         assert 0 < r.error_mean < 0.01 and 0 < r.error_std < 0.01
+
+
+def test_sampler_restatements_agree_on_random_tables(orc):
+    """C restatement vs the line-by-line numpy restatement of ransac_dr_ye.m:28-48 on random match tables (shared
+    features, k1 values that also occur as k2 values) and random uniform streams."""
+    rng = np.random.default_rng(123)
+    for trial in range(40):
+        pnum = int(rng.integers(6, 60))
+        nf = int(rng.integers(4, 80))
+        match = np.stack([np.sort(rng.choice(200, pnum, replace=False)) % max(nf, pnum), rng.integers(0, nf, pnum)], 1)
+        match = match.astype(np.int32)
+        # the loops need four matches with pairwise distinct features to terminate: skip hopeless tables
+        if len(set(match[:, 0])) < 4 or len(set(match[:, 1])) < 4:
+            continue
+        stream = rng.random(3000)
+        pos = [0]
+
+        def rand():
+            v = stream[pos[0] % stream.size]
+            pos[0] += 1
+            return v
+
+        want = []
+        for _ in range(20):
+            want.append(rn.dr_ye_sampler(match, rand))
+            if pos[0] > 2500:
+                break
+        if pos[0] > 2500:
+            continue
+        got, used = orc.dr_ye_sample_stream(stream, match, len(want))
+        np.testing.assert_array_equal(got, np.array(want, np.int32))
+        assert used == pos[0]
