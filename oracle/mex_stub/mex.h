@@ -77,6 +77,9 @@ mwIndex *mxGetIr(const mxArray *a);
 mwIndex *mxGetJc(const mxArray *a);
 size_t mxGetNumberOfElements(const mxArray *a);
 mxArray *mxCreateDoubleScalar(double v);
+mxArray *mxCreateLogicalMatrix(size_t m, size_t n); /* uint8 0/1 data, class mxLOGICAL_CLASS */
+int stub_struct_nfields(const mxArray *a);
+const char *stub_struct_field_name(const mxArray *a, int k);
 int mxIsStruct(const mxArray *a);
 mxArray *mxCreateStructMatrix(size_t m, size_t n, int nfields, const char **names);
 void mxSetField(mxArray *a, mwIndex i, const char *name, mxArray *v);

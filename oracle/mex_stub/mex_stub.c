@@ -86,7 +86,19 @@ mxArray *mxCreateDoubleScalar(double v) {
   ((double *)a->data)[0] = v;
   return a;
 }
+mxArray *mxCreateLogicalMatrix(size_t m, size_t n) {
+  mxArray *a = (mxArray *)calloc(1, sizeof(mxArray));
+  a->cls = mxLOGICAL_CLASS;
+  a->m = m;
+  a->n = n;
+  a->ndim = 2;
+  a->owns_data = 1;
+  a->data = calloc(m * n ? m * n : 1, 1);
+  return a;
+}
 int mxIsStruct(const mxArray *a) { return a->cls == mxSTRUCT_CLASS; }
+int stub_struct_nfields(const mxArray *a) { return a->cls == mxSTRUCT_CLASS ? ((stub_struct *)a->data)->nfields : 0; }
+const char *stub_struct_field_name(const mxArray *a, int k) { return ((stub_struct *)a->data)->names[k]; }
 mxArray *mxCreateStructMatrix(size_t m, size_t n, int nfields, const char **names) {
   mxArray *a = (mxArray *)calloc(1, sizeof(mxArray));
   stub_struct *s = (stub_struct *)calloc(1, sizeof(stub_struct));
