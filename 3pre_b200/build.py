@@ -84,9 +84,11 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out)
     if failed:
         raise RuntimeError("libpre3 build failed")
-    link = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
+    tmp = LIB + ".tmp"  # link beside the target and swap: a snapshot taken mid-build never sees a half-written .so
+    link = [nvcc, "-shared", "-o", tmp, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
             "-Xcompiler", "-fPIC", "-cudart", "static", "-lpthread"]
     subprocess.run(link, check=True)
+    os.replace(tmp, LIB)
     return LIB
 
 

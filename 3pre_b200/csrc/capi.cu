@@ -110,7 +110,7 @@ int ransac_impl(pre3_ctx* ctx, const double* dYa, const double* dYb, const int32
     if (dstates) return fail(ctx, PRE3_ERR_ARG, "per-hypothesis states are not reported by the dr_ye variant");
     return launch_dr_ye(ctx, b, o, dmatch, dres, dmasks, dstat, dcounts);
   }
-  PRE3_TRY(ensure_adaptive_table(ctx, o, Nmax));
+  PRE3_TRY(ensure_adaptive_table(ctx, o, Nmax, dn_corr, P, &b.tab));
   PRE3_TRY(launch_prep(ctx, b, o, 0));
   PRE3_TRY(launch_eval_waves(ctx, b, o));
   PRE3_TRY(launch_select(ctx, b, o, dres, dmasks, dcounts, dstates));
@@ -173,7 +173,9 @@ void pre3_destroy(pre3_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->ws) cudaFree(ctx->ws);
+    for (char* r : ctx->retired) cudaFree(r);
     if (ctx->d_tab) cudaFree(ctx->d_tab);
+    if (ctx->d_tab_rows) cudaFree(ctx->d_tab_rows);
     if (ctx->d_ekf_tab) cudaFree(ctx->d_ekf_tab);
     for (int i = 0; i < 2; ++i) {
       if (ctx->h_stage[i]) cudaFreeHost(ctx->h_stage[i]);

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <string>
 #include <vector>
@@ -44,7 +45,9 @@ struct pre3_ctx {
   std::vector<char*> retired;  // blocks replaced while a call was being assembled
   // cached adaptive-iteration tables, keyed by (k, mult, Nmax, max_iteration)
   int tab_k = -1, tab_mult = -1, tab_nmax = -1, tab_maxit = -1;
-  int32_t* d_tab = nullptr;       // triangular: row N starts at N*(N+1)/2, entries c = 0..N
+  int32_t* d_tab = nullptr;       // triangular: row N starts at N*(N+1)/2, entries c = 0..N (Nmax <= 2048)
+  int32_t* d_tab_rows = nullptr;  // per-call rows + row offsets for larger Nmax
+  size_t tab_rows_cap = 0;
   // cached n_hyp table of the EKF path: (F+1) x (F+1) doubles, row num_ic, column support
   double* d_ekf_tab = nullptr;
   int ekf_tab_F = -1;
@@ -99,6 +102,11 @@ inline int fail(pre3_ctx* ctx, int code, const std::string& msg) {
 // requested through ws_reserve() first (so that the block never moves mid-call).
 inline int ws_reserve(pre3_ctx* ctx, size_t bytes) {
   ctx->ws_off = 0;
+  if (!ctx->retired.empty()) {  // spill blocks of the previous call (ws_take)
+    cudaStreamSynchronize(ctx->stream);
+    for (char* r : ctx->retired) cudaFree(r);
+    ctx->retired.clear();
+  }
   if (bytes <= ctx->ws_cap) return PRE3_OK;
   size_t cap = ctx->ws_cap ? ctx->ws_cap : (size_t)1 << 20;
   while (cap < bytes) cap *= 2;
@@ -147,10 +155,25 @@ inline int ensure_copy_stream(pre3_ctx* ctx) {
   return PRE3_OK;
 }
 
+// Bump allocation.  The arena is sized by the *_workspace_bytes estimates; a request that does not fit (an estimate
+// that drifted from the sequence of takes) is served from a block of its own instead of running past the arena --
+// freed at the next ws_reserve -- and reported under PRE3_DEBUG.
 template <typename T>
 inline T* ws_take(pre3_ctx* ctx, size_t count) {
-  size_t off = align_up(ctx->ws_off);
-  ctx->ws_off = off + count * sizeof(T);
+  const size_t off = align_up(ctx->ws_off);
+  const size_t bytes = count * sizeof(T);
+  if (off + bytes > ctx->ws_cap || !ctx->ws) {
+    char* blk = nullptr;
+    if (cudaMalloc((void**)&blk, bytes ? align_up(bytes, 1024) : 1024) != cudaSuccess) {
+      cudaGetLastError();
+      ctx->err = "workspace overflow and cudaMalloc of the spill block failed";
+      return nullptr;
+    }
+    ctx->retired.push_back(blk);
+    if (getenv("PRE3_DEBUG")) fprintf(stderr, "[pre3] workspace estimate short by %zu bytes (served separately)\n", off + bytes - ctx->ws_cap);
+    return reinterpret_cast<T*>(blk);
+  }
+  ctx->ws_off = off + bytes;
   return reinterpret_cast<T*>(ctx->ws + off);
 }
 

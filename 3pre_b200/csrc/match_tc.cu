@@ -8,12 +8,17 @@
 //                  so that one TMA bulk copy (cp.async.bulk) lands a ready operand tile; plus
 //                  |x|^2 per descriptor (fp64 -> fp32), the pair's max |b| and a "values do not
 //                  fit fp16" flag.  HBM-bound.
-//   k_tc_gemm_top2 persistent, warp-specialised: TMA producer warp, single-thread tcgen05.mma
-//                  issuer (M128 x N128 x K16, kind::f16, fp32 accumulators in TMEM, four 128-column
-//                  accumulator slots = two row blocks x two pipeline sets), two epilogue warpgroups
-//                  that pull accumulators with tcgen05.ld and keep a running (argmin, second
-//                  smallest) of  |b|^2 - 2 a.b  per L1 row.  The distance matrix never exists
-//                  in memory.
+//   k_tc_gemm_pair persistent CTA PAIRS (2-CTA clusters, one per SM pair), warp-specialised: TMA producer
+//                  warp, single-thread tcgen05.mma.cta_group::2 issuer in the leader CTA (M256 x N256 x K16,
+//                  kind::f16: each CTA holds its own 128 rows of A and HALF of the B tile, so the operand
+//                  stream per SM halves; fp32 accumulators in TMEM, two 256-column stages), two epilogue
+//                  warpgroups per CTA that pull accumulators with tcgen05.ld and keep a running
+//                  (argmax, second largest) of  a.b - |b|^2/2  per L1 row.  The column norm rides in the
+//                  contraction itself as a ninth K = 16 step (four fp16 slots holding an exact split of
+//                  -|b|^2/2 against a constant A tile), so the epilogue is pure selection: 3.5 instructions
+//                  per accumulator.  The distance matrix never exists in memory.
+//   k_tc_gemm_top2 the round-1 kernel (cta_group::1, M128 x N128, norms added in the epilogue); kept
+//                  as PRE3_TC_V1=1 for A/B timing.
 //   k_tc_rescore   the proposal only PROPOSES: the candidate's distance is recomputed exactly in
 //                  the reference's arithmetic (sequential `acc += delta*delta` in the class's
 //                  accumulation type, siftmatch.c:101-107), the runner-up is bracketed with a
@@ -43,9 +48,31 @@ constexpr int THREADS = 352;                  // 11 warps: 0-3 / 4-7 epilogue, 8
 // epilogue warps they share a sub-partition with.
 constexpr int W_EPI0 = 0, W_TMA = 8, W_MMA = 9, W_ALLOC = 10;
 constexpr int SMEM_BYTES = 2 * A_BUF_BYTES + NSTAGE * BLK_BYTES + 256 /*barriers*/ + 4 * BLK * 4 /*norms*/;
+// ---- CTA-pair kernel ----
+constexpr int EXT_BYTES = BLK * 32;           // 4 KB: the ninth K step, [row 128][16 halves], 32-byte swizzle
+constexpr int P2_NSTAGE = 4;                  // B ring: (32 KB main + 4 KB ext) per stage and CTA
+constexpr int P2_STAGE_BYTES = BLK_BYTES + EXT_BYTES;
+constexpr int P2_TILE_N = 256;                // columns per B tile (128 per CTA)
+constexpr int P2_OFF_A = 0;                                   // 2 x 32 KB
+constexpr int P2_OFF_AX = 2 * BLK_BYTES;                      // constant A extension tile
+constexpr int P2_OFF_B = P2_OFF_AX + EXT_BYTES;
+constexpr int P2_OFF_BAR = P2_OFF_B + P2_NSTAGE * P2_STAGE_BYTES;
+constexpr int P2_OFF_MERGE = P2_OFF_BAR + 512;
+constexpr int P2_SMEM_BYTES = P2_OFF_MERGE + BLK * 16;
+static_assert(P2_SMEM_BYTES <= 227 * 1024, "CTA-pair matcher: shared memory");
+// exact split of g = -|b|^2/2 over four fp16 slots:  g = 4096 h1 + 4096 h2 + h3 + h4  (A side: 4096, 4096, 1, 1)
+constexpr float EXT_SCALE = 4096.0f;
+constexpr double NORM_MAX = 2.0e8;            // |x|^2 above this does not fit the split -> pair flagged bad (exact kernel)
 
 // The epilogue orders  v'(j) = |b_j|^2 + C - 2 a~.b~_j  (C = 1.0625 max_i |a_i|^2 of the pair keeps v' > 0, so
 // float bits order like unsigned integers); the low 7 bits of the key carry the column within the tile.
+// byte offset of 16-byte chunk `chunk` (0: halves 0-7, 1: halves 8-15) of row r inside a 128-row K-extension tile.
+//   layout 0  SWIZZLE_32B: 32-byte rows, the two chunks XOR-swizzled with bit 2 of the row (address bit 7)
+//   layout 1  no swizzle ("interleaved"): 8 x 16-byte core matrices, [row group][chunk][row & 7]
+__host__ __device__ __forceinline__ int ext_off(int layout, int r, int chunk) {
+  return layout == 0 ? r * 32 + ((chunk ^ ((r >> 2) & 1)) << 4) : (r >> 3) * 256 + chunk * 128 + (r & 7) * 16;
+}
+
 struct Prop {      // per L1 row, output of the proposal GEMM
   float best;      // smallest v' (low 7 mantissa bits truncated)
   float second;    // second smallest v' (+inf if < 2 columns)
@@ -73,8 +100,11 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// a wait that lasts seconds is a pipeline-protocol bug: trap instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done;
+  long long t0 = 0;
+  uint32_t polls = 0;
   do {
     asm volatile(
         "{\n"
@@ -85,6 +115,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "=r"(done)
         : "r"(bar), "r"(parity)
         : "memory");
+    if (!done && (++polls & 1023u) == 0u) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 8000000000LL) __trap();
+    }
   } while (!done);
 }
 // TMA bulk copy global -> shared, completion counted in bytes on an mbarrier
@@ -186,7 +221,7 @@ struct FrameInfo {       // per converted descriptor set ("frame")
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_tc_convert(const T* __restrict__ L, int K, int Kp, const int32_t* __restrict__ kc, unsigned char* __restrict__ img,
-             float* __restrict__ nrm, FrameInfo* __restrict__ finfo) {
+             unsigned char* __restrict__ ext, int ext_layout, float* __restrict__ nrm, FrameInfo* __restrict__ finfo) {
   __shared__ float s_max[8];
   __shared__ int s_bad[8];
   const int p = blockIdx.y;
@@ -222,7 +257,32 @@ k_tc_convert(const T* __restrict__ L, int K, int Kp, const int32_t* __restrict__
     for (int e = 0; e < 4; ++e) bad = bad || !(fabs(v[i][e]) <= 60000.0);
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
-    bad = __any_sync(0xffffffffu, bad);
+    bad = __any_sync(0xffffffffu, bad) || !(sq <= NORM_MAX);
+    if (ext && lane == 0) {
+      // ninth K step of the CTA-pair GEMM: g = -|x|^2/2 = 4096 h1 + 4096 h2 + h3 + h4 (exact in fp64 down to the fp16
+      // denormal floor 2^-25); padded rows get a value no real column can reach.  16 halves per row (ext_off).
+      __half h[4];
+      if (row < n && !bad) {
+        double g = -0.5 * sq;
+        h[0] = __double2half(g * (1.0 / 4096.0));
+        g = g - 4096.0 * (double)__half2float(h[0]);
+        h[1] = __double2half(g * (1.0 / 4096.0));
+        g = g - 4096.0 * (double)__half2float(h[1]);
+        h[2] = __double2half(g);
+        g = g - (double)__half2float(h[2]);
+        h[3] = __double2half(g);
+      } else {
+        h[0] = __float2half(-60000.0f);
+        h[1] = h[2] = h[3] = __float2half(0.0f);
+      }
+      uint4 w;
+      w.x = (unsigned)__half_as_ushort(h[0]) | ((unsigned)__half_as_ushort(h[1]) << 16);
+      w.y = (unsigned)__half_as_ushort(h[2]) | ((unsigned)__half_as_ushort(h[3]) << 16);
+      w.z = w.w = 0u;
+      unsigned char* e0 = ext + ((size_t)p * Kp + (size_t)(row & ~127)) * 32;  // the row's 4 KB tile
+      *reinterpret_cast<uint4*>(e0 + ext_off(ext_layout, row & 127, 0)) = w;
+      *reinterpret_cast<uint4*>(e0 + ext_off(ext_layout, row & 127, 1)) = make_uint4(0u, 0u, 0u, 0u);
+    }
     float f = __double2float_ru(sq);
     if (row < n) {
       wmax = fmaxf(wmax, f);
@@ -472,6 +532,320 @@ k_tc_gemm_top2(const unsigned char* __restrict__ imgA, const unsigned char* __re
 }
 
 // ---------------------------------------------------------------------------------------------
+// k_tc_gemm_pair: the CTA-pair form (cta_group::2).  Cluster = 2 CTAs on one SM pair; unit of work = (pair p,
+// 256-row group g of L1): CTA r of the cluster owns row block 2g + r.  Per B tile of 256 columns CTA r loads the
+// 128 columns 256 j + 128 r (+ their K-extension tile); the leader issues nine M256 x N256 x K16 MMAs that read A and
+// B from BOTH CTAs' shared memory and write a 128 x 256 fp32 accumulator into EACH CTA's tensor memory.
+//   barriers (per CTA unless noted):
+//     a_full / b_full    TMA bytes of this CTA landed (expect_tx)
+//     pa_full / pb_full  LEADER only: the peer's relay thread saw the peer's a_full / b_full (remote arrive)
+//     a_empty / b_empty  tcgen05.commit multicast to both CTAs: the MMAs reading the buffer have completed
+//     t_full             tcgen05.commit multicast: accumulator stage ready in both CTAs' tensor memory
+//     t_empty            LEADER only: 16 warp arrivals (8 local, 8 remote): both CTAs drained the stage
+// ---------------------------------------------------------------------------------------------
+struct PairBarriers {
+  uint64_t a_full[2], a_empty[2], pa_full[2];
+  uint64_t b_full[P2_NSTAGE], b_empty[P2_NSTAGE], pb_full[P2_NSTAGE];
+  uint64_t t_full[2], t_empty[2];
+  uint32_t tmem_base;
+};
+static_assert(sizeof(PairBarriers) <= 512, "PairBarriers");
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// wait with cluster-scope acquire (the phase may have been completed by a thread of the peer CTA); a wait that
+// lasts seconds is a protocol bug: trap instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait_cl(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  long long t0 = 0;
+  uint32_t polls = 0;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!done && (++polls & 1023u) == 0u) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 8000000000LL) __trap();
+    }
+  } while (!done);
+}
+__device__ __forceinline__ void tc_commit_mc2(uint32_t bar) {  // arrives on `bar` in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major K = 16 operand tile of the ninth step.  layout 0: SWIZZLE_32B (32-byte rows, 8-row groups 256 B apart);
+// layout 1: no swizzle, core matrices 128 B apart along K (LBO) and 256 B apart along the rows (SBO)
+__device__ __forceinline__ uint64_t umma_desc_ext(uint32_t saddr, int layout) {
+  const uint64_t common = (uint64_t)((saddr >> 4) & 0x3FFFu) | (16ull << 32) | (1ull << 46);
+  return layout == 0 ? (common | (1ull << 16) | (6ull << 61)) : (common | (8ull << 16));
+}
+// kind::f16, A = B = F16, D = F32, both K-major, M = 256 (pair), N = 256
+constexpr uint32_t IDESC_PAIR = (1u << 4) | ((uint32_t)(P2_TILE_N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+
+struct Prop2 {     // per L1 row: s(j) = a~.b~_j - |b_j|^2/2  (d2(j) = |a|^2 - 2 s(j)); larger = closer
+  float best;      // largest s (low 7 mantissa bits replaced)
+  float second;    // second largest s (-inf if < 2 columns)
+  int32_t idx;     // argmax column (-1 if none)
+};
+
+// EXP: 0 product; 1 TMA + MMA only (accumulators released unread); 2 TMA + epilogue only (no MMA issued)
+template <int EXP>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+k_tc_gemm_pair(const unsigned char* __restrict__ imgA, const unsigned char* __restrict__ imgB,
+               const unsigned char* __restrict__ extB, int ext_layout, int P, int K1p, int K2p,
+               Prop2* __restrict__ prop) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const uint32_t base = smem_u32(smem);
+  if (base & 1023u) __trap();
+  const uint32_t sA = base + P2_OFF_A, sAX = base + P2_OFF_AX, sB = base + P2_OFF_B;
+  PairBarriers* bars = reinterpret_cast<PairBarriers*>(smem + P2_OFF_BAR);
+  float4* merge = reinterpret_cast<float4*>(smem + P2_OFF_MERGE);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+  const int nblk = K1p / BLK;               // K1p, K2p are multiples of 256
+  const int groups = nblk / 2;
+  const int ntile = K2p / P2_TILE_N;
+  const long long nunits = (long long)P * groups;
+
+  if (warp == W_MMA && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&bars->a_full[i]), 1);
+      mbar_init(smem_u32(&bars->a_empty[i]), 1);
+      mbar_init(smem_u32(&bars->pa_full[i]), 1);
+      mbar_init(smem_u32(&bars->t_full[i]), 1);
+      mbar_init(smem_u32(&bars->t_empty[i]), 16);
+    }
+    for (int i = 0; i < P2_NSTAGE; ++i) {
+      mbar_init(smem_u32(&bars->b_full[i]), 1);
+      mbar_init(smem_u32(&bars->b_empty[i]), 1);
+      mbar_init(smem_u32(&bars->pb_full[i]), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == W_ALLOC) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&bars->tmem_base))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  // constant A tile of the ninth K step: every row = (4096, 4096, 1, 1, 0 ...)
+  for (int r = threadIdx.x; r < BLK; r += THREADS) {
+    const __half one = __float2half(1.0f), sc = __float2half(EXT_SCALE);
+    uint4 w;
+    w.x = (unsigned)__half_as_ushort(sc) | ((unsigned)__half_as_ushort(sc) << 16);
+    w.y = (unsigned)__half_as_ushort(one) | ((unsigned)__half_as_ushort(one) << 16);
+    w.z = w.w = 0u;
+    *reinterpret_cast<uint4*>(smem + P2_OFF_AX + ext_off(ext_layout, r, 0)) = w;
+    *reinterpret_cast<uint4*>(smem + P2_OFF_AX + ext_off(ext_layout, r, 1)) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+
+  if (warp == W_TMA) {
+    // ===== TMA producer (each CTA loads its own operand halves) ====================================
+    if (lane == 0) {
+      long long t = 0;
+      int uc = 0;
+      for (long long u = cluster_id; u < nunits; u += nclusters, ++uc) {
+        const int p = (int)(u / groups), g = (int)(u % groups);
+        const int ab = uc & 1;
+        mbar_wait(smem_u32(&bars->a_empty[ab]), ((uc >> 1) & 1) ^ 1);
+        mbar_expect_tx(smem_u32(&bars->a_full[ab]), (uint32_t)BLK_BYTES);
+        tma_bulk_g2s(sA + ab * BLK_BYTES, imgA + ((size_t)p * K1p + (size_t)(2 * g + rank) * BLK) * (ND * 2),
+                     (uint32_t)BLK_BYTES, smem_u32(&bars->a_full[ab]));
+        for (int j = 0; j < ntile; ++j, ++t) {
+          const int st = (int)(t % P2_NSTAGE);
+          mbar_wait(smem_u32(&bars->b_empty[st]), (uint32_t)(((t / P2_NSTAGE) & 1) ^ 1));
+          mbar_expect_tx(smem_u32(&bars->b_full[st]), (uint32_t)P2_STAGE_BYTES);
+          const size_t brow = (size_t)p * K2p + (size_t)j * P2_TILE_N + (size_t)rank * BLK;
+          tma_bulk_g2s(sB + st * P2_STAGE_BYTES, imgB + brow * (ND * 2), BLK_BYTES, smem_u32(&bars->b_full[st]));
+          tma_bulk_g2s(sB + st * P2_STAGE_BYTES + BLK_BYTES, extB + brow * 32, EXT_BYTES, smem_u32(&bars->b_full[st]));
+        }
+      }
+      // tail: the multicast commits that release the last buffers target THIS CTA's barriers too; stay until they
+      // have arrived (a commit must never land in the shared memory of a CTA that has exited)
+      for (int i = 0; i < P2_NSTAGE; ++i, ++t)
+        mbar_wait(smem_u32(&bars->b_empty[t % P2_NSTAGE]), (uint32_t)(((t / P2_NSTAGE) & 1) ^ 1));
+      for (int i = 0; i < 2; ++i, ++uc) mbar_wait(smem_u32(&bars->a_empty[uc & 1]), ((uc >> 1) & 1) ^ 1);
+    }
+  } else if (warp == W_MMA) {
+    if (lane == 0) {
+      long long t = 0;
+      int uc = 0;
+      if (leader) {
+        // ===== MMA issuer (one thread of the leader CTA, for both SMs) ===============================
+        uint32_t use0 = 0, use1 = 0;
+        for (long long u = cluster_id; u < nunits; u += nclusters, ++uc) {
+          const int ab = uc & 1;
+          mbar_wait(smem_u32(&bars->a_full[ab]), (uc >> 1) & 1);
+          mbar_wait_cl(smem_u32(&bars->pa_full[ab]), (uc >> 1) & 1);
+          for (int j = 0; j < ntile; ++j, ++t) {
+            const int st = (int)(t % P2_NSTAGE);
+            const int acc = (int)(t & 1);
+            const uint32_t ph = (uint32_t)((t / P2_NSTAGE) & 1);
+            mbar_wait(smem_u32(&bars->b_full[st]), ph);
+            mbar_wait_cl(smem_u32(&bars->pb_full[st]), ph);
+            uint32_t& use = acc == 0 ? use0 : use1;
+            mbar_wait_cl(smem_u32(&bars->t_empty[acc]), (use & 1) ^ 1);
+            ++use;
+            tc_fence_after();
+            const uint32_t d = tmem + (uint32_t)(acc * P2_TILE_N);
+            if (EXP != 2) {
+#pragma unroll
+              for (int k = 0; k < ND / 16; ++k) {
+                const uint32_t koff = (uint32_t)((k >> 2) * HALF_BYTES + (k & 3) * 32);
+                tc_mma_f16_2cta(d, umma_desc(sA + ab * BLK_BYTES + koff), umma_desc(sB + st * P2_STAGE_BYTES + koff),
+                                IDESC_PAIR, k > 0 ? 1u : 0u);
+              }
+              tc_mma_f16_2cta(d, umma_desc_ext(sAX, ext_layout), umma_desc_ext(sB + st * P2_STAGE_BYTES + BLK_BYTES, ext_layout),
+                              IDESC_PAIR, 1u);
+            }
+            tc_commit_mc2(smem_u32(&bars->b_empty[st]));
+            tc_commit_mc2(smem_u32(&bars->t_full[acc]));
+          }
+          tc_commit_mc2(smem_u32(&bars->a_empty[ab]));
+        }
+      } else {
+        // ===== relay (peer CTA): tells the leader's issuer that this CTA's operand bytes have landed ==
+        for (long long u = cluster_id; u < nunits; u += nclusters, ++uc) {
+          const int ab = uc & 1;
+          mbar_wait(smem_u32(&bars->a_full[ab]), (uc >> 1) & 1);
+          mbar_arrive_cluster(mapa_u32(smem_u32(&bars->pa_full[ab]), 0));
+          for (int j = 0; j < ntile; ++j, ++t) {
+            const int st = (int)(t % P2_NSTAGE);
+            mbar_wait(smem_u32(&bars->b_full[st]), (uint32_t)((t / P2_NSTAGE) & 1));
+            mbar_arrive_cluster(mapa_u32(smem_u32(&bars->pb_full[st]), 0));
+          }
+        }
+      }
+    }
+  } else if (warp < W_TMA) {
+    // ===== epilogue: warpgroup wg takes columns [128 wg, 128 wg + 128) of every tile =================
+    const int wg = (warp - W_EPI0) >> 2;
+    const int q = warp & 3;
+    const uint32_t t_empty_leader0 = mapa_u32(smem_u32(&bars->t_empty[0]), 0);
+    const uint32_t t_empty_leader1 = mapa_u32(smem_u32(&bars->t_empty[1]), 0);
+    long long t = 0;
+    uint32_t useA = 0, useB = 0;
+    uint32_t keymask;
+    asm volatile("mov.u32 %0, 0xFFFFFF80;" : "=r"(keymask));
+    for (long long u = cluster_id; u < nunits; u += nclusters) {
+      const int p = (int)(u / groups), g = (int)(u % groups);
+      float m1 = -INFINITY, m2 = -INFINITY;
+      int btile = -1;
+      for (int j = 0; j < ntile; ++j, ++t) {
+        const int acc = (int)(t & 1);
+        uint32_t& use = acc == 0 ? useA : useB;
+        mbar_wait(smem_u32(&bars->t_full[acc]), use & 1);
+        ++use;
+        tc_fence_after();
+        const float m1_in = m1;
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * P2_TILE_N + wg * BLK);
+        uint32_t buf[2][32];
+        if (EXP != 1) tc_ld_32x32(taddr, buf[0]);
+#pragma unroll
+        for (int c = 0; c < BLK / 32; ++c) {
+          if (EXP == 1) break;
+          tc_ld_wait(buf[c & 1]);
+          if (c + 1 < BLK / 32) tc_ld_32x32(taddr + (uint32_t)((c + 1) * 32), buf[(c + 1) & 1]);
+#pragma unroll
+          for (int i2 = 0; i2 < 16; ++i2) {
+            uint32_t k0, k1;  // (bits & ~127) | column within the half tile: one LOP3 each
+            asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(k0) : "r"(buf[c & 1][2 * i2]), "r"(keymask), "r"((uint32_t)(c * 32 + 2 * i2)));
+            asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(k1) : "r"(buf[c & 1][2 * i2 + 1]), "r"(keymask), "r"((uint32_t)(c * 32 + 2 * i2 + 1)));
+            const float f0 = __uint_as_float(k0), f1 = __uint_as_float(k1);
+            const float hi = fmaxf(f0, f1), lo = fminf(f0, f1);
+            m2 = fmaxf(fmaxf(m2, fminf(m1, hi)), lo);  // second largest of {m1, m2, f0, f1}
+            m1 = fmaxf(m1, hi);
+          }
+        }
+        if (m1 != m1_in) btile = j;
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (leader) mbar_arrive(smem_u32(&bars->t_empty[acc]));
+          else mbar_arrive_cluster(acc == 0 ? t_empty_leader0 : t_empty_leader1);
+        }
+      }
+      // merge the two column halves of this row block (warpgroup 1 -> warpgroup 0) and store the proposal
+      const int r = q * 32 + lane;
+      const int col = btile < 0 ? -1 : btile * P2_TILE_N + wg * BLK + (int)(__float_as_uint(m1) & 0x7Fu);
+      if (wg == 1) merge[r] = make_float4(m1, m2, __int_as_float(col), 0.f);
+      named_bar_sync(1, 256);
+      if (wg == 0) {
+        const float4 o = merge[r];
+        float b1 = m1, b2 = m2;
+        int bc = col;
+        const float o1 = o.x, o2 = o.y;
+        const int oc = __float_as_int(o.z);
+        // top-2 of the union; on equal keys the lower column (this half) stays first
+        if (oc >= 0 && (bc < 0 || o1 > b1)) {
+          b2 = fmaxf(b1, o2);
+          b1 = o1;
+          bc = oc;
+        } else {
+          b2 = fmaxf(b2, o1);
+        }
+        const int row = (2 * g + (int)rank) * BLK + r;
+        Prop2 out;
+        out.best = __uint_as_float(__float_as_uint(b1) & 0xFFFFFF80u);
+        out.second = __uint_as_float(__float_as_uint(b2) & 0xFFFFFF80u);
+        out.idx = bc;
+        prop[(size_t)p * K1p + row] = out;
+      }
+      named_bar_sync(2, 256);  // merge[] is rewritten by the next unit
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer's tensor / shared memory stay alive until the leader's MMAs have drained
+  if (warp == W_ALLOC) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // k_tc_rescore: exact candidate distance + certified ratio-test decision.  One warp handles 32
 // rows at a time: coalesced loads of the row and of its candidate column, delta*delta per
 // element into shared memory, then lane r sums row r strictly in bin order.
@@ -504,7 +878,7 @@ __device__ __forceinline__ void rescore_group(ACC (*sprod)[ND + 1], int p, int r
                                               const T* __restrict__ L1, const T* __restrict__ L2, int K1, int K2,
                                               int K1p, float thresh, const Prop* __restrict__ prop,
                                               const float* __restrict__ nrmA, const PairInfo& pi, int need_score,
-                                              MatchRow* __restrict__ rows, int32_t* __restrict__ row_list,
+                                              int v2, MatchRow* __restrict__ rows, int32_t* __restrict__ row_list,
                                               int32_t* __restrict__ row_list_n) {
   const int lane = threadIdx.x & 31;
   const int nr = min(RS_ROWS, n1 - row0);
@@ -532,10 +906,15 @@ __device__ __forceinline__ void rescore_group(ACC (*sprod)[ND + 1], int p, int r
     C = (double)(1.0625f * __uint_as_float(pi.amax_bits));
     const double ra = sqrt(na), rbm = sqrt(nbm);
     m = 1.25 * ((1.0 / 512 + 1.0 / 16384) * ra * rbm + (na + nbm + C) * (1.0 / 16384) + (ra + rbm) * (1.0 / 1048576));
-    if (pi.bad || my.idx < 0 || my.idx >= n2 || !(thresh > 0.f) || !(C - na > m) || !(my.best < INFINITY)) {
+    // CTA-pair proposal: d2~ = |a|^2 - 2 s with s = a~.b~ - |b|^2/2 accumulated in the contraction (the fp16 split of
+    // the norm is exact down to 2^-25 absolute, the 7 replaced key bits of s cost |s| 2^-16 <= (na + nbm) 2^-16)
+    if (v2) m = 1.25 * ((1.0 / 512 + 1.0 / 16384) * ra * rbm + (na + nbm) * (1.0 / 16384) + (ra + rbm) * (1.0 / 1048576) + 1.0 / 4194304);
+    const bool keys_ok = v2 ? (my.best > -INFINITY) : ((C - na > m) && (my.best < INFINITY));
+    if (pi.bad || my.idx < 0 || my.idx >= n2 || !(thresh > 0.f) || !keys_ok) {
       ambiguous = true;  // keys may be meaningless (range, sign) -> exact kernel
     } else {
-      const double b1 = (double)my.best - C + na, s2 = (double)my.second - C + na;
+      const double b1 = v2 ? na - 2.0 * (double)my.best : (double)my.best - C + na;
+      const double s2 = v2 ? na - 2.0 * (double)my.second : (double)my.second - C + na;
       const double L1b = b1 - m;  // exact best  >= L1b
       const double U2b = s2 + m;  // exact second_best <= U2b
       if (L1b > 0.0 && __fmul_rn(thresh, (float)L1b) > (float)U2b) {
@@ -591,7 +970,7 @@ __device__ __forceinline__ void rescore_group(ACC (*sprod)[ND + 1], int p, int r
     ACC acc = 0;
     for (int bin = 0; bin < ND; ++bin) acc += sprod[lane][bin];  // strictly in order (siftmatch.c:101-107)
     const double d1 = (double)acc;
-    const double s2 = (double)my.second - C + na;
+    const double s2 = v2 ? na - 2.0 * (double)my.second : (double)my.second - C + na;
     const double L2b = s2 - m, U2b = s2 + m;  // every other column's exact distance is >= L2b; one is <= U2b
     if (d1 < L2b) {
       // unique exact minimum: best = d1, bestk = idx; second_best in [L2b, U2b]
@@ -626,7 +1005,7 @@ __global__ void __launch_bounds__(32)
 k_tc_rescore(const T* __restrict__ L1, const T* __restrict__ L2, int K1, int K2, int K1p, int K2p,
              const int32_t* __restrict__ k1c, const int32_t* __restrict__ k2c, float thresh,
              const Prop* __restrict__ prop, const float* __restrict__ nrmA, const PairInfo* __restrict__ info,
-             int need_score, MatchRow* __restrict__ rows, int32_t* __restrict__ row_list,
+             int need_score, int v2, MatchRow* __restrict__ rows, int32_t* __restrict__ row_list,
              int32_t* __restrict__ row_list_n) {
   __shared__ ACC sprod[RS_ROWS][ND + 1];
   const int p = blockIdx.y;
@@ -636,8 +1015,8 @@ k_tc_rescore(const T* __restrict__ L1, const T* __restrict__ L2, int K1, int K2,
   for (int grp = 0; grp < RS_GROUPS; ++grp) {
     const int row0 = (blockIdx.x * RS_GROUPS + grp) * RS_ROWS;
     if (row0 >= n1) return;
-    rescore_group<T, ACC>(sprod, p, row0, n1, n2, L1, L2, K1, K2, K1p, thresh, prop, nrmA, pi, need_score, rows, row_list,
-                          row_list_n);
+    rescore_group<T, ACC>(sprod, p, row0, n1, n2, L1, L2, K1, K2, K1p, thresh, prop, nrmA, pi, need_score, v2, rows,
+                          row_list, row_list_n);
     __syncwarp();  // sprod is reused by the next group
   }
 }
@@ -647,7 +1026,8 @@ k_tc_rescore(const T* __restrict__ L1, const T* __restrict__ L2, int K1, int K2,
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-static inline int pad128(int k) { return (k + 127) / 128 * 128; }
+// descriptor counts are padded to whole CTA-pair tiles (256 rows / columns)
+static inline int pad128(int k) { return (k + 255) / 256 * 256; }
 
 bool match_tc_supported(int cls, int K1, int K2, int ND) {
   return (cls == PRE3_CLASS_DOUBLE || cls == PRE3_CLASS_SINGLE || cls == PRE3_CLASS_DOUBLE_F32) && ND == tc::ND &&
@@ -660,6 +1040,7 @@ size_t match_tc_workspace_bytes(int P, int K1, int K2) {
   b += align_up((size_t)(P + 1) * K1p * tc::ND * 2, 1024) + 1024;
   b += align_up((size_t)P * K2p * tc::ND * 2, 1024) + 1024;
   b += align_up((size_t)(P + 1) * K1p * 4) + align_up((size_t)P * K2p * 4);
+  b += align_up((size_t)(P + 1) * K1p * 32, 1024) + align_up((size_t)P * K2p * 32, 1024) + 2048;  // K-extension tiles
   b += align_up((size_t)P * K1p * sizeof(tc::Prop));
   b += align_up((size_t)P * sizeof(tc::PairInfo)) + 2 * align_up((size_t)(P + 1) * sizeof(tc::FrameInfo));
   b += align_up((size_t)P * K1 * 4) + 256;
@@ -678,6 +1059,7 @@ int launch_match_tc(pre3_ctx* ctx, const void* dL1, const void* dL2, int cls, in
   const bool seq = dL2 == nullptr;
   if (seq && K1 != K2) return fail(ctx, PRE3_ERR_ARG, "sequence mode needs the same descriptor count per frame");
   const int FA = seq ? P + 1 : P;  // descriptor sets behind dL1
+  static const int ext_layout = getenv("PRE3_TC_EXTLAYOUT") ? atoi(getenv("PRE3_TC_EXTLAYOUT")) : 0;
   // carve (1024-byte aligned operand images: TMA bulk copies need 16, the smem tiles 1024)
   auto take1k = [&](size_t bytes) {
     ctx->ws_off = align_up(ctx->ws_off, 1024);
@@ -686,6 +1068,8 @@ int launch_match_tc(pre3_ctx* ctx, const void* dL1, const void* dL2, int cls, in
   const size_t set_bytes = (size_t)K1p * ND * 2;
   unsigned char* imgA = take1k((size_t)FA * set_bytes);
   unsigned char* imgB = seq ? imgA + set_bytes : take1k((size_t)P * K2p * ND * 2);
+  unsigned char* extA = take1k((size_t)FA * K1p * 32);
+  unsigned char* extB = seq ? extA + (size_t)K1p * 32 : take1k((size_t)P * K2p * 32);
   float* nrmA = ws_take<float>(ctx, (size_t)FA * K1p);
   float* nrmB = seq ? nrmA + K1p : ws_take<float>(ctx, (size_t)P * K2p);
   Prop* prop = ws_take<Prop>(ctx, (size_t)P * K1p);
@@ -705,20 +1089,44 @@ int launch_match_tc(pre3_ctx* ctx, const void* dL1, const void* dL2, int cls, in
     Span span__(ctx, T_CONVERT);
     const dim3 g1(K1p / CV_ROWS, FA), g2(K2p / CV_ROWS, P);
     if (cls == PRE3_CLASS_DOUBLE) {
-      k_tc_convert<double><<<g1, 256, 0, ctx->stream>>>((const double*)dL1, K1, K1p, dk1, imgA, nrmA, fa);
-      if (!seq) k_tc_convert<double><<<g2, 256, 0, ctx->stream>>>((const double*)dL2, K2, K2p, dk2, imgB, nrmB, fb);
+      k_tc_convert<double><<<g1, 256, 0, ctx->stream>>>((const double*)dL1, K1, K1p, dk1, imgA, extA, ext_layout, nrmA, fa);
+      if (!seq) k_tc_convert<double><<<g2, 256, 0, ctx->stream>>>((const double*)dL2, K2, K2p, dk2, imgB, extB, ext_layout, nrmB, fb);
     } else {
-      k_tc_convert<float><<<g1, 256, 0, ctx->stream>>>((const float*)dL1, K1, K1p, dk1, imgA, nrmA, fa);
-      if (!seq) k_tc_convert<float><<<g2, 256, 0, ctx->stream>>>((const float*)dL2, K2, K2p, dk2, imgB, nrmB, fb);
+      k_tc_convert<float><<<g1, 256, 0, ctx->stream>>>((const float*)dL1, K1, K1p, dk1, imgA, extA, ext_layout, nrmA, fa);
+      if (!seq) k_tc_convert<float><<<g2, 256, 0, ctx->stream>>>((const float*)dL2, K2, K2p, dk2, imgB, extB, ext_layout, nrmB, fb);
     }
     k_tc_pair_info<<<(P + 255) / 256, 256, 0, ctx->stream>>>(P, fa, fb, info);
     count_launch(ctx, seq ? 2 : 3);
   }
-  {
+  static const int use_v1 = getenv("PRE3_TC_V1") ? atoi(getenv("PRE3_TC_V1")) : 0;
+  static const int exp_mode = getenv("PRE3_TC_EXP") ? atoi(getenv("PRE3_TC_EXP")) : 0;
+  if (!use_v1) {
+    // CTA pairs: one 2-CTA cluster per SM pair, unit = (pair, 256-row group)
+    Span span__(ctx, T_MATCH_TC);
+    const long long units = (long long)P * (K1p / 256);
+    const int grid = 2 * (int)std::min<long long>(units, ctx->sm_count / 2);
+#define PRE3_GEMM2(E)                                                                                              \
+  do {                                                                                                             \
+    static bool attr_done = false;                                                                                 \
+    if (!attr_done) {                                                                                              \
+      PRE3_CUDA(cudaFuncSetAttribute(k_tc_gemm_pair<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES)); \
+      attr_done = true;                                                                                            \
+    }                                                                                                              \
+    k_tc_gemm_pair<E><<<grid, THREADS, P2_SMEM_BYTES, ctx->stream>>>(imgA, imgB, extB, ext_layout, P, K1p, K2p,    \
+                                                                     reinterpret_cast<Prop2*>(prop));              \
+  } while (0)
+    switch (exp_mode) {
+      case 0: PRE3_GEMM2(0); break;
+      case 1: PRE3_GEMM2(1); break;
+      case 2: PRE3_GEMM2(2); break;
+      default: return fail(ctx, PRE3_ERR_ARG, "PRE3_TC_EXP: ablation not built for the CTA-pair kernel");
+    }
+#undef PRE3_GEMM2
+    count_launch(ctx);
+  } else {
     Span span__(ctx, T_MATCH_TC);
     const long long units = (long long)P * ((K1p / BLK + 1) / 2);
     const int grid = (int)std::min<long long>(units, ctx->sm_count);
-    static const int exp_mode = getenv("PRE3_TC_EXP") ? atoi(getenv("PRE3_TC_EXP")) : 0;
 #define PRE3_GEMM(E)                                                                                             \
   do {                                                                                                           \
     static bool attr_done = false;                                                                               \
@@ -741,21 +1149,22 @@ int launch_match_tc(pre3_ctx* ctx, const void* dL1, const void* dL2, int cls, in
 #undef PRE3_GEMM
     count_launch(ctx);
   }
+  const int v2 = use_v1 ? 0 : 1;
   {
     Span span__(ctx, T_RESCORE);
     const dim3 g((K1 + RS_ROWS * RS_GROUPS - 1) / (RS_ROWS * RS_GROUPS), P);
     if (cls == PRE3_CLASS_DOUBLE)
       k_tc_rescore<double, double><<<g, 32, 0, ctx->stream>>>((const double*)dL1, (const double*)dL2, K1, K2,
                                                                           K1p, K2p, dk1, dk2, thresh, prop, nrmA, info,
-                                                                          need_score, drows, list, list_n);
+                                                                          need_score, v2, drows, list, list_n);
     else if (cls == PRE3_CLASS_DOUBLE_F32)
       k_tc_rescore<float, double><<<g, 32, 0, ctx->stream>>>((const float*)dL1, (const float*)dL2, K1, K2,
                                                                          K1p, K2p, dk1, dk2, thresh, prop, nrmA, info,
-                                                                         need_score, drows, list, list_n);
+                                                                         need_score, v2, drows, list, list_n);
     else
       k_tc_rescore<float, float><<<g, 32, 0, ctx->stream>>>((const float*)dL1, (const float*)dL2, K1, K2,
                                                                         K1p, K2p, dk1, dk2, thresh, prop, nrmA, info,
-                                                                        need_score, drows, list, list_n);
+                                                                        need_score, v2, drows, list, list_n);
     count_launch(ctx);
   }
   PRE3_CUDA(cudaGetLastError());

@@ -14,6 +14,7 @@
 
 #include <cmath>
 #include <cstdlib>
+#include <new>
 
 namespace pre3 {
 
@@ -69,8 +70,9 @@ __device__ __forceinline__ void sample_set(uint64_t seed, uint32_t pair, uint32_
 __global__ void __launch_bounds__(256) k_prep(const double* __restrict__ Ya, const double* __restrict__ Yb,
                                               const int32_t* __restrict__ n_corr, int Nmax, int method,
                                               double thr_opt, const double* __restrict__ thr_override,
-                                              int tab_triangular, PairMeta* __restrict__ meta,
-                                              float4* __restrict__ Ya4, float4* __restrict__ Yb4) {
+                                              int tab_triangular, const int32_t* __restrict__ rowoff,
+                                              PairMeta* __restrict__ meta, float4* __restrict__ Ya4,
+                                              float4* __restrict__ Yb4) {
   const int p = blockIdx.x;
   int N = n_corr ? n_corr[p] : Nmax;
   N = max(0, min(N, Nmax));
@@ -129,7 +131,7 @@ __global__ void __launch_bounds__(256) k_prep(const double* __restrict__ Ya, con
     m.y1max = s_y1[0];
     m.xmax = s_xm[0];
     m.N = N;
-    m.pad = tab_triangular ? (int32_t)(((long long)N * (N + 1)) / 2) : 0;
+    m.pad = tab_triangular ? (int32_t)(((long long)N * (N + 1)) / 2) : (rowoff ? rowoff[N] : 0);
     meta[p] = m;
   }
 }
@@ -1339,9 +1341,9 @@ __global__ void __launch_bounds__(256) k_threshold(const double* __restrict__ Yb
 //                1e-14 variant (:211), mean / std of the residual norms (:212-215), nIterationRansac (:216)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_dy_prep(const double* __restrict__ Ya, const double* __restrict__ Yb,
-                                                 const int32_t* __restrict__ n_corr, int Nmax,
-                                                 PairMeta* __restrict__ meta, float4* __restrict__ Ya4,
-                                                 float4* __restrict__ Yb4) {
+                                                 const int32_t* __restrict__ n_corr, int Nmax, int tab_triangular,
+                                                 const int32_t* __restrict__ rowoff, PairMeta* __restrict__ meta,
+                                                 float4* __restrict__ Ya4, float4* __restrict__ Yb4) {
   const int p = blockIdx.x;
   int N = n_corr ? n_corr[p] : Nmax;
   N = max(0, min(N, Nmax));
@@ -1413,7 +1415,7 @@ __global__ void __launch_bounds__(256) k_dy_prep(const double* __restrict__ Ya, 
     m.y1max = y1;
     m.xmax = xm;
     m.N = N;
-    m.pad = (int32_t)(((long long)N * (N + 1)) / 2);
+    m.pad = tab_triangular ? (int32_t)(((long long)N * (N + 1)) / 2) : (rowoff ? rowoff[N] : 0);
     meta[p] = m;
   }
 }
@@ -1640,51 +1642,132 @@ void ransac_carve(pre3_ctx* ctx, RansacBuffers& b, int H) {
   b.stop = ws_take<int32_t>(ctx, b.P);
 }
 
-int ensure_adaptive_table(pre3_ctx* ctx, const pre3_ransac_opts& o, int Nmax) {
-  if (!o.adaptive) return PRE3_OK;
-  const int mult = o.method == PRE3_METHOD_HORN ? 1 : 5;  // x5: RANSAC_CALC_VER2.m:139, vodometry_dr_ye.m:177
-  if (ctx->d_tab && ctx->tab_k == o.k && ctx->tab_mult == mult && ctx->tab_nmax >= Nmax &&
-      ctx->tab_maxit == o.max_iteration)
-    return PRE3_OK;
-  const size_t total = ((size_t)Nmax + 1) * ((size_t)Nmax + 2) / 2;
-  std::vector<int32_t> tab(total);
+// nIterations(card, N) = mult*ceil(log(epsilon)/log(1-(card/N)^k))  (RANSAC_CALC_VER2.m:139, RANSAC_CALC_VER_test.m:102),
+// clamped to [0, MaxIteration] (the loop takes the min, :86); computed on the HOST with the libm the CPU checker uses.
+static void adaptive_row(const pre3_ransac_opts& o, int mult, int N, int32_t* row) {
   const double le = std::log(0.01);
-  for (int N = 0; N <= Nmax; ++N) {
-    int32_t* row = tab.data() + (size_t)N * (N + 1) / 2;
-    for (int c = 0; c <= N; ++c) {
-      // nIterations = mult*ceil(log(epsilon)/log(1-(card/nPoints)^k))  (RANSAC_CALC_VER2.m:139,
-      // RANSAC_CALC_VER_test.m:102), clamped to [0, MaxIteration] (the loop takes the min, :86)
-      int32_t v = o.max_iteration;
-      if (N > 0 && c >= 1) {
-        const double w = (double)c / (double)N;
-        const double d = (double)mult * std::ceil(le / std::log(1.0 - std::pow(w, (double)o.k)));
-        if (d == d) {
-          if (d < (double)o.max_iteration) v = d <= 0.0 ? 0 : (int32_t)d;
+  for (int c = 0; c <= N; ++c) {
+    int32_t v = o.max_iteration;
+    if (N > 0 && c >= 1) {
+      const double w = (double)c / (double)N;
+      const double d = (double)mult * std::ceil(le / std::log(1.0 - std::pow(w, (double)o.k)));
+      if (d == d) {
+        if (d < (double)o.max_iteration) v = d <= 0.0 ? 0 : (int32_t)d;
+      }
+    }
+    row[c] = v;
+  }
+}
+
+constexpr int TAB_TRI_MAX = 2048;             // triangular table up to this Nmax: 2.1 M entries, 8.4 MB
+constexpr size_t TAB_ROWS_MAX = (size_t)1 << 26;  // entries of a per-call row set (256 MB) before the call is refused
+
+// Table layouts (only row N of a pair is ever read; PairMeta.pad = offset of that row):
+//   Nmax <= TAB_TRI_MAX  triangular over every N <= Nmax (row N at N(N+1)/2), cached in the context;
+//   larger               one row per DISTINCT N of the call -- n_corr == nullptr: the single row N = Nmax; otherwise the
+//                        P counts are read back and `rowoff[N]` maps a pair's N to its row.  (The triangular form needs
+//                        (Nmax+1)(Nmax+2)/2 entries: 200 M at the 20 000-correspondence stress shape.)
+int ensure_adaptive_table(pre3_ctx* ctx, const pre3_ransac_opts& o, int Nmax, const int32_t* dn_corr, int P,
+                          AdaptiveTable* out) {
+  out->tab = nullptr;
+  out->rowoff = nullptr;
+  out->triangular = 0;
+  if (!o.adaptive) return PRE3_OK;
+  if (Nmax < 0) return fail(ctx, PRE3_ERR_ARG, "negative correspondence count");
+  const int mult = o.method == PRE3_METHOD_HORN ? 1 : 5;  // x5: RANSAC_CALC_VER2.m:139, vodometry_dr_ye.m:177
+  try {
+    if (Nmax <= TAB_TRI_MAX) {
+      out->triangular = 1;
+      if (!(ctx->d_tab && ctx->tab_k == o.k && ctx->tab_mult == mult && ctx->tab_nmax >= Nmax &&
+            ctx->tab_nmax <= TAB_TRI_MAX && ctx->tab_maxit == o.max_iteration)) {
+        const size_t total = ((size_t)Nmax + 1) * ((size_t)Nmax + 2) / 2;
+        std::vector<int32_t> tab(total);
+        for (int N = 0; N <= Nmax; ++N) adaptive_row(o, mult, N, tab.data() + (size_t)N * (N + 1) / 2);
+        if (ctx->d_tab) {
+          cudaStreamSynchronize(ctx->stream);
+          cudaFree(ctx->d_tab);
+          ctx->d_tab = nullptr;
+        }
+        ctx->tab_nmax = -1;
+        if (cudaMalloc((void**)&ctx->d_tab, total * sizeof(int32_t)) != cudaSuccess) {
+          ctx->d_tab = nullptr;
+          cudaGetLastError();
+          return fail(ctx, PRE3_ERR_ALLOC, "cudaMalloc of the adaptive-iteration table failed");
+        }
+        PRE3_CUDA(cudaMemcpyAsync(ctx->d_tab, tab.data(), total * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+        PRE3_CUDA(cudaStreamSynchronize(ctx->stream));  // tab goes out of scope
+        ctx->tab_k = o.k;
+        ctx->tab_mult = mult;
+        ctx->tab_nmax = Nmax;
+        ctx->tab_maxit = o.max_iteration;
+      }
+      out->tab = ctx->d_tab;
+      return PRE3_OK;
+    }
+    // rows for the distinct N of this call
+    std::vector<int32_t> off((size_t)Nmax + 1, -1);
+    std::vector<int32_t> ns;
+    if (!dn_corr) {
+      ns.push_back(Nmax);
+    } else {
+      std::vector<int32_t> nc((size_t)std::max(P, 0));
+      if (P > 0) {
+        PRE3_CUDA(cudaMemcpyAsync(nc.data(), dn_corr, sizeof(int32_t) * (size_t)P, cudaMemcpyDeviceToHost, ctx->stream));
+        PRE3_CUDA(cudaStreamSynchronize(ctx->stream));
+      }
+      std::vector<char> seen((size_t)Nmax + 1, 0);
+      for (int p = 0; p < P; ++p) {
+        const int N = std::max(0, std::min(nc[p], Nmax));
+        if (!seen[N]) {
+          seen[N] = 1;
+          ns.push_back(N);
         }
       }
-      row[c] = v;
     }
+    size_t total = 0;
+    for (int N : ns) {
+      if (total + (size_t)N + 1 > TAB_ROWS_MAX)
+        return fail(ctx, PRE3_ERR_ARG, "adaptive stop: too many distinct large correspondence counts in one call "
+                                       "(limit 2^26 table entries); split the batch or pass adaptive = 0");
+      off[N] = (int32_t)total;
+      total += (size_t)N + 1;
+    }
+    std::vector<int32_t> tab(std::max<size_t>(total, 1));
+    for (int N : ns) adaptive_row(o, mult, N, tab.data() + off[N]);
+    const size_t need = (tab.size() + off.size()) * sizeof(int32_t);
+    if (need > ctx->tab_rows_cap) {
+      if (ctx->d_tab_rows) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(ctx->d_tab_rows);
+        ctx->d_tab_rows = nullptr;
+        ctx->tab_rows_cap = 0;
+      }
+      if (cudaMalloc((void**)&ctx->d_tab_rows, need) != cudaSuccess) {
+        ctx->d_tab_rows = nullptr;
+        cudaGetLastError();
+        return fail(ctx, PRE3_ERR_ALLOC, "cudaMalloc of the adaptive-iteration rows failed");
+      }
+      ctx->tab_rows_cap = need;
+    }
+    int32_t* d_rows = ctx->d_tab_rows;
+    int32_t* d_off = d_rows + tab.size();
+    PRE3_CUDA(cudaMemcpyAsync(d_rows, tab.data(), tab.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    PRE3_CUDA(cudaMemcpyAsync(d_off, off.data(), off.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    PRE3_CUDA(cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
+    out->tab = d_rows;
+    out->rowoff = d_off;
+    return PRE3_OK;
+  } catch (const std::bad_alloc&) {
+    return fail(ctx, PRE3_ERR_ALLOC, "host allocation of the adaptive-iteration table failed");
   }
-  if (ctx->d_tab) {
-    cudaStreamSynchronize(ctx->stream);
-    cudaFree(ctx->d_tab);
-    ctx->d_tab = nullptr;
-  }
-  PRE3_CUDA(cudaMalloc((void**)&ctx->d_tab, total * sizeof(int32_t)));
-  PRE3_CUDA(cudaMemcpyAsync(ctx->d_tab, tab.data(), total * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
-  PRE3_CUDA(cudaStreamSynchronize(ctx->stream));  // tab goes out of scope
-  ctx->tab_k = o.k;
-  ctx->tab_mult = mult;
-  ctx->tab_nmax = Nmax;
-  ctx->tab_maxit = o.max_iteration;
-  return PRE3_OK;
 }
 
 int launch_prep(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts& o, int thr_given) {
   Span span__(ctx, T_PREP);
   if (b.P <= 0) return PRE3_OK;
   k_prep<<<b.P, 256, 0, ctx->stream>>>(b.Ya, b.Yb, b.n_corr, b.Nmax, thr_given ? PRE3_METHOD_HORN : o.method,
-                                       o.distance_threshold, nullptr, 1, b.meta, b.Ya4, b.Yb4);
+                                       o.distance_threshold, nullptr, b.tab.triangular, b.tab.rowoff, b.meta, b.Ya4,
+                                       b.Yb4);
   count_launch(ctx);
   PRE3_CUDA(cudaGetLastError());
   return PRE3_OK;
@@ -1774,7 +1857,7 @@ int launch_eval_waves(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_o
     if (end < H) {
       Span span__(ctx, T_SELECT);
       k_stop<<<(b.P + 7) / 8, 256, 0, ctx->stream>>>(b.meta, b.counts, b.states, b.P, H, end, o.method,
-                                                     o.max_iteration, ctx->d_tab, b.stop);
+                                                     o.max_iteration, b.tab.tab, b.stop);
       count_launch(ctx);
       PRE3_CUDA(cudaGetLastError());
     }
@@ -1796,7 +1879,7 @@ int launch_select(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts&
   int* tie_total = ws_take<int>(ctx, 64);
   if (PH >= ((size_t)1 << 31)) return fail(ctx, PRE3_ERR_ARG, "pairs x sample sets must stay below 2^31");
   PRE3_CUDA(cudaMemsetAsync(tie_total, 0, sizeof(int), ctx->stream));
-  const int32_t* tab = o.adaptive ? ctx->d_tab : nullptr;
+  const int32_t* tab = o.adaptive ? b.tab.tab : nullptr;
   const bool many = b.P >= 64;  // batches of pairs: one warp per pair; few (large) pairs: 1024 threads each
   if (many)
     k_sel_scan<32><<<b.P, 32, 0, ctx->stream>>>(b.meta, b.Nmax, o.H, o.k, o.method, o.max_iteration, o.adaptive, tab,
@@ -1843,10 +1926,11 @@ int launch_dr_ye(pre3_ctx* ctx, RansacBuffers& b, const pre3_ransac_opts& o, con
   int32_t* gen = ws_take<int32_t>(ctx, 4 * PH);
   pre3_ransac_opts oa = o;
   oa.adaptive = 1;
-  PRE3_TRY(ensure_adaptive_table(ctx, oa, b.Nmax));
+  PRE3_TRY(ensure_adaptive_table(ctx, oa, b.Nmax, b.n_corr, b.P, &b.tab));
   {
     Span span__(ctx, T_PREP);
-    k_dy_prep<<<b.P, 256, 0, ctx->stream>>>(b.Ya, b.Yb, b.n_corr, b.Nmax, b.meta, b.Ya4, b.Yb4);
+    k_dy_prep<<<b.P, 256, 0, ctx->stream>>>(b.Ya, b.Yb, b.n_corr, b.Nmax, b.tab.triangular, b.tab.rowoff, b.meta, b.Ya4,
+                                            b.Yb4);
     count_launch(ctx);
     if (!b.samples && H > 0) {
       k_dy_sample<<<dim3((H + 255) / 256, b.P), 256, 0, ctx->stream>>>(b.meta, dmatch, b.Nmax, o.seed, b.pair_id0, H,
@@ -1862,7 +1946,7 @@ int launch_dr_ye(pre3_ctx* ctx, RansacBuffers& b, const pre3_ransac_opts& o, con
   {
     Span span__(ctx, T_SELECT);
     k_dy_select<<<b.P, SEL_THREADS, 0, ctx->stream>>>(b.meta, b.Ya, b.Yb, b.Nmax, b.samples, H, o.max_iteration,
-                                                      ctx->d_tab, b.counts, dres, dmasks, scratch, dstat,
+                                                      b.tab.tab, b.counts, dres, dmasks, scratch, dstat,
                                                       dcounts_out);
     count_launch(ctx);
     PRE3_CUDA(cudaGetLastError());
@@ -1902,7 +1986,7 @@ int launch_score_given(pre3_ctx* ctx, const double* dR, const double* dT, int H,
   o.method = PRE3_METHOD_HORN;  // threshold taken as given
   o.distance_threshold = thr;
   o.k = 5;
-  k_prep<<<1, 256, 0, ctx->stream>>>(b.Ya, b.Yb, nullptr, N, o.method, thr, nullptr, 0, b.meta, b.Ya4, b.Yb4);
+  k_prep<<<1, 256, 0, ctx->stream>>>(b.Ya, b.Yb, nullptr, N, o.method, thr, nullptr, 0, nullptr, b.meta, b.Ya4, b.Yb4);
   count_launch(ctx);
   PRE3_TRY(launch_eval_mode<2>(ctx, b, o, 0, H, 0, H, nullptr, dR, dT));
   // ... ErrorSum and masks through the exact fp64 kernel

@@ -14,6 +14,13 @@ struct PairMeta {
   int32_t pad;
 };
 
+// adaptive-iteration table of one call (ensure_adaptive_table)
+struct AdaptiveTable {
+  const int32_t* tab = nullptr;     // rows of nIterations(card, N), card = 0..N
+  const int32_t* rowoff = nullptr;  // rowoff[N] = offset of row N (per-call row set), nullptr otherwise
+  int triangular = 0;               // row N at N(N+1)/2
+};
+
 struct RansacBuffers {
   const double* Ya;      // P x Nmax x 3
   const double* Yb;
@@ -28,6 +35,7 @@ struct RansacBuffers {
   const int32_t* samples;  // P x H x k or nullptr (seeded)
   uint32_t pair_id0;
   long long h0 = 0;      // global id of local sample set 0 (hypothesis-block sharding); selection kernels only
+  AdaptiveTable tab;     // set by ensure_adaptive_table when the adaptive stop is on
 };
 
 size_t ransac_workspace_bytes(int P, int Nmax, int H);
@@ -47,7 +55,8 @@ int launch_select(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts&
 // P x H x 4 explicit sets or nullptr (seeded sampler of ransac_dr_ye.m:28-48)
 int launch_dr_ye(pre3_ctx* ctx, RansacBuffers& b, const pre3_ransac_opts& o, const int32_t* dmatch,
                  pre3_pair_result* dres, uint8_t* dmasks, pre3_dr_ye_stat* dstat, int32_t* dcounts_out);
-int ensure_adaptive_table(pre3_ctx* ctx, const pre3_ransac_opts& o, int Nmax);
+int ensure_adaptive_table(pre3_ctx* ctx, const pre3_ransac_opts& o, int Nmax, const int32_t* dn_corr, int P,
+                          AdaptiveTable* out);
 
 // stage-wise entry points
 int launch_fit_only(pre3_ctx* ctx, const double* dYa, const double* dYb, int N, const int32_t* dsamples, int k,

@@ -38,12 +38,14 @@ extern "C" void mexFunction(int nout, mxArray *out[], int nin, const mxArray *in
   }
   pre3_ctx *ctx = pre3_mex_ctx();
   int32_t *pairs = (int32_t *)mxMalloc(sizeof(int32_t) * 2 * (size_t)(K1 > 0 ? K1 : 1));
-  double *score = (double *)mxMalloc(sizeof(double) * (size_t)(K1 > 0 ? K1 : 1));
+  /* scores only when asked for ([matches, D] = ...): without them the certified accept branch of the matcher skips
+   * the exact distance and nothing is copied back */
+  double *score = nout > 1 ? (double *)mxMalloc(sizeof(double) * (size_t)(K1 > 0 ? K1 : 1)) : NULL;
   int32_t n = 0;
   int rc = pre3_siftmatch(ctx, mxGetData(in[L1]), mxGetData(in[L2]), pcls, K1, K2, ND, thresh, pairs, score, &n);
   if (rc != PRE3_OK) {
     mxFree(pairs);
-    mxFree(score);
+    if (score) mxFree(score);
     pre3_mex_check(rc);
   }
   out[MATCHES] = mxCreateDoubleMatrix(2, (size_t)n, mxREAL);
@@ -59,5 +61,5 @@ extern "C" void mexFunction(int nout, mxArray *out[], int nin, const mxArray *in
     if (Dp) Dp[i] = score[i];
   }
   mxFree(pairs);
-  mxFree(score);
+  if (score) mxFree(score);
 }
