@@ -4,11 +4,13 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--pairs P]
 
 Workload (BASELINE.json configs[2], the one the metric "frame-pairs/s (match+RANSAC)" is quoted
-on): a whole synthetic sequence of 4096 frame pairs PER GPU -- 512 SIFT descriptors (128-d,
-class double holding float32 values) + 512 3-D points per frame, 300 planted correspondences,
-30 % outliers, 5-point RANSAC with 2000 seeded sample sets per pair, the reference's adaptive
-stop.  A step = one pass of pre3_pairs over the whole batch.  Pairs are independent: ranks get
-their own sequence, there is no data-path collective ("scaling": "weak").
+on): ONE synthetic sequence of 4096 frame pairs -- 512 SIFT descriptors (128-d, class double
+holding float32 values) + 512 3-D points per frame, 300 re-observed features per step, 30 %
+outliers, 5-point RANSAC with 2000 seeded sample sets per pair, the reference's adaptive stop --
+"sharded by pair across 1/2/4/8 B200": rank r takes the contiguous block of pairs
+dist.split_range(4096, r, N) and the 240-byte result records of all pairs are all-gathered to every
+rank INSIDE the timed region ("scaling": "strong").  A step = one pass over the whole sequence.
+config.weak_scaling carries the secondary figure with 4096 pairs PER GPU.
 
   value      device-resident inputs, pre3_pairs_dev, CUDA events on the launching stream
   e2e        pre3_pairs with pinned HOST buffers: H2D of descriptors / points and D2H of the
@@ -38,8 +40,9 @@ if ROOT not in sys.path:
 K_FEAT, N_CORR, OUTLIER, H_HYP, K_MIN, MAX_IT = 512, 300, 0.30, 2000, 5, 2000
 SEED = 3000  # 1000*cfg + index
 FLOPS_PER_EVAL = 27.0        # R*y 15, +t 3, -x 3, squares 5, sqrt 1
-WORKLOAD = "cfg3: sequence of {P}+1 consecutive SR4000 frames = {P} frame pairs per GPU, 512 descriptors (double) per " \
-           "frame, 300 re-observed features per step, 30% outliers, k=5, 2000 sample sets, adaptive stop"
+WORKLOAD = "cfg3: ONE sequence of {P}+1 consecutive SR4000 frames = {P} frame pairs, sharded by pair over the GPUs, 512 " \
+           "descriptors (double) per frame, 300 re-observed features per step, 30% outliers, k=5, 2000 sample sets, " \
+           "adaptive stop"
 
 
 def peaks():
@@ -117,6 +120,13 @@ def run_reference(args):
     import multiprocessing as mp
     cores = os.cpu_count() or 1
     per_step = max(cores, 8) * 4
+    # the reference's compiled siftmatch.c (oracle/_ref) and the C restatement are loaded HERE, in the parent, and
+    # exercised once, so that the process the driver observes maps the libraries the forked workers run
+    _cpu_pool_init(1)
+    from oracle import refmex
+    if refmex.available():
+        refmex.lib()
+    _cpu_pair_worker((SEED, 0))
     ctx = mp.get_context("fork")
     times = []
     with ctx.Pool(cores, initializer=_cpu_pool_init, initargs=(per_step,)) as pool:
@@ -131,9 +141,9 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "SR4000 frame-pairs/s (match+RANSAC)", "value": value,
         "unit": "frame-pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD.format(P=per_step) + f" [bounded sample: {per_step} pairs per step]"},
+        "config": {"workload": WORKLOAD.format(P=4096) + f" [bounded sample: {per_step} pairs per step, all host cores]"},
         "cpu_baseline": {"value": value, "unit": "frame-pairs/s", "cores": cores, "kind": cpu_kind(),
                          "sample": f"{per_step} pairs per step over {cores} processes"},
         "e2e": {"value": value, "unit": "frame-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -146,19 +156,52 @@ def run_reference(args):
 # clocks
 # ------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons DURING the timed region.  NVML through pynvml in a thread (a sample every ~2 ms:
+    the timed region of the default run is tens of milliseconds), nvidia-smi -lms 100 as the fallback."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nvml, self.stop_flag = index, [], None, None, False
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            return pynvml, pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+        except Exception:
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.index)
 
     def start(self):
+        try:
+            self.nvml, self.handle = self._nvml_handle()
+            self.max_mhz = float(self.nvml.nvmlDeviceGetMaxClockInfo(self.handle, self.nvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
+
+    def _poll(self):
+        n = self.nvml
+        reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag:
+            try:
+                mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                r = int(reasons(self.handle))
+                self.rows.append((time.perf_counter(), mhz, r))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def _read(self):
         for ln in self.proc.stdout:
@@ -167,6 +210,20 @@ class ClockSampler:
     def stop(self, t0=None, t1=None):
         """Samples taken inside [t0, t1] (the timed region); when the region is too short for
         three samples, every sample since start() (warm-up + timed region, same load)."""
+        if self.nvml:
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+            rows = [r for r in self.rows if t0 is None or t0 <= r[0] <= t1]
+            window = "timed region"
+            if len(rows) < 3:
+                rows, window = list(self.rows), "warm-up + timed region"
+            sm = [r[1] for r in rows]
+            bits = 0
+            for r in rows:
+                bits |= r[2]
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz,
+                    "reasons": sorted(v for k, v in self.BITS.items() if bits & k), "samples": len(sm), "window": window,
+                    "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -179,7 +236,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for r in rows for i in range(4) if r[2 + i] == "Active"})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm), "window": window}
+                "reasons": reasons, "samples": len(sm), "window": window, "source": "nvidia-smi"}
 
 
 
@@ -572,6 +629,18 @@ def other_workloads(ctx, pre3, synth, dev, rank, world):
 # ------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------
+def _summ(o, keys):
+    """Flat numeric summary of a secondary workload (what the driver's record keeps inside `config`)."""
+    out = {}
+    for k in keys:
+        v = o
+        for part in k.split("."):
+            v = v.get(part) if isinstance(v, dict) else None
+        if v is not None:
+            out[k] = v
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -585,22 +654,34 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     pre3 = importlib.import_module("3pre_b200")
     synth = importlib.import_module("3pre_b200.synth")
+    pd = importlib.import_module("3pre_b200.dist")
 
-    P = args.pairs
+    P = args.pairs                       # pairs of the WHOLE sequence (strong scaling: split over the ranks)
+    p0, p1 = pd.split_range(P, rank, world)
+    Pl = p1 - p0                         # this rank's block of pairs = frames p0 .. p1
     ctx = pre3.Context(local)
     ctx.use_torch_stream()
-    # synthetic sequence of this rank: P + 1 consecutive frames, generated on the device
-    sq = synth.make_sequence_torch(P + 1, SEED + 100000 * rank, dev, K=K_FEAT, n_corr=N_CORR, outlier_ratio=OUTLIER)
-    data = {"desc": sq["desc"], "xyz": sq["xyz"]}
+    # the same synthetic sequence on every rank (same seed, generated on the device); a rank keeps its block
+    sq = synth.make_sequence_torch(P + 1, SEED, dev, K=K_FEAT, n_corr=N_CORR, outlier_ratio=OUTLIER)
+    full = {"desc": sq["desc"], "xyz": sq["xyz"]} if world > 1 else None
+    data = {"desc": sq["desc"][p0:p1 + 1].contiguous(), "xyz": sq["xyz"][p0:p1 + 1].contiguous()}
     del sq
     torch.cuda.empty_cache()
     opts = pre3.make_opts(method=0, k=K_MIN, max_iteration=MAX_IT, adaptive=True, H=H_HYP, seed=7)
-    res = torch.zeros(P, 240, dtype=torch.uint8, device=dev)
-    matches = torch.zeros(P, K_FEAT, 2, dtype=torch.int32, device=dev)
-    masks = torch.zeros(P, K_FEAT, dtype=torch.uint8, device=dev)
+    res = torch.zeros(Pl, 240, dtype=torch.uint8, device=dev)
+    matches = torch.zeros(Pl, K_FEAT, 2, dtype=torch.int32, device=dev)
+    masks = torch.zeros(Pl, K_FEAT, dtype=torch.uint8, device=dev)
+    even = Pl * world == P
+    res_all = torch.zeros(P, 240, dtype=torch.uint8, device=dev) if world > 1 else res
+    gathered = [res_all]
 
     def step():
-        ctx.sequence_dev(data["desc"], data["xyz"], opts, res, matches, masks, pair_id0=rank * P)
+        ctx.sequence_dev(data["desc"], data["xyz"], opts, res, matches, masks, pair_id0=p0)
+        if world > 1:  # the records of every pair on every rank: 240 B per pair, one all-gather
+            if even:
+                dist.all_gather_into_tensor(res_all, res)
+            else:
+                gathered[0] = pd.gather_records(res, P)
 
     def barrier():
         if world > 1:
@@ -610,7 +691,7 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-        time.sleep(0.3)
+        time.sleep(0.05)
     for _ in range(args.warmup):
         step()
     barrier()
@@ -630,21 +711,22 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     barrier()
     ms_step = float(t.item()) / args.steps
-    value = world * P / (ms_step * 1e-3)
+    value = P / (ms_step * 1e-3)
 
-    # sanity of the timed work: every pair solved, planted motion recovered
-    r = np.frombuffer(res.cpu().numpy().tobytes(), dtype=pre3.RESULT_DTYPE)
+    # sanity of the timed work: every pair of the WHOLE sequence solved (records gathered in the timed region)
+    r = np.frombuffer(gathered[0].cpu().numpy().tobytes(), dtype=pre3.RESULT_DTYPE)
     ok_pairs = int(((r["status"] == 0) & (r["best_fit"] > 150)).sum())
+    rl = r[p0:p1]
     ends = ctx.eval_schedule(opts)  # waves: a pair that consumed n sets had ends[first i: n < ends[i]] evaluated
-    wave = np.minimum(np.searchsorted(ends, r["n_consumed"], side="right"), len(ends) - 1)
+    wave = np.minimum(np.searchsorted(ends, rl["n_consumed"], side="right"), len(ends) - 1)
     hyps_done = ends[wave].astype(np.float64)
-    evals_done = float((r["n_matches"].astype(np.float64) * hyps_done).sum())          # evaluated on the GPU
-    evals_needed = float((r["n_matches"].astype(np.float64) * r["n_consumed"]).sum())  # the reference's loop
+    evals_done = float((rl["n_matches"].astype(np.float64) * hyps_done).sum())          # evaluated on this GPU
+    evals_needed = float((rl["n_matches"].astype(np.float64) * rl["n_consumed"]).sum())  # the reference's loop
 
-    # ---- per-kernel timing (separate steps, events around every launch) -----------------
+    # ---- per-kernel timing (separate steps, events around every launch; this rank's block) -----------
     ctx.timing_enable(True)
     for _ in range(2):
-        step()
+        ctx.sequence_dev(data["desc"], data["xyz"], opts, res, matches, masks, pair_id0=p0)
     kt = ctx.timing_read()
     ctx.timing_enable(False)
     per_kernel = {k: {"ms_per_step": v[0] / 2, "launches_per_step": v[1] // 2} for k, v in kt.items()}
@@ -655,8 +737,8 @@ def run_ours(args):
     pk = peaks()
     fp32_peak = ctx.measure_fp32_peak()
     fp32_peak_3reg = ctx.measure_fp32_peak_3reg()
-    desc_bytes = float((P + 1) * K_FEAT * 128 * data["desc"].element_size())  # every frame is converted once
-    match_flops = 2.0 * K_FEAT * K_FEAT * 128 * P
+    desc_bytes = float((Pl + 1) * K_FEAT * 128 * data["desc"].element_size())  # every frame is converted once
+    match_flops = 2.0 * K_FEAT * K_FEAT * 128 * Pl
     rooflines = {}
     for name, v in per_kernel.items():
         sec = v["ms_per_step"] * 1e-3 / max(v["launches_per_step"], 1)
@@ -665,14 +747,13 @@ def run_ours(args):
             a = FLOPS_PER_EVAL * evals_done / L / sec / 1e12
             rooflines[name] = {"bound": "fp32", "achieved": a, "peak": fp32_peak, "unit": "TFLOP/s",
                                "frac": a / fp32_peak, "traffic": None,
+                               "frac_on_required_evals": FLOPS_PER_EVAL * evals_needed / L / sec / 1e12 / fp32_peak,
                                "note": "27 FLOP per hypothesis x match eval over the evaluations executed (the fp64 "
                                        "minimal fits run in the same kernel and are not counted); peak = FFMA-chain "
-                                       "microbenchmark measured in this run (MEASURED_PEAKS.json has no FP32 figure)",
+                                       "microbenchmark measured in this run (MEASURED_PEAKS.json has no FP32 figure); "
+                                       "frac_on_required_evals counts only the evals the reference loop needs",
                                "evals_per_s": evals_done / L / sec,
-                               "peak_register_operands": fp32_peak_3reg, "frac_of_register_operand_peak": a / fp32_peak_3reg,
-                               "note2": "peak_register_operands = the same FFMA chains with all three sources in registers "
-                                        "(hypothesis in registers x correspondence from shared memory): the issue rate this "
-                                        "kernel's FFMAs can reach"}
+                               "peak_register_operands": fp32_peak_3reg, "frac_of_register_operand_peak": a / fp32_peak_3reg}
         elif name in ("match_tc",):
             a = match_flops / L / sec / 1e12
             rooflines[name] = {"bound": "tensor", "achieved": a, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
@@ -687,18 +768,22 @@ def run_ours(args):
                                "frac": a / pk["hbm_gbs"], "traffic": None, "note": f"of {pk['source']}"}
     # traffic: DRAM bytes per launch measured by ncu (profiles/r01_traffic.json: bytes per pair at the same
     # per-pair shape), scaled to the pairs one launch processes here
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if not os.path.exists(tpath):
+        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
     if os.path.exists(tpath):
         tr = json.load(open(tpath))["per_pair_bytes"]
         for name in rooflines:
             if name in tr:
-                units = (P + 1) if name == "convert" else P  # convert: bytes per descriptor set (frame)
+                units = (Pl + 1) if name == "convert" else Pl  # convert: bytes per descriptor set (frame)
                 rooflines[name]["traffic"] = tr[name]["bytes"] * units
                 rooflines[name]["traffic_note"] = "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch " \
-                                                  "(profiles/r01_i_kernels.csv, per pair) x pairs per launch"
+                                                  f"({os.path.basename(tpath)}, per pair) x pairs per launch"
     roofline = dict(rooflines.get(dom, {"bound": "hbm", "achieved": None, "peak": pk["hbm_gbs"], "unit": "GB/s",
                                         "frac": None, "traffic": None}))
     roofline["kernel"] = dom
+    roofline["per_kernel"] = {k: {kk: v.get(kk) for kk in ("bound", "achieved", "peak", "unit", "frac")}
+                              for k, v in rooflines.items()}
 
     if args.profile:
         if rank == 0:
@@ -707,18 +792,54 @@ def run_ours(args):
         if world > 1:
             dist.destroy_process_group()
         return
-    # ---- e2e: host buffers through pre3_pairs ---------------------------------------------
-    Pe = min(P, args.e2e_pairs)
+
+    # ---- secondary: weak scaling (the whole 4096-pair sequence on EVERY GPU, no gather) ------------------
+    weak = None
+    if world > 1:
+        wres = torch.zeros(P, 240, dtype=torch.uint8, device=dev)
+        wm = torch.zeros(P, K_FEAT, 2, dtype=torch.int32, device=dev)
+        wk = torch.zeros(P, K_FEAT, dtype=torch.uint8, device=dev)
+
+        def wstep():
+            ctx.sequence_dev(full["desc"], full["xyz"], opts, wres, wm, wk, pair_id0=0)
+
+        for _ in range(2):
+            wstep()
+        barrier()
+        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0.record()
+        for _ in range(5):
+            wstep()
+        w1.record()
+        torch.cuda.synchronize()
+        tw = torch.tensor([w0.elapsed_time(w1) / 5], dtype=torch.float64, device=dev)
+        dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+        weak = {"pairs_per_gpu": P, "ms_per_step": float(tw.item()), "value": world * P / (float(tw.item()) * 1e-3),
+                "unit": "frame-pairs/s", "note": "every GPU runs the whole sequence (independent replicas, no collective)"}
+        del wres, wm, wk, full
+        torch.cuda.empty_cache()
+
+    # ---- e2e: host buffers through pre3_sequence, this rank's block; records gathered to every rank ------
+    Pe = min(Pl, max(1, args.e2e_pairs // world))
     host = {k: torch.empty(data[k][:Pe + 1].shape, dtype=data[k].dtype, pin_memory=True) for k in data}
     for k in host:
         host[k].copy_(data[k][:Pe + 1])
     torch.cuda.synchronize()
     hn = {k: v.numpy() for k, v in host.items()}
     out = (np.zeros(Pe, pre3.RESULT_DTYPE), np.zeros((Pe, K_FEAT, 2), np.int32), np.zeros((Pe, K_FEAT), np.uint8))
+    rec_pin = torch.empty(Pe, 240, dtype=torch.uint8, pin_memory=True)
+    rec_dev = torch.empty(Pe, 240, dtype=torch.uint8, device=dev)
+    rec_all = torch.empty(Pe * world, 240, dtype=torch.uint8, device=dev)
     ectx = pre3.Context(local)
 
     def e2e_step():
-        return ectx.sequence(hn["desc"], hn["xyz"], opts, pair_id0=rank * P, out=out)
+        o = ectx.sequence(hn["desc"], hn["xyz"], opts, pair_id0=p0, out=out)
+        if world > 1:  # every rank ends up with the records of all pairs on the HOST
+            rec_pin.numpy()[:] = np.frombuffer(out[0].tobytes(), np.uint8).reshape(Pe, 240)
+            rec_dev.copy_(rec_pin, non_blocking=True)
+            dist.all_gather_into_tensor(rec_all, rec_dev)
+            return rec_all.cpu()
+        return o
 
     for _ in range(max(1, min(args.warmup, 2))):
         e2e_step()
@@ -734,11 +855,14 @@ def run_ours(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_val = world * Pe * e2e_steps / float(te.item())
     tb1 = ectx.transfer_bytes()
-    h2d = (tb1[0] - tb0[0]) // e2e_steps   # bytes that crossed PCIe (float-exact descriptors cross as float)
-    d2h = (tb1[1] - tb0[1]) // e2e_steps
-    host_in = sum(int(hn[k].nbytes) for k in hn)
-    assert np.array_equal(out[0]["best_fit"], r["best_fit"][:Pe]), "e2e path disagrees with the device path"
+    hb = torch.tensor([(tb1[0] - tb0[0]) // e2e_steps, (tb1[1] - tb0[1]) // e2e_steps,
+                       sum(int(hn[k].nbytes) for k in hn)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(hb, op=dist.ReduceOp.SUM)   # bytes of the whole job per step
+    h2d, d2h, host_in = (int(x) for x in hb.tolist())
+    assert np.array_equal(out[0]["best_fit"], rl["best_fit"][:Pe]), "e2e path disagrees with the device path"
     ectx.close()
+    e2e_gbs = (h2d + d2h) / (float(te.item()) / e2e_steps) / 1e9
 
     others = None
     if not args.no_other:
@@ -748,18 +872,52 @@ def run_ours(args):
         barrier()
     if rank == 0:
         cpu = cpu_baseline_single()
+        other_cfg = {}
+        if others:
+            o = others
+            other_cfg = {
+                "cfg1_latency": _summ(o.get("cfg1", {}), ["k5.ms_per_pair_device_resident", "k5.ms_per_pair_host_buffers",
+                                                          "k3.ms_per_pair_device_resident"]),
+                "cfg2_matching_256x2048x2048": _summ(o.get("cfg2", {}), ["pairs_per_s", "ms_per_step", "roofline.achieved",
+                                                                         "roofline.frac"]),
+                "cfg4_ekf_200_features": _summ(o.get("cfg4", {}), ["adaptive.frames_per_s", "fixed_H.frames_per_s",
+                                                                   "fixed_H.hyp_x_feature_evals_per_s",
+                                                                   "fixed_H.roofline_score.frac", "fixed_H.roofline_gain.frac"]),
+                "cfg5_20k_x_1M_split": _summ(o.get("cfg5", {}), ["first.ms_per_solve", "reference.ms_per_solve",
+                                                                  "first.hyp_x_match_evals_per_s", "roofline.frac",
+                                                                  "roofline.evals_per_s", "error"]),
+                "dr_ye": _summ(o.get("dr_ye", {}), ["pairs_per_s"]),
+                "frames": _summ(o.get("frames", {}), ["maps.roofline.frac", "fused_features.roofline.frac"]),
+                "ekf_update": _summ(o.get("ekf_update", {}), ["frames_per_s", "fp64_tflops_executed"]),
+            }
+            for nm, key in (("cfg2", "cfg2_match_tc"), ("cfg5", "cfg5_eval")):
+                rf = (o.get(nm) or {}).get("roofline")
+                if rf:
+                    roofline["per_kernel"][key] = {kk: rf.get(kk) for kk in ("bound", "achieved", "peak", "unit", "frac")}
+            rf4 = ((o.get("cfg4") or {}).get("fixed_H") or {}).get("roofline_score")
+            if rf4:
+                roofline["per_kernel"]["cfg4_ekf_score"] = {kk: rf4.get(kk) for kk in ("bound", "achieved", "peak", "unit", "frac")}
         line = {
             "metric": "SR4000 frame-pairs/s (match+RANSAC)", "value": value, "unit": "frame-pairs/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD.format(P=P), "pairs_per_gpu": P, "sharding": "by frame pair",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD.format(P=P), "pairs_total": P, "pairs_per_gpu": Pl,
+                       "sharding": "by frame pair: rank r takes pairs dist.split_range(P, r, N); the 240-byte records of "
+                                   "all pairs are all-gathered to every rank inside the timed region",
                        "api": "pre3_sequence_dev (value) / pre3_sequence (e2e): pair p = (frame p, frame p+1)",
-                       "l2": "inputs (2.1 GB of descriptors per GPU at P=4096) larger than L2",
-                       "match_engine": "tcgen05 proposal + exact rescore" if "match_tc" in per_kernel
-                       else "exact fp64 brute force"},
+                       "l2": f"inputs ({desc_bytes / 1e9:.2f} GB of descriptors per GPU) "
+                             + ("larger than L2" if desc_bytes > 126e6 else "smaller than L2: at this GPU count the step "
+                                "re-reads them from L2"),
+                       "match_engine": "tcgen05 CTA-pair proposal + exact rescore" if "match_tc" in per_kernel
+                       else "exact fp64 brute force",
+                       "weak_scaling": weak, "other_configs": other_cfg},
             "e2e": {"value": e2e_val, "unit": "frame-pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "pairs_per_step": Pe, "steps": e2e_steps, "host_input_bytes_per_step": host_in,
-                    "note": "pre3_sequence on pinned host buffers (class double). With one rank per host, descriptors whose "
+                    "pairs_per_step": Pe * world, "steps": e2e_steps, "host_input_bytes_per_step": host_in,
+                    "pcie_gb_per_s_whole_job": e2e_gbs,
+                    "bound": "host side: one PCIe link per GPU (~55 GB/s) at N = 1; with several ranks on one host the "
+                             "shared host DRAM / root complexes (~180 GB/s aggregate measured on this pool) cap the job",
+                    "note": "pre3_sequence on pinned host buffers (class double), every rank its block of the sequence, "
+                            "records all-gathered and read back on every rank. With one rank per host, descriptors whose "
                             "values survive (double)(float)x == x are narrowed by a host thread pool and cross PCIe as "
                             "float (h2d_bytes_per_step < host_input_bytes_per_step); with several ranks per host they "
                             "cross as doubles (every GPU has its own link, the host memory is shared)"},
@@ -769,7 +927,7 @@ def run_ours(args):
             "rooflines": rooflines,
             "kernels": per_kernel,
             "evals": {"hyp_x_match_evals_per_s": world * evals_done / (ms_step * 1e-3),
-                      "executed_per_step": evals_done, "required_by_reference_loop_per_step": evals_needed},
+                      "executed_per_step_this_rank": evals_done, "required_by_reference_loop_per_step_this_rank": evals_needed},
             "cpu_baseline": cpu,
             "check": {"pairs_solved": ok_pairs, "pairs": P},
             "other_workloads": others,
@@ -803,8 +961,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--pairs", type=int, default=4096, help="frame pairs per GPU per step")
-    ap.add_argument("--e2e-pairs", type=int, default=4096, help="frame pairs per e2e step (pinned host memory)")
+    ap.add_argument("--pairs", type=int, default=4096, help="frame pairs of the whole sequence (split over the GPUs)")
+    ap.add_argument("--e2e-pairs", type=int, default=4096, help="frame pairs per e2e step, whole job (pinned host memory)")
     ap.add_argument("--no-other", action="store_true", help="skip the short cfg2 / cfg4 / cfg5 measurements")
     ap.add_argument("--profile", action="store_true",
                     help="short run for ncu: skips the e2e and cpu_baseline legs (their keys are null)")
