@@ -623,7 +623,8 @@ struct Prop2 {     // per L1 row: s(j) = a~.b~_j - |b_j|^2/2  (d2(j) = |a|^2 - 2
 };
 
 // EXP: 0 product; 1 TMA + MMA only (accumulators released unread); 2 TMA + epilogue only (no MMA issued)
-template <int EXP>
+// EPI: 1 product (selection split over the ALU and FMA pipes); 0 all-ALU selection (3.5 instructions per accumulator)
+template <int EXP, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 k_tc_gemm_pair(const unsigned char* __restrict__ imgA, const unsigned char* __restrict__ imgB,
                const unsigned char* __restrict__ extB, int ext_layout, int P, int K1p, int K2p,
@@ -761,6 +762,15 @@ k_tc_gemm_pair(const unsigned char* __restrict__ imgA, const unsigned char* __re
     }
   } else if (warp < W_TMA) {
     // ===== epilogue: warpgroup wg takes columns [128 wg, 128 wg + 128) of every tile =================
+    // The selection is bound by the ALU pipe (16 lanes per SM sub-partition: LOP3 / FMNMX issue every other cycle),
+    // not by issue slots, so everything that does not have to be exact is moved to the (idle, full-rate) FMA pipe:
+    // per two accumulators the ALU packs the column into the keys (2 LOP3), takes their maximum (carries the index
+    // exactly), advances the running maximum and the running second (one 3-input max); the pair's minimum and
+    // min(m1, hi) -- which only feed the SECOND best, a value that is bracketed with a margin anyway -- are formed
+    // arithmetically, lo = (k0 + k1) - hi and x = (m1 + hi) - max(m1, hi), as packed FADD2 on two independent chains
+    // (even / odd accumulators), 2 ulp off at most.  2.5 ALU + 1 packed FMA-pipe instruction per accumulator instead
+    // of 3.5 ALU.  The next tile's first tcgen05.ld is issued, and the accumulator stage handed back to the MMA
+    // issuer, as soon as the current tile's last load has landed in registers.
     const int wg = (warp - W_EPI0) >> 2;
     const int q = warp & 3;
     const uint32_t t_empty_leader0 = mapa_u32(smem_u32(&bars->t_empty[0]), 0);
@@ -769,52 +779,102 @@ k_tc_gemm_pair(const unsigned char* __restrict__ imgA, const unsigned char* __re
     uint32_t useA = 0, useB = 0;
     uint32_t keymask;
     asm volatile("mov.u32 %0, 0xFFFFFF80;" : "=r"(keymask));
+    const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(wg * BLK);
+    uint32_t buf[2][32];
+    auto wait_full = [&](int acc) {
+      uint32_t& use = acc == 0 ? useA : useB;
+      mbar_wait(smem_u32(&bars->t_full[acc]), use & 1);
+      ++use;
+      tc_fence_after();
+    };
+    auto release = [&](int acc) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(smem_u32(&bars->t_empty[acc]));
+        else mbar_arrive_cluster(acc == 0 ? t_empty_leader0 : t_empty_leader1);
+      }
+    };
+    bool primed = false;
     for (long long u = cluster_id; u < nunits; u += nclusters) {
       const int p = (int)(u / groups), g = (int)(u % groups);
-      float m1 = -INFINITY, m2 = -INFINITY;
-      int btile = -1;
+      float2 m1 = make_float2(-INFINITY, -INFINITY), m2 = make_float2(-INFINITY, -INFINITY);  // chains: even / odd columns
+      int btA = -1, btB = -1;
       for (int j = 0; j < ntile; ++j, ++t) {
         const int acc = (int)(t & 1);
-        uint32_t& use = acc == 0 ? useA : useB;
-        mbar_wait(smem_u32(&bars->t_full[acc]), use & 1);
-        ++use;
-        tc_fence_after();
-        const float m1_in = m1;
-        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * P2_TILE_N + wg * BLK);
-        uint32_t buf[2][32];
-        if (EXP != 1) tc_ld_32x32(taddr, buf[0]);
+        if (!primed) {
+          wait_full(acc);
+          if (EXP != 1) tc_ld_32x32(tbase + (uint32_t)(acc * P2_TILE_N), buf[0]);
+          primed = true;
+        }
+        const float2 m1_in = m1;
+        const bool has_next = (j + 1 < ntile) || (u + nclusters < nunits);
 #pragma unroll
         for (int c = 0; c < BLK / 32; ++c) {
-          if (EXP == 1) break;
-          tc_ld_wait(buf[c & 1]);
-          if (c + 1 < BLK / 32) tc_ld_32x32(taddr + (uint32_t)((c + 1) * 32), buf[(c + 1) & 1]);
+          if (EXP != 1) tc_ld_wait(buf[c & 1]);
+          if (c + 1 < BLK / 32) {
+            if (EXP != 1) tc_ld_32x32(tbase + (uint32_t)(acc * P2_TILE_N + (c + 1) * 32), buf[(c + 1) & 1]);
+          } else {
+            release(acc);  // every accumulator of this stage is in registers
+            if (has_next) {
+              wait_full(acc ^ 1);
+              if (EXP != 1) tc_ld_32x32(tbase + (uint32_t)((acc ^ 1) * P2_TILE_N), buf[0]);
+            }
+          }
+          if (EXP == 1) continue;
+          if (EPI == 0) {
 #pragma unroll
-          for (int i2 = 0; i2 < 16; ++i2) {
-            uint32_t k0, k1;  // (bits & ~127) | column within the half tile: one LOP3 each
-            asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(k0) : "r"(buf[c & 1][2 * i2]), "r"(keymask), "r"((uint32_t)(c * 32 + 2 * i2)));
-            asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(k1) : "r"(buf[c & 1][2 * i2 + 1]), "r"(keymask), "r"((uint32_t)(c * 32 + 2 * i2 + 1)));
-            const float f0 = __uint_as_float(k0), f1 = __uint_as_float(k1);
-            const float hi = fmaxf(f0, f1), lo = fminf(f0, f1);
-            m2 = fmaxf(fmaxf(m2, fminf(m1, hi)), lo);  // second largest of {m1, m2, f0, f1}
-            m1 = fmaxf(m1, hi);
+            for (int i2 = 0; i2 < 16; ++i2) {
+              uint32_t k0, k1;  // (bits & ~127) | column within the half tile: one LOP3 each
+              asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(k0) : "r"(buf[c & 1][2 * i2]), "r"(keymask), "r"((uint32_t)(c * 32 + 2 * i2)));
+              asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(k1) : "r"(buf[c & 1][2 * i2 + 1]), "r"(keymask), "r"((uint32_t)(c * 32 + 2 * i2 + 1)));
+              const float f0 = __uint_as_float(k0), f1 = __uint_as_float(k1);
+              const float hi = fmaxf(f0, f1), lo = fminf(f0, f1);
+              m2.x = fmaxf(fmaxf(m2.x, fminf(m1.x, hi)), lo);  // second largest of {m1, m2, f0, f1}
+              m1.x = fmaxf(m1.x, hi);
+            }
+          } else {
+#pragma unroll
+            for (int i4 = 0; i4 < 8; ++i4) {
+              // four consecutive accumulators v0..v3: chain A takes (v0, v2), chain B (v1, v3); (v0,v1) and (v2,v3) are
+              // adjacent registers = packed operands
+              uint32_t k[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(k[e]) : "r"(buf[c & 1][4 * i4 + e]), "r"(keymask), "r"((uint32_t)(c * 32 + 4 * i4 + e)));
+              const float2 ka = make_float2(__uint_as_float(k[0]), __uint_as_float(k[1]));
+              const float2 kb = make_float2(__uint_as_float(k[2]), __uint_as_float(k[3]));
+              const float2 hi = make_float2(fmaxf(ka.x, kb.x), fmaxf(ka.y, kb.y));
+              const float2 nhi = make_float2(-hi.x, -hi.y);
+              const float2 lo = __fadd2_rn(__fadd2_rn(ka, kb), nhi);            // min(ka, kb) up to rounding
+              const float2 m1n = make_float2(fmaxf(m1.x, hi.x), fmaxf(m1.y, hi.y));
+              const float2 x = __fadd2_rn(__fadd2_rn(m1, hi), make_float2(-m1n.x, -m1n.y));  // min(m1, hi) up to rounding
+              m2.x = fmaxf(fmaxf(m2.x, x.x), lo.x);
+              m2.y = fmaxf(fmaxf(m2.y, x.y), lo.y);
+              m1 = m1n;
+            }
           }
         }
-        if (m1 != m1_in) btile = j;
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          if (leader) mbar_arrive(smem_u32(&bars->t_empty[acc]));
-          else mbar_arrive_cluster(acc == 0 ? t_empty_leader0 : t_empty_leader1);
+        if (m1.x != m1_in.x) btA = j;
+        if (m1.y != m1_in.y) btB = j;
+      }
+      // merge the chains, then the two column halves of this row block (warpgroup 1 -> warpgroup 0); store the proposal
+      float b1, b2;
+      int col;
+      {
+        const int cA = btA < 0 ? -1 : btA * P2_TILE_N + wg * BLK + (int)(__float_as_uint(m1.x) & 0x7Fu);
+        const int cB = btB < 0 ? -1 : btB * P2_TILE_N + wg * BLK + (int)(__float_as_uint(m1.y) & 0x7Fu);
+        if (cB >= 0 && (cA < 0 || m1.y > m1.x || (m1.y == m1.x && cB < cA))) {
+          b1 = m1.y, col = cB, b2 = fmaxf(m1.x, fmaxf(m2.x, m2.y));
+        } else {
+          b1 = m1.x, col = cA, b2 = fmaxf(m1.y, fmaxf(m2.x, m2.y));
         }
       }
-      // merge the two column halves of this row block (warpgroup 1 -> warpgroup 0) and store the proposal
       const int r = q * 32 + lane;
-      const int col = btile < 0 ? -1 : btile * P2_TILE_N + wg * BLK + (int)(__float_as_uint(m1) & 0x7Fu);
-      if (wg == 1) merge[r] = make_float4(m1, m2, __int_as_float(col), 0.f);
+      if (wg == 1) merge[r] = make_float4(b1, b2, __int_as_float(col), 0.f);
       named_bar_sync(1, 256);
       if (wg == 0) {
         const float4 o = merge[r];
-        float b1 = m1, b2 = m2;
         int bc = col;
         const float o1 = o.x, o2 = o.y;
         const int oc = __float_as_int(o.z);
@@ -1105,20 +1165,23 @@ int launch_match_tc(pre3_ctx* ctx, const void* dL1, const void* dL2, int cls, in
     Span span__(ctx, T_MATCH_TC);
     const long long units = (long long)P * (K1p / 256);
     const int grid = 2 * (int)std::min<long long>(units, ctx->sm_count / 2);
-#define PRE3_GEMM2(E)                                                                                              \
+#define PRE3_GEMM2(E, EP)                                                                                            \
   do {                                                                                                             \
     static bool attr_done = false;                                                                                 \
     if (!attr_done) {                                                                                              \
-      PRE3_CUDA(cudaFuncSetAttribute(k_tc_gemm_pair<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES)); \
+      PRE3_CUDA(cudaFuncSetAttribute(k_tc_gemm_pair<E, EP>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES)); \
       attr_done = true;                                                                                            \
     }                                                                                                              \
-    k_tc_gemm_pair<E><<<grid, THREADS, P2_SMEM_BYTES, ctx->stream>>>(imgA, imgB, extB, ext_layout, P, K1p, K2p,    \
+    k_tc_gemm_pair<E, EP><<<grid, THREADS, P2_SMEM_BYTES, ctx->stream>>>(imgA, imgB, extB, ext_layout, P, K1p, K2p, \
                                                                      reinterpret_cast<Prop2*>(prop));              \
   } while (0)
-    switch (exp_mode) {
-      case 0: PRE3_GEMM2(0); break;
-      case 1: PRE3_GEMM2(1); break;
-      case 2: PRE3_GEMM2(2); break;
+    static const int epi_mode = getenv("PRE3_TC_EPI") ? atoi(getenv("PRE3_TC_EPI")) : 1;
+    switch (exp_mode * 2 + (epi_mode ? 1 : 0)) {
+      case 0: PRE3_GEMM2(0, 0); break;
+      case 1: PRE3_GEMM2(0, 1); break;
+      case 2: case 3: PRE3_GEMM2(1, 1); break;
+      case 4: PRE3_GEMM2(2, 0); break;
+      case 5: PRE3_GEMM2(2, 1); break;
       default: return fail(ctx, PRE3_ERR_ARG, "PRE3_TC_EXP: ablation not built for the CTA-pair kernel");
     }
 #undef PRE3_GEMM2

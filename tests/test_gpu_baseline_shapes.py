@@ -223,7 +223,7 @@ def test_gateway_compute_hypothesis_support_fast_mex(orc, se):
     pattern, z_id, z_euc = rne.generate_state_vector_pattern(fr.type, fr.has_z, fr.z, fr.n)
     cam = dict(se.CAM)
     s, li, le = gw(fr.x.reshape(-1, 1), cam, pattern, z_id, z_euc, fr.std_z, nout=3)
-    s0, li0, le0 = orc.ekf_support(fr.x, cam, pattern, z_id, z_euc, fr.std_z)
+    s0, li0, le0, _ = orc.ekf_support(fr.x, cam, pattern, z_id.T, z_euc.T, fr.std_z)
     assert s[0, 0] == s0 and li.dtype == bool and li.shape == (1, z_id.shape[1]) and le.shape == (1, z_euc.shape[1])
     np.testing.assert_array_equal(li.ravel(), li0.astype(bool))
     np.testing.assert_array_equal(le.ravel(), le0.astype(bool))
@@ -231,7 +231,7 @@ def test_gateway_compute_hypothesis_support_fast_mex(orc, se):
     X = np.stack([fr.x, fr.x + 1e-3, fr.x * (1 + 1e-4)], 1)
     s3, li3, _ = gw(X, cam, pattern, z_id, z_euc, fr.std_z, nout=3)
     for j in range(3):
-        sj, lij, _ = orc.ekf_support(X[:, j], cam, pattern, z_id, z_euc, fr.std_z)
+        sj, lij, _, _ = orc.ekf_support(X[:, j], cam, pattern, z_id.T, z_euc.T, fr.std_z)
         assert s3[0, j] == sj
         np.testing.assert_array_equal(li3[j], lij.astype(bool))
     # empty z_euc -> [] mask (:112-116)
