@@ -94,6 +94,7 @@ SYMBOLS = {
     "pre3_set_match_engine": (_I, [_VP, _I]),
     "pre3_sync": (_I, [_VP]),
     "pre3_launch_count": (_I64, [_VP]),
+    "pre3_set_graphs": (_I, [_VP, _I]),
     "pre3_transfer_bytes": (_I, [_VP, _VP, _VP]),
     "pre3_eval_schedule": (_I, [_OPTS, _VP, _I]),
     "pre3_timing_enable": (_I, [_VP, _I]),

@@ -159,6 +159,10 @@ class Context:
     def set_match_engine(self, engine: int):
         self._ck(self._lib.pre3_set_match_engine(self._h, int(engine)))
 
+    def set_graphs(self, on: bool = True):
+        """CUDA-graph replay of pairs_dev / sequence_dev calls that repeat a signature (pre3_set_graphs)."""
+        self._ck(self._lib.pre3_set_graphs(self._h, int(bool(on))))
+
     def sync(self):
         self._ck(self._lib.pre3_sync(self._h))
 

@@ -119,6 +119,61 @@ int ransac_impl(pre3_ctx* ctx, const double* dYa, const double* dYb, const int32
 
 }  // namespace
 
+// ---- CUDA-graph replay (pre3_set_graphs) ------------------------------------------------------------------------
+// A whole-pair call is ~15-20 short launches; at a few hundred pairs per call (a sequence sharded over 8 GPUs) the
+// host's launch rate, not the GPU, bounds the step.  With graphs on, the FIRST call with a given signature runs eagerly
+// (it also sizes the arena and the cached tables), the SECOND is captured from the stream into a graph, and every later
+// call with the same signature is one cudaGraphLaunch.  Per-launch timing switches replay off.
+namespace {
+template <typename T>
+void key_put(std::vector<unsigned char>& k, const T& v) {
+  const unsigned char* b = reinterpret_cast<const unsigned char*>(&v);
+  k.insert(k.end(), b, b + sizeof(T));
+}
+
+template <typename Body>
+int graph_or_eager(pre3_ctx* ctx, const std::vector<unsigned char>& key, Body body) {
+  if (!ctx->graphs || ctx->timing) return body();
+  if (ctx->graph_exec && key == ctx->graph_key) {
+    PRE3_CUDA(cudaGraphLaunch(ctx->graph_exec, ctx->stream));
+    ctx->launches += ctx->graph_launches;
+    return PRE3_OK;
+  }
+  if (key != ctx->graph_seen) {  // first sight: eager
+    ctx->graph_seen = key;
+    return body();
+  }
+  // second call with this signature: capture
+  if (ctx->graph_exec) {
+    cudaGraphExecDestroy(ctx->graph_exec);
+    ctx->graph_exec = nullptr;
+  }
+  const int64_t l0 = ctx->launches;
+  PRE3_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+  const int rc = body();
+  cudaGraph_t g = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
+  if (rc != PRE3_OK || e != cudaSuccess || !g) {
+    if (g) cudaGraphDestroy(g);
+    cudaGetLastError();
+    ctx->graph_seen.clear();
+    if (rc != PRE3_OK) return rc;
+    return body();  // not capturable in this state: run eagerly
+  }
+  const cudaError_t ei = cudaGraphInstantiate(&ctx->graph_exec, g, 0);
+  cudaGraphDestroy(g);
+  if (ei != cudaSuccess) {
+    ctx->graph_exec = nullptr;
+    cudaGetLastError();
+    return body();
+  }
+  ctx->graph_key = key;
+  ctx->graph_launches = ctx->launches - l0;
+  PRE3_CUDA(cudaGraphLaunch(ctx->graph_exec, ctx->stream));
+  return PRE3_OK;
+}
+}  // namespace
+
 // ================================================================================================
 // context
 // ================================================================================================
@@ -174,6 +229,7 @@ void pre3_destroy(pre3_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->ws) cudaFree(ctx->ws);
     for (char* r : ctx->retired) cudaFree(r);
+    if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
     if (ctx->d_tab) cudaFree(ctx->d_tab);
     if (ctx->d_tab_rows) cudaFree(ctx->d_tab_rows);
     if (ctx->d_ekf_tab) cudaFree(ctx->d_ekf_tab);
@@ -586,6 +642,19 @@ static int pairs_impl(pre3_ctx* ctx, const void* ddesc1, const void* ddesc2, int
   return ransac_impl(ctx, dYa, dYb, dn, P, K1, o, nullptr, pair_id0, dres, dmasks, nullptr, nullptr, dpairs);
 }
 
+int pre3_set_graphs(pre3_ctx* ctx, int on) {
+  if (!ctx || ctx->device < 0) return PRE3_ERR_CUDA;
+  ctx->graphs = on != 0;
+  if (!ctx->graphs && ctx->graph_exec) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaGraphExecDestroy(ctx->graph_exec);
+    ctx->graph_exec = nullptr;
+    ctx->graph_key.clear();
+    ctx->graph_seen.clear();
+  }
+  return PRE3_OK;
+}
+
 int pre3_pairs_dev(pre3_ctx* ctx, const void* ddesc1, const void* ddesc2, int cls, const double* dxyz1,
                    const double* dxyz2, int P, int K1, int K2, int ND, const int32_t* dk1_count,
                    const int32_t* dk2_count, const pre3_ransac_opts* opts, uint32_t pair_id0, pre3_pair_result* dres,
@@ -595,9 +664,19 @@ int pre3_pairs_dev(pre3_ctx* ctx, const void* ddesc1, const void* ddesc2, int cl
   PRE3_TRY(check_opts(ctx, opts));
   PRE3_NEED(dres && dxyz1 && dxyz2, "null pointer");
   if (P == 0) return PRE3_OK;
-  PRE3_TRY(ws_reserve(ctx, pairs_ws_bytes(cls, P, K1, K2, ND, opts->H)));
-  return pairs_impl(ctx, ddesc1, ddesc2, cls, dxyz1, dxyz2, P, K1, K2, ND, dk1_count, dk2_count, *opts, pair_id0, dres,
-                    dmatches, dmasks);
+  std::vector<unsigned char> key;
+  if (ctx->graphs) {
+    key_put(key, 1);
+    key_put(key, ddesc1); key_put(key, ddesc2); key_put(key, cls); key_put(key, dxyz1); key_put(key, dxyz2);
+    key_put(key, P); key_put(key, K1); key_put(key, K2); key_put(key, ND); key_put(key, dk1_count); key_put(key, dk2_count);
+    key_put(key, *opts); key_put(key, pair_id0); key_put(key, dres); key_put(key, dmatches); key_put(key, dmasks);
+    key_put(key, ctx->stream); key_put(key, ctx->match_engine);
+  }
+  return graph_or_eager(ctx, key, [&]() -> int {
+    PRE3_TRY(ws_reserve(ctx, pairs_ws_bytes(cls, P, K1, K2, ND, opts->H)));
+    return pairs_impl(ctx, ddesc1, ddesc2, cls, dxyz1, dxyz2, P, K1, K2, ND, dk1_count, dk2_count, *opts, pair_id0, dres,
+                      dmatches, dmasks);
+  });
 }
 
 // A SEQUENCE of F frames = F - 1 consecutive pairs (frame p, frame p + 1): what the reference's whole-sequence
@@ -611,9 +690,18 @@ int pre3_sequence_dev(pre3_ctx* ctx, const void* ddesc, int cls, const double* d
   PRE3_TRY(check_opts(ctx, opts));
   PRE3_NEED(F <= 1 || (dres && dxyz), "null pointer");
   if (F <= 1) return PRE3_OK;
-  PRE3_TRY(ws_reserve(ctx, pairs_ws_bytes(cls, F, K, K, ND, opts->H)));
-  return pairs_impl(ctx, ddesc, nullptr, cls, dxyz, nullptr, F - 1, K, K, ND, dk_count, nullptr, *opts, pair_id0, dres,
-                    dmatches, dmasks);
+  std::vector<unsigned char> key;
+  if (ctx->graphs) {
+    key_put(key, 2);
+    key_put(key, ddesc); key_put(key, cls); key_put(key, dxyz); key_put(key, F); key_put(key, K); key_put(key, ND);
+    key_put(key, dk_count); key_put(key, *opts); key_put(key, pair_id0); key_put(key, dres); key_put(key, dmatches);
+    key_put(key, dmasks); key_put(key, ctx->stream); key_put(key, ctx->match_engine);
+  }
+  return graph_or_eager(ctx, key, [&]() -> int {
+    PRE3_TRY(ws_reserve(ctx, pairs_ws_bytes(cls, F, K, K, ND, opts->H)));
+    return pairs_impl(ctx, ddesc, nullptr, cls, dxyz, nullptr, F - 1, K, K, ND, dk_count, nullptr, *opts, pair_id0, dres,
+                      dmatches, dmasks);
+  });
 }
 
 // Host buffers: the P pairs are cut into chunks that are staged on a second stream while the

@@ -69,6 +69,12 @@ struct pre3_ctx {
   char* h_stage[2] = {nullptr, nullptr};
   size_t h_stage_cap = 0;
   cudaEvent_t ev_stage_done[2] = {nullptr, nullptr};
+  // optional CUDA-graph replay of the device-resident whole-pair entry points (pre3_set_graphs): the launch sequence
+  // of one (arguments, sizes, options) signature is captured once and replayed
+  bool graphs = false;
+  cudaGraphExec_t graph_exec = nullptr;
+  std::vector<unsigned char> graph_key, graph_seen;  // signature of the captured graph / of the last eager call
+  int64_t graph_launches = 0;                        // kernel launches one replay stands for
   // optional per-launch CUDA-event timing (off by default)
   bool timing = false;
   std::vector<pre3::TimedSpan> spans;

@@ -661,6 +661,7 @@ def run_ours(args):
     Pl = p1 - p0                         # this rank's block of pairs = frames p0 .. p1
     ctx = pre3.Context(local)
     ctx.use_torch_stream()
+    ctx.set_graphs(True)   # the step repeats one call signature: its launch sequence is captured and replayed
     # the same synthetic sequence on every rank (same seed, generated on the device); a rank keeps its block
     sq = synth.make_sequence_torch(P + 1, SEED, dev, K=K_FEAT, n_corr=N_CORR, outlier_ratio=OUTLIER)
     full = {"desc": sq["desc"], "xyz": sq["xyz"]} if world > 1 else None
@@ -904,7 +905,8 @@ def run_ours(args):
             "config": {"workload": WORKLOAD.format(P=P), "pairs_total": P, "pairs_per_gpu": Pl,
                        "sharding": "by frame pair: rank r takes pairs dist.split_range(P, r, N); the 240-byte records of "
                                    "all pairs are all-gathered to every rank inside the timed region",
-                       "api": "pre3_sequence_dev (value) / pre3_sequence (e2e): pair p = (frame p, frame p+1)",
+                       "api": "pre3_sequence_dev with pre3_set_graphs(1) (value) / pre3_sequence (e2e): pair p = (frame p, "
+                              "frame p+1)",
                        "l2": f"inputs ({desc_bytes / 1e9:.2f} GB of descriptors per GPU) "
                              + ("larger than L2" if desc_bytes > 126e6 else "smaller than L2: at this GPU count the step "
                                 "re-reads them from L2"),

@@ -107,6 +107,11 @@ PRE3_API int pre3_set_match_engine(pre3_ctx *ctx, int engine);
 PRE3_API int pre3_sync(pre3_ctx *ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 PRE3_API int64_t pre3_launch_count(const pre3_ctx *ctx);
+/* CUDA-graph replay of pre3_pairs_dev / pre3_sequence_dev: the launch sequence of a call signature (pointers, sizes,
+ * options) is captured on its second occurrence and replayed afterwards -- one graph launch instead of ~15-20 kernel
+ * launches, for loops that push the same device buffers through the path (streaming ring buffers, a sequence sharded
+ * over several GPUs where a few hundred pairs per call make the step launch-bound).  Off by default. */
+PRE3_API int pre3_set_graphs(pre3_ctx *ctx, int on);
 /* bytes pre3_pairs has moved over PCIe so far (host -> device, device -> host): bench.py's e2e figures.
  * Class-double descriptors whose values all survive (double)(float)x == x -- the reference's descriptors
  * are floats stored in a double matrix, M/sift/siftdescriptor.c:500-527 -- cross as float and are widened

@@ -234,9 +234,17 @@ def test_gateway_compute_hypothesis_support_fast_mex(orc, se):
         sj, lij, _, _ = orc.ekf_support(X[:, j], cam, pattern, z_id.T, z_euc.T, fr.std_z)
         assert s3[0, j] == sj
         np.testing.assert_array_equal(li3[j], lij.astype(bool))
-    # empty z_euc -> [] mask (:112-116)
-    s4, li4, le4 = gw(fr.x.reshape(-1, 1), cam, pattern, z_id, np.zeros((0, 0)), fr.std_z, nout=3)
-    assert le4.size == 0 and s4[0, 0] == int(li0.sum())
+    # no euclidean features: empty z_euc -> [] mask (:112-116)
+    b2 = se.make_ekf_frames(1, 5001, n_id=20, n_euc=0)
+    f2 = se.frame(b2, 0)
+    p2, zi2, ze2 = rne.generate_state_vector_pattern(f2.type, f2.has_z, f2.z, f2.n)
+    s4, li4, le4 = gw(f2.x.reshape(-1, 1), cam, p2, zi2, np.zeros((0, 0)), f2.std_z, nout=3)
+    s5, li5, _, _ = orc.ekf_support(f2.x, cam, p2, zi2.T, ze2.T, f2.std_z)
+    assert le4.size == 0 and s4[0, 0] == s5
+    np.testing.assert_array_equal(li4.ravel(), li5.astype(bool))
+    # a pattern with euclidean features but no euclidean measurements is the reference's reshape error
+    with pytest.raises(refmex.MexError, match="reshape"):
+        gw(fr.x.reshape(-1, 1), cam, pattern, z_id, np.zeros((0, 0)), fr.std_z, nout=1)
     with pytest.raises(refmex.MexError, match="cam"):
         gw(fr.x.reshape(-1, 1), 1.0, pattern, z_id, z_euc, fr.std_z, nout=1)
     with pytest.raises(refmex.MexError, match="missing"):

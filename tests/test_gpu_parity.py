@@ -411,6 +411,51 @@ def test_sequence_equals_pairs(ctx, orc, synth, pre3, cls, engine):
         ctx.set_match_engine(0)
 
 
+def test_graph_replay_equals_eager(pre3, synth):
+    """pre3_set_graphs: the captured launch sequence of a repeated pre3_sequence_dev signature gives the same bytes as
+    the eager calls, also after the inputs behind the same pointers changed; a new signature falls back to eager."""
+    import torch
+    ctx = pre3.Context(0)
+    ctx.use_torch_stream()
+    F, K = 33, 256
+    sq = synth.make_sequence_torch(F, 512, "cuda", K=K, n_corr=150)
+    sq2 = synth.make_sequence_torch(F, 513, "cuda", K=K, n_corr=150)
+    opts = pre3.make_opts(H=500, seed=3)
+    P = F - 1
+
+    def run(desc, xyz):
+        r = torch.zeros(P, 240, dtype=torch.uint8, device="cuda")
+        m = torch.zeros(P, K, 2, dtype=torch.int32, device="cuda")
+        k = torch.zeros(P, K, dtype=torch.uint8, device="cuda")
+        ctx.sequence_dev(desc, xyz, opts, r, m, k, pair_id0=7)
+        ctx.sync()
+        return r.cpu().numpy().tobytes(), k.cpu().numpy().tobytes()
+
+    eager1, eager2 = run(sq["desc"], sq["xyz"]), run(sq2["desc"], sq2["xyz"])
+    ctx.set_graphs(True)
+    desc, xyz = sq["desc"].clone(), sq["xyz"].clone()
+    r = torch.zeros(P, 240, dtype=torch.uint8, device="cuda")
+    m = torch.zeros(P, K, 2, dtype=torch.int32, device="cuda")
+    k = torch.zeros(P, K, dtype=torch.uint8, device="cuda")
+    outs = []
+    launches = []
+    for it in range(5):
+        if it == 3:  # new inputs behind the same pointers: the replayed graph must pick them up
+            desc.copy_(sq2["desc"]); xyz.copy_(sq2["xyz"])
+        l0 = ctx.launch_count()
+        ctx.sequence_dev(desc, xyz, opts, r, m, k, pair_id0=7)
+        ctx.sync()
+        launches.append(ctx.launch_count() - l0)
+        outs.append((r.cpu().numpy().tobytes(), k.cpu().numpy().tobytes()))
+    assert outs[0] == outs[1] == outs[2] == eager1 and outs[3] == outs[4] == eager2
+    assert len(set(launches)) == 1 and launches[0] > 5     # a replay stands for the same number of kernel launches
+    # a different signature (other pair_id0) runs eagerly and leaves the cached graph alone
+    ctx.sequence_dev(desc, xyz, opts, r, m, k, pair_id0=8)
+    ctx.sync()
+    ctx.set_graphs(False)
+    ctx.close()
+
+
 def test_matching_full_size_properties(ctx, synth):
     """2k x 2k descriptors: planted matches are found; matching L against itself returns the
     identity with score 0; results are independent of the batch position."""
