@@ -133,7 +133,10 @@ void key_put(std::vector<unsigned char>& k, const T& v) {
 
 template <typename Body>
 int graph_or_eager(pre3_ctx* ctx, const std::vector<unsigned char>& key, Body body) {
-  if (!ctx->graphs || ctx->timing) return body();
+  // the legacy default stream cannot be captured: run eagerly there
+  if (!ctx->graphs || ctx->timing || ctx->stream == nullptr || ctx->stream == cudaStreamLegacy ||
+      ctx->stream == cudaStreamPerThread)
+    return body();
   if (ctx->graph_exec && key == ctx->graph_key) {
     PRE3_CUDA(cudaGraphLaunch(ctx->graph_exec, ctx->stream));
     ctx->launches += ctx->graph_launches;
@@ -149,7 +152,11 @@ int graph_or_eager(pre3_ctx* ctx, const std::vector<unsigned char>& key, Body bo
     ctx->graph_exec = nullptr;
   }
   const int64_t l0 = ctx->launches;
-  PRE3_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+  if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();  // this stream cannot be captured (e.g. it is itself being captured by the caller)
+    ctx->graph_seen.clear();
+    return body();
+  }
   const int rc = body();
   cudaGraph_t g = nullptr;
   const cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);

@@ -622,7 +622,8 @@ struct Prop2 {     // per L1 row: s(j) = a~.b~_j - |b_j|^2/2  (d2(j) = |a|^2 - 2
   int32_t idx;     // argmax column (-1 if none)
 };
 
-// EXP: 0 product; 1 TMA + MMA only (accumulators released unread); 2 TMA + epilogue only (no MMA issued)
+// EXP: 0 product; 1 TMA + MMA only (accumulators released unread); 2 TMA + epilogue only (no MMA issued);
+//      3 TMA + tcgen05.ld only (no MMA, accumulators read into registers but not looked at)
 // EPI: 1 product (selection split over the ALU and FMA pipes); 0 all-ALU selection (3.5 instructions per accumulator)
 template <int EXP, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
@@ -731,7 +732,7 @@ k_tc_gemm_pair(const unsigned char* __restrict__ imgA, const unsigned char* __re
             ++use;
             tc_fence_after();
             const uint32_t d = tmem + (uint32_t)(acc * P2_TILE_N);
-            if (EXP != 2) {
+            if (EXP != 2 && EXP != 3) {
 #pragma unroll
               for (int k = 0; k < ND / 16; ++k) {
                 const uint32_t koff = (uint32_t)((k >> 2) * HALF_BYTES + (k & 3) * 32);
@@ -822,6 +823,10 @@ k_tc_gemm_pair(const unsigned char* __restrict__ imgA, const unsigned char* __re
             }
           }
           if (EXP == 1) continue;
+          if (EXP == 3) {  // timing only: the accumulators reach the registers, no selection
+            m1.x = fmaxf(m1.x, __uint_as_float(buf[c & 1][0] ^ buf[c & 1][31]));
+            continue;
+          }
           if (EPI == 0) {
 #pragma unroll
             for (int i2 = 0; i2 < 16; ++i2) {
@@ -1182,6 +1187,7 @@ int launch_match_tc(pre3_ctx* ctx, const void* dL1, const void* dL2, int cls, in
       case 2: case 3: PRE3_GEMM2(1, 1); break;
       case 4: PRE3_GEMM2(2, 0); break;
       case 5: PRE3_GEMM2(2, 1); break;
+      case 6: case 7: PRE3_GEMM2(3, 1); break;
       default: return fail(ctx, PRE3_ERR_ARG, "PRE3_TC_EXP: ablation not built for the CTA-pair kernel");
     }
 #undef PRE3_GEMM2

@@ -659,6 +659,8 @@ def run_ours(args):
     P = args.pairs                       # pairs of the WHOLE sequence (strong scaling: split over the ranks)
     p0, p1 = pd.split_range(P, rank, world)
     Pl = p1 - p0                         # this rank's block of pairs = frames p0 .. p1
+    # one side stream for the library AND torch / NCCL (the legacy default stream cannot be captured into a graph)
+    torch.cuda.set_stream(torch.cuda.Stream(device=dev))
     ctx = pre3.Context(local)
     ctx.use_torch_stream()
     ctx.set_graphs(True)   # the step repeats one call signature: its launch sequence is captured and replayed

@@ -415,18 +415,19 @@ def test_graph_replay_equals_eager(pre3, synth):
     """pre3_set_graphs: the captured launch sequence of a repeated pre3_sequence_dev signature gives the same bytes as
     the eager calls, also after the inputs behind the same pointers changed; a new signature falls back to eager."""
     import torch
-    ctx = pre3.Context(0)
-    ctx.use_torch_stream()
+    ctx = pre3.Context(0)   # its own (non-default) stream: the legacy default stream cannot be captured
     F, K = 33, 256
     sq = synth.make_sequence_torch(F, 512, "cuda", K=K, n_corr=150)
     sq2 = synth.make_sequence_torch(F, 513, "cuda", K=K, n_corr=150)
     opts = pre3.make_opts(H=500, seed=3)
     P = F - 1
+    torch.cuda.synchronize()
 
     def run(desc, xyz):
         r = torch.zeros(P, 240, dtype=torch.uint8, device="cuda")
         m = torch.zeros(P, K, 2, dtype=torch.int32, device="cuda")
         k = torch.zeros(P, K, dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
         ctx.sequence_dev(desc, xyz, opts, r, m, k, pair_id0=7)
         ctx.sync()
         return r.cpu().numpy().tobytes(), k.cpu().numpy().tobytes()
@@ -437,11 +438,13 @@ def test_graph_replay_equals_eager(pre3, synth):
     r = torch.zeros(P, 240, dtype=torch.uint8, device="cuda")
     m = torch.zeros(P, K, 2, dtype=torch.int32, device="cuda")
     k = torch.zeros(P, K, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
     outs = []
     launches = []
     for it in range(5):
         if it == 3:  # new inputs behind the same pointers: the replayed graph must pick them up
             desc.copy_(sq2["desc"]); xyz.copy_(sq2["xyz"])
+            torch.cuda.synchronize()
         l0 = ctx.launch_count()
         ctx.sequence_dev(desc, xyz, opts, r, m, k, pair_id0=7)
         ctx.sync()
