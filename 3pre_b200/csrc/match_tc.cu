@@ -49,17 +49,19 @@ constexpr int THREADS = 352;                  // 11 warps: 0-3 / 4-7 epilogue, 8
 constexpr int W_EPI0 = 0, W_TMA = 8, W_MMA = 9, W_ALLOC = 10;
 constexpr int SMEM_BYTES = 2 * A_BUF_BYTES + NSTAGE * BLK_BYTES + 256 /*barriers*/ + 4 * BLK * 4 /*norms*/;
 // ---- CTA-pair kernel ----
-constexpr int EXT_BYTES = BLK * 32;           // 4 KB: the ninth K step, [row 128][16 halves], 32-byte swizzle
-constexpr int P2_NSTAGE = 4;                  // B ring: (32 KB main + 4 KB ext) per stage and CTA
-constexpr int P2_STAGE_BYTES = BLK_BYTES + EXT_BYTES;
-constexpr int P2_TILE_N = 256;                // columns per B tile (128 per CTA)
-constexpr int P2_OFF_A = 0;                                   // 2 x 32 KB
-constexpr int P2_OFF_AX = 2 * BLK_BYTES;                      // constant A extension tile
+constexpr int EXT_BYTES = BLK * 32;           // 4 KB: the ninth K step of a 128-row block, [row 128][16 halves]
+constexpr int P2_NSTAGE = 5;                  // B ring
+constexpr int P2_TILE_N = 128;                // columns per B tile (64 per CTA)
+constexpr int P2_BHALF = 64 * 128;            // one K half of a CTA's 64 B rows: 8 KB
+constexpr int P2_BEXT = 64 * 32;              // their K-extension rows: 2 KB
+constexpr int P2_STAGE_BYTES = 2 * P2_BHALF + P2_BEXT;        // 18 KB per stage and CTA
+constexpr int P2_OFF_A = 0;                                   // 2 buffers x 2 row blocks x 32 KB
+constexpr int P2_OFF_AX = 4 * BLK_BYTES;                      // constant A extension tile (4 KB)
 constexpr int P2_OFF_B = P2_OFF_AX + EXT_BYTES;
 constexpr int P2_OFF_BAR = P2_OFF_B + P2_NSTAGE * P2_STAGE_BYTES;
-constexpr int P2_OFF_MERGE = P2_OFF_BAR + 512;
-constexpr int P2_SMEM_BYTES = P2_OFF_MERGE + BLK * 16;
+constexpr int P2_SMEM_BYTES = P2_OFF_BAR + 512;
 static_assert(P2_SMEM_BYTES <= 227 * 1024, "CTA-pair matcher: shared memory");
+static_assert(P2_STAGE_BYTES % 1024 == 0, "B stages must keep the 1024-byte swizzle alignment");
 // exact split of g = -|b|^2/2 over four fp16 slots:  g = 4096 h1 + 4096 h2 + h3 + h4  (A side: 4096, 4096, 1, 1)
 constexpr float EXT_SCALE = 4096.0f;
 constexpr double NORM_MAX = 2.0e8;            // |x|^2 above this does not fit the split -> pair flagged bad (exact kernel)
@@ -533,20 +535,23 @@ k_tc_gemm_top2(const unsigned char* __restrict__ imgA, const unsigned char* __re
 
 // ---------------------------------------------------------------------------------------------
 // k_tc_gemm_pair: the CTA-pair form (cta_group::2).  Cluster = 2 CTAs on one SM pair; unit of work = (pair p,
-// 256-row group g of L1): CTA r of the cluster owns row block 2g + r.  Per B tile of 256 columns CTA r loads the
-// 128 columns 256 j + 128 r (+ their K-extension tile); the leader issues nine M256 x N256 x K16 MMAs that read A and
-// B from BOTH CTAs' shared memory and write a 128 x 256 fp32 accumulator into EACH CTA's tensor memory.
+// 512-row group g of L1): CTA r holds TWO 128-row A tiles (s = 0, 1: row blocks 4g + 2s + r), resident for the whole
+// unit.  Per B tile of 128 columns CTA r loads the 64 columns 128 j + 64 r (+ their K-extension rows); for each s the
+// leader issues nine M256 x N128 x K16 MMAs that read A and B from BOTH CTAs' shared memory and write a 128 x 128 fp32
+// accumulator into EACH CTA's tensor memory (slot = 2 stage + s; four 128-column slots).  Every operand byte crosses
+// L2 -> SM once per 512 rows of L1 (measured: the 256-row form was bound by that stream, not by the MMAs or the
+// selection: 0.227 ms at the 256 x 2048 x 2048 shape with the MMAs and the selection switched off).
 //   barriers (per CTA unless noted):
 //     a_full / b_full    TMA bytes of this CTA landed (expect_tx)
 //     pa_full / pb_full  LEADER only: the peer's relay thread saw the peer's a_full / b_full (remote arrive)
 //     a_empty / b_empty  tcgen05.commit multicast to both CTAs: the MMAs reading the buffer have completed
-//     t_full             tcgen05.commit multicast: accumulator stage ready in both CTAs' tensor memory
-//     t_empty            LEADER only: 16 warp arrivals (8 local, 8 remote): both CTAs drained the stage
+//     t_full[slot]       tcgen05.commit multicast: accumulator slot ready in both CTAs' tensor memory
+//     t_empty[slot]      LEADER only: 8 warp arrivals (4 local, 4 remote): both CTAs' warpgroup s drained the slot
 // ---------------------------------------------------------------------------------------------
 struct PairBarriers {
   uint64_t a_full[2], a_empty[2], pa_full[2];
   uint64_t b_full[P2_NSTAGE], b_empty[P2_NSTAGE], pb_full[P2_NSTAGE];
-  uint64_t t_full[2], t_empty[2];
+  uint64_t t_full[4], t_empty[4];
   uint32_t tmem_base;
 };
 static_assert(sizeof(PairBarriers) <= 512, "PairBarriers");
@@ -565,8 +570,12 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
+// remote arrive.  What it publishes was written by the async proxy (TMA bytes, observed through this CTA's own
+// mbarrier) or read from tensor memory (tcgen05.wait::ld + fence::before_thread_sync): no generic-proxy write has to be
+// made visible, so the default semantics (release at CTA scope, as CUTLASS' ClusterBarrier::arrive) suffice; the
+// cluster-scope release form costs a MEMBAR per arrival (ncu: 10 % of the kernel's stall samples).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // wait with cluster-scope acquire (the phase may have been completed by a thread of the peer CTA); a wait that
 // lasts seconds is a protocol bug: trap instead of hanging the GPU
@@ -613,7 +622,7 @@ __device__ __forceinline__ uint64_t umma_desc_ext(uint32_t saddr, int layout) {
   const uint64_t common = (uint64_t)((saddr >> 4) & 0x3FFFu) | (16ull << 32) | (1ull << 46);
   return layout == 0 ? (common | (1ull << 16) | (6ull << 61)) : (common | (8ull << 16));
 }
-// kind::f16, A = B = F16, D = F32, both K-major, M = 256 (pair), N = 256
+// kind::f16, A = B = F16, D = F32, both K-major, M = 256 (pair), N = 128
 constexpr uint32_t IDESC_PAIR = (1u << 4) | ((uint32_t)(P2_TILE_N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 
 struct Prop2 {     // per L1 row: s(j) = a~.b~_j - |b_j|^2/2  (d2(j) = |a|^2 - 2 s(j)); larger = closer
@@ -635,14 +644,13 @@ k_tc_gemm_pair(const unsigned char* __restrict__ imgA, const unsigned char* __re
   if (base & 1023u) __trap();
   const uint32_t sA = base + P2_OFF_A, sAX = base + P2_OFF_AX, sB = base + P2_OFF_B;
   PairBarriers* bars = reinterpret_cast<PairBarriers*>(smem + P2_OFF_BAR);
-  float4* merge = reinterpret_cast<float4*>(smem + P2_OFF_MERGE);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
   const int nblk = K1p / BLK;               // K1p, K2p are multiples of 256
-  const int groups = nblk / 2;
+  const int groups = (nblk + 3) / 4;        // 512-row groups; the last one may hold only two row blocks (s = 0)
   const int ntile = K2p / P2_TILE_N;
   const long long nunits = (long long)P * groups;
 
@@ -651,8 +659,10 @@ k_tc_gemm_pair(const unsigned char* __restrict__ imgA, const unsigned char* __re
       mbar_init(smem_u32(&bars->a_full[i]), 1);
       mbar_init(smem_u32(&bars->a_empty[i]), 1);
       mbar_init(smem_u32(&bars->pa_full[i]), 1);
+    }
+    for (int i = 0; i < 4; ++i) {
       mbar_init(smem_u32(&bars->t_full[i]), 1);
-      mbar_init(smem_u32(&bars->t_empty[i]), 16);
+      mbar_init(smem_u32(&bars->t_empty[i]), 8);
     }
     for (int i = 0; i < P2_NSTAGE; ++i) {
       mbar_init(smem_u32(&bars->b_full[i]), 1);
@@ -684,24 +694,31 @@ k_tc_gemm_pair(const unsigned char* __restrict__ imgA, const unsigned char* __re
   const uint32_t tmem = bars->tmem_base;
 
   if (warp == W_TMA) {
-    // ===== TMA producer (each CTA loads its own operand halves) ====================================
+    // ===== TMA producer (each CTA loads its own operand parts) =====================================
     if (lane == 0) {
       long long t = 0;
       int uc = 0;
       for (long long u = cluster_id; u < nunits; u += nclusters, ++uc) {
         const int p = (int)(u / groups), g = (int)(u % groups);
+        const int ns = min(2, (nblk - 4 * g) / 2);  // A tiles per CTA in this unit
         const int ab = uc & 1;
         mbar_wait(smem_u32(&bars->a_empty[ab]), ((uc >> 1) & 1) ^ 1);
-        mbar_expect_tx(smem_u32(&bars->a_full[ab]), (uint32_t)BLK_BYTES);
-        tma_bulk_g2s(sA + ab * BLK_BYTES, imgA + ((size_t)p * K1p + (size_t)(2 * g + rank) * BLK) * (ND * 2),
-                     (uint32_t)BLK_BYTES, smem_u32(&bars->a_full[ab]));
+        mbar_expect_tx(smem_u32(&bars->a_full[ab]), (uint32_t)(ns * BLK_BYTES));
+        for (int sidx = 0; sidx < ns; ++sidx)
+          tma_bulk_g2s(sA + (ab * 2 + sidx) * BLK_BYTES,
+                       imgA + ((size_t)p * K1p + (size_t)(4 * g + 2 * sidx + (int)rank) * BLK) * (ND * 2),
+                       (uint32_t)BLK_BYTES, smem_u32(&bars->a_full[ab]));
         for (int j = 0; j < ntile; ++j, ++t) {
           const int st = (int)(t % P2_NSTAGE);
           mbar_wait(smem_u32(&bars->b_empty[st]), (uint32_t)(((t / P2_NSTAGE) & 1) ^ 1));
           mbar_expect_tx(smem_u32(&bars->b_full[st]), (uint32_t)P2_STAGE_BYTES);
-          const size_t brow = (size_t)p * K2p + (size_t)j * P2_TILE_N + (size_t)rank * BLK;
-          tma_bulk_g2s(sB + st * P2_STAGE_BYTES, imgB + brow * (ND * 2), BLK_BYTES, smem_u32(&bars->b_full[st]));
-          tma_bulk_g2s(sB + st * P2_STAGE_BYTES + BLK_BYTES, extB + brow * 32, EXT_BYTES, smem_u32(&bars->b_full[st]));
+          // this CTA's 64 columns: rows 64 rank .. 64 rank + 63 of the 128-row block j of the B image
+          const unsigned char* blk = imgB + ((size_t)p * K2p + (size_t)j * BLK) * (ND * 2) + (size_t)rank * P2_BHALF;
+          const uint32_t dst = sB + st * P2_STAGE_BYTES;
+          tma_bulk_g2s(dst, blk, P2_BHALF, smem_u32(&bars->b_full[st]));                          // K half 0
+          tma_bulk_g2s(dst + P2_BHALF, blk + HALF_BYTES, P2_BHALF, smem_u32(&bars->b_full[st]));  // K half 1
+          tma_bulk_g2s(dst + 2 * P2_BHALF, extB + ((size_t)p * K2p + (size_t)j * BLK) * 32 + (size_t)rank * P2_BEXT,
+                       P2_BEXT, smem_u32(&bars->b_full[st]));
         }
       }
       // tail: the multicast commits that release the last buffers target THIS CTA's barriers too; stay until they
@@ -716,34 +733,43 @@ k_tc_gemm_pair(const unsigned char* __restrict__ imgA, const unsigned char* __re
       int uc = 0;
       if (leader) {
         // ===== MMA issuer (one thread of the leader CTA, for both SMs) ===============================
-        uint32_t use0 = 0, use1 = 0;
+        uint32_t use00 = 0, use01 = 0, use10 = 0, use11 = 0;  // fills of slot (stage, s)
         for (long long u = cluster_id; u < nunits; u += nclusters, ++uc) {
+          const int g = (int)(u % groups);
+          const int ns = min(2, (nblk - 4 * g) / 2);
           const int ab = uc & 1;
           mbar_wait(smem_u32(&bars->a_full[ab]), (uc >> 1) & 1);
           mbar_wait_cl(smem_u32(&bars->pa_full[ab]), (uc >> 1) & 1);
           for (int j = 0; j < ntile; ++j, ++t) {
             const int st = (int)(t % P2_NSTAGE);
-            const int acc = (int)(t & 1);
             const uint32_t ph = (uint32_t)((t / P2_NSTAGE) & 1);
             mbar_wait(smem_u32(&bars->b_full[st]), ph);
             mbar_wait_cl(smem_u32(&bars->pb_full[st]), ph);
-            uint32_t& use = acc == 0 ? use0 : use1;
-            mbar_wait_cl(smem_u32(&bars->t_empty[acc]), (use & 1) ^ 1);
-            ++use;
             tc_fence_after();
-            const uint32_t d = tmem + (uint32_t)(acc * P2_TILE_N);
-            if (EXP != 2 && EXP != 3) {
+            const uint32_t sBst = sB + st * P2_STAGE_BYTES;
 #pragma unroll
-              for (int k = 0; k < ND / 16; ++k) {
-                const uint32_t koff = (uint32_t)((k >> 2) * HALF_BYTES + (k & 3) * 32);
-                tc_mma_f16_2cta(d, umma_desc(sA + ab * BLK_BYTES + koff), umma_desc(sB + st * P2_STAGE_BYTES + koff),
-                                IDESC_PAIR, k > 0 ? 1u : 0u);
+            for (int sidx = 0; sidx < 2; ++sidx) {
+              if (sidx >= ns) break;
+              const int slot = (int)(t & 1) * 2 + sidx;
+              uint32_t& use = (t & 1) ? (sidx ? use11 : use10) : (sidx ? use01 : use00);
+              mbar_wait_cl(smem_u32(&bars->t_empty[slot]), (use & 1) ^ 1);
+              ++use;
+              tc_fence_after();
+              const uint32_t d = tmem + (uint32_t)(slot * P2_TILE_N);
+              if (EXP != 2 && EXP != 3 && EXP != 4) {
+#pragma unroll
+                for (int k = 0; k < ND / 16; ++k) {
+                  const uint32_t koa = (uint32_t)((k >> 2) * HALF_BYTES + (k & 3) * 32);
+                  const uint32_t kob = (uint32_t)((k >> 2) * P2_BHALF + (k & 3) * 32);
+                  tc_mma_f16_2cta(d, umma_desc(sA + (ab * 2 + sidx) * BLK_BYTES + koa), umma_desc(sBst + kob), IDESC_PAIR,
+                                  k > 0 ? 1u : 0u);
+                }
+                tc_mma_f16_2cta(d, umma_desc_ext(sAX, ext_layout), umma_desc_ext(sBst + 2 * P2_BHALF, ext_layout),
+                                IDESC_PAIR, 1u);
               }
-              tc_mma_f16_2cta(d, umma_desc_ext(sAX, ext_layout), umma_desc_ext(sB + st * P2_STAGE_BYTES + BLK_BYTES, ext_layout),
-                              IDESC_PAIR, 1u);
+              tc_commit_mc2(smem_u32(&bars->t_full[slot]));
             }
             tc_commit_mc2(smem_u32(&bars->b_empty[st]));
-            tc_commit_mc2(smem_u32(&bars->t_full[acc]));
           }
           tc_commit_mc2(smem_u32(&bars->a_empty[ab]));
         }
@@ -762,67 +788,90 @@ k_tc_gemm_pair(const unsigned char* __restrict__ imgA, const unsigned char* __re
       }
     }
   } else if (warp < W_TMA) {
-    // ===== epilogue: warpgroup wg takes columns [128 wg, 128 wg + 128) of every tile =================
-    // The selection is bound by the ALU pipe (16 lanes per SM sub-partition: LOP3 / FMNMX issue every other cycle),
-    // not by issue slots, so everything that does not have to be exact is moved to the (idle, full-rate) FMA pipe:
-    // per two accumulators the ALU packs the column into the keys (2 LOP3), takes their maximum (carries the index
-    // exactly), advances the running maximum and the running second (one 3-input max); the pair's minimum and
-    // min(m1, hi) -- which only feed the SECOND best, a value that is bracketed with a margin anyway -- are formed
-    // arithmetically, lo = (k0 + k1) - hi and x = (m1 + hi) - max(m1, hi), as packed FADD2 on two independent chains
-    // (even / odd accumulators), 2 ulp off at most.  2.5 ALU + 1 packed FMA-pipe instruction per accumulator instead
-    // of 3.5 ALU.  The next tile's first tcgen05.ld is issued, and the accumulator stage handed back to the MMA
-    // issuer, as soon as the current tile's last load has landed in registers.
-    const int wg = (warp - W_EPI0) >> 2;
+    // ===== epilogue: warpgroup s owns A tile s of this CTA (row block 4g + 2s + rank) ================
+    // The selection runs on the ALU pipe (LOP3 and the 3-input FMNMX3 issue at half rate, the 2-input FMNMX at full
+    // rate: tools/pipebench.cu); what does not have to be exact is moved to the FMA pipe: per two accumulators the ALU
+    // packs the column into the keys (2 LOP3), takes their maximum (carries the index exactly), advances the running
+    // maximum and the running second (one 3-input max); the pair's minimum and min(m1, hi) -- which only feed the
+    // SECOND best, a value that is bracketed with a margin anyway -- are formed arithmetically, lo = (k0 + k1) - hi and
+    // x = (m1 + hi) - max(m1, hi), as packed FADD2 on two independent chains (even / odd accumulators), 2 ulp off at
+    // most.  The next tile's first tcgen05.ld is issued, and the accumulator slot handed back to the MMA issuer, as
+    // soon as the current tile's last load has landed in registers.
+    const int sidx = (warp - W_EPI0) >> 2;
     const int q = warp & 3;
-    const uint32_t t_empty_leader0 = mapa_u32(smem_u32(&bars->t_empty[0]), 0);
-    const uint32_t t_empty_leader1 = mapa_u32(smem_u32(&bars->t_empty[1]), 0);
+    const uint32_t tel0 = mapa_u32(smem_u32(&bars->t_empty[sidx]), 0);      // the leader's t_empty of (stage 0, s)
+    const uint32_t tel1 = mapa_u32(smem_u32(&bars->t_empty[2 + sidx]), 0);  // (stage 1, s)
     long long t = 0;
-    uint32_t useA = 0, useB = 0;
+    uint32_t use0 = 0, use1 = 0;  // times this warpgroup has waited for its slot of stage 0 / 1
     uint32_t keymask;
     asm volatile("mov.u32 %0, 0xFFFFFF80;" : "=r"(keymask));
-    const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(wg * BLK);
+    const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(sidx * P2_TILE_N);
     uint32_t buf[2][32];
-    auto wait_full = [&](int acc) {
-      uint32_t& use = acc == 0 ? useA : useB;
-      mbar_wait(smem_u32(&bars->t_full[acc]), use & 1);
+    auto wait_full = [&](int stg) {
+      uint32_t& use = stg == 0 ? use0 : use1;
+      mbar_wait(smem_u32(&bars->t_full[stg * 2 + sidx]), use & 1);
       ++use;
       tc_fence_after();
     };
-    auto release = [&](int acc) {
+    auto release = [&](int stg) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (leader) mbar_arrive(smem_u32(&bars->t_empty[acc]));
-        else mbar_arrive_cluster(acc == 0 ? t_empty_leader0 : t_empty_leader1);
+        if (leader) mbar_arrive(smem_u32(&bars->t_empty[stg * 2 + sidx]));
+        else mbar_arrive_cluster(stg == 0 ? tel0 : tel1);
       }
     };
     bool primed = false;
+    // units in which this warpgroup has a tile: all but a trailing half group for s = 1
     for (long long u = cluster_id; u < nunits; u += nclusters) {
       const int p = (int)(u / groups), g = (int)(u % groups);
+      const int ns = min(2, (nblk - 4 * g) / 2);
+      if (sidx >= ns) {  // no A tile for this warpgroup: the issuer skips the slot as well
+        t += ntile;
+        continue;
+      }
+      // does the next unit this warpgroup takes part in exist?  (needed for the prefetch of its first tile)
+      bool next_unit = false;
+      for (long long v = u + nclusters; v < nunits; v += nclusters)
+        if (sidx < min(2, (nblk - 4 * (int)(v % groups)) / 2)) {
+          next_unit = true;
+          break;
+        }
       float2 m1 = make_float2(-INFINITY, -INFINITY), m2 = make_float2(-INFINITY, -INFINITY);  // chains: even / odd columns
       int btA = -1, btB = -1;
       for (int j = 0; j < ntile; ++j, ++t) {
-        const int acc = (int)(t & 1);
+        const int stg = (int)(t & 1);
         if (!primed) {
-          wait_full(acc);
-          if (EXP != 1) tc_ld_32x32(tbase + (uint32_t)(acc * P2_TILE_N), buf[0]);
+          wait_full(stg);
+          if (EXP != 1 && EXP != 4) tc_ld_32x32(tbase + (uint32_t)(stg * 2 * P2_TILE_N), buf[0]);
           primed = true;
         }
         const float2 m1_in = m1;
-        const bool has_next = (j + 1 < ntile) || (u + nclusters < nunits);
+        const bool has_next = (j + 1 < ntile) || next_unit;
 #pragma unroll
-        for (int c = 0; c < BLK / 32; ++c) {
-          if (EXP != 1) tc_ld_wait(buf[c & 1]);
-          if (c + 1 < BLK / 32) {
-            if (EXP != 1) tc_ld_32x32(tbase + (uint32_t)(acc * P2_TILE_N + (c + 1) * 32), buf[(c + 1) & 1]);
+        for (int c = 0; c < P2_TILE_N / 32; ++c) {
+          if (EXP != 1 && EXP != 4) tc_ld_wait(buf[c & 1]);
+          if (c + 1 < P2_TILE_N / 32) {
+            if (EXP != 1 && EXP != 4) tc_ld_32x32(tbase + (uint32_t)(stg * 2 * P2_TILE_N + (c + 1) * 32), buf[(c + 1) & 1]);
           } else {
-            release(acc);  // every accumulator of this stage is in registers
+            release(stg);  // every accumulator of this slot is in registers
             if (has_next) {
-              wait_full(acc ^ 1);
-              if (EXP != 1) tc_ld_32x32(tbase + (uint32_t)((acc ^ 1) * P2_TILE_N), buf[0]);
+              // the next tile of this warpgroup: stage t + 1 when it is in this unit; in the next unit the tile counter
+              // has skipped the units without an s = 1 tile, so its stage is that of the unit's first tile
+              int nstg = stg ^ 1;
+              if (j + 1 >= ntile) {
+                long long tt = t + 1;
+                for (long long v = u + nclusters; v < nunits; v += nclusters) {
+                  if (sidx < min(2, (nblk - 4 * (int)(v % groups)) / 2)) break;
+                  tt += ntile;
+                }
+                nstg = (int)(tt & 1);
+              }
+              wait_full(nstg);
+              if (EXP != 1 && EXP != 4) tc_ld_32x32(tbase + (uint32_t)(nstg * 2 * P2_TILE_N), buf[0]);
             }
           }
-          if (EXP == 1) continue;
+          if (EXP == 1 || EXP == 4) continue;
           if (EXP == 3) {  // timing only: the accumulators reach the registers, no selection
             m1.x = fmaxf(m1.x, __uint_as_float(buf[c & 1][0] ^ buf[c & 1][31]));
             continue;
@@ -830,7 +879,7 @@ k_tc_gemm_pair(const unsigned char* __restrict__ imgA, const unsigned char* __re
           if (EPI == 0) {
 #pragma unroll
             for (int i2 = 0; i2 < 16; ++i2) {
-              uint32_t k0, k1;  // (bits & ~127) | column within the half tile: one LOP3 each
+              uint32_t k0, k1;  // (bits & ~127) | column within the tile: one LOP3 each
               asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(k0) : "r"(buf[c & 1][2 * i2]), "r"(keymask), "r"((uint32_t)(c * 32 + 2 * i2)));
               asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(k1) : "r"(buf[c & 1][2 * i2 + 1]), "r"(keymask), "r"((uint32_t)(c * 32 + 2 * i2 + 1)));
               const float f0 = __uint_as_float(k0), f1 = __uint_as_float(k1);
@@ -863,42 +912,24 @@ k_tc_gemm_pair(const unsigned char* __restrict__ imgA, const unsigned char* __re
         if (m1.x != m1_in.x) btA = j;
         if (m1.y != m1_in.y) btB = j;
       }
-      // merge the chains, then the two column halves of this row block (warpgroup 1 -> warpgroup 0); store the proposal
+      // merge the two chains and store the proposal of this row
       float b1, b2;
       int col;
       {
-        const int cA = btA < 0 ? -1 : btA * P2_TILE_N + wg * BLK + (int)(__float_as_uint(m1.x) & 0x7Fu);
-        const int cB = btB < 0 ? -1 : btB * P2_TILE_N + wg * BLK + (int)(__float_as_uint(m1.y) & 0x7Fu);
+        const int cA = btA < 0 ? -1 : btA * P2_TILE_N + (int)(__float_as_uint(m1.x) & 0x7Fu);
+        const int cB = btB < 0 ? -1 : btB * P2_TILE_N + (int)(__float_as_uint(m1.y) & 0x7Fu);
         if (cB >= 0 && (cA < 0 || m1.y > m1.x || (m1.y == m1.x && cB < cA))) {
           b1 = m1.y, col = cB, b2 = fmaxf(m1.x, fmaxf(m2.x, m2.y));
         } else {
           b1 = m1.x, col = cA, b2 = fmaxf(m1.y, fmaxf(m2.x, m2.y));
         }
       }
-      const int r = q * 32 + lane;
-      if (wg == 1) merge[r] = make_float4(b1, b2, __int_as_float(col), 0.f);
-      named_bar_sync(1, 256);
-      if (wg == 0) {
-        const float4 o = merge[r];
-        int bc = col;
-        const float o1 = o.x, o2 = o.y;
-        const int oc = __float_as_int(o.z);
-        // top-2 of the union; on equal keys the lower column (this half) stays first
-        if (oc >= 0 && (bc < 0 || o1 > b1)) {
-          b2 = fmaxf(b1, o2);
-          b1 = o1;
-          bc = oc;
-        } else {
-          b2 = fmaxf(b2, o1);
-        }
-        const int row = (2 * g + (int)rank) * BLK + r;
-        Prop2 out;
-        out.best = __uint_as_float(__float_as_uint(b1) & 0xFFFFFF80u);
-        out.second = __uint_as_float(__float_as_uint(b2) & 0xFFFFFF80u);
-        out.idx = bc;
-        prop[(size_t)p * K1p + row] = out;
-      }
-      named_bar_sync(2, 256);  // merge[] is rewritten by the next unit
+      const int row = (4 * g + 2 * sidx + (int)rank) * BLK + q * 32 + lane;
+      Prop2 out;
+      out.best = __uint_as_float(__float_as_uint(b1) & 0xFFFFFF80u);
+      out.second = __uint_as_float(__float_as_uint(b2) & 0xFFFFFF80u);
+      out.idx = col;
+      prop[(size_t)p * K1p + row] = out;
     }
   }
   tc_fence_before();
@@ -1168,7 +1199,7 @@ int launch_match_tc(pre3_ctx* ctx, const void* dL1, const void* dL2, int cls, in
   if (!use_v1) {
     // CTA pairs: one 2-CTA cluster per SM pair, unit = (pair, 256-row group)
     Span span__(ctx, T_MATCH_TC);
-    const long long units = (long long)P * (K1p / 256);
+    const long long units = (long long)P * ((K1p / BLK + 3) / 4);
     const int grid = 2 * (int)std::min<long long>(units, ctx->sm_count / 2);
 #define PRE3_GEMM2(E, EP)                                                                                            \
   do {                                                                                                             \
@@ -1188,6 +1219,7 @@ int launch_match_tc(pre3_ctx* ctx, const void* dL1, const void* dL2, int cls, in
       case 4: PRE3_GEMM2(2, 0); break;
       case 5: PRE3_GEMM2(2, 1); break;
       case 6: case 7: PRE3_GEMM2(3, 1); break;
+      case 8: case 9: PRE3_GEMM2(4, 1); break;
       default: return fail(ctx, PRE3_ERR_ARG, "PRE3_TC_EXP: ablation not built for the CTA-pair kernel");
     }
 #undef PRE3_GEMM2
