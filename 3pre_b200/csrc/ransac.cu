@@ -20,7 +20,7 @@ namespace pre3 {
 
 constexpr int EV_THREADS = 128;
 constexpr int EV_TILE = 512;
-constexpr int EV_LIST = 1024;
+constexpr int EV_LIST = 1024;  // borderline list entries per block (hypothesis id in 8 bits: blocks of <= 256)
 constexpr int SEL_THREADS = 256;
 constexpr int MAX_K = 8;
 
@@ -162,6 +162,196 @@ __device__ __forceinline__ float2 fmul2(float2 a, float2 b) { return __fmul2_rn(
 // 32 packed FMA-pipe instructions + ~9 for the count (sign bit of r^2 - thr^2) and the borderline test (one
 // rarely-taken branch).  Measured against the scalar loop of round 1 and three other mappings in tools/evalbench.cu
 // (B200, N = 20 000): 1.76 vs 1.22 T evals/s (2 hypotheses x 1 match 1.55, 4 hypotheses x 1 match 1.68).
+struct EvalHyp {     // what the scorer keeps of one hypothesis
+  float2 cf[12];     // R (row-major) and t, each duplicated
+  float2 nthr;       // -thr^2 (twice); +1 when the hypothesis is not scored
+  float delta;       // certified fp32 error band around thr^2; -1 when not scored
+  int state;
+  bool scored, exact_me;
+};
+
+// sample set -> fit (registers) -> fp64 (R, t) into sRt_row[12], fp32 copies + error band into hy
+template <int K, int MODE>
+__device__ __forceinline__ void eval_fit(const PairMeta& m, const double* __restrict__ ya, const double* __restrict__ yb,
+                                         bool valid, int p, int h, const int32_t* __restrict__ samples, uint64_t seed,
+                                         uint32_t pair_id0, long long h0, int H, const double* __restrict__ Rin,
+                                         const double* __restrict__ Tin, double* __restrict__ sRt_row, EvalHyp& hy) {
+  const int N = m.N;
+  hy.state = 0;
+  hy.exact_me = false;
+  Rigid fit;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) fit.R[i] = 0.0;
+  fit.t[0] = fit.t[1] = fit.t[2] = 0.0;
+  if (valid) {
+    if (MODE == 2) {
+      const double* r = Rin + ((size_t)p * H + h) * 9;
+      const double* t = Tin + ((size_t)p * H + h) * 3;
+#pragma unroll
+      for (int rr = 0; rr < 3; ++rr)
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) fit.R[3 * rr + cc] = r[3 * cc + rr];
+      fit.t[0] = t[0];
+      fit.t[1] = t[1];
+      fit.t[2] = t[2];
+      hy.state = 1;
+    } else {
+      int idx[K > 0 ? K : 1];
+      if (samples) {
+        const int32_t* s = samples + ((size_t)p * H + h) * K;
+#pragma unroll
+        for (int i = 0; i < K; ++i) idx[i] = min(max(s[i], 0), N - 1);
+      } else {
+        sample_set<K>(seed, pair_id0 + (uint32_t)p, (uint32_t)(h0 + h), N, K, idx);
+      }
+      double pa[K > 0 ? K : 1][3], pb[K > 0 ? K : 1][3];
+#pragma unroll
+      for (int i = 0; i < K; ++i)
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          pa[i][r] = ya[3 * idx[i] + r];
+          pb[i][r] = yb[3 * idx[i] + r];
+        }
+      auto get = [&](int i, double* a, double* b) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          a[r] = pa[i][r];
+          b[r] = pb[i][r];
+        }
+      };
+      if (MODE == 0 || MODE == 3)
+        hy.state = fit_kabsch<K>(K, get, fit);
+      else
+        hy.state = fit_horn<K>(K, get, fit);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 9; ++i) sRt_row[i] = fit.R[i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) sRt_row[9 + i] = fit.t[i];
+
+  hy.scored = valid && !(MODE == 0 && hy.state == -1);
+  // fp32 copies and the certified error band
+  float c32[12];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) c32[i] = __double2float_rn(fit.R[i]);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) c32[9 + i] = __double2float_rn(fit.t[i]);
+  float thr2 = m.thr2;
+  {
+    float rmax = 0.f;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) rmax = fmaxf(rmax, __double2float_ru(fabs(fit.R[i])));
+    const float tmax = fmaxf(fabsf(c32[9]), fmaxf(fabsf(c32[10]), fabsf(c32[11]))) * 1.0000002f;
+    // |e32 - e| <= 12 u (Rmax*|yb|_1 + |t| + |ya|): 2u input rounding per product term, u per
+    // fma/sub rounding, generous constant; u = 2^-24.
+    const float bound = rmax * m.y1max + tmax + m.xmax;
+    const float eps = 1.001f * 12.0f * 5.9604645e-8f * bound;
+    const float thrf = MODE == 3 ? __fsqrt_ru(__double2float_ru(m.thr)) : __double2float_ru(m.thr);
+    // |r2_32 - r2| <= eps (2 sqrt(3) r + 3 eps) + 4u r2 near r = thr; doubled for slack.
+    hy.delta = 1.01f * (2.0f * eps * (3.4641018f * thrf + 3.0f * eps) + 8.0f * 5.9604645e-8f * thr2);
+    // a garbage fit (state 0: rot = H) with non-finite or huge entries could produce inf - inf = NaN in the fp32
+    // scorer, whose sign bit means nothing: such a hypothesis is counted in fp64 instead
+    hy.exact_me = hy.scored && !(bound < 1.0e18f);
+  }
+  if (!hy.scored || hy.exact_me) {  // can neither count nor be borderline in the fp32 pass
+    thr2 = -1.0f;
+    hy.delta = -1.0f;
+  }
+#pragma unroll
+  for (int i = 0; i < 12; ++i) hy.cf[i] = make_float2(c32[i], c32[i]);
+  hy.nthr = make_float2(-thr2, -thr2);
+}
+
+// one tile of correspondences -> shared memory, coordinate by coordinate; padded to `cap` with a point no hypothesis
+// can reach (never an inlier, never borderline)
+template <int NT, int TL>
+__device__ __forceinline__ void eval_stage(float (*sM)[TL], const float4* __restrict__ A4,
+                                           const float4* __restrict__ B4, int tn, int cap) {
+  for (int i = threadIdx.x; i < cap; i += NT) {
+    float4 a = make_float4(1.0e9f, 1.0e9f, 1.0e9f, 0.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < tn) {
+      a = A4[i];
+      b = B4[i];
+    }
+    sM[0][i] = b.x, sM[1][i] = b.y, sM[2][i] = b.z, sM[3][i] = -a.x, sM[4][i] = -a.y, sM[5][i] = -a.z;
+  }
+}
+
+// the hot loop: support of one hypothesis over the staged tile (tn correspondences, global index base + i)
+template <int TL, int LIST>
+__device__ __forceinline__ int eval_score_tile(const float (*sM)[TL], int tn, int base, const EvalHyp& hy,
+                                               int hyp_local, uint32_t* sList, int* sListN) {
+  int cnt = 0;
+  const int tn4 = (tn + 3) & ~3;
+  for (int i = 0; i < tn4; i += 4) {
+    const float4 bx = *reinterpret_cast<const float4*>(&sM[0][i]);
+    const float4 by = *reinterpret_cast<const float4*>(&sM[1][i]);
+    const float4 bz = *reinterpret_cast<const float4*>(&sM[2][i]);
+    const float4 nx = *reinterpret_cast<const float4*>(&sM[3][i]);
+    const float4 ny = *reinterpret_cast<const float4*>(&sM[4][i]);
+    const float4 nz = *reinterpret_cast<const float4*>(&sM[5][i]);
+    float2 d[2];
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      const float2 x = g ? make_float2(bx.z, bx.w) : make_float2(bx.x, bx.y);
+      const float2 y = g ? make_float2(by.z, by.w) : make_float2(by.x, by.y);
+      const float2 z = g ? make_float2(bz.z, bz.w) : make_float2(bz.x, bz.y);
+      const float2 px = g ? make_float2(nx.z, nx.w) : make_float2(nx.x, nx.y);
+      const float2 py = g ? make_float2(ny.z, ny.w) : make_float2(ny.x, ny.y);
+      const float2 pz = g ? make_float2(nz.z, nz.w) : make_float2(nz.x, nz.y);
+      const float2 ex = fadd2(ffma2(hy.cf[0], x, ffma2(hy.cf[1], y, ffma2(hy.cf[2], z, hy.cf[9]))), px);
+      const float2 ey = fadd2(ffma2(hy.cf[3], x, ffma2(hy.cf[4], y, ffma2(hy.cf[5], z, hy.cf[10]))), py);
+      const float2 ez = fadd2(ffma2(hy.cf[6], x, ffma2(hy.cf[7], y, ffma2(hy.cf[8], z, hy.cf[11]))), pz);
+      d[g] = fadd2(ffma2(ex, ex, ffma2(ey, ey, fmul2(ez, ez))), hy.nthr);  // r^2 - thr^2
+    }
+    cnt += (int)(__float_as_uint(d[0].x) >> 31) + (int)(__float_as_uint(d[0].y) >> 31) +
+           (int)(__float_as_uint(d[1].x) >> 31) + (int)(__float_as_uint(d[1].y) >> 31);
+    const float mn = fminf(fminf(fabsf(d[0].x), fabsf(d[0].y)), fminf(fabsf(d[1].x), fabsf(d[1].y)));
+    if (mn <= hy.delta) {  // a threshold-borderline residual among the 4: fp64 recheck after the loop
+      const float dd[4] = {d[0].x, d[0].y, d[1].x, d[1].y};
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (fabsf(dd[e]) <= hy.delta) {
+          const int slot = atomicAdd(sListN, 1);
+          if (slot < LIST)
+            sList[slot] = ((uint32_t)hyp_local << 24) | ((dd[e] < 0.f ? 1u : 0u) << 23) | (uint32_t)(base + i + e);
+        }
+    }
+  }
+  return cnt;
+}
+
+// fp64 recheck of the queued borderline residuals (counts become those of the fp64 reference); hypotheses flagged
+// exact_me (or every scored one when the list overflowed) are recounted in fp64.  Call with all NT threads.
+template <int MODE, int NT, int LIST>
+__device__ __forceinline__ void eval_recheck(const PairMeta& m, const double* __restrict__ ya,
+                                             const double* __restrict__ yb, const double* sRt, int* sCnt,
+                                             const uint32_t* sList, const int* sListN, bool scored, bool exact_me) {
+  const int tid = threadIdx.x;
+  __syncthreads();
+  const int nl = *sListN;
+  if (nl > LIST) exact_me = scored;  // too many borderline residuals (degenerate scale)
+  if (nl <= LIST) {
+    for (int it = tid; it < nl; it += NT) {
+      const uint32_t item = sList[it];
+      const int hl = item >> 24;
+      const bool in32 = (item >> 23) & 1u;
+      const int mi = item & 0x7FFFFFu;
+      const bool in64 = exact_inlier<MODE>(&sRt[hl * 12], &sRt[hl * 12 + 9], ya + 3 * mi, yb + 3 * mi, m.thr);
+      if (in64 != in32) atomicAdd(&sCnt[hl], in64 ? 1 : -1);
+    }
+  }
+  __syncthreads();
+  if (exact_me) {
+    int c = 0;
+    for (int i = 0; i < m.N; ++i)
+      c += exact_inlier<MODE>(&sRt[tid * 12], &sRt[tid * 12 + 9], ya + 3 * i, yb + 3 * i, m.thr) ? 1 : 0;
+    sCnt[tid] = c;
+  }
+}
+
+// grid (sample-set blocks, pairs): the fixed-H paths, single large pairs, small adaptive batches (waves)
 template <int K, int MODE>
 __global__ void __launch_bounds__(EV_THREADS, 6)
 k_eval(const PairMeta* __restrict__ meta, const double* __restrict__ Ya, const double* __restrict__ Yb,
@@ -188,171 +378,141 @@ k_eval(const PairMeta* __restrict__ meta, const double* __restrict__ Ya, const d
   if (tid == 0) sListN = 0;
 
   const bool valid = (h < hend) && (MODE == 2 || N >= K) && N > 0;
-  int state = 0;
-  bool scored, exact_me = false;
-  float2 cf[12], nthr;
-  float delta;
-  {
-    Rigid fit;
-#pragma unroll
-    for (int i = 0; i < 9; ++i) fit.R[i] = 0.0;
-    fit.t[0] = fit.t[1] = fit.t[2] = 0.0;
-    if (valid) {
-      if (MODE == 2) {
-        const double* r = Rin + ((size_t)p * H + h) * 9;
-        const double* t = Tin + ((size_t)p * H + h) * 3;
-#pragma unroll
-        for (int rr = 0; rr < 3; ++rr)
-#pragma unroll
-          for (int cc = 0; cc < 3; ++cc) fit.R[3 * rr + cc] = r[3 * cc + rr];
-        fit.t[0] = t[0];
-        fit.t[1] = t[1];
-        fit.t[2] = t[2];
-        state = 1;
-      } else {
-        int idx[K > 0 ? K : 1];
-        if (samples) {
-          const int32_t* s = samples + ((size_t)p * H + h) * K;
-#pragma unroll
-          for (int i = 0; i < K; ++i) idx[i] = min(max(s[i], 0), N - 1);
-        } else {
-          sample_set<K>(seed, pair_id0 + (uint32_t)p, (uint32_t)(h0 + h), N, K, idx);
-        }
-        double pa[K > 0 ? K : 1][3], pb[K > 0 ? K : 1][3];
-#pragma unroll
-        for (int i = 0; i < K; ++i)
-#pragma unroll
-          for (int r = 0; r < 3; ++r) {
-            pa[i][r] = ya[3 * idx[i] + r];
-            pb[i][r] = yb[3 * idx[i] + r];
-          }
-        auto get = [&](int i, double* a, double* b) {
-#pragma unroll
-          for (int r = 0; r < 3; ++r) {
-            a[r] = pa[i][r];
-            b[r] = pb[i][r];
-          }
-        };
-        if (MODE == 0 || MODE == 3)
-          state = fit_kabsch<K>(K, get, fit);
-        else
-          state = fit_horn<K>(K, get, fit);
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < 9; ++i) sRt[tid * 12 + i] = fit.R[i];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) sRt[tid * 12 + 9 + i] = fit.t[i];
-
-    scored = valid && !(MODE == 0 && state == -1);
-    // fp32 copies and the certified error band
-    float c32[12];
-#pragma unroll
-    for (int i = 0; i < 9; ++i) c32[i] = __double2float_rn(fit.R[i]);
-#pragma unroll
-    for (int i = 0; i < 3; ++i) c32[9 + i] = __double2float_rn(fit.t[i]);
-    float thr2 = m.thr2;
-    {
-      float rmax = 0.f;
-#pragma unroll
-      for (int i = 0; i < 9; ++i) rmax = fmaxf(rmax, __double2float_ru(fabs(fit.R[i])));
-      const float tmax = fmaxf(fabsf(c32[9]), fmaxf(fabsf(c32[10]), fabsf(c32[11]))) * 1.0000002f;
-      // |e32 - e| <= 12 u (Rmax*|yb|_1 + |t| + |ya|): 2u input rounding per product term, u per
-      // fma/sub rounding, generous constant; u = 2^-24.
-      const float bound = rmax * m.y1max + tmax + m.xmax;
-      const float eps = 1.001f * 12.0f * 5.9604645e-8f * bound;
-      const float thrf = MODE == 3 ? __fsqrt_ru(__double2float_ru(m.thr)) : __double2float_ru(m.thr);
-      // |r2_32 - r2| <= eps (2 sqrt(3) r + 3 eps) + 4u r2 near r = thr; doubled for slack.
-      delta = 1.01f * (2.0f * eps * (3.4641018f * thrf + 3.0f * eps) + 8.0f * 5.9604645e-8f * thr2);
-      // a garbage fit (state 0: rot = H) with non-finite or huge entries could produce inf - inf = NaN in the fp32
-      // scorer, whose sign bit means nothing: such a hypothesis is counted in fp64 instead
-      exact_me = scored && !(bound < 1.0e18f);
-    }
-    if (!scored || exact_me) {  // can neither count nor be borderline in the fp32 pass
-      thr2 = -1.0f;
-      delta = -1.0f;
-    }
-#pragma unroll
-    for (int i = 0; i < 12; ++i) cf[i] = make_float2(c32[i], c32[i]);
-    nthr = make_float2(-thr2, -thr2);
-  }
-
+  EvalHyp hy;
+  eval_fit<K, MODE>(m, ya, yb, valid, p, h, samples, seed, pair_id0, h0, H, Rin, Tin, &sRt[tid * 12], hy);
   int cnt = 0;
   for (int base = 0; base < N; base += EV_TILE) {
     const int tn = min(EV_TILE, N - base);
     __syncthreads();
-    for (int i = tid; i < EV_TILE; i += EV_THREADS) {
-      // padding: a point no hypothesis can reach (never an inlier, never borderline)
-      float4 a = make_float4(1.0e9f, 1.0e9f, 1.0e9f, 0.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (i < tn) {
-        a = Ya4[(size_t)p * Nmax + base + i];
-        b = Yb4[(size_t)p * Nmax + base + i];
-      }
-      sM[0][i] = b.x, sM[1][i] = b.y, sM[2][i] = b.z, sM[3][i] = -a.x, sM[4][i] = -a.y, sM[5][i] = -a.z;
-    }
+    eval_stage<EV_THREADS, EV_TILE>(sM, Ya4 + (size_t)p * Nmax + base, Yb4 + (size_t)p * Nmax + base, tn, (tn + 3) & ~3);
     __syncthreads();
-    const int tn4 = (tn + 3) & ~3;
-    for (int i = 0; i < tn4; i += 4) {
-      const float4 bx = *reinterpret_cast<const float4*>(&sM[0][i]);
-      const float4 by = *reinterpret_cast<const float4*>(&sM[1][i]);
-      const float4 bz = *reinterpret_cast<const float4*>(&sM[2][i]);
-      const float4 nx = *reinterpret_cast<const float4*>(&sM[3][i]);
-      const float4 ny = *reinterpret_cast<const float4*>(&sM[4][i]);
-      const float4 nz = *reinterpret_cast<const float4*>(&sM[5][i]);
-      float2 d[2];
-#pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        const float2 x = g ? make_float2(bx.z, bx.w) : make_float2(bx.x, bx.y);
-        const float2 y = g ? make_float2(by.z, by.w) : make_float2(by.x, by.y);
-        const float2 z = g ? make_float2(bz.z, bz.w) : make_float2(bz.x, bz.y);
-        const float2 px = g ? make_float2(nx.z, nx.w) : make_float2(nx.x, nx.y);
-        const float2 py = g ? make_float2(ny.z, ny.w) : make_float2(ny.x, ny.y);
-        const float2 pz = g ? make_float2(nz.z, nz.w) : make_float2(nz.x, nz.y);
-        const float2 ex = fadd2(ffma2(cf[0], x, ffma2(cf[1], y, ffma2(cf[2], z, cf[9]))), px);
-        const float2 ey = fadd2(ffma2(cf[3], x, ffma2(cf[4], y, ffma2(cf[5], z, cf[10]))), py);
-        const float2 ez = fadd2(ffma2(cf[6], x, ffma2(cf[7], y, ffma2(cf[8], z, cf[11]))), pz);
-        d[g] = fadd2(ffma2(ex, ex, ffma2(ey, ey, fmul2(ez, ez))), nthr);  // r^2 - thr^2
-      }
-      cnt += (int)(__float_as_uint(d[0].x) >> 31) + (int)(__float_as_uint(d[0].y) >> 31) +
-             (int)(__float_as_uint(d[1].x) >> 31) + (int)(__float_as_uint(d[1].y) >> 31);
-      const float mn = fminf(fminf(fabsf(d[0].x), fabsf(d[0].y)), fminf(fabsf(d[1].x), fabsf(d[1].y)));
-      if (mn <= delta) {  // a threshold-borderline residual among the 4: fp64 recheck after the loop
-        const float dd[4] = {d[0].x, d[0].y, d[1].x, d[1].y};
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-          if (fabsf(dd[e]) <= delta) {
-            const int slot = atomicAdd(&sListN, 1);
-            if (slot < EV_LIST)
-              sList[slot] = ((uint32_t)tid << 24) | ((dd[e] < 0.f ? 1u : 0u) << 23) | (uint32_t)(base + i + e);
-          }
-      }
-    }
+    cnt += eval_score_tile<EV_TILE, EV_LIST>(sM, tn, base, hy, tid, sList, &sListN);
   }
   sCnt[tid] = cnt;
-  __syncthreads();
-  const int nl = sListN;
-  if (nl > EV_LIST) exact_me = scored;  // too many borderline residuals (degenerate scale): fp64 recount for the block
-  if (nl <= EV_LIST) {
-    for (int it = tid; it < nl; it += EV_THREADS) {
-      const uint32_t item = sList[it];
-      const int hl = item >> 24;
-      const bool in32 = (item >> 23) & 1u;
-      const int mi = item & 0x7FFFFFu;
-      const bool in64 = exact_inlier<MODE>(&sRt[hl * 12], &sRt[hl * 12 + 9], ya + 3 * mi, yb + 3 * mi, m.thr);
-      if (in64 != in32) atomicAdd(&sCnt[hl], in64 ? 1 : -1);
-    }
-  }
-  __syncthreads();
-  if (exact_me) {
-    int c = 0;
-    for (int i = 0; i < N; ++i)
-      c += exact_inlier<MODE>(&sRt[tid * 12], &sRt[tid * 12 + 9], ya + 3 * i, yb + 3 * i, m.thr) ? 1 : 0;
-    sCnt[tid] = c;
-  }
+  eval_recheck<MODE, EV_THREADS, EV_LIST>(m, ya, yb, sRt, sCnt, sList, &sListN, hy.scored, hy.exact_me);
   if (h < hend) {
-    counts[(size_t)p * H + h] = scored ? sCnt[tid] : -1;
-    if (states) states[(size_t)p * H + h] = (int8_t)state;
+    counts[(size_t)p * H + h] = hy.scored ? sCnt[tid] : -1;
+    if (states) states[(size_t)p * H + h] = (int8_t)hy.state;
   }
+}
+
+// One block per PAIR, adaptive stop: the block walks the pair's sample sets in chunks of EVP_THREADS, and after every
+// chunk replays the reference's loop control (RANSAC_CALC_VER2.m:86, :97-99, :137-140) over the chunk's cardinalities
+// with the running (recorded hypotheses, max cardinality) carried from the chunks before; it ends with the chunk in
+// which the reference's loop ends.  No waves, no per-wave stop kernel, and the work follows the reference's own
+// iteration count to within one chunk (the wave schedule of round 1 evaluated 1.34x the sample sets the loop needs).
+// Entries beyond the last chunk are never written: k_sel_scan finds the same stop index and reads nothing past it.
+constexpr int EVP_THREADS = 64;
+constexpr int EVP_TILE = 384;   // a whole SR4000 pair (~300 matches) in one tile: staged once per block
+constexpr int EVP_LIST = 256;
+
+template <int K, int MODE>
+__global__ void __launch_bounds__(EVP_THREADS, 10)
+k_eval_pairloop(const PairMeta* __restrict__ meta, const double* __restrict__ Ya, const double* __restrict__ Yb,
+                const float4* __restrict__ Ya4, const float4* __restrict__ Yb4, int Nmax,
+                const int32_t* __restrict__ samples, uint64_t seed, uint32_t pair_id0, int H, int method,
+                int max_iteration, const int32_t* __restrict__ tab, int32_t* __restrict__ counts,
+                int8_t* __restrict__ states, int32_t* __restrict__ evaluated) {
+  __shared__ __align__(16) float sM[6][EVP_TILE];
+  __shared__ double sRt[EVP_THREADS * 12];
+  __shared__ int sCnt[EVP_THREADS];
+  __shared__ int sState[EVP_THREADS];
+  __shared__ uint32_t sList[EVP_LIST];
+  __shared__ int sListN, sStop;
+
+  const int p = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const PairMeta m = meta[p];
+  const int N = m.N;
+  const double* ya = Ya + (size_t)p * Nmax * 3;
+  const double* yb = Yb + (size_t)p * Nmax * 3;
+  const int32_t* trow = tab + m.pad;
+  if (N < K || N <= 0) {  // get_rand(k, N) errors in the reference: k_sel_scan reports it, nothing to evaluate
+    if (tid == 0 && evaluated) evaluated[p] = 0;
+    return;
+  }
+  const bool one_tile = N <= EVP_TILE;
+  if (one_tile) eval_stage<EVP_THREADS, EVP_TILE>(sM, Ya4 + (size_t)p * Nmax, Yb4 + (size_t)p * Nmax, N, (N + 3) & ~3);
+  int car_c = 0, car_m = 0;  // recorded hypotheses / max cardinality over the chunks before
+  int hdone = 0;
+  for (int hbeg = 0; hbeg < H; hbeg += EVP_THREADS) {
+    const int h = hbeg + tid;
+    if (tid == 0) sListN = 0;
+    const bool valid = h < H;
+    EvalHyp hy;
+    eval_fit<K, MODE>(m, ya, yb, valid, p, h, samples, seed, pair_id0, 0, H, nullptr, nullptr, &sRt[tid * 12], hy);
+    int cnt = 0;
+    if (one_tile) {
+      __syncthreads();  // staged tile / list counter visible
+      cnt = eval_score_tile<EVP_TILE, EVP_LIST>(sM, N, 0, hy, tid, sList, &sListN);
+    } else {
+      for (int base = 0; base < N; base += EVP_TILE) {
+        const int tn = min(EVP_TILE, N - base);
+        __syncthreads();
+        eval_stage<EVP_THREADS, EVP_TILE>(sM, Ya4 + (size_t)p * Nmax + base, Yb4 + (size_t)p * Nmax + base, tn, (tn + 3) & ~3);
+        __syncthreads();
+        cnt += eval_score_tile<EVP_TILE, EVP_LIST>(sM, tn, base, hy, tid, sList, &sListN);
+      }
+    }
+    sCnt[tid] = cnt;
+    eval_recheck<MODE, EVP_THREADS, EVP_LIST>(m, ya, yb, sRt, sCnt, sList, &sListN, hy.scored, hy.exact_me);
+    const int c = hy.scored ? sCnt[tid] : -1;
+    if (h < H) {
+      counts[(size_t)p * H + h] = c;
+      states[(size_t)p * H + h] = (int8_t)hy.state;
+    }
+    sState[tid] = (h < H && !(method == PRE3_METHOD_SVD && hy.state == -1)) ? 1 : 0;  // recorded by the reference's loop
+    sCnt[tid] = c;
+    __syncthreads();
+    // loop control over this chunk: warp 0, two sample sets per lane, in order
+    if (tid < 32) {
+      const int s0 = 2 * lane, s1 = 2 * lane + 1;
+      const int r0 = sState[s0], r1 = sState[s1];
+      const int c0 = r0 ? sCnt[s0] : 0, c1 = r1 ? sCnt[s1] : 0;
+      int pc = r0 + r1, pm = max(c0, c1);
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int cc = __shfl_up_sync(0xffffffffu, pc, off);
+        const int mm = __shfl_up_sync(0xffffffffu, pm, off);
+        if (lane >= off) {
+          pc += cc;
+          pm = max(pm, mm);
+        }
+      }
+      const int tot_c = __shfl_sync(0xffffffffu, pc, 31), tot_m = __shfl_sync(0xffffffffu, pm, 31);
+      pc = __shfl_up_sync(0xffffffffu, pc, 1);
+      pm = __shfl_up_sync(0xffffffffu, pm, 1);
+      if (lane == 0) {
+        pc = 0;
+        pm = 0;
+      }
+      pc += car_c;
+      pm = max(pm, car_m);
+      int my_stop = 0x7fffffff;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int sl = 2 * lane + e;
+        if (hbeg + sl < H && my_stop == 0x7fffffff) {
+          int nit = max_iteration;
+          if (pm >= 5) nit = min(trow[min(pm, N)], max_iteration);
+          if (!(1 + pc < nit)) my_stop = hbeg + sl;
+          if (e == 0 && r0) {
+            ++pc;
+            pm = max(pm, c0);
+          }
+        }
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) my_stop = min(my_stop, __shfl_xor_sync(0xffffffffu, my_stop, off));
+      if (lane == 0) sStop = my_stop;
+      car_c += tot_c;
+      car_m = max(car_m, tot_m);
+    }
+    __syncthreads();
+    hdone = min(H, hbeg + EVP_THREADS);
+    if (sStop != 0x7fffffff) break;
+  }
+  if (tid == 0 && evaluated) evaluated[p] = hdone;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1845,23 +2005,36 @@ int launch_eval(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts& o
   return fail(ctx, PRE3_ERR_ARG, "unknown RANSAC method");
 }
 
-// Hypothesis evaluation in waves when the reference's adaptive stop is on: after each wave a
-// scan decides per pair whether its loop has already ended (typically within the first 256
-// sample sets at SR4000 inlier ratios); later waves skip those pairs.  Entries that are never
-// evaluated stay zeroed and lie beyond the stop index, so k_select never reads them.
-// Wave boundaries of launch_eval_waves: ends[i] = number of sample sets evaluated after wave i.
-int eval_wave_ends(const pre3_ransac_opts& o, int32_t* ends, int cap) {
+// Adaptive stop on: batches of pairs run k_eval_pairloop (one block per pair, the reference's loop control inside the
+// kernel, chunks of EVP_THREADS sample sets); a FEW pairs (one pair cannot fill the machine with one block) are
+// evaluated in waves over all SMs, with a scan between waves that drops the pairs whose loop has ended.
+constexpr int PAIRLOOP_MIN_P = 64;
+
+static bool use_pairloop(const RansacBuffers& b, const pre3_ransac_opts& o) {
+  return o.adaptive && b.P >= PAIRLOOP_MIN_P && b.tab.tab != nullptr && o.k >= 3 && o.k <= 8;
+}
+
+// Boundaries of the evaluation schedule: ends[i] = number of sample sets evaluated once step i is done (a pair whose
+// loop ends inside step i has had ends[i] sets evaluated).  P: pairs in the call (<= 0: a large batch).
+int eval_wave_ends(const pre3_ransac_opts& o, int32_t* ends, int cap, int P) {
   const int H = o.H;
   int n = 0;
   if (H <= 0) return 0;
+  if (o.adaptive && (P <= 0 || P >= PAIRLOOP_MIN_P)) {
+    for (int e = EVP_THREADS; ; e += EVP_THREADS) {
+      if (n < cap) ends[n] = std::min(e, H);
+      ++n;
+      if (e >= H) break;
+    }
+    return n;
+  }
   if (!o.adaptive || H <= 384) {
     if (n < cap) ends[n] = H;
     return 1;
   }
   // The reference's loop ends after 5*ceil(log(0.01)/log(1-w^k)) recorded hypotheses once a sample whose support is the
-  // fraction w of the matches has been seen: ~215 at the SR4000 shapes of the bench (w ~ 0.63, k = 5).  First wave 256,
-  // then doubling (measured: a 192-wide first wave sends most pairs into a second wave, eval 0.44 -> 0.60 ms; finer
-  // waves 256/384/512/... measured equal or slower).
+  // fraction w of the matches has been seen: ~190 at the SR4000 shapes of the bench (w ~ 0.65, k = 5).  First wave 256,
+  // then doubling.
   int beg = 0, width = 256;
   while (beg < H) {
     int end = std::min(H, beg + width);
@@ -1874,11 +2047,39 @@ int eval_wave_ends(const pre3_ransac_opts& o, int32_t* ends, int cap) {
   return n;
 }
 
+template <int MODE>
+static int launch_eval_pairloop_mode(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts& o) {
+  Span span__(ctx, T_EVAL);
+#define PRE3_EVALP(KK)                                                                                          \
+  k_eval_pairloop<KK, MODE><<<b.P, EVP_THREADS, 0, ctx->stream>>>(b.meta, b.Ya, b.Yb, b.Ya4, b.Yb4, b.Nmax,     \
+                                                                  b.samples, o.seed, b.pair_id0, o.H, o.method, \
+                                                                  o.max_iteration, b.tab.tab, b.counts,         \
+                                                                  b.states, b.stop)
+  switch (o.k) {
+    case 3: PRE3_EVALP(3); break;
+    case 4: PRE3_EVALP(4); break;
+    case 5: PRE3_EVALP(5); break;
+    case 6: PRE3_EVALP(6); break;
+    case 7: PRE3_EVALP(7); break;
+    case 8: PRE3_EVALP(8); break;
+    default: return fail(ctx, PRE3_ERR_ARG, "minimal sample size k must be in 3..8");
+  }
+#undef PRE3_EVALP
+  count_launch(ctx);
+  PRE3_CUDA(cudaGetLastError());
+  return PRE3_OK;
+}
+
 int launch_eval_waves(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts& o) {
   if (b.P <= 0 || o.H <= 0) return PRE3_OK;
   const int H = o.H;
+  if (use_pairloop(b, o)) {
+    if (o.method == PRE3_METHOD_SVD) return launch_eval_pairloop_mode<0>(ctx, b, o);
+    if (o.method == PRE3_METHOD_HORN) return launch_eval_pairloop_mode<1>(ctx, b, o);
+    return fail(ctx, PRE3_ERR_ARG, "unknown RANSAC method");
+  }
   int32_t ends[40];
-  const int nw = eval_wave_ends(o, ends, 40);
+  const int nw = eval_wave_ends(o, ends, 40, b.P);
   if (nw <= 1) return launch_eval(ctx, b, o, 0, 0, H, nullptr);
   PRE3_CUDA(cudaMemsetAsync(b.counts, 0, sizeof(int32_t) * (size_t)b.P * H, ctx->stream));
   PRE3_CUDA(cudaMemsetAsync(b.states, 0, (size_t)b.P * H, ctx->stream));

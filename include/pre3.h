@@ -117,10 +117,10 @@ PRE3_API int pre3_set_graphs(pre3_ctx *ctx, int on);
  * are floats stored in a double matrix, M/sift/siftdescriptor.c:500-527 -- cross as float and are widened
  * on the device (same arithmetic); PRE3_HOST_F32=0 in the environment turns that off. */
 PRE3_API int pre3_transfer_bytes(const pre3_ctx *ctx, int64_t *h2d, int64_t *d2h);
-/* With the adaptive stop on, the batch entry points evaluate the sample sets of a pair in waves
- * and skip the later waves of pairs whose loop (RANSAC_CALC_VER2.m:86) has already ended.
- * Writes the wave boundaries (sample sets evaluated after wave i) into ends[0..cap) and returns the
- * number of waves: a pair that consumed n sets had ends[min{i : n < ends[i]}] (or H) sets evaluated.
+/* Evaluation schedule of the adaptive-stop paths, for a BATCH of pairs (>= 64 per call: one block per pair walks the
+ * sample sets in chunks of 64 and replays the reference's loop control after every chunk; smaller batches run in waves
+ * over the whole GPU).  Writes the boundaries (sample sets evaluated after step i) into ends[0..cap) and returns their
+ * number: a pair that consumed n sets had ends[min{i : n < ends[i]}] (or H) sets evaluated.
  * bench.py derives the executed hypothesis x match evaluations from this. */
 PRE3_API int pre3_eval_schedule(const pre3_ransac_opts *opts, int32_t *ends, int cap);
 /* Per-kernel CUDA-event timing on the context's stream (off by default; bench.py's roofline
