@@ -112,6 +112,11 @@ int ransac_impl(pre3_ctx* ctx, const double* dYa, const double* dYb, const int32
   }
   PRE3_TRY(ensure_adaptive_table(ctx, o, Nmax, dn_corr, P, &b.tab));
   PRE3_TRY(launch_prep(ctx, b, o, 0));
+  // Selection inside the evaluation kernel (one launch for stages 2-4) is built and parity-green, but measured slower
+  // at the sequence shape (eval + select 0.57 ms separate, 0.73 ms fused per 4096 pairs: 64 threads per pair leave the
+  // fp64 tie sums and the refit too little parallelism); PRE3_FUSED_SELECT=1 switches it on.
+  static const int fuse = getenv("PRE3_FUSED_SELECT") ? atoi(getenv("PRE3_FUSED_SELECT")) : 0;
+  if (!dcounts && !dstates && fuse && ransac_can_fuse_select(b, o)) return launch_eval_select_fused(ctx, b, o, dres, dmasks);
   PRE3_TRY(launch_eval_waves(ctx, b, o));
   PRE3_TRY(launch_select(ctx, b, o, dres, dmasks, dcounts, dstates));
   return PRE3_OK;

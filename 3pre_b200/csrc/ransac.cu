@@ -22,6 +22,9 @@ constexpr int EV_THREADS = 128;
 constexpr int EV_TILE = 512;
 constexpr int EV_LIST = 1024;  // borderline list entries per block (hypothesis id in 8 bits: blocks of <= 256)
 constexpr int SEL_THREADS = 256;
+constexpr int EVP_THREADS = 64;  // k_eval_pairloop: sample sets per chunk = threads per block
+constexpr int EVP_TILE = 384;    // a whole SR4000 pair (~300 matches) in one tile: staged once per block
+constexpr int EVP_LIST = 256;
 constexpr int MAX_K = 8;
 
 // ------------------------------------------------------------------------------------------
@@ -394,125 +397,6 @@ k_eval(const PairMeta* __restrict__ meta, const double* __restrict__ Ya, const d
     counts[(size_t)p * H + h] = hy.scored ? sCnt[tid] : -1;
     if (states) states[(size_t)p * H + h] = (int8_t)hy.state;
   }
-}
-
-// One block per PAIR, adaptive stop: the block walks the pair's sample sets in chunks of EVP_THREADS, and after every
-// chunk replays the reference's loop control (RANSAC_CALC_VER2.m:86, :97-99, :137-140) over the chunk's cardinalities
-// with the running (recorded hypotheses, max cardinality) carried from the chunks before; it ends with the chunk in
-// which the reference's loop ends.  No waves, no per-wave stop kernel, and the work follows the reference's own
-// iteration count to within one chunk (the wave schedule of round 1 evaluated 1.34x the sample sets the loop needs).
-// Entries beyond the last chunk are never written: k_sel_scan finds the same stop index and reads nothing past it.
-constexpr int EVP_THREADS = 64;
-constexpr int EVP_TILE = 384;   // a whole SR4000 pair (~300 matches) in one tile: staged once per block
-constexpr int EVP_LIST = 256;
-
-template <int K, int MODE>
-__global__ void __launch_bounds__(EVP_THREADS, 10)
-k_eval_pairloop(const PairMeta* __restrict__ meta, const double* __restrict__ Ya, const double* __restrict__ Yb,
-                const float4* __restrict__ Ya4, const float4* __restrict__ Yb4, int Nmax,
-                const int32_t* __restrict__ samples, uint64_t seed, uint32_t pair_id0, int H, int method,
-                int max_iteration, const int32_t* __restrict__ tab, int32_t* __restrict__ counts,
-                int8_t* __restrict__ states, int32_t* __restrict__ evaluated) {
-  __shared__ __align__(16) float sM[6][EVP_TILE];
-  __shared__ double sRt[EVP_THREADS * 12];
-  __shared__ int sCnt[EVP_THREADS];
-  __shared__ int sState[EVP_THREADS];
-  __shared__ uint32_t sList[EVP_LIST];
-  __shared__ int sListN, sStop;
-
-  const int p = blockIdx.x;
-  const int tid = threadIdx.x, lane = tid & 31;
-  const PairMeta m = meta[p];
-  const int N = m.N;
-  const double* ya = Ya + (size_t)p * Nmax * 3;
-  const double* yb = Yb + (size_t)p * Nmax * 3;
-  const int32_t* trow = tab + m.pad;
-  if (N < K || N <= 0) {  // get_rand(k, N) errors in the reference: k_sel_scan reports it, nothing to evaluate
-    if (tid == 0 && evaluated) evaluated[p] = 0;
-    return;
-  }
-  const bool one_tile = N <= EVP_TILE;
-  if (one_tile) eval_stage<EVP_THREADS, EVP_TILE>(sM, Ya4 + (size_t)p * Nmax, Yb4 + (size_t)p * Nmax, N, (N + 3) & ~3);
-  int car_c = 0, car_m = 0;  // recorded hypotheses / max cardinality over the chunks before
-  int hdone = 0;
-  for (int hbeg = 0; hbeg < H; hbeg += EVP_THREADS) {
-    const int h = hbeg + tid;
-    if (tid == 0) sListN = 0;
-    const bool valid = h < H;
-    EvalHyp hy;
-    eval_fit<K, MODE>(m, ya, yb, valid, p, h, samples, seed, pair_id0, 0, H, nullptr, nullptr, &sRt[tid * 12], hy);
-    int cnt = 0;
-    if (one_tile) {
-      __syncthreads();  // staged tile / list counter visible
-      cnt = eval_score_tile<EVP_TILE, EVP_LIST>(sM, N, 0, hy, tid, sList, &sListN);
-    } else {
-      for (int base = 0; base < N; base += EVP_TILE) {
-        const int tn = min(EVP_TILE, N - base);
-        __syncthreads();
-        eval_stage<EVP_THREADS, EVP_TILE>(sM, Ya4 + (size_t)p * Nmax + base, Yb4 + (size_t)p * Nmax + base, tn, (tn + 3) & ~3);
-        __syncthreads();
-        cnt += eval_score_tile<EVP_TILE, EVP_LIST>(sM, tn, base, hy, tid, sList, &sListN);
-      }
-    }
-    sCnt[tid] = cnt;
-    eval_recheck<MODE, EVP_THREADS, EVP_LIST>(m, ya, yb, sRt, sCnt, sList, &sListN, hy.scored, hy.exact_me);
-    const int c = hy.scored ? sCnt[tid] : -1;
-    if (h < H) {
-      counts[(size_t)p * H + h] = c;
-      states[(size_t)p * H + h] = (int8_t)hy.state;
-    }
-    sState[tid] = (h < H && !(method == PRE3_METHOD_SVD && hy.state == -1)) ? 1 : 0;  // recorded by the reference's loop
-    sCnt[tid] = c;
-    __syncthreads();
-    // loop control over this chunk: warp 0, two sample sets per lane, in order
-    if (tid < 32) {
-      const int s0 = 2 * lane, s1 = 2 * lane + 1;
-      const int r0 = sState[s0], r1 = sState[s1];
-      const int c0 = r0 ? sCnt[s0] : 0, c1 = r1 ? sCnt[s1] : 0;
-      int pc = r0 + r1, pm = max(c0, c1);
-#pragma unroll
-      for (int off = 1; off < 32; off <<= 1) {
-        const int cc = __shfl_up_sync(0xffffffffu, pc, off);
-        const int mm = __shfl_up_sync(0xffffffffu, pm, off);
-        if (lane >= off) {
-          pc += cc;
-          pm = max(pm, mm);
-        }
-      }
-      const int tot_c = __shfl_sync(0xffffffffu, pc, 31), tot_m = __shfl_sync(0xffffffffu, pm, 31);
-      pc = __shfl_up_sync(0xffffffffu, pc, 1);
-      pm = __shfl_up_sync(0xffffffffu, pm, 1);
-      if (lane == 0) {
-        pc = 0;
-        pm = 0;
-      }
-      pc += car_c;
-      pm = max(pm, car_m);
-      int my_stop = 0x7fffffff;
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int sl = 2 * lane + e;
-        if (hbeg + sl < H && my_stop == 0x7fffffff) {
-          int nit = max_iteration;
-          if (pm >= 5) nit = min(trow[min(pm, N)], max_iteration);
-          if (!(1 + pc < nit)) my_stop = hbeg + sl;
-          if (e == 0 && r0) {
-            ++pc;
-            pm = max(pm, c0);
-          }
-        }
-      }
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) my_stop = min(my_stop, __shfl_xor_sync(0xffffffffu, my_stop, off));
-      if (lane == 0) sStop = my_stop;
-      car_c += tot_c;
-      car_m = max(car_m, tot_m);
-    }
-    __syncthreads();
-    hdone = min(H, hbeg + EVP_THREADS);
-    if (sStop != 0x7fffffff) break;
-  }
-  if (tid == 0 && evaluated) evaluated[p] = hdone;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1237,6 +1121,321 @@ k_sel_final(const PairMeta* __restrict__ meta, const double* __restrict__ Ya, co
     for (int i = 0; i < 3; ++i) out->T_hyp[i] = f.t[i];
   }
 }
+// ------------------------------------------------------------------------------------------
+// Selection of one pair by the block that evaluated it (64 threads): the work of k_sel_scan / k_sel_tie / k_sel_final
+// (RANSAC_CALC_VER2.m:165-175 and the refit :186) without leaving the kernel.  The loop control already gave the stop
+// index S_end, length(M) = n_iter and the max cardinality maxc.  The selection is latency bound (a handful of fp64
+// fits and index-ordered sums per pair); inside the evaluation kernel it overlaps with the scoring of the other pairs
+// resident on the SM.
+//   ties at max cardinality are visited in ascending order, 16 at a time: FOUR lanes per tie rebuild its ErrorSum
+//   (:135, summed strictly in index order; non-inliers add an exact +0.0) with width-4 shuffles;
+//   [C, I] = min(eee1): min ErrorSum among the ties, 10000 for every other recorded hypothesis, first index wins;
+//   winner: hypothesis again, mask, ErrorSum, least-squares refit on the support set by warp 0.
+// scratch: sRt (>= 16 doubles), sCnt / sState (>= 64 ints) of the evaluation phase.
+// ------------------------------------------------------------------------------------------
+__device__ __noinline__ void pairloop_select(const PairMeta& m, const double* __restrict__ ya,
+                                                const double* __restrict__ yb, const int32_t* __restrict__ samples,
+                                                uint64_t seed, uint32_t pair_id0, int H, int k, int method, int p,
+                                                const int32_t* __restrict__ cnt, const int8_t* __restrict__ sts,
+                                                int S_end, int n_iter, int maxc, pre3_pair_result* __restrict__ out,
+                                                uint8_t* __restrict__ mask, int mask_stride, double* sRt, int* sA,
+                                                int* sB) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int N = m.N;
+  __syncthreads();  // counts / states of the last chunk are in global memory, the scratch arrays are free
+  if (n_iter < 1) {  // nothing recorded: M(1).ErrorSum = [] in the reference -> error
+    if (tid == 0) result_init(out, 2, S_end, N, m.thr);
+    for (int i = tid; i < mask_stride; i += EVP_THREADS) mask[i] = 0;
+    return;
+  }
+  auto recorded = [&](int s) { return !(method == PRE3_METHOD_SVD && sts[s] == -1); };
+  // ---- ties in ascending order, 16 per round; running (min ErrorSum, first index) -----------------------------
+  double best_es = INFINITY;
+  int best_s = 0x7fffffff, first_nonmax = 0x7fffffff;
+  int* sTie = sA;          // ties gathered for the current round
+  int* sWarpN = sB;        // per-warp tie counts of a 64-wide scan tile
+  int nt = 0;              // ties waiting in sTie (same value in every thread)
+  const int sub = tid & 3, quad = tid >> 2;
+  auto flush = [&](int n) {  // ErrorSum of sTie[0..n), n <= 16: every thread takes part (full-warp shuffles)
+    const bool live = quad < n;
+    const int s = live ? sTie[quad] : 0;
+    Rigid f;
+    if (live) {  // (no shuffles inside: idle quads skip the fit)
+      int idx[MAX_K];
+      load_sample(samples, seed, pair_id0 + (uint32_t)p, 0, s, H, p, N, k, idx);
+      fit_sample(method, ya, yb, idx, k, f);
+    }
+    double es = 0.0;
+    for (int ib = 0; ib < N; ib += 8) {
+      double v0 = 0.0, v1 = 0.0;
+      const int i0 = ib + sub, i1 = ib + 4 + sub;
+      if (live && i0 < N) {
+        const double nr = residual_norm(f.R, f.t, ya + 3 * i0, yb + 3 * i0);
+        v0 = nr < m.thr ? nr : 0.0;  // sum(normResidu(inliers)) in index order (:135); + 0.0 is exact
+      }
+      if (live && i1 < N) {
+        const double nr = residual_norm(f.R, f.t, ya + 3 * i1, yb + 3 * i1);
+        v1 = nr < m.thr ? nr : 0.0;
+      }
+#pragma unroll
+      for (int l = 0; l < 4; ++l) es = es + __shfl_sync(0xffffffffu, v0, l, 4);
+#pragma unroll
+      for (int l = 0; l < 4; ++l) es = es + __shfl_sync(0xffffffffu, v1, l, 4);
+    }
+    // min over the round (ascending s inside the round: strict < keeps the first), then against the running best
+    double e = live ? es : INFINITY;
+    int si = live ? s : 0x7fffffff;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const double oe = __shfl_xor_sync(0xffffffffu, e, off);
+      const int os = __shfl_xor_sync(0xffffffffu, si, off);
+      if (oe < e || (oe == e && os < si)) {
+        e = oe;
+        si = os;
+      }
+    }
+    __syncthreads();  // sTie has been read by every quad
+    double* sE = sRt;  // [2] per-warp minima
+    if (lane == 0) {
+      sE[warp] = e;
+      sB[32 + warp] = si;
+    }
+    __syncthreads();
+    const double e0 = sE[0], e1 = sE[1];
+    const int i0 = sB[32], i1 = sB[33];
+    double re = e0;
+    int rs = i0;
+    if (e1 < re || (e1 == re && i1 < rs)) {
+      re = e1;
+      rs = i1;
+    }
+    if (re < best_es || (re == best_es && rs < best_s)) {  // earlier rounds hold lower indices
+      best_es = re;
+      best_s = rs;
+    }
+    __syncthreads();  // the scratch is rewritten by the next scan tile
+  };
+  for (int base = 0; base < S_end; base += EVP_THREADS) {
+    const int s = base + tid;
+    const bool rec = s < S_end && recorded(s);
+    const bool is_tie = rec && maxc > 0 && cnt[s] == maxc;
+    if (rec && !is_tie) first_nonmax = min(first_nonmax, s);
+    const unsigned bal = __ballot_sync(0xffffffffu, is_tie);
+    if (lane == 0) sWarpN[warp] = __popc(bal);
+    __syncthreads();
+    const int n0 = sWarpN[0], n1 = sWarpN[1];
+    __syncthreads();
+    // append this tile's ties (ascending) to the round buffer; flush whenever 16 are waiting
+    int off_in_tile = __popc(bal & ((1u << lane) - 1u)) + (warp ? n0 : 0);
+    int remaining = n0 + n1, consumed = 0;
+    while (remaining > 0) {
+      const int take = min(16 - nt, remaining);
+      if (is_tie && off_in_tile >= consumed && off_in_tile < consumed + take) sTie[nt + off_in_tile - consumed] = s;
+      __syncthreads();
+      nt += take;
+      consumed += take;
+      remaining -= take;
+      if (nt == 16) {
+        flush(16);
+        nt = 0;
+      }
+    }
+  }
+  if (nt > 0) flush(nt);
+  // first recorded non-tie over the block
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) first_nonmax = min(first_nonmax, __shfl_xor_sync(0xffffffffu, first_nonmax, off));
+  if (lane == 0) sB[40 + warp] = first_nonmax;
+  __syncthreads();
+  const int fn = min(sB[40], sB[41]);
+  int win = best_s;
+  if (best_s == 0x7fffffff) {
+    win = fn;  // maxc == 0: every entry of eee1 is 10000 -> I = first recorded
+  } else if (fn != 0x7fffffff && (10000.0 < best_es || (10000.0 == best_es && fn < best_s))) {
+    win = fn;
+  }
+  // BestFitIdx: recorded hypotheses up to and including the winner
+  int win_iter = 0;
+  for (int s = tid; s <= win; s += EVP_THREADS) win_iter += recorded(s) ? 1 : 0;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) win_iter += __shfl_xor_sync(0xffffffffu, win_iter, off);
+  if (lane == 0) sB[44 + warp] = win_iter;
+  __syncthreads();
+  win_iter = sB[44] + sB[45];
+  // ---- winner: hypothesis, mask, ErrorSum; refit on the support set (:186) --------------------------
+  for (int i = N + tid; i < mask_stride; i += EVP_THREADS) mask[i] = 0;
+  if (warp != 0) return;
+  int idx[MAX_K];
+  load_sample(samples, seed, pair_id0 + (uint32_t)p, 0, win, H, p, N, k, idx);
+  Rigid f;
+  fit_sample(method, ya, yb, idx, k, f);  // every lane computes the same fit
+  for (int i = lane; i < N; i += 32) mask[i] = residual_norm(f.R, f.t, ya + 3 * i, yb + 3 * i) < m.thr ? 1 : 0;
+  __syncwarp();
+  double es = best_es;
+  if (win != best_s) es = warp_errsum(f.R, f.t, ya, yb, N, m.thr, nullptr, nullptr);
+  Rigid rf;
+  const int st = warp_refit(method, ya, yb, mask, N, rf);
+  if (lane == 0) {
+    out->status = 0;
+    out->state = st;
+    out->best_fit = maxc;
+    out->best_sample = win;
+    out->best_iter = win_iter;
+    out->n_iter = n_iter;
+    out->n_consumed = S_end;
+    out->n_matches = N;
+    out->thr = m.thr;
+    out->error_sum = es;
+    store_colmajor(out->R, rf.R);
+    for (int i = 0; i < 3; ++i) out->T[i] = rf.t[i];
+    store_colmajor(out->R_hyp, f.R);
+    for (int i = 0; i < 3; ++i) out->T_hyp[i] = f.t[i];
+  }
+}
+
+// One block per PAIR, adaptive stop: the block walks the pair's sample sets in chunks of EVP_THREADS, and after every
+// chunk replays the reference's loop control (RANSAC_CALC_VER2.m:86, :97-99, :137-140) over the chunk's cardinalities
+// with the running (recorded hypotheses, max cardinality) carried from the chunks before; it ends with the chunk in
+// which the reference's loop ends.  No waves, no per-wave stop kernel, and the work follows the reference's own
+// iteration count to within one chunk (the wave schedule of round 1 evaluated 1.34x the sample sets the loop needs).
+// Entries beyond the last chunk are never written: k_sel_scan finds the same stop index and reads nothing past it.
+// SELECT: the block also runs the selection of its pair (pairloop_select below) -- no selection kernels.
+template <int K, int MODE, bool SELECT>
+__global__ void __launch_bounds__(EVP_THREADS, 10)
+k_eval_pairloop(const PairMeta* __restrict__ meta, const double* __restrict__ Ya, const double* __restrict__ Yb,
+                const float4* __restrict__ Ya4, const float4* __restrict__ Yb4, int Nmax,
+                const int32_t* __restrict__ samples, uint64_t seed, uint32_t pair_id0, int H, int method,
+                int max_iteration, const int32_t* __restrict__ tab, int32_t* __restrict__ counts,
+                int8_t* __restrict__ states, int32_t* __restrict__ evaluated, pre3_pair_result* __restrict__ res,
+                uint8_t* __restrict__ masks, int mask_stride, uint8_t* __restrict__ mask_scratch) {
+  __shared__ __align__(16) float sM[6][EVP_TILE];
+  __shared__ double sRt[EVP_THREADS * 12];
+  __shared__ int sCnt[EVP_THREADS];
+  __shared__ int sState[EVP_THREADS];
+  __shared__ uint32_t sList[EVP_LIST];
+  __shared__ int sListN, sStop, sSel[3];
+
+  const int p = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const PairMeta m = meta[p];
+  const int N = m.N;
+  const double* ya = Ya + (size_t)p * Nmax * 3;
+  const double* yb = Yb + (size_t)p * Nmax * 3;
+  const int32_t* trow = tab + m.pad;
+  if (N < K || N <= 0) {  // get_rand(k, N) errors in the reference (get_rand.m:39-41): nothing to evaluate
+    if (tid == 0 && evaluated) evaluated[p] = 0;
+    if (SELECT) {
+      if (tid == 0) result_init(res + p, 1, 0, N, m.thr);
+      if (masks)
+        for (int i = tid; i < mask_stride; i += EVP_THREADS) masks[(size_t)p * mask_stride + i] = 0;
+    }
+    return;
+  }
+  const bool one_tile = N <= EVP_TILE;
+  if (one_tile) eval_stage<EVP_THREADS, EVP_TILE>(sM, Ya4 + (size_t)p * Nmax, Yb4 + (size_t)p * Nmax, N, (N + 3) & ~3);
+  int car_c = 0, car_m = 0;  // recorded hypotheses / max cardinality over the chunks before
+  int hdone = 0;
+  for (int hbeg = 0; hbeg < H; hbeg += EVP_THREADS) {
+    const int h = hbeg + tid;
+    if (tid == 0) sListN = 0;
+    const bool valid = h < H;
+    EvalHyp hy;
+    eval_fit<K, MODE>(m, ya, yb, valid, p, h, samples, seed, pair_id0, 0, H, nullptr, nullptr, &sRt[tid * 12], hy);
+    int cnt = 0;
+    if (one_tile) {
+      __syncthreads();  // staged tile / list counter visible
+      cnt = eval_score_tile<EVP_TILE, EVP_LIST>(sM, N, 0, hy, tid, sList, &sListN);
+    } else {
+      for (int base = 0; base < N; base += EVP_TILE) {
+        const int tn = min(EVP_TILE, N - base);
+        __syncthreads();
+        eval_stage<EVP_THREADS, EVP_TILE>(sM, Ya4 + (size_t)p * Nmax + base, Yb4 + (size_t)p * Nmax + base, tn, (tn + 3) & ~3);
+        __syncthreads();
+        cnt += eval_score_tile<EVP_TILE, EVP_LIST>(sM, tn, base, hy, tid, sList, &sListN);
+      }
+    }
+    sCnt[tid] = cnt;
+    eval_recheck<MODE, EVP_THREADS, EVP_LIST>(m, ya, yb, sRt, sCnt, sList, &sListN, hy.scored, hy.exact_me);
+    const int c = hy.scored ? sCnt[tid] : -1;
+    if (h < H) {
+      counts[(size_t)p * H + h] = c;
+      states[(size_t)p * H + h] = (int8_t)hy.state;
+    }
+    sState[tid] = (h < H && !(method == PRE3_METHOD_SVD && hy.state == -1)) ? 1 : 0;  // recorded by the reference's loop
+    sCnt[tid] = c;
+    __syncthreads();
+    // loop control over this chunk: warp 0, two sample sets per lane, in order
+    if (tid < 32) {
+      const int s0 = 2 * lane, s1 = 2 * lane + 1;
+      const int r0 = sState[s0], r1 = sState[s1];
+      const int c0 = r0 ? sCnt[s0] : 0, c1 = r1 ? sCnt[s1] : 0;
+      int pc = r0 + r1, pm = max(c0, c1);
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int cc = __shfl_up_sync(0xffffffffu, pc, off);
+        const int mm = __shfl_up_sync(0xffffffffu, pm, off);
+        if (lane >= off) {
+          pc += cc;
+          pm = max(pm, mm);
+        }
+      }
+      const int tot_c = __shfl_sync(0xffffffffu, pc, 31), tot_m = __shfl_sync(0xffffffffu, pm, 31);
+      pc = __shfl_up_sync(0xffffffffu, pc, 1);
+      pm = __shfl_up_sync(0xffffffffu, pm, 1);
+      if (lane == 0) {
+        pc = 0;
+        pm = 0;
+      }
+      pc += car_c;
+      pm = max(pm, car_m);
+      int my_stop = 0x7fffffff, stop_pc = 0, stop_pm = 0;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int sl = 2 * lane + e;
+        if (hbeg + sl < H && my_stop == 0x7fffffff) {
+          int nit = max_iteration;
+          if (pm >= 5) nit = min(trow[min(pm, N)], max_iteration);
+          if (!(1 + pc < nit)) {
+            my_stop = hbeg + sl;  // the reference's loop condition fails here: recorded count / max cardinality so far
+            stop_pc = pc;
+            stop_pm = pm;
+          }
+          if (e == 0 && r0) {
+            ++pc;
+            pm = max(pm, c0);
+          }
+        }
+      }
+      int first = my_stop;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, off));
+      car_c += tot_c;
+      car_m = max(car_m, tot_m);
+      if (first != 0x7fffffff) {
+        if (my_stop == first) {
+          sSel[0] = first;
+          sSel[1] = stop_pc;
+          sSel[2] = stop_pm;
+        }
+      } else if (lane == 0 && hbeg + EVP_THREADS >= H) {  // ran through every sample set
+        sSel[0] = H;
+        sSel[1] = car_c;
+        sSel[2] = car_m;
+      }
+      if (lane == 0) sStop = first;
+    }
+    __syncthreads();
+    hdone = min(H, hbeg + EVP_THREADS);
+    if (sStop != 0x7fffffff) break;
+  }
+  if (tid == 0 && evaluated) evaluated[p] = hdone;
+  if (SELECT)
+    pairloop_select(m, ya, yb, samples, seed, pair_id0, H, K, method, p, counts + (size_t)p * H, states + (size_t)p * H,
+                    sSel[0], sSel[1], sSel[2], res + p,
+                    masks ? masks + (size_t)p * mask_stride : mask_scratch + (size_t)p * Nmax, masks ? mask_stride : 0,
+                    sRt, sCnt, sState);
+}
+
 // ------------------------------------------------------------------------------------------
 // stage-wise kernels
 // ------------------------------------------------------------------------------------------
@@ -2047,14 +2246,14 @@ int eval_wave_ends(const pre3_ransac_opts& o, int32_t* ends, int cap, int P) {
   return n;
 }
 
-template <int MODE>
-static int launch_eval_pairloop_mode(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts& o) {
+template <int MODE, bool SELECT>
+static int launch_eval_pairloop_mode(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts& o,
+                                     pre3_pair_result* dres, uint8_t* dmasks, uint8_t* scratch) {
   Span span__(ctx, T_EVAL);
-#define PRE3_EVALP(KK)                                                                                          \
-  k_eval_pairloop<KK, MODE><<<b.P, EVP_THREADS, 0, ctx->stream>>>(b.meta, b.Ya, b.Yb, b.Ya4, b.Yb4, b.Nmax,     \
-                                                                  b.samples, o.seed, b.pair_id0, o.H, o.method, \
-                                                                  o.max_iteration, b.tab.tab, b.counts,         \
-                                                                  b.states, b.stop)
+#define PRE3_EVALP(KK)                                                                                             \
+  k_eval_pairloop<KK, MODE, SELECT><<<b.P, EVP_THREADS, 0, ctx->stream>>>(                                          \
+      b.meta, b.Ya, b.Yb, b.Ya4, b.Yb4, b.Nmax, b.samples, o.seed, b.pair_id0, o.H, o.method, o.max_iteration,     \
+      b.tab.tab, b.counts, b.states, b.stop, dres, dmasks, b.Nmax, scratch)
   switch (o.k) {
     case 3: PRE3_EVALP(3); break;
     case 4: PRE3_EVALP(4); break;
@@ -2070,12 +2269,24 @@ static int launch_eval_pairloop_mode(pre3_ctx* ctx, const RansacBuffers& b, cons
   return PRE3_OK;
 }
 
+// evaluation AND selection of a batch of pairs in one launch (adaptive stop, >= PAIRLOOP_MIN_P pairs)
+bool ransac_can_fuse_select(const RansacBuffers& b, const pre3_ransac_opts& o) { return use_pairloop(b, o); }
+
+int launch_eval_select_fused(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts& o, pre3_pair_result* dres,
+                             uint8_t* dmasks) {
+  if (b.P <= 0) return PRE3_OK;
+  uint8_t* scratch = dmasks ? nullptr : ws_take<uint8_t>(ctx, (size_t)b.P * b.Nmax);
+  if (o.method == PRE3_METHOD_SVD) return launch_eval_pairloop_mode<0, true>(ctx, b, o, dres, dmasks, scratch);
+  if (o.method == PRE3_METHOD_HORN) return launch_eval_pairloop_mode<1, true>(ctx, b, o, dres, dmasks, scratch);
+  return fail(ctx, PRE3_ERR_ARG, "unknown RANSAC method");
+}
+
 int launch_eval_waves(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts& o) {
   if (b.P <= 0 || o.H <= 0) return PRE3_OK;
   const int H = o.H;
   if (use_pairloop(b, o)) {
-    if (o.method == PRE3_METHOD_SVD) return launch_eval_pairloop_mode<0>(ctx, b, o);
-    if (o.method == PRE3_METHOD_HORN) return launch_eval_pairloop_mode<1>(ctx, b, o);
+    if (o.method == PRE3_METHOD_SVD) return launch_eval_pairloop_mode<0, false>(ctx, b, o, nullptr, nullptr, nullptr);
+    if (o.method == PRE3_METHOD_HORN) return launch_eval_pairloop_mode<1, false>(ctx, b, o, nullptr, nullptr, nullptr);
     return fail(ctx, PRE3_ERR_ARG, "unknown RANSAC method");
   }
   int32_t ends[40];

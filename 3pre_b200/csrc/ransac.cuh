@@ -49,6 +49,10 @@ int launch_eval(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts& o
                 const int32_t* stop);
 int launch_eval_waves(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts& o);
 int eval_wave_ends(const pre3_ransac_opts& o, int32_t* ends, int cap, int P = 0);
+// batches of pairs with the adaptive stop: evaluation and selection in ONE launch (one block per pair)
+bool ransac_can_fuse_select(const RansacBuffers& b, const pre3_ransac_opts& o);
+int launch_eval_select_fused(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts& o, pre3_pair_result* dres,
+                             uint8_t* dmasks);
 int launch_select(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts& o, pre3_pair_result* dres,
                   uint8_t* dmasks, int32_t* dcounts_out, int8_t* dstates_out);
 // M/code_from_dr_ye variant (vodometry_dr_ye.m:147-220); dmatch: P x Nmax x 2 match ids or nullptr; b.samples:
