@@ -133,6 +133,8 @@ SYMBOLS = {
     "pre3_ransac_block_select_dev": (_I, [_VP, _VP, _VP, _I, _OPTS, _VP, _I64, _I, _D, _VP, _VP]),
     "pre3_ransac_finish_dev": (_I, [_VP, _VP, _VP, _I, _OPTS, _VP, _I64, _D, _VP, _VP]),
     "pre3_distance_threshold_dev": (_I, [_VP, _VP, _I, _VP]),
+    "pre3_ransac_split_local_dev": (_I, [_VP, _VP, _VP, _I, _OPTS, _VP, _I64, _I, _I, _VP, _VP, _VP]),
+    "pre3_ransac_split_finish_dev": (_I, [_VP, _VP, _VP, _I, _OPTS, _VP, _I64, _I, _I, _VP, _I, _I, _VP, _VP]),
     "pre3_R2q": (None, [_VP, _VP]),
     "pre3_ekf_support": (_I, [_VP, _VP, _I, _I, C.POINTER(Cam), _VP, _VP, _I, _VP, _I, _D, _VP, _VP, _VP]),
     "pre3_ransac_hypotheses_batch": (_I, [_VP, _I, _I, _I, _VP, _VP, _D, C.POINTER(Cam), _VP, _VP, _VP, _VP, _VP, _VP,

@@ -685,6 +685,20 @@ class Context:
                                                         _ptr(samples), int(h0), int(Hloc), float(thr), _ptr(res),
                                                         _ptr(mask)))
 
+    def ransac_split_local_dev(self, Ya, Yb, opts: RansacOpts, h0: int, Hloc: int, mode: int, key, res=None, mask=None,
+                               samples=None):
+        """Stream-ordered hypothesis-block split, local part (pre3_ransac_split_local_dev): key int64 tensor (1,)
+        (mode 0) or (2,) (mode 1); res uint8 (240,), mask uint8 (N,) for mode 1."""
+        self._ck(self._lib.pre3_ransac_split_local_dev(self._h, _ptr(Ya), _ptr(Yb), Ya.shape[0], C.byref(opts),
+                                                       _ptr(samples), int(h0), int(Hloc), int(mode), _ptr(key),
+                                                       _ptr(res), _ptr(mask)))
+
+    def ransac_split_finish_dev(self, Ya, Yb, opts: RansacOpts, h0: int, Hloc: int, mode: int, exchanged, world: int,
+                                rank: int, res, mask=None, samples=None):
+        self._ck(self._lib.pre3_ransac_split_finish_dev(self._h, _ptr(Ya), _ptr(Yb), Ya.shape[0], C.byref(opts),
+                                                        _ptr(samples), int(h0), int(Hloc), int(mode), _ptr(exchanged),
+                                                        int(world), int(rank), _ptr(res), _ptr(mask)))
+
     def ransac_finish_dev(self, Ya, Yb, opts: RansacOpts, winner_id: int, thr: float, res, mask=None,
                           sample_of_winner=None):
         self._ck(self._lib.pre3_ransac_finish_dev(self._h, _ptr(Ya), _ptr(Yb), Ya.shape[0], C.byref(opts),

@@ -1023,6 +1023,68 @@ int pre3_ransac_finish_dev(pre3_ctx* ctx, const double* dYa, const double* dYb, 
   return PRE3_OK;
 }
 
+// ---- the hypothesis-block split, stream-ordered (no host read between the kernels and the collective) ----------
+// mode 0 ("first": max count, lowest id): dkey[0] = this block's key; the caller all-reduces it (MAX) on the same
+// stream and calls pre3_ransac_split_finish_dev.  mode 1 (reference rule): the block's own full selection (record +
+// mask) and dkey[0..1] = (key, ErrorSum bits); the caller all-gathers the 16 bytes and calls split_finish.
+// The threshold (RANSAC_CALC_VER2.m:69-72 for the SVD method) is computed on the device.
+static int split_setup(pre3_ctx* ctx, const double* dYa, const double* dYb, int N, pre3_ransac_opts& o,
+                       const int32_t* dsamples, int Hloc, RansacBuffers& b) {
+  PRE3_TRY(ws_reserve(ctx, ransac_ws_bytes(1, N, Hloc) + 1024));
+  b.Ya = dYa;
+  b.Yb = dYb;
+  b.n_corr = nullptr;
+  b.P = 1;
+  b.Nmax = N;
+  b.samples = dsamples;
+  b.pair_id0 = 0;
+  ransac_carve(ctx, b, std::max(Hloc, 1));
+  double* dthr = nullptr;
+  if (o.method == PRE3_METHOD_SVD) {
+    dthr = ws_take<double>(ctx, 1);
+    PRE3_TRY(launch_threshold(ctx, dYb, N, dthr));
+  }
+  o.adaptive = 0;  // fixed-H by construction
+  PRE3_TRY(launch_prep(ctx, b, o, 1, dthr));
+  return PRE3_OK;
+}
+
+int pre3_ransac_split_local_dev(pre3_ctx* ctx, const double* dYa, const double* dYb, int N, const pre3_ransac_opts* opts,
+                                const int32_t* dsamples, int64_t h0, int Hloc, int mode, uint64_t* dkey,
+                                pre3_pair_result* dres, uint8_t* dmask) {
+  PRE3_LIVE();
+  PRE3_TRY(check_opts(ctx, opts));
+  PRE3_NEED(dYa && dYb && dkey, "null pointer");
+  PRE3_NEED(N >= 1 && Hloc >= 0 && h0 >= 0, "bad sizes");
+  PRE3_NEED(mode == 0 || (mode == 1 && dres), "mode 1 needs the record buffer");
+  pre3_ransac_opts o = *opts;
+  o.H = Hloc;
+  if (mode == 1) o.max_iteration = Hloc + 1;  // the loop runs over every sample set of the block
+  RansacBuffers b{};
+  PRE3_TRY(split_setup(ctx, dYa, dYb, N, o, dsamples, Hloc, b));
+  b.h0 = h0;
+  PRE3_TRY(launch_eval(ctx, b, o, h0, 0, Hloc, nullptr));
+  if (mode == 0) return launch_block_best(ctx, b, o, h0, Hloc, dkey, nullptr);
+  PRE3_TRY(launch_select(ctx, b, o, dres, dmask, nullptr, nullptr));
+  return launch_split_pack(ctx, dres, h0, dkey);
+}
+
+int pre3_ransac_split_finish_dev(pre3_ctx* ctx, const double* dYa, const double* dYb, int N, const pre3_ransac_opts* opts,
+                                 const int32_t* dsamples, int64_t h0, int Hloc, int mode, const uint64_t* dexchanged,
+                                 int world, int rank, pre3_pair_result* dres, uint8_t* dmask) {
+  PRE3_LIVE();
+  PRE3_TRY(check_opts(ctx, opts));
+  PRE3_NEED(dYa && dYb && dexchanged && dres, "null pointer");
+  PRE3_NEED(N >= 1 && Hloc >= 0 && h0 >= 0 && world >= 1 && rank >= 0 && rank < world, "bad sizes");
+  if (mode == 1) return launch_split_keep(ctx, dexchanged, world, rank, h0, dres, dmask, N);
+  pre3_ransac_opts o = *opts;
+  o.H = Hloc;
+  RansacBuffers b{};
+  PRE3_TRY(split_setup(ctx, dYa, dYb, N, o, dsamples, 1, b));
+  uint8_t* scratch = dmask ? nullptr : ws_take<uint8_t>(ctx, (size_t)N);
+  return launch_finish_key(ctx, b, o, dexchanged, h0, Hloc, dres, dmask ? dmask : scratch);
+}
+
 // R2q of slamToolbox (M/slamToolbox_11_02_18/FrameTransforms/Rotations/R2q.m:11-55): host helper.
 void pre3_R2q(const double* Rc, double* q) {
   // column-major: R(i,j) = Rc[3*(j-1) + (i-1)]

@@ -1622,11 +1622,26 @@ __global__ void k_key_errsum(const PairMeta* __restrict__ meta, const double* __
 __global__ void __launch_bounds__(SEL_THREADS)
 k_finish(const PairMeta* __restrict__ meta, const double* __restrict__ Ya, const double* __restrict__ Yb,
          const int32_t* __restrict__ sample_of_winner, uint64_t seed, uint32_t pair_id0, long long winner_id,
-         int k, int method, pre3_pair_result* __restrict__ res, uint8_t* __restrict__ mask) {
+         int k, int method, pre3_pair_result* __restrict__ res, uint8_t* __restrict__ mask,
+         const unsigned long long* __restrict__ dkey, long long h0, int Hloc, const int32_t* __restrict__ block_samples) {
   __shared__ SelShared sh;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const PairMeta m = meta[0];
   const int N = m.N;
+  if (dkey) {
+    // winner = the exchanged key (max count, lowest id); only the rank whose block holds it does the work, the others
+    // zero their record and mask (a SUM all-reduce then delivers the owner's)
+    const unsigned long long kk = *dkey;
+    winner_id = (long long)(0xFFFFFFFFu - (uint32_t)(kk & 0xFFFFFFFFull));
+    if (kk == 0ull || winner_id < h0 || winner_id >= h0 + Hloc) {
+      unsigned char* rb = reinterpret_cast<unsigned char*>(res);
+      for (int i = tid; i < (int)sizeof(pre3_pair_result); i += SEL_THREADS) rb[i] = 0;
+      if (mask)
+        for (int i = tid; i < N; i += SEL_THREADS) mask[i] = 0;
+      return;
+    }
+    sample_of_winner = block_samples ? block_samples + (size_t)(winner_id - h0) * k : nullptr;
+  }
   pre3_pair_result out;
   if (tid == 0) {
     int idx[MAX_K];
@@ -1684,6 +1699,53 @@ k_finish(const PairMeta* __restrict__ meta, const double* __restrict__ Ya, const
     for (int i = 0; i < 3; ++i) out.T_hyp[i] = sh.Rt[9 + i];
     res[0] = out;
   }
+}
+
+// ---- hypothesis-block split without host round trips (BASELINE config 5) ---------------------------------------
+// Every rank: k_threshold -> k_prep(threshold from device memory) -> k_eval(block) -> local key; ONE collective on the
+// same stream (all-reduce MAX of the 8-byte key, or all-gather of 16 bytes per rank); then k_finish / k_split_keep read
+// the exchanged keys from device memory and only the owner's record survives (the others write zeros, so a SUM
+// all-reduce delivers it).  Nothing is read back before the caller wants the record.
+__global__ void k_split_pack(const pre3_pair_result* __restrict__ res, long long h0, unsigned long long* __restrict__ key2) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (res->status == 0) {
+    key2[0] = ((unsigned long long)(uint32_t)res->best_fit << 32) |
+              (unsigned long long)(0xFFFFFFFFu - (uint32_t)(h0 + res->best_sample));
+    key2[1] = (unsigned long long)__double_as_longlong(res->error_sum);
+  } else {
+    key2[0] = ~0ull;  // no recorded hypothesis in this block
+    key2[1] = (unsigned long long)__double_as_longlong(INFINITY);
+  }
+}
+
+// reference rule over the ranks' local winners (RANSAC_CALC_VER2.m:165-175): max cardinality, then min ErrorSum, then
+// the lowest hypothesis id; the owner keeps its record (best_sample made global), every other rank zeroes its own.
+__global__ void __launch_bounds__(256)
+k_split_keep(const unsigned long long* __restrict__ gathered, int ws, int rank, long long h0,
+             pre3_pair_result* __restrict__ res, uint8_t* __restrict__ mask, int N) {
+  int owner = -1;
+  unsigned long long bk = 0ull;
+  double be = INFINITY;
+  for (int r = 0; r < ws; ++r) {
+    const unsigned long long k = gathered[2 * r];
+    if (k == ~0ull) continue;
+    const double e = __longlong_as_double((long long)gathered[2 * r + 1]);
+    const uint32_t c = (uint32_t)(k >> 32), bc = (uint32_t)(bk >> 32);
+    const uint32_t id = 0xFFFFFFFFu - (uint32_t)(k & 0xFFFFFFFFull), bid = 0xFFFFFFFFu - (uint32_t)(bk & 0xFFFFFFFFull);
+    if (owner < 0 || c > bc || (c == bc && (e < be || (e == be && id < bid)))) {
+      owner = r;
+      bk = k;
+      be = e;
+    }
+  }
+  if (owner == rank) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) res->best_sample = (int32_t)(0xFFFFFFFFu - (uint32_t)(bk & 0xFFFFFFFFull));
+    return;
+  }
+  unsigned char* rb = reinterpret_cast<unsigned char*>(res);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (int)sizeof(pre3_pair_result); i += gridDim.x * blockDim.x) rb[i] = 0;
+  if (mask)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) mask[i] = 0;
 }
 
 __global__ void __launch_bounds__(256) k_threshold(const double* __restrict__ Yb, int N, double* __restrict__ thr) {
@@ -2154,11 +2216,11 @@ int ensure_adaptive_table(pre3_ctx* ctx, const pre3_ransac_opts& o, int Nmax, co
   }
 }
 
-int launch_prep(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts& o, int thr_given) {
+int launch_prep(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts& o, int thr_given, const double* dthr) {
   Span span__(ctx, T_PREP);
   if (b.P <= 0) return PRE3_OK;
   k_prep<<<b.P, 256, 0, ctx->stream>>>(b.Ya, b.Yb, b.n_corr, b.Nmax, thr_given ? PRE3_METHOD_HORN : o.method,
-                                       o.distance_threshold, nullptr, b.tab.triangular, b.tab.rowoff, b.meta, b.Ya4,
+                                       o.distance_threshold, dthr, b.tab.triangular, b.tab.rowoff, b.meta, b.Ya4,
                                        b.Yb4);
   count_launch(ctx);
   PRE3_CUDA(cudaGetLastError());
@@ -2473,7 +2535,34 @@ int launch_finish(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts&
                   pre3_pair_result* dres, uint8_t* dmask) {
   Span span__(ctx, T_OTHER);
   k_finish<<<1, SEL_THREADS, 0, ctx->stream>>>(b.meta, b.Ya, b.Yb, b.samples, o.seed, b.pair_id0, winner_id, o.k,
-                                               o.method, dres, dmask);
+                                               o.method, dres, dmask, nullptr, 0, 0, nullptr);
+  count_launch(ctx);
+  PRE3_CUDA(cudaGetLastError());
+  return PRE3_OK;
+}
+
+int launch_finish_key(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts& o, const uint64_t* dkey,
+                      long long h0, int Hloc, pre3_pair_result* dres, uint8_t* dmask) {
+  Span span__(ctx, T_OTHER);
+  k_finish<<<1, SEL_THREADS, 0, ctx->stream>>>(b.meta, b.Ya, b.Yb, nullptr, o.seed, b.pair_id0, 0, o.k, o.method, dres,
+                                               dmask, (const unsigned long long*)dkey, h0, Hloc, b.samples);
+  count_launch(ctx);
+  PRE3_CUDA(cudaGetLastError());
+  return PRE3_OK;
+}
+
+int launch_split_pack(pre3_ctx* ctx, const pre3_pair_result* dres, long long h0, uint64_t* dkey2) {
+  Span span__(ctx, T_OTHER);
+  k_split_pack<<<1, 32, 0, ctx->stream>>>(dres, h0, (unsigned long long*)dkey2);
+  count_launch(ctx);
+  PRE3_CUDA(cudaGetLastError());
+  return PRE3_OK;
+}
+
+int launch_split_keep(pre3_ctx* ctx, const uint64_t* dgathered, int ws, int rank, long long h0, pre3_pair_result* dres,
+                      uint8_t* dmask, int N) {
+  Span span__(ctx, T_OTHER);
+  k_split_keep<<<dmask ? 8 : 1, 256, 0, ctx->stream>>>((const unsigned long long*)dgathered, ws, rank, h0, dres, dmask, N);
   count_launch(ctx);
   PRE3_CUDA(cudaGetLastError());
   return PRE3_OK;

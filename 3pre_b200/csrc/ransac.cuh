@@ -43,7 +43,8 @@ size_t ransac_workspace_bytes(int P, int Nmax, int H);
 void ransac_carve(pre3_ctx* ctx, RansacBuffers& b, int H);
 
 // thr_given != 0: use o.distance_threshold whatever the method (hypothesis-block entry points)
-int launch_prep(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts& o, int thr_given);
+// dthr != nullptr: the threshold is read from device memory (stream-ordered hypothesis-block split)
+int launch_prep(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts& o, int thr_given, const double* dthr = nullptr);
 // sample sets [hbeg, hend) of every pair (global hypothesis id = h0 + index); pairs with stop[p] >= 0 are skipped
 int launch_eval(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts& o, long long h0, int hbeg, int hend,
                 const int32_t* stop);
@@ -74,5 +75,11 @@ int launch_block_best(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_o
 int launch_finish(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts& o, long long winner_id,
                   pre3_pair_result* dres, uint8_t* dmask);
 int launch_threshold(pre3_ctx* ctx, const double* dYb, int N, double* dthr);
+// stream-ordered hypothesis-block split: winner read from a device key / the gathered (key, ErrorSum) pairs
+int launch_finish_key(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts& o, const uint64_t* dkey,
+                      long long h0, int Hloc, pre3_pair_result* dres, uint8_t* dmask);
+int launch_split_pack(pre3_ctx* ctx, const pre3_pair_result* dres, long long h0, uint64_t* dkey2);
+int launch_split_keep(pre3_ctx* ctx, const uint64_t* dgathered, int ws, int rank, long long h0, pre3_pair_result* dres,
+                      uint8_t* dmask, int N);
 
 }  // namespace pre3

@@ -151,7 +151,13 @@ def ransac_hypothesis_split(ctx, Ya, Yb, opts, samples=None, mode="first", group
     samples: this rank's OWN slice (Hloc, k) int32 CUDA tensor of explicit sample sets, or None
     (seeded: hypothesis id h uses the same set on any rank count).  Returns (record, mask) with
     record a numpy RESULT_DTYPE scalar (best_sample = GLOBAL hypothesis id) and mask (N,) uint8 numpy
-    (None unless want_mask) -- identical on every rank."""
+    (None unless want_mask) -- identical on every rank.
+
+    STREAM-ORDERED: threshold, keys and winner stay in device memory; the sequence on the context's stream (which
+    must be torch's current stream: ctx.use_torch_stream()) is
+        split_local kernels -> ONE collective (8-byte MAX all-reduce, or 16-byte-per-rank all-gather)
+        -> split_finish kernel -> SUM all-reduce of the 240-byte record (+ mask on request)
+    and the only host synchronisation is the final read of the record."""
     import torch
     from .api import RESULT_DTYPE
     dist = _dist()
@@ -159,42 +165,34 @@ def ransac_hypothesis_split(ctx, Ya, Yb, opts, samples=None, mode="first", group
     dev = Ya.device
     N, H = Ya.shape[0], int(opts.H)
     h0, h1 = split_range(H, rank, ws)
-    thr_t = torch.zeros(1, dtype=torch.float64, device=dev)
-    if opts.method == 0:  # RANSAC_CALC_VER2.m:69-72 overrides options.DistanceThreshold
-        ctx.distance_threshold_dev(Yb, thr_t)
-        ctx.sync()
-        thr = float(thr_t.item())
-    else:
-        thr = float(opts.distance_threshold)
+    m = 0 if mode == "first" else 1
+    if mode not in ("first", "reference"):
+        raise ValueError("mode must be 'first' or 'reference'")
     res = torch.zeros(240, dtype=torch.uint8, device=dev)
-    mask = torch.zeros(N, dtype=torch.uint8, device=dev)
-    if mode == "first":
-        key = torch.zeros(1, dtype=torch.int64, device=dev)
-        ctx.ransac_block_dev(Ya, Yb, opts, h0, h1 - h0, thr, key, None, samples=samples)
-        ctx.sync()
-        allreduce_max_key(key, group)          # <- the one collective
-        k = int(key.item())
-        if k == 0:
-            return None, None
-        count, gid = unpack_key(k)
-        owner = next(r for r in range(ws) if split_range(H, r, ws)[0] <= gid < split_range(H, r, ws)[1])
-        if rank == owner:
-            sow = samples[gid - h0].contiguous() if samples is not None else None
-            ctx.ransac_finish_dev(Ya, Yb, opts, gid, thr, res, mask, sample_of_winner=sow)
-            ctx.sync()
+    mask = torch.zeros(N, dtype=torch.uint8, device=dev) if (want_mask or m == 1) else None
+    key = torch.zeros(2, dtype=torch.int64, device=dev)
+    ctx.ransac_split_local_dev(Ya, Yb, opts, h0, h1 - h0, m, key, res if m == 1 else None, mask if m == 1 else None,
+                               samples=samples)
+    if m == 0:
+        exchanged = key[:1]
+        if ws > 1:
+            dist.all_reduce(exchanged, op=dist.ReduceOp.MAX, group=group)          # <- the one collective
     else:
-        ctx.ransac_block_select_dev(Ya, Yb, opts, h0, h1 - h0, thr, res, mask, samples=samples)
-        ctx.sync()
-        loc = np.frombuffer(res.cpu().numpy().tobytes(), dtype=RESULT_DTYPE)[0]
-        ok = loc["status"] == 0
-        owner, count, gid, _ = agree_on_winner(int(loc["best_fit"]) if ok else -1, h0 + int(loc["best_sample"]),
-                                               float(loc["error_sum"]), "reference", dev, group)   # <- the one collective
-        if owner < 0:
-            return None, None
-    if ws > 1:  # result delivery (not part of the selection): 240 B record (+ N-byte mask on request)
-        dist.broadcast(res, src=dist.get_global_rank(group, owner) if group is not None else owner, group=group)
+        if ws > 1:
+            exchanged = torch.empty(2 * ws, dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(exchanged, key, group=group)               # <- the one collective
+        else:
+            exchanged = key
+    ctx.ransac_split_finish_dev(Ya, Yb, opts, h0, h1 - h0, m, exchanged, ws, rank, res, mask if (want_mask or m == 1) else None,
+                                samples=samples)
+    if ws > 1:  # result delivery (not part of the selection): every rank but the owner holds zeros
+        dist.all_reduce(res, op=dist.ReduceOp.SUM, group=group)
         if want_mask:
-            dist.broadcast(mask, src=dist.get_global_rank(group, owner) if group is not None else owner, group=group)
+            dist.all_reduce(mask, op=dist.ReduceOp.SUM, group=group)
+    ctx.sync()  # the only host synchronisation: the record is read
     rec = np.frombuffer(res.cpu().numpy().tobytes(), dtype=RESULT_DTYPE)[0].copy()
-    rec["best_sample"] = gid
+    if m == 0 and int(key[0].item()) == 0:
+        return None, None
+    if m == 1 and rec["best_fit"] == 0 and rec["n_matches"] == 0:
+        return None, None
     return rec, (mask.cpu().numpy() if want_mask else None)

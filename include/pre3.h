@@ -368,6 +368,24 @@ PRE3_API int pre3_ransac_finish_dev(pre3_ctx *ctx, const double *dYa, const doub
                            int64_t winner_id, double thr, pre3_pair_result *dres, uint8_t *dmask);
 /* thr := 0.01*||Yb(:,argmin z)|| (RANSAC_CALC_VER2.m:69-72), computed on the device. */
 PRE3_API int pre3_distance_threshold_dev(pre3_ctx *ctx, const double *dYb, int N, double *dthr);
+/* The same split, STREAM-ORDERED: nothing is read back between the kernels and the collective (the threshold, the
+ * keys and the winner stay in device memory), so one solve is  split_local -> ONE collective -> split_finish -> a SUM
+ * all-reduce of the 240-byte record (every rank but the owner holds zeros).
+ *   mode 0 ("first": max inlier count, lowest hypothesis id -- what BASELINE.json config 5 specifies):
+ *     split_local writes dkey[0] = (count << 32) | (0xFFFFFFFF - global id); the caller all-reduces it with MAX;
+ *     split_finish(dexchanged = the reduced key) lets the rank whose block holds the winner compute hypothesis, mask,
+ *     ErrorSum and refit (RANSAC_CALC_VER2.m:186); the other ranks write zeros.
+ *   mode 1 (the reference's full rule :165-175): split_local runs the block's own selection (record in dres, mask in
+ *     dmask) and writes dkey[0..1] = (key, ErrorSum bits); the caller all-gathers the 16 bytes of every rank;
+ *     split_finish(dexchanged = world x 2 words) picks max count, min ErrorSum, lowest id: the owner keeps its record
+ *     (best_sample made global), the others zero theirs. */
+PRE3_API int pre3_ransac_split_local_dev(pre3_ctx *ctx, const double *dYa, const double *dYb, int N,
+                                         const pre3_ransac_opts *opts, const int32_t *dsamples, int64_t h0, int Hloc,
+                                         int mode, uint64_t *dkey, pre3_pair_result *dres, uint8_t *dmask);
+PRE3_API int pre3_ransac_split_finish_dev(pre3_ctx *ctx, const double *dYa, const double *dYb, int N,
+                                          const pre3_ransac_opts *opts, const int32_t *dsamples, int64_t h0, int Hloc,
+                                          int mode, const uint64_t *dexchanged, int world, int rank,
+                                          pre3_pair_result *dres, uint8_t *dmask);
 
 /* ---- config 4: 1-point-RANSAC EKF hypotheses --------------------------------------------
  * ransac_hypotheses (M/ransac_hypotheses.m:27-85) and compute_hypothesis_support_fast

@@ -571,6 +571,58 @@ def test_hypothesis_block_split_reference_mode(ctx, orc, synth, pre3, supplied):
     assert rec["best_fit"] == g.counts.max() and rec["best_sample"] == int(np.flatnonzero(g.counts == g.counts.max())[0])
 
 
+@pytest.mark.parametrize("mode", ["first", "reference"])
+def test_split_stream_ordered_emulated(ctx, synth, pre3, mode):
+    """The stream-ordered split (pre3_ransac_split_local_dev / _finish_dev), G ranks emulated one after the other on one
+    GPU with the collective done by torch on the device: the summed records equal the single run; ranks that do not own
+    the winner contribute zeros."""
+    import torch
+    pd = importlib.import_module("3pre_b200.dist")
+    N, H, G = 600, 4000, 4
+    c = synth.make_correspondences(33, N=N, outlier_ratio=0.5, noise=0.0005)
+    opts = pre3.make_opts(method=0, k=5, max_iteration=H + 1, adaptive=False, H=H, seed=23)
+    g = ctx.ransac(c.Ya, c.Yb, None, opts)
+    Ya, Yb = torch.from_numpy(c.Ya).cuda(), torch.from_numpy(c.Yb).cuda()
+    m = 0 if mode == "first" else 1
+    torch.cuda.synchronize()
+    keys, recs, masks = [], [], []
+    for r in range(G):
+        h0, h1 = pd.split_range(H, r, G)
+        key = torch.zeros(2, dtype=torch.int64, device="cuda")
+        res = torch.zeros(240, dtype=torch.uint8, device="cuda")
+        mask = torch.zeros(N, dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        ctx.ransac_split_local_dev(Ya, Yb, opts, h0, h1 - h0, m, key, res if m else None, mask if m else None)
+        ctx.sync()
+        keys.append(key); recs.append(res); masks.append(mask)
+    if m == 0:
+        exchanged = torch.stack([k[0] for k in keys]).max().reshape(1).contiguous()      # all_reduce(MAX)
+    else:
+        exchanged = torch.cat(keys).contiguous()                                           # all_gather
+    torch.cuda.synchronize()
+    for r in range(G):
+        h0, h1 = pd.split_range(H, r, G)
+        ctx.ransac_split_finish_dev(Ya, Yb, opts, h0, h1 - h0, m, exchanged, G, r, recs[r], masks[r])
+    ctx.sync()
+    nonzero = [r for r in range(G) if recs[r].any().item()]
+    assert len(nonzero) == 1                                                               # one owner
+    total = torch.stack(recs).sum(0).to(torch.uint8)                                       # all_reduce(SUM)
+    rec = np.frombuffer(total.cpu().numpy().tobytes(), dtype=pre3.RESULT_DTYPE)[0]
+    mk = torch.stack(masks).sum(0).cpu().numpy().astype(bool)
+    first = int(np.flatnonzero(g.counts == g.counts.max())[0])
+    if mode == "first":
+        assert (rec["best_fit"], rec["best_sample"]) == (g.counts.max(), first)
+        h0o, h1o = pd.split_range(H, nonzero[0], G)
+        assert h0o <= first < h1o
+    else:
+        assert (rec["best_fit"], rec["best_sample"], rec["error_sum"]) == (g.best_fit, g.best_sample, g.error_sum)
+        np.testing.assert_array_equal(mk, g.mask)
+        r_ = pre3.unpack_result(rec)
+        np.testing.assert_array_equal(r_.R, g.R)
+        np.testing.assert_array_equal(r_.T, g.T)
+    assert mk.sum() == rec["best_fit"]
+
+
 def test_matlab_mirror_roundtrip(ctx, orc, synth):
     m = importlib.import_module("3pre_b200.matlab")
     c = synth.make_correspondences(8, N=200, outlier_ratio=0.3)
