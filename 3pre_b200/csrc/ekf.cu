@@ -24,6 +24,7 @@
 // oracle/pre3_oracle_ekf.c, so supports, masks and selection equal the CPU checker's bit for bit.
 // Compile with -fmad=false.
 #include <cmath>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -332,6 +333,7 @@ struct HypRec {
   double innov[6];  // zi - hi
   double cam[7];    // updated camera position + quaternion
   double Rw[9];     // q2r of the updated quaternion
+  double w[6];      // inv(S)*(zi - hi): the FAST form x + G*w of the state update (proposes, never decides)
   int32_t sel[3];   // the selected features
   int32_t d;        // 2 m
 };
@@ -361,6 +363,18 @@ __device__ __forceinline__ double updated_state(const double* __restrict__ x, co
       dx = j == 0 ? term : dx + term;
     }
   }
+  return x[e] + dx;
+}
+
+// xi[e] ~ x[e] + sum_c G[e][c]*w[c] with w = inv(S)*innov: the same update re-associated (6 multiply-adds per state instead
+// of 42).  Its residual only PROPOSES: k_ekf_score re-evaluates in the literal K-form above every residual that could
+// decide the minimum or sit at a threshold.
+__device__ __forceinline__ double updated_state_fast(const double* __restrict__ x, const double* __restrict__ G,
+                                                     const size_t* goff, const double* w, int d, int e) {
+  double dx = 0.0;
+#pragma unroll
+  for (int c = 0; c < 6; ++c)
+    if (c < d) dx = fma(__ldg(G + goff[c] + e), w[c], dx);
   return x[e] + dx;
 }
 
@@ -521,6 +535,11 @@ k_ekf_hyp(const ScoreArgs A, int Fr, HypRec* __restrict__ rec, int rec_stride, i
   __syncwarp();
   for (int i = lane; i < 36; i += 32) out->Sinv[i] = i < d * d ? Sinv[i] : 0.0;
   if (lane < 6) out->innov[lane] = lane < d ? innov[lane] : 0.0;
+  if (lane < 6) {
+    double wv = 0.0;
+    for (int j = 0; j < d; ++j) wv = fma(lane < d ? Sinv[lane * d + j] : 0.0, innov[j], wv);
+    out->w[lane] = lane < d ? wv : 0.0;
+  }
   if (lane < 7) out->cam[lane] = cam[lane];
   if (lane < 3) out->sel[lane] = lane < m ? sh.sel[lane] : 0;
   if (lane == 0) {
@@ -540,7 +559,8 @@ struct ScoreShared {
 };
 
 // One block per (frame, hypothesis), one thread per measured feature.
-template <bool FINAL>
+// FAST: the re-associated proposal + literal recheck described below; !FAST: every residual in the literal K-form.
+template <bool FINAL, bool FAST>
 __global__ void __launch_bounds__(256) k_ekf_score(const ScoreArgs A, const HypRec* __restrict__ rec, int rec_stride) {
   extern __shared__ double s_res[];  // one residual per measured feature
   __shared__ ScoreShared sh;
@@ -573,26 +593,93 @@ __global__ void __launch_bounds__(256) k_ekf_score(const ScoreArgs A, const HypR
   __syncthreads();
 
   // ---- one thread per measured feature ---------------------------------------------------------
-  double lmin = __longlong_as_double(0x7ff8000000000000LL);
-  for (int j = tid; j < fi.n_meas; j += blockDim.x) {
-    const int f = A.meas[fF + j];
-    const int ty = A.type[fF + f], p = A.pos[fF + f];
+  // The literal update xi = x + (P*Hi'*inv(S))*(zi - hi) (ransac_hypotheses.m:61-63) rebuilds a row of K for every
+  // state of every feature of every hypothesis: 468 of the ~600 flops of an evaluation.  Here the re-associated form
+  // x + G*w (36 multiply-adds per feature) gives a residual r~ that differs from the literal one by rounding only;
+  // it PROPOSES, and the literal form is evaluated for every residual that could DECIDE something:
+  //   - candidates for the minimum of the inverse-depth residuals (r~ within 2 delta of the smallest r~),
+  //   - residuals within 2 delta of the inlier limit (min + threshold, or threshold for cartesian features),
+  //   - residuals that are not finite.
+  // delta = 1e-6 (1 + |r~|) pixels is ~9 orders of magnitude above the re-association error of well-conditioned
+  // features; near-singular projections give huge or non-finite residuals, which take the literal path.  Supports,
+  // masks and the selected hypothesis therefore equal those of the literal evaluation (the CPU checker's), at about a
+  // quarter of its arithmetic: typically ONE literal evaluation per hypothesis (the minimum itself).
+  auto literal = [&](int f, int ty, int p) {
     double s[6];
 #pragma unroll
     for (int t = 0; t < 6; ++t)
       s[t] = (t < 3 || ty == 0) ? updated_state(x, A.G, sh.goff, sh.rec.Sinv, sh.rec.innov, d, p + t) : 0.0;
-    const double r = feature_residual(ty, s, sh.rec.cam, sh.rec.Rw, A.cam, A.z[(fF + f) * 2], A.z[(fF + f) * 2 + 1]);
+    return feature_residual(ty, s, sh.rec.cam, sh.rec.Rw, A.cam, A.z[(fF + f) * 2], A.z[(fF + f) * 2 + 1]);
+  };
+  auto band = [](double r) { return 2.0e-6 * (1.0 + fabs(r)); };
+  const double QNAN = __longlong_as_double(0x7ff8000000000000LL);
+  double lmin = QNAN;
+  for (int j = tid; j < fi.n_meas; j += blockDim.x) {
+    const int f = A.meas[fF + j];
+    const int ty = A.type[fF + f], p = A.pos[fF + f];
+    double r;
+    if (FAST) {
+      double s[6];
+#pragma unroll
+      for (int t = 0; t < 6; ++t) s[t] = (t < 3 || ty == 0) ? updated_state_fast(x, A.G, sh.goff, sh.rec.w, d, p + t) : 0.0;
+      r = feature_residual(ty, s, sh.rec.cam, sh.rec.Rw, A.cam, A.z[(fF + f) * 2], A.z[(fF + f) * 2 + 1]);
+      if (!(fabs(r) < 1.0e300)) r = QNAN;  // not finite: decided by the literal form below
+    } else {
+      r = literal(f, ty, p);
+    }
     s_res[j] = r;
     if (ty == 0) lmin = nanmin2(lmin, r);
   }
-  const double mn = block_nanmin(lmin, sh.red);
+  const double mn_fast = block_nanmin(lmin, sh.red);
+  if (!FAST) {  // every residual is already the literal one
+    const double lim0 = mn_fast + A.thr;
+    int cnt0 = 0;
+    for (int j = tid; j < fi.n_meas; j += blockDim.x) {
+      const int f = A.meas[fF + j];
+      const bool in = A.type[fF + f] == 0 ? (s_res[j] < lim0) : (s_res[j] < A.thr);
+      cnt0 += in ? 1 : 0;
+      if (FINAL) A.li[fF + f] = in ? 1 : 0;
+    }
+    if (!FINAL) {
+      const int total0 = block_sum_int(cnt0, sh.ired);
+      if (tid == 0) A.supports[(size_t)frame * A.H + hyp] = total0;
+    }
+    return;
+  }
+  // exact minimum: literal residuals of the candidates (every other inverse-depth residual is provably larger)
+  double emin = QNAN;
+  unsigned exact_mask = 0u;  // bit i: the i-th feature of this thread holds a literal residual in s_res
+  {
+    int it = 0;
+    for (int j = tid; j < fi.n_meas; j += blockDim.x, ++it) {
+      const int f = A.meas[fF + j];
+      const int ty = A.type[fF + f];
+      const double r = s_res[j];
+      const bool cand = ty == 0 && (r != r || mn_fast != mn_fast || r <= mn_fast + band(mn_fast) + band(r));
+      if (cand || r != r) {
+        const double re = literal(f, ty, A.pos[fF + f]);
+        s_res[j] = re;
+        if (it < 32) exact_mask |= 1u << it;
+        if (ty == 0) emin = nanmin2(emin, re);
+      }
+    }
+  }
+  const double mn = block_nanmin(emin, sh.red);
   const double lim = mn + A.thr;
   int cnt = 0;
-  for (int j = tid; j < fi.n_meas; j += blockDim.x) {
-    const int f = A.meas[fF + j];
-    const bool in = A.type[fF + f] == 0 ? (s_res[j] < lim) : (s_res[j] < A.thr);
-    cnt += in ? 1 : 0;
-    if (FINAL) A.li[fF + f] = in ? 1 : 0;
+  {
+    int it = 0;
+    for (int j = tid; j < fi.n_meas; j += blockDim.x, ++it) {
+      const int f = A.meas[fF + j];
+      const int ty = A.type[fF + f];
+      const double limit = ty == 0 ? lim : A.thr;
+      double r = s_res[j];
+      const bool is_exact = it < 32 && ((exact_mask >> it) & 1u);
+      if (!is_exact && !(fabs(r - limit) > band(r) + band(limit))) r = literal(f, ty, A.pos[fF + f]);  // borderline (or NaN limit)
+      const bool in = r < limit;
+      cnt += in ? 1 : 0;
+      if (FINAL) A.li[fF + f] = in ? 1 : 0;
+    }
   }
   if (!FINAL) {
     const int total = block_sum_int(cnt, sh.ired);
@@ -854,6 +941,9 @@ static int ekf_impl(pre3_ctx* ctx, int Fr, int n, int F, const double* dx, const
                                                          dHcam + fo * F * 26, dHfeat + fo * F * 12, idx, ic_list, G);
       count_launch(ctx);
     }
+    // PRE3_EKF_FAST=1: re-associated proposal + literal recheck in k_ekf_score (same supports / masks; measured slower at the
+    // config-4 shape: the block's latency chain grows by one literal evaluation and two reductions)
+    static const bool ekf_fast = getenv("PRE3_EKF_FAST") && atoi(getenv("PRE3_EKF_FAST")) != 0;
     PRE3_CUDA(cudaMemsetAsync(sup, 0, 4 * (size_t)nc * std::max(H, 1), ctx->stream));
     PRE3_CUDA(cudaMemsetAsync(stop, 0xFF, 4 * (size_t)nc, ctx->stream));
     ScoreArgs a;
@@ -891,7 +981,8 @@ static int ekf_impl(pre3_ctx* ctx, int Fr, int n, int F, const double* dx, const
         a.hend = end;
         const long long warps = (long long)nc * (end - beg);
         k_ekf_hyp<<<(unsigned)((warps + HYP_WARPS - 1) / HYP_WARPS), HYP_WARPS * 32, 0, ctx->stream>>>(a, nc, rec, maxw, 0);
-        k_ekf_score<false><<<dim3(end - beg, nc), bs, smem, ctx->stream>>>(a, rec, maxw);
+        if (ekf_fast) k_ekf_score<false, true><<<dim3(end - beg, nc), bs, smem, ctx->stream>>>(a, rec, maxw);
+        else k_ekf_score<false, false><<<dim3(end - beg, nc), bs, smem, ctx->stream>>>(a, rec, maxw);
         count_launch(ctx, 2);
       }
       if (end < limit) {
@@ -914,7 +1005,8 @@ static int ekf_impl(pre3_ctx* ctx, int Fr, int n, int F, const double* dx, const
       a.hbeg = 0;
       a.hend = 1;
       k_ekf_hyp<<<(nc + HYP_WARPS - 1) / HYP_WARPS, HYP_WARPS * 32, 0, ctx->stream>>>(a, nc, rec, maxw, 1);
-      k_ekf_score<true><<<dim3(1, nc), bs, smem, ctx->stream>>>(a, rec, maxw);
+      if (ekf_fast) k_ekf_score<true, true><<<dim3(1, nc), bs, smem, ctx->stream>>>(a, rec, maxw);
+      else k_ekf_score<true, false><<<dim3(1, nc), bs, smem, ctx->stream>>>(a, rec, maxw);
       count_launch(ctx, 2);
     }
     PRE3_CUDA(cudaGetLastError());

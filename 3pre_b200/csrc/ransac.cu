@@ -26,6 +26,7 @@ constexpr int EVP_THREADS = 64;  // k_eval_pairloop: sample sets per chunk = thr
 constexpr int EVP_TILE = 384;    // a whole SR4000 pair (~300 matches) in one tile: staged once per block
 constexpr int EVP_LIST = 256;
 constexpr int MAX_K = 8;
+constexpr int FIN_CHUNK = 2048;   // k_finish: correspondences per compaction round of the ordered ErrorSum
 
 // ------------------------------------------------------------------------------------------
 // seeded sample sets: SPEC in oracle/pre3_oracle.c (orc_sample_set), the stand-in for
@@ -1662,22 +1663,48 @@ k_finish(const PairMeta* __restrict__ meta, const double* __restrict__ Ya, const
     c += in ? 1 : 0;
   }
   const double cs = block_sum((double)c, sh.scratch);
+  // ErrorSum = sum(normResidu(inliers)) strictly in index order (:135).  A chain of ~N/2 dependent fp64 adds cannot be
+  // parallelised without changing the rounding, but it can be FED in parallel: per chunk of FIN_CHUNK correspondences
+  // the block compacts the inliers' residual norms, in order, into shared memory (each thread owns 8 consecutive
+  // correspondences; block scan of the counts) and one thread runs the add chain over the compacted list (8000 inliers:
+  // 0.16 ms with the ballot / shuffle walk of one warp, ~0.04 ms this way).
   double es = 0.0;
-  if (warp == 0) {
-    for (int ib = 0; ib < N; ib += 32) {
-      const int i = ib + lane;
-      double nr = 0.0;
-      bool in = false;
-      if (i < N) {
-        in = mask[i] != 0;
-        if (in) nr = residual_norm(&sh.Rt[0], &sh.Rt[9], Ya + 3 * i, Yb + 3 * i);
+  {
+    __shared__ double s_nr[FIN_CHUNK];
+    __shared__ int s_wsum[SEL_THREADS / 32], s_total;
+    for (int base = 0; base < N; base += FIN_CHUNK) {
+      double nr[FIN_CHUNK / SEL_THREADS];
+      int cntl = 0;
+#pragma unroll
+      for (int j = 0; j < FIN_CHUNK / SEL_THREADS; ++j) {
+        const int i = base + (FIN_CHUNK / SEL_THREADS) * tid + j;
+        nr[j] = -1.0;
+        if (i < N && mask[i]) {
+          nr[j] = residual_norm(&sh.Rt[0], &sh.Rt[9], Ya + 3 * i, Yb + 3 * i);
+          ++cntl;
+        }
       }
-      unsigned inb = __ballot_sync(0xffffffffu, in);
-      while (inb) {
-        const int li = __ffs(inb) - 1;
-        inb &= inb - 1;
-        es = es + __shfl_sync(0xffffffffu, nr, li);
+      int incl = cntl;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += v;
       }
+      if (lane == 31) s_wsum[warp] = incl;
+      __syncthreads();
+      int woff = 0;
+      for (int w = 0; w < warp; ++w) woff += s_wsum[w];
+      if (tid == SEL_THREADS - 1) s_total = woff + incl;
+      int pos = woff + incl - cntl;
+#pragma unroll
+      for (int j = 0; j < FIN_CHUNK / SEL_THREADS; ++j)
+        if (nr[j] >= 0.0) s_nr[pos++] = nr[j];
+      __syncthreads();
+      if (tid == 0) {
+        const int tot = s_total;
+        for (int q = 0; q < tot; ++q) es = es + s_nr[q];
+      }
+      __syncthreads();
     }
   }
   Rigid rf;
