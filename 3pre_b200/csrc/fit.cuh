@@ -69,6 +69,67 @@ __device__ __forceinline__ double det3(const double* m) {
          m[2] * (m[3] * m[7] - m[4] * m[6]);
 }
 
+// V*U' of a well-conditioned H by Newton's polar iteration instead of the SVD: SPEC in oracle/pre3_oracle.c
+// (orc_polar_fast), same operations in the same order.  Seven iterations (~1300 instructions) instead of ~5 Jacobi sweeps
+// (~2800), the same count in every lane, and
+// a reflection (det H < 0, no singular value near the threshold: state -1, skipped uncounted by the RANSAC loop) costs
+// the determinant only.  Returns 1 (Xq filled), -1 (reflection), 0 (use the SVD).
+__device__ __forceinline__ int polar_fast(const double* H, double threshold, double* Xq) {
+  double nf2 = 0.0;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) nf2 = nf2 + H[i] * H[i];
+  const double detH = det3(H);
+  if (!(nf2 > 0.0)) return 0;
+  if (!(fabs(detH) > 50.0 * threshold * nf2)) return 0;
+  const double rn = sqrt(nf2);
+  if (!(fabs(detH) > 0.000000001 * (nf2 * rn))) return 0;
+  if (detH < 0.0) return -1;
+  const double sc = 1.0 / rn;
+  double X[9], C[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) X[i] = H[i] * sc;
+  for (int it = 0; it < 40; ++it) {
+    C[0] = X[4] * X[8] - X[5] * X[7];
+    C[1] = X[5] * X[6] - X[3] * X[8];
+    C[2] = X[3] * X[7] - X[4] * X[6];
+    C[3] = X[2] * X[7] - X[1] * X[8];
+    C[4] = X[0] * X[8] - X[2] * X[6];
+    C[5] = X[1] * X[6] - X[0] * X[7];
+    C[6] = X[1] * X[5] - X[2] * X[4];
+    C[7] = X[2] * X[3] - X[0] * X[5];
+    C[8] = X[0] * X[4] - X[1] * X[3];
+    const double dt = (X[0] * C[0] + X[1] * C[1]) + X[2] * C[2];
+    double hx = 0.5, hc;
+    if (it < 3) {  // scaled steps: 7 iterations suffice whatever the conditioning of the admitted H
+      double a = 0.0, b = 0.0;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) {
+        a = a + C[i] * C[i];
+        b = b + X[i] * X[i];
+      }
+      const double g = sqrt(sqrt(a / ((dt * dt) * b)));
+      hx = 0.5 * g;
+      hc = 0.5 / (dt * g);
+    } else {
+      hc = 0.5 / dt;
+    }
+    double diff2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      const double y = hx * X[i] + C[i] * hc;
+      const double e = y - X[i];
+      diff2 = diff2 + e * e;
+      X[i] = y;
+    }
+    if (diff2 <= 1e-28) break;
+  }
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) Xq[3 * r + c] = X[3 * c + r];
+  return 1;
+}
+
 // Tail of find_transform_matrix once H (row-major), ct1, ct2 are known (:17-42).
 // Returns state; fills out (rot row-major, trans).
 // threshold: 1e-11 (find_transform_matrix.m:20) or 1e-14 (code_from_dr_ye/find_transform_matrix_dr_ye.m:19).
@@ -80,7 +141,8 @@ __device__ __forceinline__ int kabsch_from_H(const double* H, const double* ct1,
   int state;
   double A[9], V[9], sig[3], U[9], Xq[9];
   int nsmall = 0, jsmall = -1;
-  if (finite) {
+  const int fast = finite ? polar_fast(H, threshold, Xq) : 0;
+  if (finite && fast == 0) {
 #pragma unroll
     for (int i = 0; i < 9; ++i) A[i] = H[i];
     svd3_cols(A, V, sig);
@@ -93,6 +155,8 @@ __device__ __forceinline__ int kabsch_from_H(const double* H, const double* ct1,
   }
   if (!finite) {
     state = 0;
+  } else if (fast != 0) {
+    state = fast;  // 1: Xq from the polar iteration; -1: reflection
   } else if (nsmall >= 2) {
     state = -1;
   } else {

@@ -75,7 +75,8 @@ ORC_MATCH(orc_siftmatch_i8, signed char, int, 0x7fffffff)
 ORC_MATCH(orc_siftmatch_u8, unsigned char, int, 0x7fffffff)
 
 /* ------------------------------------------------------------------------- */
-/* 3x3 one-sided Jacobi SVD (stands in for MATLAB svd, find_transform_matrix.m:17)
+/* 3x3 one-sided Jacobi SVD (stands in for MATLAB svd, find_transform_matrix.m:17; used for H that is not clearly
+ * well-conditioned, see orc_polar_fast below)
  *
  * SPEC (shared with 3pre_b200/csrc/fit.cuh, which implements the same order):
  *   A := H (row-major a[r][c]),  V := I.
@@ -131,6 +132,84 @@ static double orc_det3(double m[3][3]) {
   return (m[0][0] * (m[1][1] * m[2][2] - m[1][2] * m[2][1]) -
           m[0][1] * (m[1][0] * m[2][2] - m[1][2] * m[2][0])) +
          m[0][2] * (m[1][0] * m[2][1] - m[1][1] * m[2][0]);
+}
+
+/* V*U' of a WELL-CONDITIONED H without the SVD: Xq = V*U' is the transpose of the orthogonal polar factor of H
+ * (H = U S V' = (U V')(V S V')), which Newton's iteration X <- (X + X^-T)/2 reaches quadratically.
+ *
+ * SPEC (shared with 3pre_b200/csrc/fit.cuh: same operations in the same order; + - * / sqrt only):
+ *   nf2  = sum of the squares of the entries of H, row-major order, accumulated from 0.0
+ *   detH = orc_det3(H)
+ *   the fast path applies iff  nf2 > 0,  |detH| > 50*threshold*nf2   (then sigma_min >= 2|detH|/nf2 > 100*threshold: no
+ *   singular value anywhere near the reference's test `S(i,i) < threshold`, find_transform_matrix.m:20,:26)  and
+ *   |detH| > 1e-9*(nf2*sqrt(nf2))  (condition number below ~3e4); otherwise the Jacobi SVD above is used.
+ *     detH < 0:  det(V*U') = -1 with no small singular value  ->  state -1 (:25-36), nothing else to compute.
+ *     detH > 0:  X = H*(1/sqrt(nf2));  repeat at most 40 times:
+ *                  C = cofactors of X (C00 = x11*x22 - x12*x21, C01 = x12*x20 - x10*x22, C02 = x10*x21 - x11*x20,
+ *                      C10 = x02*x21 - x01*x22, C11 = x00*x22 - x02*x20, C12 = x01*x20 - x00*x21,
+ *                      C20 = x01*x12 - x02*x11, C21 = x02*x10 - x00*x12, C22 = x00*x11 - x01*x10)
+ *                  dt = (x00*C00 + x01*C01) + x02*C02
+ *                  iterations 0..2 are SCALED (Higham: gamma = (||X^-T||_F / ||X||_F)^(1/2); 7 iterations then suffice
+ *                  for every admitted H, whatever its conditioning):
+ *                      a = sum C[r][c]^2, b = sum X[r][c]^2 (row-major, from 0.0)
+ *                      g = sqrt(sqrt(a / ((dt*dt)*b)));  hx = 0.5*g;  hc = 0.5/(dt*g)
+ *                  later iterations: hx = 0.5;  hc = 0.5/dt
+ *                  Y[r][c] = hx*X[r][c] + C[r][c]*hc;   e = Y[r][c] - X[r][c], diff2 += e*e (row-major, from 0.0)
+ *                  X = Y;  stop when diff2 <= 1e-28
+ *                Xq = X'  ->  state 1.
+ * Returns 1 (Xq filled), -1 (reflection), 0 (not applicable: use the SVD). */
+static int orc_polar_fast(double H[3][3], double threshold, double Xq[3][3]) {
+  double nf2 = 0.0;
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) nf2 = nf2 + H[r][c] * H[r][c];
+  const double detH = orc_det3(H);
+  if (!(nf2 > 0.0)) return 0;
+  if (!(fabs(detH) > 50.0 * threshold * nf2)) return 0;
+  const double rn = sqrt(nf2);
+  if (!(fabs(detH) > 0.000000001 * (nf2 * rn))) return 0;
+  if (detH < 0.0) return -1;
+  const double sc = 1.0 / rn;
+  double X[3][3], Y[3][3], C[3][3];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) X[r][c] = H[r][c] * sc;
+  for (int it = 0; it < 40; ++it) {
+    C[0][0] = X[1][1] * X[2][2] - X[1][2] * X[2][1];
+    C[0][1] = X[1][2] * X[2][0] - X[1][0] * X[2][2];
+    C[0][2] = X[1][0] * X[2][1] - X[1][1] * X[2][0];
+    C[1][0] = X[0][2] * X[2][1] - X[0][1] * X[2][2];
+    C[1][1] = X[0][0] * X[2][2] - X[0][2] * X[2][0];
+    C[1][2] = X[0][1] * X[2][0] - X[0][0] * X[2][1];
+    C[2][0] = X[0][1] * X[1][2] - X[0][2] * X[1][1];
+    C[2][1] = X[0][2] * X[1][0] - X[0][0] * X[1][2];
+    C[2][2] = X[0][0] * X[1][1] - X[0][1] * X[1][0];
+    const double dt = (X[0][0] * C[0][0] + X[0][1] * C[0][1]) + X[0][2] * C[0][2];
+    double hx = 0.5, hc;
+    if (it < 3) {
+      double a = 0.0, b = 0.0;
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) {
+          a = a + C[r][c] * C[r][c];
+          b = b + X[r][c] * X[r][c];
+        }
+      const double g = sqrt(sqrt(a / ((dt * dt) * b)));
+      hx = 0.5 * g;
+      hc = 0.5 / (dt * g);
+    } else {
+      hc = 0.5 / dt;
+    }
+    double diff2 = 0.0;
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) {
+        Y[r][c] = hx * X[r][c] + C[r][c] * hc;
+        const double e = Y[r][c] - X[r][c];
+        diff2 = diff2 + e * e;
+      }
+    memcpy(X, Y, sizeof X);
+    if (diff2 <= 1e-28) break;
+  }
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) Xq[r][c] = X[c][r];
+  return 1;
 }
 
 /* find_transform_matrix  (M/mex_files/RANSAC_CALCULATION/find_transform_matrix.m:2-42)
@@ -197,7 +276,8 @@ ORC_API int orc_find_transform_thr(const double *pset1, const double *pset2,
   double U[3][3], V[3][3], sig[3], A[3][3], Xq[3][3];
   memcpy(A, H, sizeof A);
   int nsmall = 0, jsmall = -1;
-  if (finite) {
+  const int fast = finite ? orc_polar_fast(H, threshold, Xq) : 0;
+  if (finite && fast == 0) {
     orc_svd3_cols(A, V, sig);
     for (int j = 0; j < 3; ++j)
       if (sig[j] < threshold) {
@@ -207,6 +287,8 @@ ORC_API int orc_find_transform_thr(const double *pset1, const double *pset2,
   }
   if (!finite) {
     state = 0;
+  } else if (fast != 0) {
+    state = fast; /* 1: Xq = V*U' from the polar iteration; -1: reflection, no singular value near the threshold */
   } else if (nsmall >= 2) {
     state = -1;
   } else {
