@@ -288,13 +288,21 @@ __device__ __forceinline__ int eval_score_tile(const float (*sM)[TL], int tn, in
                                                int hyp_local, uint32_t* sList, int* sListN) {
   int cnt = 0;
   const int tn4 = (tn + 3) & ~3;
+  // the operands of trip i + 1 are loaded before trip i is computed (the kernel runs at 16-20 warps per SM: the ~30
+  // cycles of a shared-memory load are not hidden by other warps alone)
+  float4 nbx = *reinterpret_cast<const float4*>(&sM[0][0]), nby = *reinterpret_cast<const float4*>(&sM[1][0]);
+  float4 nbz = *reinterpret_cast<const float4*>(&sM[2][0]), nnx = *reinterpret_cast<const float4*>(&sM[3][0]);
+  float4 nny = *reinterpret_cast<const float4*>(&sM[4][0]), nnz = *reinterpret_cast<const float4*>(&sM[5][0]);
   for (int i = 0; i < tn4; i += 4) {
-    const float4 bx = *reinterpret_cast<const float4*>(&sM[0][i]);
-    const float4 by = *reinterpret_cast<const float4*>(&sM[1][i]);
-    const float4 bz = *reinterpret_cast<const float4*>(&sM[2][i]);
-    const float4 nx = *reinterpret_cast<const float4*>(&sM[3][i]);
-    const float4 ny = *reinterpret_cast<const float4*>(&sM[4][i]);
-    const float4 nz = *reinterpret_cast<const float4*>(&sM[5][i]);
+    const float4 bx = nbx, by = nby, bz = nbz, nx = nnx, ny = nny, nz = nnz;
+    if (i + 4 < tn4) {
+      nbx = *reinterpret_cast<const float4*>(&sM[0][i + 4]);
+      nby = *reinterpret_cast<const float4*>(&sM[1][i + 4]);
+      nbz = *reinterpret_cast<const float4*>(&sM[2][i + 4]);
+      nnx = *reinterpret_cast<const float4*>(&sM[3][i + 4]);
+      nny = *reinterpret_cast<const float4*>(&sM[4][i + 4]);
+      nnz = *reinterpret_cast<const float4*>(&sM[5][i + 4]);
+    }
     float2 d[2];
 #pragma unroll
     for (int g = 0; g < 2; ++g) {
@@ -1301,8 +1309,8 @@ __device__ __noinline__ void pairloop_select(const PairMeta& m, const double* __
 // iteration count to within one chunk (the wave schedule of round 1 evaluated 1.34x the sample sets the loop needs).
 // Entries beyond the last chunk are never written: k_sel_scan finds the same stop index and reads nothing past it.
 // SELECT: the block also runs the selection of its pair (pairloop_select below) -- no selection kernels.
-template <int K, int MODE, bool SELECT>
-__global__ void __launch_bounds__(EVP_THREADS, 10)
+template <int K, int MODE, bool SELECT, int MINB = 8>
+__global__ void __launch_bounds__(EVP_THREADS, MINB)
 k_eval_pairloop(const PairMeta* __restrict__ meta, const double* __restrict__ Ya, const double* __restrict__ Yb,
                 const float4* __restrict__ Ya4, const float4* __restrict__ Yb4, int Nmax,
                 const int32_t* __restrict__ samples, uint64_t seed, uint32_t pair_id0, int H, int method,
@@ -2343,6 +2351,26 @@ static int launch_eval_pairloop_mode(pre3_ctx* ctx, const RansacBuffers& b, cons
   k_eval_pairloop<KK, MODE, SELECT><<<b.P, EVP_THREADS, 0, ctx->stream>>>(                                          \
       b.meta, b.Ya, b.Yb, b.Ya4, b.Yb4, b.Nmax, b.samples, o.seed, b.pair_id0, o.H, o.method, o.max_iteration,     \
       b.tab.tab, b.counts, b.states, b.stop, dres, dmasks, b.Nmax, scratch)
+  // PRE3_EVP_MINB: blocks per SM the k = 5 / find_transform_matrix instance is compiled for (occupancy vs spills)
+  // (measured at the sequence shape, eval ms per 4096 pairs: 8 -> 0.338, 10 -> 0.351, 12 -> 0.382, 16 -> 0.393: the
+  // spills of the fp64 fit cost more than the extra warps bring)
+  static const int minb = getenv("PRE3_EVP_MINB") ? atoi(getenv("PRE3_EVP_MINB")) : 8;
+  if (o.k == 5 && MODE == 0 && !SELECT && minb != 8) {
+#define PRE3_EVALPB(MB)                                                                                            \
+  k_eval_pairloop<5, 0, false, MB><<<b.P, EVP_THREADS, 0, ctx->stream>>>(                                          \
+      b.meta, b.Ya, b.Yb, b.Ya4, b.Yb4, b.Nmax, b.samples, o.seed, b.pair_id0, o.H, o.method, o.max_iteration,     \
+      b.tab.tab, b.counts, b.states, b.stop, dres, dmasks, b.Nmax, scratch)
+    if (minb == 6) PRE3_EVALPB(6);
+    else if (minb == 10) PRE3_EVALPB(10);
+    else if (minb == 12) PRE3_EVALPB(12);
+    else if (minb == 14) PRE3_EVALPB(14);
+    else if (minb == 16) PRE3_EVALPB(16);
+    else return fail(ctx, PRE3_ERR_ARG, "PRE3_EVP_MINB: 6, 8, 10, 12, 14 or 16");
+#undef PRE3_EVALPB
+    count_launch(ctx);
+    PRE3_CUDA(cudaGetLastError());
+    return PRE3_OK;
+  }
   switch (o.k) {
     case 3: PRE3_EVALP(3); break;
     case 4: PRE3_EVALP(4); break;
