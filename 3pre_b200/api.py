@@ -262,6 +262,53 @@ class Context:
                                                 _ptr(n)))
         return [(pairs[p, : n[p]].copy(), score[p, : n[p]].copy()) for p in range(P)]
 
+    def siftmatch_sweep(self, L1, L2, thresh: float = 1.5, k2_count=None):
+        """One set L1 (K1,ND) against P sets L2 (P,K2,ND) -- the loop of find_consistent_sift_matches.m:39-65.
+        Returns list of (pairs, score) per later frame."""
+        L1, L2 = _c(L1), _c(L2)
+        if L1.dtype != L2.dtype or L1.dtype not in _CLS:
+            raise ValueError("Unsupported numeric class")
+        K1, ND = L1.shape
+        P, K2 = L2.shape[0], L2.shape[1]
+        pairs = np.zeros((max(P, 1), max(K1, 1), 2), np.int32)
+        score = np.zeros((max(P, 1), max(K1, 1)), np.float64)
+        n = np.zeros(max(P, 1), np.int32)
+        k2c = None if k2_count is None else _c(k2_count, np.int32)
+        self._ck(self._lib.pre3_siftmatch_sweep(self._h, _ptr(L1), _ptr(L2), _CLS[L1.dtype], P, K1, K2, ND, _ptr(k2c),
+                                                float(thresh), _ptr(pairs), _ptr(score), _ptr(n)))
+        return [(pairs[p, : n[p]].copy(), score[p, : n[p]].copy()) for p in range(P)]
+
+    def siftmatch_sweep_dev(self, L1, L2, pairs, score, n_out, thresh=1.5, k2_count=None):
+        import torch
+        cls = {torch.float64: L.CLASS_DOUBLE, torch.float32: L.CLASS_SINGLE, torch.int8: L.CLASS_INT8,
+               torch.uint8: L.CLASS_UINT8}[L1.dtype]
+        K1, ND = L1.shape
+        P, K2 = L2.shape[0], L2.shape[1]
+        self._ck(self._lib.pre3_siftmatch_sweep_dev(self._h, _ptr(L1), _ptr(L2), cls, P, K1, K2, ND, _ptr(k2_count),
+                                                    float(thresh), _ptr(pairs), _ptr(score), _ptr(n_out)))
+
+    def matching_sift_based_batch(self, des1, des2, h, S11, pos2, f_count=None, k2_count=None, thresh: float = 1.5):
+        """matching_sift_based.m:104-135 for P frames.  des1 (P,F,ND) descriptors of the predicted features, des2
+        (P,K2,ND) Descriptor_RAW, h (P,F,2), S11 (P,F) (NaN = empty S), pos2 (P,K2,2).  Returns a dict: ic (P,F) bool,
+        z (P,F,2) (NaN where not compatible), match (P,F) 0-based k2 | -1, n_match (P,), n_discarded (P,)."""
+        d1, d2 = _c(des1), _c(des2)
+        if d1.dtype != d2.dtype or d1.dtype not in _CLS:
+            raise ValueError("Unsupported numeric class")
+        P, F, ND = d1.shape
+        K2 = d2.shape[1]
+        h, S11, pos2 = _c(h, np.float64), _c(S11, np.float64), _c(pos2, np.float64)
+        Pm, Fm = max(P, 1), max(F, 1)
+        ic, z, mt = np.zeros((Pm, Fm), np.uint8), np.zeros((Pm, Fm, 2)), np.zeros((Pm, Fm), np.int32)
+        nm, nd = np.zeros(Pm, np.int32), np.zeros(Pm, np.int32)
+        fc = None if f_count is None else _c(f_count, np.int32)
+        k2c = None if k2_count is None else _c(k2_count, np.int32)
+        self._ck(self._lib.pre3_matching_sift_based_batch(self._h, _ptr(d1), _ptr(d2), _CLS[d1.dtype], P, F, K2, ND,
+                                                          _ptr(fc), _ptr(k2c), _ptr(h), _ptr(S11), _ptr(pos2),
+                                                          float(thresh), _ptr(ic), _ptr(z), _ptr(mt), _ptr(nm),
+                                                          _ptr(nd)))
+        return {"ic": ic[:P, :F].astype(bool), "z": z[:P, :F], "match": mt[:P, :F], "n_match": nm[:P],
+                "n_discarded": nd[:P]}
+
     # ---- stage 2 ------------------------------------------------------------------------
     def find_transform_matrix(self, pset1, pset2):
         """pset (n,3).  Returns rot (3,3), trans (3,), state (find_transform_matrix.m:2-42)."""

@@ -388,6 +388,111 @@ int pre3_siftmatch_batch(pre3_ctx* ctx, const void* L1, const void* L2, int cls,
   return PRE3_OK;
 }
 
+// ONE descriptor set L1 against P sets L2: the sweep of find_consistent_sift_matches.m:39-65 (the first frame's good
+// descriptors against every later frame).  L1 is converted for the tensor cores once and stays L2-resident; the rest is
+// the batched matcher.
+int pre3_siftmatch_sweep_dev(pre3_ctx* ctx, const void* dL1, const void* dL2, int cls, int P, int K1, int K2, int ND,
+                             const int32_t* dk2_count, double thresh, int32_t* dpairs, double* dscore, int32_t* dn_out) {
+  PRE3_LIVE();
+  PRE3_TRY(check_match_args(ctx, dL1, dL2, cls, P, K1, K2, ND));
+  PRE3_NEED(dn_out != nullptr, "n_out missing");
+  if (P == 0) return PRE3_OK;
+  PRE3_TRY(ws_reserve(ctx, match_ws_bytes(cls, P, K1, K2, ND)));
+  MatchRow* rows = nullptr;
+  ctx->l1_shared = 1;
+  int rc = PRE3_OK;
+  if (K1 > 0) rc = match_impl(ctx, dL1, dL2, cls, P, K1, K2, ND, nullptr, dk2_count, thresh, dscore != nullptr, &rows);
+  ctx->l1_shared = 0;
+  PRE3_TRY(rc);
+  return launch_match_compact(ctx, rows, P, K1, nullptr, dpairs, dscore, dn_out, nullptr, nullptr, K2, nullptr, nullptr);
+}
+
+int pre3_siftmatch_sweep(pre3_ctx* ctx, const void* L1, const void* L2, int cls, int P, int K1, int K2, int ND,
+                         const int32_t* k2_count, double thresh, int32_t* pairs, double* score, int32_t* n_out) {
+  PRE3_LIVE();
+  PRE3_TRY(check_match_args(ctx, L1, L2, cls, P, K1, K2, ND));
+  PRE3_NEED(n_out != nullptr, "n_out missing");
+  if (P == 0) return PRE3_OK;
+  const size_t es = class_size(cls);
+  const size_t b1 = (size_t)K1 * ND * es, b2 = (size_t)P * K2 * ND * es;
+  const size_t np = (size_t)P * K1;
+  PRE3_TRY(ws_reserve(ctx, match_ws_bytes(cls, P, K1, K2, ND) + align_up(b1) + align_up(b2) + align_up(4 * (size_t)P) +
+                               2 * align_up(8 * np) + align_up(4 * (size_t)P) + 4096));
+  char* d1 = ws_take<char>(ctx, b1);
+  char* d2 = ws_take<char>(ctx, b2);
+  int32_t* dk2 = k2_count ? ws_take<int32_t>(ctx, P) : nullptr;
+  int32_t* dpairs = ws_take<int32_t>(ctx, 2 * np);
+  double* dscore = ws_take<double>(ctx, np);
+  int32_t* dn = ws_take<int32_t>(ctx, P);
+  PRE3_TRY(h2d(ctx, d1, L1, b1));
+  PRE3_TRY(h2d(ctx, d2, L2, b2));
+  if (dk2) PRE3_TRY(h2d(ctx, dk2, k2_count, 4 * (size_t)P));
+  MatchRow* rows = nullptr;
+  ctx->l1_shared = 1;
+  int rc = PRE3_OK;
+  if (K1 > 0) rc = match_impl(ctx, d1, d2, cls, P, K1, K2, ND, nullptr, dk2, thresh, score != nullptr, &rows);
+  ctx->l1_shared = 0;
+  PRE3_TRY(rc);
+  PRE3_TRY(launch_match_compact(ctx, rows, P, K1, nullptr, dpairs, dscore, dn, nullptr, nullptr, K2, nullptr, nullptr));
+  if (pairs) PRE3_TRY(d2h(ctx, pairs, dpairs, 8 * np));
+  if (score) PRE3_TRY(d2h(ctx, score, dscore, 8 * np));
+  PRE3_TRY(d2h(ctx, n_out, dn, 4 * (size_t)P));
+  PRE3_CUDA(cudaStreamSynchronize(ctx->stream));
+  return PRE3_OK;
+}
+
+// matching_sift_based.m:104-135 for P frames: des1 = the descriptors of the PREDICTED map features (F per frame,
+// f_count valid), des2 = Descriptor_RAW of the frame (K2, k2_count valid), h = predicted image positions (2 x F),
+// S11 = S(1,1) of every predicted feature (NaN: S empty -> radius 40), pos2 = SCALE_ORIENT_POS_RAW(1:2,:) (2 x K2).
+// siftmatch (default threshold 1.5) followed by the search-region gate; outputs per predicted feature.
+int pre3_matching_sift_based_batch(pre3_ctx* ctx, const void* des1, const void* des2, int cls, int P, int F, int K2,
+                                   int ND, const int32_t* f_count, const int32_t* k2_count, const double* h,
+                                   const double* S11, const double* pos2, double thresh, uint8_t* ic, double* z,
+                                   int32_t* match, int32_t* n_match, int32_t* n_discarded) {
+  PRE3_LIVE();
+  PRE3_TRY(check_match_args(ctx, des1, des2, cls, P, F, K2, ND));
+  PRE3_NEED(P == 0 || F == 0 || (h && S11 && ic && z && match), "null pointer");
+  PRE3_NEED(P == 0 || K2 == 0 || pos2, "null pointer");
+  if (P == 0) return PRE3_OK;
+  const size_t es = class_size(cls);
+  const size_t b1 = (size_t)P * F * ND * es, b2 = (size_t)P * K2 * ND * es;
+  const size_t np = (size_t)P * F;
+  PRE3_TRY(ws_reserve(ctx, match_ws_bytes(cls, P, F, K2, ND) + align_up(b1) + align_up(b2) + 4 * align_up(4 * (size_t)P) +
+                               align_up(8 * np) + 2 * align_up(16 * np) + align_up(8 * np) + align_up(16 * (size_t)P * K2) +
+                               align_up(np) + align_up(4 * np) + 8192));
+  char* d1 = ws_take<char>(ctx, b1);
+  char* d2 = ws_take<char>(ctx, b2);
+  int32_t* dk1 = f_count ? ws_take<int32_t>(ctx, P) : nullptr;
+  int32_t* dk2 = k2_count ? ws_take<int32_t>(ctx, P) : nullptr;
+  int32_t* dpairs = ws_take<int32_t>(ctx, 2 * np);
+  int32_t* dn = ws_take<int32_t>(ctx, P);
+  int32_t* dnd = ws_take<int32_t>(ctx, P);
+  double* dh = ws_take<double>(ctx, 2 * np);
+  double* dz = ws_take<double>(ctx, 2 * np);
+  double* dS = ws_take<double>(ctx, np);
+  double* dpos = ws_take<double>(ctx, 2 * (size_t)P * K2);
+  uint8_t* dic = ws_take<uint8_t>(ctx, np);
+  int32_t* dm = ws_take<int32_t>(ctx, np);
+  PRE3_TRY(h2d(ctx, d1, des1, b1));
+  PRE3_TRY(h2d(ctx, d2, des2, b2));
+  if (dk1) PRE3_TRY(h2d(ctx, dk1, f_count, 4 * (size_t)P));
+  if (dk2) PRE3_TRY(h2d(ctx, dk2, k2_count, 4 * (size_t)P));
+  PRE3_TRY(h2d(ctx, dh, h, 16 * np));
+  PRE3_TRY(h2d(ctx, dS, S11, 8 * np));
+  PRE3_TRY(h2d(ctx, dpos, pos2, 16 * (size_t)P * K2));
+  MatchRow* rows = nullptr;
+  if (F > 0) PRE3_TRY(match_impl(ctx, d1, d2, cls, P, F, K2, ND, dk1, dk2, thresh, 0, &rows));
+  PRE3_TRY(launch_match_compact(ctx, rows, P, F, dk1, dpairs, nullptr, dn, nullptr, nullptr, K2, nullptr, nullptr));
+  PRE3_TRY(launch_match_gate(ctx, dpairs, dn, P, F, K2, dh, dS, dpos, dic, dz, dm, dnd));
+  PRE3_TRY(d2h(ctx, ic, dic, np));
+  PRE3_TRY(d2h(ctx, z, dz, 16 * np));
+  PRE3_TRY(d2h(ctx, match, dm, 4 * np));
+  if (n_match) PRE3_TRY(d2h(ctx, n_match, dn, 4 * (size_t)P));
+  if (n_discarded) PRE3_TRY(d2h(ctx, n_discarded, dnd, 4 * (size_t)P));
+  PRE3_CUDA(cudaStreamSynchronize(ctx->stream));
+  return PRE3_OK;
+}
+
 int pre3_siftmatch(pre3_ctx* ctx, const void* L1, const void* L2, int cls, int K1, int K2, int ND, double thresh,
                    int32_t* pairs, double* score, int32_t* n_out) {
   return pre3_siftmatch_batch(ctx, L1, L2, cls, 1, K1, K2, ND, nullptr, nullptr, thresh, pairs, score, n_out);

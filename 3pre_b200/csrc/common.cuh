@@ -34,6 +34,7 @@ struct pre3_ctx {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   int match_engine = PRE3_MATCH_AUTO;
+  int l1_shared = 0;  // set by the sweep entry points: ONE L1 descriptor set serves every problem of the batch
   int sm_count = 148;
   int64_t launches = 0;
   int64_t h2d_bytes = 0, d2h_bytes = 0;  // moved by the host-pointer whole-pair entry point (bench.py's e2e)

@@ -36,4 +36,9 @@ int launch_match_compact(pre3_ctx* ctx, const MatchRow* drows, int P, int K1, co
                          int32_t* dpairs, double* dscore, int32_t* dn_out, const double* dxyz1,
                          const double* dxyz2, int K2, double* dYa, double* dYb);
 
+// search-region gate of matching_sift_based.m:118-135 over the compacted match lists (P problems, F rows each)
+int launch_match_gate(pre3_ctx* ctx, const int32_t* dpairs, const int32_t* dn_match, int P, int F, int K2, const double* dh,
+                      const double* dS11, const double* dpos2, uint8_t* dic, double* dz, int32_t* dmatch,
+                      int32_t* dn_disc);
+
 }  // namespace pre3

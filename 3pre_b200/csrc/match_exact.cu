@@ -60,15 +60,16 @@ __global__ void __launch_bounds__(256)
 k_match_exact(const T* __restrict__ L1, const T* __restrict__ L2, int K1, int K2, int ND,
               const int32_t* __restrict__ k1c, const int32_t* __restrict__ k2c, float thresh,
               const int32_t* __restrict__ row_list, const int32_t* __restrict__ row_list_n,
-              MatchRow* __restrict__ rows) {
+              MatchRow* __restrict__ rows, int a_shared) {
   __shared__ T sa[MT][MB + 1];
   __shared__ T sb[MT][MB + 1];
   const int p = blockIdx.y;
-  const int n1 = k1c ? min(k1c[p], K1) : K1;
+  const int pa = a_shared ? 0 : p;  // one L1 set for every problem (find_consistent_sift_matches.m:39-65)
+  const int n1 = k1c ? min(k1c[pa], K1) : K1;
   const int n2 = k2c ? min(k2c[p], K2) : K2;
   const int row0 = blockIdx.x * MT;
   if (row0 >= n1) return;
-  const T* A = L1 + (size_t)p * K1 * ND;
+  const T* A = L1 + (size_t)pa * K1 * ND;
   const T* B = L2 + (size_t)p * K2 * ND;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   Top2<ACC> st[2];
@@ -154,7 +155,8 @@ template <typename T, typename ACC>
 __global__ void __launch_bounds__(RXB_THREADS)
 k_match_rows_exact_blk(const T* __restrict__ L1, const T* __restrict__ L2, int K1, int K2, int ND,
                        const int32_t* __restrict__ k2c, float thresh, const int32_t* __restrict__ row_list,
-                       const int32_t* __restrict__ row_list_n, int list_cap, MatchRow* __restrict__ rows) {
+                       const int32_t* __restrict__ row_list_n, int list_cap, MatchRow* __restrict__ rows,
+                       int a_shared) {
   __shared__ ACC sa[RX_ND];
   __shared__ Top2<ACC> sred[RXB_THREADS / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -163,7 +165,7 @@ k_match_rows_exact_blk(const T* __restrict__ L1, const T* __restrict__ L2, int K
     const int rid = row_list[w];
     const int p = rid / K1;
     const int n2 = k2c ? min(k2c[p], K2) : K2;
-    const T* a = L1 + (size_t)rid * ND;
+    const T* a = L1 + (size_t)(a_shared ? rid % K1 : rid) * ND;
     const T* B = L2 + (size_t)p * K2 * ND;
     __syncthreads();  // sa / sred of the previous row are no longer read
     for (int e = tid; e < RX_ND; e += RXB_THREADS) sa[e] = (ACC)a[e];
@@ -267,25 +269,25 @@ int launch_match_exact(pre3_ctx* ctx, const void* dL1, const void* dL2, int cls,
   switch (cls) {
     case PRE3_CLASS_DOUBLE:
       k_match_exact<double, double><<<grid, 256, 0, ctx->stream>>>((const double*)dL1, (const double*)dL2, K1, K2, ND,
-                                                                    dk1, dk2, thresh, nullptr, nullptr, drows);
+                                                                    dk1, dk2, thresh, nullptr, nullptr, drows, ctx->l1_shared);
       break;
     case PRE3_CLASS_SINGLE:
       k_match_exact<float, float><<<grid, 256, 0, ctx->stream>>>((const float*)dL1, (const float*)dL2, K1, K2, ND, dk1,
-                                                                  dk2, thresh, nullptr, nullptr, drows);
+                                                                  dk2, thresh, nullptr, nullptr, drows, ctx->l1_shared);
       break;
     case PRE3_CLASS_DOUBLE_F32:  // class double stored as float: double arithmetic
       k_match_exact<float, double><<<grid, 256, 0, ctx->stream>>>((const float*)dL1, (const float*)dL2, K1, K2, ND, dk1,
-                                                                   dk2, thresh, nullptr, nullptr, drows);
+                                                                   dk2, thresh, nullptr, nullptr, drows, ctx->l1_shared);
       break;
     case PRE3_CLASS_INT8:
       k_match_exact<signed char, int><<<grid, 256, 0, ctx->stream>>>((const signed char*)dL1, (const signed char*)dL2,
                                                                       K1, K2, ND, dk1, dk2, thresh, nullptr, nullptr,
-                                                                      drows);
+                                                                      drows, ctx->l1_shared);
       break;
     case PRE3_CLASS_UINT8:
       k_match_exact<unsigned char, int><<<grid, 256, 0, ctx->stream>>>((const unsigned char*)dL1,
                                                                         (const unsigned char*)dL2, K1, K2, ND, dk1,
-                                                                        dk2, thresh, nullptr, nullptr, drows);
+                                                                        dk2, thresh, nullptr, nullptr, drows, ctx->l1_shared);
       break;
     default:
       return fail(ctx, PRE3_ERR_CLASS, "Unsupported numeric class");
@@ -303,13 +305,13 @@ int launch_match_rows_exact(pre3_ctx* ctx, const void* dL1, const void* dL2, int
   const int blocks = 4 * ctx->sm_count;
   if (cls == PRE3_CLASS_DOUBLE)
     k_match_rows_exact_blk<double, double><<<blocks, RXB_THREADS, 0, ctx->stream>>>(
-        (const double*)dL1, (const double*)dL2, K1, K2, ND, dk2, thresh, drow_list, drow_list_n, list_cap, drows);
+        (const double*)dL1, (const double*)dL2, K1, K2, ND, dk2, thresh, drow_list, drow_list_n, list_cap, drows, ctx->l1_shared);
   else if (cls == PRE3_CLASS_SINGLE)
     k_match_rows_exact_blk<float, float><<<blocks, RXB_THREADS, 0, ctx->stream>>>(
-        (const float*)dL1, (const float*)dL2, K1, K2, ND, dk2, thresh, drow_list, drow_list_n, list_cap, drows);
+        (const float*)dL1, (const float*)dL2, K1, K2, ND, dk2, thresh, drow_list, drow_list_n, list_cap, drows, ctx->l1_shared);
   else if (cls == PRE3_CLASS_DOUBLE_F32)
     k_match_rows_exact_blk<float, double><<<blocks, RXB_THREADS, 0, ctx->stream>>>(
-        (const float*)dL1, (const float*)dL2, K1, K2, ND, dk2, thresh, drow_list, drow_list_n, list_cap, drows);
+        (const float*)dL1, (const float*)dL2, K1, K2, ND, dk2, thresh, drow_list, drow_list_n, list_cap, drows, ctx->l1_shared);
   else
     return fail(ctx, PRE3_ERR_CLASS, "row recheck: class must be double or single");
   count_launch(ctx);
@@ -323,6 +325,64 @@ int launch_match_compact(pre3_ctx* ctx, const MatchRow* drows, int P, int K1, co
   Span span__(ctx, T_COMPACT);
   if (P <= 0) return PRE3_OK;
   k_match_compact<<<P, 256, 0, ctx->stream>>>(drows, K1, dk1, dpairs, dscore, dn_out, dxyz1, dxyz2, K2, dYa, dYb);
+  count_launch(ctx);
+  PRE3_CUDA(cudaGetLastError());
+  return PRE3_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Search-region gate of the EKF's SIFT matcher (M/matching_sift_based.m:118-135), as a post-filter over the compacted
+// match list of each problem: match i = (k1, k2) is accepted as individually compatible iff
+//     norm(pos2(:,k2) - h(:,k1)) <= half_search_region_size_x,
+// half_search_region_size_x = ceil(3*sqrt(S(1,1))) of the i-th PREDICTED feature (the reference indexes S with the
+// loop counter over the matches, `features_info(index_in_info(i)).S`, :120 -- reproduced), 40 when that S is empty
+// (NaN here).  Accepted: ic(k1) = 1, z(:,k1) = pos2(:,k2), match(k1) = k2; the others are counted as discarded.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_match_gate(const int32_t* __restrict__ pairs, const int32_t* __restrict__ n_match, int P, int F, int K2,
+             const double* __restrict__ h, const double* __restrict__ S11, const double* __restrict__ pos2,
+             uint8_t* __restrict__ ic, double* __restrict__ z, int32_t* __restrict__ match, int32_t* __restrict__ n_disc) {
+  const int p = blockIdx.x;
+  const double QNAN = __longlong_as_double(0x7ff8000000000000LL);
+  for (int f = threadIdx.x; f < F; f += blockDim.x) {
+    ic[(size_t)p * F + f] = 0;
+    match[(size_t)p * F + f] = -1;
+    z[((size_t)p * F + f) * 2] = QNAN;
+    z[((size_t)p * F + f) * 2 + 1] = QNAN;
+  }
+  __syncthreads();
+  const int n = n_match[p];
+  int disc = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int k1 = pairs[((size_t)p * F + i) * 2], k2 = pairs[((size_t)p * F + i) * 2 + 1];
+    const double S = S11[(size_t)p * F + i];
+    const double radius = (S != S) ? 40.0 : ceil(3.0 * sqrt(S));
+    const double dx = pos2[((size_t)p * K2 + k2) * 2] - h[((size_t)p * F + k1) * 2];
+    const double dy = pos2[((size_t)p * K2 + k2) * 2 + 1] - h[((size_t)p * F + k1) * 2 + 1];
+    const double dist = sqrt(dx * dx + dy * dy);
+    if (dist <= radius) {
+      ic[(size_t)p * F + k1] = 1;
+      match[(size_t)p * F + k1] = k2;
+      z[((size_t)p * F + k1) * 2] = pos2[((size_t)p * K2 + k2) * 2];
+      z[((size_t)p * F + k1) * 2 + 1] = pos2[((size_t)p * K2 + k2) * 2 + 1];
+    } else {
+      ++disc;
+    }
+  }
+  __shared__ int s_disc;
+  if (threadIdx.x == 0) s_disc = 0;
+  __syncthreads();
+  if (disc) atomicAdd(&s_disc, disc);
+  __syncthreads();
+  if (threadIdx.x == 0) n_disc[p] = s_disc;
+}
+
+int launch_match_gate(pre3_ctx* ctx, const int32_t* dpairs, const int32_t* dn_match, int P, int F, int K2, const double* dh,
+                      const double* dS11, const double* dpos2, uint8_t* dic, double* dz, int32_t* dmatch,
+                      int32_t* dn_disc) {
+  Span span__(ctx, T_COMPACT);
+  if (P <= 0) return PRE3_OK;
+  k_match_gate<<<P, 256, 0, ctx->stream>>>(dpairs, dn_match, P, F, K2, dh, dS11, dpos2, dic, dz, dmatch, dn_disc);
   count_launch(ctx);
   PRE3_CUDA(cudaGetLastError());
   return PRE3_OK;

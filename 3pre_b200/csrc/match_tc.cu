@@ -311,13 +311,14 @@ k_tc_convert(const T* __restrict__ L, int K, int Kp, const int32_t* __restrict__
 
 // per pair: bounds of its two descriptor sets (fa[p], fb[p])
 __global__ void k_tc_pair_info(int P, const FrameInfo* __restrict__ fa, const FrameInfo* __restrict__ fb,
-                               PairInfo* __restrict__ info) {
+                               PairInfo* __restrict__ info, int a_shared) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P) return;
+  const int pa = a_shared ? 0 : p;
   PairInfo o;
-  o.amax_bits = fa[p].max_bits;
+  o.amax_bits = fa[pa].max_bits;
   o.bmax_bits = fb[p].max_bits;
-  o.bad = fa[p].bad | fb[p].bad;
+  o.bad = fa[pa].bad | fb[p].bad;
   o.pad = 0;
   info[p] = o;
 }
@@ -342,7 +343,7 @@ template <int EXP>
 __global__ void __launch_bounds__(THREADS, 1)
 k_tc_gemm_top2(const unsigned char* __restrict__ imgA, const unsigned char* __restrict__ imgB,
                const float* __restrict__ nrmB, const PairInfo* __restrict__ pinfo, int P, int K1p, int K2p,
-               Prop* __restrict__ prop) {
+               Prop* __restrict__ prop, int a_shared) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t base = smem_u32(smem);
   if (base & 1023u) __trap();  // SWIZZLE_128B tiles need 1024-byte alignment
@@ -393,7 +394,7 @@ k_tc_gemm_top2(const unsigned char* __restrict__ imgA, const unsigned char* __re
         const int ab = uc & 1;
         mbar_wait(smem_u32(&bars->a_empty[ab]), ((uc >> 1) & 1) ^ 1);
         mbar_expect_tx(smem_u32(&bars->a_full[ab]), (uint32_t)(nrb * BLK_BYTES));
-        tma_bulk_g2s(sA + ab * A_BUF_BYTES, imgA + ((size_t)p * K1p + (size_t)g * 2 * BLK) * (ND * 2),
+        tma_bulk_g2s(sA + ab * A_BUF_BYTES, imgA + ((size_t)(a_shared ? 0 : p) * K1p + (size_t)g * 2 * BLK) * (ND * 2),
                      (uint32_t)(nrb * BLK_BYTES), smem_u32(&bars->a_full[ab]));
         for (int j = 0; j < ntile; ++j, ++t) {
           if (EXP >= 5) continue;
@@ -638,7 +639,7 @@ template <int EXP, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 k_tc_gemm_pair(const unsigned char* __restrict__ imgA, const unsigned char* __restrict__ imgB,
                const unsigned char* __restrict__ extB, int ext_layout, int P, int K1p, int K2p,
-               Prop2* __restrict__ prop) {
+               Prop2* __restrict__ prop, int a_shared) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t base = smem_u32(smem);
   if (base & 1023u) __trap();
@@ -706,7 +707,7 @@ k_tc_gemm_pair(const unsigned char* __restrict__ imgA, const unsigned char* __re
         mbar_expect_tx(smem_u32(&bars->a_full[ab]), (uint32_t)(ns * BLK_BYTES));
         for (int sidx = 0; sidx < ns; ++sidx)
           tma_bulk_g2s(sA + (ab * 2 + sidx) * BLK_BYTES,
-                       imgA + ((size_t)p * K1p + (size_t)(4 * g + 2 * sidx + (int)rank) * BLK) * (ND * 2),
+                       imgA + ((size_t)(a_shared ? 0 : p) * K1p + (size_t)(4 * g + 2 * sidx + (int)rank) * BLK) * (ND * 2),
                        (uint32_t)BLK_BYTES, smem_u32(&bars->a_full[ab]));
         for (int j = 0; j < ntile; ++j, ++t) {
           const int st = (int)(t % P2_NSTAGE);
@@ -974,9 +975,10 @@ __device__ __forceinline__ void rescore_group(ACC (*sprod)[ND + 1], int p, int r
                                               const T* __restrict__ L1, const T* __restrict__ L2, int K1, int K2,
                                               int K1p, float thresh, const Prop* __restrict__ prop,
                                               const float* __restrict__ nrmA, const PairInfo& pi, int need_score,
-                                              int v2, MatchRow* __restrict__ rows, int32_t* __restrict__ row_list,
-                                              int32_t* __restrict__ row_list_n) {
+                                              int v2, int a_shared, MatchRow* __restrict__ rows,
+                                              int32_t* __restrict__ row_list, int32_t* __restrict__ row_list_n) {
   const int lane = threadIdx.x & 31;
+  const int pa = a_shared ? 0 : p;  // one L1 set for every problem
   const int nr = min(RS_ROWS, n1 - row0);
   const int k1 = row0 + lane;
   const bool mine = lane < nr;
@@ -997,7 +999,7 @@ __device__ __forceinline__ void rescore_group(ACC (*sprod)[ND + 1], int p, int r
   out.accept = 0;
   if (mine && n2 > 0) {
     my = prop[(size_t)p * K1p + k1];
-    na = (double)nrmA[(size_t)p * K1p + k1];
+    na = (double)nrmA[(size_t)pa * K1p + k1];
     const double nbm = (double)__uint_as_float(pi.bmax_bits);
     C = (double)(1.0625f * __uint_as_float(pi.amax_bits));
     const double ra = sqrt(na), rbm = sqrt(nbm);
@@ -1048,7 +1050,7 @@ __device__ __forceinline__ void rescore_group(ACC (*sprod)[ND + 1], int p, int r
 #pragma unroll
     for (int u = 0; u < 4; ++u)  // all loads of up to four rows in flight together
       if (rr[u] >= 0) {
-        load_row4<T, ACC>(L1 + ((size_t)p * K1 + row0 + rr[u]) * ND + 4 * lane, va[u]);
+        load_row4<T, ACC>(L1 + ((size_t)pa * K1 + row0 + rr[u]) * ND + 4 * lane, va[u]);
         load_row4<T, ACC>(L2 + ((size_t)p * K2 + ii[u]) * ND + 4 * lane, vb[u]);
       }
 #pragma unroll
@@ -1101,18 +1103,18 @@ __global__ void __launch_bounds__(32)
 k_tc_rescore(const T* __restrict__ L1, const T* __restrict__ L2, int K1, int K2, int K1p, int K2p,
              const int32_t* __restrict__ k1c, const int32_t* __restrict__ k2c, float thresh,
              const Prop* __restrict__ prop, const float* __restrict__ nrmA, const PairInfo* __restrict__ info,
-             int need_score, int v2, MatchRow* __restrict__ rows, int32_t* __restrict__ row_list,
+             int need_score, int v2, int a_shared, MatchRow* __restrict__ rows, int32_t* __restrict__ row_list,
              int32_t* __restrict__ row_list_n) {
   __shared__ ACC sprod[RS_ROWS][ND + 1];
   const int p = blockIdx.y;
-  const int n1 = k1c ? max(0, min(k1c[p], K1)) : K1;
+  const int n1 = k1c ? max(0, min(k1c[a_shared ? 0 : p], K1)) : K1;
   const int n2 = k2c ? max(0, min(k2c[p], K2)) : K2;
   const PairInfo pi = info[p];
   for (int grp = 0; grp < RS_GROUPS; ++grp) {
     const int row0 = (blockIdx.x * RS_GROUPS + grp) * RS_ROWS;
     if (row0 >= n1) return;
-    rescore_group<T, ACC>(sprod, p, row0, n1, n2, L1, L2, K1, K2, K1p, thresh, prop, nrmA, pi, need_score, v2, rows,
-                          row_list, row_list_n);
+    rescore_group<T, ACC>(sprod, p, row0, n1, n2, L1, L2, K1, K2, K1p, thresh, prop, nrmA, pi, need_score, v2, a_shared,
+                          rows, row_list, row_list_n);
     __syncwarp();  // sprod is reused by the next group
   }
 }
@@ -1154,7 +1156,8 @@ int launch_match_tc(pre3_ctx* ctx, const void* dL1, const void* dL2, int cls, in
   // pair p - 1: half the conversion traffic of 2 P independent sets.
   const bool seq = dL2 == nullptr;
   if (seq && K1 != K2) return fail(ctx, PRE3_ERR_ARG, "sequence mode needs the same descriptor count per frame");
-  const int FA = seq ? P + 1 : P;  // descriptor sets behind dL1
+  const int shared = (!seq && ctx->l1_shared) ? 1 : 0;  // ONE L1 set for all P problems (the sweep entry points)
+  const int FA = seq ? P + 1 : (shared ? 1 : P);  // descriptor sets behind dL1
   static const int ext_layout = getenv("PRE3_TC_EXTLAYOUT") ? atoi(getenv("PRE3_TC_EXTLAYOUT")) : 0;
   // carve (1024-byte aligned operand images: TMA bulk copies need 16, the smem tiles 1024)
   auto take1k = [&](size_t bytes) {
@@ -1191,7 +1194,7 @@ int launch_match_tc(pre3_ctx* ctx, const void* dL1, const void* dL2, int cls, in
       k_tc_convert<float><<<g1, 256, 0, ctx->stream>>>((const float*)dL1, K1, K1p, dk1, imgA, extA, ext_layout, nrmA, fa);
       if (!seq) k_tc_convert<float><<<g2, 256, 0, ctx->stream>>>((const float*)dL2, K2, K2p, dk2, imgB, extB, ext_layout, nrmB, fb);
     }
-    k_tc_pair_info<<<(P + 255) / 256, 256, 0, ctx->stream>>>(P, fa, fb, info);
+    k_tc_pair_info<<<(P + 255) / 256, 256, 0, ctx->stream>>>(P, fa, fb, info, shared);
     count_launch(ctx, seq ? 2 : 3);
   }
   static const int use_v1 = getenv("PRE3_TC_V1") ? atoi(getenv("PRE3_TC_V1")) : 0;
@@ -1209,7 +1212,7 @@ int launch_match_tc(pre3_ctx* ctx, const void* dL1, const void* dL2, int cls, in
       attr_done = true;                                                                                            \
     }                                                                                                              \
     k_tc_gemm_pair<E, EP><<<grid, THREADS, P2_SMEM_BYTES, ctx->stream>>>(imgA, imgB, extB, ext_layout, P, K1p, K2p, \
-                                                                     reinterpret_cast<Prop2*>(prop));              \
+                                                                     reinterpret_cast<Prop2*>(prop), shared);      \
   } while (0)
     static const int epi_mode = getenv("PRE3_TC_EPI") ? atoi(getenv("PRE3_TC_EPI")) : 1;
     switch (exp_mode * 2 + (epi_mode ? 1 : 0)) {
@@ -1235,7 +1238,7 @@ int launch_match_tc(pre3_ctx* ctx, const void* dL1, const void* dL2, int cls, in
       PRE3_CUDA(cudaFuncSetAttribute(k_tc_gemm_top2<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); \
       attr_done = true;                                                                                          \
     }                                                                                                            \
-    k_tc_gemm_top2<E><<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(imgA, imgB, nrmB, info, P, K1p, K2p, prop);           \
+    k_tc_gemm_top2<E><<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(imgA, imgB, nrmB, info, P, K1p, K2p, prop, shared);   \
   } while (0)
     switch (exp_mode) {
       case 0: PRE3_GEMM(0); break;
@@ -1257,15 +1260,15 @@ int launch_match_tc(pre3_ctx* ctx, const void* dL1, const void* dL2, int cls, in
     if (cls == PRE3_CLASS_DOUBLE)
       k_tc_rescore<double, double><<<g, 32, 0, ctx->stream>>>((const double*)dL1, (const double*)dL2, K1, K2,
                                                                           K1p, K2p, dk1, dk2, thresh, prop, nrmA, info,
-                                                                          need_score, v2, drows, list, list_n);
+                                                                          need_score, v2, shared, drows, list, list_n);
     else if (cls == PRE3_CLASS_DOUBLE_F32)
       k_tc_rescore<float, double><<<g, 32, 0, ctx->stream>>>((const float*)dL1, (const float*)dL2, K1, K2,
                                                                          K1p, K2p, dk1, dk2, thresh, prop, nrmA, info,
-                                                                         need_score, v2, drows, list, list_n);
+                                                                         need_score, v2, shared, drows, list, list_n);
     else
       k_tc_rescore<float, float><<<g, 32, 0, ctx->stream>>>((const float*)dL1, (const float*)dL2, K1, K2,
                                                                         K1p, K2p, dk1, dk2, thresh, prop, nrmA, info,
-                                                                        need_score, v2, drows, list, list_n);
+                                                                        need_score, v2, shared, drows, list, list_n);
     count_launch(ctx);
   }
   PRE3_CUDA(cudaGetLastError());

@@ -77,6 +77,58 @@ def siftmatch(L1, L2, thresh=1.5, nargout=1):
     return matches
 
 
+def siftmatch_sweep(descriptor1, descriptors2, thresh=1.5):
+    """The loop of M/find_consistent_sift_matches.m:39-65: `matches = siftmatch(descriptor1, descriptor2)` for every
+    later frame, the first frame's (good) descriptors fixed.  descriptor1: ND x K1; descriptors2: list of ND x K2_f
+    matrices of the same class.  Returns the list of 2 x n double 1-based matches, one GPU call for all frames."""
+    d1 = np.atleast_2d(np.asarray(descriptor1))
+    ds = [np.atleast_2d(np.asarray(d)) for d in descriptors2]
+    for d in ds:
+        if d.shape[0] != d1.shape[0]:
+            raise MexError("L1 and L2 must have the same number of rows")
+        if d.dtype != d1.dtype:
+            raise MexError("L1 and L2 must be of the same class")
+    if d1.dtype not in (np.float64, np.float32, np.int8, np.uint8):
+        raise MexError("Unsupported numeric class")
+    if not ds:
+        return []
+    K2 = max(d.shape[1] for d in ds)
+    L2 = np.zeros((len(ds), max(K2, 1), d1.shape[0]), d1.dtype)
+    for f, d in enumerate(ds):
+        L2[f, : d.shape[1]] = d.T
+    out = context().siftmatch_sweep(np.ascontiguousarray(d1.T), L2, float(thresh),
+                                    k2_count=np.array([d.shape[1] for d in ds], np.int32))
+    return [(p.T + 1).astype(np.float64) for p, _ in out]
+
+
+def matching_sift_based(SCAN_SIFT, features_info, step_global=0):
+    """features_info = matching_sift_based(im, features_info, cam)  (M/matching_sift_based.m:27-151).  The reference
+    loads SCAN_SIFT (fields Descriptor_RAW: ND x K2, SCALE_ORIENT_POS_RAW: >=2 x K2) from the step's .mat file; here
+    it is an argument.  features_info: list of dicts (h, S, Descriptor, ...).  Matched and gated features get
+    individually_compatible = 1, z, last_visible and the refreshed Descriptor (:125-129); everything else is left as
+    it was.  Returns (features_info, discarded_sift_match)."""
+    des2 = np.atleast_2d(np.asarray(_field(SCAN_SIFT, "Descriptor_RAW")))
+    pos = np.asarray(_field(SCAN_SIFT, "SCALE_ORIENT_POS_RAW"), np.float64)
+    idx = [i for i, fi in enumerate(features_info) if np.size(fi.get("h", ())) > 0]  # :108-113
+    if not idx:
+        return features_info, 0  # :114-116
+    des1 = np.stack([np.asarray(features_info[i]["Descriptor"]).reshape(-1) for i in idx]).astype(des2.dtype)
+    h = np.stack([np.asarray(features_info[i]["h"], np.float64).reshape(-1)[:2] for i in idx])
+    S11 = np.array([np.asarray(features_info[i]["S"], np.float64)[0, 0] if np.size(features_info[i].get("S", ())) else
+                    np.nan for i in idx])
+    r = context().matching_sift_based_batch(des1[None], np.ascontiguousarray(des2.T)[None], h[None], S11[None],
+                                            np.ascontiguousarray(pos[:2].T)[None])
+    for j, i in enumerate(idx):
+        if r["ic"][0, j]:
+            k2 = int(r["match"][0, j])
+            fi = features_info[i]
+            fi["individually_compatible"] = 1
+            fi["z"] = r["z"][0, j].copy()
+            fi["last_visible"] = step_global
+            fi["Descriptor"] = des2[:, k2].copy()
+    return features_info, int(r["n_discarded"][0])
+
+
 def find_transform_matrix(pset1, pset2):
     """[rot, trans, state] = find_transform_matrix(pset1, pset2)
     (M/mex_files/RANSAC_CALCULATION/find_transform_matrix.m:2-42); pset: 3 x n."""

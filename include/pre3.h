@@ -146,6 +146,29 @@ PRE3_API int pre3_measure_fp32_peak_mode(pre3_ctx *ctx, int mode, double *tflops
 PRE3_API int pre3_siftmatch(pre3_ctx *ctx, const void *L1, const void *L2, int cls, int K1, int K2,
                    int ND, double thresh, int32_t *pairs, double *score, int32_t *n_out);
 
+/* Callers of siftmatch.
+ * pre3_siftmatch_sweep: ONE descriptor set L1 (ND x K1) against P sets L2 (each ND x K2, k2_count valid) -- the loop of
+ * M/find_consistent_sift_matches.m:39-65, `matches = siftmatch(descriptor1, descriptor2)` with the first frame's
+ * descriptors fixed.  Outputs as pre3_siftmatch_batch (P x K1 x 2 pairs, P x K1 scores, P counts); L1 is converted for
+ * the tensor cores once.
+ * pre3_matching_sift_based_batch: M/matching_sift_based.m:104-135 for P frames -- des1 = descriptors of the predicted
+ * map features (ND x F per frame, f_count valid), des2 = Descriptor_RAW (ND x K2), siftmatch with `thresh` (the reference
+ * uses the default 1.5), then the search-region gate :119-135: match i = (k1, k2) becomes individually compatible iff
+ * norm(pos2(:,k2) - h(:,k1)) <= ceil(3*sqrt(S11(i))) (40 when S11(i) is NaN = empty S; the reference indexes S with the
+ * loop counter i over the matches, reproduced).  h: P x F x 2, S11: P x F, pos2: P x K2 x 2 (column-major 2 x n each).
+ * Outputs per predicted feature: ic (P x F, 0/1), z (P x F x 2: pos2 of the match, NaN where ic = 0), match (P x F:
+ * 0-based k2 or -1); per frame: n_match (matches before the gate), n_discarded (StatData.DISCARDED_SIFT_MATCH). */
+PRE3_API int pre3_siftmatch_sweep(pre3_ctx *ctx, const void *L1, const void *L2, int cls, int P, int K1, int K2, int ND,
+                                  const int32_t *k2_count, double thresh, int32_t *pairs, double *score,
+                                  int32_t *n_out);
+PRE3_API int pre3_siftmatch_sweep_dev(pre3_ctx *ctx, const void *dL1, const void *dL2, int cls, int P, int K1, int K2,
+                                      int ND, const int32_t *dk2_count, double thresh, int32_t *dpairs, double *dscore,
+                                      int32_t *dn_out);
+PRE3_API int pre3_matching_sift_based_batch(pre3_ctx *ctx, const void *des1, const void *des2, int cls, int P, int F,
+                                            int K2, int ND, const int32_t *f_count, const int32_t *k2_count,
+                                            const double *h, const double *S11, const double *pos2, double thresh,
+                                            uint8_t *ic, double *z, int32_t *match, int32_t *n_match,
+                                            int32_t *n_discarded);
 /* P independent (L1_p, L2_p) problems, each padded to K1 x K2 with the valid counts in
  * k1_count / k2_count (NULL = all K1 / K2 valid).  pairs: P x (2 x K1), score: P x K1,
  * n_out: P.  (find_consistent_sift_matches.m:39-65 and SIFT_match_save.m:33 in bulk.) */

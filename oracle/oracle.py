@@ -104,6 +104,26 @@ def siftmatch(L1, L2, thresh: float = 1.5):
     return pairs[:n].copy(), score[:n].copy()
 
 
+def matching_sift_based(des1, des2, h, S11, pos2, thresh: float = 1.5):
+    """matching_sift_based.m:117-150 for one frame: siftmatch, then the search-region gate.  des1 (F,ND) descriptors of
+    the predicted features, des2 (K2,ND), h (F,2), S11 (F,) with NaN for an empty S, pos2 (K2,2).  The reference reads
+    S with the LOOP COUNTER over the matches (:120 `features_info(index_in_info(i)).S`), restated as is.  norm() of
+    the 2-vector is sqrt(dx*dx + dy*dy).  Returns ic (F,) bool, z (F,2) NaN-filled, match (F,) 0-based | -1, n_match,
+    n_discarded."""
+    pairs, _ = siftmatch(des1, des2, thresh)
+    F = des1.shape[0]
+    ic, z, mt, disc = np.zeros(F, bool), np.full((F, 2), np.nan), np.full(F, -1, np.int32), 0
+    for i, (k1, k2) in enumerate(pairs):
+        S = S11[i]
+        radius = 40.0 if np.isnan(S) else np.ceil(3.0 * np.sqrt(S))  # :121-127
+        dx, dy = pos2[k2, 0] - h[k1, 0], pos2[k2, 1] - h[k1, 1]
+        if np.sqrt(dx * dx + dy * dy) <= radius:  # :128-129
+            ic[k1], z[k1], mt[k1] = True, pos2[k2], k2
+        else:
+            disc += 1  # :146
+    return ic, z, mt, len(pairs), disc
+
+
 def find_transform_matrix(pset1, pset2, idx=None):
     """find_transform_matrix.m:2-42.  pset: (n,3).  Returns rot(3,3), trans(3,), state."""
     p1, p2 = _f64(pset1), _f64(pset2)

@@ -201,3 +201,23 @@ def test_R2q(orc):
                        [2 * (b * d - a * c), 2 * (c * d + a * b), a * a - b * b - c * c + d * d]])
         assert np.abs(Rq - R).max() < 1e-12
     assert np.allclose(orc.R2q(np.diag([1.0, -1.0, -1.0])), [0, -1, 0, 0])
+
+
+def test_matching_gate_known_answer(orc):
+    """matching_sift_based.m:117-150 on a hand-made case: three predicted features with unambiguous matches; the
+    radius comes from S of the i-th PREDICTED feature (loop counter), 40 when S is empty."""
+    e = np.eye(8)
+    des1 = np.stack([10 * e[0], 10 * e[1], 10 * e[2]])
+    des2 = np.stack([10 * e[2], 10 * e[0], 10 * e[1], 10 * e[5]])          # matches: (0,1) (1,2) (2,0)
+    pos2 = np.array([[100.0, 100.0], [10.0, 10.0], [50.0, 50.0], [0.0, 0.0]])
+    h = np.array([[10.0, 49.0],      # dist to pos2[1] = 39 <= 40 (S empty)            -> compatible
+                  [50.0, 56.5],      # dist to pos2[2] = 6.5 > ceil(3*sqrt(4)) = 6       -> discarded
+                  [100.0, 91.0]])    # dist to pos2[0] = 9 <= ceil(3*sqrt(8.5)) = 9      -> compatible (<=)
+    S11 = np.array([np.nan, 4.0, 8.5])
+    ic, z, mt, nm, nd = orc.matching_sift_based(des1, des2, h, S11, pos2)
+    assert nm == 3 and nd == 1
+    np.testing.assert_array_equal(ic, [True, False, True])
+    np.testing.assert_array_equal(mt, [1, -1, 0])
+    np.testing.assert_array_equal(z[0], pos2[1])
+    np.testing.assert_array_equal(z[2], pos2[0])
+    assert np.isnan(z[1]).all()
