@@ -63,12 +63,18 @@ int match_impl(pre3_ctx* ctx, const void* dL1, const void* dL2, int cls, int P, 
                const int32_t* dk1, const int32_t* dk2, double thresh, int need_score, MatchRow** rows_out) {
   MatchRow* rows = ws_take<MatchRow>(ctx, (size_t)P * K1);
   const float th = (float)thresh;  // narrowed like the reference (siftmatch.c:87,:205)
-  bool tc = false;
-  if (ctx->match_engine != PRE3_MATCH_EXACT) tc = match_tc_supported(cls, K1, K2, ND);
-  if (ctx->match_engine == PRE3_MATCH_TC && !tc)
-    return fail(ctx, PRE3_ERR_ARG, "tensor-core matcher needs class double/single and ND == 128");
+  bool tc = false, ti = false;
+  if (ctx->match_engine != PRE3_MATCH_EXACT) {
+    tc = match_tc_supported(cls, K1, K2, ND);
+    // integer classes: exact kind::i8 GEMM (the 16-byte vector loads of its converter need aligned descriptor sets)
+    ti = match_i8_supported(cls, K1, K2, ND) && (((uintptr_t)dL1 | (uintptr_t)dL2) & 15u) == 0;
+  }
+  if (ctx->match_engine == PRE3_MATCH_TC && !tc && !ti)
+    return fail(ctx, PRE3_ERR_ARG, "tensor-core matcher needs ND == 128 (and 16-byte aligned int8 / uint8 descriptors)");
   if (tc) {
     PRE3_TRY(launch_match_tc(ctx, dL1, dL2, cls, P, K1, K2, ND, dk1, dk2, th, need_score, rows));
+  } else if (ti) {
+    PRE3_TRY(launch_match_i8(ctx, dL1, dL2, cls, P, K1, K2, ND, dk1, dk2, th, rows));
   } else {
     if (!dL2) {  // sequence mode: pair p = (set p, set p + 1) of dL1
       const size_t esz = cls == PRE3_CLASS_DOUBLE_F32 ? 4 : class_size(cls);

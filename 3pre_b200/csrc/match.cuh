@@ -30,6 +30,13 @@ size_t match_tc_workspace_bytes(int P, int K1, int K2);
 int launch_match_tc(pre3_ctx* ctx, const void* dL1, const void* dL2, int cls, int P, int K1, int K2, int ND,
                     const int32_t* dk1, const int32_t* dk2, float thresh, int need_score, MatchRow* drows);
 
+// Exact integer tensor-core matcher (tcgen05 kind::i8, s32 accumulators) for class int8 / uint8, ND == 128: writes the
+// final rows, nothing to rescore.  Descriptor pointers must be 16-byte aligned.
+bool match_i8_supported(int cls, int K1, int K2, int ND);
+size_t match_i8_workspace_bytes(int P, int K1, int K2);
+int launch_match_i8(pre3_ctx* ctx, const void* dL1, const void* dL2, int cls, int P, int K1, int K2, int ND,
+                    const int32_t* dk1, const int32_t* dk2, float thresh, MatchRow* drows);
+
 // rows -> compact (k1,k2) list in k1 order (siftmatch.c:238-246) and, optionally, the gathered
 // correspondences Ya = xyz1(:,k1), Yb = xyz2(:,k2) (SIFT_match_save.m:53).
 int launch_match_compact(pre3_ctx* ctx, const MatchRow* drows, int P, int K1, const int32_t* dk1,

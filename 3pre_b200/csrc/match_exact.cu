@@ -258,6 +258,7 @@ k_match_compact(const MatchRow* __restrict__ rows, int K1, const int32_t* __rest
 size_t match_workspace_bytes(int cls, int P, int K1, int K2, int ND) {
   size_t b = align_up(sizeof(MatchRow) * (size_t)P * K1) + 4096;
   if (match_tc_supported(cls, K1, K2, ND)) b += match_tc_workspace_bytes(P, K1, K2);
+  if (match_i8_supported(cls, K1, K2, ND)) b += match_i8_workspace_bytes(P, K1, K2);
   return b;
 }
 
