@@ -9,8 +9,8 @@ fallback: without the built library (or without a B200) every call raises.
 from . import _lib
 from ._lib import Pre3Error, RansacOpts, PairResult, Cam, EkfOpts, EkfResult, DrYeStat, FrameOpts
 from .api import (Context, R2q, make_opts, unpack_result, RESULT_DTYPE, make_cam, make_ekf_opts,
-                  EKF_RESULT_DTYPE, DR_YE_STAT_DTYPE, make_frame_opts)
+                  EKF_RESULT_DTYPE, DR_YE_STAT_DTYPE, make_frame_opts, COV_RESULT_DTYPE, unpack_cov)
 
-__all__ = ["Context", "Pre3Error", "RansacOpts", "PairResult", "R2q", "make_opts", "unpack_result", "RESULT_DTYPE",
+__all__ = ["Context", "Pre3Error", "RansacOpts", "PairResult", "R2q", "make_opts", "unpack_result", "RESULT_DTYPE", "COV_RESULT_DTYPE", "unpack_cov",
            "Cam", "EkfOpts", "EkfResult", "make_cam", "make_ekf_opts", "EKF_RESULT_DTYPE",
            "DrYeStat", "DR_YE_STAT_DTYPE", "FrameOpts", "make_frame_opts"]

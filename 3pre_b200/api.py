@@ -37,6 +37,9 @@ assert EKF_RESULT_DTYPE.itemsize == C.sizeof(EkfResult) == 32
 DR_YE_STAT_DTYPE = np.dtype([("error_mean", "<f8"), ("error_std", "<f8"), ("dist", "<f8"),
                              ("n_iteration_ransac", "<i4"), ("n_loops", "<i4")])
 assert DR_YE_STAT_DTYPE.itemsize == C.sizeof(DrYeStat) == 32
+COV_RESULT_DTYPE = np.dtype([("cov", "<f8", (49,)), ("G2tot", "<f8", (49,)), ("Gtot", "<f8", (7,)), ("dA_dz", "<f8", (42,)),
+                             ("Etot", "<f8"), ("s2", "<f8"), ("n", "<i4"), ("status", "<i4")])
+assert COV_RESULT_DTYPE.itemsize == 8 * (49 + 49 + 7 + 42 + 2) + 8
 
 
 def _ptr(a):
@@ -49,6 +52,13 @@ def _ptr(a):
 
 def _c(a, dtype=None):
     return np.ascontiguousarray(a, dtype=dtype)
+
+
+def unpack_cov(rec) -> dict:
+    """One COV_RESULT_DTYPE record -> MATLAB-shaped arrays."""
+    return {"cov": rec["cov"].reshape(7, 7).T.copy(), "G2tot": rec["G2tot"].reshape(7, 7).T.copy(),
+            "Gtot": rec["Gtot"].copy(), "dA_dz": rec["dA_dz"].reshape(6, 7).T.copy(), "Etot": float(rec["Etot"]),
+            "s2": float(rec["s2"]), "n": int(rec["n"]), "status": int(rec["status"])}
 
 
 def make_frame_opts(sigma=2.0, boundary=0, mode=0, rows=720, use_confidence=1) -> FrameOpts:
@@ -707,6 +717,28 @@ class Context:
         self._ck(self._lib.pre3_siftmatch_batch_dev(self._h, _ptr(L1), _ptr(L2), cls, P, K1, K2, ND, _ptr(k1_count),
                                                     _ptr(k2_count), float(thresh), _ptr(pairs), _ptr(score),
                                                     _ptr(n_out)))
+
+    def cov_est_ransac_batch(self, Ya, Yb, R, T, n_corr=None, masks=None):
+        """cov_est_RANSAC_deriv.m for P pairs.  Ya, Yb (P,Nmax,3); R (P,3,3) with Ya ~ R Yb + T; T (P,3); masks (P,Nmax)
+        = the winner's support set or None.  Returns a list of dicts: cov (7,7) over [T1 T2 T3 q1 q2 q3 q4], G2tot
+        (7,7), Gtot (7,), dA_dz (7,6), Etot, s2, n, status."""
+        ya, yb = _c(Ya, np.float64), _c(Yb, np.float64)
+        P, Nmax = ya.shape[0], ya.shape[1]
+        Rc = _c(np.asarray(R, np.float64).reshape(P, 3, 3).transpose(0, 2, 1)).reshape(P, 9)
+        Tc = _c(np.asarray(T, np.float64).reshape(P, 3))
+        nc = None if n_corr is None else _c(n_corr, np.int32)
+        mk = None if masks is None else _c(np.asarray(masks).astype(np.uint8))
+        out = np.zeros(max(P, 1), COV_RESULT_DTYPE)
+        self._ck(self._lib.pre3_cov_est_ransac_batch(self._h, _ptr(ya), _ptr(yb), _ptr(nc), _ptr(mk), P, Nmax, _ptr(Rc),
+                                                     _ptr(Tc), _ptr(out)))
+        return [unpack_cov(out[p]) for p in range(P)]
+
+    def cov_est_ransac_batch_dev(self, Ya, Yb, RT, rt_stride, out, n_corr=None, masks=None):
+        """CUDA tensors.  RT: tensor (or data pointer holder) whose element p * rt_stride starts R (9, column-major)
+        then T (3); out: (P, COV_RESULT_DTYPE.itemsize) uint8."""
+        self._ck(self._lib.pre3_cov_est_ransac_batch_dev(self._h, _ptr(Ya), _ptr(Yb), _ptr(n_corr), _ptr(masks),
+                                                         int(Ya.shape[0]), int(Ya.shape[1]), _ptr(RT), int(rt_stride),
+                                                         _ptr(out)))
 
     def ransac_batch_dev(self, Ya, Yb, opts: RansacOpts, res, n_corr=None, samples=None, masks=None):
         P, Nmax = Ya.shape[0], Ya.shape[1]

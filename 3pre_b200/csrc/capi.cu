@@ -10,6 +10,7 @@
 
 #include "common.cuh"
 #include "match.cuh"
+#include "cov.cuh"
 #include "ransac.cuh"
 
 using namespace pre3;
@@ -1040,6 +1041,54 @@ int pre3_sequence(pre3_ctx* ctx, const void* desc, int cls, const double* xyz, i
   if (F <= 1) return ctx ? PRE3_OK : PRE3_ERR_ARG;
   return pairs_host(ctx, desc, nullptr, cls, xyz, nullptr, F - 1, K, K, ND, k_count, nullptr, opts, pair_id0, res,
                     matches, masks, true);
+}
+
+// ================================================================================================
+// covariance of the RANSAC pose (cov_est_RANSAC_deriv.m)
+// ================================================================================================
+int pre3_cov_est_ransac_batch_dev(pre3_ctx* ctx, const double* dYa, const double* dYb, const int32_t* dn_corr,
+                                  const uint8_t* dmasks, int P, int Nmax, const double* dRT, int rt_stride,
+                                  pre3_cov_result* dout) {
+  PRE3_LIVE();
+  PRE3_NEED(P >= 0 && Nmax >= 0 && rt_stride >= 12, "bad sizes");
+  if (P == 0) return PRE3_OK;
+  PRE3_NEED(dYa && dYb && dRT && dout, "null pointer");
+  PRE3_TRY(ws_reserve(ctx, cov_workspace_bytes(P, Nmax)));
+  return launch_cov_est(ctx, dYa, dYb, dn_corr, dmasks, P, Nmax, dRT, rt_stride, dout);
+}
+
+int pre3_cov_est_ransac_batch(pre3_ctx* ctx, const double* Ya, const double* Yb, const int32_t* n_corr,
+                              const uint8_t* masks, int P, int Nmax, const double* R, const double* T,
+                              pre3_cov_result* out) {
+  PRE3_LIVE();
+  PRE3_NEED(P >= 0 && Nmax >= 0, "bad sizes");
+  if (P == 0) return PRE3_OK;
+  PRE3_NEED(Ya && Yb && R && T && out, "null pointer");
+  const size_t pts = (size_t)P * Nmax * 3 * sizeof(double);
+  PRE3_TRY(ws_reserve(ctx, cov_workspace_bytes(P, Nmax) + 2 * align_up(pts) + align_up((size_t)P * Nmax) +
+                               align_up(4 * (size_t)P) + align_up(96 * (size_t)P) +
+                               align_up(sizeof(pre3_cov_result) * (size_t)P) + 4096));
+  double* dYa = ws_take<double>(ctx, (size_t)P * Nmax * 3);
+  double* dYb = ws_take<double>(ctx, (size_t)P * Nmax * 3);
+  uint8_t* dm = masks ? ws_take<uint8_t>(ctx, (size_t)P * Nmax) : nullptr;
+  int32_t* dn = n_corr ? ws_take<int32_t>(ctx, P) : nullptr;
+  double* dRT = ws_take<double>(ctx, (size_t)P * 12);
+  pre3_cov_result* dout = ws_take<pre3_cov_result>(ctx, P);
+  std::vector<double> rt((size_t)P * 12);
+  for (int p = 0; p < P; ++p) {
+    for (int i = 0; i < 9; ++i) rt[(size_t)p * 12 + i] = R[(size_t)p * 9 + i];
+    for (int i = 0; i < 3; ++i) rt[(size_t)p * 12 + 9 + i] = T[(size_t)p * 3 + i];
+  }
+  PRE3_TRY(h2d(ctx, dYa, Ya, pts));
+  PRE3_TRY(h2d(ctx, dYb, Yb, pts));
+  if (dm) PRE3_TRY(h2d(ctx, dm, masks, (size_t)P * Nmax));
+  if (dn) PRE3_TRY(h2d(ctx, dn, n_corr, 4 * (size_t)P));
+  PRE3_TRY(h2d(ctx, dRT, rt.data(), 96 * (size_t)P));
+  PRE3_CUDA(cudaStreamSynchronize(ctx->stream));  // rt is a local
+  PRE3_TRY(launch_cov_est(ctx, dYa, dYb, dn, dm, P, Nmax, dRT, 12, dout));
+  PRE3_TRY(d2h(ctx, out, dout, sizeof(pre3_cov_result) * (size_t)P));
+  PRE3_CUDA(cudaStreamSynchronize(ctx->stream));
+  return PRE3_OK;
 }
 
 // ================================================================================================

@@ -225,6 +225,20 @@ def Calculate_V_Omega_RANSAC_my_version(DataPre, DataCurrent, **kw):
 # ---------------------------------------------------------------------------------------
 # the step after the path (SURVEY.md 8f rank 3): the EKF partial updates
 # ---------------------------------------------------------------------------------------
+def cov_est_RANSAC_deriv(Ya, Yb, R_ab, T_ab):
+    """res = cov_est_RANSAC_deriv(Ya, Yb, R_ab, T_ab)  (M/cov_est_RANSAC_deriv.m:1-244; call site
+    RANSAC_CALC_VER2.m:204-206, commented out in the reference).  Ya, Yb: 3 x n support set, Ya ~ R_ab*Yb + T_ab.
+    Returns the reference's struct as a dict (sm_cov_censi 7 x 7 over [T; q]) plus the intermediate sums."""
+    ya = _cols(Ya, 3, np.float64, "Ya")
+    yb = _cols(Yb, 3, np.float64, "Yb")
+    if ya.shape != yb.shape:
+        raise MexError("Ya and Yb must have the same size")
+    r = context().cov_est_ransac_batch(ya[None], yb[None], np.asarray(R_ab, np.float64).reshape(1, 3, 3),
+                                       np.asarray(T_ab, np.float64).reshape(1, 3))[0]
+    return {"sm_cov_censi": r["cov"], "Etot": r["Etot"], "Gtot": r["Gtot"], "G2tot": r["G2tot"], "dA_dz": r["dA_dz"],
+            "s2": r["s2"]}
+
+
 def update(x_km1_k, p_km1_k, H, R, z, h):
     """[x_k_k, p_k_k, K] = update(x_km1_k, p_km1_k, H, R, z, h)   (M/update.m:27-56).  H may be a scipy sparse
     matrix (the reference stacks sparse 2 x n blocks); K = 0 when z is empty (:54)."""

@@ -93,6 +93,20 @@ typedef struct {
   double T_hyp[3];
 } pre3_pair_result;
 
+/* Covariance of the RANSAC pose estimate (M/cov_est_RANSAC_deriv.m:1-244; call site, commented out in the reference,
+ * M/mex_files/RANSAC_CALCULATION/RANSAC_CALC_VER2.m:204-206).  State x = [T1 T2 T3 q1 q2 q3 q4] with q = R2q(R);
+ * all matrices column-major. */
+typedef struct pre3_cov_result {
+  double cov[49];    /* res.sm_cov_censi = dA_dz * blkdiag(R, R) * dA_dz'  (:215) */
+  double G2tot[49];  /* summed second derivatives d2E/dx2 (:156) */
+  double Gtot[7];    /* summed gradient (:153) */
+  double dA_dz[42];  /* 7 x 6: G2tot \ [d2E/dx dz_k] (:200) */
+  double Etot;       /* summed squared residuals (:150) */
+  double s2;         /* Etot / (k - 3) (:216-217) */
+  int32_t n;         /* k: support points used */
+  int32_t status;    /* 0 ok, 1 empty support set, 2 singular G2tot (a zero pivot) */
+} pre3_cov_result;
+
 /* ---- context ------------------------------------------------------------------- */
 /* device < 0 selects the current CUDA device.  Lazy one-time initialisation of the
  * stream / workspace arena, as a MEX file would do on first call and undo in mexAtExit
@@ -225,6 +239,20 @@ PRE3_API int pre3_ransac_batch(pre3_ctx *ctx, const double *Ya, const double *Yb
 PRE3_API int pre3_ransac_batch_dev(pre3_ctx *ctx, const double *dYa, const double *dYb,
                           const int32_t *dn_corr, int P, int Nmax, const pre3_ransac_opts *opts,
                           const int32_t *dsamples, pre3_pair_result *dres, uint8_t *dmasks);
+
+/* ---- covariance of the RANSAC pose -------------------------------------
+ * cov_est_RANSAC_deriv(M(BestFitIdx).SupportSet.Ya, M(BestFitIdx).SupportSet.Yb, R, T) for P pairs.  Ya, Yb: P x Nmax x 3
+ * correspondences (n_corr valid per pair, NULL: Nmax); masks: P x Nmax inlier flags of the winner = the SupportSet
+ * (NULL: every correspondence); R: P x 9 column-major, T: P x 3 with Ya ~ R*Yb + T.  The _dev form reads R and T as 12
+ * consecutive doubles per pair, rt_stride doubles apart: 12 for a packed array, sizeof(pre3_pair_result)/8 with dRT =
+ * &res[0].R to run on the records pre3_pairs_dev / pre3_ransac_batch_dev left on the device.  Nested central
+ * differences with eps 1e-6 (M/deriv.m:7-9): agreement with the reference is ~1e-6 relative, not bit for bit. */
+PRE3_API int pre3_cov_est_ransac_batch(pre3_ctx *ctx, const double *Ya, const double *Yb, const int32_t *n_corr,
+                                       const uint8_t *masks, int P, int Nmax, const double *R, const double *T,
+                                       pre3_cov_result *out);
+PRE3_API int pre3_cov_est_ransac_batch_dev(pre3_ctx *ctx, const double *dYa, const double *dYb,
+                                           const int32_t *dn_corr, const uint8_t *dmasks, int P, int Nmax,
+                                           const double *dRT, int rt_stride, pre3_cov_result *dout);
 
 /* ---- EKF partial updates around ransac_hypotheses (first part) -----
  * [x_k_k, p_k_k] = update(x, p, H, R, z, h) (M/update.m:27-56) for Fr frames, with z, h, H stacked from the features

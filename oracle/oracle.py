@@ -394,6 +394,20 @@ def features_xyz(sr, frames, sigma=2.0, boundary=0, mode=0, use_conf=1):
     return xyz[:K], keep[:K].astype(bool), idx[:n].copy(), int(oob.value)
 
 
+def cov_est_ransac_deriv(Ya, Yb, R, T):
+    """cov_est_RANSAC_deriv.m (pre3_oracle_cov.c).  Ya, Yb (n,3), R (3,3), T (3,).  Returns dict like
+    3pre_b200.api.unpack_cov."""
+    ya, yb = _f64(Ya), _f64(Yb)
+    r, t = _f64(np.asarray(R).reshape(3, 3)), _f64(np.asarray(T).reshape(3))
+    cov, G2, G, dA, sc = np.zeros(49), np.zeros(49), np.zeros(7), np.zeros(42), np.zeros(2)
+    f = lib().orc_cov_est_ransac_deriv
+    f.restype = C.c_int
+    st = f(_p(ya, C.c_double), _p(yb, C.c_double), C.c_int(ya.shape[0]), _p(r, C.c_double), _p(t, C.c_double),
+           _p(cov, C.c_double), _p(G2, C.c_double), _p(G, C.c_double), _p(dA, C.c_double), _p(sc, C.c_double))
+    return {"cov": cov.reshape(7, 7).T.copy(), "G2tot": G2.reshape(7, 7).T.copy(), "Gtot": G, "dA_dz": dA.reshape(6, 7).T.copy(),
+            "Etot": float(sc[0]), "s2": float(sc[1]), "n": ya.shape[0], "status": 2 if st else 0}
+
+
 def R2q(R):
     r = _f64(R).reshape(9)
     q = np.zeros(4)
