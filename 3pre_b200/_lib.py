@@ -107,6 +107,10 @@ SYMBOLS = {
     "pre3_siftmatch_batch_dev": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _I, _VP, _VP, _D, _VP, _VP, _VP]),
     "pre3_cov_est_ransac_batch": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, _VP, _VP, _VP]),
     "pre3_cov_est_ransac_batch_dev": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, _VP, _I, _VP]),
+    "pre3_ekf_predict_measurements_batch": (_I, [_VP, _I, _I, _I, _VP, _VP, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP,
+                                                 _VP, _VP]),
+    "pre3_ekf_predict_measurements_batch_dev": (_I, [_VP, _I, _I, _I, _VP, _VP, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP,
+                                                     _VP, _VP, _VP]),
     "pre3_siftmatch_sweep": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _I, _VP, _D, _VP, _VP, _VP]),
     "pre3_siftmatch_sweep_dev": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _I, _VP, _D, _VP, _VP, _VP]),
     "pre3_matching_sift_based_batch": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _D, _VP, _VP,

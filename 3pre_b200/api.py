@@ -692,6 +692,33 @@ class Context:
             _ptr(frames["z"]), _ptr(frames["h"] if h is None else h), _ptr(frames["Hcam"] if Hcam is None else Hcam),
             _ptr(frames["Hfeat"] if Hfeat is None else Hfeat), _ptr(hi)))
 
+    def ekf_predict_measurements_batch(self, x, cam, n_rows, n_cols, types, pos, has_h, h_in):
+        """rescue_hi_inliers.m:32-33 (predict_camera_measurements + calculate_derivatives at x) for Fr frames.
+        x (Fr,n); types, pos (Fr,F) int32; has_h (Fr,F) | None; h_in (Fr,F,2).  Returns h (Fr,F,2), has_h (Fr,F) bool,
+        predicted (Fr,F) bool, Hcam (Fr,F,13,2), Hfeat (Fr,F,6,2)."""
+        x = _c(x, np.float64)
+        ty, ps = _c(types, np.int32), _c(pos, np.int32)
+        Fr, n = x.shape
+        F = ty.shape[1]
+        hh = None if has_h is None else _c(np.asarray(has_h).astype(np.uint8))
+        hi = _c(h_in, np.float64)
+        h, has, pred = np.zeros((Fr, F, 2)), np.zeros((Fr, F), np.uint8), np.zeros((Fr, F), np.uint8)
+        Hc, Hf = np.zeros((Fr, F, 13, 2)), np.zeros((Fr, F, 6, 2))
+        c = make_cam(cam)
+        self._ck(self._lib.pre3_ekf_predict_measurements_batch(self._h, Fr, n, F, _ptr(x), C.byref(c), int(n_rows),
+                                                               int(n_cols), _ptr(ty), _ptr(ps), _ptr(hh), _ptr(hi),
+                                                               _ptr(h), _ptr(has), _ptr(pred), _ptr(Hc), _ptr(Hf)))
+        return h, has.astype(bool), pred.astype(bool), Hc, Hf
+
+    def ekf_predict_measurements_batch_dev(self, x, cam, n_rows, n_cols, types, pos, has_h, h_in, h_out, has_h_out,
+                                           predicted, Hcam, Hfeat):
+        """CUDA tensors, shapes as the host form; stream-ordered."""
+        Fr, n = x.shape
+        c = make_cam(cam)
+        self._ck(self._lib.pre3_ekf_predict_measurements_batch_dev(
+            self._h, Fr, n, int(types.shape[1]), _ptr(x), C.byref(c), int(n_rows), int(n_cols), _ptr(types), _ptr(pos),
+            _ptr(has_h), _ptr(h_in), _ptr(h_out), _ptr(has_h_out), _ptr(predicted), _ptr(Hcam), _ptr(Hfeat)))
+
     # ---- device-pointer entry points (torch CUDA tensors, stream-ordered, no sync) --------
     def pairs_dev(self, desc1, desc2, xyz1, xyz2, opts: RansacOpts, res, matches=None, masks=None, pair_id0=0,
                   k1_count=None, k2_count=None):

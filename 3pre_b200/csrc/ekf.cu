@@ -829,6 +829,167 @@ k_ekf_support_given(const double* __restrict__ xi, int n, pre3_cam cam, const in
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------
+// Re-prediction at x_k_k (M/@ekf_filter/rescue_hi_inliers.m:32-33): predict_camera_measurements.m:27-68 followed by
+// calculate_derivatives.m:27-59, one thread per feature.  Same specification as oracle/pre3_oracle_ekf.c
+// (orc_ekf_predict): inv() = Gauss-Jordan with partial pivoting, sin / cos = sincos_spec, products accumulated left to
+// right.  A feature that fails the field-of-view or image-bounds test keeps its previous h; H is produced for every
+// feature whose h is not empty, evaluated at that h (calculate_Hi_inverse_depth_my_version.m:29).
+// ---------------------------------------------------------------------------------------------
+template <int D>
+__device__ void inv_spec(const double* S, double* out) {  // row-major D x D
+  double a[D][2 * D];
+  for (int r = 0; r < D; ++r)
+    for (int c = 0; c < D; ++c) {
+      a[r][c] = S[r * D + c];
+      a[r][D + c] = (r == c) ? 1.0 : 0.0;
+    }
+  for (int col = 0; col < D; ++col) {
+    int pr = col;
+    double best = fabs(a[col][col]);
+    for (int r = col + 1; r < D; ++r)
+      if (fabs(a[r][col]) > best) best = fabs(a[r][col]), pr = r;
+    if (pr != col)
+      for (int c = 0; c < 2 * D; ++c) {
+        const double t = a[col][c];
+        a[col][c] = a[pr][c], a[pr][c] = t;
+      }
+    const double piv = a[col][col];
+    for (int c = 0; c < 2 * D; ++c) a[col][c] = a[col][c] / piv;
+    for (int r = 0; r < D; ++r) {
+      if (r == col) continue;
+      const double f = a[r][col];
+      for (int c = 0; c < 2 * D; ++c) a[r][c] = a[r][c] - f * a[col][c];
+    }
+  }
+  for (int r = 0; r < D; ++r)
+    for (int c = 0; c < D; ++c) out[r * D + c] = a[r][D + c];
+}
+
+__device__ void mm_spec(const double* A, int ra, int ca, const double* B, int cb, double* C) {  // row-major
+  for (int i = 0; i < ra; ++i)
+    for (int j = 0; j < cb; ++j) {
+      double s = A[i * ca] * B[j];
+      for (int k = 1; k < ca; ++k) s = s + A[i * ca + k] * B[k * cb + j];
+      C[i * cb + j] = s;
+    }
+}
+
+__global__ void __launch_bounds__(64)
+k_ekf_predict(const double* __restrict__ X, int n, pre3_cam cam, int nRows, int nCols, int F,
+              const int32_t* __restrict__ type, const int32_t* __restrict__ pos, const uint8_t* __restrict__ has_h_in,
+              const double* __restrict__ h_in, double* __restrict__ h_out, uint8_t* __restrict__ has_h_out,
+              uint8_t* __restrict__ predicted, double* __restrict__ Hcam, double* __restrict__ Hfeat) {
+  const int fr = blockIdx.y, i = blockIdx.x * 64 + threadIdx.x;
+  if (i >= F) return;
+  const double* x = X + (size_t)fr * n;
+  const size_t fi = (size_t)fr * F + i;
+  double Rw[9], Rrw[9];
+  q2r(x + 3, Rw);
+  inv_spec<3>(Rw, Rrw);
+  const int ty = type[fi];
+  const double* y = x + pos[fi];
+  double a[3], st = 0, ct = 0, sp = 0, cp = 0, rho = 1.0;
+  if (ty == 0) {
+    sincos_spec(y[3], st, ct);
+    sincos_spec(y[4], sp, cp);
+    const double mi[3] = {cp * st, -sp, cp * ct};
+    rho = y[5];
+    for (int k = 0; k < 3; ++k) a[k] = (y[k] - x[k]) * rho + mi[k];
+  } else {
+    for (int k = 0; k < 3; ++k) a[k] = y[k] - x[k];
+  }
+  double hrl[3];
+  if (ty == 0) {
+    for (int k = 0; k < 3; ++k) hrl[k] = (Rw[k] * a[0] + Rw[3 + k] * a[1]) + Rw[6 + k] * a[2];  // r_wc' (hi_inverse_depth.m:33)
+  } else {
+    mm_spec(Rrw, 3, 3, a, 1, hrl);                                                                // inv(r_wc) (hi_cartesian.m:33)
+  }
+  const double PI = 3.14159265358979323846;
+  bool ok = true;
+  const double ax = atan2(hrl[0], hrl[2]) * 180 / PI, ay = atan2(hrl[1], hrl[2]) * 180 / PI;
+  if (ax < -60 || ax > 60 || ay < -60 || ay > 60) ok = false;
+  double ud = 0, vd = 0;
+  if (ok) {
+    const double u = cam.Cx + (hrl[0] / hrl[2]) * cam.f, v = cam.Cy + (hrl[1] / hrl[2]) * cam.f;
+    const double xu = (u - cam.Cx) / cam.f, yu = (v - cam.Cy) / cam.f;
+    const double ru = sqrt(xu * xu + yu * yu);
+    const double ru2 = ru * ru;
+    const double Dd = (1.0 + cam.k1 * ru2) + cam.k2 * (ru2 * ru2);
+    ud = (xu * Dd) * cam.f + cam.Cx, vd = (yu * Dd) * cam.f + cam.Cy;
+    if (!(ud > 0 && ud < nCols && vd > 0 && vd < nRows)) ok = false;
+  }
+  const bool has = ok || (has_h_in ? has_h_in[fi] != 0 : true);
+  predicted[fi] = ok ? 1 : 0;
+  has_h_out[fi] = has ? 1 : 0;
+  const double uu = ok ? ud : h_in[2 * fi], vv = ok ? vd : h_in[2 * fi + 1];
+  h_out[2 * fi] = uu;
+  h_out[2 * fi + 1] = vv;
+  double* Hc = Hcam + 26 * fi;
+  double* Hf = Hfeat + 12 * fi;
+  for (int k = 0; k < 26; ++k) Hc[k] = 0.0;
+  for (int k = 0; k < 12; ++k) Hf[k] = 0.0;
+  if (!has) return;  // calculate_derivatives.m:34
+  double hc[3];
+  mm_spec(Rrw, 3, 3, a, 1, hc);
+  const double f = cam.f;
+  const double dhu[6] = {f / hc[2], 0.0, -hc[0] * f / (hc[2] * hc[2]), 0.0, f / hc[2], -hc[1] * f / (hc[2] * hc[2])};
+  const double xd = uu - cam.Cx, yd = vv - cam.Cy;
+  const double r2 = (xd * xd + yd * yd) / (f * f), r4 = r2 * r2;
+  const double k1 = cam.k1, k2 = cam.k2;
+  double J[4], Ji[4], Jii[4];
+  J[0] = (1 + k1 * r2 + k2 * r4) + (uu - cam.Cx) * (k1 + 2 * k2 * r2) * (2 * (uu - cam.Cx) / (f * f));
+  J[3] = (1 + k1 * r2 + k2 * r4) + (vv - cam.Cy) * (k1 + 2 * k2 * r2) * (2 * (vv - cam.Cy) / (f * f));
+  J[1] = (uu - cam.Cx) * (k1 + 2 * k2 * r2) * (2 * (vv - cam.Cy) / (f * f));
+  J[2] = (vv - cam.Cy) * (k1 + 2 * k2 * r2) * (2 * (uu - cam.Cx) / (f * f));
+  inv_spec<2>(J, Ji);
+  inv_spec<2>(Ji, Jii);
+  double dh[6];
+  mm_spec(Jii, 2, 2, dhu, 3, dh);
+  double drw[9], Hrw[6];
+  for (int k = 0; k < 9; ++k) drw[k] = ty == 0 ? -Rrw[k] * rho : -Rrw[k];
+  mm_spec(dh, 2, 3, drw, 3, Hrw);
+  const double q0 = x[3], qx = -x[4], qy = -x[5], qz = -x[6];  // qconj (dRq_times_a_by_dq.m:26-103)
+  const double dR[4][9] = {{2 * q0, -2 * qz, 2 * qy, 2 * qz, 2 * q0, -2 * qx, -2 * qy, 2 * qx, 2 * q0},
+                           {2 * qx, 2 * qy, 2 * qz, 2 * qy, -2 * qx, -2 * q0, 2 * qz, 2 * q0, -2 * qx},
+                           {-2 * qy, 2 * qx, 2 * q0, 2 * qx, 2 * qy, 2 * qz, -2 * q0, 2 * qz, -2 * qy},
+                           {-2 * qz, -2 * q0, 2 * qx, 2 * q0, -2 * qz, 2 * qy, 2 * qx, 2 * qy, 2 * qz}};
+  double dq[12];
+  for (int c = 0; c < 4; ++c) {
+    double t[3];
+    mm_spec(dR[c], 3, 3, a, 1, t);
+    for (int r = 0; r < 3; ++r) dq[r * 4 + c] = c == 0 ? t[r] : t[r] * -1.0;  // * dqbar_by_dq = diag([1 -1 -1 -1])
+  }
+  double Hq[8];
+  mm_spec(dh, 2, 3, dq, 4, Hq);
+  for (int r = 0; r < 2; ++r) {
+    for (int c = 0; c < 3; ++c) Hc[2 * c + r] = Hrw[r * 3 + c];
+    for (int c = 0; c < 4; ++c) Hc[2 * (3 + c) + r] = Hq[r * 4 + c];
+  }
+  if (ty == 0) {
+    double dy[18];
+    const double dth[3] = {cp * ct, 0.0, -cp * st}, dph[3] = {-sp * st, -cp, -sp * ct};
+    const double yr[3] = {y[0] - x[0], y[1] - x[1], y[2] - x[2]};
+    double c4[3], c5[3], c6[3];
+    mm_spec(Rrw, 3, 3, dth, 1, c4);
+    mm_spec(Rrw, 3, 3, dph, 1, c5);
+    mm_spec(Rrw, 3, 3, yr, 1, c6);
+    for (int r = 0; r < 3; ++r) {
+      for (int c = 0; c < 3; ++c) dy[r * 6 + c] = rho * Rrw[r * 3 + c];
+      dy[r * 6 + 3] = c4[r], dy[r * 6 + 4] = c5[r], dy[r * 6 + 5] = c6[r];
+    }
+    double Hy[12];
+    mm_spec(dh, 2, 3, dy, 6, Hy);
+    for (int r = 0; r < 2; ++r)
+      for (int c = 0; c < 6; ++c) Hf[2 * c + r] = Hy[r * 6 + c];
+  } else {
+    double Hy[6];
+    mm_spec(dh, 2, 3, Rrw, 3, Hy);
+    for (int r = 0; r < 2; ++r)
+      for (int c = 0; c < 3; ++c) Hf[2 * c + r] = Hy[r * 3 + c];
+  }
+}
+
 static int wave_ends(const pre3_ekf_opts& o, int32_t* ends, int cap) {
   const int limit = std::min(o.H, o.n_hyp_init);
   if (limit <= 0) return 0;
@@ -1169,6 +1330,61 @@ int pre3_ekf_support(pre3_ctx* ctx, const double* xi, int n, int B, const pre3_c
   if (li_id && n_id) PRE3_CUDA(cudaMemcpyAsync(li_id, dli, (size_t)B * n_id, cudaMemcpyDeviceToHost, ctx->stream));
   if (li_euc && n_euc) PRE3_CUDA(cudaMemcpyAsync(li_euc, dle, (size_t)B * n_euc, cudaMemcpyDeviceToHost, ctx->stream));
   PRE3_CUDA(cudaStreamSynchronize(ctx->stream));  // the index vectors go out of scope
+  return PRE3_OK;
+}
+
+int pre3_ekf_predict_measurements_batch_dev(pre3_ctx* ctx, int Fr, int n, int F, const double* dx, const pre3_cam* cam,
+                                            int nRows, int nCols, const int32_t* dtype, const int32_t* dpos,
+                                            const uint8_t* dhas_h, const double* dh_in, double* dh_out,
+                                            uint8_t* dhas_h_out, uint8_t* dpredicted, double* dHcam, double* dHfeat) {
+  EKF_LIVE();
+  if (Fr < 0 || n < 13 || F < 0 || !cam) return fail(ctx, PRE3_ERR_ARG, "bad sizes");
+  if (Fr == 0 || F == 0) return PRE3_OK;
+  if (!dx || !dtype || !dpos || !dh_in || !dh_out || !dhas_h_out || !dpredicted || !dHcam || !dHfeat)
+    return fail(ctx, PRE3_ERR_ARG, "null pointer");
+  Span span__(ctx, T_EKF_UPDATE);
+  k_ekf_predict<<<dim3((F + 63) / 64, Fr), 64, 0, ctx->stream>>>(dx, n, *cam, nRows, nCols, F, dtype, dpos, dhas_h, dh_in,
+                                                                  dh_out, dhas_h_out, dpredicted, dHcam, dHfeat);
+  count_launch(ctx);
+  PRE3_CUDA(cudaGetLastError());
+  return PRE3_OK;
+}
+
+int pre3_ekf_predict_measurements_batch(pre3_ctx* ctx, int Fr, int n, int F, const double* x, const pre3_cam* cam,
+                                        int nRows, int nCols, const int32_t* type, const int32_t* pos,
+                                        const uint8_t* has_h, const double* h_in, double* h_out, uint8_t* has_h_out,
+                                        uint8_t* predicted, double* Hcam, double* Hfeat) {
+  EKF_LIVE();
+  if (Fr < 0 || n < 13 || F < 0 || !cam) return fail(ctx, PRE3_ERR_ARG, "bad sizes");
+  if (Fr == 0 || F == 0) return PRE3_OK;
+  if (!x || !type || !pos || !h_in || !h_out || !has_h_out || !predicted || !Hcam || !Hfeat)
+    return fail(ctx, PRE3_ERR_ARG, "null pointer");
+  const size_t ff = (size_t)Fr * F;
+  PRE3_TRY(ws_reserve(ctx, align_up(8 * (size_t)Fr * n) + 2 * align_up(4 * ff) + 3 * align_up(ff) + 2 * align_up(16 * ff) +
+                               align_up(208 * ff) + align_up(96 * ff) + 4096));
+  double* dx = ws_take<double>(ctx, (size_t)Fr * n);
+  int32_t* dty = ws_take<int32_t>(ctx, ff);
+  int32_t* dps = ws_take<int32_t>(ctx, ff);
+  uint8_t* dhh = has_h ? ws_take<uint8_t>(ctx, ff) : nullptr;
+  uint8_t* dho = ws_take<uint8_t>(ctx, ff);
+  uint8_t* dpr = ws_take<uint8_t>(ctx, ff);
+  double* dhi = ws_take<double>(ctx, 2 * ff);
+  double* dhO = ws_take<double>(ctx, 2 * ff);
+  double* dHc = ws_take<double>(ctx, 26 * ff);
+  double* dHf = ws_take<double>(ctx, 12 * ff);
+  PRE3_CUDA(cudaMemcpyAsync(dx, x, 8 * (size_t)Fr * n, cudaMemcpyHostToDevice, ctx->stream));
+  PRE3_CUDA(cudaMemcpyAsync(dty, type, 4 * ff, cudaMemcpyHostToDevice, ctx->stream));
+  PRE3_CUDA(cudaMemcpyAsync(dps, pos, 4 * ff, cudaMemcpyHostToDevice, ctx->stream));
+  if (dhh) PRE3_CUDA(cudaMemcpyAsync(dhh, has_h, ff, cudaMemcpyHostToDevice, ctx->stream));
+  PRE3_CUDA(cudaMemcpyAsync(dhi, h_in, 16 * ff, cudaMemcpyHostToDevice, ctx->stream));
+  PRE3_TRY(pre3_ekf_predict_measurements_batch_dev(ctx, Fr, n, F, dx, cam, nRows, nCols, dty, dps, dhh, dhi, dhO, dho, dpr,
+                                                   dHc, dHf));
+  PRE3_CUDA(cudaMemcpyAsync(h_out, dhO, 16 * ff, cudaMemcpyDeviceToHost, ctx->stream));
+  PRE3_CUDA(cudaMemcpyAsync(has_h_out, dho, ff, cudaMemcpyDeviceToHost, ctx->stream));
+  PRE3_CUDA(cudaMemcpyAsync(predicted, dpr, ff, cudaMemcpyDeviceToHost, ctx->stream));
+  PRE3_CUDA(cudaMemcpyAsync(Hcam, dHc, 208 * ff, cudaMemcpyDeviceToHost, ctx->stream));
+  PRE3_CUDA(cudaMemcpyAsync(Hfeat, dHf, 96 * ff, cudaMemcpyDeviceToHost, ctx->stream));
+  PRE3_CUDA(cudaStreamSynchronize(ctx->stream));
   return PRE3_OK;
 }
 

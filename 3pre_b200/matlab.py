@@ -500,6 +500,82 @@ def features_to_frame(filter, features_info, cam):
                 std_z=float(_field(filter, "std_z")), cam=cam, n=n, F=F)
 
 
+def predict_and_differentiate(x_k_k, cam, features_info):
+    """features_info = predict_camera_measurements(x_k_k, cam, features_info);
+    features_info = calculate_derivatives(x_k_k, cam, features_info)   (rescue_hi_inliers.m:32-33;
+    M/predict_camera_measurements.m:27-68, M/calculate_derivatives.m:27-59).  cam needs f, Cx, Cy, k1, k2, nRows,
+    nCols.  Updates h (1 x 2) and H (2 x n, dense) of every feature in place and returns the list."""
+    x = np.asarray(x_k_k, np.float64).reshape(-1)
+    F, n = len(features_info), len(x)
+    ty, ps = np.zeros(F, np.int32), np.zeros(F, np.int32)
+    p = 13
+    for i, fi in enumerate(features_info):
+        t = str(_field(fi, "type"))
+        if t not in ("inversedepth", "cartesian"):
+            raise MexError("feature type must be 'inversedepth' or 'cartesian'")
+        ty[i], ps[i] = (0, p) if t == "inversedepth" else (1, p)
+        p += 6 if ty[i] == 0 else 3
+    if p != n:
+        raise MexError("state size does not match the features (13 + 6 n_id + 3 n_euc)")
+    has = np.array([np.size(fi.get("h", ())) > 0 for fi in features_info])
+    h_in = np.zeros((F, 2))
+    for i in np.flatnonzero(has):
+        h_in[i] = np.asarray(features_info[i]["h"], np.float64).reshape(-1)[:2]
+    h, has_o, _, Hc, Hf = context().ekf_predict_measurements_batch(x[None], cam, int(_field(cam, "nRows")),
+                                                                   int(_field(cam, "nCols")), ty[None], ps[None],
+                                                                   has[None], h_in[None])
+    for i, fi in enumerate(features_info):
+        if not has_o[0, i]:
+            continue
+        fi["h"] = h[0, i].reshape(1, 2).copy()
+        Hi = np.zeros((2, n))
+        Hi[:, :13] = Hc[0, i].T
+        nf = 6 if ty[i] == 0 else 3
+        Hi[:, ps[i]:ps[i] + nf] = Hf[0, i, :nf].T
+        fi["H"] = Hi
+    return features_info
+
+
+def rescue_hi_inliers(filter, features_info, cam):
+    """features_info = rescue_hi_inliers(filter, features_info, cam)   (M/@ekf_filter/rescue_hi_inliers.m:27-47).
+    filter: dict / object with x_k_k, p_k_k.  Re-predicts h and H at x_k_k, then sets high_innovation_inlier for the
+    features that are individually compatible but not low-innovation inliers (chi2inv(0.95, 2) = 5.9915)."""
+    import torch
+    x = np.asarray(_field(filter, "x_k_k"), np.float64).reshape(-1)
+    P = np.asarray(_field(filter, "p_k_k"), np.float64)
+    features_info = predict_and_differentiate(x, cam, features_info)
+    F, n = len(features_info), len(x)
+    ty, ps = np.zeros(F, np.int32), np.zeros(F, np.int32)
+    ic, li = np.zeros(F, np.uint8), np.zeros(F, np.uint8)
+    z, h, Hc, Hf = np.zeros((F, 2)), np.zeros((F, 2)), np.zeros((F, 13, 2)), np.zeros((F, 6, 2))
+    p = 13
+    for i, fi in enumerate(features_info):
+        ty[i] = 0 if str(_field(fi, "type")) == "inversedepth" else 1
+        ps[i] = p
+        nf = 6 if ty[i] == 0 else 3
+        p += nf
+        ic[i] = bool(fi.get("individually_compatible", 0))
+        li[i] = bool(fi.get("low_innovation_inlier", 0))
+        if ic[i] and not li[i]:
+            z[i] = np.asarray(fi["z"], np.float64).reshape(-1)[:2]
+            h[i] = np.asarray(fi["h"], np.float64).reshape(-1)[:2]
+            Hi = np.asarray(fi["H"], np.float64)
+            Hc[i], Hf[i, :nf] = Hi[:, :13].T, Hi[:, ps[i]:ps[i] + nf].T
+    ctx = context()
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)[None]).cuda()
+    frames = {"type": dev(ty), "pos": dev(ps), "ic": dev(ic), "z": dev(z), "h": dev(h), "Hcam": dev(Hc), "Hfeat": dev(Hf),
+              "x": dev(x)}
+    hi = torch.full((1, F), 7, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    ctx.ekf_rescue_hi_inliers_batch_dev(frames, dev(np.ascontiguousarray(P.T)), dev(li), hi)
+    ctx.sync()
+    out = hi[0].cpu().numpy()
+    for i, fi in enumerate(features_info):
+        if out[i] != 7:
+            fi["high_innovation_inlier"] = int(out[i])
+    return features_info
+
+
 def ransac_hypotheses(filter, features_info, cam, *, selections=None, seed=0, n_hyp=1000, adaptive=True):
     """features_info = ransac_hypotheses(filter, features_info, cam)  (M/ransac_hypotheses.m:27-85).
     filter: dict / object with x_k_km1, p_k_km1, std_z (what get_x_k_km1 / get_p_k_km1 / get_std_z

@@ -513,6 +513,25 @@ PRE3_API int pre3_measure_fp64_peak(pre3_ctx *ctx, double *tflops);
  * helper used by the Calculate_V_Omega_RANSAC* shims: q = [a -b -c -d]'. */
 PRE3_API void pre3_R2q(const double *R_colmajor, double *q);
 
+/* Re-prediction at x_k_k, the first two lines of rescue_hi_inliers.m (:32-33): predict_camera_measurements.m:27-68
+ * (hi_inverse_depth.m / hi_cartesian.m: +-60 degree field of view, pinhole, radial distortion, image bounds 0 < u < nCols,
+ * 0 < v < nRows) and calculate_derivatives.m:27-59 (calculate_Hi_inverse_depth_my_version.m / calculate_Hi_cartesian_
+ * my_version.m) for Fr frames of F features.  x: Fr x n; type / pos as above; has_h (Fr x F, NULL = all 1): the feature
+ * carries a previous prediction h_in (Fr x F x 2).  Outputs: h_out (a feature that fails a visibility test keeps h_in,
+ * predict_camera_measurements.m:37-39), has_h_out, predicted (passed the tests at x), Hcam (2 x 13 per feature; columns
+ * 8..13 are zero) and Hfeat (2 x 6) for every feature with has_h_out, zeros otherwise -- the inputs
+ * pre3_ekf_rescue_hi_inliers_batch_dev and the hi-inlier update take. */
+PRE3_API int pre3_ekf_predict_measurements_batch(pre3_ctx *ctx, int Fr, int n, int F, const double *x,
+                                                 const pre3_cam *cam, int nRows, int nCols, const int32_t *type,
+                                                 const int32_t *pos, const uint8_t *has_h, const double *h_in,
+                                                 double *h_out, uint8_t *has_h_out, uint8_t *predicted, double *Hcam,
+                                                 double *Hfeat);
+PRE3_API int pre3_ekf_predict_measurements_batch_dev(pre3_ctx *ctx, int Fr, int n, int F, const double *dx,
+                                                     const pre3_cam *cam, int nRows, int nCols, const int32_t *dtype,
+                                                     const int32_t *dpos, const uint8_t *dhas_h, const double *dh_in,
+                                                     double *dh_out, uint8_t *dhas_h_out, uint8_t *dpredicted,
+                                                     double *dHcam, double *dHfeat);
+
 #ifdef __cplusplus
 }
 #endif

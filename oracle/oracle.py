@@ -488,6 +488,22 @@ def ekf_support(xi, cam, pattern, z_id, z_euc, threshold):
     return sup, li_id[:n_id].astype(bool), li_euc[:n_euc].astype(bool), res[:n_id + n_euc].copy()
 
 
+def ekf_predict(x, cam, n_rows, n_cols, types, pos, has_h, h_in):
+    """predict_camera_measurements + calculate_derivatives at x (rescue_hi_inliers.m:32-33; pre3_oracle_ekf.c:
+    orc_ekf_predict).  Returns h (F,2), has_h (F,) bool, predicted (F,) bool, Hcam (F,13,2), Hfeat (F,6,2)."""
+    x = _f64(x)
+    ty, ps = _i32(types), _i32(pos)
+    F = len(ty)
+    hh, hi = np.ascontiguousarray(np.asarray(has_h).astype(np.uint8)), _f64(h_in).reshape(F, 2)
+    h, has, pred = np.zeros((F, 2)), np.zeros(F, np.uint8), np.zeros(F, np.uint8)
+    Hc, Hf = np.zeros((F, 13, 2)), np.zeros((F, 6, 2))
+    c = _cam(cam)
+    lib().orc_ekf_predict(_p(x, C.c_double), len(x), C.byref(c), int(n_rows), int(n_cols), F, _p(ty, C.c_int32),
+                          _p(ps, C.c_int32), _p(hh, C.c_uint8), _p(hi, C.c_double), _p(h, C.c_double),
+                          _p(has, C.c_uint8), _p(pred, C.c_uint8), _p(Hc, C.c_double), _p(Hf, C.c_double))
+    return h, has.astype(bool), pred.astype(bool), Hc, Hf
+
+
 def ransac_hypotheses(fr, sel=None, H=1000, n_hyp_init=1000, seed=0, frame_id=0, adaptive=True):
     """ransac_hypotheses.m:27-85 on one synth_ekf.EkfFrame.  sel: (H,3) 0-based feature indices or None
     (seeded).  Returns dict(li, n_hyp, max_support, best_hyp, n_evaluated, supports, status, m, num_ic)."""

@@ -485,3 +485,144 @@ ORC_API int orc_ransac_hypotheses(const double *x, const double *P, int n, doubl
   free(z_euc);
   return rc;
 }
+
+/* ------------------------------------------------------------------------- */
+/* Re-prediction at x_k_k: M/@ekf_filter/rescue_hi_inliers.m:32-33
+ *   features_info = predict_camera_measurements(filter.x_k_k, cam, features_info)   (M/predict_camera_measurements.m:27-68)
+ *   features_info = calculate_derivatives(filter.x_k_k, cam, features_info)         (M/calculate_derivatives.m:27-59)
+ * predict: hi_inverse_depth.m:27-86 / hi_cartesian.m:27-80 -- hrl = rotcw * v, the +-60 degree field-of-view test on
+ *   atan2(hrl(1), hrl(3)) and atan2(hrl(2), hrl(3)) (:60-66), hu_my_version.m:32-41, distort_fm_my_version.m:52-61, the
+ *   image-bounds test (:79); a feature that fails a test KEEPS its previous h (predict_camera_measurements.m:37-39,:62-64).
+ * derivatives, for every feature whose h is not empty (calculate_derivatives.m:34), zi = that h:
+ *   calculate_Hi_inverse_depth_my_version.m:27-190 / calculate_Hi_cartesian_my_version.m:27-168
+ *     Rrw = inv(q2r(q))                          dhu_dhrl = [f/hz 0 -hx f/hz^2; 0 f/hz -hy f/hz^2]
+ *     dhd_dhu = inv(inv(jacob_distor(cam, zi)))   (jacob_undistor_fm_my_version.m:38 inverts once, dhd_dhu again)
+ *     jacob_distor_fm_my_version.m:38-60          dh_dhrl = dhd_dhu * dhu_dhrl
+ *     H(:,1:3) = dh_dhrl * (-Rrw * rho)  [cartesian: -Rrw]
+ *     H(:,4:7) = dh_dhrl * dRq_times_a_by_dq(qconj(q), a) * diag([1 -1 -1 -1])   (dRq_times_a_by_dq.m:26-103)
+ *     H(:,8:13) = 0
+ *     feature block = dh_dhrl * [rho*Rrw, Rrw*dm/dtheta, Rrw*dm/dphi, Rrw*(y - rw)]   [cartesian: dh_dhrl * Rrw]
+ * Specification shared with 3pre_b200/csrc/ekf.cu (k_ekf_predict): inv() = orc_inv (Gauss-Jordan above), sin / cos =
+ * orc_sincos, every product  C(i,j) = sum_k A(i,k) B(k,j)  accumulated left to right in k starting from the k = 0
+ * term.  MATLAB's inv / mtimes (LAPACK / BLAS, possibly FMA) differ from this by rounding: checked against an
+ * independent numpy restatement at 1e-9 (tests/test_oracle_ekf_update_cpu.py). */
+static void mm(const double *A, int ra, int ca, const double *B, int cb, double *C) { /* row-major */
+  for (int i = 0; i < ra; ++i)
+    for (int j = 0; j < cb; ++j) {
+      double s = A[i * ca] * B[j];
+      for (int k = 1; k < ca; ++k) s = s + A[i * ca + k] * B[k * cb + j];
+      C[i * cb + j] = s;
+    }
+}
+
+ORC_API void orc_ekf_predict(const double *x, int n, const orc_cam *cam, int nRows, int nCols, int F,
+                             const int32_t *type, const int32_t *pos, const uint8_t *has_h_in, const double *h_in,
+                             double *h_out, uint8_t *has_h_out, uint8_t *predicted, double *Hcam, double *Hfeat) {
+  (void)n;
+  double Rwc[3][3], Rf[9], Rrw[9];
+  orc_q2r(x + 3, Rwc);
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) Rf[i * 3 + j] = Rwc[i][j];
+  orc_inv(Rf, 3, Rrw); /* inv(q2r(q)) of the Jacobians */
+  const double PI = 3.14159265358979323846;
+  for (int i = 0; i < F; ++i) {
+    const double *y = x + pos[i];
+    double a[3], mi[3] = {0, 0, 0}, st = 0, ct = 0, sp = 0, cp = 0, rho = 1.0;
+    if (type[i] == 0) {
+      orc_sincos(y[3], &st, &ct);
+      orc_sincos(y[4], &sp, &cp);
+      mi[0] = cp * st, mi[1] = -sp, mi[2] = cp * ct; /* m.m:32-34 */
+      rho = y[5];
+      for (int k = 0; k < 3; ++k) a[k] = (y[k] - x[k]) * rho + mi[k];
+    } else {
+      for (int k = 0; k < 3; ++k) a[k] = y[k] - x[k];
+    }
+    /* ---- predict_camera_measurements: r_cw = r_wc' (hi_inverse_depth.m:33) / inv(r_wc) (hi_cartesian.m:33) ---- */
+    double hrl[3];
+    if (type[i] == 0) {
+      for (int k = 0; k < 3; ++k) hrl[k] = (Rwc[0][k] * a[0] + Rwc[1][k] * a[1]) + Rwc[2][k] * a[2];
+    } else {
+      mm(Rrw, 3, 3, a, 1, hrl);
+    }
+    int ok = 1;
+    const double ax = atan2(hrl[0], hrl[2]) * 180 / PI, ay = atan2(hrl[1], hrl[2]) * 180 / PI;
+    if (ax < -60 || ax > 60 || ay < -60 || ay > 60) ok = 0;
+    double ud = 0, vd = 0;
+    if (ok) {
+      const double u = cam->Cx + (hrl[0] / hrl[2]) * cam->f, v = cam->Cy + (hrl[1] / hrl[2]) * cam->f;
+      const double xu = (u - cam->Cx) / cam->f, yu = (v - cam->Cy) / cam->f;
+      const double ru = sqrt(xu * xu + yu * yu);
+      const double ru2 = ru * ru;
+      const double D = (1.0 + cam->k1 * ru2) + cam->k2 * (ru2 * ru2);
+      ud = (xu * D) * cam->f + cam->Cx, vd = (yu * D) * cam->f + cam->Cy;
+      if (!(ud > 0 && ud < nCols && vd > 0 && vd < nRows)) ok = 0;
+    }
+    predicted[i] = (uint8_t)ok;
+    has_h_out[i] = (uint8_t)(ok || has_h_in[i]);
+    h_out[2 * i] = ok ? ud : h_in[2 * i];
+    h_out[2 * i + 1] = ok ? vd : h_in[2 * i + 1];
+    for (int k = 0; k < 26; ++k) Hcam[26 * (size_t)i + k] = 0.0;
+    for (int k = 0; k < 12; ++k) Hfeat[12 * (size_t)i + k] = 0.0;
+    if (!has_h_out[i]) continue; /* calculate_derivatives.m:34 */
+    /* ---- calculate_derivatives ---- */
+    double hc[3];
+    mm(Rrw, 3, 3, a, 1, hc);
+    const double f = cam->f;
+    const double dhu[6] = {f / hc[2], 0.0, -hc[0] * f / (hc[2] * hc[2]), 0.0, f / hc[2], -hc[1] * f / (hc[2] * hc[2])};
+    const double uu = h_out[2 * i], vv = h_out[2 * i + 1];
+    const double xd = uu - cam->Cx, yd = vv - cam->Cy;
+    const double r2 = (xd * xd + yd * yd) / (f * f), r4 = r2 * r2;
+    const double k1 = cam->k1, k2 = cam->k2;
+    double J[4], Ji[4], Jii[4];
+    J[0] = (1 + k1 * r2 + k2 * r4) + (uu - cam->Cx) * (k1 + 2 * k2 * r2) * (2 * (uu - cam->Cx) / (f * f));
+    J[3] = (1 + k1 * r2 + k2 * r4) + (vv - cam->Cy) * (k1 + 2 * k2 * r2) * (2 * (vv - cam->Cy) / (f * f));
+    J[1] = (uu - cam->Cx) * (k1 + 2 * k2 * r2) * (2 * (vv - cam->Cy) / (f * f));
+    J[2] = (vv - cam->Cy) * (k1 + 2 * k2 * r2) * (2 * (uu - cam->Cx) / (f * f));
+    orc_inv(J, 2, Ji);
+    orc_inv(Ji, 2, Jii);
+    double dh[6];
+    mm(Jii, 2, 2, dhu, 3, dh); /* dh_dhrl, 2 x 3 */
+    double drw[9], Hrw[6];
+    for (int k = 0; k < 9; ++k) drw[k] = type[i] == 0 ? -Rrw[k] * rho : -Rrw[k];
+    mm(dh, 2, 3, drw, 3, Hrw);
+    /* dRq_times_a_by_dq(qconj(q), a) * diag([1 -1 -1 -1]) */
+    const double q0 = x[3], qx = -x[4], qy = -x[5], qz = -x[6];
+    const double dR[4][9] = {{2 * q0, -2 * qz, 2 * qy, 2 * qz, 2 * q0, -2 * qx, -2 * qy, 2 * qx, 2 * q0},
+                             {2 * qx, 2 * qy, 2 * qz, 2 * qy, -2 * qx, -2 * q0, 2 * qz, 2 * q0, -2 * qx},
+                             {-2 * qy, 2 * qx, 2 * q0, 2 * qx, 2 * qy, 2 * qz, -2 * q0, 2 * qz, -2 * qy},
+                             {-2 * qz, -2 * q0, 2 * qx, 2 * q0, -2 * qz, 2 * qy, 2 * qx, 2 * qy, 2 * qz}};
+    double dq[12]; /* 3 x 4 row-major */
+    for (int c = 0; c < 4; ++c) {
+      double t[3];
+      mm(dR[c], 3, 3, a, 1, t);
+      for (int r = 0; r < 3; ++r) dq[r * 4 + c] = c == 0 ? t[r] : t[r] * -1.0;
+    }
+    double Hq[8];
+    mm(dh, 2, 3, dq, 4, Hq);
+    for (int r = 0; r < 2; ++r) {
+      for (int c = 0; c < 3; ++c) Hcam[26 * (size_t)i + 2 * c + r] = Hrw[r * 3 + c];
+      for (int c = 0; c < 4; ++c) Hcam[26 * (size_t)i + 2 * (3 + c) + r] = Hq[r * 4 + c];
+    }
+    if (type[i] == 0) {
+      double dy[18]; /* 3 x 6 row-major */
+      const double dth[3] = {cp * ct, 0.0, -cp * st}, dph[3] = {-sp * st, -cp, -sp * ct};
+      double yr[3] = {y[0] - x[0], y[1] - x[1], y[2] - x[2]}, c4[3], c5[3], c6[3];
+      mm(Rrw, 3, 3, dth, 1, c4);
+      mm(Rrw, 3, 3, dph, 1, c5);
+      mm(Rrw, 3, 3, yr, 1, c6);
+      for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) dy[r * 6 + c] = rho * Rrw[r * 3 + c];
+        dy[r * 6 + 3] = c4[r], dy[r * 6 + 4] = c5[r], dy[r * 6 + 5] = c6[r];
+      }
+      double Hy[12];
+      mm(dh, 2, 3, dy, 6, Hy);
+      for (int r = 0; r < 2; ++r)
+        for (int c = 0; c < 6; ++c) Hfeat[12 * (size_t)i + 2 * c + r] = Hy[r * 6 + c];
+    } else {
+      double Hy[6];
+      mm(dh, 2, 3, Rrw, 3, Hy);
+      for (int r = 0; r < 2; ++r)
+        for (int c = 0; c < 3; ++c) Hfeat[12 * (size_t)i + 2 * c + r] = Hy[r * 3 + c];
+    }
+  }
+}

@@ -222,3 +222,82 @@ def rescue_hi_inliers(fr, p_k_k, li, h=None):
             nu = fr.z[i] - h[i]
             out[i] = 1 if nu @ np.linalg.inv(Si) @ nu < 5.9915 else 0
     return out
+
+
+# ------------------------------------------------------------------------------------------
+# re-prediction at x_k_k (rescue_hi_inliers.m:32-33): independent restatement with numpy / LAPACK
+# ------------------------------------------------------------------------------------------
+def _h_of(x, cam, ty, ps):
+    """hi_inverse_depth.m:27-86 / hi_cartesian.m:27-80 without the visibility tests: the distorted pixel."""
+    Rcw = q2r(x[3:7]).T
+    y = x[ps:ps + (6 if ty == 0 else 3)]
+    if ty == 0:
+        v = (y[:3] - x[:3]) * y[5] + m(y[3:5])[:, 0]
+    else:
+        v = y - x[:3]
+    hrl = Rcw @ v
+    uv = np.array([cam["Cx"] + hrl[0] / hrl[2] * cam["f"], cam["Cy"] + hrl[1] / hrl[2] * cam["f"]])
+    return distort_fm(uv, cam)[:, 0], hrl
+
+
+def predict_and_derivatives(x, cam, n_rows, n_cols, types, pos, has_h, h_in):
+    """predict_camera_measurements.m:27-68 + calculate_derivatives.m:27-59.  Returns h (F,2), has_h (F,), predicted (F,),
+    H (F,2,n) dense (zero rows where h is empty)."""
+    x = np.asarray(x, np.float64)
+    F, n = len(types), len(x)
+    h = np.array(h_in, np.float64).copy()
+    has = np.array(has_h, bool).copy()
+    pred = np.zeros(F, bool)
+    H = np.zeros((F, 2, n))
+    Rrw = np.linalg.inv(q2r(x[3:7]))
+    f, Cx, Cy, k1, k2 = cam["f"], cam["Cx"], cam["Cy"], cam["k1"], cam["k2"]
+    for i in range(F):
+        ty, ps = int(types[i]), int(pos[i])
+        hd, hrl = _h_of(x, cam, ty, ps)
+        ax, ay = np.degrees(np.arctan2(hrl[0], hrl[2])), np.degrees(np.arctan2(hrl[1], hrl[2]))
+        ok = (-60 <= ax <= 60) and (-60 <= ay <= 60) and (0 < hd[0] < n_cols) and (0 < hd[1] < n_rows)
+        if ok:
+            h[i], has[i], pred[i] = hd, True, True
+        if not has[i]:
+            continue
+        y = x[ps:ps + (6 if ty == 0 else 3)]
+        rho = y[5] if ty == 0 else 1.0
+        a = ((y[:3] - x[:3]) * y[5] + m(y[3:5])[:, 0]) if ty == 0 else (y - x[:3])
+        hc = Rrw @ a
+        dhu = np.array([[f / hc[2], 0, -hc[0] * f / hc[2] ** 2], [0, f / hc[2], -hc[1] * f / hc[2] ** 2]])
+        u, v = h[i]
+        r2 = ((u - Cx) ** 2 + (v - Cy) ** 2) / f ** 2
+        g = k1 + 2 * k2 * r2
+        D = 1 + k1 * r2 + k2 * r2 * r2
+        J = np.array([[D + (u - Cx) * g * 2 * (u - Cx) / f ** 2, (u - Cx) * g * 2 * (v - Cy) / f ** 2],
+                      [(v - Cy) * g * 2 * (u - Cx) / f ** 2, D + (v - Cy) * g * 2 * (v - Cy) / f ** 2]])
+        dh = np.linalg.inv(np.linalg.inv(J)) @ dhu
+        q0, qx, qy, qz = x[3], -x[4], -x[5], -x[6]
+        dR = [np.array([[2 * q0, -2 * qz, 2 * qy], [2 * qz, 2 * q0, -2 * qx], [-2 * qy, 2 * qx, 2 * q0]]),
+              np.array([[2 * qx, 2 * qy, 2 * qz], [2 * qy, -2 * qx, -2 * q0], [2 * qz, 2 * q0, -2 * qx]]),
+              np.array([[-2 * qy, 2 * qx, 2 * q0], [2 * qx, 2 * qy, 2 * qz], [-2 * q0, 2 * qz, -2 * qy]]),
+              np.array([[-2 * qz, -2 * q0, 2 * qx], [2 * q0, -2 * qz, 2 * qy], [2 * qx, 2 * qy, 2 * qz]])]
+        dq = np.stack([d @ a for d in dR], 1) @ np.diag([1.0, -1, -1, -1])
+        H[i, :, 0:3] = dh @ (-Rrw * rho)
+        H[i, :, 3:7] = dh @ dq
+        if ty == 0:
+            th, ph = y[3], y[4]
+            dy = np.column_stack([rho * Rrw, Rrw @ np.array([np.cos(ph) * np.cos(th), 0, -np.cos(ph) * np.sin(th)]),
+                                  Rrw @ np.array([-np.sin(ph) * np.sin(th), -np.cos(ph), -np.sin(ph) * np.cos(th)]),
+                                  Rrw @ (y[:3] - x[:3])])
+            H[i, :, ps:ps + 6] = dh @ dy
+        else:
+            H[i, :, ps:ps + 3] = dh @ Rrw
+    return h, has, pred, H
+
+
+def numeric_H(x, cam, ty, ps, eps=1e-6):
+    """Central-difference Jacobian of the predicted (distorted) pixel with respect to the state."""
+    x = np.asarray(x, np.float64)
+    H = np.zeros((2, len(x)))
+    for k in list(range(7)) + list(range(ps, ps + (6 if ty == 0 else 3))):
+        hi, lo = x.copy(), x.copy()
+        hi[k] += eps
+        lo[k] -= eps
+        H[:, k] = (_h_of(hi, cam, ty, ps)[0] - _h_of(lo, cam, ty, ps)[0]) / (2 * eps)
+    return H

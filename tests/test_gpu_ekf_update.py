@@ -190,3 +190,108 @@ def test_mex_gateway_update_shadows_update_m():
         call([fr.x.reshape(-1, 1), fr.P], 1)
     with pytest.raises(refmex.MexError, match="H must be"):
         call([fr.x.reshape(-1, 1), fr.P, H[:, :5], np.eye(len(z)), z.reshape(-1, 1), h.reshape(-1, 1)], 1)
+
+
+def test_reprediction_at_x_k_k_vs_oracle(ctx, orc):
+    """rescue_hi_inliers.m:32-33 on the GPU (k_ekf_predict) against the C oracle sharing its specification: flags and
+    h bit for bit (same sincos / operation order), H to 1e-12 of its largest entry (CUDA's atan2 only feeds the
+    comparisons; -fmad=false keeps the products unfused), and against the independent numpy restatement at 1e-9."""
+    Fr = 3
+    b = se.make_ekf_frames(Fr, 91, n_id=60, n_euc=20, interleave=True)
+    fb = se.batch_to_numpy(b)
+    x = fb["x"].copy()
+    x[:, 3:7] /= np.linalg.norm(x[:, 3:7], axis=1, keepdims=True)
+    rng = np.random.default_rng(8)
+    has = rng.uniform(size=fb["type"].shape) < 0.9
+    h_prev = fb["h"] + rng.normal(size=fb["h"].shape)
+    for f in range(Fr):                                   # push some features out of view
+        for i in rng.choice(fb["type"].shape[1], 6, replace=False):
+            if fb["type"][f, i] == 0:
+                x[f, fb["pos"][f, i] + 3] += 1.4
+            else:
+                x[f, fb["pos"][f, i]] += 50.0
+    h, has_o, pred, Hc, Hf = ctx.ekf_predict_measurements_batch(x, se.CAM, 144, 176, fb["type"], fb["pos"], has, h_prev)
+    n_unpred = 0
+    for f in range(Fr):
+        oh, ohas, opred, oHc, oHf = orc.ekf_predict(x[f], se.CAM, 144, 176, fb["type"][f], fb["pos"][f], has[f], h_prev[f])
+        np.testing.assert_array_equal(pred[f], opred)
+        np.testing.assert_array_equal(has_o[f], ohas)
+        np.testing.assert_array_equal(h[f][ohas], oh[ohas])
+        sc = max(np.abs(oHc).max(), np.abs(oHf).max())
+        np.testing.assert_allclose(Hc[f], oHc, rtol=0, atol=1e-12 * sc)
+        np.testing.assert_allclose(Hf[f], oHf, rtol=0, atol=1e-12 * sc)
+        n_unpred += int((~opred).sum())
+        h2, has2, pred2, H2 = rne.predict_and_derivatives(x[f], se.CAM, 144, 176, fb["type"][f], fb["pos"][f], has[f], h_prev[f])
+        for i in np.flatnonzero(has2):
+            Hd = np.zeros((2, x.shape[1]))
+            Hd[:, :13] = Hc[f, i].T
+            nf = 6 if fb["type"][f, i] == 0 else 3
+            Hd[:, fb["pos"][f, i]: fb["pos"][f, i] + nf] = Hf[f, i, :nf].T
+            assert np.abs(Hd - H2[i]).max() <= 1e-9 * max(1.0, np.abs(H2[i]).max())
+    assert n_unpred >= 10
+
+
+def test_rescue_with_reprediction_device_sequence(ctx):
+    """li update -> re-prediction at x_k_k -> chi2 test -> hi update, all on device buffers: the whole of
+    rescue_hi_inliers.m, compared with the numpy restatements chained the same way."""
+    torch = pytest.importorskip("torch")
+    Fr = 2
+    b = se.make_ekf_frames(Fr, 778, device="cuda", n_id=40, n_euc=8, interleave=True, outlier_ratio=0.3)
+    b["cam"] = dict(se.CAM)
+    F, n = b["F"], b["n"]
+    li = (~b["outlier"]).to(torch.uint8)
+    li[:, ::4] = 0
+    x1 = torch.zeros_like(b["x"]); P1 = torch.zeros_like(b["P"])
+    ctx.ekf_update_batch_dev(b, li, x1, P1)
+    h1 = torch.zeros_like(b["h"]); Hc1 = torch.zeros_like(b["Hcam"]); Hf1 = torch.zeros_like(b["Hfeat"])
+    has1 = torch.zeros(Fr, F, dtype=torch.uint8, device="cuda"); pr1 = torch.zeros_like(has1)
+    ctx.ekf_predict_measurements_batch_dev(x1, se.CAM, 144, 176, b["type"], b["pos"], None, b["h"], h1, has1, pr1, Hc1, Hf1)
+    hi = torch.full((Fr, F), 7, dtype=torch.uint8, device="cuda")
+    ctx.ekf_rescue_hi_inliers_batch_dev(b, P1, li, hi, h=h1, Hcam=Hc1, Hfeat=Hf1)
+    ctx.sync()
+    for f in range(Fr):
+        fr = se.frame(b, f)
+        lf = li[f].cpu().numpy()
+        gx, gP = rne.ekf_update_inliers(fr, lf)
+        h2, has2, pred2, H2 = rne.predict_and_derivatives(gx, se.CAM, 144, 176, fr.type, fr.pos, np.ones(F, bool), fr.h)
+        assert pred2.sum() >= F - 4
+        np.testing.assert_allclose(h1[f].cpu().numpy(), h2, rtol=0, atol=1e-7)   # x1 vs gx differ by rounding of the update
+        got = hi[f].cpu().numpy().astype(np.int32)
+        for i in range(F):
+            tested = fr.ic[i] == 1 and lf[i] == 0
+            assert (got[i] != 7) == tested
+            if tested:
+                nu = fr.z[i] - h2[i]
+                q = nu @ np.linalg.inv(H2[i] @ gP @ H2[i].T) @ nu
+                if abs(q - 5.9915) > 1e-4:
+                    assert got[i] == (1 if q < 5.9915 else 0)
+
+
+def test_matlab_rescue_hi_inliers_mirror(ctx):
+    """The MATLAB-shaped mirror of rescue_hi_inliers(filter, features_info, cam) on a features_info list."""
+    M = importlib.import_module("3pre_b200.matlab")
+    b = se.make_ekf_frames(1, 779, n_id=20, n_euc=6, interleave=True, outlier_ratio=0.3)
+    fr = se.frame(b, 0)
+    li = (~fr.outlier).astype(np.uint8); li[::3] = 0
+    x1, P1 = rne.ekf_update_inliers(fr, li)
+    cam = dict(se.CAM, nRows=144, nCols=176)
+    feats = []
+    for i in range(fr.F):
+        feats.append({"type": "inversedepth" if fr.type[i] == 0 else "cartesian", "h": fr.h[i].reshape(1, 2),
+                      "z": fr.z[i].copy(), "individually_compatible": int(fr.ic[i]), "low_innovation_inlier": int(li[i]),
+                      "H": rne.dense_H(fr, i)})
+    out = M.rescue_hi_inliers({"x_k_k": x1, "p_k_k": P1}, feats, cam)
+    h2, has2, pred2, H2 = rne.predict_and_derivatives(x1, se.CAM, 144, 176, fr.type, fr.pos, np.ones(fr.F, bool), fr.h)
+    n_tested = 0
+    for i in range(fr.F):
+        np.testing.assert_allclose(out[i]["h"].reshape(-1), h2[i], rtol=0, atol=1e-10)
+        assert np.abs(out[i]["H"] - H2[i]).max() <= 1e-9 * max(1.0, np.abs(H2[i]).max())
+        tested = fr.ic[i] == 1 and li[i] == 0
+        assert ("high_innovation_inlier" in out[i]) == tested
+        if tested:
+            n_tested += 1
+            nu = fr.z[i] - h2[i]
+            q = nu @ np.linalg.inv(H2[i] @ P1 @ H2[i].T) @ nu
+            if abs(q - 5.9915) > 1e-4:
+                assert out[i]["high_innovation_inlier"] == (1 if q < 5.9915 else 0)
+    assert n_tested >= 5
