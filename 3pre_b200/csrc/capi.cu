@@ -66,12 +66,13 @@ int match_impl(pre3_ctx* ctx, const void* dL1, const void* dL2, int cls, int P, 
   const float th = (float)thresh;  // narrowed like the reference (siftmatch.c:87,:205)
   bool tc = false, ti = false;
   if (ctx->match_engine != PRE3_MATCH_EXACT) {
-    tc = match_tc_supported(cls, K1, K2, ND);
-    // integer classes: exact kind::i8 GEMM (the 16-byte vector loads of its converter need aligned descriptor sets)
-    ti = match_i8_supported(cls, K1, K2, ND) && (((uintptr_t)dL1 | (uintptr_t)dL2) & 15u) == 0;
+    // the converters of both tensor-core engines (and the row recheck) read descriptors with 16-byte vector loads
+    const bool aligned = (((uintptr_t)dL1 | (uintptr_t)dL2) & 15u) == 0;
+    tc = aligned && match_tc_supported(cls, K1, K2, ND);
+    ti = aligned && match_i8_supported(cls, K1, K2, ND);  // integer classes: exact kind::i8 GEMM
   }
   if (ctx->match_engine == PRE3_MATCH_TC && !tc && !ti)
-    return fail(ctx, PRE3_ERR_ARG, "tensor-core matcher needs ND == 128 (and 16-byte aligned int8 / uint8 descriptors)");
+    return fail(ctx, PRE3_ERR_ARG, "tensor-core matcher needs ND == 128 and 16-byte aligned descriptor sets");
   if (tc) {
     PRE3_TRY(launch_match_tc(ctx, dL1, dL2, cls, P, K1, K2, ND, dk1, dk2, th, need_score, rows));
   } else if (ti) {
@@ -550,6 +551,23 @@ int pre3_horn(pre3_ctx* ctx, const double* A, const double* B, int n, int do_sca
   return PRE3_OK;
 }
 
+// Explicit sample sets index the correspondences: an index outside 0..N-1 is MATLAB's "Index exceeds matrix dimensions"
+// (Ya(:, idx)), reported here instead of being clamped.  Pairs with fewer than k correspondences never sample.
+static int check_samples(pre3_ctx* ctx, const int32_t* samples, int P, int H, int k, const int32_t* n_corr, int Nmax) {
+  if (!samples) return PRE3_OK;
+  for (int p = 0; p < P; ++p) {
+    const int N = n_corr ? std::min(n_corr[p], Nmax) : Nmax;
+    if (N < k) continue;
+    const int32_t* sp = samples + (size_t)p * H * k;
+    for (size_t i = 0; i < (size_t)H * k; ++i)
+      if (sp[i] < 0 || sp[i] >= N)
+        return fail(ctx, PRE3_ERR_ARG, "sample index out of range (Index exceeds matrix dimensions): pair " +
+                                           std::to_string(p) + ", set " + std::to_string(i / k) + ", value " +
+                                           std::to_string(sp[i]) + " with N = " + std::to_string(N));
+  }
+  return PRE3_OK;
+}
+
 int pre3_fit_batch(pre3_ctx* ctx, const double* Ya, const double* Yb, int N, const int32_t* samples, int k, int H,
                    int method, double* R, double* T, int32_t* state) {
   PRE3_LIVE();
@@ -558,6 +576,7 @@ int pre3_fit_batch(pre3_ctx* ctx, const double* Ya, const double* Yb, int N, con
   PRE3_NEED(k >= 3 && k <= 8, "minimal sample size k must be in 3..8");
   PRE3_NEED(method == PRE3_METHOD_SVD || method == PRE3_METHOD_HORN, "unknown method");
   if (H == 0) return PRE3_OK;
+  PRE3_TRY(check_samples(ctx, samples, 1, H, k, nullptr, N));
   const size_t pb = 3 * (size_t)N * 8, sb = 4 * (size_t)k * H;
   PRE3_TRY(ws_reserve(ctx, 2 * align_up(pb) + align_up(sb) + align_up(72 * (size_t)H) + align_up(24 * (size_t)H) +
                                align_up(4 * (size_t)H) + 4096));
@@ -636,6 +655,7 @@ static int ransac_batch_host(pre3_ctx* ctx, const double* Ya, const double* Yb, 
   PRE3_NEED((Ya && Yb) || (size_t)P * Nmax == 0, "null correspondences");
   if (P == 0) return PRE3_OK;
   const int H = opts->H;
+  PRE3_TRY(check_samples(ctx, samples, P, H, opts->k, n_corr, Nmax));
   const size_t pb = 3 * (size_t)P * Nmax * 8;
   const size_t sb = samples ? 4 * (size_t)P * opts->k * H : 0;
   const size_t rb = sizeof(pre3_pair_result) * (size_t)P;
@@ -708,6 +728,7 @@ int pre3_vodometry_dr_ye_batch(pre3_ctx* ctx, const double* Ya, const double* Yb
   PRE3_NEED((Ya && Yb) || (size_t)P * Nmax == 0, "null correspondences");
   if (P == 0) return PRE3_OK;
   const int H = o.H;
+  PRE3_TRY(check_samples(ctx, samples, P, H, 4, n_corr, Nmax));
   const size_t pb = 3 * (size_t)P * Nmax * 8;
   const size_t sb = samples ? 16 * (size_t)P * H : 0;
   const size_t mtb = match ? 8 * (size_t)P * Nmax : 0;

@@ -149,15 +149,36 @@ constexpr int RX_ND = 128;
 // per column in registers (strictly in bin order, siftmatch.c:101-107), the A row in shared memory.  The rows the proposal
 // cannot certify are few (a handful per thousand pairs), so what matters is the latency of ONE row: a warp per row
 // needs ~100 us for 512 columns, a 256-thread block a few.
-constexpr int RXB_THREADS = 256;
+constexpr int RXB_THREADS = 128;  // 4 warps
+constexpr int RXB_COLS = 32;      // columns per warp pass
 
+template <typename T>
+__device__ __forceinline__ void load_vec4(const T* src, T* v);
+template <>
+__device__ __forceinline__ void load_vec4<double>(const double* src, double* v) {
+  const double2 x = __ldg(reinterpret_cast<const double2*>(src));
+  const double2 y = __ldg(reinterpret_cast<const double2*>(src) + 1);
+  v[0] = x.x, v[1] = x.y, v[2] = y.x, v[3] = y.y;
+}
+template <>
+__device__ __forceinline__ void load_vec4<float>(const float* src, float* v) {
+  const float4 x = __ldg(reinterpret_cast<const float4*>(src));
+  v[0] = x.x, v[1] = x.y, v[2] = x.z, v[3] = x.w;
+}
+
+// A warp takes 32 columns at a time: every column is read as ONE coalesced row (lane = 4 consecutive bins), the
+// products delta*delta go to shared memory, then lane L sums column L strictly in bin order (row stride 129: no bank
+// conflicts).  The first version walked one column per THREAD (32 lanes x 1 KB apart per load): 47 us for a handful of
+// rows, all of it exposed L2 latency (ncu r02_p: long scoreboard 49 warps per issue).
 template <typename T, typename ACC>
 __global__ void __launch_bounds__(RXB_THREADS)
 k_match_rows_exact_blk(const T* __restrict__ L1, const T* __restrict__ L2, int K1, int K2, int ND,
                        const int32_t* __restrict__ k2c, float thresh, const int32_t* __restrict__ row_list,
                        const int32_t* __restrict__ row_list_n, int list_cap, MatchRow* __restrict__ rows,
                        int a_shared) {
-  __shared__ ACC sa[RX_ND];
+  extern __shared__ __align__(16) unsigned char rx_smem[];
+  ACC* sa = reinterpret_cast<ACC*>(rx_smem);                                 // the L1 row
+  ACC(*sprod)[RX_ND + 1] = reinterpret_cast<ACC(*)[RX_ND + 1]>(sa + RX_ND);  // [warp * 32 + column][bin]
   __shared__ Top2<ACC> sred[RXB_THREADS / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = min(*row_list_n, list_cap);
@@ -170,19 +191,34 @@ k_match_rows_exact_blk(const T* __restrict__ L1, const T* __restrict__ L2, int K
     __syncthreads();  // sa / sred of the previous row are no longer read
     for (int e = tid; e < RX_ND; e += RXB_THREADS) sa[e] = (ACC)a[e];
     __syncthreads();
+    ACC av[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) av[e] = sa[4 * lane + e];
     Top2<ACC> st;
     st.best = maxval<ACC>();
     st.second = maxval<ACC>();
     st.bestk = -1;
-    for (int c = tid; c < n2; c += RXB_THREADS) {  // ascending columns per thread: top2_update keeps the first minimum
-      const T* b = B + (size_t)c * ND;
-      ACC acc = 0;
-#pragma unroll 8
-      for (int e = 0; e < RX_ND; ++e) {
-        const ACC d = sa[e] - (ACC)b[e];
-        acc += d * d;  // strictly in bin order (siftmatch.c:101-107)
+    ACC(*mine)[RX_ND + 1] = sprod + warp * RXB_COLS;
+    for (int c0 = warp * RXB_COLS; c0 < n2; c0 += (RXB_THREADS / 32) * RXB_COLS) {
+      const int nc = min(RXB_COLS, n2 - c0);
+#pragma unroll 4
+      for (int j = 0; j < nc; ++j) {
+        T bv[4];
+        load_vec4<T>(B + (size_t)(c0 + j) * ND + 4 * lane, bv);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const ACC d = av[e] - (ACC)bv[e];
+          mine[j][4 * lane + e] = d * d;
+        }
       }
-      top2_update(st, acc, c);
+      __syncwarp();
+      if (lane < nc) {
+        ACC acc = 0;
+#pragma unroll 16
+        for (int e = 0; e < RX_ND; ++e) acc += mine[lane][e];  // strictly in bin order (siftmatch.c:101-107)
+        top2_update(st, acc, c0 + lane);  // ascending columns per lane: the first minimum is kept
+      }
+      __syncwarp();
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
@@ -204,6 +240,11 @@ k_match_rows_exact_blk(const T* __restrict__ L1, const T* __restrict__ L2, int K
       rows[rid] = o;
     }
   }
+}
+
+template <typename ACC>
+constexpr size_t rxb_smem_bytes() {
+  return sizeof(ACC) * (RX_ND + (size_t)(RXB_THREADS / 32) * RXB_COLS * (RX_ND + 1));
 }
 
 // rows -> compact list in k1 order + gathered correspondences.  One block per pair.
@@ -303,18 +344,29 @@ int launch_match_rows_exact(pre3_ctx* ctx, const void* dL1, const void* dL2, int
                             int list_cap, MatchRow* drows) {
   Span span__(ctx, T_RESCORE);
   if (ND != RX_ND) return fail(ctx, PRE3_ERR_ARG, "row recheck: ND must be 128");
-  const int blocks = 4 * ctx->sm_count;
+  const int blocks = 2 * ctx->sm_count;
+  // rows of L1 / L2 are read with 16-byte vector loads
+  if ((((uintptr_t)dL1 | (uintptr_t)dL2) & 15u) != 0) return fail(ctx, PRE3_ERR_ARG, "row recheck: descriptors must be 16-byte aligned");
+#define PRE3_RXB(T, ACC)                                                                                               \
+  do {                                                                                                                 \
+    static bool attr_done = false;                                                                                     \
+    if (!attr_done) {                                                                                                  \
+      PRE3_CUDA(cudaFuncSetAttribute(k_match_rows_exact_blk<T, ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                     (int)rxb_smem_bytes<ACC>()));                                                     \
+      attr_done = true;                                                                                                \
+    }                                                                                                                  \
+    k_match_rows_exact_blk<T, ACC><<<blocks, RXB_THREADS, rxb_smem_bytes<ACC>(), ctx->stream>>>(                       \
+        (const T*)dL1, (const T*)dL2, K1, K2, ND, dk2, thresh, drow_list, drow_list_n, list_cap, drows, ctx->l1_shared); \
+  } while (0)
   if (cls == PRE3_CLASS_DOUBLE)
-    k_match_rows_exact_blk<double, double><<<blocks, RXB_THREADS, 0, ctx->stream>>>(
-        (const double*)dL1, (const double*)dL2, K1, K2, ND, dk2, thresh, drow_list, drow_list_n, list_cap, drows, ctx->l1_shared);
+    PRE3_RXB(double, double);
   else if (cls == PRE3_CLASS_SINGLE)
-    k_match_rows_exact_blk<float, float><<<blocks, RXB_THREADS, 0, ctx->stream>>>(
-        (const float*)dL1, (const float*)dL2, K1, K2, ND, dk2, thresh, drow_list, drow_list_n, list_cap, drows, ctx->l1_shared);
+    PRE3_RXB(float, float);
   else if (cls == PRE3_CLASS_DOUBLE_F32)
-    k_match_rows_exact_blk<float, double><<<blocks, RXB_THREADS, 0, ctx->stream>>>(
-        (const float*)dL1, (const float*)dL2, K1, K2, ND, dk2, thresh, drow_list, drow_list_n, list_cap, drows, ctx->l1_shared);
+    PRE3_RXB(float, double);
   else
     return fail(ctx, PRE3_ERR_CLASS, "row recheck: class must be double or single");
+#undef PRE3_RXB
   count_launch(ctx);
   PRE3_CUDA(cudaGetLastError());
   return PRE3_OK;

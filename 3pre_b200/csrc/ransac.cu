@@ -1020,7 +1020,9 @@ k_sel_tie_quad(const PairMeta* __restrict__ meta, const double* __restrict__ Ya,
 }
 
 // NT threads per pair: 32 (one warp, batches of pairs) or 512 (a few large pairs).
-template <int NT>
+// FUSED (ablation, see launch_select): the ErrorSum of the pair's tied hypotheses is computed here, four lanes per tie
+// (the work of k_sel_tie_quad); with NT > 32 the pair's correspondences are staged in 48 Nmax bytes of shared memory.
+template <int NT, bool FUSED>
 __global__ void __launch_bounds__(NT)
 k_sel_final(const PairMeta* __restrict__ meta, const double* __restrict__ Ya, const double* __restrict__ Yb, int P,
             int Nmax, const int32_t* __restrict__ samples, uint64_t seed, uint32_t pair_id0, long long h0, int H, int k,
@@ -1039,6 +1041,18 @@ k_sel_final(const PairMeta* __restrict__ meta, const double* __restrict__ Ya, co
   const int N = m.N;
   const double* ya = Ya + (size_t)p * Nmax * 3;
   const double* yb = Yb + (size_t)p * Nmax * 3;
+  extern __shared__ double s_pts[];
+  if (FUSED && NT > 32) {
+    double* sa = s_pts;
+    double* sb = s_pts + 3 * (size_t)Nmax;
+    for (int i = tid; i < 3 * N; i += NT) {
+      sa[i] = ya[i];
+      sb[i] = yb[i];
+    }
+    ya = sa;
+    yb = sb;
+    __syncthreads();
+  }
   const int8_t* sts = states + (size_t)p * H;
   uint8_t* mask = masks ? masks + (size_t)p * mask_stride : mask_scratch + (size_t)p * Nmax;
   auto recorded = [&](int s) { return !(method == PRE3_METHOD_SVD && sts[s] == -1); };
@@ -1046,12 +1060,48 @@ k_sel_final(const PairMeta* __restrict__ meta, const double* __restrict__ Ya, co
   // ---- min ErrorSum over this pair's ties (listed in ascending s), first index on equal sums --------
   double best_es = INFINITY;
   int best_s = 0x7fffffff;
-  for (int j = tid; j < si.n_ties; j += NT) {
-    const int s = pair_ties[(size_t)p * H + j];
-    const double es = es_in[(size_t)p * H + s];
-    if (es < best_es) {  // ascending s within a thread: strict < keeps the first
-      best_es = es;
-      best_s = s;
+  if (FUSED) {
+    constexpr int G = 4;  // lanes per tie (k_sel_tie_quad: 4 measured best)
+    const int sub = tid & (G - 1), qid = tid / G, quads = NT / G;
+    for (int j0 = 0; j0 < si.n_ties; j0 += quads) {
+      const int j = j0 + qid;
+      const bool live = j < si.n_ties;
+      if (!__any_sync(0xffffffffu, live)) continue;  // warp-uniform
+      const int s = pair_ties[(size_t)p * H + (live ? j : 0)];
+      int idx[MAX_K];
+      load_sample(samples, seed, pair_id0 + (uint32_t)p, h0, s, H, p, max(N, 1), k, idx);
+      Rigid f;
+      fit_sample(method, ya, yb, idx, k, f);
+      double es = 0.0;
+      for (int ib = 0; ib < N; ib += 2 * G) {
+        double v0 = 0.0, v1 = 0.0;
+        const int i0 = ib + sub, i1 = ib + G + sub;
+        if (i0 < N) {
+          const double nr = residual_norm(f.R, f.t, ya + 3 * i0, yb + 3 * i0);
+          v0 = nr < m.thr ? nr : 0.0;  // sum(normResidu(inliers)) in index order (:135); + 0.0 is exact
+        }
+        if (i1 < N) {
+          const double nr = residual_norm(f.R, f.t, ya + 3 * i1, yb + 3 * i1);
+          v1 = nr < m.thr ? nr : 0.0;
+        }
+#pragma unroll
+        for (int l = 0; l < G; ++l) es = es + __shfl_sync(0xffffffffu, v0, l, G);
+#pragma unroll
+        for (int l = 0; l < G; ++l) es = es + __shfl_sync(0xffffffffu, v1, l, G);
+      }
+      if (live && es < best_es) {  // ascending s within a quad: strict < keeps the first
+        best_es = es;
+        best_s = s;
+      }
+    }
+  } else {
+    for (int j = tid; j < si.n_ties; j += NT) {
+      const int s = pair_ties[(size_t)p * H + j];
+      const double es = es_in[(size_t)p * H + s];
+      if (es < best_es) {  // ascending s within a thread: strict < keeps the first
+        best_es = es;
+        best_s = s;
+      }
     }
   }
 #pragma unroll
@@ -2453,6 +2503,27 @@ int launch_select(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts&
                                                     dstates_out, info, ties, tie_total, pair_ties);
   const size_t tie_warps = TIE_THREADS / 32;
   const int tie_blocks = (int)std::min<size_t>((PH + tie_warps - 1) / tie_warps, (size_t)ctx->sm_count * 16);
+  // Ablation (off by default): ties + winner + refit of a pair in ONE block (PRE3_SEL_FUSED=1: a warp per pair, 2: 64
+  // threads with the points staged in shared memory).  Measured on the 4096-pair step: select 0.34 / 0.33 ms against
+  // 0.216 ms for the three-launch form below -- serialising a pair's tie sums and its winner's mask + refit in one block
+  // lengthens the fp64 critical path more than the saved launch and the re-read of the points (L2 hits) cost.
+  static const int fuse_ties = getenv("PRE3_SEL_FUSED") ? atoi(getenv("PRE3_SEL_FUSED")) : 0;
+  if (many && fuse_ties == 2 && (size_t)b.Nmax * 48 <= 48 * 1024) {
+    k_sel_final<64, true><<<b.P, 64, (size_t)b.Nmax * 48, ctx->stream>>>(
+        b.meta, b.Ya, b.Yb, b.P, b.Nmax, b.samples, o.seed, b.pair_id0, b.h0, o.H, o.k, o.method, b.counts, b.states, info,
+        pair_ties, es, dres, dmasks, b.Nmax, scratch);
+    count_launch(ctx, 2);
+    PRE3_CUDA(cudaGetLastError());
+    return PRE3_OK;
+  }
+  if (many && fuse_ties == 1 && b.Nmax <= 2048) {  // one warp per pair, eight ties at a time, points through L1
+    k_sel_final<32, true><<<b.P, 32, 0, ctx->stream>>>(
+        b.meta, b.Ya, b.Yb, b.P, b.Nmax, b.samples, o.seed, b.pair_id0, b.h0, o.H, o.k, o.method, b.counts, b.states, info,
+        pair_ties, es, dres, dmasks, b.Nmax, scratch);
+    count_launch(ctx, 2);
+    PRE3_CUDA(cudaGetLastError());
+    return PRE3_OK;
+  }
   if (b.Nmax <= 2048) {  // thread per tie; the ordered sum of a long residual list wants a warp per tie
     // 4 lanes per tie measured best (select 0.34 -> 0.27 ms per 4096 pairs; 8 lanes 0.28, 16 lanes 0.31)
     const int tb = (int)std::min<size_t>((4 * PH + TIE_THREADS - 1) / TIE_THREADS, (size_t)ctx->sm_count * 16);
@@ -2463,11 +2534,11 @@ int launch_select(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts&
                                                            b.h0, o.H, o.k, o.method, ties, tie_total, (int)PH, es);
   }
   if (many)
-    k_sel_final<32><<<b.P, 32, 0, ctx->stream>>>(b.meta, b.Ya, b.Yb, b.P, b.Nmax, b.samples, o.seed, b.pair_id0, b.h0,
+    k_sel_final<32, false><<<b.P, 32, 0, ctx->stream>>>(b.meta, b.Ya, b.Yb, b.P, b.Nmax, b.samples, o.seed, b.pair_id0, b.h0,
                                                  o.H, o.k, o.method, b.counts, b.states, info, pair_ties, es, dres,
                                                  dmasks, b.Nmax, scratch);
   else
-    k_sel_final<512><<<b.P, 512, 0, ctx->stream>>>(b.meta, b.Ya, b.Yb, b.P, b.Nmax, b.samples, o.seed, b.pair_id0,
+    k_sel_final<512, false><<<b.P, 512, 0, ctx->stream>>>(b.meta, b.Ya, b.Yb, b.P, b.Nmax, b.samples, o.seed, b.pair_id0,
                                                      b.h0, o.H, o.k, o.method, b.counts, b.states, info, pair_ties, es,
                                                      dres, dmasks, b.Nmax, scratch);
   count_launch(ctx, 3);

@@ -294,7 +294,27 @@ def bench_cfg2(ctx, pre3, synth, dev, rank, P=256, K=2048, steps=5, warmup=2):
         out["roofline"] = {"kernel": "match_tc", "bound": "tensor", "achieved": a, "peak": pk["bf16_tflops"],
                            "unit": "TFLOP/s", "frac": a / pk["bf16_tflops"], "traffic": None,
                            "note": f"algorithmic 2*K1*K2*128 per pair; peak {pk['source']}"}
+    # the uint8 variant of the same config (sift_demo2.m:93-94: uint8(512 * descr)): tcgen05 kind::i8, exact, no rescore
+    u1 = torch.clamp(torch.floor(512.0 * d1 + 0.5), 0, 255).to(torch.uint8)
+    u2 = torch.clamp(torch.floor(512.0 * d2 + 0.5), 0, 255).to(torch.uint8)
     del d1, d2
+
+    def step_u8():
+        ctx.siftmatch_batch_dev(u1, u2, pairs, None, n_out, 1.5)
+
+    ms8 = _time_steps(step_u8, steps, warmup)
+    kt8 = _kernel_times(ctx, step_u8)
+    g8 = kt8.get("match_tc", {}).get("ms_per_step", 0.0)
+    out["uint8"] = {"pairs_per_s": P / (ms8 * 1e-3), "ms_per_step": ms8,
+                    "accepted_matches_per_pair": float(n_out.float().mean().item()), "kernels": kt8}
+    if g8 > 0:
+        a8 = flops / (g8 * 1e-3) / 1e12
+        out["uint8"]["roofline"] = {"kernel": "k_i8_gemm_pair", "bound": "tensor", "achieved": a8,
+                                    "peak": 2.0 * pk["bf16_tflops"], "unit": "TOP/s", "frac": a8 / (2.0 * pk["bf16_tflops"]),
+                                    "traffic": None,
+                                    "note": "algorithmic 2*K1*K2*128 integer ops per pair; peak = 2 x the measured bf16 rate "
+                                            "(the int8 tensor rate is not in MEASURED_PEAKS.json; nominal int8 = 2 x bf16)"}
+    del u1, u2
     torch.cuda.empty_cache()
     return out
 
@@ -882,7 +902,8 @@ def run_ours(args):
                 "cfg1_latency": _summ(o.get("cfg1", {}), ["k5.ms_per_pair_device_resident", "k5.ms_per_pair_host_buffers",
                                                           "k3.ms_per_pair_device_resident"]),
                 "cfg2_matching_256x2048x2048": _summ(o.get("cfg2", {}), ["pairs_per_s", "ms_per_step", "roofline.achieved",
-                                                                         "roofline.frac"]),
+                                                                         "roofline.frac", "uint8.pairs_per_s",
+                                                                         "uint8.ms_per_step", "uint8.roofline.achieved"]),
                 "cfg4_ekf_200_features": _summ(o.get("cfg4", {}), ["adaptive.frames_per_s", "fixed_H.frames_per_s",
                                                                    "fixed_H.hyp_x_feature_evals_per_s",
                                                                    "fixed_H.roofline_score.frac", "fixed_H.roofline_gain.frac"]),

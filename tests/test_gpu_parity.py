@@ -718,3 +718,18 @@ def test_process_sequence_from_cached_sift_results(ctx, pre3, orc, synth, tmp_pa
             (g.status, g.best_fit, g.best_sample, g.state), (p, res[p], g)
         T, R, st = fm.load_ransac_step(fm.ransac_step_path(folder, 10 + p, 11 + p))
         assert st == g.state and np.abs(R - g.R).max() < 1e-9 and np.abs(T.ravel() - g.T).max() < 1e-9
+
+
+def test_sample_index_out_of_range_is_an_error(ctx, synth, pre3):
+    """MATLAB raises 'Index exceeds matrix dimensions' for Ya(:, idx) with idx > N; explicit sample sets handed to the
+    host entry points are validated the same way instead of being clamped."""
+    c = synth.make_correspondences(5, N=50, outlier_ratio=0.2)
+    samples = synth.make_samples(6, 20, 50, 5)
+    bad = samples.copy(); bad[7, 2] = 50
+    with pytest.raises(pre3.Pre3Error, match="Index exceeds matrix dimensions"):
+        ctx.ransac(c.Ya, c.Yb, bad, pre3.make_opts(adaptive=False))
+    neg = samples.copy(); neg[0, 0] = -1
+    with pytest.raises(pre3.Pre3Error, match="Index exceeds matrix dimensions"):
+        ctx.fit_batch(c.Ya, c.Yb, neg, 0)
+    g = ctx.ransac(c.Ya, c.Yb, samples, pre3.make_opts(adaptive=False))   # the context stays usable
+    assert g.status == 0
