@@ -97,6 +97,7 @@ SYMBOLS = {
     "pre3_set_graphs": (_I, [_VP, _I]),
     "pre3_transfer_bytes": (_I, [_VP, _VP, _VP]),
     "pre3_eval_schedule": (_I, [_OPTS, _VP, _I]),
+    "pre3_eval_schedule_for": (_I, [_OPTS, _I, _VP, _I]),
     "pre3_timing_enable": (_I, [_VP, _I]),
     "pre3_timing_read": (_I, [_VP, _VP, _VP]),
     "pre3_timing_name": (C.c_char_p, [_I]),

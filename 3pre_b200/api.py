@@ -185,10 +185,13 @@ class Context:
         self._ck(self._lib.pre3_transfer_bytes(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
 
-    def eval_schedule(self, opts: RansacOpts):
-        """Wave boundaries of the hypothesis evaluation (pre3_eval_schedule)."""
+    def eval_schedule(self, opts: RansacOpts, P: int | None = None):
+        """Wave boundaries of the hypothesis evaluation (pre3_eval_schedule; with P: for a call of exactly P pairs)."""
         ends = np.zeros(40, np.int32)
-        n = self._lib.pre3_eval_schedule(C.byref(opts), _ptr(ends), 40)
+        if P is None:
+            n = self._lib.pre3_eval_schedule(C.byref(opts), _ptr(ends), 40)
+        else:
+            n = self._lib.pre3_eval_schedule_for(C.byref(opts), int(P), _ptr(ends), 40)
         if n < 0:
             raise L.Pre3Error(n, "pre3_eval_schedule")
         return ends[:n].copy()

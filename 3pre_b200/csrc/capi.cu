@@ -309,6 +309,11 @@ int pre3_eval_schedule(const pre3_ransac_opts* opts, int32_t* ends, int cap) {
   return eval_wave_ends(*opts, ends, cap);
 }
 
+int pre3_eval_schedule_for(const pre3_ransac_opts* opts, int P, int32_t* ends, int cap) {
+  if (!opts || P < 1 || (cap > 0 && !ends)) return PRE3_ERR_ARG;
+  return eval_wave_ends(*opts, ends, cap, P);
+}
+
 int pre3_timing_enable(pre3_ctx* ctx, int on) {
   if (!ctx || ctx->device < 0) return PRE3_ERR_CUDA;
   ctx->timing = on != 0;

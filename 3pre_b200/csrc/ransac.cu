@@ -1359,8 +1359,10 @@ __device__ __noinline__ void pairloop_select(const PairMeta& m, const double* __
 // iteration count to within one chunk (the wave schedule of round 1 evaluated 1.34x the sample sets the loop needs).
 // Entries beyond the last chunk are never written: k_sel_scan finds the same stop index and reads nothing past it.
 // SELECT: the block also runs the selection of its pair (pairloop_select below) -- no selection kernels.
-template <int K, int MODE, bool SELECT, int MINB = 8>
-__global__ void __launch_bounds__(EVP_THREADS, MINB)
+// NT: threads per block = sample sets per chunk (64; 128 / 256 when a GPU holds fewer pairs than it has block slots:
+// fewer, wider chunks shorten a pair's critical path at the price of evaluating sets the reference loop would not reach)
+template <int K, int MODE, bool SELECT, int MINB = 8, int NT = EVP_THREADS>
+__global__ void __launch_bounds__(NT, MINB)
 k_eval_pairloop(const PairMeta* __restrict__ meta, const double* __restrict__ Ya, const double* __restrict__ Yb,
                 const float4* __restrict__ Ya4, const float4* __restrict__ Yb4, int Nmax,
                 const int32_t* __restrict__ samples, uint64_t seed, uint32_t pair_id0, int H, int method,
@@ -1368,10 +1370,12 @@ k_eval_pairloop(const PairMeta* __restrict__ meta, const double* __restrict__ Ya
                 int8_t* __restrict__ states, int32_t* __restrict__ evaluated, pre3_pair_result* __restrict__ res,
                 uint8_t* __restrict__ masks, int mask_stride, uint8_t* __restrict__ mask_scratch) {
   __shared__ __align__(16) float sM[6][EVP_TILE];
-  __shared__ double sRt[EVP_THREADS * 12];
-  __shared__ int sCnt[EVP_THREADS];
-  __shared__ int sState[EVP_THREADS];
-  __shared__ uint32_t sList[EVP_LIST];
+  static_assert(!SELECT || NT == EVP_THREADS, "fused selection is built for 64 threads");
+  constexpr int LIST = EVP_LIST * (NT / EVP_THREADS);
+  __shared__ double sRt[NT * 12];
+  __shared__ int sCnt[NT];
+  __shared__ int sState[NT];
+  __shared__ uint32_t sList[LIST];
   __shared__ int sListN, sStop, sSel[3];
 
   const int p = blockIdx.x;
@@ -1386,15 +1390,15 @@ k_eval_pairloop(const PairMeta* __restrict__ meta, const double* __restrict__ Ya
     if (SELECT) {
       if (tid == 0) result_init(res + p, 1, 0, N, m.thr);
       if (masks)
-        for (int i = tid; i < mask_stride; i += EVP_THREADS) masks[(size_t)p * mask_stride + i] = 0;
+        for (int i = tid; i < mask_stride; i += NT) masks[(size_t)p * mask_stride + i] = 0;
     }
     return;
   }
   const bool one_tile = N <= EVP_TILE;
-  if (one_tile) eval_stage<EVP_THREADS, EVP_TILE>(sM, Ya4 + (size_t)p * Nmax, Yb4 + (size_t)p * Nmax, N, (N + 3) & ~3);
+  if (one_tile) eval_stage<NT, EVP_TILE>(sM, Ya4 + (size_t)p * Nmax, Yb4 + (size_t)p * Nmax, N, (N + 3) & ~3);
   int car_c = 0, car_m = 0;  // recorded hypotheses / max cardinality over the chunks before
   int hdone = 0;
-  for (int hbeg = 0; hbeg < H; hbeg += EVP_THREADS) {
+  for (int hbeg = 0; hbeg < H; hbeg += NT) {
     const int h = hbeg + tid;
     if (tid == 0) sListN = 0;
     const bool valid = h < H;
@@ -1403,18 +1407,18 @@ k_eval_pairloop(const PairMeta* __restrict__ meta, const double* __restrict__ Ya
     int cnt = 0;
     if (one_tile) {
       __syncthreads();  // staged tile / list counter visible
-      cnt = eval_score_tile<EVP_TILE, EVP_LIST>(sM, N, 0, hy, tid, sList, &sListN);
+      cnt = eval_score_tile<EVP_TILE, LIST>(sM, N, 0, hy, tid, sList, &sListN);
     } else {
       for (int base = 0; base < N; base += EVP_TILE) {
         const int tn = min(EVP_TILE, N - base);
         __syncthreads();
-        eval_stage<EVP_THREADS, EVP_TILE>(sM, Ya4 + (size_t)p * Nmax + base, Yb4 + (size_t)p * Nmax + base, tn, (tn + 3) & ~3);
+        eval_stage<NT, EVP_TILE>(sM, Ya4 + (size_t)p * Nmax + base, Yb4 + (size_t)p * Nmax + base, tn, (tn + 3) & ~3);
         __syncthreads();
-        cnt += eval_score_tile<EVP_TILE, EVP_LIST>(sM, tn, base, hy, tid, sList, &sListN);
+        cnt += eval_score_tile<EVP_TILE, LIST>(sM, tn, base, hy, tid, sList, &sListN);
       }
     }
     sCnt[tid] = cnt;
-    eval_recheck<MODE, EVP_THREADS, EVP_LIST>(m, ya, yb, sRt, sCnt, sList, &sListN, hy.scored, hy.exact_me);
+    eval_recheck<MODE, NT, LIST>(m, ya, yb, sRt, sCnt, sList, &sListN, hy.scored, hy.exact_me);
     const int c = hy.scored ? sCnt[tid] : -1;
     if (h < H) {
       counts[(size_t)p * H + h] = c;
@@ -1423,18 +1427,24 @@ k_eval_pairloop(const PairMeta* __restrict__ meta, const double* __restrict__ Ya
     sState[tid] = (h < H && !(method == PRE3_METHOD_SVD && hy.state == -1)) ? 1 : 0;  // recorded by the reference's loop
     sCnt[tid] = c;
     __syncthreads();
-    // loop control over this chunk: warp 0, two sample sets per lane, in order
+    // loop control over this chunk: warp 0, NT / 32 consecutive sample sets per lane, in order
     if (tid < 32) {
-      const int s0 = 2 * lane, s1 = 2 * lane + 1;
-      const int r0 = sState[s0], r1 = sState[s1];
-      const int c0 = r0 ? sCnt[s0] : 0, c1 = r1 ? sCnt[s1] : 0;
-      int pc = r0 + r1, pm = max(c0, c1);
+      constexpr int E = NT / 32;
+      int rr[E], cc[E];
+      int pc = 0, pm = 0;
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        rr[e] = sState[E * lane + e];
+        cc[e] = rr[e] ? sCnt[E * lane + e] : 0;
+        pc += rr[e];
+        pm = max(pm, cc[e]);
+      }
 #pragma unroll
       for (int off = 1; off < 32; off <<= 1) {
-        const int cc = __shfl_up_sync(0xffffffffu, pc, off);
+        const int c2 = __shfl_up_sync(0xffffffffu, pc, off);
         const int mm = __shfl_up_sync(0xffffffffu, pm, off);
         if (lane >= off) {
-          pc += cc;
+          pc += c2;
           pm = max(pm, mm);
         }
       }
@@ -1449,8 +1459,8 @@ k_eval_pairloop(const PairMeta* __restrict__ meta, const double* __restrict__ Ya
       pm = max(pm, car_m);
       int my_stop = 0x7fffffff, stop_pc = 0, stop_pm = 0;
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int sl = 2 * lane + e;
+      for (int e = 0; e < E; ++e) {
+        const int sl = E * lane + e;
         if (hbeg + sl < H && my_stop == 0x7fffffff) {
           int nit = max_iteration;
           if (pm >= 5) nit = min(trow[min(pm, N)], max_iteration);
@@ -1459,9 +1469,9 @@ k_eval_pairloop(const PairMeta* __restrict__ meta, const double* __restrict__ Ya
             stop_pc = pc;
             stop_pm = pm;
           }
-          if (e == 0 && r0) {
+          if (rr[e]) {
             ++pc;
-            pm = max(pm, c0);
+            pm = max(pm, cc[e]);
           }
         }
       }
@@ -1476,7 +1486,7 @@ k_eval_pairloop(const PairMeta* __restrict__ meta, const double* __restrict__ Ya
           sSel[1] = stop_pc;
           sSel[2] = stop_pm;
         }
-      } else if (lane == 0 && hbeg + EVP_THREADS >= H) {  // ran through every sample set
+      } else if (lane == 0 && hbeg + NT >= H) {  // ran through every sample set
         sSel[0] = H;
         sSel[1] = car_c;
         sSel[2] = car_m;
@@ -1484,11 +1494,11 @@ k_eval_pairloop(const PairMeta* __restrict__ meta, const double* __restrict__ Ya
       if (lane == 0) sStop = first;
     }
     __syncthreads();
-    hdone = min(H, hbeg + EVP_THREADS);
+    hdone = min(H, hbeg + NT);
     if (sStop != 0x7fffffff) break;
   }
   if (tid == 0 && evaluated) evaluated[p] = hdone;
-  if (SELECT)
+  if constexpr (SELECT)
     pairloop_select(m, ya, yb, samples, seed, pair_id0, H, K, method, p, counts + (size_t)p * H, states + (size_t)p * H,
                     sSel[0], sSel[1], sSel[2], res + p,
                     masks ? masks + (size_t)p * mask_stride : mask_scratch + (size_t)p * Nmax, masks ? mask_stride : 0,
@@ -2356,6 +2366,18 @@ int launch_eval(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts& o
 // evaluated in waves over all SMs, with a scan between waves that drops the pairs whose loop has ended.
 constexpr int PAIRLOOP_MIN_P = 64;
 
+// threads per pair block of k_eval_pairloop: 64, or 128 / 256 (k = 5, find_transform_matrix) when the batch leaves block
+// slots idle (148 SMs x 8 blocks of 64 threads); PRE3_EVP_NT overrides
+static int pairloop_threads(const pre3_ransac_opts& o, int P) {
+  if (!(o.k == 5 && o.method == PRE3_METHOD_SVD)) return EVP_THREADS;
+  static const int forced = getenv("PRE3_EVP_NT") ? atoi(getenv("PRE3_EVP_NT")) : 0;
+  if (forced == 64 || forced == 128 || forced == 256) return forced;
+  if (P <= 0) return EVP_THREADS;
+  if (P <= 296) return 256;
+  if (P <= 592) return 128;
+  return EVP_THREADS;
+}
+
 static bool use_pairloop(const RansacBuffers& b, const pre3_ransac_opts& o) {
   return o.adaptive && b.P >= PAIRLOOP_MIN_P && b.tab.tab != nullptr && o.k >= 3 && o.k <= 8;
 }
@@ -2367,7 +2389,8 @@ int eval_wave_ends(const pre3_ransac_opts& o, int32_t* ends, int cap, int P) {
   int n = 0;
   if (H <= 0) return 0;
   if (o.adaptive && (P <= 0 || P >= PAIRLOOP_MIN_P)) {
-    for (int e = EVP_THREADS; ; e += EVP_THREADS) {
+    const int chunk = pairloop_threads(o, P);
+    for (int e = chunk; ; e += chunk) {
       if (n < cap) ends[n] = std::min(e, H);
       ++n;
       if (e >= H) break;
@@ -2405,6 +2428,21 @@ static int launch_eval_pairloop_mode(pre3_ctx* ctx, const RansacBuffers& b, cons
   // (measured at the sequence shape, eval ms per 4096 pairs: 8 -> 0.338, 10 -> 0.351, 12 -> 0.382, 16 -> 0.393: the
   // spills of the fp64 fit cost more than the extra warps bring)
   static const int minb = getenv("PRE3_EVP_MINB") ? atoi(getenv("PRE3_EVP_MINB")) : 8;
+  if constexpr (MODE == 0 && !SELECT) {
+    const int nt = pairloop_threads(o, b.P);
+    if (nt != EVP_THREADS) {  // few pairs per GPU: wider blocks (same registers per thread: 4 / 2 blocks per SM)
+#define PRE3_EVALPW(MB, NTT)                                                                                       \
+  k_eval_pairloop<5, 0, false, MB, NTT><<<b.P, NTT, 0, ctx->stream>>>(                                              \
+      b.meta, b.Ya, b.Yb, b.Ya4, b.Yb4, b.Nmax, b.samples, o.seed, b.pair_id0, o.H, o.method, o.max_iteration,     \
+      b.tab.tab, b.counts, b.states, b.stop, dres, dmasks, b.Nmax, scratch)
+      if (nt == 128) PRE3_EVALPW(4, 128);
+      else PRE3_EVALPW(2, 256);
+#undef PRE3_EVALPW
+      count_launch(ctx);
+      PRE3_CUDA(cudaGetLastError());
+      return PRE3_OK;
+    }
+  }
   if (o.k == 5 && MODE == 0 && !SELECT && minb != 8) {
 #define PRE3_EVALPB(MB)                                                                                            \
   k_eval_pairloop<5, 0, false, MB><<<b.P, EVP_THREADS, 0, ctx->stream>>>(                                          \
@@ -2526,9 +2564,20 @@ int launch_select(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts&
   }
   if (b.Nmax <= 2048) {  // thread per tie; the ordered sum of a long residual list wants a warp per tie
     // 4 lanes per tie measured best (select 0.34 -> 0.27 ms per 4096 pairs; 8 lanes 0.28, 16 lanes 0.31)
-    const int tb = (int)std::min<size_t>((4 * PH + TIE_THREADS - 1) / TIE_THREADS, (size_t)ctx->sm_count * 16);
-    k_sel_tie_quad<4><<<tb, TIE_THREADS, 0, ctx->stream>>>(b.meta, b.Ya, b.Yb, b.Nmax, b.samples, o.seed, b.pair_id0,
-                                                           b.h0, o.H, o.k, o.method, ties, tie_total, (int)PH, es);
+    // lanes per tie: 4 when the batch fills the machine (4096 pairs x ~8 ties); with fewer pairs per GPU the residual
+    // loop of a tie is the critical path and more lanes shorten it (PRE3_TIE_G overrides)
+    static const int forced_g = getenv("PRE3_TIE_G") ? atoi(getenv("PRE3_TIE_G")) : 0;
+    int G = b.P >= 2048 ? 4 : (b.P >= 768 ? 8 : 16);
+    if (forced_g == 4 || forced_g == 8 || forced_g == 16 || forced_g == 32) G = forced_g;
+    const int tb = (int)std::min<size_t>(((size_t)G * PH + TIE_THREADS - 1) / TIE_THREADS, (size_t)ctx->sm_count * 16);
+#define PRE3_TIE(GG)                                                                                                  \
+  k_sel_tie_quad<GG><<<tb, TIE_THREADS, 0, ctx->stream>>>(b.meta, b.Ya, b.Yb, b.Nmax, b.samples, o.seed, b.pair_id0,  \
+                                                          b.h0, o.H, o.k, o.method, ties, tie_total, (int)PH, es)
+    if (G == 4) PRE3_TIE(4);
+    else if (G == 8) PRE3_TIE(8);
+    else if (G == 16) PRE3_TIE(16);
+    else PRE3_TIE(32);
+#undef PRE3_TIE
   } else {
     k_sel_tie<<<tie_blocks, TIE_THREADS, 0, ctx->stream>>>(b.meta, b.Ya, b.Yb, b.Nmax, b.samples, o.seed, b.pair_id0,
                                                            b.h0, o.H, o.k, o.method, ties, tie_total, (int)PH, es);

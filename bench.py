@@ -740,7 +740,7 @@ def run_ours(args):
     r = np.frombuffer(gathered[0].cpu().numpy().tobytes(), dtype=pre3.RESULT_DTYPE)
     ok_pairs = int(((r["status"] == 0) & (r["best_fit"] > 150)).sum())
     rl = r[p0:p1]
-    ends = ctx.eval_schedule(opts)  # schedule of the batched path: a pair that consumed n sets had ends[first i: n < ends[i]] evaluated
+    ends = ctx.eval_schedule(opts, P=p1 - p0)  # schedule of the batched path: a pair that consumed n sets had ends[first i: n < ends[i]] evaluated
     wave = np.minimum(np.searchsorted(ends, rl["n_consumed"], side="right"), len(ends) - 1)
     hyps_done = ends[wave].astype(np.float64)
     evals_done = float((rl["n_matches"].astype(np.float64) * hyps_done).sum())          # evaluated on this GPU

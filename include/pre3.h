@@ -137,6 +137,10 @@ PRE3_API int pre3_transfer_bytes(const pre3_ctx *ctx, int64_t *h2d, int64_t *d2h
  * number: a pair that consumed n sets had ends[min{i : n < ends[i]}] (or H) sets evaluated.
  * bench.py derives the executed hypothesis x match evaluations from this. */
 PRE3_API int pre3_eval_schedule(const pre3_ransac_opts *opts, int32_t *ends, int cap);
+/* The same for a call with exactly P pairs: fewer than 64 pairs run in waves; batches that leave block slots idle
+ * (P <= 592 / P <= 296 with k = 5, find_transform_matrix) use chunks of 128 / 256 sample sets -- a shorter critical
+ * path per pair at the price of evaluating sets the reference loop would not reach. */
+PRE3_API int pre3_eval_schedule_for(const pre3_ransac_opts *opts, int P, int32_t *ends, int cap);
 /* Per-kernel CUDA-event timing on the context's stream (off by default; bench.py's roofline
  * numbers).  pre3_timing_read synchronises, adds the elapsed ms and launch counts of every
  * bracketed launch since the last read into ms[cat] / count[cat] (PRE3_TIMING_NCAT entries
