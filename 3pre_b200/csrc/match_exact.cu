@@ -201,15 +201,20 @@ k_match_rows_exact_blk(const T* __restrict__ L1, const T* __restrict__ L2, int K
     ACC(*mine)[RX_ND + 1] = sprod + warp * RXB_COLS;
     for (int c0 = warp * RXB_COLS; c0 < n2; c0 += (RXB_THREADS / 32) * RXB_COLS) {
       const int nc = min(RXB_COLS, n2 - c0);
-#pragma unroll 4
-      for (int j = 0; j < nc; ++j) {
-        T bv[4];
-        load_vec4<T>(B + (size_t)(c0 + j) * ND + 4 * lane, bv);
+      for (int j0 = 0; j0 < nc; j0 += 16) {  // sixteen columns' loads in flight together: a row is a latency chain
+        T bv[16][4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const ACC d = av[e] - (ACC)bv[e];
-          mine[j][4 * lane + e] = d * d;
-        }
+        for (int u = 0; u < 16; ++u)
+          if (j0 + u < nc) load_vec4<T>(B + (size_t)(c0 + j0 + u) * ND + 4 * lane, bv[u]);
+#pragma unroll
+        for (int u = 0; u < 16; ++u)
+          if (j0 + u < nc) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const ACC d = av[e] - (ACC)bv[u][e];
+              mine[j0 + u][4 * lane + e] = d * d;
+            }
+          }
       }
       __syncwarp();
       if (lane < nc) {

@@ -966,6 +966,162 @@ k_tc_rescore(const T* __restrict__ L1, const T* __restrict__ L2, int K1, int K2,
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// k_tc_rescore2: the same decisions as k_tc_rescore in two phases per 256-row block.  Phase A: one THREAD per row
+// decides what the proposal's brackets decide (rejected for sure / accepted without recomputing) and lists the rows
+// that need the exact candidate distance; phase B: two warps take the listed rows 32 at a time (coalesced loads of the
+// row and of its candidate column, products in shared memory, lane r sums row r strictly in bin order).  k_tc_rescore
+// ran one warp per 16 rows with 16.5 KB of shared memory per warp: 13 warps per SM, half of their lanes idle, for a
+// phase-B population of a few per cent of the rows (ncu r02_p: 85 us per 4096 pairs, warps active 18 %).
+// ---------------------------------------------------------------------------------------------
+constexpr int RS2_THREADS = 256;
+constexpr int RS2_BW = 2;      // warps of the exact pass
+constexpr int RS2_ROWS = 32;   // rows per warp pass
+
+struct RsDecision {
+  Prop my;
+  double na, m;
+  MatchRow out;
+  bool need_exact, ambiguous;
+};
+
+__device__ __forceinline__ RsDecision rescore_decide(int p, int pa, int k1, int n2, int K1p, float thresh,
+                                                     const Prop* __restrict__ prop, const float* __restrict__ nrmA,
+                                                     const PairInfo& pi, int need_score) {
+  RsDecision d;
+  d.out.best = INFINITY;
+  d.out.bestk = -1;
+  d.out.accept = 0;
+  d.need_exact = d.ambiguous = false;
+  d.my.best = d.my.second = INFINITY;
+  d.my.idx = -1;
+  d.na = d.m = 0.0;
+  if (n2 <= 0) return d;
+  d.my = prop[(size_t)p * K1p + k1];
+  const double na = (double)nrmA[(size_t)pa * K1p + k1];
+  const double nbm = (double)__uint_as_float(pi.bmax_bits);
+  const double ra = sqrt(na), rbm = sqrt(nbm);
+  // error bound of the CTA-pair proposal (see rescore_group)
+  const double m = 1.25 * ((1.0 / 512 + 1.0 / 16384) * ra * rbm + (na + nbm) * (1.0 / 16384) + (ra + rbm) * (1.0 / 1048576) + 1.0 / 4194304);
+  d.na = na;
+  d.m = m;
+  if (pi.bad || d.my.idx < 0 || d.my.idx >= n2 || !(thresh > 0.f) || !(d.my.best > -INFINITY)) {
+    d.ambiguous = true;
+    return d;
+  }
+  const double b1 = na - 2.0 * (double)d.my.best, s2 = na - 2.0 * (double)d.my.second;
+  const double L1b = b1 - m, U2b = s2 + m;
+  if (L1b > 0.0 && __fmul_rn(thresh, (float)L1b) > (float)U2b) {
+    d.out.accept = 0;
+  } else if (!need_score && b1 + m < s2 - m && __fmul_rn(thresh, (float)(b1 + m)) <= (float)(s2 - m)) {
+    d.out.accept = 1;
+    d.out.bestk = d.my.idx;
+    d.out.best = b1;
+  } else {
+    d.need_exact = true;
+  }
+  return d;
+}
+
+template <typename T, typename ACC>
+__global__ void __launch_bounds__(RS2_THREADS)
+k_tc_rescore2(const T* __restrict__ L1, const T* __restrict__ L2, int K1, int K2, int K1p, int K2p,
+              const int32_t* __restrict__ k1c, const int32_t* __restrict__ k2c, float thresh,
+              const Prop* __restrict__ prop, const float* __restrict__ nrmA, const PairInfo* __restrict__ info,
+              int need_score, int a_shared, MatchRow* __restrict__ rows, int32_t* __restrict__ row_list,
+              int32_t* __restrict__ row_list_n) {
+  extern __shared__ __align__(16) unsigned char rs2_smem[];
+  ACC(*sprod)[ND + 1] = reinterpret_cast<ACC(*)[ND + 1]>(rs2_smem);  // [warp * 32 + row][bin]
+  __shared__ int s_list[RS2_THREADS];
+  __shared__ int s_n;
+  const int p = blockIdx.y, pa = a_shared ? 0 : p;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n1 = k1c ? max(0, min(k1c[pa], K1)) : K1;
+  const int n2 = k2c ? max(0, min(k2c[p], K2)) : K2;
+  const int row0 = blockIdx.x * RS2_THREADS;
+  if (row0 >= n1) return;
+  const PairInfo pi = info[p];
+  if (tid == 0) s_n = 0;
+  __syncthreads();
+  // ---- phase A ------------------------------------------------------------------------------------
+  const int k1 = row0 + tid;
+  if (k1 < n1) {
+    const RsDecision d = rescore_decide(p, pa, k1, n2, K1p, thresh, prop, nrmA, pi, need_score);
+    if (d.need_exact) {
+      s_list[atomicAdd(&s_n, 1)] = k1;
+    } else {
+      if (d.ambiguous) row_list[atomicAdd(row_list_n, 1)] = p * K1 + k1;
+      rows[(size_t)p * K1 + k1] = d.out;
+    }
+  }
+  __syncthreads();
+  // ---- phase B ------------------------------------------------------------------------------------
+  const int n = s_n;
+  if (warp >= RS2_BW) return;
+  ACC(*mine)[ND + 1] = sprod + warp * RS2_ROWS;
+  for (int base = warp * RS2_ROWS; base < n; base += RS2_BW * RS2_ROWS) {
+    const int nr = min(RS2_ROWS, n - base);
+    const int r1 = lane < nr ? s_list[base + lane] : -1;
+    RsDecision d;
+    d.my.idx = 0;
+    if (r1 >= 0) d = rescore_decide(p, pa, r1, n2, K1p, thresh, prop, nrmA, pi, need_score);
+    for (int r = 0; r < nr; r += 4) {  // up to four rows' loads in flight together
+      ACC va[4][4], vb[4][4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (r + u < nr) {
+          const int rr = __shfl_sync(0xffffffffu, r1, r + u), ii = __shfl_sync(0xffffffffu, d.my.idx, r + u);
+          load_row4<T, ACC>(L1 + ((size_t)pa * K1 + rr) * ND + 4 * lane, va[u]);
+          load_row4<T, ACC>(L2 + ((size_t)p * K2 + ii) * ND + 4 * lane, vb[u]);
+        }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (r + u < nr) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const ACC dd = va[u][e] - vb[u][e];
+            mine[r + u][4 * lane + e] = dd * dd;
+          }
+        }
+    }
+    __syncwarp();
+    if (r1 >= 0) {
+      ACC acc = 0;
+      for (int bin = 0; bin < ND; ++bin) acc += mine[lane][bin];  // strictly in order (siftmatch.c:101-107)
+      const double d1 = (double)acc;
+      const double s2 = d.na - 2.0 * (double)d.my.second;
+      const double L2b = s2 - d.m, U2b = s2 + d.m;
+      MatchRow out = d.out;
+      bool ambiguous = false;
+      if (d1 < L2b) {
+        const float lhs = __fmul_rn(thresh, (float)acc);
+        out.best = d1;
+        out.bestk = d.my.idx;
+        if (lhs <= (float)L2b)
+          out.accept = 1;
+        else if (lhs > (float)U2b)
+          out.accept = 0;
+        else
+          ambiguous = true;
+      } else {
+        const double hi = d1 > U2b ? d1 : U2b;
+        if (L2b > 0.0 && __fmul_rn(thresh, (float)L2b) > (float)hi)
+          out.accept = 0;
+        else
+          ambiguous = true;
+      }
+      if (ambiguous) row_list[atomicAdd(row_list_n, 1)] = p * K1 + r1;
+      rows[(size_t)p * K1 + r1] = out;
+    }
+    __syncwarp();
+  }
+}
+
+template <typename ACC>
+constexpr size_t rs2_smem_bytes() {
+  return sizeof(ACC) * (size_t)RS2_BW * RS2_ROWS * (ND + 1);
+}
+
 }  // namespace tc
 
 // ---------------------------------------------------------------------------------------------
@@ -1101,7 +1257,31 @@ int launch_match_tc(pre3_ctx* ctx, const void* dL1, const void* dL2, int cls, in
     count_launch(ctx);
   }
   const int v2 = use_v1 ? 0 : 1;
-  {
+  static const int rescore_v1 = getenv("PRE3_RESCORE_V1") ? atoi(getenv("PRE3_RESCORE_V1")) : 0;
+  if (v2 && !rescore_v1) {
+    Span span__(ctx, T_RESCORE);
+    const dim3 g((K1 + RS2_THREADS - 1) / RS2_THREADS, P);
+#define PRE3_RS2(T, ACC)                                                                                              \
+  do {                                                                                                                \
+    static bool attr_done = false;                                                                                    \
+    if (!attr_done) {                                                                                                 \
+      PRE3_CUDA(cudaFuncSetAttribute(k_tc_rescore2<T, ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize,              \
+                                     (int)rs2_smem_bytes<ACC>()));                                                    \
+      attr_done = true;                                                                                               \
+    }                                                                                                                 \
+    k_tc_rescore2<T, ACC><<<g, RS2_THREADS, rs2_smem_bytes<ACC>(), ctx->stream>>>(                                    \
+        (const T*)dL1, (const T*)dL2, K1, K2, K1p, K2p, dk1, dk2, thresh, prop, nrmA, info, need_score, shared, drows, \
+        list, list_n);                                                                                                \
+  } while (0)
+    if (cls == PRE3_CLASS_DOUBLE)
+      PRE3_RS2(double, double);
+    else if (cls == PRE3_CLASS_DOUBLE_F32)
+      PRE3_RS2(float, double);
+    else
+      PRE3_RS2(float, float);
+#undef PRE3_RS2
+    count_launch(ctx);
+  } else {
     Span span__(ctx, T_RESCORE);
     const dim3 g((K1 + RS_ROWS * RS_GROUPS - 1) / (RS_ROWS * RS_GROUPS), P);
     if (cls == PRE3_CLASS_DOUBLE)

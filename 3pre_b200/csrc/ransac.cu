@@ -925,6 +925,23 @@ k_sel_scan(const PairMeta* __restrict__ meta, int Nmax, int H, int k, int method
   }
 }
 
+// the fit of sample set s of pair p if k_eval_pairloop kept it (fc == nullptr: no cache in this call)
+__device__ __forceinline__ bool fit_cached(const FitCacheEntry* __restrict__ fc, const int32_t* __restrict__ fcn, int p,
+                                           int s, Rigid& f) {
+  if (!fc) return false;
+  const int n = min(fcn[p], FIT_CACHE_CAP);
+  const FitCacheEntry* e = fc + (size_t)p * FIT_CACHE_CAP;
+  for (int j = 0; j < n; ++j)
+    if (e[j].h == s) {
+#pragma unroll
+      for (int i = 0; i < 9; ++i) f.R[i] = e[j].Rt[i];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) f.t[i] = e[j].Rt[9 + i];
+      return true;
+    }
+  return false;
+}
+
 constexpr int TIE_THREADS = 128;
 
 // sum of v over the 32 lanes strictly in lane order, continued from acc (every lane returns it)
@@ -978,7 +995,8 @@ __global__ void __launch_bounds__(TIE_THREADS, 4)
 k_sel_tie_quad(const PairMeta* __restrict__ meta, const double* __restrict__ Ya, const double* __restrict__ Yb,
                int Nmax, const int32_t* __restrict__ samples, uint64_t seed, uint32_t pair_id0, long long h0, int H,
                int k, int method, const int2* __restrict__ ties, const int* __restrict__ tie_total, int cap,
-               double* __restrict__ es_out) {
+               double* __restrict__ es_out, const FitCacheEntry* __restrict__ fcache,
+               const int32_t* __restrict__ fcache_n) {
   const int total = min(*tie_total, cap);
   const int sub = threadIdx.x & (G - 1);
   const int quads = (gridDim.x * TIE_THREADS) / G;
@@ -993,10 +1011,12 @@ k_sel_tie_quad(const PairMeta* __restrict__ meta, const double* __restrict__ Ya,
     const int N = live ? m.N : 0;
     const double* ya = Ya + (size_t)p * Nmax * 3;
     const double* yb = Yb + (size_t)p * Nmax * 3;
-    int idx[MAX_K];
-    load_sample(samples, seed, pair_id0 + (uint32_t)p, h0, s, H, p, max(m.N, 1), k, idx);
     Rigid f;
-    fit_sample(method, ya, yb, idx, k, f);
+    if (!fit_cached(fcache, fcache_n, p, s, f)) {
+      int idx[MAX_K];
+      load_sample(samples, seed, pair_id0 + (uint32_t)p, h0, s, H, p, max(m.N, 1), k, idx);
+      fit_sample(method, ya, yb, idx, k, f);
+    }
     const int Nw = __reduce_max_sync(0xffffffffu, N);
     double es = 0.0;
     for (int ib = 0; ib < Nw; ib += 2 * G) {
@@ -1029,7 +1049,8 @@ k_sel_final(const PairMeta* __restrict__ meta, const double* __restrict__ Ya, co
             int method, const int32_t* __restrict__ counts, const int8_t* __restrict__ states,
             const SelInfo* __restrict__ info, const int32_t* __restrict__ pair_ties, const double* __restrict__ es_in,
             pre3_pair_result* __restrict__ res, uint8_t* __restrict__ masks, int mask_stride,
-            uint8_t* __restrict__ mask_scratch) {
+            uint8_t* __restrict__ mask_scratch, const FitCacheEntry* __restrict__ fcache,
+            const int32_t* __restrict__ fcache_n) {
   __shared__ double s_es[32];
   __shared__ int s_i[32];
   const int p = blockIdx.x;
@@ -1149,10 +1170,12 @@ k_sel_final(const PairMeta* __restrict__ meta, const double* __restrict__ Ya, co
   }
 
   // ---- winner: hypothesis, mask, ErrorSum; refit on the support set (:186) --------------------------
-  int idx[MAX_K];
-  load_sample(samples, seed, pair_id0 + (uint32_t)p, h0, win, H, p, N, k, idx);
   Rigid f;
-  fit_sample(method, ya, yb, idx, k, f);  // every thread computes the same fit
+  if (!fit_cached(fcache, fcache_n, p, win, f)) {
+    int idx[MAX_K];
+    load_sample(samples, seed, pair_id0 + (uint32_t)p, h0, win, H, p, N, k, idx);
+    fit_sample(method, ya, yb, idx, k, f);  // every thread computes the same fit
+  }
   for (int i = tid; i < N; i += NT) mask[i] = residual_norm(f.R, f.t, ya + 3 * i, yb + 3 * i) < m.thr ? 1 : 0;
   if (masks)
     for (int i = N + tid; i < mask_stride; i += NT) mask[i] = 0;
@@ -1368,7 +1391,8 @@ k_eval_pairloop(const PairMeta* __restrict__ meta, const double* __restrict__ Ya
                 const int32_t* __restrict__ samples, uint64_t seed, uint32_t pair_id0, int H, int method,
                 int max_iteration, const int32_t* __restrict__ tab, int32_t* __restrict__ counts,
                 int8_t* __restrict__ states, int32_t* __restrict__ evaluated, pre3_pair_result* __restrict__ res,
-                uint8_t* __restrict__ masks, int mask_stride, uint8_t* __restrict__ mask_scratch) {
+                uint8_t* __restrict__ masks, int mask_stride, uint8_t* __restrict__ mask_scratch,
+                FitCacheEntry* __restrict__ fcache, int32_t* __restrict__ fcache_n) {
   __shared__ __align__(16) float sM[6][EVP_TILE];
   static_assert(!SELECT || NT == EVP_THREADS, "fused selection is built for 64 threads");
   constexpr int LIST = EVP_LIST * (NT / EVP_THREADS);
@@ -1376,7 +1400,7 @@ k_eval_pairloop(const PairMeta* __restrict__ meta, const double* __restrict__ Ya
   __shared__ int sCnt[NT];
   __shared__ int sState[NT];
   __shared__ uint32_t sList[LIST];
-  __shared__ int sListN, sStop, sSel[3];
+  __shared__ int sListN, sStop, sSel[3], sMaxNow, sCacheN;
 
   const int p = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31;
@@ -1387,6 +1411,7 @@ k_eval_pairloop(const PairMeta* __restrict__ meta, const double* __restrict__ Ya
   const int32_t* trow = tab + m.pad;
   if (N < K || N <= 0) {  // get_rand(k, N) errors in the reference (get_rand.m:39-41): nothing to evaluate
     if (tid == 0 && evaluated) evaluated[p] = 0;
+    if (tid == 0 && fcache_n) fcache_n[p] = 0;
     if (SELECT) {
       if (tid == 0) result_init(res + p, 1, 0, N, m.thr);
       if (masks)
@@ -1398,6 +1423,7 @@ k_eval_pairloop(const PairMeta* __restrict__ meta, const double* __restrict__ Ya
   if (one_tile) eval_stage<NT, EVP_TILE>(sM, Ya4 + (size_t)p * Nmax, Yb4 + (size_t)p * Nmax, N, (N + 3) & ~3);
   int car_c = 0, car_m = 0;  // recorded hypotheses / max cardinality over the chunks before
   int hdone = 0;
+  if (tid == 0) sCacheN = 0;
   for (int hbeg = 0; hbeg < H; hbeg += NT) {
     const int h = hbeg + tid;
     if (tid == 0) sListN = 0;
@@ -1491,13 +1517,31 @@ k_eval_pairloop(const PairMeta* __restrict__ meta, const double* __restrict__ Ya
         sSel[1] = car_c;
         sSel[2] = car_m;
       }
-      if (lane == 0) sStop = first;
+      if (lane == 0) {
+        sStop = first;
+        sMaxNow = car_m;
+      }
     }
     __syncthreads();
+    // a hypothesis that holds the running maximum may tie at the final one: keep its fit for the selection
+    if (fcache && sState[tid] && sMaxNow > 0 && sCnt[tid] == sMaxNow) {
+      const int slot = atomicAdd(&sCacheN, 1);
+      if (slot < FIT_CACHE_CAP) {
+        FitCacheEntry* e = fcache + (size_t)p * FIT_CACHE_CAP + slot;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) e->Rt[i] = sRt[tid * 12 + i];
+        e->h = hbeg + tid;
+        e->c = sMaxNow;
+      }
+    }
     hdone = min(H, hbeg + NT);
     if (sStop != 0x7fffffff) break;
   }
   if (tid == 0 && evaluated) evaluated[p] = hdone;
+  if (fcache_n) {
+    __syncthreads();
+    if (tid == 0) fcache_n[p] = min(sCacheN, FIT_CACHE_CAP);
+  }
   if constexpr (SELECT)
     pairloop_select(m, ya, yb, samples, seed, pair_id0, H, K, method, p, counts + (size_t)p * H, states + (size_t)p * H,
                     sSel[0], sSel[1], sSel[2], res + p,
@@ -2179,6 +2223,7 @@ size_t ransac_workspace_bytes(int P, int Nmax, int H) {
   b += align_up((size_t)P * Nmax);  // mask scratch
   b += align_up(sizeof(SelInfo) * (size_t)P) + 3 * align_up(8 * (size_t)P * (H > 0 ? H : 1)) + 512;  // selection
   b += align_up(sizeof(int32_t) * (size_t)P);  // stop flags
+  b += align_up(sizeof(FitCacheEntry) * (size_t)P * FIT_CACHE_CAP) + align_up(sizeof(int32_t) * (size_t)P);
   return b + 4096;
 }
 
@@ -2189,6 +2234,8 @@ void ransac_carve(pre3_ctx* ctx, RansacBuffers& b, int H) {
   b.counts = ws_take<int32_t>(ctx, (size_t)b.P * H);
   b.states = ws_take<int8_t>(ctx, (size_t)b.P * H);
   b.stop = ws_take<int32_t>(ctx, b.P);
+  b.fcache = ws_take<FitCacheEntry>(ctx, (size_t)b.P * FIT_CACHE_CAP);
+  b.fcache_n = ws_take<int32_t>(ctx, b.P);
 }
 
 // nIterations(card, N) = mult*ceil(log(epsilon)/log(1-(card/N)^k))  (RANSAC_CALC_VER2.m:139, RANSAC_CALC_VER_test.m:102),
@@ -2423,7 +2470,8 @@ static int launch_eval_pairloop_mode(pre3_ctx* ctx, const RansacBuffers& b, cons
 #define PRE3_EVALP(KK)                                                                                             \
   k_eval_pairloop<KK, MODE, SELECT><<<b.P, EVP_THREADS, 0, ctx->stream>>>(                                          \
       b.meta, b.Ya, b.Yb, b.Ya4, b.Yb4, b.Nmax, b.samples, o.seed, b.pair_id0, o.H, o.method, o.max_iteration,     \
-      b.tab.tab, b.counts, b.states, b.stop, dres, dmasks, b.Nmax, scratch)
+      b.tab.tab, b.counts, b.states, b.stop, dres, dmasks, b.Nmax, scratch, SELECT ? nullptr : b.fcache,       \
+      SELECT ? nullptr : b.fcache_n)
   // PRE3_EVP_MINB: blocks per SM the k = 5 / find_transform_matrix instance is compiled for (occupancy vs spills)
   // (measured at the sequence shape, eval ms per 4096 pairs: 8 -> 0.338, 10 -> 0.351, 12 -> 0.382, 16 -> 0.393: the
   // spills of the fp64 fit cost more than the extra warps bring)
@@ -2434,7 +2482,8 @@ static int launch_eval_pairloop_mode(pre3_ctx* ctx, const RansacBuffers& b, cons
 #define PRE3_EVALPW(MB, NTT)                                                                                       \
   k_eval_pairloop<5, 0, false, MB, NTT><<<b.P, NTT, 0, ctx->stream>>>(                                              \
       b.meta, b.Ya, b.Yb, b.Ya4, b.Yb4, b.Nmax, b.samples, o.seed, b.pair_id0, o.H, o.method, o.max_iteration,     \
-      b.tab.tab, b.counts, b.states, b.stop, dres, dmasks, b.Nmax, scratch)
+      b.tab.tab, b.counts, b.states, b.stop, dres, dmasks, b.Nmax, scratch, SELECT ? nullptr : b.fcache,       \
+      SELECT ? nullptr : b.fcache_n)
       if (nt == 128) PRE3_EVALPW(4, 128);
       else PRE3_EVALPW(2, 256);
 #undef PRE3_EVALPW
@@ -2447,7 +2496,8 @@ static int launch_eval_pairloop_mode(pre3_ctx* ctx, const RansacBuffers& b, cons
 #define PRE3_EVALPB(MB)                                                                                            \
   k_eval_pairloop<5, 0, false, MB><<<b.P, EVP_THREADS, 0, ctx->stream>>>(                                          \
       b.meta, b.Ya, b.Yb, b.Ya4, b.Yb4, b.Nmax, b.samples, o.seed, b.pair_id0, o.H, o.method, o.max_iteration,     \
-      b.tab.tab, b.counts, b.states, b.stop, dres, dmasks, b.Nmax, scratch)
+      b.tab.tab, b.counts, b.states, b.stop, dres, dmasks, b.Nmax, scratch, SELECT ? nullptr : b.fcache,       \
+      SELECT ? nullptr : b.fcache_n)
     if (minb == 6) PRE3_EVALPB(6);
     else if (minb == 10) PRE3_EVALPB(10);
     else if (minb == 12) PRE3_EVALPB(12);
@@ -2531,6 +2581,11 @@ int launch_select(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts&
   PRE3_CUDA(cudaMemsetAsync(tie_total, 0, sizeof(int), ctx->stream));
   const int32_t* tab = o.adaptive ? b.tab.tab : nullptr;
   const bool many = b.P >= 64;  // batches of pairs: one warp per pair; few (large) pairs: 1024 threads each
+  // fits kept by k_eval_pairloop (same condition as launch_eval_waves; PRE3_FIT_CACHE=0 refits everything)
+  static const int use_cache = getenv("PRE3_FIT_CACHE") ? atoi(getenv("PRE3_FIT_CACHE")) : 1;
+  const bool cached = use_cache && use_pairloop(b, o) && b.h0 == 0 && b.fcache != nullptr;
+  const FitCacheEntry* fc = cached ? b.fcache : nullptr;
+  const int32_t* fcn = cached ? b.fcache_n : nullptr;
   if (many)
     k_sel_scan<32><<<b.P, 32, 0, ctx->stream>>>(b.meta, b.Nmax, o.H, o.k, o.method, o.max_iteration, o.adaptive, tab,
                                                 b.counts, b.states, dres, dmasks, b.Nmax, dcounts_out, dstates_out,
@@ -2549,7 +2604,7 @@ int launch_select(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts&
   if (many && fuse_ties == 2 && (size_t)b.Nmax * 48 <= 48 * 1024) {
     k_sel_final<64, true><<<b.P, 64, (size_t)b.Nmax * 48, ctx->stream>>>(
         b.meta, b.Ya, b.Yb, b.P, b.Nmax, b.samples, o.seed, b.pair_id0, b.h0, o.H, o.k, o.method, b.counts, b.states, info,
-        pair_ties, es, dres, dmasks, b.Nmax, scratch);
+        pair_ties, es, dres, dmasks, b.Nmax, scratch, nullptr, nullptr);
     count_launch(ctx, 2);
     PRE3_CUDA(cudaGetLastError());
     return PRE3_OK;
@@ -2557,7 +2612,7 @@ int launch_select(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts&
   if (many && fuse_ties == 1 && b.Nmax <= 2048) {  // one warp per pair, eight ties at a time, points through L1
     k_sel_final<32, true><<<b.P, 32, 0, ctx->stream>>>(
         b.meta, b.Ya, b.Yb, b.P, b.Nmax, b.samples, o.seed, b.pair_id0, b.h0, o.H, o.k, o.method, b.counts, b.states, info,
-        pair_ties, es, dres, dmasks, b.Nmax, scratch);
+        pair_ties, es, dres, dmasks, b.Nmax, scratch, nullptr, nullptr);
     count_launch(ctx, 2);
     PRE3_CUDA(cudaGetLastError());
     return PRE3_OK;
@@ -2572,7 +2627,7 @@ int launch_select(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts&
     const int tb = (int)std::min<size_t>(((size_t)G * PH + TIE_THREADS - 1) / TIE_THREADS, (size_t)ctx->sm_count * 16);
 #define PRE3_TIE(GG)                                                                                                  \
   k_sel_tie_quad<GG><<<tb, TIE_THREADS, 0, ctx->stream>>>(b.meta, b.Ya, b.Yb, b.Nmax, b.samples, o.seed, b.pair_id0,  \
-                                                          b.h0, o.H, o.k, o.method, ties, tie_total, (int)PH, es)
+                                                          b.h0, o.H, o.k, o.method, ties, tie_total, (int)PH, es, fc, fcn)
     if (G == 4) PRE3_TIE(4);
     else if (G == 8) PRE3_TIE(8);
     else if (G == 16) PRE3_TIE(16);
@@ -2585,11 +2640,11 @@ int launch_select(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts&
   if (many)
     k_sel_final<32, false><<<b.P, 32, 0, ctx->stream>>>(b.meta, b.Ya, b.Yb, b.P, b.Nmax, b.samples, o.seed, b.pair_id0, b.h0,
                                                  o.H, o.k, o.method, b.counts, b.states, info, pair_ties, es, dres,
-                                                 dmasks, b.Nmax, scratch);
+                                                 dmasks, b.Nmax, scratch, fc, fcn);
   else
     k_sel_final<512, false><<<b.P, 512, 0, ctx->stream>>>(b.meta, b.Ya, b.Yb, b.P, b.Nmax, b.samples, o.seed, b.pair_id0,
                                                      b.h0, o.H, o.k, o.method, b.counts, b.states, info, pair_ties, es,
-                                                     dres, dmasks, b.Nmax, scratch);
+                                                     dres, dmasks, b.Nmax, scratch, fc, fcn);
   count_launch(ctx, 3);
   PRE3_CUDA(cudaGetLastError());
   return PRE3_OK;

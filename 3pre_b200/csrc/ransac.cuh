@@ -21,6 +21,15 @@ struct AdaptiveTable {
   int triangular = 0;               // row N at N(N+1)/2
 };
 
+// (R, t) of the hypotheses that held the running maximum cardinality when k_eval_pairloop evaluated them: the only ones
+// that can tie at the final maximum.  The selection reads them instead of fitting the sample again.
+constexpr int FIT_CACHE_CAP = 24;
+struct FitCacheEntry {
+  double Rt[12];  // R row-major, t
+  int32_t h;      // sample set
+  int32_t c;      // its cardinality
+};
+
 struct RansacBuffers {
   const double* Ya;      // P x Nmax x 3
   const double* Yb;
@@ -36,6 +45,8 @@ struct RansacBuffers {
   uint32_t pair_id0;
   long long h0 = 0;      // global id of local sample set 0 (hypothesis-block sharding); selection kernels only
   AdaptiveTable tab;     // set by ensure_adaptive_table when the adaptive stop is on
+  FitCacheEntry* fcache = nullptr;  // P x FIT_CACHE_CAP
+  int32_t* fcache_n = nullptr;      // P: valid entries (written by k_eval_pairloop only)
 };
 
 size_t ransac_workspace_bytes(int P, int Nmax, int H);
