@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-2 GPU job 1: eval microbench, CTA-pair matcher bring-up (both K-extension layouts), baseline-shape tests
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv
 (timeout 120 tools/evalbench.bin 20000 454656; timeout 120 tools/evalbench.bin 300 4546560) > gpurun_out/evalbench_a.log 2>&1

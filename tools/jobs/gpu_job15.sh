@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 echo "=== i8 tests"
 timeout 600 python -m pytest tests/test_gpu_match_i8.py tests/test_gpu_callers.py -x -q 2>&1 | tail -25 | tee gpurun_out/i8_tests.log

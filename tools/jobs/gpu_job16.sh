@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_gpu_cov.py -x -q 2>&1 | tail -25 | tee gpurun_out/cov_tests.log
 timeout 300 python - <<'PY' 2>&1 | tee gpurun_out/cov_bench.log

@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 echo "=== new tests"
 timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -k "sample_index or ransac" 2>&1 | tail -5

@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 echo "=== bench (plain, same command as the profiled one)"
 timeout 600 python bench.py --steps 2 --warmup 3 --no-other > gpurun_out/bench_r02_k.json 2> gpurun_out/bench_r02_k.err || { tail -5 gpurun_out/bench_r02_k.err; exit 1; }

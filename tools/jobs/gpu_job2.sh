@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-2 GPU job 2: full GPU suite on the new kernels, matcher epilogue A/B, bench
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader
 echo "=== match_bench: product (EPI=1), EPI=0, epilogue-only EPI=1 / EPI=0, MMA-only"

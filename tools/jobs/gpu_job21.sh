@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 for m in 0 1 2; do
   echo "=== PRE3_SEL_FUSED=$m"

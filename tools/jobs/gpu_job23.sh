@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 echo "=== baseline knobs (NT=64, G=4)"
 PRE3_EVP_NT=64 PRE3_TIE_G=4 timeout 300 python tools/shard_bench.py 2>&1 | tee gpurun_out/shard_base.log

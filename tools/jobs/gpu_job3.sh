@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-2 GPU job 3: instruction-throughput microbench, full GPU suite, bench with graphs
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 120 tools/pipebench.bin | tee gpurun_out/pipebench.log
 echo "=== full GPU suite"

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-2 GPU job 4: matcher ablation 3, full GPU suite, bench with graphs, ncu of the two hot kernels
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 PRE3_TC_EXP=3 timeout 200 python tools/match_bench.py 2>&1 | tail -2 | tee gpurun_out/mb4_exp3.log
 echo "=== full GPU suite"

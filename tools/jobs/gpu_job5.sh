@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-2 GPU job 5: 512-row CTA-pair matcher: parity, ablations, bench
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 300 python -m pytest tests/test_gpu_parity.py tests/test_gpu_baseline_shapes.py -m gpu -q -x -k "siftmatch or cfg2 or box or sequence or graph" 2>&1 | tail -8 | tee gpurun_out/pair3_parity.log
 for e in 0 1 2 3; do

@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 echo "=== full GPU suite"
 timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -15 | tee gpurun_out/gpu_suite_g.log

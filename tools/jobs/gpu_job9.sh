@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests -m gpu -q -x -k "pairs or sequence or ransac or smoke or cfg3" 2>&1 | tail -4
 echo "=== bench (fused select)"
