@@ -95,6 +95,7 @@ SYMBOLS = {
     "pre3_sync": (_I, [_VP]),
     "pre3_launch_count": (_I64, [_VP]),
     "pre3_set_graphs": (_I, [_VP, _I]),
+    "pre3_set_pipeline": (_I, [_VP, _I]),
     "pre3_transfer_bytes": (_I, [_VP, _VP, _VP]),
     "pre3_eval_schedule": (_I, [_OPTS, _VP, _I]),
     "pre3_eval_schedule_for": (_I, [_OPTS, _I, _VP, _I]),

@@ -173,6 +173,10 @@ class Context:
         """CUDA-graph replay of pairs_dev / sequence_dev calls that repeat a signature (pre3_set_graphs)."""
         self._ck(self._lib.pre3_set_graphs(self._h, int(bool(on))))
 
+    def set_pipeline(self, chunks: int = -1):
+        """Chunked stage pipeline of pairs_dev / sequence_dev (pre3_set_pipeline): -1 automatic, 0 off, n chunks."""
+        self._ck(self._lib.pre3_set_pipeline(self._h, int(chunks)))
+
     def sync(self):
         self._ck(self._lib.pre3_sync(self._h))
 

@@ -116,9 +116,11 @@ int ransac_impl(pre3_ctx* ctx, const double* dYa, const double* dYb, const int32
   ransac_carve(ctx, b, o.H);
   if (o.method == PRE3_METHOD_DR_YE) {
     if (dstates) return fail(ctx, PRE3_ERR_ARG, "per-hypothesis states are not reported by the dr_ye variant");
+    PRE3_TRY(pipe_enter(ctx, PS_EVAL));
     return launch_dr_ye(ctx, b, o, dmatch, dres, dmasks, dstat, dcounts);
   }
   PRE3_TRY(ensure_adaptive_table(ctx, o, Nmax, dn_corr, P, &b.tab));
+  PRE3_TRY(pipe_enter(ctx, PS_EVAL));
   PRE3_TRY(launch_prep(ctx, b, o, 0));
   // Selection inside the evaluation kernel (one launch for stages 2-4) is built and parity-green, but measured slower
   // at the sequence shape (eval + select 0.57 ms separate, 0.73 ms fused per 4096 pairs: 64 threads per pair leave the
@@ -126,6 +128,7 @@ int ransac_impl(pre3_ctx* ctx, const double* dYa, const double* dYb, const int32
   static const int fuse = getenv("PRE3_FUSED_SELECT") ? atoi(getenv("PRE3_FUSED_SELECT")) : 0;
   if (!dcounts && !dstates && fuse && ransac_can_fuse_select(b, o)) return launch_eval_select_fused(ctx, b, o, dres, dmasks);
   PRE3_TRY(launch_eval_waves(ctx, b, o));
+  PRE3_TRY(pipe_enter(ctx, PS_SELECT));
   PRE3_TRY(launch_select(ctx, b, o, dres, dmasks, dcounts, dstates));
   return PRE3_OK;
 }
@@ -192,6 +195,75 @@ int graph_or_eager(pre3_ctx* ctx, const std::vector<unsigned char>& key, Body bo
   PRE3_CUDA(cudaGraphLaunch(ctx->graph_exec, ctx->stream));
   return PRE3_OK;
 }
+}  // namespace
+
+namespace {
+// ---- software pipeline over chunks of pairs (pre3_set_pipeline) ---------------------------------------------------
+// The stages of the path are bound by different units: convert by HBM, the descriptor GEMM by the tensor cores and the
+// shared-memory operand stream, the hypothesis evaluation by FP32 issue slots, the selection by dependent fp64 chains.
+// Run back to back each leaves the other units idle.  The pairs of a call are cut into chunks, every stage gets its own
+// stream, and chunk c + 1 enters a stage as soon as chunk c has left it: kernels of different stages then share the SMs
+// (a persistent GEMM CTA with 352 threads leaves room for convert / evaluation / selection blocks beside it).  Each
+// chunk carves its own part of the arena, so the chunks have no buffers in common; results are those of the unchunked
+// call (every pair is independent: tests/test_gpu_parity.py::test_pipeline_*).  In sequence mode the frame on a chunk
+// boundary is converted by both chunks.
+static int ensure_pipe_streams(pre3_ctx* ctx) {
+  if (ctx->pipe_fork) return PRE3_OK;
+  int lo = 0, hi = 0;  // numerically lower = higher priority
+  PRE3_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  // later stages drain first: a chunk that has reached the selection should not wait behind the conversion of the next
+  const int use_prio = getenv("PRE3_PIPE_PRIO") ? atoi(getenv("PRE3_PIPE_PRIO")) : 1;
+  for (int i = 0; i < 4; ++i) {
+    const int pr = use_prio ? std::max(hi, lo - i) : lo;
+    PRE3_CUDA(cudaStreamCreateWithPriority(&ctx->pipe_stream[i], cudaStreamNonBlocking, pr));
+    PRE3_CUDA(cudaEventCreateWithFlags(&ctx->pipe_ev[i], cudaEventDisableTiming));
+  }
+  PRE3_CUDA(cudaEventCreateWithFlags(&ctx->pipe_fork, cudaEventDisableTiming));
+  if (const char* m = getenv("PRE3_PIPE_MAP")) {  // e.g. "0122": evaluation and selection on one stream
+    for (int i = 0; i < 4 && m[i] >= '0' && m[i] <= '3'; ++i) ctx->pipe_map[i] = m[i] - '0';
+  }
+  return PRE3_OK;
+}
+
+// chunks a call of P pairs is cut into (1: no pipeline)
+static int pipe_chunk_count(const pre3_ctx* ctx, int P, int K1, int K2) {
+  if (ctx->timing || ctx->pipe_chunks == 0 || ctx->pipe_chunks == 1) return 1;
+  if (K1 > 2048 || K2 > 2048) return 1;  // large pairs: the per-call adaptive rows are built with a host round trip
+  static const int env = getenv("PRE3_PIPE_CHUNKS") ? atoi(getenv("PRE3_PIPE_CHUNKS")) : -1;
+  int n = env >= 0 ? env : ctx->pipe_chunks;
+  if (n < 0) n = P >= 1024 ? std::min(P / 512, 8) : 1;  // automatic: chunks of >= 512 pairs (measured)
+  const int min_pairs = 128;  // a chunk must keep the batch forms of the kernels (>= 64 pairs) and fill the GEMM grid
+  n = std::min(n, P / min_pairs);
+  return std::max(n, 1);
+}
+
+// Body(p0, n): issue the launches of pairs [p0, p0 + n) on ctx->stream (stage switches through pipe_enter).
+template <typename Body>
+static int run_pipelined(pre3_ctx* ctx, int P, int nchunks, Body body) {
+  if (nchunks <= 1) return body(0, P);
+  PRE3_TRY(ensure_pipe_streams(ctx));
+  cudaStream_t main_stream = ctx->stream;
+  PRE3_CUDA(cudaEventRecord(ctx->pipe_fork, main_stream));
+  for (int i = 0; i < 4; ++i) PRE3_CUDA(cudaStreamWaitEvent(ctx->pipe_stream[i], ctx->pipe_fork, 0));
+  ctx->pipe_total_P = P;
+  int rc = PRE3_OK;
+  for (int c = 0; c < nchunks && rc == PRE3_OK; ++c) {
+    const int p0 = (int)((long long)P * c / nchunks), p1 = (int)((long long)P * (c + 1) / nchunks);
+    ctx->stream = ctx->pipe_stream[ctx->pipe_map[0]];  // a new chunk starts at the first stage, behind nothing but
+    ctx->pipe_stage = 0;                               // the previous chunk's launches on that stream
+    rc = body(p0, p1 - p0);
+  }
+  ctx->pipe_stage = -1;
+  ctx->pipe_total_P = 0;
+  ctx->stream = main_stream;
+  // join (also on failure: a capture must not be left with unjoined streams)
+  for (int i = 0; i < 4; ++i) {
+    cudaEventRecord(ctx->pipe_ev[i], ctx->pipe_stream[i]);
+    cudaStreamWaitEvent(main_stream, ctx->pipe_ev[i], 0);
+  }
+  return rc;
+}
+
 }  // namespace
 
 // ================================================================================================
@@ -261,6 +333,11 @@ void pre3_destroy(pre3_ctx* ctx) {
     for (void* p : ctx->aux) cudaFree(p);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    for (int i = 0; i < 4; ++i) {
+      if (ctx->pipe_stream[i]) cudaStreamDestroy(ctx->pipe_stream[i]);
+      if (ctx->pipe_ev[i]) cudaEventDestroy(ctx->pipe_ev[i]);
+    }
+    if (ctx->pipe_fork) cudaEventDestroy(ctx->pipe_fork);
     for (int i = 0; i < 2; ++i) {
       if (ctx->ev_slot_full[i]) cudaEventDestroy(ctx->ev_slot_full[i]);
       if (ctx->ev_slot_free[i]) cudaEventDestroy(ctx->ev_slot_free[i]);
@@ -805,6 +882,20 @@ int pre3_set_graphs(pre3_ctx* ctx, int on) {
   return PRE3_OK;
 }
 
+int pre3_set_pipeline(pre3_ctx* ctx, int chunks) {
+  if (!ctx || ctx->device < 0) return PRE3_ERR_CUDA;
+  if (chunks < -1 || chunks > 64) return fail(ctx, PRE3_ERR_ARG, "pipeline chunks: -1 (automatic), 0 / 1 (off) or 2..64");
+  if (chunks != ctx->pipe_chunks && ctx->graph_exec) {  // a captured graph has the old chunking baked in
+    cudaStreamSynchronize(ctx->stream);
+    cudaGraphExecDestroy(ctx->graph_exec);
+    ctx->graph_exec = nullptr;
+    ctx->graph_key.clear();
+    ctx->graph_seen.clear();
+  }
+  ctx->pipe_chunks = chunks;
+  return PRE3_OK;
+}
+
 int pre3_pairs_dev(pre3_ctx* ctx, const void* ddesc1, const void* ddesc2, int cls, const double* dxyz1,
                    const double* dxyz2, int P, int K1, int K2, int ND, const int32_t* dk1_count,
                    const int32_t* dk2_count, const pre3_ransac_opts* opts, uint32_t pair_id0, pre3_pair_result* dres,
@@ -822,10 +913,19 @@ int pre3_pairs_dev(pre3_ctx* ctx, const void* ddesc1, const void* ddesc2, int cl
     key_put(key, *opts); key_put(key, pair_id0); key_put(key, dres); key_put(key, dmatches); key_put(key, dmasks);
     key_put(key, ctx->stream); key_put(key, ctx->match_engine);
   }
+  const int nch = pipe_chunk_count(ctx, P, K1, K2);
+  if (ctx->graphs) key_put(key, nch);
   return graph_or_eager(ctx, key, [&]() -> int {
-    PRE3_TRY(ws_reserve(ctx, pairs_ws_bytes(cls, P, K1, K2, ND, opts->H)));
-    return pairs_impl(ctx, ddesc1, ddesc2, cls, dxyz1, dxyz2, P, K1, K2, ND, dk1_count, dk2_count, *opts, pair_id0, dres,
-                      dmatches, dmasks);
+    const int cmax = (P + nch - 1) / nch;
+    PRE3_TRY(ws_reserve(ctx, (size_t)nch * pairs_ws_bytes(cls, cmax, K1, K2, ND, opts->H)));
+    const size_t es = class_size(cls);
+    return run_pipelined(ctx, P, nch, [&](int p0, int n) -> int {
+      return pairs_impl(ctx, (const char*)ddesc1 + (size_t)p0 * K1 * ND * es, (const char*)ddesc2 + (size_t)p0 * K2 * ND * es,
+                        cls, dxyz1 + 3 * (size_t)p0 * K1, dxyz2 + 3 * (size_t)p0 * K2, n, K1, K2, ND,
+                        dk1_count ? dk1_count + p0 : nullptr, dk2_count ? dk2_count + p0 : nullptr, *opts,
+                        pair_id0 + (uint32_t)p0, dres + p0, dmatches ? dmatches + 2 * (size_t)p0 * K1 : nullptr,
+                        dmasks ? dmasks + (size_t)p0 * K1 : nullptr);
+    });
   });
 }
 
@@ -847,10 +947,18 @@ int pre3_sequence_dev(pre3_ctx* ctx, const void* ddesc, int cls, const double* d
     key_put(key, dk_count); key_put(key, *opts); key_put(key, pair_id0); key_put(key, dres); key_put(key, dmatches);
     key_put(key, dmasks); key_put(key, ctx->stream); key_put(key, ctx->match_engine);
   }
+  const int nch = pipe_chunk_count(ctx, F - 1, K, K);
+  if (ctx->graphs) key_put(key, nch);
   return graph_or_eager(ctx, key, [&]() -> int {
-    PRE3_TRY(ws_reserve(ctx, pairs_ws_bytes(cls, F, K, K, ND, opts->H)));
-    return pairs_impl(ctx, ddesc, nullptr, cls, dxyz, nullptr, F - 1, K, K, ND, dk_count, nullptr, *opts, pair_id0, dres,
-                      dmatches, dmasks);
+    const int cmax = (F - 1 + nch - 1) / nch;
+    PRE3_TRY(ws_reserve(ctx, (size_t)nch * pairs_ws_bytes(cls, cmax + 1, K, K, ND, opts->H)));
+    const size_t es = class_size(cls);
+    return run_pipelined(ctx, F - 1, nch, [&](int p0, int n) -> int {  // pairs [p0, p0 + n) = frames p0 .. p0 + n
+      return pairs_impl(ctx, (const char*)ddesc + (size_t)p0 * K * ND * es, nullptr, cls, dxyz + 3 * (size_t)p0 * K, nullptr,
+                        n, K, K, ND, dk_count ? dk_count + p0 : nullptr, nullptr, *opts, pair_id0 + (uint32_t)p0,
+                        dres + p0, dmatches ? dmatches + 2 * (size_t)p0 * K : nullptr,
+                        dmasks ? dmasks + (size_t)p0 * K : nullptr);
+    });
   });
 }
 

@@ -76,6 +76,16 @@ struct pre3_ctx {
   cudaGraphExec_t graph_exec = nullptr;
   std::vector<unsigned char> graph_key, graph_seen;  // signature of the captured graph / of the last eager call
   int64_t graph_launches = 0;                        // kernel launches one replay stands for
+  // Software pipeline of the whole-pair entry points (pre3_set_pipeline): the pairs of a call are cut into chunks
+  // and the stages of a chunk (convert | GEMM + rescore + compact | prep + eval | select) run on their own streams, so
+  // that the HBM-bound, tensor-bound, FP32-issue-bound and latency-bound kernels of DIFFERENT chunks share the SMs.
+  int pipe_chunks = -1;                  // -1: automatic, 0 / 1: off, n: chunks per call
+  cudaStream_t pipe_stream[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t pipe_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t pipe_fork = nullptr;
+  int pipe_stage = -1;                   // stage the launches are currently issued for (-1: no pipeline running)
+  int pipe_map[4] = {0, 1, 2, 3};        // stage -> stream
+  int pipe_total_P = 0;                  // pairs of the whole call while a pipeline runs (occupancy heuristics)
   // optional per-launch CUDA-event timing (off by default)
   bool timing = false;
   std::vector<pre3::TimedSpan> spans;
@@ -185,6 +195,25 @@ inline T* ws_take(pre3_ctx* ctx, size_t count) {
 }
 
 inline void count_launch(pre3_ctx* ctx, int n = 1) { ctx->launches += n; }
+
+// Pipeline stages of a whole-pair call (pre3_set_pipeline).  No-ops unless a pipeline is running.
+enum PipeStage { PS_CONVERT = 0, PS_MATCH = 1, PS_EVAL = 2, PS_SELECT = 3 };
+// The launches that follow belong to `stage`: they are issued on that stage's stream, after everything issued so far
+// for the current chunk (event from the stream being left).
+inline int pipe_enter(pre3_ctx* ctx, int stage) {
+  if (ctx->pipe_stage < 0 || stage == ctx->pipe_stage) return PRE3_OK;
+  cudaStream_t next = ctx->pipe_stream[ctx->pipe_map[stage]];
+  if (next != ctx->stream) {
+    cudaEvent_t ev = ctx->pipe_ev[ctx->pipe_stage];
+    PRE3_CUDA(cudaEventRecord(ev, ctx->stream));
+    PRE3_CUDA(cudaStreamWaitEvent(next, ev, 0));
+    ctx->stream = next;
+  }
+  ctx->pipe_stage = stage;
+  return PRE3_OK;
+}
+// number of pairs the occupancy heuristics should assume are in flight
+inline int pipe_pairs(const pre3_ctx* ctx, int P) { return ctx->pipe_stage >= 0 && ctx->pipe_total_P > P ? ctx->pipe_total_P : P; }
 
 inline cudaEvent_t timing_event(pre3_ctx* ctx) {
   if (ctx->ev_used == ctx->ev_pool.size()) {

@@ -405,6 +405,7 @@ int launch_match_i8(pre3_ctx* ctx, const void* dL1, const void* dL2, int cls, in
     if (dk1) dk2 = dk1 + 1;
   }
   const bool sgn = cls == PRE3_CLASS_INT8;
+  PRE3_TRY(pipe_enter(ctx, PS_CONVERT));
   {
     Span span__(ctx, T_CONVERT);
     const dim3 g1(K1p / CV_ROWS, FA), g2(K2p / CV_ROWS, P);
@@ -417,6 +418,7 @@ int launch_match_i8(pre3_ctx* ctx, const void* dL1, const void* dL2, int cls, in
     }
     count_launch(ctx, seq ? 1 : 2);
   }
+  PRE3_TRY(pipe_enter(ctx, PS_MATCH));
   {
     Span span__(ctx, T_MATCH_TC);
     const long long units = (long long)P * ((K1p / BLK + 3) / 4);

@@ -1180,6 +1180,7 @@ int launch_match_tc(pre3_ctx* ctx, const void* dL1, const void* dL2, int cls, in
   FrameInfo* fb = seq ? fa + 1 : ws_take<FrameInfo>(ctx, (size_t)P);
   int32_t* list = ws_take<int32_t>(ctx, (size_t)P * K1);
   int32_t* list_n = ws_take<int32_t>(ctx, 64);
+  PRE3_TRY(pipe_enter(ctx, PS_CONVERT));
   PRE3_CUDA(cudaMemsetAsync(fa, 0, sizeof(FrameInfo) * (size_t)FA, ctx->stream));
   if (!seq) PRE3_CUDA(cudaMemsetAsync(fb, 0, sizeof(FrameInfo) * (size_t)P, ctx->stream));
   PRE3_CUDA(cudaMemsetAsync(list_n, 0, sizeof(int32_t), ctx->stream));
@@ -1200,6 +1201,7 @@ int launch_match_tc(pre3_ctx* ctx, const void* dL1, const void* dL2, int cls, in
     k_tc_pair_info<<<(P + 255) / 256, 256, 0, ctx->stream>>>(P, fa, fb, info, shared);
     count_launch(ctx, seq ? 2 : 3);
   }
+  PRE3_TRY(pipe_enter(ctx, PS_MATCH));
   static const int use_v1 = getenv("PRE3_TC_V1") ? atoi(getenv("PRE3_TC_V1")) : 0;
   static const int exp_mode = getenv("PRE3_TC_EXP") ? atoi(getenv("PRE3_TC_EXP")) : 0;
   if (!use_v1) {

@@ -2477,7 +2477,7 @@ static int launch_eval_pairloop_mode(pre3_ctx* ctx, const RansacBuffers& b, cons
   // spills of the fp64 fit cost more than the extra warps bring)
   static const int minb = getenv("PRE3_EVP_MINB") ? atoi(getenv("PRE3_EVP_MINB")) : 8;
   if constexpr (MODE == 0 && !SELECT) {
-    const int nt = pairloop_threads(o, b.P);
+    const int nt = pairloop_threads(o, pipe_pairs(ctx, b.P));
     if (nt != EVP_THREADS) {  // few pairs per GPU: wider blocks (same registers per thread: 4 / 2 blocks per SM)
 #define PRE3_EVALPW(MB, NTT)                                                                                       \
   k_eval_pairloop<5, 0, false, MB, NTT><<<b.P, NTT, 0, ctx->stream>>>(                                              \
@@ -2622,7 +2622,8 @@ int launch_select(pre3_ctx* ctx, const RansacBuffers& b, const pre3_ransac_opts&
     // lanes per tie: 4 when the batch fills the machine (4096 pairs x ~8 ties); with fewer pairs per GPU the residual
     // loop of a tie is the critical path and more lanes shorten it (PRE3_TIE_G overrides)
     static const int forced_g = getenv("PRE3_TIE_G") ? atoi(getenv("PRE3_TIE_G")) : 0;
-    int G = b.P >= 2048 ? 4 : (b.P >= 768 ? 8 : 16);
+    const int Pfly = pipe_pairs(ctx, b.P);
+    int G = Pfly >= 2048 ? 4 : (Pfly >= 768 ? 8 : 16);
     if (forced_g == 4 || forced_g == 8 || forced_g == 16 || forced_g == 32) G = forced_g;
     const int tb = (int)std::min<size_t>(((size_t)G * PH + TIE_THREADS - 1) / TIE_THREADS, (size_t)ctx->sm_count * 16);
 #define PRE3_TIE(GG)                                                                                                  \

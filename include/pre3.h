@@ -126,6 +126,14 @@ PRE3_API int64_t pre3_launch_count(const pre3_ctx *ctx);
  * launches, for loops that push the same device buffers through the path (streaming ring buffers, a sequence sharded
  * over several GPUs where a few hundred pairs per call make the step launch-bound).  Off by default. */
 PRE3_API int pre3_set_graphs(pre3_ctx *ctx, int on);
+/* Software pipeline of pre3_pairs_dev / pre3_sequence_dev: the pairs of a call are cut into `chunks` blocks whose stages
+ * (descriptor conversion | GEMM + rescore + gather | hypothesis evaluation | selection) run on four internal streams,
+ * so that kernels bound by different units of the GPU (HBM, tensor cores, FP32 issue, fp64 latency chains) overlap --
+ * the batched stand-in for the reference's frame loop (find_consistent_sift_matches.m:22-32), whose iterations are
+ * independent.  Results are those of the unchunked call.  chunks = -1: automatic (the default), 0 or 1: off, 2..64:
+ * that many chunks (never fewer than 128 pairs each).  The caller's stream sees one call: the internal streams fork
+ * from it and join it again. */
+PRE3_API int pre3_set_pipeline(pre3_ctx *ctx, int chunks);
 /* bytes pre3_pairs has moved over PCIe so far (host -> device, device -> host): bench.py's e2e figures.
  * Class-double descriptors whose values all survive (double)(float)x == x -- the reference's descriptors
  * are floats stored in a double matrix, M/sift/siftdescriptor.c:500-527 -- cross as float and are widened

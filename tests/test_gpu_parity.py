@@ -411,6 +411,64 @@ def test_sequence_equals_pairs(ctx, orc, synth, pre3, cls, engine):
         ctx.set_match_engine(0)
 
 
+@pytest.mark.parametrize("cls", ["f64", "u8"])
+@pytest.mark.parametrize("graphs", [False, True])
+def test_pipeline_equals_unchunked(pre3, synth, cls, graphs):
+    """pre3_set_pipeline: the chunked, four-stream form of pre3_sequence_dev / pre3_pairs_dev gives the bytes of the
+    single-stream call (records, matches, masks) -- eager and as a replayed CUDA graph, ragged frame sizes included,
+    chunk boundaries that do not divide the pair count; one pair is also compared with the oracle elsewhere
+    (test_sequence_equals_pairs), so this pins the pipeline to the already-pinned path."""
+    import torch
+    ctx = pre3.Context(0)
+    try:
+        F, K = 418, 160  # 417 pairs -> 3 chunks of 139 pairs
+        sq = synth.make_sequence_torch(F, 901, "cuda", K=K, n_corr=100)
+        desc, xyz = sq["desc"], sq["xyz"]
+        if cls == "u8":
+            desc = torch.clamp(torch.floor(512.0 * desc + 0.5), 0, 255).to(torch.uint8)
+        kc = torch.full((F,), K, dtype=torch.int32, device="cuda")
+        kc[7] = K - 5
+        kc[139] = K - 31  # the frame on a chunk boundary
+        kc[300] = K - 1
+        opts = pre3.make_opts(H=300, seed=4)
+        P = F - 1
+
+        def run(chunks, seq):
+            ctx.set_pipeline(chunks)
+            r = torch.zeros(P, 240, dtype=torch.uint8, device="cuda")
+            m = torch.zeros(P, K, 2, dtype=torch.int32, device="cuda")
+            k = torch.zeros(P, K, dtype=torch.uint8, device="cuda")
+            for _ in range(3 if graphs else 1):  # eager, capture, replay
+                r.zero_(); m.zero_(); k.zero_()
+                torch.cuda.synchronize()
+                if seq:
+                    ctx.sequence_dev(desc, xyz, opts, r, m, k, pair_id0=11, k_count=kc)
+                else:
+                    ctx.pairs_dev(d1, d2, x1, x2, opts, r, m, k, pair_id0=11, k1_count=kc1, k2_count=kc2)
+                ctx.sync()
+            return r.cpu().numpy().tobytes(), m.cpu().numpy(), k.cpu().numpy()
+
+        d1, d2 = desc[:-1].contiguous(), desc[1:].contiguous()
+        x1, x2 = xyz[:-1].contiguous(), xyz[1:].contiguous()
+        kc1, kc2 = kc[:-1].contiguous(), kc[1:].contiguous()
+        ctx.set_graphs(graphs)
+        for seq in (True, False):
+            r0, m0, k0 = run(0, seq)
+            rec = np.frombuffer(r0, dtype=pre3.RESULT_DTYPE)
+            assert (rec["status"] == 0).all() and (rec["best_fit"] > 30).all()
+            for chunks in (3, 2):
+                r1, m1, k1 = run(chunks, seq)
+                assert r1 == r0
+                for p in range(P):
+                    n = int(rec["n_matches"][p])
+                    np.testing.assert_array_equal(m1[p, :n], m0[p, :n])
+                    np.testing.assert_array_equal(k1[p, :n], k0[p, :n])
+        with pytest.raises(Exception):
+            ctx.set_pipeline(65)
+    finally:
+        ctx.close()
+
+
 def test_graph_replay_equals_eager(pre3, synth):
     """pre3_set_graphs: the captured launch sequence of a repeated pre3_sequence_dev signature gives the same bytes as
     the eager calls, also after the inputs behind the same pointers changed; a new signature falls back to eager."""
