@@ -15,7 +15,7 @@ OK, ERR_ARG, ERR_CUDA, ERR_ALLOC, ERR_CLASS = 0, -1, -2, -3, -4
 CLASS_DOUBLE, CLASS_SINGLE, CLASS_INT8, CLASS_UINT8 = 0, 1, 2, 3
 METHOD_SVD, METHOD_HORN, METHOD_DR_YE = 0, 1, 2
 MATCH_AUTO, MATCH_EXACT, MATCH_TC = 0, 1, 2
-TIMING_NCAT = 14
+TIMING_NCAT = 15
 
 
 class RansacOpts(C.Structure):

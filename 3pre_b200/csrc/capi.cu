@@ -231,7 +231,7 @@ static int pipe_chunk_count(const pre3_ctx* ctx, int P, int K1, int K2) {
   if (K1 > 2048 || K2 > 2048) return 1;  // large pairs: the per-call adaptive rows are built with a host round trip
   static const int env = getenv("PRE3_PIPE_CHUNKS") ? atoi(getenv("PRE3_PIPE_CHUNKS")) : -1;
   int n = env >= 0 ? env : ctx->pipe_chunks;
-  if (n < 0) n = P >= 1024 ? std::min(P / 512, 8) : 1;  // automatic: chunks of >= 512 pairs (measured)
+  if (n < 0) n = 1;  // automatic = off: measured slower at 4096 and at 512 pairs (profiles/r02_pipeline_sweep.log)
   const int min_pairs = 128;  // a chunk must keep the batch forms of the kernels (>= 64 pairs) and fill the GEMM grid
   n = std::min(n, P / min_pairs);
   return std::max(n, 1);
@@ -414,7 +414,7 @@ int pre3_timing_read(pre3_ctx* ctx, double* ms, int64_t* count) {
 const char* pre3_timing_name(int cat) {
   static const char* names[T_NCAT] = {"convert", "match_tc", "match_exact", "rescore", "compact",
                                       "prep",    "eval",     "select",      "other",   "ekf_gain",
-                                      "ekf_score", "ekf_select", "frames", "ekf_update"};
+                                      "ekf_score", "ekf_select", "frames", "ekf_update", "match_fused"};
   return (cat >= 0 && cat < T_NCAT) ? names[cat] : "?";
 }
 

@@ -22,7 +22,7 @@ void host_pool_destroy(HostPool* p);
 int host_pool_size(const HostPool* p);
 bool host_narrow(HostPool* pool, const double* s, float* d, size_t n);
 // per-kernel timing categories (pre3_timing_*): bench.py's roofline numbers come from here
-enum TimeCat { T_CONVERT = 0, T_MATCH_TC, T_MATCH_EXACT, T_RESCORE, T_COMPACT, T_PREP, T_EVAL, T_SELECT, T_OTHER, T_EKF_GAIN, T_EKF_SCORE, T_EKF_SELECT, T_FRAMES, T_EKF_UPDATE, T_NCAT };
+enum TimeCat { T_CONVERT = 0, T_MATCH_TC, T_MATCH_EXACT, T_RESCORE, T_COMPACT, T_PREP, T_EVAL, T_SELECT, T_OTHER, T_EKF_GAIN, T_EKF_SCORE, T_EKF_SELECT, T_FRAMES, T_EKF_UPDATE, T_MATCH_FUSED, T_NCAT };
 struct TimedSpan {
   int cat;
   cudaEvent_t a, b;

@@ -790,6 +790,427 @@ k_tc_gemm_pair(const unsigned char* __restrict__ imgA, const unsigned char* __re
 }
 
 // ---------------------------------------------------------------------------------------------
+// k_tc_seq_fused: conversion AND proposal GEMM of a SEQUENCE in one kernel (K1p = K2p = 512).
+//
+// k_tc_convert is bound by HBM (it reads every descriptor as fp64), k_tc_gemm_pair by the tensor pipe and the
+// epilogue's issue slots; run one after the other each leaves the other unit idle, and the fp16 image makes a round
+// trip through HBM / L2 in between.  Here every CTA pair takes a CONTIGUOUS run of pairs u0 .. u1-1, i.e. frames
+// u0 .. u1, and keeps three frames resident in shared memory as fp16 operand images: frame i is the B operand of pair
+// i-1 and then -- the same bytes, untouched -- the A operand of pair i, while converter warps read frame i+1 from HBM
+// (fp64 or fp32), convert it in registers and store it swizzled into the third buffer.  The fp16 image never exists in
+// global memory; the descriptors are read from HBM once per sequence (plus one frame per CTA pair).
+//
+// One frame image per CTA (64 KB + 8 KB of K-extension rows): [sidx 2][K half 2][row 128][128 B], where the 128 rows of
+// part sidx are rows 64 rank .. 64 rank + 63 of the frame's 128-row block 2 sidx followed by the same rows of block
+// 2 sidx + 1.  As A operand part sidx is one M = 128 tile of this CTA; as B operand the 64 rows of block j are this
+// CTA's half of the N = 128 tile j.  Arithmetic (fp16 rounding, MMA order, selection) is that of k_tc_convert +
+// k_tc_gemm_pair: the proposals are identical.
+//   barriers:  f_full[buf][j]  LEADER only: one arrival per converted quad of rows, 16 local + 16 remote (release.cluster):
+//                              tile j of the frame in `buf` is in both CTAs' shared memory
+//              f_empty[buf]    tcgen05.commit multicast: the MMAs of the pair that used `buf` as A have completed
+//              t_full / t_empty as in k_tc_gemm_pair
+// ---------------------------------------------------------------------------------------------
+constexpr int FZ_NCW = 7;                                  // converter warps per CTA (16 warps: 4 per sub-partition)
+constexpr int FZ_W_CONV = 8, FZ_W_ALLOC = FZ_W_CONV, FZ_W_MMA = 8 + FZ_NCW;  // 0-7: the two epilogue warpgroups
+constexpr int FZ_THREADS = 32 * (9 + FZ_NCW);
+constexpr int FZ_KP = 512;                                 // padded descriptor count this kernel is built for
+constexpr int FZ_IMG_BYTES = 2 * BLK_BYTES;                // 64 KB per frame and CTA
+constexpr int FZ_EXT_BYTES = 4 * P2_BEXT;                  // 8 KB
+constexpr int FZ_BUF_BYTES = FZ_IMG_BYTES + FZ_EXT_BYTES;
+constexpr int FZ_NBUF = 3;
+constexpr int FZ_OFF_AX = FZ_NBUF * FZ_BUF_BYTES;
+constexpr int FZ_OFF_BAR = FZ_OFF_AX + EXT_BYTES;
+constexpr int FZ_SMEM_BYTES = FZ_OFF_BAR + 512;
+constexpr int FZ_QROWS = 4;                                // rows a converter warp converts at a time ("quad")
+constexpr int FZ_TQUADS = 64 / FZ_QROWS;                   // quads per tile and CTA
+constexpr int FZ_FQUADS = 4 * FZ_TQUADS;                   // quads per frame and CTA
+static_assert(FZ_SMEM_BYTES + 1024 <= 227 * 1024, "fused sequence matcher: shared memory");
+static_assert(FZ_BUF_BYTES % 1024 == 0, "fused sequence matcher: layout");
+
+struct FusedBarriers {
+  uint64_t f_full[FZ_NBUF][4], f_empty[FZ_NBUF];
+  uint64_t t_full[4], t_empty[4];
+  uint32_t tmem_base;
+};
+static_assert(sizeof(FusedBarriers) <= 512, "FusedBarriers");
+
+__device__ __forceinline__ void mbar_arrive_release_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+
+template <typename T>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FZ_THREADS, 1)
+k_tc_seq_fused(const T* __restrict__ L, int K, const int32_t* __restrict__ kc, int P, int ext_layout,
+               float* __restrict__ nrm, FrameInfo* __restrict__ finfo, Prop2* __restrict__ prop) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const uint32_t base = smem_u32(smem);
+  if (base & 1023u) __trap();
+  const uint32_t sAX = base + FZ_OFF_AX;
+  FusedBarriers* bars = reinterpret_cast<FusedBarriers*>(smem + FZ_OFF_BAR);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+  const int u0 = (int)((long long)P * cluster_id / nclusters), u1 = (int)((long long)P * (cluster_id + 1) / nclusters);
+  const int npairs = u1 - u0;  // >= 1: the grid never has more CTA pairs than frame pairs
+
+  if (warp == FZ_W_MMA && lane == 0) {
+    for (int b = 0; b < FZ_NBUF; ++b) {
+      for (int j = 0; j < 4; ++j) mbar_init(smem_u32(&bars->f_full[b][j]), 2 * FZ_TQUADS);
+      mbar_init(smem_u32(&bars->f_empty[b]), 1);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(smem_u32(&bars->t_full[i]), 1);
+      mbar_init(smem_u32(&bars->t_empty[i]), 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == FZ_W_ALLOC) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&bars->tmem_base))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  for (int r = threadIdx.x; r < BLK; r += FZ_THREADS) {  // constant A tile of the ninth K step
+    const __half one = __float2half(1.0f), sc = __float2half(EXT_SCALE);
+    uint4 w;
+    w.x = (unsigned)__half_as_ushort(sc) | ((unsigned)__half_as_ushort(sc) << 16);
+    w.y = (unsigned)__half_as_ushort(one) | ((unsigned)__half_as_ushort(one) << 16);
+    w.z = w.w = 0u;
+    *reinterpret_cast<uint4*>(smem + FZ_OFF_AX + ext_off(ext_layout, r, 0)) = w;
+    *reinterpret_cast<uint4*>(smem + FZ_OFF_AX + ext_off(ext_layout, r, 1)) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+
+  if (warp >= FZ_W_CONV && warp < FZ_W_CONV + FZ_NCW) {
+    // ===== converters: frame u0 + i -> buffer i % 3, this CTA's 64 rows of every 128-row block ========
+    // Work item = a quad of 4 rows (1 KB each: lane l holds elements 4l .. 4l+3).  The loads of the next quad are in
+    // flight while the current one is converted (two register sets), across tile and frame boundaries; only the
+    // shared-memory writes wait for the buffer.  |x|^2: the per-lane partial sums of the four rows are reduced
+    // together -- the xor-16 and xor-8 steps of k_tc_convert's butterfly as a reduce-scatter (a lane keeps the rows its
+    // lane bits select), then xor 4, 2, 1 -- so every row's sum has the operand pairing of k_tc_convert (a + b is
+    // commutative: the same bits) and lane l ends with the norm of row (l >> 3) & 3; lanes 0, 8, 16, 24 then write the
+    // K-extension rows and the norms of their rows in parallel.
+    const int cw = warp - FZ_W_CONV;
+    const int total = (npairs + 1) * FZ_FQUADS;  // quads of this CTA's stream; warp cw takes quads cw, cw + NCW, ...
+    // this lane's byte offset inside a 128-byte image row group: K half, swizzled 16-byte chunk, 8-byte half of it
+    // (the swizzle key tr & 7 = e & 3 | (quad & 1) << 2 is added per row below)
+    const uint32_t lane_img = (uint32_t)((lane >> 4) * HALF_BYTES + ((lane & 1) << 3));
+    const uint32_t lane_c = (uint32_t)((lane & 15) >> 1);
+    // bounds of the frame a stream of quads is in: max |value| (float bits, sign cleared: NaN and inf order above every
+    // finite value), max |x|^2, "some |x|^2 does not fit the split"
+    struct Stats {
+      unsigned amax;
+      float wmax;
+      int wbad, fi;
+    };
+    auto flush_bounds = [&](Stats& st) {  // idempotent: a boundary frame is converted by two CTA pairs
+      const unsigned mx = __reduce_max_sync(0xffffffffu, __float_as_uint(st.wmax));  // non-negative floats order as uints
+      const unsigned am = __reduce_max_sync(0xffffffffu, st.amax);
+      const unsigned bd = __reduce_or_sync(0xffffffffu, (unsigned)st.wbad);
+      if (lane == 0) {
+        if (mx != 0u) atomicMax(&finfo[u0 + st.fi].max_bits, mx);
+        if (bd || am > __float_as_uint(60000.0f)) atomicOr(&finfo[u0 + st.fi].bad, 1);
+      }
+      st.wmax = 0.f;
+      st.wbad = 0;
+      st.amax = 0u;
+    };
+    int cur_i = -1;  // newest frame whose buffer this warp has acquired
+    // position of a quad in the stream, advanced by 2 FZ_NCW quads at a time without divisions
+    struct Pos {
+      int i, hq;  // frame (relative to u0), quad within the frame (tile j = hq >> 4, quad of the tile = hq & 15)
+      __device__ __forceinline__ void advance(int by) {
+        hq += by;
+        if (hq >= FZ_FQUADS) {
+          hq -= FZ_FQUADS;
+          ++i;
+        }
+      }
+    };
+    auto issue = [&](const Pos& q, double (&v)[FZ_QROWS][4]) {
+      const int f = u0 + q.i;
+      const int n = kc ? max(0, min(__ldg(kc + f), K)) : K;
+      const int row0 = (q.hq >> 4) * BLK + 64 * (int)rank + (q.hq & 15) * FZ_QROWS;
+      const T* src = L + ((size_t)f * K + row0) * ND + 4 * lane;
+#pragma unroll
+      for (int e = 0; e < FZ_QROWS; ++e) {
+        v[e][0] = v[e][1] = v[e][2] = v[e][3] = 0.0;
+        if (row0 + e < n) load4(src + (size_t)e * ND, v[e]);
+      }
+    };
+    auto acquire = [&](const Pos& q) {  // first write of this warp into the buffer for frame q.i: the pair that used it as A must be done
+      if (q.i > cur_i) {
+        cur_i = q.i;
+        mbar_wait(smem_u32(&bars->f_empty[q.i % FZ_NBUF]), (uint32_t)(((q.i / FZ_NBUF) & 1) ^ 1));
+        tc_fence_after();
+      }
+    };
+    // part 1 of a quad: fp16 image rows into the buffer, this lane's partial |x|^2 of the four rows; frees the raw values
+    auto convert = [&](const Pos& q, double (&v)[FZ_QROWS][4], double (&sq)[FZ_QROWS], Stats& st) {
+      if (q.i != st.fi) {
+        if (st.fi >= 0) flush_bounds(st);
+        st.fi = q.i;
+      }
+      const int j = q.hq >> 4, qd = q.hq & 15;
+      const int tr0 = (j & 1) * 64 + qd * FZ_QROWS;  // first row of the quad within the 128-row tile of part j >> 1
+      unsigned char* dst0 = smem + (q.i % FZ_NBUF) * FZ_BUF_BYTES + (j >> 1) * BLK_BYTES + tr0 * 128 + lane_img;
+#pragma unroll
+      for (int e = 0; e < FZ_QROWS; ++e) {
+        const float f0 = (float)v[e][0], f1 = (float)v[e][1], f2 = (float)v[e][2], f3 = (float)v[e][3];
+        __half2 h01 = __floats2half2_rn(f0, f1);
+        __half2 h23 = __floats2half2_rn(f2, f3);
+        uint2 packed;
+        packed.x = *reinterpret_cast<unsigned*>(&h01);
+        packed.y = *reinterpret_cast<unsigned*>(&h23);
+        const uint32_t key = (uint32_t)(e | ((qd & 1) << 2));  // (tr0 + e) & 7
+        *reinterpret_cast<uint2*>(dst0 + e * 128 + ((lane_c ^ key) << 4)) = packed;
+        sq[e] = (v[e][0] * v[e][0] + v[e][1] * v[e][1]) + (v[e][2] * v[e][2] + v[e][3] * v[e][3]);
+        // range check on the float images (a value fits fp16 iff its float image does; NaN / inf compare above)
+        st.amax = max(st.amax, max(__float_as_uint(f0) & 0x7FFFFFFFu, __float_as_uint(f1) & 0x7FFFFFFFu));
+        st.amax = max(st.amax, max(__float_as_uint(f2) & 0x7FFFFFFFu, __float_as_uint(f3) & 0x7FFFFFFFu));
+      }
+    };
+    // part 2: |x|^2 of the four rows -- reduce-scatter over lane bits 4 and 3, butterfly over bits 2, 1, 0: lane l ends
+    // with the sum of row l >> 3, every row with the operand pairing of k_tc_convert's butterfly
+    auto reduce = [&](const double (&sq)[FZ_QROWS]) -> double {
+      const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0;
+      const double s0 = b4 ? sq[0] : sq[2], s1 = b4 ? sq[1] : sq[3];
+      const double k0 = b4 ? sq[2] : sq[0], k1 = b4 ? sq[3] : sq[1];
+      const double w0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 16);
+      const double w1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 16);
+      const double s2 = b3 ? w0 : w1, k2 = b3 ? w1 : w0;
+      double t = k2 + __shfl_xor_sync(0xffffffffu, s2, 8);
+      t += __shfl_xor_sync(0xffffffffu, t, 4);
+      t += __shfl_xor_sync(0xffffffffu, t, 2);
+      t += __shfl_xor_sync(0xffffffffu, t, 1);
+      return t;
+    };
+    // part 3 (lanes 0, 8, 16, 24: one row each): K-extension row = the exact four-slot split of -|x|^2/2 (k_tc_convert),
+    // the norm.  A frame with an out-of-range VALUE is flagged as a whole (flush_bounds): its pairs never use the proposal
+    auto finish = [&](const Pos& q, double t, Stats& st) {
+      const int j = q.hq >> 4;
+      const int rl = (q.hq & 15) * FZ_QROWS + (lane >> 3);
+      const int row = j * BLK + 64 * (int)rank + rl;
+      const int f = u0 + q.i;
+      const int n = kc ? max(0, min(__ldg(kc + f), K)) : K;
+      const bool bad = !(t <= NORM_MAX);
+      __half h[4];
+      if (row < n && !bad) {
+        double gq = -0.5 * t;
+        h[0] = __double2half(gq * (1.0 / 4096.0));
+        gq = gq - 4096.0 * (double)__half2float(h[0]);
+        h[1] = __double2half(gq * (1.0 / 4096.0));
+        gq = gq - 4096.0 * (double)__half2float(h[1]);
+        h[2] = __double2half(gq);
+        gq = gq - (double)__half2float(h[2]);
+        h[3] = __double2half(gq);
+      } else {
+        h[0] = __float2half(-60000.0f);
+        h[1] = h[2] = h[3] = __float2half(0.0f);
+      }
+      uint4 w;
+      w.x = (unsigned)__half_as_ushort(h[0]) | ((unsigned)__half_as_ushort(h[1]) << 16);
+      w.y = (unsigned)__half_as_ushort(h[2]) | ((unsigned)__half_as_ushort(h[3]) << 16);
+      w.z = w.w = 0u;
+      unsigned char* e0 = smem + (q.i % FZ_NBUF) * FZ_BUF_BYTES + FZ_IMG_BYTES + j * P2_BEXT;  // SWIZZLE_32B rows (ext_off)
+      *reinterpret_cast<uint4*>(e0 + ext_off(0, rl, 0)) = w;
+      *reinterpret_cast<uint4*>(e0 + ext_off(0, rl, 1)) = make_uint4(0u, 0u, 0u, 0u);
+      const float fn = __double2float_ru(t);
+      nrm[(size_t)f * FZ_KP + row] = (row < n) ? fn : INFINITY;
+      if (row < n) {
+        st.wmax = fmaxf(st.wmax, fn);
+        st.wbad |= bad ? 1 : 0;
+      }
+    };
+    auto arrive = [&](const Pos& q) {
+      const uint32_t bar = smem_u32(&bars->f_full[q.i % FZ_NBUF][q.hq >> 4]);
+      if (leader) mbar_arrive(bar);
+      else mbar_arrive_cluster(mapa_u32(bar, 0));
+    };
+    // Two quads per trip (streams a and b, FZ_NCW quads apart).  The raw values of a quad are dead once `convert` has
+    // run, so the loads of the quad two trips ahead are issued right behind it and stay in flight during the serial
+    // rest of the trip (the shuffle chains and the dependent conversions of the split), which the two quads run
+    // interleaved.
+    double va[FZ_QROWS][4], vb[FZ_QROWS][4];
+    Stats sa{0u, 0.f, 0, -1}, sb{0u, 0.f, 0, -1};
+    Pos qa{0, cw}, qb{0, cw};
+    qb.advance(FZ_NCW);
+    int Q = cw;  // stream index of qa
+    if (Q < total) issue(qa, va);
+    if (Q + FZ_NCW < total) issue(qb, vb);
+#pragma unroll 1
+    for (; Q < total; Q += 2 * FZ_NCW) {
+      const bool has_b = Q + FZ_NCW < total;
+      const Pos ca = qa, cb = qb;
+      double sqa[FZ_QROWS], sqb[FZ_QROWS] = {0.0, 0.0, 0.0, 0.0};
+      acquire(ca);
+      convert(ca, va, sqa, sa);
+      qa.advance(2 * FZ_NCW);
+      if (Q + 2 * FZ_NCW < total) issue(qa, va);
+      if (has_b) {
+        acquire(cb);
+        convert(cb, vb, sqb, sb);
+      }
+      qb.advance(2 * FZ_NCW);
+      if (Q + 3 * FZ_NCW < total) issue(qb, vb);
+      const double ta = reduce(sqa);
+      const double tb = reduce(sqb);
+      if ((lane & 7) == 0) {
+        finish(ca, ta, sa);
+        if (has_b) finish(cb, tb, sb);
+      }
+      // the quads are written: generic-proxy writes -> async proxy, then tell the issuer (CTA-scope release, as every
+      // other remote arrive of these kernels: what the arrive publishes are this SM's shared-memory writes, already
+      // pushed to the async proxy by the fence; a cluster-scope release would also wait for the global norm stores:
+      // measured 1.00 -> 0.78 ms per 4096 pairs)
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        arrive(ca);
+        if (has_b) arrive(cb);
+      }
+    }
+    if (sa.fi >= 0) flush_bounds(sa);
+    if (sb.fi >= 0) flush_bounds(sb);
+    // the commit that releases the last pair's A buffer targets THIS CTA's barrier too: stay until it has arrived
+    if (cw == 0) mbar_wait(smem_u32(&bars->f_empty[(npairs - 1) % FZ_NBUF]), (uint32_t)(((npairs - 1) / FZ_NBUF) & 1));
+  } else if (warp == FZ_W_MMA) {
+    if (lane == 0 && leader) {
+      // ===== MMA issuer (one thread of the leader CTA, for both SMs) =================================
+      uint32_t use[4] = {0, 0, 0, 0};
+      for (int i = 0; i < npairs; ++i) {
+        const int bA = i % FZ_NBUF, bB = (i + 1) % FZ_NBUF;
+        const uint32_t phA = (uint32_t)((i / FZ_NBUF) & 1), phB = (uint32_t)(((i + 1) / FZ_NBUF) & 1);
+        const uint32_t sAf = base + bA * FZ_BUF_BYTES, sBf = base + bB * FZ_BUF_BYTES;
+        for (int j = 0; j < 4; ++j) mbar_wait_cl(smem_u32(&bars->f_full[bA][j]), phA);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          mbar_wait_cl(smem_u32(&bars->f_full[bB][j]), phB);
+          tc_fence_after();
+          const uint32_t sBt = sBf + (j >> 1) * BLK_BYTES + (j & 1) * P2_BHALF;
+#pragma unroll
+          for (int sidx = 0; sidx < 2; ++sidx) {
+            const int slot = (j & 1) * 2 + sidx;
+            mbar_wait_cl(smem_u32(&bars->t_empty[slot]), (use[slot] & 1) ^ 1);
+            ++use[slot];
+            tc_fence_after();
+            const uint32_t d = tmem + (uint32_t)(slot * P2_TILE_N);
+#pragma unroll
+            for (int k = 0; k < ND / 16; ++k) {
+              const uint32_t ko = (uint32_t)((k >> 2) * HALF_BYTES + (k & 3) * 32);
+              tc_mma_f16_2cta(d, umma_desc(sAf + sidx * BLK_BYTES + ko), umma_desc(sBt + ko), IDESC_PAIR, k > 0 ? 1u : 0u);
+            }
+            tc_mma_f16_2cta(d, umma_desc_ext(sAX, ext_layout),
+                            umma_desc_ext(sBf + FZ_IMG_BYTES + j * P2_BEXT, ext_layout), IDESC_PAIR, 1u);
+            tc_commit_mc2(smem_u32(&bars->t_full[slot]));
+          }
+        }
+        tc_commit_mc2(smem_u32(&bars->f_empty[bA]));
+      }
+    }
+  } else if (warp < FZ_W_CONV) {
+    // ===== epilogue: the selection of k_tc_gemm_pair (EPI = 1); warpgroup s owns part s of this CTA ==
+    const int sidx = warp >> 2;
+    const int q = warp & 3;
+    const uint32_t tel0 = mapa_u32(smem_u32(&bars->t_empty[sidx]), 0);
+    const uint32_t tel1 = mapa_u32(smem_u32(&bars->t_empty[2 + sidx]), 0);
+    uint32_t use0 = 0, use1 = 0;
+    uint32_t keymask;
+    asm volatile("mov.u32 %0, 0xFFFFFF80;" : "=r"(keymask));
+    const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(sidx * P2_TILE_N);
+    uint32_t buf[2][32];
+    auto wait_full = [&](int stg) {
+      uint32_t& use = stg == 0 ? use0 : use1;
+      mbar_wait(smem_u32(&bars->t_full[stg * 2 + sidx]), use & 1);
+      ++use;
+      tc_fence_after();
+    };
+    auto release = [&](int stg) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(smem_u32(&bars->t_empty[stg * 2 + sidx]));
+        else mbar_arrive_cluster(stg == 0 ? tel0 : tel1);
+      }
+    };
+    wait_full(0);
+    tc_ld_32x32(tbase, buf[0]);
+    for (int i = 0; i < npairs; ++i) {
+      float2 m1 = make_float2(-INFINITY, -INFINITY), m2 = make_float2(-INFINITY, -INFINITY);
+      int btA = -1, btB = -1;
+      for (int j = 0; j < 4; ++j) {
+        const int stg = j & 1;
+        const float2 m1_in = m1;
+        const bool has_next = (j + 1 < 4) || (i + 1 < npairs);
+#pragma unroll
+        for (int c = 0; c < P2_TILE_N / 32; ++c) {
+          tc_ld_wait(buf[c & 1]);
+          if (c + 1 < P2_TILE_N / 32) {
+            tc_ld_32x32(tbase + (uint32_t)(stg * 2 * P2_TILE_N + (c + 1) * 32), buf[(c + 1) & 1]);
+          } else {
+            release(stg);
+            if (has_next) {
+              wait_full(stg ^ 1);
+              tc_ld_32x32(tbase + (uint32_t)((stg ^ 1) * 2 * P2_TILE_N), buf[0]);
+            }
+          }
+#pragma unroll
+          for (int i4 = 0; i4 < 8; ++i4) {
+            uint32_t k[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(k[e]) : "r"(buf[c & 1][4 * i4 + e]), "r"(keymask), "r"((uint32_t)(c * 32 + 4 * i4 + e)));
+            const float2 ka = make_float2(__uint_as_float(k[0]), __uint_as_float(k[1]));
+            const float2 kb = make_float2(__uint_as_float(k[2]), __uint_as_float(k[3]));
+            const float2 hi = make_float2(fmaxf(ka.x, kb.x), fmaxf(ka.y, kb.y));
+            const float2 nhi = make_float2(-hi.x, -hi.y);
+            const float2 lo = __fadd2_rn(__fadd2_rn(ka, kb), nhi);
+            const float2 m1n = make_float2(fmaxf(m1.x, hi.x), fmaxf(m1.y, hi.y));
+            const float2 x = __fadd2_rn(__fadd2_rn(m1, hi), make_float2(-m1n.x, -m1n.y));
+            m2.x = fmaxf(fmaxf(m2.x, x.x), lo.x);
+            m2.y = fmaxf(fmaxf(m2.y, x.y), lo.y);
+            m1 = m1n;
+          }
+        }
+        if (m1.x != m1_in.x) btA = j;
+        if (m1.y != m1_in.y) btB = j;
+      }
+      float b1, b2;
+      int col;
+      {
+        const int cA = btA < 0 ? -1 : btA * P2_TILE_N + (int)(__float_as_uint(m1.x) & 0x7Fu);
+        const int cB = btB < 0 ? -1 : btB * P2_TILE_N + (int)(__float_as_uint(m1.y) & 0x7Fu);
+        if (cB >= 0 && (cA < 0 || m1.y > m1.x || (m1.y == m1.x && cB < cA))) {
+          b1 = m1.y, col = cB, b2 = fmaxf(m1.x, fmaxf(m2.x, m2.y));
+        } else {
+          b1 = m1.x, col = cA, b2 = fmaxf(m1.y, fmaxf(m2.x, m2.y));
+        }
+      }
+      const int r = q * 32 + lane;  // row within part sidx: rows 64 rank .. of block 2 sidx, then of block 2 sidx + 1
+      const int row = (2 * sidx + (r >> 6)) * BLK + 64 * (int)rank + (r & 63);
+      Prop2 out;
+      out.best = __uint_as_float(__float_as_uint(b1) & 0xFFFFFF80u);
+      out.second = __uint_as_float(__float_as_uint(b2) & 0xFFFFFF80u);
+      out.idx = col;
+      prop[(size_t)(u0 + i) * FZ_KP + row] = out;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == FZ_W_ALLOC) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // k_tc_rescore: exact candidate distance + certified ratio-test decision.  One warp handles 32
 // rows at a time: coalesced loads of the row and of its candidate column, delta*delta per
 // element into shared memory, then lane r sums row r strictly in bin order.
@@ -1188,6 +1609,38 @@ int launch_match_tc(pre3_ctx* ctx, const void* dL1, const void* dL2, int cls, in
     dL2 = (const char*)dL1 + (size_t)K1 * ND * (cls == PRE3_CLASS_DOUBLE ? 8 : 4);
     if (dk1) dk2 = dk1 + 1;
   }
+  static const int use_v1 = getenv("PRE3_TC_V1") ? atoi(getenv("PRE3_TC_V1")) : 0;
+  static const int exp_mode = getenv("PRE3_TC_EXP") ? atoi(getenv("PRE3_TC_EXP")) : 0;
+  // A sequence of 512-row frames: conversion and GEMM in ONE kernel (k_tc_seq_fused; PRE3_TC_FUSED=0 keeps them apart)
+  const int fused_env = getenv("PRE3_TC_FUSED") ? atoi(getenv("PRE3_TC_FUSED")) : 1;
+  static const int epi_env = getenv("PRE3_TC_EPI") ? atoi(getenv("PRE3_TC_EPI")) : 1;
+  const bool fused = seq && fused_env && !use_v1 && exp_mode == 0 && epi_env && ext_layout == 0 && K1p == FZ_KP && K2p == FZ_KP;
+  if (fused) {
+    {
+      Span span__(ctx, T_MATCH_FUSED);
+      const int grid = 2 * std::min(P, ctx->sm_count / 2);
+#define PRE3_FUSED(T)                                                                                                \
+  do {                                                                                                               \
+    static bool attr_done = false;                                                                                   \
+    if (!attr_done) {                                                                                                \
+      PRE3_CUDA(cudaFuncSetAttribute(k_tc_seq_fused<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, FZ_SMEM_BYTES)); \
+      attr_done = true;                                                                                              \
+    }                                                                                                                \
+    k_tc_seq_fused<T><<<grid, FZ_THREADS, FZ_SMEM_BYTES, ctx->stream>>>((const T*)dL1, K1, dk1, P, ext_layout, nrmA, fa, \
+                                                                       reinterpret_cast<Prop2*>(prop));             \
+  } while (0)
+      if (cls == PRE3_CLASS_DOUBLE) PRE3_FUSED(double);
+      else PRE3_FUSED(float);
+#undef PRE3_FUSED
+      count_launch(ctx);
+    }
+    PRE3_TRY(pipe_enter(ctx, PS_MATCH));
+    {
+      Span span__(ctx, T_RESCORE);  // the pair bounds are an input of the rescore
+      k_tc_pair_info<<<(P + 255) / 256, 256, 0, ctx->stream>>>(P, fa, fb, info, shared);
+      count_launch(ctx);
+    }
+  } else
   {
     Span span__(ctx, T_CONVERT);
     const dim3 g1(K1p / CV_ROWS, FA), g2(K2p / CV_ROWS, P);
@@ -1202,9 +1655,9 @@ int launch_match_tc(pre3_ctx* ctx, const void* dL1, const void* dL2, int cls, in
     count_launch(ctx, seq ? 2 : 3);
   }
   PRE3_TRY(pipe_enter(ctx, PS_MATCH));
-  static const int use_v1 = getenv("PRE3_TC_V1") ? atoi(getenv("PRE3_TC_V1")) : 0;
-  static const int exp_mode = getenv("PRE3_TC_EXP") ? atoi(getenv("PRE3_TC_EXP")) : 0;
-  if (!use_v1) {
+  if (fused) {
+    // proposals already written
+  } else if (!use_v1) {
     // CTA pairs: one 2-CTA cluster per SM pair, unit = (pair, 256-row group)
     Span span__(ctx, T_MATCH_TC);
     const long long units = (long long)P * ((K1p / BLK + 3) / 4);

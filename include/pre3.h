@@ -153,7 +153,7 @@ PRE3_API int pre3_eval_schedule_for(const pre3_ransac_opts *opts, int P, int32_t
  * numbers).  pre3_timing_read synchronises, adds the elapsed ms and launch counts of every
  * bracketed launch since the last read into ms[cat] / count[cat] (PRE3_TIMING_NCAT entries
  * each, caller-zeroed) and forgets them.  pre3_timing_name(cat) names a category. */
-#define PRE3_TIMING_NCAT 14
+#define PRE3_TIMING_NCAT 15
 PRE3_API int pre3_timing_enable(pre3_ctx *ctx, int on);
 PRE3_API int pre3_timing_read(pre3_ctx *ctx, double *ms, int64_t *count);
 PRE3_API const char *pre3_timing_name(int cat);

@@ -469,6 +469,54 @@ def test_pipeline_equals_unchunked(pre3, synth, cls, graphs):
         ctx.close()
 
 
+@pytest.mark.parametrize("cls", ["f64", "f32"])
+@pytest.mark.parametrize("K,P", [(512, 160), (500, 37), (300, 3)])
+def test_fused_sequence_matcher_equals_separate_kernels(pre3, synth, cls, K, P):
+    """k_tc_seq_fused (conversion + proposal GEMM of a sequence in one kernel, frames resident in shared memory) against
+    k_tc_convert + k_tc_gemm_pair (PRE3_TC_FUSED=0): records, matches and masks bit for bit; more pairs than CTA pairs
+    (160 > 74: runs of 2-3 pairs per CTA pair, every buffer rotation), fewer (37, 3), ragged frames, K < 512."""
+    import os
+    import torch
+    F = P + 1
+    sq = synth.make_sequence_torch(F, 313 + K, "cuda", K=K, n_corr=min(250, K // 2))
+    desc, xyz = sq["desc"], sq["xyz"]
+    if cls == "f32":
+        desc = desc.to(torch.float32)
+    kc = torch.full((F,), K, dtype=torch.int32, device="cuda")
+    kc[1] = K - 7
+    kc[F - 1] = K - 40
+    if F > 20:
+        kc[17] = K - 129
+    opts = pre3.make_opts(H=300, seed=21)
+    out = {}
+    old = os.environ.get("PRE3_TC_FUSED")
+    try:
+        for mode in ("1", "0"):
+            os.environ["PRE3_TC_FUSED"] = mode
+            ctx = pre3.Context(0)
+            ctx.set_match_engine(1)
+            r = torch.zeros(P, 240, dtype=torch.uint8, device="cuda")
+            m = torch.zeros(P, K, 2, dtype=torch.int32, device="cuda")
+            k = torch.zeros(P, K, dtype=torch.uint8, device="cuda")
+            torch.cuda.synchronize()
+            ctx.sequence_dev(desc, xyz, opts, r, m, k, pair_id0=3, k_count=kc)
+            ctx.sync()
+            out[mode] = (r.cpu().numpy().tobytes(), m.cpu().numpy(), k.cpu().numpy())
+            ctx.close()
+    finally:
+        if old is None:
+            os.environ.pop("PRE3_TC_FUSED", None)
+        else:
+            os.environ["PRE3_TC_FUSED"] = old
+    rec = np.frombuffer(out["1"][0], dtype=pre3.RESULT_DTYPE)
+    assert out["1"][0] == out["0"][0]
+    assert (rec["status"] == 0).all() and (rec["n_matches"] > 50).all()
+    for p in range(P):
+        n = int(rec["n_matches"][p])
+        np.testing.assert_array_equal(out["1"][1][p, :n], out["0"][1][p, :n])
+        np.testing.assert_array_equal(out["1"][2][p, :n], out["0"][2][p, :n])
+
+
 def test_graph_replay_equals_eager(pre3, synth):
     """pre3_set_graphs: the captured launch sequence of a repeated pre3_sequence_dev signature gives the same bytes as
     the eager calls, also after the inputs behind the same pointers changed; a new signature falls back to eager."""
