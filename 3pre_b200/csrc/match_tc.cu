@@ -902,24 +902,22 @@ k_tc_seq_fused(const T* __restrict__ L, int K, const int32_t* __restrict__ kc, i
     // (the swizzle key tr & 7 = e & 3 | (quad & 1) << 2 is added per row below)
     const uint32_t lane_img = (uint32_t)((lane >> 4) * HALF_BYTES + ((lane & 1) << 3));
     const uint32_t lane_c = (uint32_t)((lane & 15) >> 1);
-    // bounds of the frame a stream of quads is in: max |value| (float bits, sign cleared: NaN and inf order above every
-    // finite value), max |x|^2, "some |x|^2 does not fit the split"
+    // bounds of the frame a stream of quads is in: max |x|^2, "some |x|^2 does not fit the split".  (k_tc_convert also
+    // tests every value against 60000; that test is implied by the one on |x|^2: a value above 14143 -- or a NaN / inf --
+    // puts |x|^2 above NORM_MAX = 2e8, or makes it NaN.)
     struct Stats {
-      unsigned amax;
       float wmax;
       int wbad, fi;
     };
     auto flush_bounds = [&](Stats& st) {  // idempotent: a boundary frame is converted by two CTA pairs
       const unsigned mx = __reduce_max_sync(0xffffffffu, __float_as_uint(st.wmax));  // non-negative floats order as uints
-      const unsigned am = __reduce_max_sync(0xffffffffu, st.amax);
       const unsigned bd = __reduce_or_sync(0xffffffffu, (unsigned)st.wbad);
       if (lane == 0) {
         if (mx != 0u) atomicMax(&finfo[u0 + st.fi].max_bits, mx);
-        if (bd || am > __float_as_uint(60000.0f)) atomicOr(&finfo[u0 + st.fi].bad, 1);
+        if (bd) atomicOr(&finfo[u0 + st.fi].bad, 1);
       }
       st.wmax = 0.f;
       st.wbad = 0;
-      st.amax = 0u;
     };
     int cur_i = -1;  // newest frame whose buffer this warp has acquired
     // position of a quad in the stream, advanced by 2 FZ_NCW quads at a time without divisions
@@ -971,31 +969,35 @@ k_tc_seq_fused(const T* __restrict__ L, int K, const int32_t* __restrict__ kc, i
         const uint32_t key = (uint32_t)(e | ((qd & 1) << 2));  // (tr0 + e) & 7
         *reinterpret_cast<uint2*>(dst0 + e * 128 + ((lane_c ^ key) << 4)) = packed;
         sq[e] = (v[e][0] * v[e][0] + v[e][1] * v[e][1]) + (v[e][2] * v[e][2] + v[e][3] * v[e][3]);
-        // range check on the float images (a value fits fp16 iff its float image does; NaN / inf compare above)
-        st.amax = max(st.amax, max(__float_as_uint(f0) & 0x7FFFFFFFu, __float_as_uint(f1) & 0x7FFFFFFFu));
-        st.amax = max(st.amax, max(__float_as_uint(f2) & 0x7FFFFFFFu, __float_as_uint(f3) & 0x7FFFFFFFu));
       }
     };
-    // part 2: |x|^2 of the four rows -- reduce-scatter over lane bits 4 and 3, butterfly over bits 2, 1, 0: lane l ends
-    // with the sum of row l >> 3, every row with the operand pairing of k_tc_convert's butterfly
-    auto reduce = [&](const double (&sq)[FZ_QROWS]) -> double {
-      const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0;
-      const double s0 = b4 ? sq[0] : sq[2], s1 = b4 ? sq[1] : sq[3];
-      const double k0 = b4 ? sq[2] : sq[0], k1 = b4 ? sq[3] : sq[1];
-      const double w0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 16);
-      const double w1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 16);
-      const double s2 = b3 ? w0 : w1, k2 = b3 ? w1 : w0;
-      double t = k2 + __shfl_xor_sync(0xffffffffu, s2, 8);
-      t += __shfl_xor_sync(0xffffffffu, t, 4);
+    // part 2: |x|^2 of the eight rows of two quads (a: rows 0-3, b: rows 4-7) -- reduce-scatter over lane bits 4, 3, 2
+    // (a lane keeps the rows its bits select), butterfly over bits 1, 0: lane l ends with the sum of row
+    // (l >> 2) & 3 of quad l >> 4, every row with the operand pairing of k_tc_convert's xor-16-8-4-2-1 butterfly
+    auto reduce8 = [&](const double (&sa4)[FZ_QROWS], const double (&sb4)[FZ_QROWS]) -> double {
+      const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0, b2 = (lane & 4) != 0;
+      double w[4], u[2];
+#pragma unroll
+      for (int x = 0; x < 4; ++x) {
+        const double snd = b4 ? sa4[x] : sb4[x], kp = b4 ? sb4[x] : sa4[x];
+        w[x] = kp + __shfl_xor_sync(0xffffffffu, snd, 16);
+      }
+#pragma unroll
+      for (int x = 0; x < 2; ++x) {
+        const double snd = b3 ? w[x] : w[x + 2], kp = b3 ? w[x + 2] : w[x];
+        u[x] = kp + __shfl_xor_sync(0xffffffffu, snd, 8);
+      }
+      const double snd = b2 ? u[0] : u[1], kp = b2 ? u[1] : u[0];
+      double t = kp + __shfl_xor_sync(0xffffffffu, snd, 4);
       t += __shfl_xor_sync(0xffffffffu, t, 2);
       t += __shfl_xor_sync(0xffffffffu, t, 1);
       return t;
     };
-    // part 3 (lanes 0, 8, 16, 24: one row each): K-extension row = the exact four-slot split of -|x|^2/2 (k_tc_convert),
+    // part 3 (lanes 0, 4, .. 28: one row each): K-extension row = the exact four-slot split of -|x|^2/2 (k_tc_convert),
     // the norm.  A frame with an out-of-range VALUE is flagged as a whole (flush_bounds): its pairs never use the proposal
-    auto finish = [&](const Pos& q, double t, Stats& st) {
+    auto finish = [&](const Pos& q, double t, float& fn_out, int& bad_out) {
       const int j = q.hq >> 4;
-      const int rl = (q.hq & 15) * FZ_QROWS + (lane >> 3);
+      const int rl = (q.hq & 15) * FZ_QROWS + ((lane >> 2) & 3);
       const int row = j * BLK + 64 * (int)rank + rl;
       const int f = u0 + q.i;
       const int n = kc ? max(0, min(__ldg(kc + f), K)) : K;
@@ -1023,10 +1025,8 @@ k_tc_seq_fused(const T* __restrict__ L, int K, const int32_t* __restrict__ kc, i
       *reinterpret_cast<uint4*>(e0 + ext_off(0, rl, 1)) = make_uint4(0u, 0u, 0u, 0u);
       const float fn = __double2float_ru(t);
       nrm[(size_t)f * FZ_KP + row] = (row < n) ? fn : INFINITY;
-      if (row < n) {
-        st.wmax = fmaxf(st.wmax, fn);
-        st.wbad |= bad ? 1 : 0;
-      }
+      fn_out = row < n ? fn : 0.f;
+      bad_out = (row < n && bad) ? 1 : 0;
     };
     auto arrive = [&](const Pos& q) {
       const uint32_t bar = smem_u32(&bars->f_full[q.i % FZ_NBUF][q.hq >> 4]);
@@ -1038,7 +1038,7 @@ k_tc_seq_fused(const T* __restrict__ L, int K, const int32_t* __restrict__ kc, i
     // rest of the trip (the shuffle chains and the dependent conversions of the split), which the two quads run
     // interleaved.
     double va[FZ_QROWS][4], vb[FZ_QROWS][4];
-    Stats sa{0u, 0.f, 0, -1}, sb{0u, 0.f, 0, -1};
+    Stats sa{0.f, 0, -1}, sb{0.f, 0, -1};
     Pos qa{0, cw}, qb{0, cw};
     qb.advance(FZ_NCW);
     int Q = cw;  // stream index of qa
@@ -1059,11 +1059,16 @@ k_tc_seq_fused(const T* __restrict__ L, int K, const int32_t* __restrict__ kc, i
       }
       qb.advance(2 * FZ_NCW);
       if (Q + 3 * FZ_NCW < total) issue(qb, vb);
-      const double ta = reduce(sqa);
-      const double tb = reduce(sqb);
-      if ((lane & 7) == 0) {
-        finish(ca, ta, sa);
-        if (has_b) finish(cb, tb, sb);
+      const double t = reduce8(sqa, sqb);
+      if ((lane & 3) == 0 && (lane < 16 || has_b)) {  // lanes 0-15 hold the rows of quad a, 16-31 those of quad b
+        Pos cq;
+        cq.i = lane < 16 ? ca.i : cb.i;
+        cq.hq = lane < 16 ? ca.hq : cb.hq;
+        float fn;
+        int bd;
+        finish(cq, t, fn, bd);
+        if (lane < 16) sa.wmax = fmaxf(sa.wmax, fn), sa.wbad |= bd;
+        else sb.wmax = fmaxf(sb.wmax, fn), sb.wbad |= bd;
       }
       // the quads are written: generic-proxy writes -> async proxy, then tell the issuer (CTA-scope release, as every
       // other remote arrive of these kernels: what the arrive publishes are this SM's shared-memory writes, already

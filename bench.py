@@ -785,6 +785,17 @@ def run_ours(args):
             a = match_flops / L / sec / 1e12
             rooflines[name] = {"bound": "fp64", "achieved": a, "peak": None, "unit": "TFLOP/s", "frac": None,
                                "traffic": None, "note": "exact fp64 brute force (3 flop per 2 algorithmic)"}
+        elif name == "match_fused":
+            # conversion + proposal GEMM in one kernel (k_tc_seq_fused): the roofline that bounds it at this shape is HBM
+            # (reading the fp64 descriptors: 0.33 ms at the measured copy rate) -- the tensor floor of its
+            # 2*K1*K2*128 flop per pair is 0.16 ms at the measured bf16 rate
+            a = desc_bytes / L / sec / 1e9  # every descriptor set read once (class double: 8 B per value); nothing written back
+            tf = match_flops / L / sec / 1e12
+            rooflines[name] = {"bound": "hbm", "achieved": a, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                               "frac": a / pk["hbm_gbs"], "traffic": None,
+                               "tensor_tflops": tf, "tensor_frac": tf / pk["bf16_tflops"],
+                               "note": f"algorithmic bytes = the descriptor sets of the sequence read once; of {pk['source']}; "
+                                       "the same launch also does the 2*K1*K2*128 flop per pair (tensor_tflops)"}
         elif name == "convert":
             a = desc_bytes * 1.25 / L / sec / 1e9  # read f64 descriptors + write the f16 operand image
             rooflines[name] = {"bound": "hbm", "achieved": a, "peak": pk["hbm_gbs"], "unit": "GB/s",
@@ -798,7 +809,7 @@ def run_ours(args):
         tr = json.load(open(tpath))["per_pair_bytes"]
         for name in rooflines:
             if name in tr:
-                units = (Pl + 1) if name == "convert" else Pl  # convert: bytes per descriptor set (frame)
+                units = (Pl + 1) if name in ("convert", "match_fused") else Pl  # bytes per descriptor set (frame)
                 rooflines[name]["traffic"] = tr[name]["bytes"] * units
                 rooflines[name]["traffic_note"] = "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch " \
                                                   f"({os.path.basename(tpath)}, per pair) x pairs per launch"
@@ -933,7 +944,8 @@ def run_ours(args):
                        "l2": f"inputs ({desc_bytes / 1e9:.2f} GB of descriptors per GPU) "
                              + ("larger than L2" if desc_bytes > 126e6 else "smaller than L2: at this GPU count the step "
                                 "re-reads them from L2"),
-                       "match_engine": "tcgen05 CTA-pair proposal + exact rescore" if "match_tc" in per_kernel
+                       "match_engine": "tcgen05 CTA-pair proposal (conversion fused into the GEMM kernel) + exact rescore" if "match_fused" in per_kernel
+                       else "tcgen05 CTA-pair proposal + exact rescore" if "match_tc" in per_kernel
                        else "exact fp64 brute force",
                        "weak_scaling": weak, "other_configs": other_cfg},
             "e2e": {"value": e2e_val, "unit": "frame-pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
