@@ -841,7 +841,7 @@ __device__ __forceinline__ void mbar_arrive_release_cluster(uint32_t cluster_add
 template <typename T>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FZ_THREADS, 1)
 k_tc_seq_fused(const T* __restrict__ L, int K, const int32_t* __restrict__ kc, int P, int ext_layout,
-               float* __restrict__ nrm, FrameInfo* __restrict__ finfo, Prop2* __restrict__ prop) {
+               float* __restrict__ nrm, FrameInfo* __restrict__ finfo, Prop2* __restrict__ prop, int pf_quads) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t base = smem_u32(smem);
   if (base & 1023u) __trap();
@@ -891,11 +891,10 @@ k_tc_seq_fused(const T* __restrict__ L, int K, const int32_t* __restrict__ kc, i
     // ===== converters: frame u0 + i -> buffer i % 3, this CTA's 64 rows of every 128-row block ========
     // Work item = a quad of 4 rows (1 KB each: lane l holds elements 4l .. 4l+3).  The loads of the next quad are in
     // flight while the current one is converted (two register sets), across tile and frame boundaries; only the
-    // shared-memory writes wait for the buffer.  |x|^2: the per-lane partial sums of the four rows are reduced
-    // together -- the xor-16 and xor-8 steps of k_tc_convert's butterfly as a reduce-scatter (a lane keeps the rows its
-    // lane bits select), then xor 4, 2, 1 -- so every row's sum has the operand pairing of k_tc_convert (a + b is
-    // commutative: the same bits) and lane l ends with the norm of row (l >> 3) & 3; lanes 0, 8, 16, 24 then write the
-    // K-extension rows and the norms of their rows in parallel.
+    // shared-memory writes wait for the buffer.  |x|^2 (fp32, see `convert`): the per-lane partial sums of the rows of
+    // two quads are reduced together -- the xor-16, 8 and 4 steps of the butterfly as a reduce-scatter (a lane keeps the
+    // rows its lane bits select), then xor 2, 1 -- and lane l ends with the norm of row (l >> 2) & 3 of quad l >> 4;
+    // lanes 0, 4, .. 28 then write the K-extension rows and the norms of their rows in parallel.
     const int cw = warp - FZ_W_CONV;
     const int total = (npairs + 1) * FZ_FQUADS;  // quads of this CTA's stream; warp cw takes quads cw, cw + NCW, ...
     // this lane's byte offset inside a 128-byte image row group: K half, swizzled 16-byte chunk, 8-byte half of it
@@ -936,6 +935,18 @@ k_tc_seq_fused(const T* __restrict__ L, int K, const int32_t* __restrict__ kc, i
       const int n = kc ? max(0, min(__ldg(kc + f), K)) : K;
       const int row0 = (q.hq >> 4) * BLK + 64 * (int)rank + (q.hq & 15) * FZ_QROWS;
       const T* src = L + ((size_t)f * K + row0) * ND + 4 * lane;
+      // ablation (PRE3_FZ_PF, off by default: measured slower): the quad this warp converts pf_quads later (a multiple
+      // of 2 FZ_NCW: the same warp, the same stream) is asked into L2 by one bulk prefetch of its 4 contiguous rows
+      if (pf_quads > 0 && lane == 0) {
+        Pos qp = q;
+        qp.advance(pf_quads);
+        if (qp.hq >= FZ_FQUADS) qp.hq -= FZ_FQUADS, ++qp.i;
+        const int rowp = (qp.hq >> 4) * BLK + 64 * (int)rank + (qp.hq & 15) * FZ_QROWS;
+        if (qp.i <= npairs && rowp + FZ_QROWS <= K) {
+          const T* pa = L + ((size_t)(u0 + qp.i) * K + rowp) * ND;
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pa), "r"((uint32_t)(FZ_QROWS * ND * sizeof(T))) : "memory");
+        }
+      }
 #pragma unroll
       for (int e = 0; e < FZ_QROWS; ++e) {
         v[e][0] = v[e][1] = v[e][2] = v[e][3] = 0.0;
@@ -949,8 +960,15 @@ k_tc_seq_fused(const T* __restrict__ L, int K, const int32_t* __restrict__ kc, i
         tc_fence_after();
       }
     };
-    // part 1 of a quad: fp16 image rows into the buffer, this lane's partial |x|^2 of the four rows; frees the raw values
-    auto convert = [&](const Pos& q, double (&v)[FZ_QROWS][4], double (&sq)[FZ_QROWS], Stats& st) {
+    // part 1 of a quad: fp16 image rows into the buffer, this lane's partial |x|^2 of the four rows; frees the raw values.
+    // |x|^2 is summed in FP32 from the float-rounded values (the ones the fp16 image is made of): FMA-pipe instructions
+    // instead of 7 per row on the fp64 pipe, 32-bit shuffles, 4-cycle dependent adds.  ncu of the fp64 form
+    // (profiles/r02_g_fused_source.md): the converter warps were never waiting for memory (long scoreboard 3 % of their
+    // samples) -- they were busy, a third of the time throttled on the fp64 pipe, and the MMA issuer waited for them.
+    // Error of the fp32 sum: the input rounding (2^-23 on x^2), one rounding per product and per level of the pairwise
+    // tree (2 in the lane + 5 shuffle levels; all terms are non-negative, so every partial sum is below the total):
+    // |t - |x|^2| <= 2^-20 |x|^2, carried by the rescore's bound (rescore_group / rescore_decide).
+    auto convert = [&](const Pos& q, double (&v)[FZ_QROWS][4], float (&sq)[FZ_QROWS], Stats& st) {
       if (q.i != st.fi) {
         if (st.fi >= 0) flush_bounds(st);
         st.fi = q.i;
@@ -968,50 +986,51 @@ k_tc_seq_fused(const T* __restrict__ L, int K, const int32_t* __restrict__ kc, i
         packed.y = *reinterpret_cast<unsigned*>(&h23);
         const uint32_t key = (uint32_t)(e | ((qd & 1) << 2));  // (tr0 + e) & 7
         *reinterpret_cast<uint2*>(dst0 + e * 128 + ((lane_c ^ key) << 4)) = packed;
-        sq[e] = (v[e][0] * v[e][0] + v[e][1] * v[e][1]) + (v[e][2] * v[e][2] + v[e][3] * v[e][3]);
+        sq[e] = __fadd_rn(__fmaf_rn(f0, f0, __fmul_rn(f1, f1)), __fmaf_rn(f2, f2, __fmul_rn(f3, f3)));
       }
     };
     // part 2: |x|^2 of the eight rows of two quads (a: rows 0-3, b: rows 4-7) -- reduce-scatter over lane bits 4, 3, 2
     // (a lane keeps the rows its bits select), butterfly over bits 1, 0: lane l ends with the sum of row
-    // (l >> 2) & 3 of quad l >> 4, every row with the operand pairing of k_tc_convert's xor-16-8-4-2-1 butterfly
-    auto reduce8 = [&](const double (&sa4)[FZ_QROWS], const double (&sb4)[FZ_QROWS]) -> double {
+    // (l >> 2) & 3 of quad l >> 4, a pairwise tree over the 32 lanes
+    auto reduce8 = [&](const float (&sa4)[FZ_QROWS], const float (&sb4)[FZ_QROWS]) -> float {
       const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0, b2 = (lane & 4) != 0;
-      double w[4], u[2];
+      float w[4], u[2];
 #pragma unroll
       for (int x = 0; x < 4; ++x) {
-        const double snd = b4 ? sa4[x] : sb4[x], kp = b4 ? sb4[x] : sa4[x];
-        w[x] = kp + __shfl_xor_sync(0xffffffffu, snd, 16);
+        const float snd = b4 ? sa4[x] : sb4[x], kp = b4 ? sb4[x] : sa4[x];
+        w[x] = __fadd_rn(kp, __shfl_xor_sync(0xffffffffu, snd, 16));
       }
 #pragma unroll
       for (int x = 0; x < 2; ++x) {
-        const double snd = b3 ? w[x] : w[x + 2], kp = b3 ? w[x + 2] : w[x];
-        u[x] = kp + __shfl_xor_sync(0xffffffffu, snd, 8);
+        const float snd = b3 ? w[x] : w[x + 2], kp = b3 ? w[x + 2] : w[x];
+        u[x] = __fadd_rn(kp, __shfl_xor_sync(0xffffffffu, snd, 8));
       }
-      const double snd = b2 ? u[0] : u[1], kp = b2 ? u[1] : u[0];
-      double t = kp + __shfl_xor_sync(0xffffffffu, snd, 4);
-      t += __shfl_xor_sync(0xffffffffu, t, 2);
-      t += __shfl_xor_sync(0xffffffffu, t, 1);
+      const float snd = b2 ? u[0] : u[1], kp = b2 ? u[1] : u[0];
+      float t = __fadd_rn(kp, __shfl_xor_sync(0xffffffffu, snd, 4));
+      t = __fadd_rn(t, __shfl_xor_sync(0xffffffffu, t, 2));
+      t = __fadd_rn(t, __shfl_xor_sync(0xffffffffu, t, 1));
       return t;
     };
-    // part 3 (lanes 0, 4, .. 28: one row each): K-extension row = the exact four-slot split of -|x|^2/2 (k_tc_convert),
-    // the norm.  A frame with an out-of-range VALUE is flagged as a whole (flush_bounds): its pairs never use the proposal
-    auto finish = [&](const Pos& q, double t, float& fn_out, int& bad_out) {
+    // part 3 (lanes 0, 4, .. 28: one row each): K-extension row = the exact four-slot split of -t/2 (the split of
+    // k_tc_convert in fp32: t has 24 bits, every residual is exact), the norm t itself.  A frame with an out-of-range
+    // VALUE is flagged as a whole (flush_bounds): its pairs never use the proposal
+    auto finish = [&](const Pos& q, float t, float& fn_out, int& bad_out) {
       const int j = q.hq >> 4;
       const int rl = (q.hq & 15) * FZ_QROWS + ((lane >> 2) & 3);
       const int row = j * BLK + 64 * (int)rank + rl;
       const int f = u0 + q.i;
       const int n = kc ? max(0, min(__ldg(kc + f), K)) : K;
-      const bool bad = !(t <= NORM_MAX);
+      const bool bad = !(t <= (float)NORM_MAX);
       __half h[4];
       if (row < n && !bad) {
-        double gq = -0.5 * t;
-        h[0] = __double2half(gq * (1.0 / 4096.0));
-        gq = gq - 4096.0 * (double)__half2float(h[0]);
-        h[1] = __double2half(gq * (1.0 / 4096.0));
-        gq = gq - 4096.0 * (double)__half2float(h[1]);
-        h[2] = __double2half(gq);
-        gq = gq - (double)__half2float(h[2]);
-        h[3] = __double2half(gq);
+        float gq = -0.5f * t;
+        h[0] = __float2half_rn(gq * (1.0f / 4096.0f));
+        gq = __fmaf_rn(-4096.0f, __half2float(h[0]), gq);
+        h[1] = __float2half_rn(gq * (1.0f / 4096.0f));
+        gq = __fmaf_rn(-4096.0f, __half2float(h[1]), gq);
+        h[2] = __float2half_rn(gq);
+        gq = __fsub_rn(gq, __half2float(h[2]));
+        h[3] = __float2half_rn(gq);
       } else {
         h[0] = __float2half(-60000.0f);
         h[1] = h[2] = h[3] = __float2half(0.0f);
@@ -1023,9 +1042,8 @@ k_tc_seq_fused(const T* __restrict__ L, int K, const int32_t* __restrict__ kc, i
       unsigned char* e0 = smem + (q.i % FZ_NBUF) * FZ_BUF_BYTES + FZ_IMG_BYTES + j * P2_BEXT;  // SWIZZLE_32B rows (ext_off)
       *reinterpret_cast<uint4*>(e0 + ext_off(0, rl, 0)) = w;
       *reinterpret_cast<uint4*>(e0 + ext_off(0, rl, 1)) = make_uint4(0u, 0u, 0u, 0u);
-      const float fn = __double2float_ru(t);
-      nrm[(size_t)f * FZ_KP + row] = (row < n) ? fn : INFINITY;
-      fn_out = row < n ? fn : 0.f;
+      nrm[(size_t)f * FZ_KP + row] = (row < n) ? t : INFINITY;
+      fn_out = row < n ? t : 0.f;
       bad_out = (row < n && bad) ? 1 : 0;
     };
     auto arrive = [&](const Pos& q) {
@@ -1048,7 +1066,7 @@ k_tc_seq_fused(const T* __restrict__ L, int K, const int32_t* __restrict__ kc, i
     for (; Q < total; Q += 2 * FZ_NCW) {
       const bool has_b = Q + FZ_NCW < total;
       const Pos ca = qa, cb = qb;
-      double sqa[FZ_QROWS], sqb[FZ_QROWS] = {0.0, 0.0, 0.0, 0.0};
+      float sqa[FZ_QROWS], sqb[FZ_QROWS] = {0.f, 0.f, 0.f, 0.f};
       acquire(ca);
       convert(ca, va, sqa, sa);
       qa.advance(2 * FZ_NCW);
@@ -1059,7 +1077,7 @@ k_tc_seq_fused(const T* __restrict__ L, int K, const int32_t* __restrict__ kc, i
       }
       qb.advance(2 * FZ_NCW);
       if (Q + 3 * FZ_NCW < total) issue(qb, vb);
-      const double t = reduce8(sqa, sqb);
+      const float t = reduce8(sqa, sqb);
       if ((lane & 3) == 0 && (lane < 16 || has_b)) {  // lanes 0-15 hold the rows of quad a, 16-31 those of quad b
         Pos cq;
         cq.i = lane < 16 ? ca.i : cb.i;
@@ -1278,8 +1296,10 @@ __device__ __forceinline__ void rescore_group(ACC (*sprod)[ND + 1], int p, int r
     const double ra = sqrt(na), rbm = sqrt(nbm);
     m = 1.25 * ((1.0 / 512 + 1.0 / 16384) * ra * rbm + (na + nbm + C) * (1.0 / 16384) + (ra + rbm) * (1.0 / 1048576));
     // CTA-pair proposal: d2~ = |a|^2 - 2 s with s = a~.b~ - |b|^2/2 accumulated in the contraction (the fp16 split of
-    // the norm is exact down to 2^-25 absolute, the 7 replaced key bits of s cost |s| 2^-16 <= (na + nbm) 2^-16)
-    if (v2) m = 1.25 * ((1.0 / 512 + 1.0 / 16384) * ra * rbm + (na + nbm) * (1.0 / 16384) + (ra + rbm) * (1.0 / 1048576) + 1.0 / 4194304);
+    // the norm is exact down to 2^-25 absolute, the 7 replaced key bits of s cost |s| 2^-16 <= (na + nbm) 2^-16).
+    // k_tc_seq_fused sums |x|^2 in fp32 from the float-rounded values: both norms are within 2^-20 relative of the
+    // exact ones (derivation at its `convert`), the (na + nbm) 2^-19 term
+    if (v2) m = 1.25 * ((1.0 / 512 + 1.0 / 16384) * ra * rbm + (na + nbm) * (1.0 / 16384 + 1.0 / 524288) + (ra + rbm) * (1.0 / 1048576) + 1.0 / 4194304);
     const bool keys_ok = v2 ? (my.best > -INFINITY) : ((C - na > m) && (my.best < INFINITY));
     if (pi.bad || my.idx < 0 || my.idx >= n2 || !(thresh > 0.f) || !keys_ok) {
       ambiguous = true;  // keys may be meaningless (range, sign) -> exact kernel
@@ -1428,7 +1448,7 @@ __device__ __forceinline__ RsDecision rescore_decide(int p, int pa, int k1, int 
   const double nbm = (double)__uint_as_float(pi.bmax_bits);
   const double ra = sqrt(na), rbm = sqrt(nbm);
   // error bound of the CTA-pair proposal (see rescore_group)
-  const double m = 1.25 * ((1.0 / 512 + 1.0 / 16384) * ra * rbm + (na + nbm) * (1.0 / 16384) + (ra + rbm) * (1.0 / 1048576) + 1.0 / 4194304);
+  const double m = 1.25 * ((1.0 / 512 + 1.0 / 16384) * ra * rbm + (na + nbm) * (1.0 / 16384 + 1.0 / 524288) + (ra + rbm) * (1.0 / 1048576) + 1.0 / 4194304);
   d.na = na;
   d.m = m;
   if (pi.bad || d.my.idx < 0 || d.my.idx >= n2 || !(thresh > 0.f) || !(d.my.best > -INFINITY)) {
@@ -1624,6 +1644,11 @@ int launch_match_tc(pre3_ctx* ctx, const void* dL1, const void* dL2, int cls, in
     {
       Span span__(ctx, T_MATCH_FUSED);
       const int grid = 2 * std::min(P, ctx->sm_count / 2);
+      // L2 prefetch distance of the converters in trips of 2 FZ_NCW quads (PRE3_FZ_PF).  Off: measured 0.602 ms per
+      // 4096 pairs without, 0.634 / 0.638 / 0.650 / 0.685 ms at 2 / 4 / 6 / 9 trips (profiles/r02_fused_prefetch.log) --
+      // the converters are not what the kernel waits for
+      static const int pf_trips = getenv("PRE3_FZ_PF") ? atoi(getenv("PRE3_FZ_PF")) : 0;
+      const int pf_quads = std::max(0, std::min(pf_trips, 9)) * 2 * FZ_NCW;
 #define PRE3_FUSED(T)                                                                                                \
   do {                                                                                                               \
     static bool attr_done = false;                                                                                   \
@@ -1632,7 +1657,7 @@ int launch_match_tc(pre3_ctx* ctx, const void* dL1, const void* dL2, int cls, in
       attr_done = true;                                                                                              \
     }                                                                                                                \
     k_tc_seq_fused<T><<<grid, FZ_THREADS, FZ_SMEM_BYTES, ctx->stream>>>((const T*)dL1, K1, dk1, P, ext_layout, nrmA, fa, \
-                                                                       reinterpret_cast<Prop2*>(prop));             \
+                                                                       reinterpret_cast<Prop2*>(prop), pf_quads);   \
   } while (0)
       if (cls == PRE3_CLASS_DOUBLE) PRE3_FUSED(double);
       else PRE3_FUSED(float);

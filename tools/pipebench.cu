@@ -73,6 +73,44 @@ __global__ void __launch_bounds__(1024, 1) k_op2(float2* out, float2 a, float2 b
   out[blockIdx.x * 1024 + threadIdx.x] = s;
 }
 
+// fp64 pipe and the 64-bit conversions the fused sequence matcher's converter warps are made of: 4 chains per thread,
+// THREADS / 128 warps per sub-partition (the converters run 2 per sub-partition)
+template <int OP, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) k_opd(double* out, double a, double b) {
+  double v[4];
+  uint32_t acc = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = threadIdx.x * 0.001 + i;
+  for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (OP == 0) asm volatile("mul.rn.f64 %0, %0, %1;" : "+d"(v[i]) : "d"(a));
+      if (OP == 1) asm volatile("add.rn.f64 %0, %0, %1;" : "+d"(v[i]) : "d"(a));
+      if (OP == 2) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(v[i]) : "d"(a), "d"(b));
+      if (OP == 3) {
+        uint32_t f;
+        asm volatile("cvt.rn.f32.f64 %0, %1;" : "=r"(f) : "d"(v[i]));
+        acc ^= f;
+      }
+      if (OP == 4) {
+        uint16_t h;
+        asm volatile("cvt.rn.f16.f64 %0, %1;" : "=h"(h) : "d"(v[i]));
+        acc ^= h;
+      }
+      if (OP == 5) {
+        double d;
+        asm volatile("cvt.f64.f32 %0, %1;" : "=d"(d) : "r"(acc + i));
+        acc ^= (uint32_t)__double_as_longlong(d);
+      }
+    }
+    a += 1.0e-9;
+  }
+  double s = (double)acc;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) s += v[i];
+  out[blockIdx.x * THREADS + threadIdx.x] = s;
+}
+
 template <typename F>
 static void run(const char* name, F launch, double ops_per_thread) {
   cudaEvent_t e0, e1;
@@ -117,5 +155,17 @@ int main() {
   run("FADD2 (packed, per instr)", [&]() { k_op2<0><<<148, 1024>>>((float2*)out, make_float2(1.0f, 2.0f), make_float2(0.5f, 0.25f)); }, n2);
   run("FFMA2 (packed, per instr)", [&]() { k_op2<1><<<148, 1024>>>((float2*)out, make_float2(1.0f, 0.99f), make_float2(0.5f, 0.25f)); }, n2);
   run("FMUL2 (packed, per instr)", [&]() { k_op2<2><<<148, 1024>>>((float2*)out, make_float2(1.0f, 0.99f), make_float2(0.5f, 0.25f)); }, n2);
+  // run() assumes 1024 threads per SM: scale the per-thread count by THREADS / 1024
+#define RUND(OP, T, NAME) run(NAME, [&]() { k_opd<OP, T><<<148, T>>>((double*)out, 1.0000001, 0.5); }, n2 * T / 1024.0)
+  RUND(0, 1024, "DMUL 8 warps/SMSP");
+  RUND(0, 256, "DMUL 2 warps/SMSP");
+  RUND(1, 1024, "DADD 8 warps/SMSP");
+  RUND(1, 256, "DADD 2 warps/SMSP");
+  RUND(2, 1024, "DFMA 8 warps/SMSP");
+  RUND(2, 256, "DFMA 2 warps/SMSP");
+  RUND(3, 1024, "F2F.F32.F64 (+LOP3) 8 warps/SMSP");
+  RUND(3, 256, "F2F.F32.F64 (+LOP3) 2 warps/SMSP");
+  RUND(4, 1024, "F2F.F16.F64 (+LOP3) 8 warps/SMSP");
+  RUND(5, 1024, "F2F.F64.F32 (+2 ALU) 8 warps/SMSP");
   return 0;
 }
