@@ -841,7 +841,7 @@ __device__ __forceinline__ void mbar_arrive_release_cluster(uint32_t cluster_add
 template <typename T>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FZ_THREADS, 1)
 k_tc_seq_fused(const T* __restrict__ L, int K, const int32_t* __restrict__ kc, int P, int ext_layout,
-               float* __restrict__ nrm, FrameInfo* __restrict__ finfo, Prop2* __restrict__ prop, int pf_quads) {
+               float* __restrict__ nrm, FrameInfo* __restrict__ finfo, Prop2* __restrict__ prop) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t base = smem_u32(smem);
   if (base & 1023u) __trap();
@@ -930,27 +930,31 @@ k_tc_seq_fused(const T* __restrict__ L, int K, const int32_t* __restrict__ kc, i
         }
       }
     };
-    auto issue = [&](const Pos& q, double (&v)[FZ_QROWS][4]) {
-      const int f = u0 + q.i;
-      const int n = kc ? max(0, min(__ldg(kc + f), K)) : K;
-      const int row0 = (q.hq >> 4) * BLK + 64 * (int)rank + (q.hq & 15) * FZ_QROWS;
-      const T* src = L + ((size_t)f * K + row0) * ND + 4 * lane;
-      // ablation (PRE3_FZ_PF, off by default: measured slower): the quad this warp converts pf_quads later (a multiple
-      // of 2 FZ_NCW: the same warp, the same stream) is asked into L2 by one bulk prefetch of its 4 contiguous rows
-      if (pf_quads > 0 && lane == 0) {
-        Pos qp = q;
-        qp.advance(pf_quads);
-        if (qp.hq >= FZ_FQUADS) qp.hq -= FZ_FQUADS, ++qp.i;
-        const int rowp = (qp.hq >> 4) * BLK + 64 * (int)rank + (qp.hq & 15) * FZ_QROWS;
-        if (qp.i <= npairs && rowp + FZ_QROWS <= K) {
-          const T* pa = L + ((size_t)(u0 + qp.i) * K + rowp) * ND;
-          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pa), "r"((uint32_t)(FZ_QROWS * ND * sizeof(T))) : "memory");
-        }
+    // valid rows of frame u0 + i (kc: per-frame descriptor counts), looked up once per frame
+    int nf_i = -1, nf_n = K;
+    auto frame_rows = [&](int i) -> int {
+      if (kc && i != nf_i) {
+        nf_i = i;
+        nf_n = max(0, min(__ldg(kc + u0 + i), K));
       }
+      return nf_n;
+    };
+    // (An L2 bulk prefetch of the quad a warp converts 2 .. 9 trips later was tried here and measured slower at every
+    // distance, 0.602 -> 0.634 .. 0.685 ms per 4096 pairs, profiles/r02_fused_prefetch.log: the converters do not wait
+    // for memory.)
+    auto issue = [&](const Pos& q, double (&v)[FZ_QROWS][4]) {
+      const int n = frame_rows(q.i);
+      const int row0 = (q.hq >> 4) * BLK + 64 * (int)rank + (q.hq & 15) * FZ_QROWS;
+      const T* src = L + ((size_t)(u0 + q.i) * K + row0) * ND + 4 * lane;
+      if (row0 + FZ_QROWS <= n) {  // the usual quad: all four rows exist, no predicates, nothing to clear
 #pragma unroll
-      for (int e = 0; e < FZ_QROWS; ++e) {
-        v[e][0] = v[e][1] = v[e][2] = v[e][3] = 0.0;
-        if (row0 + e < n) load4(src + (size_t)e * ND, v[e]);
+        for (int e = 0; e < FZ_QROWS; ++e) load4(src + (size_t)e * ND, v[e]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < FZ_QROWS; ++e) {
+          v[e][0] = v[e][1] = v[e][2] = v[e][3] = 0.0;
+          if (row0 + e < n) load4(src + (size_t)e * ND, v[e]);
+        }
       }
     };
     auto acquire = [&](const Pos& q) {  // first write of this warp into the buffer for frame q.i: the pair that used it as A must be done
@@ -1019,7 +1023,7 @@ k_tc_seq_fused(const T* __restrict__ L, int K, const int32_t* __restrict__ kc, i
       const int rl = (q.hq & 15) * FZ_QROWS + ((lane >> 2) & 3);
       const int row = j * BLK + 64 * (int)rank + rl;
       const int f = u0 + q.i;
-      const int n = kc ? max(0, min(__ldg(kc + f), K)) : K;
+      const int n = frame_rows(q.i);
       const bool bad = !(t <= (float)NORM_MAX);
       __half h[4];
       if (row < n && !bad) {
@@ -1644,11 +1648,6 @@ int launch_match_tc(pre3_ctx* ctx, const void* dL1, const void* dL2, int cls, in
     {
       Span span__(ctx, T_MATCH_FUSED);
       const int grid = 2 * std::min(P, ctx->sm_count / 2);
-      // L2 prefetch distance of the converters in trips of 2 FZ_NCW quads (PRE3_FZ_PF).  Off: measured 0.602 ms per
-      // 4096 pairs without, 0.634 / 0.638 / 0.650 / 0.685 ms at 2 / 4 / 6 / 9 trips (profiles/r02_fused_prefetch.log) --
-      // the converters are not what the kernel waits for
-      static const int pf_trips = getenv("PRE3_FZ_PF") ? atoi(getenv("PRE3_FZ_PF")) : 0;
-      const int pf_quads = std::max(0, std::min(pf_trips, 9)) * 2 * FZ_NCW;
 #define PRE3_FUSED(T)                                                                                                \
   do {                                                                                                               \
     static bool attr_done = false;                                                                                   \
@@ -1657,7 +1656,7 @@ int launch_match_tc(pre3_ctx* ctx, const void* dL1, const void* dL2, int cls, in
       attr_done = true;                                                                                              \
     }                                                                                                                \
     k_tc_seq_fused<T><<<grid, FZ_THREADS, FZ_SMEM_BYTES, ctx->stream>>>((const T*)dL1, K1, dk1, P, ext_layout, nrmA, fa, \
-                                                                       reinterpret_cast<Prop2*>(prop), pf_quads);   \
+                                                                       reinterpret_cast<Prop2*>(prop));             \
   } while (0)
       if (cls == PRE3_CLASS_DOUBLE) PRE3_FUSED(double);
       else PRE3_FUSED(float);
