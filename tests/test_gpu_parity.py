@@ -517,6 +517,57 @@ def test_fused_sequence_matcher_equals_separate_kernels(pre3, synth, cls, K, P):
         np.testing.assert_array_equal(out["1"][2][p, :n], out["0"][2][p, :n])
 
 
+@pytest.mark.parametrize("scale", [1.0, 512.0])
+@pytest.mark.parametrize("ratio", [1.5, 1.0000001])
+def test_fused_sequence_matcher_adversarial_vs_reference(pre3, orc, scale, ratio):
+    """The matches of k_tc_seq_fused (fp16 proposal, |x|^2 summed in fp32, certified rescore) against the reference
+    siftmatch on frames built to sit on the decisions: a frame holds exact copies of the previous frame's descriptors,
+    copies perturbed by 1e-4 and 1e-7 (best / second best a few ulps of the proposal apart, ratios at the threshold),
+    duplicated columns (first index wins), zero rows; at unit norm and at the uint8 scale (integer-valued doubles up to
+    ~150, |x|^2 ~ 2.6e5, where the fp32 norm is off by up to 0.25 absolute)."""
+    import torch
+    rng = np.random.default_rng(77)
+    F, K = 6, 512
+    base = np.abs(rng.normal(size=(K, 128)))
+    base /= np.linalg.norm(base, axis=1, keepdims=True)
+    frames = [base]
+    for f in range(1, F):
+        prev = frames[-1]
+        cur = np.abs(rng.normal(size=(K, 128)))
+        cur /= np.linalg.norm(cur, axis=1, keepdims=True)
+        perm = rng.permutation(K)
+        cur[perm[:128]] = prev[:128]                                             # exact copies (distance 0)
+        cur[perm[128:256]] = prev[128:256] + 1e-4 * rng.normal(size=(128, 128))  # near copies
+        cur[perm[256:320]] = prev[:64] * (1 + 1e-7)                              # second copy of rows that already have one
+        cur[perm[320:336]] = cur[perm[0:16]]                                     # duplicated columns
+        cur[perm[336:340]] = 0.0
+        frames.append(cur)
+    desc = np.stack(frames)
+    if scale != 1.0:
+        desc = np.rint(desc * scale)
+    desc = desc.astype(np.float32).astype(np.float64)
+    xyz = rng.normal(size=(F, K, 3)) + np.array([0.0, 0.0, 3.0])
+    P = F - 1
+    opts = pre3.make_opts(H=64, ratio=ratio, seed=5)
+    ctx = pre3.Context(0)
+    try:
+        ctx.set_match_engine(1)
+        r = torch.zeros(P, 240, dtype=torch.uint8, device="cuda")
+        m = torch.zeros(P, K, 2, dtype=torch.int32, device="cuda")
+        k = torch.zeros(P, K, dtype=torch.uint8, device="cuda")
+        ctx.sequence_dev(torch.from_numpy(desc).cuda(), torch.from_numpy(xyz).cuda(), opts, r, m, k)
+        ctx.sync()
+        rec = np.frombuffer(r.cpu().numpy().tobytes(), dtype=pre3.RESULT_DTYPE)
+        mm = m.cpu().numpy()
+    finally:
+        ctx.close()
+    for p in range(P):
+        op, _ = orc.siftmatch(desc[p], desc[p + 1], ratio)
+        n = int(rec["n_matches"][p])
+        assert n == len(op) and n >= 64  # at least the rows with a single exact copy are matched
+        np.testing.assert_array_equal(mm[p, :n], op)
+
+
 def test_graph_replay_equals_eager(pre3, synth):
     """pre3_set_graphs: the captured launch sequence of a repeated pre3_sequence_dev signature gives the same bytes as
     the eager calls, also after the inputs behind the same pointers changed; a new signature falls back to eager."""
