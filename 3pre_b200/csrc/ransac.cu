@@ -925,21 +925,31 @@ k_sel_scan(const PairMeta* __restrict__ meta, int Nmax, int H, int k, int method
   }
 }
 
-// the fit of sample set s of pair p if k_eval_pairloop kept it (fc == nullptr: no cache in this call)
-__device__ __forceinline__ bool fit_cached(const FitCacheEntry* __restrict__ fc, const int32_t* __restrict__ fcn, int p,
-                                           int s, Rigid& f) {
+// The fit of sample set s of pair p if k_eval_pairloop kept it (fc == nullptr: no cache in this call), looked up by a
+// GROUP of G lanes (a power of two; all lanes of the warp call it, the lanes of a group with the same p and s): lane `sub`
+// of the group tests entries sub, sub + G, ... -- their loads are independent, where a one-thread loop walks up to 24
+// cache lines one after the other (ncu source page: 6-10 % of the selection kernels' samples) -- and the first matching
+// entry in list order is taken.
+template <int G>
+__device__ __forceinline__ bool fit_cached_group(const FitCacheEntry* __restrict__ fc, const int32_t* __restrict__ fcn,
+                                                 int p, int s, int sub, Rigid& f) {
   if (!fc) return false;
   const int n = min(fcn[p], FIT_CACHE_CAP);
   const FitCacheEntry* e = fc + (size_t)p * FIT_CACHE_CAP;
-  for (int j = 0; j < n; ++j)
-    if (e[j].h == s) {
+  int found = 0x7fffffff;
 #pragma unroll
-      for (int i = 0; i < 9; ++i) f.R[i] = e[j].Rt[i];
+  for (int r = 0; r < (FIT_CACHE_CAP + G - 1) / G; ++r) {
+    const int j = r * G + sub;
+    if (j < n && e[j].h == s) found = min(found, j);
+  }
 #pragma unroll
-      for (int i = 0; i < 3; ++i) f.t[i] = e[j].Rt[9 + i];
-      return true;
-    }
-  return false;
+  for (int off = G / 2; off > 0; off >>= 1) found = min(found, __shfl_xor_sync(0xffffffffu, found, off, G));
+  if (found == 0x7fffffff) return false;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) f.R[i] = e[found].Rt[i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) f.t[i] = e[found].Rt[9 + i];
+  return true;
 }
 
 constexpr int TIE_THREADS = 128;
@@ -1012,7 +1022,7 @@ k_sel_tie_quad(const PairMeta* __restrict__ meta, const double* __restrict__ Ya,
     const double* ya = Ya + (size_t)p * Nmax * 3;
     const double* yb = Yb + (size_t)p * Nmax * 3;
     Rigid f;
-    if (!fit_cached(fcache, fcache_n, p, s, f)) {
+    if (!fit_cached_group<G>(fcache, fcache_n, p, s, sub, f)) {
       int idx[MAX_K];
       load_sample(samples, seed, pair_id0 + (uint32_t)p, h0, s, H, p, max(m.N, 1), k, idx);
       fit_sample(method, ya, yb, idx, k, f);
@@ -1171,12 +1181,26 @@ k_sel_final(const PairMeta* __restrict__ meta, const double* __restrict__ Ya, co
 
   // ---- winner: hypothesis, mask, ErrorSum; refit on the support set (:186) --------------------------
   Rigid f;
-  if (!fit_cached(fcache, fcache_n, p, win, f)) {
+  if (!fit_cached_group<32>(fcache, fcache_n, p, win, lane, f)) {
     int idx[MAX_K];
     load_sample(samples, seed, pair_id0 + (uint32_t)p, h0, win, H, p, N, k, idx);
     fit_sample(method, ya, yb, idx, k, f);  // every thread computes the same fit
   }
-  for (int i = tid; i < N; i += NT) mask[i] = residual_norm(f.R, f.t, ya + 3 * i, yb + 3 * i) < m.thr ? 1 : 0;
+  for (int i = tid; i < N; i += 4 * NT) {  // four correspondences per trip: their loads are in flight together
+    double ra[4][3], rb[4][3];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int iu = min(i + u * NT, N - 1);
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        ra[u][r] = ya[3 * iu + r];
+        rb[u][r] = yb[3 * iu + r];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i + u * NT < N) mask[i + u * NT] = residual_norm(f.R, f.t, ra[u], rb[u]) < m.thr ? 1 : 0;
+  }
   if (masks)
     for (int i = N + tid; i < mask_stride; i += NT) mask[i] = 0;
   if (NT > 32) __syncthreads(); else __syncwarp();

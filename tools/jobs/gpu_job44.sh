@@ -1,0 +1,7 @@
+#!/bin/bash
+cd "$(dirname "$0")/../.."
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests/ -x -q -m gpu 2>&1 | tail -4 | tee gpurun_out/t44.log
+python bench.py --no-other > gpurun_out/b44.json 2> gpurun_out/b44.err
+python tools/bench_summary.py < gpurun_out/b44.json 2>/dev/null | head -3 | tee -a gpurun_out/t44.log
+bash tools/jobs/gpu_job43.sh
