@@ -1032,6 +1032,11 @@ k_sel_tie_quad(const PairMeta* __restrict__ meta, const double* __restrict__ Ya,
     for (int ib = 0; ib < Nw; ib += 2 * G) {
       double v0 = 0.0, v1 = 0.0;
       const int i0 = ib + sub, i1 = ib + G + sub;
+      {  // the lines the walk reaches three trips from now are asked into L1 (no registers held)
+        const int ipf = min(i0 + 6 * G, max(N, 1) - 1);
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(ya + 3 * ipf));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(yb + 3 * ipf));
+      }
       if (i0 < N) {
         const double nr = residual_norm(f.R, f.t, ya + 3 * i0, yb + 3 * i0);
         v0 = nr < m.thr ? nr : 0.0;  // sum(normResidu(inliers)) in index order (:135); + 0.0 is exact
