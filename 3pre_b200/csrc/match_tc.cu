@@ -922,11 +922,13 @@ k_tc_seq_fused(const T* __restrict__ L, int K, const int32_t* __restrict__ kc, i
     // position of a quad in the stream, advanced by 2 FZ_NCW quads at a time without divisions
     struct Pos {
       int i, hq;  // frame (relative to u0), quad within the frame (tile j = hq >> 4, quad of the tile = hq & 15)
+      int b;      // i % FZ_NBUF: the frame's buffer (kept incrementally: a division by 3 per use otherwise)
       __device__ __forceinline__ void advance(int by) {
         hq += by;
         if (hq >= FZ_FQUADS) {
           hq -= FZ_FQUADS;
           ++i;
+          b = b == FZ_NBUF - 1 ? 0 : b + 1;
         }
       }
     };
@@ -960,7 +962,7 @@ k_tc_seq_fused(const T* __restrict__ L, int K, const int32_t* __restrict__ kc, i
     auto acquire = [&](const Pos& q) {  // first write of this warp into the buffer for frame q.i: the pair that used it as A must be done
       if (q.i > cur_i) {
         cur_i = q.i;
-        mbar_wait(smem_u32(&bars->f_empty[q.i % FZ_NBUF]), (uint32_t)(((q.i / FZ_NBUF) & 1) ^ 1));
+        mbar_wait(smem_u32(&bars->f_empty[q.b]), (uint32_t)(((q.i / FZ_NBUF) & 1) ^ 1));
         tc_fence_after();
       }
     };
@@ -979,7 +981,7 @@ k_tc_seq_fused(const T* __restrict__ L, int K, const int32_t* __restrict__ kc, i
       }
       const int j = q.hq >> 4, qd = q.hq & 15;
       const int tr0 = (j & 1) * 64 + qd * FZ_QROWS;  // first row of the quad within the 128-row tile of part j >> 1
-      unsigned char* dst0 = smem + (q.i % FZ_NBUF) * FZ_BUF_BYTES + (j >> 1) * BLK_BYTES + tr0 * 128 + lane_img;
+      unsigned char* dst0 = smem + q.b * FZ_BUF_BYTES + (j >> 1) * BLK_BYTES + tr0 * 128 + lane_img;
 #pragma unroll
       for (int e = 0; e < FZ_QROWS; ++e) {
         const float f0 = (float)v[e][0], f1 = (float)v[e][1], f2 = (float)v[e][2], f3 = (float)v[e][3];
@@ -1043,7 +1045,7 @@ k_tc_seq_fused(const T* __restrict__ L, int K, const int32_t* __restrict__ kc, i
       w.x = (unsigned)__half_as_ushort(h[0]) | ((unsigned)__half_as_ushort(h[1]) << 16);
       w.y = (unsigned)__half_as_ushort(h[2]) | ((unsigned)__half_as_ushort(h[3]) << 16);
       w.z = w.w = 0u;
-      unsigned char* e0 = smem + (q.i % FZ_NBUF) * FZ_BUF_BYTES + FZ_IMG_BYTES + j * P2_BEXT;  // SWIZZLE_32B rows (ext_off)
+      unsigned char* e0 = smem + q.b * FZ_BUF_BYTES + FZ_IMG_BYTES + j * P2_BEXT;  // SWIZZLE_32B rows (ext_off)
       *reinterpret_cast<uint4*>(e0 + ext_off(0, rl, 0)) = w;
       *reinterpret_cast<uint4*>(e0 + ext_off(0, rl, 1)) = make_uint4(0u, 0u, 0u, 0u);
       nrm[(size_t)f * FZ_KP + row] = (row < n) ? t : INFINITY;
@@ -1051,7 +1053,7 @@ k_tc_seq_fused(const T* __restrict__ L, int K, const int32_t* __restrict__ kc, i
       bad_out = (row < n && bad) ? 1 : 0;
     };
     auto arrive = [&](const Pos& q) {
-      const uint32_t bar = smem_u32(&bars->f_full[q.i % FZ_NBUF][q.hq >> 4]);
+      const uint32_t bar = smem_u32(&bars->f_full[q.b][q.hq >> 4]);
       if (leader) mbar_arrive(bar);
       else mbar_arrive_cluster(mapa_u32(bar, 0));
     };
@@ -1061,7 +1063,7 @@ k_tc_seq_fused(const T* __restrict__ L, int K, const int32_t* __restrict__ kc, i
     // interleaved.
     double va[FZ_QROWS][4], vb[FZ_QROWS][4];
     Stats sa{0.f, 0, -1}, sb{0.f, 0, -1};
-    Pos qa{0, cw}, qb{0, cw};
+    Pos qa{0, cw, 0}, qb{0, cw, 0};
     qb.advance(FZ_NCW);
     int Q = cw;  // stream index of qa
     if (Q < total) issue(qa, va);
@@ -1086,6 +1088,7 @@ k_tc_seq_fused(const T* __restrict__ L, int K, const int32_t* __restrict__ kc, i
         Pos cq;
         cq.i = lane < 16 ? ca.i : cb.i;
         cq.hq = lane < 16 ? ca.hq : cb.hq;
+        cq.b = lane < 16 ? ca.b : cb.b;
         float fn;
         int bd;
         finish(cq, t, fn, bd);
