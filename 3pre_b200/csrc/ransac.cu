@@ -1003,7 +1003,7 @@ k_sel_tie(const PairMeta* __restrict__ meta, const double* __restrict__ Ya, cons
 // times the warps of the thread-per-tie form for the same ties: the kernel is latency bound (sqrt / dependent
 // adds), not throughput bound.
 template <int G>
-__global__ void __launch_bounds__(TIE_THREADS, 4)
+__global__ void __launch_bounds__(TIE_THREADS, G >= 16 ? 3 : 4)
 k_sel_tie_quad(const PairMeta* __restrict__ meta, const double* __restrict__ Ya, const double* __restrict__ Yb,
                int Nmax, const int32_t* __restrict__ samples, uint64_t seed, uint32_t pair_id0, long long h0, int H,
                int k, int method, const int2* __restrict__ ties, const int* __restrict__ tie_total, int cap,
